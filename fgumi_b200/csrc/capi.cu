@@ -1,0 +1,505 @@
+// C-ABI implementation (include/fgumi_b200.h): handle lifecycle, tile planner, vote launches,
+// the chunked host-buffer pipeline, strand-combine launches and the device counters.
+// There is no CPU fallback anywhere in this file: without a CUDA device every compute entry point
+// returns FGB_ERR_NO_DEVICE / FGB_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fgumi_b200.h"
+#include "combine_kernels.cuh"
+#include "fgb_config.h"
+#include "host_tables.h"
+#include "vote_kernel.cuh"
+
+using namespace fgb;
+
+static_assert(sizeof(fgb_unit) == 16, "fgb_unit must be 16 bytes");
+static_assert(sizeof(fgb_tile) == 32, "fgb_tile must be 32 bytes");
+static_assert(sizeof(Stage) % 16 == 0, "Stage must keep 16-byte TMA alignment");
+static_assert(offsetof(Stage, quals) % 16 == 0 && offsetof(Stage, reads) % 16 == 0 &&
+                  offsetof(Stage, units) % 16 == 0 && offsetof(Stage, tile) % 16 == 0,
+              "TMA destinations must be 16-byte aligned");
+
+namespace {
+
+constexpr int kSlots = 2;                        // chunk pipeline depth of fgb_submit
+constexpr uint64_t kChunkColumnBytes = 96ull << 20;  // per-column bytes per chunk
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  uint8_t* bases = nullptr;
+  uint8_t* quals = nullptr;
+  uint64_t* reads = nullptr;
+  fgb_unit* units = nullptr;
+  fgb_tile* tiles = nullptr;
+  uint8_t* out_base = nullptr;
+  uint8_t* out_qual = nullptr;
+  uint16_t* out_depth = nullptr;
+  uint16_t* out_errors = nullptr;
+  uint64_t cap_bytes = 0, cap_reads = 0, cap_units = 0, cap_tiles = 0, cap_out = 0;
+};
+
+}  // namespace
+
+struct fgb_handle {
+  int device = -1;
+  int sm_count = 0;
+  fgb_params params{};
+  HostTables host_tables{};
+  DeviceTables* d_tables = nullptr;
+  unsigned long long* d_counters = nullptr;
+  uint64_t launches = 0;
+  std::string last_error;
+  Slot slots[kSlots];
+  bool submit_pending = false;
+};
+
+namespace {
+
+fgb_status cuda_fail(fgb_handle* h, cudaError_t e, const char* what) {
+  if (h) {
+    h->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  }
+  return FGB_ERR_CUDA;
+}
+
+#define FGB_CUDA(h, call)                                   \
+  do {                                                      \
+    cudaError_t e__ = (call);                               \
+    if (e__ != cudaSuccess) return cuda_fail((h), e__, #call); \
+  } while (0)
+
+template <class T>
+fgb_status ensure(fgb_handle* h, T** p, uint64_t* cap, uint64_t need) {
+  if (need <= *cap && *p) return FGB_OK;
+  if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+  uint64_t n = need + need / 8 + 64;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+  if (e != cudaSuccess) { cuda_fail(h, e, "cudaMalloc"); return FGB_ERR_NOMEM; }
+  *cap = n;
+  return FGB_OK;
+}
+
+fgb_status launch_vote(fgb_handle* h, const fgb_batch& b, const fgb_columns& out,
+                       cudaStream_t stream) {
+  if (b.n_tiles == 0) return FGB_OK;
+  VoteArgs a;
+  a.bases = b.bases; a.quals = b.quals; a.reads = b.reads; a.units = b.units; a.tiles = b.tiles;
+  a.n_tiles = b.n_tiles;
+  a.out_base = out.base; a.out_qual = out.qual; a.out_depth = out.depth; a.out_errors = out.errors;
+  a.tables = h->d_tables;
+  a.counters = h->d_counters;
+  a.min_reads = h->params.min_reads;
+  a.min_cons_q = h->params.min_consensus_base_quality;
+  a.fast_qual = h->host_tables.fast_qual;
+  uint64_t max_grid = static_cast<uint64_t>(h->sm_count) * 2u;
+  unsigned grid = static_cast<unsigned>(std::min<uint64_t>(b.n_tiles, max_grid));
+  vote_kernel<<<grid, kThreads, sizeof(VoteSmem), stream>>>(a);
+  h->launches++;
+  FGB_CUDA(h, cudaGetLastError());
+  return FGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t fgb_abi_version(void) { return FGB_ABI_VERSION; }
+
+const char* fgb_strerror(fgb_status s) {
+  switch (s) {
+    case FGB_OK: return "ok";
+    case FGB_ERR_INVALID_ARG: return "invalid argument";
+    case FGB_ERR_CUDA: return "CUDA runtime error";
+    case FGB_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (this engine has no CPU fallback)";
+    case FGB_ERR_LAYOUT: return "batch violates the SoA layout rules";
+    case FGB_ERR_UNIT_TOO_LARGE: return "unit exceeds the supported size";
+    case FGB_ERR_NOMEM: return "out of memory";
+    case FGB_ERR_BUSY: return "a previous fgb_submit has not been waited on";
+    default: return "unknown status";
+  }
+}
+
+size_t fgb_last_error(const fgb_handle* h, char* buf, size_t buf_len) {
+  if (!h) return 0;
+  if (buf && buf_len) {
+    size_t n = std::min(buf_len - 1, h->last_error.size());
+    std::memcpy(buf, h->last_error.data(), n);
+    buf[n] = 0;
+  }
+  return h->last_error.size();
+}
+
+fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
+  if (!params || !out) return FGB_ERR_INVALID_ARG;
+  if (params->error_rate_pre_umi > FGB_MAX_PHRED || params->error_rate_post_umi > FGB_MAX_PHRED ||
+      params->min_reads == 0)
+    return FGB_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) {
+    cudaGetLastError();
+    return FGB_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FGB_ERR_NO_DEVICE;
+  if (prop.major != 10) return FGB_ERR_NO_DEVICE;   // kernels are sm_100a only
+  fgb_handle* h = new (std::nothrow) fgb_handle();
+  if (!h) return FGB_ERR_NOMEM;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->params = *params;
+  build_host_tables(params->error_rate_pre_umi, params->error_rate_post_umi, &h->host_tables);
+
+  auto fail = [&](cudaError_t e, const char* what) {
+    fprintf(stderr, "fgumi_b200: fgb_create: %s: %s\n", what, cudaGetErrorString(e));
+    fgb_destroy(h);
+    return FGB_ERR_CUDA;
+  };
+  cudaError_t e;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+  if ((e = cudaMalloc(&h->d_tables, sizeof(DeviceTables))) != cudaSuccess) return fail(e, "cudaMalloc tables");
+  if ((e = cudaMalloc(&h->d_counters, sizeof(unsigned long long) * FGB_NCOUNTERS)) != cudaSuccess)
+    return fail(e, "cudaMalloc counters");
+  DeviceTables dt;
+  std::memset(&dt, 0, sizeof(dt));
+  std::memcpy(dt.correct, h->host_tables.correct, sizeof(dt.correct));
+  std::memcpy(dt.err_alt, h->host_tables.err_alt, sizeof(dt.err_alt));
+  dt.ln_pre = h->host_tables.ln_pre;
+  std::memcpy(dt.single_q, h->host_tables.single_q, sizeof(dt.single_q));
+  std::memcpy(dt.qt, h->host_tables.qt, sizeof(dt.qt));
+  if ((e = cudaMemcpy(h->d_tables, &dt, sizeof(dt), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return fail(e, "cudaMemcpy tables");
+  if ((e = cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * FGB_NCOUNTERS)) != cudaSuccess)
+    return fail(e, "cudaMemset counters");
+  if ((e = cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(VoteSmem)))) != cudaSuccess)
+    return fail(e, "cudaFuncSetAttribute(vote_kernel)");
+  for (int s = 0; s < kSlots; ++s)
+    if ((e = cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking)) != cudaSuccess)
+      return fail(e, "cudaStreamCreate");
+  *out = h;
+  return FGB_OK;
+}
+
+void fgb_destroy(fgb_handle* h) {
+  if (!h) return;
+  if (h->device >= 0) cudaSetDevice(h->device);
+  for (int s = 0; s < kSlots; ++s) {
+    Slot& sl = h->slots[s];
+    if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.reads); cudaFree(sl.units);
+    cudaFree(sl.tiles); cudaFree(sl.out_base); cudaFree(sl.out_qual); cudaFree(sl.out_depth);
+    cudaFree(sl.out_errors);
+  }
+  cudaFree(h->d_tables);
+  cudaFree(h->d_counters);
+  delete h;
+}
+
+fgb_status fgb_get_tables(const fgb_handle* h, double* correct, double* err_alt, double* ln_pre,
+                          uint8_t* single_input_q) {
+  if (!h) return FGB_ERR_INVALID_ARG;
+  if (correct) std::memcpy(correct, h->host_tables.correct, sizeof(double) * FGB_NTABLE);
+  if (err_alt) std::memcpy(err_alt, h->host_tables.err_alt, sizeof(double) * FGB_NTABLE);
+  if (ln_pre) *ln_pre = h->host_tables.ln_pre;
+  if (single_input_q) std::memcpy(single_input_q, h->host_tables.single_q, FGB_NTABLE);
+  return FGB_OK;
+}
+
+fgb_status fgb_host_tables(uint8_t pre, uint8_t post, double* correct, double* err_alt,
+                           double* ln_pre, uint8_t* single_input_q, uint8_t* qt,
+                           uint32_t* fast_qual) {
+  if (pre > FGB_MAX_PHRED || post > FGB_MAX_PHRED) return FGB_ERR_INVALID_ARG;
+  HostTables t;
+  build_host_tables(pre, post, &t);
+  if (correct) std::memcpy(correct, t.correct, sizeof(double) * FGB_NTABLE);
+  if (err_alt) std::memcpy(err_alt, t.err_alt, sizeof(double) * FGB_NTABLE);
+  if (ln_pre) *ln_pre = t.ln_pre;
+  if (single_input_q) std::memcpy(single_input_q, t.single_q, FGB_NTABLE);
+  if (qt) std::memcpy(qt, t.qt, sizeof(t.qt));
+  if (fast_qual) *fast_qual = t.fast_qual;
+  return FGB_OK;
+}
+
+// ---- planner ------------------------------------------------------------------------------------
+uint32_t fgb_tile_capacity_bytes(void) { return kTileCapBytes; }
+uint32_t fgb_tile_max_units(void) { return kTileMaxUnits; }
+uint32_t fgb_tile_max_reads(void) { return kTileMaxReads; }
+
+fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_read_desc* reads,
+                          uint64_t n_reads, fgb_tile* out, uint64_t cap, uint64_t* n_tiles) {
+  if (!n_tiles || (n_units && (!units || (!reads && n_reads)))) return FGB_ERR_INVALID_ARG;
+  if (n_units >= 0xFFFFFFFFull || n_reads >= 0xFFFFFFFFull) return FGB_ERR_INVALID_ARG;
+  uint64_t nt = 0;
+  fgb_tile cur{};
+  bool open = false;
+  uint64_t cur_end = 0;   // exclusive end (unaligned) of the open tile's byte range
+  uint64_t prev_read_end = 0;
+
+  auto emit = [&]() {
+    cur.byte_len = static_cast<uint32_t>(((cur_end + 15u) & ~15ull) - cur.byte_begin);
+    if (cur.flags & kTileFlagDirect) { cur.byte_len = 0; }
+    if (out && nt < cap) out[nt] = cur;
+    ++nt;
+    open = false;
+  };
+
+  if (n_units && units[0].read_begin != 0) return FGB_ERR_LAYOUT;
+  for (uint64_t u = 0; u < n_units; ++u) {
+    const fgb_unit& un = units[u];
+    const fgb_unit& nx = units[u + 1];
+    if (nx.read_begin < un.read_begin || nx.read_begin > n_reads) return FGB_ERR_LAYOUT;
+    uint32_t nr = nx.read_begin - un.read_begin;
+    if (un.out_off % FGB_OUT_ALIGN) return FGB_ERR_LAYOUT;
+    if (nx.out_off != un.out_off + ((static_cast<uint64_t>(un.cons_len) + 3u) & ~3ull))
+      return FGB_ERR_LAYOUT;   // output rows are dense, each padded to FGB_OUT_ALIGN
+    if (un.cons_len > FGB_MAX_READ_LEN) return FGB_ERR_UNIT_TOO_LARGE;
+    if (nr == 0 && un.cons_len != 0) return FGB_ERR_LAYOUT;
+    if (nr > 0xFFFFu) return FGB_ERR_UNIT_TOO_LARGE;   // u16 observation counters, base_builder.rs:236
+    uint64_t ub = 0, ue = 0;   // byte range of this unit
+    uint32_t maxlen = 0;
+    for (uint32_t r = un.read_begin; r < nx.read_begin; ++r) {
+      uint64_t off = FGB_READ_OFF(reads[r]);
+      uint32_t len = FGB_READ_LEN(reads[r]);
+      if (off % FGB_READ_ALIGN) return FGB_ERR_LAYOUT;
+      if (off < prev_read_end) return FGB_ERR_LAYOUT;   // rows ascend and do not overlap
+      prev_read_end = off + len;
+      if (r == un.read_begin) ub = off;
+      ue = off + len;
+      maxlen = std::max(maxlen, len);
+    }
+    if (un.cons_len > maxlen) return FGB_ERR_LAYOUT;
+    if (nr == 0) { ub = ue = open ? cur_end : prev_read_end; }
+
+    // Can the unit join the open tile?
+    if (open) {
+      uint64_t span = ((ue + 15u) & ~15ull) - cur.byte_begin;
+      uint32_t skew = cur.read_begin & 1u;
+      bool fits = !(cur.flags & kTileFlagDirect) && span <= kTileCapBytes &&
+                  cur.n_units + 1 <= kTileMaxUnits &&
+                  cur.n_reads + nr + skew <= kTileMaxReads;
+      if (!fits) emit();
+    }
+    if (!open) {
+      std::memset(&cur, 0, sizeof(cur));
+      cur.byte_begin = ub & ~15ull;
+      cur.unit_begin = static_cast<uint32_t>(u);
+      cur.read_begin = un.read_begin;
+      cur_end = ub;
+      open = true;
+      uint64_t span = ((ue + 15u) & ~15ull) - cur.byte_begin;
+      if (span > kTileCapBytes || nr + (cur.read_begin & 1u) > kTileMaxReads)
+        cur.flags |= kTileFlagDirect;   // oversize unit: kernel votes it straight from HBM
+    }
+    cur.n_units += 1;
+    cur.n_reads += nr;
+    cur_end = std::max(cur_end, ue);
+    if (cur.flags & kTileFlagDirect) emit();
+  }
+  if (open) emit();
+  *n_tiles = nt;
+  return FGB_OK;
+}
+
+// ---- vote ---------------------------------------------------------------------------------------
+fgb_status fgb_vote_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* out,
+                           void* stream) {
+  if (!h || !in || !out) return FGB_ERR_INVALID_ARG;
+  if (in->n_tiles && (!in->tiles || !in->units || !out->base || !out->qual || !out->depth ||
+                      !out->errors))
+    return FGB_ERR_INVALID_ARG;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  return launch_vote(h, *in, *out, static_cast<cudaStream_t>(stream));
+}
+
+fgb_status fgb_host_alloc(void** p, size_t bytes) {
+  if (!p) return FGB_ERR_INVALID_ARG;
+  cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; return FGB_ERR_NOMEM; }
+  return FGB_OK;
+}
+void fgb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out) {
+  if (!h || !in || !out) return FGB_ERR_INVALID_ARG;
+  if (h->submit_pending) return FGB_ERR_BUSY;
+  if (in->n_tiles == 0) return FGB_OK;
+  if (!in->tiles || !in->units || !in->reads || !in->bases || !in->quals || !out->base ||
+      !out->qual || !out->depth || !out->errors)
+    return FGB_ERR_INVALID_ARG;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  h->submit_pending = true;
+
+  const fgb_tile* T = in->tiles;
+  uint64_t t0 = 0;
+  int chunk = 0;
+  while (t0 < in->n_tiles) {
+    // Grow the chunk tile by tile up to kChunkColumnBytes of column bytes.
+    uint64_t t1 = t0;
+    const uint64_t byte0 = T[t0].flags & kTileFlagDirect
+                               ? (FGB_READ_OFF(in->reads[T[t0].read_begin]) & ~15ull)
+                               : T[t0].byte_begin;
+    uint64_t byte1 = byte0;
+    while (t1 < in->n_tiles) {
+      const fgb_tile& tl = T[t1];
+      uint64_t end;
+      if (tl.flags & kTileFlagDirect) {
+        fgb_read_desc last = in->reads[tl.read_begin + tl.n_reads - 1];
+        end = (FGB_READ_OFF(last) + FGB_READ_LEN(last) + 15u) & ~15ull;
+      } else {
+        end = tl.byte_begin + tl.byte_len;
+      }
+      end = std::max(end, byte1);
+      if (t1 > t0 && end - byte0 > kChunkColumnBytes) break;
+      byte1 = end;
+      ++t1;
+    }
+    const fgb_tile& first = T[t0];
+    const fgb_tile& last = T[t1 - 1];
+    const uint64_t u0 = first.unit_begin, u1 = static_cast<uint64_t>(last.unit_begin) + last.n_units;
+    const uint64_t r0 = first.read_begin & ~1ull;
+    const uint64_t r1 = static_cast<uint64_t>(last.read_begin) + last.n_reads;
+    const uint64_t o0 = in->units[u0].out_off, o1 = in->units[u1].out_off;
+    const uint64_t nbytes = byte1 - byte0;
+    const uint64_t valid_bytes = std::min(byte1, in->n_bytes) - std::min(byte0, in->n_bytes);
+
+    Slot& sl = h->slots[chunk % kSlots];
+    // In-stream order makes slot reuse safe: chunk c+kSlots queues behind chunk c's D2H.
+    fgb_status st;
+    uint64_t cap2 = sl.cap_bytes;
+    if ((st = ensure(h, &sl.bases, &sl.cap_bytes, nbytes + 16)) != FGB_OK) return st;
+    if ((st = ensure(h, &sl.quals, &cap2, nbytes + 16)) != FGB_OK) return st;
+    if ((st = ensure(h, &sl.reads, &sl.cap_reads, r1 - r0 + 2)) != FGB_OK) return st;
+    if ((st = ensure(h, &sl.units, &sl.cap_units, u1 - u0 + 1)) != FGB_OK) return st;
+    if ((st = ensure(h, &sl.tiles, &sl.cap_tiles, t1 - t0)) != FGB_OK) return st;
+    uint64_t c1 = sl.cap_out, c2 = sl.cap_out, c3 = sl.cap_out;
+    if ((st = ensure(h, &sl.out_base, &sl.cap_out, o1 - o0 + 4)) != FGB_OK) return st;
+    if ((st = ensure(h, &sl.out_qual, &c1, o1 - o0 + 4)) != FGB_OK) return st;
+    if ((st = ensure(h, &sl.out_depth, &c2, o1 - o0 + 4)) != FGB_OK) return st;
+    if ((st = ensure(h, &sl.out_errors, &c3, o1 - o0 + 4)) != FGB_OK) return st;
+
+    cudaStream_t s = sl.stream;
+    FGB_CUDA(h, cudaMemcpyAsync(sl.bases, in->bases + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
+    FGB_CUDA(h, cudaMemcpyAsync(sl.quals, in->quals + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
+    FGB_CUDA(h, cudaMemcpyAsync(sl.reads, in->reads + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, s));
+    FGB_CUDA(h, cudaMemcpyAsync(sl.units, in->units + u0, (u1 - u0 + 1) * sizeof(fgb_unit),
+                                cudaMemcpyHostToDevice, s));
+    FGB_CUDA(h, cudaMemcpyAsync(sl.tiles, T + t0, (t1 - t0) * sizeof(fgb_tile),
+                                cudaMemcpyHostToDevice, s));
+    // Descriptors keep their absolute offsets; the kernel gets base pointers biased by the chunk
+    // origin (byte0 / r0 / u0 / o0 keep every TMA source 16-byte aligned).
+    fgb_batch db;
+    std::memset(&db, 0, sizeof(db));
+    db.n_tiles = t1 - t0;
+    db.bases = sl.bases - byte0;
+    db.quals = sl.quals - byte0;
+    db.reads = sl.reads - r0;
+    db.units = sl.units - u0;
+    db.tiles = sl.tiles;
+    fgb_columns dc;
+    dc.base = sl.out_base - o0;
+    dc.qual = sl.out_qual - o0;
+    dc.depth = sl.out_depth - o0;
+    dc.errors = sl.out_errors - o0;
+    if ((st = launch_vote(h, db, dc, s)) != FGB_OK) return st;
+    const uint64_t no = o1 - o0;
+    FGB_CUDA(h, cudaMemcpyAsync(out->base + o0, sl.out_base, no, cudaMemcpyDeviceToHost, s));
+    FGB_CUDA(h, cudaMemcpyAsync(out->qual + o0, sl.out_qual, no, cudaMemcpyDeviceToHost, s));
+    FGB_CUDA(h, cudaMemcpyAsync(out->depth + o0, sl.out_depth, no * 2, cudaMemcpyDeviceToHost, s));
+    FGB_CUDA(h, cudaMemcpyAsync(out->errors + o0, sl.out_errors, no * 2, cudaMemcpyDeviceToHost, s));
+    t0 = t1;
+    ++chunk;
+  }
+  return FGB_OK;
+}
+
+fgb_status fgb_wait(fgb_handle* h) {
+  if (!h) return FGB_ERR_INVALID_ARG;
+  h->submit_pending = false;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  for (int s = 0; s < kSlots; ++s) FGB_CUDA(h, cudaStreamSynchronize(h->slots[s].stream));
+  return FGB_OK;
+}
+
+// ---- strand combine -----------------------------------------------------------------------------
+fgb_status fgb_duplex_combine_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss,
+                                     const fgb_duplex_job* jobs, uint64_t n_jobs,
+                                     const fgb_duplex_out* out, void* stream) {
+  if (!h || !in || !ss || !out || (n_jobs && !jobs)) return FGB_ERR_INVALID_ARG;
+  if (n_jobs == 0) return FGB_OK;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  DuplexArgs a;
+  a.bases = in->bases; a.reads = in->reads; a.units = in->units;
+  a.ss_base = ss->base; a.ss_qual = ss->qual; a.ss_depth = ss->depth; a.ss_errors = ss->errors;
+  a.jobs = jobs; a.n_jobs = n_jobs;
+  a.out_base = out->base; a.out_qual = out->qual; a.out_errors = out->errors;
+  a.out_status = out->status;
+  a.counters = h->d_counters;
+  unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n_jobs + kCombineJobsPerCta - 1) / kCombineJobsPerCta,
+                                                           static_cast<uint64_t>(h->sm_count) * 8u));
+  duplex_combine_kernel<<<grid, kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  h->launches++;
+  FGB_CUDA(h, cudaGetLastError());
+  return FGB_OK;
+}
+
+fgb_status fgb_codec_combine_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss,
+                                    const fgb_codec_job* jobs, uint64_t n_jobs,
+                                    const fgb_codec_params* cp, const fgb_codec_out* out,
+                                    void* stream) {
+  if (!h || !in || !ss || !out || !cp || (n_jobs && !jobs)) return FGB_ERR_INVALID_ARG;
+  if (n_jobs == 0) return FGB_OK;
+  if (!out->status || !out->cols.base || !out->cols.qual || !out->cols.depth || !out->cols.errors)
+    return FGB_ERR_INVALID_ARG;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  CodecArgs a;
+  a.units = in->units;
+  a.ss_base = ss->base; a.ss_qual = ss->qual; a.ss_depth = ss->depth; a.ss_errors = ss->errors;
+  a.jobs = jobs; a.n_jobs = n_jobs;
+  a.cp = *cp;
+  a.out_base = out->cols.base; a.out_qual = out->cols.qual; a.out_depth = out->cols.depth;
+  a.out_errors = out->cols.errors;
+  a.status = out->status; a.disagreements = out->disagreements; a.duplex_bases = out->duplex_bases;
+  a.counters = h->d_counters;
+  unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n_jobs + kCodecJobsPerCta - 1) / kCodecJobsPerCta,
+                                                           static_cast<uint64_t>(h->sm_count) * 8u));
+  codec_combine_kernel<<<grid, kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  h->launches++;
+  FGB_CUDA(h, cudaGetLastError());
+  return FGB_OK;
+}
+
+// ---- statistics ---------------------------------------------------------------------------------
+fgb_status fgb_stats(fgb_handle* h, uint64_t counters[FGB_NCOUNTERS]) {
+  if (!h || !counters) return FGB_ERR_INVALID_ARG;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  FGB_CUDA(h, cudaDeviceSynchronize());
+  FGB_CUDA(h, cudaMemcpy(counters, h->d_counters, sizeof(uint64_t) * FGB_NCOUNTERS,
+                         cudaMemcpyDeviceToHost));
+  return FGB_OK;
+}
+
+fgb_status fgb_stats_device_ptr(fgb_handle* h, uint64_t** dev_counters) {
+  if (!h || !dev_counters) return FGB_ERR_INVALID_ARG;
+  *dev_counters = reinterpret_cast<uint64_t*>(h->d_counters);
+  return FGB_OK;
+}
+
+fgb_status fgb_stats_reset(fgb_handle* h) {
+  if (!h) return FGB_ERR_INVALID_ARG;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  FGB_CUDA(h, cudaDeviceSynchronize());
+  FGB_CUDA(h, cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * FGB_NCOUNTERS));
+  return FGB_OK;
+}
+
+uint64_t fgb_launch_count(const fgb_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,510 @@
+// K1 — simplex / single-strand consensus vote for sm_100a.
+//
+// Replaces (reference = /root/reference/crates/fgumi-consensus/src/):
+//   vanilla_caller.rs:1260-1358  create_consensus_from_source_reads (position loop, thresholds,
+//                                single-read LUT path)
+//   base_builder.rs:295-327      ConsensusBaseBuilder::add   (4-lane f64 Kahan likelihoods)
+//   base_builder.rs:338-379      try_unanimous_fast_path
+//   base_builder.rs:391-458      call (log-sum-exp, argmax / tie -> N, posterior -> phred)
+//
+// Shape of the kernel:
+//   * persistent CTAs (2 per SM), each walks tiles  t = blockIdx.x, +gridDim.x, ...
+//   * one elected thread stages a tile (base bytes, qual bytes, read descriptors, unit
+//     descriptors) into shared memory with four TMA bulk copies (cp.async.bulk ... mbarrier
+//     complete_tx), double buffered so the next tile streams from HBM while this one is voted;
+//   * FAST PASS: one thread per 4 consecutive positions (uchar4 words).  Over the depth axis it
+//     keeps a SWAR "all reads equal the first read" mask and a SWAR "every quality >= qT(n)" mask;
+//     a position that is unanimous over A/C/G/T, covered by every read and passes the quality
+//     mask is PROVEN to take the reference's unanimous fast path (sum of per-read likelihood gaps
+//     >= n*Dmono[qT] > 23), whose result is the constant (base, phred(ln_pre)) — no f64 needed;
+//   * everything else (disagreements, Ns, ragged ends, shallow / low-quality pileups) is queued in
+//     shared memory and resolved in the EXACT PASS by the literal algorithm: sequential, in-order,
+//     4-lane f64 Kahan accumulation from the host-built tables, then the f64 call() tail.  Lanes
+//     are packed (one queued position per thread) so the f64 work never runs divergent;
+//   * results leave as coalesced uchar4 / ushort4 stores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fgumi_b200.h"
+#include "device_math.cuh"
+#include "fgb_config.h"
+
+namespace fgb {
+
+struct DeviceTables {
+  double correct[FGB_NTABLE];   // adjusted_correct_table, base_builder.rs:265
+  double err_alt[FGB_NTABLE];   // adjusted_error_per_alt, base_builder.rs:268
+  double ln_pre;                // ln_error_pre_umi, base_builder.rs:277
+  uint8_t single_q[96];         // single_input_consensus_quals, vanilla_caller.rs:463-482
+  uint8_t qt[kQtEntries];       // fast-path quality threshold by depth; 255 = never
+};
+
+struct VoteArgs {
+  const uint8_t* bases;
+  const uint8_t* quals;
+  const uint64_t* reads;
+  const fgb_unit* units;
+  const fgb_tile* tiles;
+  uint64_t n_tiles;
+  uint8_t* out_base;
+  uint8_t* out_qual;
+  uint16_t* out_depth;
+  uint16_t* out_errors;
+  const DeviceTables* tables;
+  unsigned long long* counters;
+  uint32_t min_reads;
+  uint32_t min_cons_q;
+  uint32_t fast_qual;   // ln_prob_to_phred(ln_pre), host-evaluated (base_builder.rs:370)
+};
+
+struct __align__(16) Stage {
+  uint8_t bases[kTileCapBytes];
+  uint8_t quals[kTileCapBytes];
+  uint64_t reads[kTileMaxReads + 2];
+  fgb_unit units[kTileMaxUnits + 1];
+  fgb_tile tile;
+};
+
+struct __align__(128) VoteSmem {
+  Stage st[kStages];
+  double correct[FGB_NTABLE];
+  double err_alt[FGB_NTABLE];
+  double ln_pre;
+  uint64_t full[kStages];
+  uint32_t queue[kSlowQueueCap];
+  uint32_t q_count[2];
+  uint8_t single_q[96];
+  uint8_t qt[kQtEntries];
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- memory-space policy: tiles live in shared memory, oversize units are read from HBM -------
+struct ShMem {
+  using addr_t = uint32_t;
+  using off_t = uint32_t;
+  static __device__ __forceinline__ addr_t make(const void* p) { return smem_u32(p); }
+  static __device__ __forceinline__ uint32_t ld8(addr_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+  }
+  static __device__ __forceinline__ uint32_t ld32(addr_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+  }
+  static __device__ __forceinline__ uint64_t ld64(addr_t a) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+  }
+};
+struct GlMem {
+  using addr_t = const uint8_t*;
+  using off_t = uint64_t;
+  static __device__ __forceinline__ addr_t make(const void* p) {
+    return static_cast<const uint8_t*>(p);
+  }
+  static __device__ __forceinline__ uint32_t ld8(addr_t a) { return __ldg(a); }
+  static __device__ __forceinline__ uint32_t ld32(addr_t a) {
+    return __ldg(reinterpret_cast<const uint32_t*>(a));
+  }
+  static __device__ __forceinline__ uint64_t ld64(addr_t a) {
+    return __ldg(reinterpret_cast<const unsigned long long*>(a));
+  }
+};
+
+template <class M>
+struct TileView {
+  typename M::addr_t bases;   // address of byte `byte_base` of the base column
+  typename M::addr_t quals;
+  typename M::addr_t reads;   // address of the descriptor of read `read_base`
+  uint64_t byte_base;
+  uint32_t read_base;
+};
+
+__device__ __forceinline__ bool is_acgt_upper(uint32_t b) {
+  // 'A'=65 'C'=67 'G'=71 'T'=84 -> bits 1,3,7,20 of a mask indexed by b-64
+  uint32_t t = b - 64u;
+  return t < 32u && ((0x0010008Au >> t) & 1u);
+}
+// BASE_TO_INDEX, base_builder.rs:204-215 (case-insensitive A,C,G,T -> 0..3, else 4)
+__device__ __forceinline__ uint32_t base_to_index(uint32_t b) {
+  uint32_t u = b & 0xDFu;
+  return u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : u == 'T' ? 3u : 4u;
+}
+
+struct Called {
+  uint32_t base, qual, depth, errors;
+};
+
+// The literal per-position algorithm (vanilla_caller.rs:1319-1355 + base_builder.rs:295-458).
+template <class M>
+__device__ __noinline__ Called exact_position(const TileView<M>& tv, const VoteSmem& S,
+                                              uint32_t read_begin, uint32_t n_reads,
+                                              uint32_t pos, uint32_t min_reads,
+                                              uint32_t min_cons_q, uint32_t fast_qual) {
+  double ll[4] = {0.0, 0.0, 0.0, 0.0};   // LN_ONE
+  double kc[4] = {0.0, 0.0, 0.0, 0.0};   // Kahan compensations
+  uint64_t cnt = 0;                      // 4 x u16 observation counters
+  for (uint32_t r = 0; r < n_reads; ++r) {
+    uint64_t d = M::ld64(tv.reads + static_cast<typename M::off_t>(read_begin - tv.read_base + r) * 8u);
+    uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
+    if (pos < len) {                                          // vanilla_caller.rs:1323
+      typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + pos;
+      uint32_t b = M::ld8(tv.bases + row);
+      uint32_t idx = base_to_index(b);
+      if (b != 'N' && idx < 4u) {                             // :1328 and base_builder.rs:300
+        uint32_t q = M::ld8(tv.quals + row);
+        q = q > FGB_MAX_PHRED ? FGB_MAX_PHRED : q;            // base_builder.rs:307
+        double c = S.correct[q];
+        double e = S.err_alt[q];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                         // base_builder.rs:312-324
+          double v = (static_cast<uint32_t>(i) == idx) ? c : e;
+          double y = __dsub_rn(v, kc[i]);
+          double t = __dadd_rn(ll[i], y);
+          kc[i] = __dsub_rn(__dsub_rn(t, ll[i]), y);
+          ll[i] = t;
+        }
+        cnt += 1ull << (16u * idx);
+      }
+    }
+  }
+  uint32_t n0 = cnt & 0xFFFFu, n1 = (cnt >> 16) & 0xFFFFu, n2 = (cnt >> 32) & 0xFFFFu,
+           n3 = (cnt >> 48) & 0xFFFFu;
+  uint32_t depth = (n0 + n1 + n2 + n3) & 0xFFFFu;             // contributions(): u16 sum
+  uint32_t cbase = 'N', cqual = 2;                            // base_builder.rs:392-394
+  uint32_t nobs_call = 0;
+  if (depth != 0) {
+    uint32_t kinds = (n0 != 0) + (n1 != 0) + (n2 != 0) + (n3 != 0);
+    bool done = false;
+    if (kinds == 1) {                                         // base_builder.rs:338-379
+      uint32_t w = n0 ? 0u : n1 ? 1u : n2 ? 2u : 3u;
+      double winner = w == 0 ? ll[0] : w == 1 ? ll[1] : w == 2 ? ll[2] : ll[3];
+      double loser = w == 0 ? ll[1] : w == 1 ? ll[2] : w == 2 ? ll[3] : ll[0];
+      if (__dsub_rn(winner, loser) > 23.0) {
+        cbase = (0x54474341u >> (8u * w)) & 0xFFu;
+        cqual = fast_qual;
+        nobs_call = depth;
+        done = true;
+      }
+    }
+    if (!done) {                                              // base_builder.rs:401-457
+      double ln_sum = dm::ln_sum_exp_array4(ll);
+      double mx = -CUDART_INF;
+      int mi = -1;
+      bool tie = false;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double v = ll[i];
+        if (v > mx) { mx = v; mi = i; tie = false; }
+        else if (v == mx) { tie = true; }
+        else if (v < mx) { if (fabs(__dsub_rn(v, mx)) <= dm::kEps) tie = true; }
+      }
+      if (!(tie || mi < 0)) {
+        double post = __dsub_rn(mx, ln_sum);
+        double err = dm::ln_one_minus_exp(post);
+        double fin = dm::ln_error_prob_two_trials(S.ln_pre, err);
+        cbase = (0x54474341u >> (8 * mi)) & 0xFFu;
+        cqual = dm::ln_prob_to_phred(fin);
+        nobs_call = mi == 0 ? n0 : mi == 1 ? n1 : mi == 2 ? n2 : n3;
+      }
+    }
+  }
+  Called out;
+  out.depth = depth;
+  out.errors = (depth - nobs_call) & 0xFFFFu;                 // vanilla_caller.rs:1341
+  if (depth < min_reads) { out.base = 'N'; out.qual = 0; }    // :1345-1346
+  else if (cqual < min_cons_q) { out.base = 'N'; out.qual = 2; }  // :1347-1348
+  else { out.base = cbase; out.qual = cqual; }
+  return out;
+}
+
+struct LocalStats {
+  uint32_t positions, exact, nocall;
+};
+
+template <class M>
+__device__ __forceinline__ void write_called(const VoteArgs& a, uint64_t o, const Called& c) {
+  a.out_base[o] = static_cast<uint8_t>(c.base);
+  a.out_qual[o] = static_cast<uint8_t>(c.qual);
+  a.out_depth[o] = static_cast<uint16_t>(c.depth);
+  a.out_errors[o] = static_cast<uint16_t>(c.errors);
+}
+
+// Votes one tile.  All threads of the CTA call this.
+template <class M>
+__device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const Stage& st,
+                                          const TileView<M>& tv, uint32_t* q_count,
+                                          LocalStats& ls) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t n_units = st.tile.n_units;
+  const uint64_t out0 = st.units[0].out_off;
+  const uint32_t n_items = static_cast<uint32_t>((st.units[n_units].out_off - out0) >> 2);
+  const uint32_t min_reads = a.min_reads, min_cons_q = a.min_cons_q, fast_qual = a.fast_qual;
+  // constant result of a proven-unanimous position after the thresholds of vanilla_caller.rs:1345-1349
+  const bool fast_masked = fast_qual < min_cons_q;
+  const uint32_t fq = fast_masked ? 2u : fast_qual;
+
+  // ---------------- FAST PASS: one thread per uchar4 of output ----------------
+  for (uint32_t item = tid; item < n_items; item += kThreads) {
+    // unit lookup: largest u with start(u) <= item
+    uint32_t lo = 0, hi = n_units;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      uint32_t start = static_cast<uint32_t>((st.units[mid].out_off - out0) >> 2);
+      if (start <= item) lo = mid; else hi = mid;
+    }
+    const uint32_t u = lo;
+    const fgb_unit un = st.units[u];
+    const uint32_t rb = un.read_begin;
+    const uint32_t n = st.units[u + 1].read_begin - rb;
+    const uint32_t cons_len = un.cons_len;
+    const uint32_t p0 = (item - static_cast<uint32_t>((un.out_off - out0) >> 2)) << 2;
+    const uint64_t o = out0 + (static_cast<uint64_t>(item) << 2);
+
+    uint32_t wbase = 0, wqual = 0;           // 4 output bases / quals
+    uint32_t dep[4] = {0, 0, 0, 0}, err[4] = {0, 0, 0, 0};
+
+    if (n == 1) {
+      // single-read consensus, vanilla_caller.rs:1285-1316
+      uint64_t d = M::ld64(tv.reads + (rb - tv.read_base) * 8u);
+      uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
+      typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + p0;
+      uint32_t wb = 0, wq = 0;
+      if (p0 < len) { wb = M::ld32(tv.bases + row); wq = M::ld32(tv.quals + row); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t pos = p0 + j;
+        if (pos < cons_len) {
+          uint32_t b = (wb >> (8 * j)) & 0xFFu, q = (wq >> (8 * j)) & 0xFFu;
+          uint32_t ob = 'N', oq = 2, od = 0;
+          if (pos < len) {
+            uint32_t adj = q < FGB_NTABLE ? S.single_q[q] : 0u;   // `.get(idx).unwrap_or(0)`
+            if (adj >= min_cons_q) { ob = b; oq = adj; }
+            od = (b != 'N');
+          }
+          wbase |= ob << (8 * j);
+          wqual |= oq << (8 * j);
+          dep[j] = od;
+          ls.positions++;
+          ls.nocall += (ob == 'N');
+        }
+      }
+    } else {
+      const uint32_t qt = S.qt[n < kQtEntries ? n : kQtEntries - 1];
+      const bool fast_ok = (qt <= FGB_MAX_PHRED) && (n >= min_reads) && (n <= 0xFFFFu);
+      uint32_t b0 = 0, diff = 0, okq = 0x80808080u, minlen = 0xFFFFFFFFu;
+      if (fast_ok) {
+        const uint32_t tsplat = qt * 0x01010101u;
+        typename M::addr_t rd = tv.reads + (rb - tv.read_base) * 8u;
+        for (uint32_t r = 0; r < n; ++r) {
+          uint64_t d = M::ld64(rd + r * 8u);
+          uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
+          minlen = len < minlen ? len : minlen;
+          if (len > p0) {
+            typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + p0;
+            uint32_t wb = M::ld32(tv.bases + row);
+            uint32_t wq = M::ld32(tv.quals + row);
+            if (r == 0) b0 = wb;
+            diff |= wb ^ b0;
+            okq &= (wq | 0x80808080u) - tsplat;   // byte high bit survives iff q >= qT (no borrows)
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t pos = p0 + j;
+        if (pos < cons_len) {
+          uint32_t b = (b0 >> (8 * j)) & 0xFFu;
+          bool fast = fast_ok && pos < minlen && ((diff >> (8 * j)) & 0xFFu) == 0 &&
+                      ((okq >> (8 * j + 7)) & 1u) && is_acgt_upper(b);
+          ls.positions++;
+          if (fast) {
+            wbase |= (fast_masked ? static_cast<uint32_t>('N') : b) << (8 * j);
+            wqual |= fq << (8 * j);
+            dep[j] = n;
+            ls.nocall += fast_masked;
+          } else {
+            uint32_t slot = atomicAdd(q_count, 1u);
+            if (slot < kSlowQueueCap) {
+              S.queue[slot] = (u << 16) | pos;
+            } else {  // queue full: resolve in place (correct, just divergent)
+              Called c = exact_position<M>(tv, S, rb, n, pos, min_reads, min_cons_q, fast_qual);
+              wbase |= c.base << (8 * j);
+              wqual |= c.qual << (8 * j);
+              dep[j] = c.depth;
+              err[j] = c.errors;
+              ls.exact++;
+              ls.nocall += (c.base == 'N');
+            }
+          }
+        }
+      }
+    }
+    *reinterpret_cast<uint32_t*>(a.out_base + o) = wbase;
+    *reinterpret_cast<uint32_t*>(a.out_qual + o) = wqual;
+    *reinterpret_cast<uint2*>(a.out_depth + o) = make_uint2(dep[0] | (dep[1] << 16), dep[2] | (dep[3] << 16));
+    *reinterpret_cast<uint2*>(a.out_errors + o) = make_uint2(err[0] | (err[1] << 16), err[2] | (err[3] << 16));
+  }
+  __syncthreads();
+
+  // ---------------- EXACT PASS: one queued position per thread ----------------
+  uint32_t qn = *q_count;
+  qn = qn < kSlowQueueCap ? qn : kSlowQueueCap;
+  for (uint32_t e = tid; e < qn; e += kThreads) {
+    uint32_t ent = S.queue[e];
+    uint32_t u = ent >> 16, pos = ent & 0xFFFFu;
+    const fgb_unit un = st.units[u];
+    uint32_t n = st.units[u + 1].read_begin - un.read_begin;
+    Called c = exact_position<M>(tv, S, un.read_begin, n, pos, min_reads, min_cons_q, fast_qual);
+    write_called<M>(a, un.out_off + pos, c);
+    ls.exact++;
+    ls.nocall += (c.base == 'N');
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  VoteSmem& S = *reinterpret_cast<VoteSmem*>(smem_raw);
+  const uint32_t tid = threadIdx.x;
+
+  for (uint32_t i = tid; i < FGB_NTABLE; i += kThreads) {
+    S.correct[i] = a.tables->correct[i];
+    S.err_alt[i] = a.tables->err_alt[i];
+  }
+  for (uint32_t i = tid; i < 96; i += kThreads) S.single_q[i] = a.tables->single_q[i];
+  for (uint32_t i = tid; i < kQtEntries; i += kThreads) S.qt[i] = a.tables->qt[i];
+  if (tid == 0) {
+    S.ln_pre = a.tables->ln_pre;
+    for (int s = 0; s < kStages; ++s) mbar_init(&S.full[s], 1);
+    S.q_count[0] = 0;
+    S.q_count[1] = 0;
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](uint64_t t, int s) {   // elected thread only
+    Stage& st = S.st[s];
+    const uint4* gt = reinterpret_cast<const uint4*>(a.tiles + t);
+    uint4 t0 = __ldg(gt), t1 = __ldg(gt + 1);
+    *reinterpret_cast<uint4*>(&st.tile) = t0;
+    *(reinterpret_cast<uint4*>(&st.tile) + 1) = t1;
+    uint64_t byte_begin = (static_cast<uint64_t>(t0.y) << 32) | t0.x;
+    uint32_t byte_len = t0.z, unit_begin = t0.w, n_units = t1.x, read_begin = t1.y,
+             n_reads = t1.z, flags = t1.w;
+    uint32_t units_bytes = (n_units + 1u) * 16u;
+    bool direct = (flags & kTileFlagDirect) != 0;
+    uint32_t rskew = read_begin & 1u;
+    uint32_t rbytes = ((n_reads + rskew + 1u) & ~1u) * 8u;
+    uint32_t tx = units_bytes + (direct ? 0u : 2u * byte_len + rbytes);
+    mbar_arrive_expect_tx(&S.full[s], tx);
+    tma_load_1d(st.units, a.units + unit_begin, units_bytes, &S.full[s]);
+    if (!direct) {
+      if (byte_len) {
+        tma_load_1d(st.bases, a.bases + byte_begin, byte_len, &S.full[s]);
+        tma_load_1d(st.quals, a.quals + byte_begin, byte_len, &S.full[s]);
+      }
+      if (rbytes) tma_load_1d(st.reads, a.reads + (read_begin - rskew), rbytes, &S.full[s]);
+    }
+  };
+
+  const uint64_t grid = gridDim.x;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      uint64_t t = blockIdx.x + static_cast<uint64_t>(s) * grid;
+      if (t < a.n_tiles) issue(t, s);
+    }
+  }
+
+  LocalStats ls = {0, 0, 0};
+  uint64_t n_units_done = 0, n_reads_done = 0;
+  uint32_t k = 0;
+  for (uint64_t t = blockIdx.x; t < a.n_tiles; t += grid, ++k) {
+    const int s = k % kStages;
+    mbar_wait(&S.full[s], (k / kStages) & 1u);
+    Stage& st = S.st[s];
+    uint32_t* qc = &S.q_count[k & 1u];
+    if (st.tile.flags & kTileFlagDirect) {
+      TileView<GlMem> tv;
+      tv.bases = a.bases; tv.quals = a.quals;
+      tv.reads = reinterpret_cast<const uint8_t*>(a.reads + st.tile.read_begin);
+      tv.byte_base = 0; tv.read_base = st.tile.read_begin;
+      vote_tile<GlMem>(a, S, st, tv, qc, ls);
+    } else {
+      TileView<ShMem> tv;
+      tv.bases = smem_u32(st.bases); tv.quals = smem_u32(st.quals);
+      tv.reads = smem_u32(st.reads) + (st.tile.read_begin & 1u) * 8u;
+      tv.byte_base = st.tile.byte_begin; tv.read_base = st.tile.read_begin;
+      vote_tile<ShMem>(a, S, st, tv, qc, ls);
+    }
+    if (tid == 0) { n_units_done += st.tile.n_units; n_reads_done += st.tile.n_reads; }
+    __syncthreads();   // stage s and the queue are free again
+    if (tid == 0) {
+      *qc = 0;
+      uint64_t nt = t + static_cast<uint64_t>(kStages) * grid;
+      if (nt < a.n_tiles) issue(nt, s);
+    }
+  }
+
+  // ---- counters: warp-reduce, one atomic per warp ----
+  uint32_t v0 = ls.positions, v1 = ls.exact, v2 = ls.nocall;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    v0 += __shfl_down_sync(0xFFFFFFFFu, v0, off);
+    v1 += __shfl_down_sync(0xFFFFFFFFu, v1, off);
+    v2 += __shfl_down_sync(0xFFFFFFFFu, v2, off);
+  }
+  if ((tid & 31u) == 0) {
+    if (v0) atomicAdd(a.counters + FGB_CTR_POSITIONS, static_cast<unsigned long long>(v0));
+    if (v1) atomicAdd(a.counters + FGB_CTR_EXACT_POSITIONS, static_cast<unsigned long long>(v1));
+    if (v2) atomicAdd(a.counters + FGB_CTR_NOCALL_POSITIONS, static_cast<unsigned long long>(v2));
+  }
+  if (tid == 0) {
+    if (n_units_done) atomicAdd(a.counters + FGB_CTR_UNITS, static_cast<unsigned long long>(n_units_done));
+    if (n_reads_done) atomicAdd(a.counters + FGB_CTR_INPUT_READS, static_cast<unsigned long long>(n_reads_done));
+  }
+}
+
+}  // namespace fgb

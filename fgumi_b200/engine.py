@@ -1,0 +1,332 @@
+"""Host-side mirror of the consensus boundary over the C-ABI (include/fgumi_b200.h).
+
+`Engine` owns one `fgb_handle` (one per GPU, like one caller per worker in the reference,
+simplex.rs:574).  `PackedBatch` is the SoA batch the ABI consumes: base/qual byte columns with
+per-read descriptors, per-unit descriptors and the tile table.  PyTorch is used only to hold
+device memory and streams; every computation happens in libfgumi_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import lib as _l
+
+UNIT_DTYPE = np.dtype([("out_off", "<u8"), ("read_begin", "<u4"), ("cons_len", "<u4")])
+TILE_DTYPE = np.dtype([("byte_begin", "<u8"), ("byte_len", "<u4"), ("unit_begin", "<u4"),
+                       ("n_units", "<u4"), ("read_begin", "<u4"), ("n_reads", "<u4"),
+                       ("flags", "<u4")])
+DUPLEX_JOB_DTYPE = np.dtype([("unit_a", "<u4"), ("unit_b", "<u4"), ("out_off", "<u8")])
+CODEC_JOB_DTYPE = np.dtype([("unit_a", "<u4"), ("unit_b", "<u4"), ("out_off", "<u8"),
+                            ("len", "<u4"), ("pad_a_left", "<u4"), ("pad_b_left", "<u4"),
+                            ("rc_a", "u1"), ("rc_b", "u1"), ("rc_out", "u1"), ("reserved0", "u1")])
+assert UNIT_DTYPE.itemsize == 16 and TILE_DTYPE.itemsize == 32
+assert DUPLEX_JOB_DTYPE.itemsize == 16 and CODEC_JOB_DTYPE.itemsize == 32
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class VanillaUmiConsensusOptions:
+    """vanilla_caller.rs:284-341 (defaults :322-341); CLI defaults are common.rs:225-249."""
+    error_rate_pre_umi: int = 45
+    error_rate_post_umi: int = 40
+    min_input_base_quality: int = 10
+    min_reads: int = 2
+    max_reads: Optional[int] = None
+    produce_per_base_tags: bool = True
+    trim: bool = False
+    min_consensus_base_quality: int = 40
+
+
+@dataclass
+class PackedBatch:
+    """Host (numpy) form of fgb_batch."""
+    bases: np.ndarray       # uint8, length padded to a multiple of 16
+    quals: np.ndarray       # uint8, same length
+    reads: np.ndarray       # uint64 descriptors (off << 16 | len), length padded to even
+    units: np.ndarray       # UNIT_DTYPE, U+1 entries (sentinel last)
+    n_units: int
+    n_reads: int
+    n_bytes: int
+    n_out: int
+    tiles: Optional[np.ndarray] = None   # TILE_DTYPE
+
+    def unit_slices(self) -> List[slice]:
+        u = self.units
+        return [slice(int(u["out_off"][i]), int(u["out_off"][i]) + int(u["cons_len"][i]))
+                for i in range(self.n_units)]
+
+
+def consensus_length(lengths: Sequence[int], min_reads: int) -> int:
+    """min_reads-th longest read, vanilla_caller.rs:1269-1277."""
+    s = sorted(lengths, reverse=True)
+    return s[min_reads - 1]
+
+
+def pack_source_reads(units: Sequence[Sequence[Tuple[bytes, bytes]]], min_reads: int) -> PackedBatch:
+    """Pack already-prepared SourceRead rows (bases, quals) per unit.  Small-scale packer used by
+    tests; rows are padded to FGB_READ_ALIGN, outputs to FGB_OUT_ALIGN."""
+    n_units = len(units)
+    n_reads = sum(len(u) for u in units)
+    reads = np.zeros(_round_up(n_reads, 2) + 2, dtype=np.uint64)
+    uarr = np.zeros(n_units + 1, dtype=UNIT_DTYPE)
+    chunks_b, chunks_q = [], []
+    off = 0
+    r = 0
+    out = 0
+    for i, unit in enumerate(units):
+        uarr[i]["read_begin"] = r
+        uarr[i]["out_off"] = out
+        lens = []
+        for (b, q) in unit:
+            if len(b) != len(q):
+                raise ValueError("bases/quals length mismatch")
+            ln = len(b)
+            lens.append(ln)
+            reads[r] = (off << 16) | ln
+            pad = _round_up(ln, _l.FGB_READ_ALIGN) - ln
+            chunks_b.append(np.frombuffer(bytes(b) + b"\0" * pad, dtype=np.uint8))
+            chunks_q.append(np.frombuffer(bytes(q) + b"\0" * pad, dtype=np.uint8))
+            off += ln + pad
+            r += 1
+        cl = consensus_length(lens, min_reads) if len(lens) >= max(1, min_reads) else 0
+        uarr[i]["cons_len"] = cl
+        out += _round_up(cl, _l.FGB_OUT_ALIGN)
+    uarr[n_units]["read_begin"] = r
+    uarr[n_units]["out_off"] = out
+    n_bytes = off
+    tot = _round_up(max(n_bytes, 1), 16)
+    bases = np.zeros(tot, dtype=np.uint8)
+    quals = np.zeros(tot, dtype=np.uint8)
+    if chunks_b:
+        bases[:n_bytes] = np.concatenate(chunks_b)
+        quals[:n_bytes] = np.concatenate(chunks_q)
+    return PackedBatch(bases, quals, reads, uarr, n_units, n_reads, n_bytes, out)
+
+
+def pack_uniform(bases: np.ndarray, quals: np.ndarray, min_reads: int = 1) -> PackedBatch:
+    """Pack a dense [U, D, L] uint8 pileup (fixed depth D, fixed length L) — vectorised."""
+    U, D, L = bases.shape
+    Lp = _round_up(L, _l.FGB_READ_ALIGN)
+    bp = np.zeros((U, D, Lp), dtype=np.uint8)
+    qp = np.zeros((U, D, Lp), dtype=np.uint8)
+    bp[:, :, :L] = bases
+    qp[:, :, :L] = quals
+    n_reads = U * D
+    n_bytes = n_reads * Lp
+    tot = _round_up(max(n_bytes, 1), 16)
+    fb = np.zeros(tot, dtype=np.uint8)
+    fq = np.zeros(tot, dtype=np.uint8)
+    fb[:n_bytes] = bp.reshape(-1)
+    fq[:n_bytes] = qp.reshape(-1)
+    reads = np.zeros(_round_up(n_reads, 2) + 2, dtype=np.uint64)
+    reads[:n_reads] = (np.arange(n_reads, dtype=np.uint64) * np.uint64(Lp) << np.uint64(16)) | np.uint64(L)
+    Lo = _round_up(L, _l.FGB_OUT_ALIGN)
+    uarr = np.zeros(U + 1, dtype=UNIT_DTYPE)
+    uarr["read_begin"] = np.arange(U + 1, dtype=np.uint32) * D
+    uarr["out_off"] = np.arange(U + 1, dtype=np.uint64) * Lo
+    uarr["cons_len"][:U] = L if D >= min_reads else 0
+    return PackedBatch(fb, fq, reads, uarr, U, n_reads, n_bytes, U * Lo)
+
+
+def plan_tiles(batch: PackedBatch) -> np.ndarray:
+    """fgb_plan_tiles: greedy segmentation of the batch into shared-memory tiles."""
+    lib = _l.load()
+    n = C.c_uint64(0)
+    up = batch.units.ctypes.data_as(C.c_void_p)
+    rp = batch.reads.ctypes.data_as(C.c_void_p)
+    st = lib.fgb_plan_tiles(up, batch.n_units, rp, batch.n_reads, None, 0, C.byref(n))
+    if st != _l.FGB_OK:
+        raise _l.FgbError(st, "fgb_plan_tiles")
+    tiles = np.zeros(max(int(n.value), 1), dtype=TILE_DTYPE)
+    st = lib.fgb_plan_tiles(up, batch.n_units, rp, batch.n_reads, tiles.ctypes.data_as(C.c_void_p),
+                            int(n.value), C.byref(n))
+    if st != _l.FGB_OK:
+        raise _l.FgbError(st, "fgb_plan_tiles")
+    batch.tiles = tiles[: int(n.value)]
+    return batch.tiles
+
+
+@dataclass
+class HostColumns:
+    base: np.ndarray
+    qual: np.ndarray
+    depth: np.ndarray
+    errors: np.ndarray
+
+    @staticmethod
+    def alloc(n_out: int) -> "HostColumns":
+        n = max(n_out, 1)
+        return HostColumns(np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint16),
+                           np.zeros(n, np.uint16))
+
+
+class DeviceBatch:
+    """fgb_batch whose arrays are torch CUDA tensors (device-resident form)."""
+
+    def __init__(self, batch: PackedBatch, device):
+        import torch
+        if batch.tiles is None:
+            plan_tiles(batch)
+        self.host = batch
+        self.device = device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(device)
+        self.bases = t(batch.bases)
+        self.quals = t(batch.quals)
+        self.reads = t(batch.reads)
+        self.units = t(batch.units)
+        self.tiles = t(batch.tiles) if len(batch.tiles) else torch.zeros(32, dtype=torch.uint8, device=device)
+        self.n_tiles = len(batch.tiles)
+
+    def struct(self) -> _l.FgbBatch:
+        b = self.host
+        return _l.FgbBatch(b.n_units, b.n_reads, b.n_bytes, b.n_out, self.n_tiles,
+                           self.bases.data_ptr(), self.quals.data_ptr(), self.reads.data_ptr(),
+                           self.units.data_ptr(), self.tiles.data_ptr())
+
+
+class DeviceColumns:
+    def __init__(self, n_out: int, device):
+        import torch
+        n = max(n_out, 4)
+        self.n_out = n_out
+        self.base = torch.zeros(n, dtype=torch.uint8, device=device)
+        self.qual = torch.zeros(n, dtype=torch.uint8, device=device)
+        self.depth = torch.zeros(n, dtype=torch.int16, device=device)
+        self.errors = torch.zeros(n, dtype=torch.int16, device=device)
+
+    def struct(self) -> _l.FgbColumns:
+        return _l.FgbColumns(self.base.data_ptr(), self.qual.data_ptr(), self.depth.data_ptr(),
+                             self.errors.data_ptr())
+
+    def to_host(self) -> HostColumns:
+        n = self.n_out
+        return HostColumns(self.base[:n].cpu().numpy(), self.qual[:n].cpu().numpy(),
+                           self.depth[:n].cpu().numpy().view(np.uint16),
+                           self.errors[:n].cpu().numpy().view(np.uint16))
+
+
+class Engine:
+    """One GPU's consensus engine (fgb_handle)."""
+
+    def __init__(self, device: int = 0, error_rate_pre_umi: int = 45, error_rate_post_umi: int = 40,
+                 min_reads: int = 1, min_consensus_base_quality: int = 2):
+        self._lib = _l.load()
+        self._h = C.c_void_p()
+        p = _l.FgbParams(error_rate_pre_umi, error_rate_post_umi, min_consensus_base_quality, 0,
+                         min_reads)
+        st = self._lib.fgb_create(device, C.byref(p), C.byref(self._h))
+        if st != _l.FGB_OK:
+            self._h = C.c_void_p()
+            raise _l.FgbError(st, "fgb_create")
+        self.device = device
+        self.min_reads = min_reads
+
+    @classmethod
+    def from_options(cls, opt: VanillaUmiConsensusOptions, device: int = 0) -> "Engine":
+        return cls(device, opt.error_rate_pre_umi, opt.error_rate_post_umi, opt.min_reads,
+                   opt.min_consensus_base_quality)
+
+    def close(self):
+        if self._h:
+            self._lib.fgb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int, where: str):
+        if st != _l.FGB_OK:
+            buf = C.create_string_buffer(512)
+            self._lib.fgb_last_error(self._h, buf, 512)
+            raise _l.FgbError(st, where, buf.value.decode(errors="replace"))
+
+    def tables(self):
+        correct = np.zeros(94, np.float64)
+        err_alt = np.zeros(94, np.float64)
+        ln_pre = C.c_double()
+        sq = np.zeros(94, np.uint8)
+        self._check(self._lib.fgb_get_tables(self._h, correct.ctypes.data, err_alt.ctypes.data,
+                                             C.addressof(ln_pre), sq.ctypes.data), "fgb_get_tables")
+        return correct, err_alt, ln_pre.value, sq
+
+    # ---- device-resident vote -----------------------------------------------------------------
+    def vote_device(self, db: DeviceBatch, out: DeviceColumns, stream: Optional[int] = None):
+        b = db.struct()
+        c = out.struct()
+        self._check(self._lib.fgb_vote_device(self._h, C.byref(b), C.byref(c),
+                                              C.c_void_p(stream or 0)), "fgb_vote_device")
+
+    # ---- host-buffer vote (what a ConsensusCaller implementation calls) -------------------------
+    def submit(self, batch: PackedBatch, out: HostColumns):
+        if batch.tiles is None:
+            plan_tiles(batch)
+        self._keep = (batch, out)
+        b = _l.FgbBatch(batch.n_units, batch.n_reads, batch.n_bytes, batch.n_out, len(batch.tiles),
+                        batch.bases.ctypes.data, batch.quals.ctypes.data, batch.reads.ctypes.data,
+                        batch.units.ctypes.data, batch.tiles.ctypes.data)
+        c = _l.FgbColumns(out.base.ctypes.data, out.qual.ctypes.data, out.depth.ctypes.data,
+                          out.errors.ctypes.data)
+        self._check(self._lib.fgb_submit(self._h, C.byref(b), C.byref(c)), "fgb_submit")
+
+    def wait(self):
+        self._check(self._lib.fgb_wait(self._h), "fgb_wait")
+        self._keep = None
+
+    def vote(self, batch: PackedBatch) -> HostColumns:
+        out = HostColumns.alloc(batch.n_out)
+        self.submit(batch, out)
+        self.wait()
+        return out
+
+    # ---- strand combine -----------------------------------------------------------------------
+    def duplex_combine_device(self, db: DeviceBatch, ss: DeviceColumns, jobs, n_jobs: int,
+                              out_base, out_qual, out_errors, out_status, stream: Optional[int] = None):
+        b = db.struct()
+        c = ss.struct()
+        o = _l.FgbDuplexOut(out_base.data_ptr(), out_qual.data_ptr(), out_errors.data_ptr(),
+                            out_status.data_ptr() if out_status is not None else None)
+        self._check(self._lib.fgb_duplex_combine_device(self._h, C.byref(b), C.byref(c),
+                                                        C.c_void_p(jobs.data_ptr()), n_jobs,
+                                                        C.byref(o), C.c_void_p(stream or 0)),
+                    "fgb_duplex_combine_device")
+
+    def codec_combine_device(self, db: DeviceBatch, ss: DeviceColumns, jobs, n_jobs: int,
+                             params: _l.FgbCodecParams, out: DeviceColumns, status, disagreements=None,
+                             duplex_bases=None, stream: Optional[int] = None):
+        b = db.struct()
+        c = ss.struct()
+        o = _l.FgbCodecOut(out.struct(), status.data_ptr(),
+                           disagreements.data_ptr() if disagreements is not None else None,
+                           duplex_bases.data_ptr() if duplex_bases is not None else None)
+        self._check(self._lib.fgb_codec_combine_device(self._h, C.byref(b), C.byref(c),
+                                                       C.c_void_p(jobs.data_ptr()), n_jobs,
+                                                       C.byref(params), C.byref(o),
+                                                       C.c_void_p(stream or 0)),
+                    "fgb_codec_combine_device")
+
+    # ---- statistics ---------------------------------------------------------------------------
+    def stats(self) -> dict:
+        arr = (C.c_uint64 * _l.FGB_NCOUNTERS)()
+        self._check(self._lib.fgb_stats(self._h, arr), "fgb_stats")
+        return dict(zip(_l.COUNTER_NAMES, [int(x) for x in arr]))
+
+    def stats_device_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.fgb_stats_device_ptr(self._h, C.byref(p)), "fgb_stats_device_ptr")
+        return int(p.value)
+
+    def stats_reset(self):
+        self._check(self._lib.fgb_stats_reset(self._h), "fgb_stats_reset")
+
+    def launch_count(self) -> int:
+        return int(self._lib.fgb_launch_count(self._h))

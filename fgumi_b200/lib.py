@@ -1,0 +1,200 @@
+"""ctypes binding of the C-ABI in include/fgumi_b200.h (libfgumi_b200.so, built in-tree).
+
+The library is the product; this file only declares its symbols.  Loading fails loudly when the
+shared object is missing — there is no Python/CPU fallback for any compute entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfgumi_b200.so")
+
+FGB_OK = 0
+FGB_ERR_INVALID_ARG = 1
+FGB_ERR_CUDA = 2
+FGB_ERR_NO_DEVICE = 3
+FGB_ERR_LAYOUT = 4
+FGB_ERR_UNIT_TOO_LARGE = 5
+FGB_ERR_NOMEM = 6
+FGB_ERR_BUSY = 7
+
+FGB_READ_ALIGN = 4
+FGB_OUT_ALIGN = 4
+FGB_NCOUNTERS = 8
+COUNTER_NAMES = (
+    "units", "positions", "exact_positions", "nocall_positions", "input_reads",
+    "duplex_bases", "duplex_disagreements", "combined_jobs",
+)
+
+FGB_DUPLEX_BOTH, FGB_DUPLEX_A_ONLY, FGB_DUPLEX_B_ONLY, FGB_DUPLEX_NONE = 0, 1, 2, 3
+FGB_CODEC_OK, FGB_CODEC_HIGH_DISAGREEMENT_COUNT, FGB_CODEC_HIGH_DISAGREEMENT_RATE = 0, 1, 2
+
+
+class FgbParams(C.Structure):
+    _fields_ = [
+        ("error_rate_pre_umi", C.c_uint8),
+        ("error_rate_post_umi", C.c_uint8),
+        ("min_consensus_base_quality", C.c_uint8),
+        ("reserved0", C.c_uint8),
+        ("min_reads", C.c_uint32),
+    ]
+
+
+class FgbUnit(C.Structure):
+    _fields_ = [("out_off", C.c_uint64), ("read_begin", C.c_uint32), ("cons_len", C.c_uint32)]
+
+
+class FgbTile(C.Structure):
+    _fields_ = [
+        ("byte_begin", C.c_uint64),
+        ("byte_len", C.c_uint32),
+        ("unit_begin", C.c_uint32),
+        ("n_units", C.c_uint32),
+        ("read_begin", C.c_uint32),
+        ("n_reads", C.c_uint32),
+        ("flags", C.c_uint32),
+    ]
+
+
+class FgbBatch(C.Structure):
+    _fields_ = [
+        ("n_units", C.c_uint64),
+        ("n_reads", C.c_uint64),
+        ("n_bytes", C.c_uint64),
+        ("n_out", C.c_uint64),
+        ("n_tiles", C.c_uint64),
+        ("bases", C.c_void_p),
+        ("quals", C.c_void_p),
+        ("reads", C.c_void_p),
+        ("units", C.c_void_p),
+        ("tiles", C.c_void_p),
+    ]
+
+
+class FgbColumns(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("qual", C.c_void_p), ("depth", C.c_void_p),
+                ("errors", C.c_void_p)]
+
+
+class FgbDuplexJob(C.Structure):
+    _fields_ = [("unit_a", C.c_uint32), ("unit_b", C.c_uint32), ("out_off", C.c_uint64)]
+
+
+class FgbDuplexOut(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("qual", C.c_void_p), ("errors", C.c_void_p),
+                ("status", C.c_void_p)]
+
+
+class FgbCodecJob(C.Structure):
+    _fields_ = [
+        ("unit_a", C.c_uint32),
+        ("unit_b", C.c_uint32),
+        ("out_off", C.c_uint64),
+        ("len", C.c_uint32),
+        ("pad_a_left", C.c_uint32),
+        ("pad_b_left", C.c_uint32),
+        ("rc_a", C.c_uint8),
+        ("rc_b", C.c_uint8),
+        ("rc_out", C.c_uint8),
+        ("reserved0", C.c_uint8),
+    ]
+
+
+class FgbCodecParams(C.Structure):
+    _fields_ = [
+        ("single_strand_qual", C.c_int32),
+        ("outer_bases_qual", C.c_int32),
+        ("outer_bases_length", C.c_uint32),
+        ("max_duplex_disagreements", C.c_uint32),
+        ("max_duplex_disagreement_rate", C.c_double),
+    ]
+
+
+class FgbCodecOut(C.Structure):
+    _fields_ = [("cols", FgbColumns), ("status", C.c_void_p), ("disagreements", C.c_void_p),
+                ("duplex_bases", C.c_void_p)]
+
+
+# Every symbol include/fgumi_b200.h declares; tests check the .so exports all of them.
+SYMBOLS = (
+    "fgb_abi_version", "fgb_create", "fgb_destroy", "fgb_strerror", "fgb_last_error",
+    "fgb_get_tables", "fgb_host_tables", "fgb_tile_capacity_bytes", "fgb_tile_max_units", "fgb_tile_max_reads",
+    "fgb_plan_tiles", "fgb_vote_device", "fgb_submit", "fgb_wait", "fgb_host_alloc",
+    "fgb_host_free", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
+    "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
+)
+
+_lib = None
+
+
+class FgbError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        msg = f"{where}: fgb_status {status}"
+        try:
+            msg += f" ({load().fgb_strerror(status).decode()})"
+        except Exception:  # pragma: no cover
+            pass
+        if detail:
+            msg += f": {detail}"
+        super().__init__(msg)
+
+
+def load() -> C.CDLL:
+    """dlopen libfgumi_b200.so and declare prototypes.  Raises if the library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  fgumi_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+    lib.fgb_abi_version.restype = u32
+    lib.fgb_create.argtypes = [C.c_int, C.POINTER(FgbParams), C.POINTER(vp)]
+    lib.fgb_create.restype = C.c_int32
+    lib.fgb_destroy.argtypes = [vp]
+    lib.fgb_destroy.restype = None
+    lib.fgb_strerror.argtypes = [C.c_int32]
+    lib.fgb_strerror.restype = C.c_char_p
+    lib.fgb_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]
+    lib.fgb_last_error.restype = C.c_size_t
+    lib.fgb_get_tables.argtypes = [vp, vp, vp, vp, vp]
+    lib.fgb_get_tables.restype = C.c_int32
+    lib.fgb_host_tables.argtypes = [C.c_uint8, C.c_uint8, vp, vp, vp, vp, vp, vp]
+    lib.fgb_host_tables.restype = C.c_int32
+    for f in ("fgb_tile_capacity_bytes", "fgb_tile_max_units", "fgb_tile_max_reads"):
+        getattr(lib, f).restype = u32
+        getattr(lib, f).argtypes = []
+    lib.fgb_plan_tiles.argtypes = [vp, u64, vp, u64, vp, u64, C.POINTER(u64)]
+    lib.fgb_plan_tiles.restype = C.c_int32
+    lib.fgb_vote_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), vp]
+    lib.fgb_vote_device.restype = C.c_int32
+    lib.fgb_submit.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns)]
+    lib.fgb_submit.restype = C.c_int32
+    lib.fgb_wait.argtypes = [vp]
+    lib.fgb_wait.restype = C.c_int32
+    lib.fgb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.fgb_host_alloc.restype = C.c_int32
+    lib.fgb_host_free.argtypes = [vp]
+    lib.fgb_host_free.restype = None
+    lib.fgb_duplex_combine_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), vp,
+                                              u64, C.POINTER(FgbDuplexOut), vp]
+    lib.fgb_duplex_combine_device.restype = C.c_int32
+    lib.fgb_codec_combine_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), vp,
+                                             u64, C.POINTER(FgbCodecParams),
+                                             C.POINTER(FgbCodecOut), vp]
+    lib.fgb_codec_combine_device.restype = C.c_int32
+    lib.fgb_stats.argtypes = [vp, C.POINTER(u64)]
+    lib.fgb_stats.restype = C.c_int32
+    lib.fgb_stats_device_ptr.argtypes = [vp, C.POINTER(vp)]
+    lib.fgb_stats_device_ptr.restype = C.c_int32
+    lib.fgb_stats_reset.argtypes = [vp]
+    lib.fgb_stats_reset.restype = C.c_int32
+    lib.fgb_launch_count.argtypes = [vp]
+    lib.fgb_launch_count.restype = u64
+    _lib = lib
+    return lib

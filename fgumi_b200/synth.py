@@ -1,0 +1,162 @@
+"""Synthetic grouped-family generator (restates the model of `fgumi simulate grouped-reads`).
+
+Model (reference, /root/reference/src/lib/):
+  * template bases uniform over ACGT; every read of a family copies the template
+    (commands/simulate/grouped_reads.rs:530-556);
+  * qualities from PositionQualityModel::default — ramp 25->37 over the first 10 bases, 37 flat,
+    -0.08/base after position 100, + N(0, 2) noise, round, clamp to [2, 41]; R2 gets -2
+    (simulate/quality.rs:54-66, 99-124, 187-199);
+plus the two knobs BASELINE.json's configs need and the reference's simulator lacks (SURVEY §0
+fact 4): a FIXED (or Zipf) family depth and Bernoulli(error_rate) substitution errors, uniform over
+the three alternative bases.  The reference's RNG stream (StdRng/ChaCha12) is not reproducible here;
+only the model is restated.
+
+`host_pileup` builds small dense pileups with numpy (tests, CPU baseline sample);
+`device_batch_fixed` / `device_batch_ragged` build BASELINE-size batches directly in HBM with torch
+(plumbing only: the consensus itself never runs in torch).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import lib as _l
+from .engine import PackedBatch, TILE_DTYPE, UNIT_DTYPE, _round_up
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def _base_quality_curve(L: int) -> np.ndarray:
+    pos = np.arange(L, dtype=np.float64)
+    q = np.where(pos < 10, 25.0 + (pos / 10.0) * 12.0, 37.0)
+    q = np.where(pos >= 100, np.maximum(37.0 - (pos - 100.0) * 0.08, 2.0), q)
+    return q
+
+
+def host_pileup(n_units: int, depth: int, L: int = 150, error_rate: float = 1e-3, seed: int = 42,
+                r2: bool = False, n_rate: float = 0.0, min_input_q: int = 10):
+    """Dense [U, D, L] bases/quals as SourceRead rows (quality masking of
+    vanilla_caller.rs:903-911 already applied: q < min_input_q -> ('N', 2))."""
+    rng = np.random.default_rng(seed)
+    tmpl = ACGT[rng.integers(0, 4, size=(n_units, 1, L))]
+    bases = np.broadcast_to(tmpl, (n_units, depth, L)).copy()
+    if error_rate > 0:
+        err = rng.random((n_units, depth, L)) < error_rate
+        shift = rng.integers(1, 4, size=(n_units, depth, L))
+        code = np.searchsorted(ACGT, bases)          # A,C,G,T -> 0..3 (ACGT is sorted in ASCII)
+        alt = ACGT[(code + shift) % 4]
+        bases = np.where(err, alt, bases)
+    q = _base_quality_curve(L)[None, None, :] + rng.normal(0.0, 2.0, size=(n_units, depth, L))
+    q = np.clip(np.rint(q), 2, 41)
+    if r2:
+        q = np.clip(q - 2, 2, 41)
+    quals = q.astype(np.uint8)
+    if n_rate > 0:
+        nm = rng.random((n_units, depth, L)) < n_rate
+        bases = np.where(nm, np.uint8(ord("N")), bases)
+        quals = np.where(nm, np.uint8(2), quals)
+    low = quals < min_input_q
+    bases = np.where(low, np.uint8(ord("N")), bases).astype(np.uint8)
+    quals = np.where(low, np.uint8(2), quals).astype(np.uint8)
+    return bases, quals
+
+
+def zipf_depths(n_units: int, lo: int = 1, hi: int = 100, s: float = 1.0, seed: int = 42) -> np.ndarray:
+    """Truncated Zipf(s) on [lo, hi] (BASELINE.json config 5)."""
+    rng = np.random.default_rng(seed)
+    k = np.arange(lo, hi + 1, dtype=np.float64)
+    p = k ** (-s)
+    p /= p.sum()
+    return rng.choice(np.arange(lo, hi + 1), size=n_units, p=p).astype(np.int64)
+
+
+class TorchBatch:
+    """A device-resident fgb_batch built by torch (same fields as engine.DeviceBatch)."""
+
+    def __init__(self, bases, quals, reads, units, tiles, host: PackedBatch):
+        self.bases, self.quals, self.reads, self.units, self.tiles = bases, quals, reads, units, tiles
+        self.host = host
+        self.n_tiles = len(host.tiles)
+
+    def struct(self) -> _l.FgbBatch:
+        b = self.host
+        return _l.FgbBatch(b.n_units, b.n_reads, b.n_bytes, b.n_out, self.n_tiles,
+                           self.bases.data_ptr(), self.quals.data_ptr(), self.reads.data_ptr(),
+                           self.units.data_ptr(), self.tiles.data_ptr())
+
+
+def _gen_rows(torch, dev, gen, depths_t, L, Lp, error_rate, out_b, out_q, row0, chunk_units):
+    """Fill rows [row0, row0 + sum(depths)) of the [R, Lp] byte matrices for one chunk of units."""
+    U = depths_t.numel()
+    acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+    curve = torch.from_numpy(_base_quality_curve(L)).to(dev, torch.float32)
+    tmpl_code = torch.randint(0, 4, (U, L), device=dev, generator=gen, dtype=torch.int64)
+    unit_of_row = torch.repeat_interleave(torch.arange(U, device=dev), depths_t)
+    R = unit_of_row.numel()
+    code = tmpl_code[unit_of_row]                                   # [R, L]
+    if error_rate > 0:
+        err = torch.rand((R, L), device=dev, generator=gen) < error_rate
+        shift = torch.randint(1, 4, (R, L), device=dev, generator=gen, dtype=torch.int64)
+        code = torch.where(err, (code + shift) % 4, code)
+    q = curve[None, :] + 2.0 * torch.randn((R, L), device=dev, generator=gen)
+    q = torch.clamp(torch.round(q), 2, 41).to(torch.uint8)
+    b = acgt[code]
+    low = q < 10                                                    # min_input_base_quality mask
+    b = torch.where(low, torch.tensor(78, dtype=torch.uint8, device=dev), b)
+    q = torch.where(low, torch.tensor(2, dtype=torch.uint8, device=dev), q)
+    out_b[row0:row0 + R, :L] = b
+    out_q[row0:row0 + R, :L] = q
+    return R
+
+
+def make_descriptors(depths: np.ndarray, L: int = 150, min_reads: int = 1) -> PackedBatch:
+    """Read/unit/tile descriptors of a batch whose reads all have length L (columns left empty)."""
+    from .engine import plan_tiles
+    depths = np.asarray(depths, dtype=np.int64)
+    U = int(depths.size)
+    Lp = _round_up(L, _l.FGB_READ_ALIGN)
+    Lo = _round_up(L, _l.FGB_OUT_ALIGN)
+    read_begin = np.zeros(U + 1, dtype=np.int64)
+    np.cumsum(depths, out=read_begin[1:])
+    R = int(read_begin[-1])
+    reads = np.zeros(_round_up(R, 2) + 2, dtype=np.uint64)
+    reads[:R] = ((np.arange(R, dtype=np.uint64) * np.uint64(Lp)) << np.uint64(16)) | np.uint64(L)
+    units = np.zeros(U + 1, dtype=UNIT_DTYPE)
+    units["read_begin"] = read_begin.astype(np.uint32)
+    units["out_off"] = np.arange(U + 1, dtype=np.uint64) * np.uint64(Lo)
+    units["cons_len"][:U] = np.where(depths >= min_reads, L, 0)
+    host = PackedBatch(np.zeros(0, np.uint8), np.zeros(0, np.uint8), reads, units, U, R, R * Lp,
+                       U * Lo)
+    plan_tiles(host)
+    return host
+
+
+def device_batch(torch, device, depths: np.ndarray, L: int = 150, error_rate: float = 1e-3,
+                 seed: int = 42, min_reads: int = 1, chunk_rows: int = 2_000_000) -> TorchBatch:
+    """Build a batch with per-unit depths `depths` (fixed or ragged), all reads of length L,
+    directly in device memory.  Host keeps only the (small) unit/read/tile descriptors."""
+    depths = np.asarray(depths, dtype=np.int64)
+    U = int(depths.size)
+    Lp = _round_up(L, _l.FGB_READ_ALIGN)
+    host = make_descriptors(depths, L, min_reads)
+    reads, units = host.reads, host.units
+    read_begin = units["read_begin"].astype(np.int64)
+    R = host.n_reads
+    # device columns
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    tot_rows = R + (16 // 4)   # >= 16 bytes of slack so the last tile's 16-byte round-up is in bounds
+    bmat = torch.zeros((tot_rows, Lp), dtype=torch.uint8, device=dev)
+    qmat = torch.zeros((tot_rows, Lp), dtype=torch.uint8, device=dev)
+    u0 = 0
+    while u0 < U:
+        # take units until ~chunk_rows rows
+        u1 = int(np.searchsorted(read_begin, read_begin[u0] + chunk_rows, side="right")) - 1
+        u1 = max(u0 + 1, min(U, u1))
+        d = torch.from_numpy(depths[u0:u1]).to(dev)
+        _gen_rows(torch, dev, gen, d, L, Lp, error_rate, bmat, qmat, int(read_begin[u0]), u1 - u0)
+        u0 = u1
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
+    tiles = host.tiles if len(host.tiles) else np.zeros(1, dtype=TILE_DTYPE)
+    return TorchBatch(bmat.reshape(-1), qmat.reshape(-1), to_dev(reads), to_dev(units), to_dev(tiles),
+                      host)

@@ -1,0 +1,275 @@
+/*
+ * fgumi_b200.h — C-ABI of the B200-native UMI-consensus engine.
+ *
+ * This is the drop-in boundary for fgumi's consensus hot path.  The reference (fgumi 0.2.0,
+ * pure Rust, `#![deny(unsafe_code)]`) has no FFI; its only boundary is the trait
+ *     crates/fgumi-consensus/src/caller.rs:205-234   trait ConsensusCaller
+ *         fn consensus_reads(&mut self, records: Vec<RawRecord>) -> Result<ConsensusOutput>
+ * whose per-family inner loops are
+ *     vanilla_caller.rs:1260-1358  create_consensus_from_source_reads   -> fgb_vote_* / fgb_submit
+ *     base_builder.rs:295-458      ConsensusBaseBuilder::{add,call}      -> (inside the vote kernel)
+ *     duplex_caller.rs:838-1015    DuplexConsensusCaller::duplex_consensus -> fgb_duplex_combine_*
+ *     codec_caller.rs:1029-1212    build_duplex_consensus_from_padded +
+ *                                  mask_consensus_quals_query_based      -> fgb_codec_combine_*
+ *     caller.rs:238-286            ConsensusCallingStats                 -> fgb_stats
+ * A Rust maintainer binds these entry points with a `extern "C"` block behind a
+ * `ConsensusCaller` impl (INTEGRATION.md shows the stub).  Everything here is plain pointers
+ * and sizes; no C++/torch types cross the boundary.  Errors are status codes — no exceptions,
+ * no aborts across the ABI (anyhow::Error maps to a non-zero fgb_status + fgb_last_error()).
+ *
+ * Data model ("SoA base/qual byte columns with per-family offsets"):
+ *   unit   = one sub-family = one consensus read (Fragment / R1 / R2 of an MI group;
+ *            vanilla_caller.rs:1124 process_subgroup).  Its reads are the SourceRead rows
+ *            (vanilla_caller.rs:129-146) AFTER host prep: oriented, quality-masked, clipped,
+ *            CIGAR-filtered, in reference order (order matters: the f64 Kahan vote is
+ *            order-dependent, base_builder.rs:312-324).
+ *   bases[], quals[]  two byte columns; read r occupies bytes
+ *            [off_r, off_r+len_r) of BOTH columns, off_r % FGB_READ_ALIGN == 0.
+ *   reads[r] = FGB_READ_DESC(off_r, len_r); reads of a unit are consecutive.
+ *   units[u] = {out_off, read_begin, cons_len}; units[U] is a sentinel
+ *            {n_out, n_reads, 0}.  cons_len = min_reads-th longest read
+ *            (vanilla_caller.rs:1269-1277), out_off % FGB_OUT_ALIGN == 0.
+ *   tiles[t] = a run of consecutive units that fits one shared-memory stage; produced by
+ *            fgb_plan_tiles() — part of the packed batch, like the offsets.
+ *   output   four columns cons_base/cons_qual (u8) and cons_depth/cons_errors (u16); unit u
+ *            owns elements [out_off, out_off+cons_len).
+ */
+#ifndef FGUMI_B200_H
+#define FGUMI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FGB_ABI_VERSION 1
+#define FGB_READ_ALIGN 4u   /* byte alignment of every read row in bases[]/quals[]          */
+#define FGB_OUT_ALIGN 4u    /* element alignment of every unit's output row                 */
+#define FGB_MAX_READ_LEN 65535u
+#define FGB_MAX_PHRED 93u   /* phred.rs:28 */
+#define FGB_NTABLE 94u      /* tables are indexed by input quality 0..=93, base_builder.rs:258 */
+
+typedef int32_t fgb_status;
+enum {
+  FGB_OK = 0,
+  FGB_ERR_INVALID_ARG = 1,   /* null pointer, bad size, bad params                           */
+  FGB_ERR_CUDA = 2,          /* a CUDA runtime call failed; see fgb_last_error()              */
+  FGB_ERR_NO_DEVICE = 3,     /* no usable sm_100 device — the engine has NO CPU fallback      */
+  FGB_ERR_LAYOUT = 4,        /* batch violates the layout rules above (alignment, ranges)     */
+  FGB_ERR_UNIT_TOO_LARGE = 5,/* a single unit exceeds fgb_tile_capacity_bytes()               */
+  FGB_ERR_NOMEM = 6,
+  FGB_ERR_BUSY = 7           /* fgb_submit while a previous submit has not been waited on     */
+};
+
+typedef struct fgb_handle fgb_handle;   /* one per GPU; thread-compatible, not thread-safe    */
+
+/* Mirrors the arithmetic-relevant part of VanillaUmiConsensusOptions
+ * (vanilla_caller.rs:284-341; CLI defaults common.rs:225-249).  Host-prep options
+ * (min_input_base_quality, trim, max_reads) live in the host caller, not here. */
+typedef struct fgb_params {
+  uint8_t error_rate_pre_umi;          /* -1, default 45 */
+  uint8_t error_rate_post_umi;         /* -2, default 40 */
+  uint8_t min_consensus_base_quality;  /* default 2 (CLI) / 40 (library default)              */
+  uint8_t reserved0;
+  uint32_t min_reads;                  /* per-position depth gate, vanilla_caller.rs:1345     */
+} fgb_params;
+
+typedef uint64_t fgb_read_desc;        /* (byte_off << 16) | len                              */
+#define FGB_READ_DESC(off, len) ((((uint64_t)(off)) << 16) | ((uint64_t)(len) & 0xFFFFu))
+#define FGB_READ_OFF(d) ((uint64_t)(d) >> 16)
+#define FGB_READ_LEN(d) ((uint32_t)((d) & 0xFFFFu))
+
+typedef struct fgb_unit {
+  uint64_t out_off;     /* first output element of this unit                                  */
+  uint32_t read_begin;  /* index of its first read in reads[]; n_reads = next.read_begin - it */
+  uint32_t cons_len;    /* consensus length (positions to call)                               */
+} fgb_unit;
+
+typedef struct fgb_tile {
+  uint64_t byte_begin;  /* 16-aligned start of the tile's byte range in bases[]/quals[]       */
+  uint32_t byte_len;    /* multiple of 16                                                     */
+  uint32_t unit_begin;
+  uint32_t n_units;
+  uint32_t read_begin;
+  uint32_t n_reads;
+  uint32_t flags;       /* reserved, 0                                                        */
+} fgb_tile;
+
+typedef struct fgb_batch {
+  uint64_t n_units;     /* U */
+  uint64_t n_reads;     /* R */
+  uint64_t n_bytes;     /* valid bytes in bases[]/quals[]; allocation must be padded to 16    */
+  uint64_t n_out;       /* elements in each output column                                     */
+  uint64_t n_tiles;     /* T */
+  const uint8_t* bases;
+  const uint8_t* quals;
+  const fgb_read_desc* reads;  /* [R]   */
+  const fgb_unit* units;       /* [U+1] */
+  const fgb_tile* tiles;       /* [T]   */
+} fgb_batch;
+
+typedef struct fgb_columns {   /* consensus output columns, [n_out] each                      */
+  uint8_t* base;
+  uint8_t* qual;
+  uint16_t* depth;
+  uint16_t* errors;
+} fgb_columns;
+
+/* Device-side counters accumulated over every launch on a handle (the part of
+ * ConsensusCallingStats / CodecConsensusStats that is computed inside the kernels; the
+ * host-side read/rejection counters live in the host caller).  These are what the multi-GPU
+ * driver all-reduces (sum) over NCCL at end of run. */
+enum {
+  FGB_CTR_UNITS = 0,            /* units voted                                                */
+  FGB_CTR_POSITIONS = 1,        /* consensus positions emitted                                */
+  FGB_CTR_EXACT_POSITIONS = 2,  /* positions that took the exact f64 path (diagnostic)        */
+  FGB_CTR_NOCALL_POSITIONS = 3, /* positions emitted as N                                     */
+  FGB_CTR_INPUT_READS = 4,      /* source reads consumed                                      */
+  FGB_CTR_DUPLEX_BASES = 5,     /* codec_caller.rs:1157 consensus_duplex_bases_emitted        */
+  FGB_CTR_DUPLEX_DISAGREE = 6,  /* codec_caller.rs:1158 duplex_disagreement_base_count        */
+  FGB_CTR_COMBINED = 7,         /* strand-combine jobs processed                              */
+  FGB_NCOUNTERS = 8
+};
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+/* Builds the two 94-entry f64 likelihood tables (base_builder.rs:252-278) and the
+ * single-input quality LUT (vanilla_caller.rs:463-482) with the host libm, uploads them, and
+ * creates the streams/events the handle owns.  Fails with FGB_ERR_NO_DEVICE if `device` is not
+ * a CUDA device of compute capability 10.x. */
+fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out);
+void fgb_destroy(fgb_handle* h);
+const char* fgb_strerror(fgb_status s);
+/* Copies the last detailed error text of this handle (e.g. the CUDA error string). */
+size_t fgb_last_error(const fgb_handle* h, char* buf, size_t buf_len);
+uint32_t fgb_abi_version(void);
+
+/* The host-computed tables, for inspection/tests: correct[94], err_alt[94], *ln_pre,
+ * single_input_q[94] (any pointer may be NULL). */
+fgb_status fgb_get_tables(const fgb_handle* h, double* correct, double* err_alt, double* ln_pre,
+                          uint8_t* single_input_q);
+
+/* Pure host function (no device): the same tables fgb_create builds, for any (pre, post).
+ * qt[256] is the fast-path quality threshold by depth (255 = never); any pointer may be NULL. */
+fgb_status fgb_host_tables(uint8_t error_rate_pre_umi, uint8_t error_rate_post_umi,
+                           double* correct, double* err_alt, double* ln_pre,
+                           uint8_t* single_input_q, uint8_t* qt, uint32_t* fast_qual);
+
+/* ---- batch planning (pure host code, no device needed) -------------------------------- */
+/* Bytes of one column that a tile may span. */
+uint32_t fgb_tile_capacity_bytes(void);
+uint32_t fgb_tile_max_units(void);
+uint32_t fgb_tile_max_reads(void);
+/* Greedy segmentation of units[0..n_units) into tiles.  Writes at most `cap` tiles to `out`
+ * (may be NULL to count) and returns the number of tiles needed through *n_tiles.  Validates the
+ * layout rules (FGB_ERR_LAYOUT) and the capacity (FGB_ERR_UNIT_TOO_LARGE). */
+fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_read_desc* reads,
+                          uint64_t n_reads, fgb_tile* out, uint64_t cap, uint64_t* n_tiles);
+
+/* ---- the vote (simplex / single-strand consensus), K1 --------------------------------- */
+/* Device-resident form: every pointer in `in`/`out` is a DEVICE pointer on the handle's GPU.
+ * Enqueues ONE kernel launch on `stream` (a cudaStream_t passed as void*; NULL = default
+ * stream) that calls every position of every unit.  Asynchronous. */
+fgb_status fgb_vote_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* out,
+                           void* stream);
+
+/* Host-buffer form — the call a ConsensusCaller implementation makes.  Every pointer is a HOST
+ * pointer (pinned memory makes the copies asynchronous; pageable memory works).  The library
+ * owns the device buffers, chunks the batch at tile boundaries and overlaps H2D copy / vote /
+ * D2H copy on its own streams.  Returns after enqueueing; fgb_wait() blocks until the output
+ * columns are complete.  The caller owns all host buffers and must keep them alive until
+ * fgb_wait() returns. */
+fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out);
+fgb_status fgb_wait(fgb_handle* h);
+
+/* Pinned host allocation helpers (cudaHostAlloc / cudaFreeHost). */
+fgb_status fgb_host_alloc(void** p, size_t bytes);
+void fgb_host_free(void* p);
+
+/* ---- strand combine, K2 (duplex) and K3 (CODEC) --------------------------------------- */
+/* One duplex combine job: AB single-strand unit ⊕ BA single-strand unit → one duplex read.
+ * len = min(cons_len[unit_a], cons_len[unit_b]) (duplex_caller.rs:846-849).  Errors are
+ * recounted against the pooled source reads of both units (duplex_caller.rs:943-951). */
+typedef struct fgb_duplex_job {
+  uint32_t unit_a;      /* index into the voted batch's units[]                               */
+  uint32_t unit_b;
+  uint64_t out_off;     /* first output element (FGB_OUT_ALIGN-aligned)                       */
+} fgb_duplex_job;
+
+enum {   /* per-job status: which arm of duplex_consensus (duplex_caller.rs:855-1013) was taken */
+  FGB_DUPLEX_BOTH = 0,     /* combined; output length = min(cons_len a, cons_len b)            */
+  FGB_DUPLEX_A_ONLY = 1,   /* B had no coverage in the truncated region; output = A, full len  */
+  FGB_DUPLEX_B_ONLY = 2,   /* A had no coverage; output = B, full len (is_ba_only)             */
+  FGB_DUPLEX_NONE = 3      /* neither strand has coverage: no duplex read                       */
+};
+
+typedef struct fgb_duplex_out {
+  uint8_t* base;           /* [n_out]; a job's row must hold max(cons_len a, cons_len b)       */
+  uint8_t* qual;           /* [n_out] */
+  uint16_t* errors;        /* [n_out] */
+  uint8_t* status;         /* [n_jobs] FGB_DUPLEX_* (may be NULL)                              */
+} fgb_duplex_out;
+
+/* `ss` are the four single-strand columns the vote wrote for `in` (device pointers). */
+fgb_status fgb_duplex_combine_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss,
+                                     const fgb_duplex_job* jobs, uint64_t n_jobs,
+                                     const fgb_duplex_out* out, void* stream);
+
+/* One CODEC combine job (codec_caller.rs:721-781): the two single-strand consensuses are
+ * oriented (reverse-complemented when flagged, :507-520), padded with lowercase 'n'/Q0/0/0 to
+ * `len` (:980), combined (:1029-1152), quality-masked (:1183-1212) and, when `rc_out`, the
+ * result is reverse-complemented back (:783-784). */
+typedef struct fgb_codec_job {
+  uint32_t unit_a;      /* R1 single-strand unit                                              */
+  uint32_t unit_b;      /* R2 single-strand unit                                              */
+  uint64_t out_off;
+  uint32_t len;         /* consensus_length                                                   */
+  uint32_t pad_a_left;  /* 'n' columns to the left of A after orientation                     */
+  uint32_t pad_b_left;
+  uint8_t rc_a, rc_b;   /* reverse-complement the single-strand consensus before padding      */
+  uint8_t rc_out;       /* reverse-complement the combined consensus                          */
+  uint8_t reserved0;
+} fgb_codec_job;
+
+typedef struct fgb_codec_params {   /* CodecConsensusOptions, codec_caller.rs:99-166          */
+  int32_t single_strand_qual;       /* -1 = None                                              */
+  int32_t outer_bases_qual;         /* -1 = None                                              */
+  uint32_t outer_bases_length;
+  uint32_t max_duplex_disagreements;
+  double max_duplex_disagreement_rate;
+} fgb_codec_params;
+
+enum {   /* per-job status byte (the reference raises anyhow::bail! and the command downgrades
+            it to a per-group rejection by substring match, commands/codec.rs:391,617-624)    */
+  FGB_CODEC_OK = 0,
+  FGB_CODEC_HIGH_DISAGREEMENT_COUNT = 1,   /* codec_caller.rs:1160-1162 */
+  FGB_CODEC_HIGH_DISAGREEMENT_RATE = 2     /* codec_caller.rs:1163-1165 */
+};
+
+typedef struct fgb_codec_out {
+  fgb_columns cols;        /* [n_out] combined consensus columns                               */
+  uint8_t* status;         /* [n_jobs] FGB_CODEC_*                                             */
+  uint32_t* disagreements; /* [n_jobs] duplex_disagreements (may be NULL)                      */
+  uint32_t* duplex_bases;  /* [n_jobs] duplex_bases_count   (may be NULL)                      */
+} fgb_codec_out;
+
+fgb_status fgb_codec_combine_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss,
+                                    const fgb_codec_job* jobs, uint64_t n_jobs,
+                                    const fgb_codec_params* cp, const fgb_codec_out* out,
+                                    void* stream);
+
+/* ---- statistics, K4 -------------------------------------------------------------------- */
+/* Synchronises the handle's streams and copies the device counters (cumulative). */
+fgb_status fgb_stats(fgb_handle* h, uint64_t counters[FGB_NCOUNTERS]);
+/* Device pointer to the live counter block (u64[FGB_NCOUNTERS]) so a multi-GPU driver can
+ * ncclAllReduce it in place without a host round trip. */
+fgb_status fgb_stats_device_ptr(fgb_handle* h, uint64_t** dev_counters);
+fgb_status fgb_stats_reset(fgb_handle* h);
+/* Number of kernel launches this handle has enqueued (for bench.py's gpu_launches). */
+uint64_t fgb_launch_count(const fgb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FGUMI_B200_H */

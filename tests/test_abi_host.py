@@ -1,0 +1,150 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol
+include/fgumi_b200.h declares, the host-built tables are bit-identical to the oracle's, the tile
+planner honours the layout rules, and compute entry points fail loudly without a GPU (no CPU
+fallback).  No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as graft
+from tests import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fg():
+    graft.build()
+    import fgumi_b200
+    return fgumi_b200
+
+
+def test_header_symbols_exported(fg):
+    hdr = open(os.path.join(ROOT, "include", "fgumi_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(fgb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = fg.lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(fg.lib.SYMBOLS)
+    assert lib.fgb_abi_version() == 1
+
+
+def test_struct_sizes_match_header(fg):
+    l = fg.lib
+    assert C.sizeof(l.FgbUnit) == 16 and C.sizeof(l.FgbTile) == 32
+    assert C.sizeof(l.FgbParams) == 8
+    assert C.sizeof(l.FgbDuplexJob) == 16 and C.sizeof(l.FgbCodecJob) == 32
+    assert C.sizeof(l.FgbCodecParams) == 24
+
+
+@pytest.mark.parametrize("pre,post", [(45, 40), (50, 50), (93, 93), (93, 10), (30, 20), (10, 45)])
+def test_host_tables_bit_identical_to_oracle(fg, pre, post):
+    lib = fg.lib.load()
+    c = np.zeros(94); e = np.zeros(94); lp = C.c_double(); sq = np.zeros(94, np.uint8)
+    qt = np.zeros(256, np.uint8); fq = C.c_uint32()
+    st = lib.fgb_host_tables(pre, post, c.ctypes.data, e.ctypes.data, C.addressof(lp),
+                             sq.ctypes.data, qt.ctypes.data, C.addressof(fq))
+    assert st == 0
+    oc, oe, olp, osq = O.tables(pre, post)
+    assert c.tobytes() == oc.tobytes() and e.tobytes() == oe.tobytes()
+    assert lp.value == olp and np.array_equal(sq, osq)
+    assert fq.value == O.load().orc_ln_prob_to_phred(olp)
+    # the proof table: n identical observations at quality >= qt[n] must clear the 23.0 gap
+    d = oc - oe
+    for n in (1, 2, 3, 8, 100, 255):
+        if qt[n] <= 93:
+            dm = min(d[qt[n]:])
+            assert n * dm > 23.0
+            b, q, _, ll = O.builder_call(pre, post, b"A" * n, [int(qt[n])] * n)
+            assert ll[0] - ll[1] > 23.0 and (b, q) == ("A", fq.value)
+
+
+def test_fast_path_threshold_defaults(fg):
+    lib = fg.lib.load()
+    qt = np.zeros(256, np.uint8)
+    lib.fgb_host_tables(45, 40, None, None, None, None, qt.ctypes.data, None)
+    assert qt[0] == 255 and qt[1] == 255 and qt[2] == 255   # depth <= 2 can never clear 23
+    assert qt[8] <= 10           # depth 8: every unmasked base (q >= 10) qualifies
+    assert qt[3] <= 31
+
+
+def test_create_without_gpu_fails_loudly(fg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(fg.lib.FgbError) as ei:
+        fg.Engine(device=0)
+    assert ei.value.status == fg.lib.FGB_ERR_NO_DEVICE
+
+
+def _plan(fg, units, min_reads=1):
+    b = fg.pack_source_reads(units, min_reads)
+    return b, fg.plan_tiles(b)
+
+
+def test_planner_small_and_empty(fg):
+    b, tiles = _plan(fg, [])
+    assert len(tiles) == 0
+    rows = [(b"ACGT" * 10, bytes([30] * 40))] * 3
+    b, tiles = _plan(fg, [rows, rows])
+    assert len(tiles) == 1
+    t = tiles[0]
+    assert t["n_units"] == 2 and t["n_reads"] == 6 and t["byte_begin"] == 0
+    assert t["byte_len"] % 16 == 0 and t["byte_len"] >= 6 * 40
+
+
+def test_planner_splits_on_capacity(fg):
+    cap = fg.lib.load().fgb_tile_capacity_bytes()
+    L = 152
+    rows = [(b"A" * L, bytes([30] * L))] * 8
+    n_units = 3 * (cap // (8 * L)) + 1
+    b, tiles = _plan(fg, [rows] * n_units)
+    assert tiles["n_units"].sum() == n_units and tiles["n_reads"].sum() == 8 * n_units
+    assert (tiles["byte_len"] <= cap).all() and (tiles["byte_begin"] % 16 == 0).all()
+    assert len(tiles) == 4
+    # tiles are contiguous in unit order
+    assert np.array_equal(tiles["unit_begin"][1:], np.cumsum(tiles["n_units"])[:-1])
+
+
+def test_planner_flags_oversize_unit_direct(fg):
+    cap = fg.lib.load().fgb_tile_capacity_bytes()
+    big = [(b"C" * 200, bytes([30] * 200))] * (cap // 200 + 5)
+    small = [(b"A" * 20, bytes([30] * 20))] * 2
+    b, tiles = _plan(fg, [small, big, small])
+    assert len(tiles) == 3
+    assert list(tiles["flags"]) == [0, 1, 0]
+    many = [(b"A" * 4, bytes([30] * 4))] * (fg.lib.load().fgb_tile_max_reads() + 1)
+    b, tiles = _plan(fg, [many])
+    assert list(tiles["flags"]) == [1]
+
+
+def test_planner_rejects_bad_layout(fg):
+    lib = fg.lib.load()
+    b = fg.pack_source_reads([[(b"ACGTA", bytes([30] * 5))] * 2], 1)
+    n = C.c_uint64()
+
+    def plan(batch):
+        return lib.fgb_plan_tiles(batch.units.ctypes.data, batch.n_units, batch.reads.ctypes.data,
+                                  batch.n_reads, None, 0, C.byref(n))
+    assert plan(b) == 0
+    bad = fg.pack_source_reads([[(b"ACGTA", bytes([30] * 5))] * 2], 1)
+    bad.reads[1] = ((int(bad.reads[1]) >> 16) + 1) << 16 | 5      # misaligned row
+    assert plan(bad) == fg.lib.FGB_ERR_LAYOUT
+    bad = fg.pack_source_reads([[(b"ACGTA", bytes([30] * 5))] * 2], 1)
+    bad.units["out_off"][1] += 4                                   # output rows not dense
+    assert plan(bad) == fg.lib.FGB_ERR_LAYOUT
+    bad = fg.pack_source_reads([[(b"ACGTA", bytes([30] * 5))] * 2], 1)
+    bad.units["cons_len"][0] = 9                                   # longer than any read
+    bad.units["out_off"][1] = 12
+    assert plan(bad) == fg.lib.FGB_ERR_LAYOUT
+
+
+def test_consensus_length_rule(fg):
+    assert fg.consensus_length([10, 8, 6], 1) == 10
+    assert fg.consensus_length([6, 10, 8], 2) == 8
+    assert fg.consensus_length([6, 10, 8], 3) == 6

@@ -1,0 +1,200 @@
+"""GPU parity: the sm_100a vote (through the C-ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): consensus bases, depths, errors and lengths bit-exact; consensus
+qualities within +-1 phred (the tests additionally report how many differ at all — expected 0)."""
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+QUAL_TOL = 1   # phred units, stated by BASELINE.json
+
+
+@pytest.fixture(scope="module")
+def fg():
+    import __graft_entry__ as graft
+    graft.build()
+    import fgumi_b200
+    return fgumi_b200
+
+
+def check(fg, batch, pre=45, post=40, min_reads=1, min_cons_q=2, device_path=False, threads=4):
+    eng = fg.Engine(0, pre, post, min_reads, min_cons_q)
+    try:
+        if device_path:
+            import torch
+            db = fg.DeviceBatch(batch, "cuda:0")
+            dc = fg.DeviceColumns(batch.n_out, "cuda:0")
+            eng.vote_device(db, dc, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            out = dc.to_host()
+        else:
+            out = eng.vote(batch)
+        stats = eng.stats()
+    finally:
+        eng.close()
+    ob, oq, od, oe, cl = O.simplex_batch(batch, pre, post, min_reads, min_cons_q, threads)
+    assert np.array_equal(cl, batch.units["cons_len"][: batch.n_units])
+    n = batch.n_out
+    # compare only real positions (rows are padded to 4)
+    mask = np.zeros(max(n, 1), bool)
+    for sl in batch.unit_slices():
+        mask[sl] = True
+    mask = mask[:n]
+    gb, gq, gd, ge = out.base[:n][mask], out.qual[:n][mask], out.depth[:n][mask], out.errors[:n][mask]
+    rb, rq, rd, re_ = ob[:n][mask], oq[:n][mask], od[:n][mask], oe[:n][mask]
+    assert np.array_equal(gb, rb), f"{(gb != rb).sum()} consensus bases differ"
+    assert np.array_equal(gd, rd), "depths differ"
+    assert np.array_equal(ge, re_), "errors differ"
+    dq = np.abs(gq.astype(int) - rq.astype(int))
+    assert dq.max(initial=0) <= QUAL_TOL, f"max |dq| = {dq.max()}"
+    assert (dq != 0).sum() == 0, f"{(dq != 0).sum()} qualities differ by 1 (within tolerance, but unexpected)"
+    assert stats["positions"] == int(mask.sum())
+    assert stats["units"] == batch.n_units
+    return stats
+
+
+def test_known_answer_vectors(fg):
+    """The reference's own KATs pushed through the GPU path."""
+    q = lambda v, n: bytes([v] * n)
+    units = [
+        [(b"GATTACA", q(10, 7))] * 2,                                   # vanilla_caller.rs:2083
+        [(b"GATTACA", q(10, 7)), (b"GATTACA", q(10, 7)), (b"GATTTCA", q(10, 7))],  # :2117
+        [(b"A" * 10, q(30, 10))] * 3 + [(b"AAAAACAAAA", q(30, 10))],    # :2396
+        [(b"GATNACAG", q(20, 8)), (b"GATGACAG", q(20, 8)), (b"GATGACAG", q(20, 8)),
+         (b"GATTACAG", q(20, 8))],                                      # :2473
+        [(b"A" * 10, q(30, 10)), (b"A" * 8, q(30, 8)), (b"A" * 6, q(30, 6))],   # :2157
+        [(b"A", q(37, 1))], [(b"AA", q(37, 2))] * 2, [(b"ACG", q(37, 3))] * 3,   # Appendix B
+        [(b"C" * 5, q(20, 5))] * 300,                                   # deep pileup
+        [(b"AC", bytes([20, 20])), (b"CA", bytes([20, 20]))],           # exact tie -> N
+    ]
+    for pre, post, mr, mq in ((45, 40, 1, 0), (93, 93, 1, 0), (50, 50, 1, 2), (45, 40, 2, 40)):
+        usable = [u for u in units if len(u) >= mr]
+        check(fg, fg.pack_source_reads(usable, mr), pre, post, mr, mq)
+
+
+def test_config1_plumbing_depth3(fg):
+    """BASELINE config 1: 1k molecules -> 2k units (R1, R2), depth 3, 150 bp, no errors."""
+    from fgumi_b200 import synth
+    b1, q1 = synth.host_pileup(1000, 3, 150, 0.0, seed=42)
+    b2, q2 = synth.host_pileup(1000, 3, 150, 0.0, seed=43, r2=True)
+    bases = np.stack([b1, b2], 1).reshape(2000, 3, 150)
+    quals = np.stack([q1, q2], 1).reshape(2000, 3, 150)
+    st = check(fg, fg.pack_uniform(bases, quals, 1))
+    assert st["input_reads"] == 6000
+
+
+@pytest.mark.parametrize("depth,err,seed", [(8, 1e-3, 1), (8, 0.05, 2), (4, 1e-2, 3), (2, 1e-2, 4),
+                                           (1, 0.0, 5), (33, 0.02, 6), (100, 1e-3, 7)])
+def test_uniform_depths(fg, depth, err, seed):
+    from fgumi_b200 import synth
+    n = 3000 if depth <= 8 else 300
+    bases, quals = synth.host_pileup(n, depth, 150, err, seed=seed)
+    st = check(fg, fg.pack_uniform(bases, quals, 1), device_path=(seed % 2 == 0))
+    if depth == 8 and err == 1e-3:
+        # the fast path must carry the clean data: < 3 % of positions may need the f64 path
+        assert st["exact_positions"] < 0.03 * st["positions"]
+
+
+def test_heavy_disagreement_and_ns(fg):
+    from fgumi_b200 import synth
+    bases, quals = synth.host_pileup(1500, 6, 150, 0.25, seed=11, n_rate=0.1)
+    check(fg, fg.pack_uniform(bases, quals, 1))
+    check(fg, fg.pack_uniform(bases, quals, 3), min_reads=3, min_cons_q=30)
+
+
+def _ragged_units(rng, n_units, max_depth, lmin, lmax, alphabet=b"ACGTN", qlo=2, qhi=45):
+    units = []
+    for _ in range(n_units):
+        d = int(rng.integers(1, max_depth + 1))
+        tmpl = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=lmax)
+        rows = []
+        for _ in range(d):
+            ln = int(rng.integers(lmin, lmax + 1))
+            b = tmpl[:ln].copy()
+            m = rng.random(ln) < 0.08
+            b[m] = rng.choice(np.frombuffer(alphabet, np.uint8), size=int(m.sum()))
+            qv = rng.integers(qlo, qhi + 1, size=ln).astype(np.uint8)
+            rows.append((b.tobytes(), qv.tobytes()))
+        units.append(rows)
+    return units
+
+
+def test_ragged_lengths_and_depths(fg):
+    rng = np.random.default_rng(5)
+    units = _ragged_units(rng, 800, 12, 1, 170)
+    check(fg, fg.pack_source_reads(units, 1))
+    units2 = [u for u in units if len(u) >= 2]
+    check(fg, fg.pack_source_reads(units2, 2), min_reads=2, min_cons_q=10)
+
+
+def test_odd_alphabet_and_qualities(fg):
+    """lowercase bases, IUPAC codes, quality bytes above 93 and 0xFF."""
+    rng = np.random.default_rng(6)
+    units = _ragged_units(rng, 400, 9, 5, 60, alphabet=b"ACGTNacgtnRYKM.", qlo=0, qhi=255)
+    check(fg, fg.pack_source_reads(units, 1), min_cons_q=0)
+
+
+def test_order_sensitive_ties(fg):
+    """two competing bases carrying the same multiset of qualities — the call depends
+    on the f64 accumulation order, so the GPU must replay the reference's order exactly."""
+    rng = np.random.default_rng(8)
+    units = []
+    for _ in range(3000):
+        k = int(rng.integers(1, 6))
+        qs = rng.integers(5, 45, size=k)
+        obs = [(ord("A"), int(x)) for x in qs] + [(ord("C"), int(x)) for x in rng.permutation(qs)]
+        order = rng.permutation(len(obs))
+        rows = [(bytes([obs[i][0]]) * 3, bytes([obs[i][1]]) * 3) for i in order]
+        units.append(rows)
+    st = check(fg, fg.pack_source_reads(units, 1), min_cons_q=0)
+    assert st["exact_positions"] == st["positions"]
+
+
+def test_zipf_depths(fg):
+    from fgumi_b200 import synth
+    rng = np.random.default_rng(9)
+    depths = synth.zipf_depths(400, 1, 100, 1.0, seed=9)
+    units = []
+    for d in depths:
+        b, q = synth.host_pileup(1, int(d), 150, 5e-3, seed=int(rng.integers(1 << 30)))
+        units.append([(b[0, r].tobytes(), q[0, r].tobytes()) for r in range(int(d))])
+    check(fg, fg.pack_source_reads(units, 1))
+
+
+def test_oversize_units_take_direct_path(fg):
+    """Units too big for a shared-memory stage are voted straight from HBM."""
+    from fgumi_b200 import synth
+    cap = fg.lib.load().fgb_tile_capacity_bytes()
+    d_big = cap // 152 + 40
+    units = []
+    for d, seed in ((3, 1), (d_big, 2), (5, 3), (600, 4), (2, 5)):
+        b, q = synth.host_pileup(1, d, 150, 0.02, seed=seed)
+        units.append([(b[0, r].tobytes(), q[0, r].tobytes()) for r in range(d)])
+    batch = fg.pack_source_reads(units, 1)
+    tiles = fg.plan_tiles(batch)
+    assert (tiles["flags"] == 1).sum() == 2
+    check(fg, batch)
+    check(fg, batch, device_path=True)
+
+
+def test_empty_and_tiny_batches(fg):
+    eng = fg.Engine(0)
+    out = eng.vote(fg.pack_source_reads([], 1))
+    assert eng.stats()["units"] == 0
+    eng.close()
+    check(fg, fg.pack_source_reads([[(b"A", bytes([30]))]], 1))
+    check(fg, fg.pack_source_reads([[(b"ACG", bytes([30] * 3))] * 2], 1))
+
+
+def test_multi_chunk_submit(fg):
+    """A host batch larger than one pipeline chunk (96 MiB per column) is split at tile boundaries."""
+    from fgumi_b200 import synth
+    bases, quals = synth.host_pileup(4000, 8, 150, 2e-3, seed=21)
+    reps = 24   # 4000*24 units * 8 reads * 152 B = 116.7 MB per column
+    bases = np.tile(bases, (reps, 1, 1))
+    quals = np.tile(quals, (reps, 1, 1))
+    st = check(fg, fg.pack_uniform(bases, quals, 1), threads=8)
+    assert st["units"] == 4000 * reps
