@@ -23,6 +23,7 @@ __device__ constexpr double kMaxPhredAsLnError = -93.0 * 2.302585092994046 / 10.
 __device__ __forceinline__ uint32_t ln_prob_to_phred(double ln_prob) {
   if (ln_prob < kMaxPhredAsLnError) return 93u;
   double phred = floor(__dadd_rn(__ddiv_rn(__dmul_rn(-10.0, ln_prob), kLn10), 0.001));
+  if (isnan(phred)) return 0u;   // Rust: NaN.clamp(..) is NaN and `NaN as u8` saturates to 0
   phred = phred < 2.0 ? 2.0 : phred;
   phred = phred > 93.0 ? 93.0 : phred;
   return (uint32_t)phred;

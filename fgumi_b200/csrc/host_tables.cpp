@@ -57,6 +57,7 @@ unsigned host_ln_prob_to_phred(double ln_prob) {  // phred.rs:119-135
   const double max_as_ln = -93.0 * kLn10 / 10.0;
   if (ln_prob < max_as_ln) return 93;
   double p = std::floor(-10.0 * ln_prob / kLn10 + 0.001);
+  if (std::isnan(p)) return 0;
   if (p < 2.0) p = 2.0;
   if (p > 93.0) p = 93.0;
   return static_cast<unsigned>(p);

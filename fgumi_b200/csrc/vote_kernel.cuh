@@ -257,7 +257,7 @@ __device__ __noinline__ Called exact_position(const TileView<M>& tv, const VoteS
   out.errors = (depth - nobs_call) & 0xFFFFu;                 // vanilla_caller.rs:1341
   if (depth < min_reads) { out.base = 'N'; out.qual = 0; }    // :1345-1346
   else if (cqual < min_cons_q) { out.base = 'N'; out.qual = 2; }  // :1347-1348
-  else { out.base = cbase; out.qual = cqual; }
+  else { out.base = cbase; out.qual = cqual & 0xFFu; }
   return out;
 }
 

@@ -32,7 +32,9 @@ uint8_t ln_prob_to_phred(double ln_prob) {
   const double MAX_PHRED_AS_LN_ERROR = -static_cast<double>(MAX_PHRED) * LN_10 / 10.0;  // :34
   if (ln_prob < MAX_PHRED_AS_LN_ERROR) return MAX_PHRED;
   double phred = std::floor(-10.0 * ln_prob / LN_10 + PHRED_PRECISION);
-  // f64::clamp then `as u8` (NaN would saturate to 0 in Rust; unreachable on this path)
+  // f64::clamp keeps NaN, and Rust's saturating `NaN as u8` is 0 (reachable: a Q0 observation
+  // makes correct[0] = -inf and the Kahan compensation NaN)
+  if (std::isnan(phred)) return 0;
   if (phred < static_cast<double>(MIN_PHRED)) phred = MIN_PHRED;
   if (phred > static_cast<double>(MAX_PHRED)) phred = MAX_PHRED;
   return static_cast<uint8_t>(phred);
