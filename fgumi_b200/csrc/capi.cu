@@ -174,6 +174,9 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   dt.ln_pre = h->host_tables.ln_pre;
   std::memcpy(dt.single_q, h->host_tables.single_q, sizeof(dt.single_q));
   std::memcpy(dt.qt, h->host_tables.qt, sizeof(dt.qt));
+  std::memcpy(dt.dfix, h->host_tables.dfix, sizeof(dt.dfix));
+  dt.g2fix = h->host_tables.g2fix;
+  dt.nmax2 = h->host_tables.nmax2;
   if ((e = cudaMemcpy(h->d_tables, &dt, sizeof(dt), cudaMemcpyHostToDevice)) != cudaSuccess)
     return fail(e, "cudaMemcpy tables");
   if ((e = cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * FGB_NCOUNTERS)) != cudaSuccess)
@@ -228,6 +231,17 @@ fgb_status fgb_host_tables(uint8_t pre, uint8_t post, double* correct, double* e
   return FGB_OK;
 }
 
+fgb_status fgb_host_proof_tables(uint8_t pre, uint8_t post, int32_t* dfix, int32_t* g2fix,
+                                 uint32_t* nmax2) {
+  if (pre > FGB_MAX_PHRED || post > FGB_MAX_PHRED) return FGB_ERR_INVALID_ARG;
+  HostTables t;
+  build_host_tables(pre, post, &t);
+  if (dfix) std::memcpy(dfix, t.dfix, sizeof(t.dfix));
+  if (g2fix) *g2fix = t.g2fix;
+  if (nmax2) *nmax2 = t.nmax2;
+  return FGB_OK;
+}
+
 // ---- planner ------------------------------------------------------------------------------------
 uint32_t fgb_tile_capacity_bytes(void) { return kTileCapBytes; }
 uint32_t fgb_tile_max_units(void) { return kTileMaxUnits; }
@@ -243,9 +257,12 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
   uint64_t cur_end = 0;   // exclusive end (unaligned) of the open tile's byte range
   uint64_t prev_read_end = 0;
 
+  uint32_t cur_items = 0;     // uchar4 items per unit if uniform so far, 0xFFFFFFFF = mixed
   auto emit = [&]() {
     cur.byte_len = static_cast<uint32_t>(((cur_end + 15u) & ~15ull) - cur.byte_begin);
     if (cur.flags & kTileFlagDirect) { cur.byte_len = 0; }
+    if (cur_items != 0xFFFFFFFFu && cur_items >= 2 && cur_items <= 4096)   // umulhi exactness
+      cur.flags |= cur_items << 8;    // hint: unit index = item / cur_items
     if (out && nt < cap) out[nt] = cur;
     ++nt;
     open = false;
@@ -268,7 +285,7 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
     for (uint32_t r = un.read_begin; r < nx.read_begin; ++r) {
       uint64_t off = FGB_READ_OFF(reads[r]);
       uint32_t len = FGB_READ_LEN(reads[r]);
-      if (off % FGB_READ_ALIGN) return FGB_ERR_LAYOUT;
+      if (off % FGB_READ_ALIGN || len == 0) return FGB_ERR_LAYOUT;   // no empty rows
       if (off < prev_read_end) return FGB_ERR_LAYOUT;   // rows ascend and do not overlap
       prev_read_end = off + len;
       if (r == un.read_begin) ub = off;
@@ -297,6 +314,11 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
       uint64_t span = ((ue + 15u) & ~15ull) - cur.byte_begin;
       if (span > kTileCapBytes || nr + (cur.read_begin & 1u) > kTileMaxReads)
         cur.flags |= kTileFlagDirect;   // oversize unit: kernel votes it straight from HBM
+    }
+    {
+      uint32_t items = (un.cons_len + 3u) >> 2;
+      if (cur.n_units == 0) cur_items = items;
+      else if (cur_items != items) cur_items = 0xFFFFFFFFu;
     }
     cur.n_units += 1;
     cur.n_reads += nr;

@@ -8,6 +8,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstdint>
 #include <limits>
 
 namespace fgb {
@@ -81,11 +82,45 @@ void build_host_tables(unsigned pre, unsigned post, HostTables* t) {
   }
   t->single_q[94] = t->single_q[95] = 0;
 
-  // Fast-path proof table.  For a pileup of n identical A/C/G/T observations with qualities
-  // q_i >= qT, winner_ll - loser_ll = sum_i (correct[q_i] - err_alt[q_i]) >= n * dmono[qT], where
-  // dmono[q] = min_{q' >= q} (correct[q'] - err_alt[q']).  qt[n] is the smallest qT with
-  // n * dmono[qT] > 23 + margin, so the reference's `> 23.0` test (base_builder.rs:364-375) is
-  // guaranteed to pass; the margin (1e-6) dwarfs the <=1e-12 rounding of two Kahan sums.
+  // ---- Proof tables (DESIGN.md "exactness") ------------------------------------------------------
+  // Let D[q] = correct[q] - err_alt[q] and, for one position, S_b = sum of D[q_i] over the
+  // observations of base b (S_b = 0 for an unobserved base).  In exact arithmetic
+  // ll[w] - ll[b] = S_w - S_b, so g = S_w - max_{b != w} S_b is the winner's likelihood gap.
+  //
+  // (1) Reference fast path (base_builder.rs:338-379): one observed base and gap > 23.0
+  //     => (w, phred(ln_pre)).
+  // (2) "Dominant winner": if g >= G2 the full path (base_builder.rs:401-457) ALSO returns
+  //     (w, phred(ln_pre)):  ln_sum = ll[w] + delta with 0 <= delta <= 3e^-g plus <= 64 ulp(|ll|)
+  //     of rounding, so |posterior| <= 3e^-g + 64*2^-53*n*Vmax, ln_not(posterior) <= ln of that
+  //     (or -inf), and ln_error_prob_two_trials(ln_pre, err) returns ln_pre unchanged as soon as
+  //     ln_pre - err >= 6 (phred.rs:238).  G2 and nmax2 make both terms <= 0.5*e^(ln_pre-6.01).
+  //     No tie is possible (gaps >> f64::EPSILON) and every table value involved is finite
+  //     (quality 0, whose correct[] is -inf, is excluded through the dfix sentinel).
+  // Everything here is conservative: a position that fails a proof is evaluated by the literal
+  // f64 algorithm, so the proofs can only ever save work, never change a result.
+  const double u = 1.1102230246251565e-16;   // 2^-53
+  double vmax = 0.0;
+  bool finite_ok = true;
+  for (unsigned q = 1; q < 94; ++q) {
+    if (!std::isfinite(t->correct[q]) || !std::isfinite(t->err_alt[q])) finite_ok = false;
+    vmax = std::fmax(vmax, std::fmax(std::fabs(t->correct[q]), std::fabs(t->err_alt[q])));
+  }
+  const double lim = t->ln_pre - 6.01;
+  t->g2 = -lim + std::log(6.0) + 1e-6;
+  double nmax = 0.5 * std::exp(lim) / (64.0 * u * (vmax > 1.0 ? vmax : 1.0));
+  if (!finite_ok || !(nmax >= 1.0)) nmax = 0.0;
+  if (nmax > 1024.0) nmax = 1024.0;          // keeps the int32 fixed-point sums exact
+  t->nmax2 = static_cast<uint32_t>(nmax);
+  t->g2fix = static_cast<int32_t>(std::ceil(t->g2 * 65536.0));
+  for (unsigned q = 0; q < 96; ++q) t->dfix[q] = INT32_MIN;
+  for (unsigned q = 1; q < 94; ++q) {
+    double d = t->correct[q] - t->err_alt[q];
+    if (std::isfinite(d) && std::fabs(d) < 30000.0) t->dfix[q] = static_cast<int32_t>(std::llrint(d * 65536.0));
+  }
+
+  // SWAR fast-pass threshold: n identical A/C/G/T observations with qualities q_i >= qT have
+  // gap = sum D[q_i] >= n * dmono[qT], dmono[q] = min_{q' >= q} D[q'].  qt[n] is the smallest qT
+  // whose bound clears min(23, G2) (+1e-6, which dwarfs the <= 1e-9 rounding of the Kahan sums).
   double dmono[94];
   double run = std::numeric_limits<double>::infinity();
   for (int q = 93; q >= 0; --q) {
@@ -94,9 +129,12 @@ void build_host_tables(unsigned pre, unsigned post, HostTables* t) {
     dmono[q] = run;
   }
   for (unsigned n = 0; n < 256; ++n) {
+    double thr = 23.0 + 1e-6;
+    // qt[255] also serves every n > 255, so it keeps the reference's own 23.0 threshold
+    if (n < 255 && n <= t->nmax2 && t->g2 < thr) thr = t->g2;
     unsigned qt = 255;
-    for (unsigned q = 0; q < 94; ++q) {
-      if (static_cast<double>(n) * dmono[q] > 23.0 + 1e-6) { qt = q; break; }
+    for (unsigned q = 1; q < 94; ++q) {
+      if (static_cast<double>(n) * dmono[q] > thr) { qt = q; break; }
     }
     t->qt[n] = static_cast<uint8_t>(qt);
   }

@@ -11,6 +11,11 @@ struct HostTables {
   uint8_t single_q[96];
   uint8_t qt[256];
   unsigned fast_qual;
+  // "dominant winner" proof (host_tables.cpp): fixed-point likelihood gaps
+  int32_t dfix[96];      // round((correct[q] - err_alt[q]) * 65536); INT32_MIN = unusable quality
+  int32_t g2fix;         // ceil(G2 * 65536)
+  uint32_t nmax2;        // proof valid for pileups of at most this many observations (0 = off)
+  double g2;             // G2 in nats
 };
 
 void build_host_tables(unsigned pre, unsigned post, HostTables* t);

@@ -9,18 +9,21 @@
 //
 // Shape of the kernel:
 //   * persistent CTAs (2 per SM), each walks tiles  t = blockIdx.x, +gridDim.x, ...
-//   * one elected thread stages a tile (base bytes, qual bytes, read descriptors, unit
-//     descriptors) into shared memory with four TMA bulk copies (cp.async.bulk ... mbarrier
-//     complete_tx), double buffered so the next tile streams from HBM while this one is voted;
+//   * warp-specialised: one PRODUCER warp stages tiles (base bytes, qual bytes, read descriptors,
+//     unit descriptors) into shared memory with four TMA bulk copies (cp.async.bulk ... mbarrier
+//     complete_tx) as soon as a stage's "empty" mbarrier says all eight CONSUMER warps are done
+//     with it; consumers never meet at a CTA barrier, so a warp that finishes its share of a tile
+//     moves straight on to the next one while HBM streams into the other stage;
 //   * FAST PASS: one thread per 4 consecutive positions (uchar4 words).  Over the depth axis it
 //     keeps a SWAR "all reads equal the first read" mask and a SWAR "every quality >= qT(n)" mask;
 //     a position that is unanimous over A/C/G/T, covered by every read and passes the quality
 //     mask is PROVEN to take the reference's unanimous fast path (sum of per-read likelihood gaps
 //     >= n*Dmono[qT] > 23), whose result is the constant (base, phred(ln_pre)) — no f64 needed;
-//   * everything else (disagreements, Ns, ragged ends, shallow / low-quality pileups) is queued in
-//     shared memory and resolved in the EXACT PASS by the literal algorithm: sequential, in-order,
-//     4-lane f64 Kahan accumulation from the host-built tables, then the f64 call() tail.  Lanes
-//     are packed (one queued position per thread) so the f64 work never runs divergent;
+//   * everything else (disagreements, Ns, ragged ends, shallow / low-quality pileups) goes to a
+//     warp-private queue in shared memory and is resolved, packed one position per lane, first by
+//     the integer "dominant winner" proof (host_tables.cpp) and only then by the literal algorithm:
+//     sequential, in-order, 4-lane f64 Kahan accumulation from the host-built tables and the f64
+//     call() tail;
 //   * results leave as coalesced uchar4 / ushort4 stores.
 #pragma once
 #include <cuda_runtime.h>
@@ -38,6 +41,9 @@ struct DeviceTables {
   double ln_pre;                // ln_error_pre_umi, base_builder.rs:277
   uint8_t single_q[96];         // single_input_consensus_quals, vanilla_caller.rs:463-482
   uint8_t qt[kQtEntries];       // fast-path quality threshold by depth; 255 = never
+  int32_t dfix[96];             // fixed-point likelihood gaps (host_tables.cpp), INT32_MIN = unusable
+  int32_t g2fix;                // dominant-winner threshold, fixed point
+  uint32_t nmax2;               // dominant-winner proof valid up to this many observations
 };
 
 struct VoteArgs {
@@ -72,10 +78,14 @@ struct __align__(128) VoteSmem {
   double err_alt[FGB_NTABLE];
   double ln_pre;
   uint64_t full[kStages];
-  uint32_t queue[kSlowQueueCap];
-  uint32_t q_count[2];
+  uint64_t empty[kStages];
+  uint32_t queue[kConsumerWarps][kWarpQueueCap];
+  uint32_t q_count[kConsumerWarps];
   uint8_t single_q[96];
   uint8_t qt[kQtEntries];
+  int32_t dfix[96];
+  int32_t g2fix;
+  uint32_t nmax2;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -92,6 +102,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
@@ -120,37 +133,34 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 
 // ---- memory-space policy: tiles live in shared memory, oversize units are read from HBM -------
 struct ShMem {
-  using addr_t = uint32_t;
+  // Plain pointers derived from the extern __shared__ block: nvcc's address-space inference turns
+  // these into LDS and is free to batch the independent loads of an unrolled depth loop.
+  using addr_t = const uint8_t*;
   using off_t = uint32_t;
-  static __device__ __forceinline__ addr_t make(const void* p) { return smem_u32(p); }
-  static __device__ __forceinline__ uint32_t ld8(addr_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-  }
+  static __device__ __forceinline__ uint32_t ld8(addr_t a) { return *a; }
   static __device__ __forceinline__ uint32_t ld32(addr_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
+    return *reinterpret_cast<const uint32_t*>(a);
   }
   static __device__ __forceinline__ uint64_t ld64(addr_t a) {
-    uint64_t v;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
-    return v;
+    return *reinterpret_cast<const uint64_t*>(a);
+  }
+  // tile-relative byte offset of a read row: 32-bit arithmetic is enough inside a stage
+  static __device__ __forceinline__ off_t row_offset(uint64_t d, uint64_t, uint32_t base32) {
+    return static_cast<uint32_t>(d >> 16) - base32;
   }
 };
 struct GlMem {
   using addr_t = const uint8_t*;
   using off_t = uint64_t;
-  static __device__ __forceinline__ addr_t make(const void* p) {
-    return static_cast<const uint8_t*>(p);
-  }
   static __device__ __forceinline__ uint32_t ld8(addr_t a) { return __ldg(a); }
   static __device__ __forceinline__ uint32_t ld32(addr_t a) {
     return __ldg(reinterpret_cast<const uint32_t*>(a));
   }
   static __device__ __forceinline__ uint64_t ld64(addr_t a) {
     return __ldg(reinterpret_cast<const unsigned long long*>(a));
+  }
+  static __device__ __forceinline__ off_t row_offset(uint64_t d, uint64_t byte_base, uint32_t) {
+    return (d >> 16) - byte_base;
   }
 };
 
@@ -265,7 +275,6 @@ struct LocalStats {
   uint32_t positions, exact, nocall;
 };
 
-template <class M>
 __device__ __forceinline__ void write_called(const VoteArgs& a, uint64_t o, const Called& c) {
   a.out_base[o] = static_cast<uint8_t>(c.base);
   a.out_qual[o] = static_cast<uint8_t>(c.qual);
@@ -273,47 +282,152 @@ __device__ __forceinline__ void write_called(const VoteArgs& a, uint64_t o, cons
   a.out_errors[o] = static_cast<uint16_t>(c.errors);
 }
 
-// Votes one tile.  All threads of the CTA call this.
+// "Dominant winner" evaluation of one position in integers (proof: host_tables.cpp).  Returns true
+// and fills `out` when the reference's result is PROVEN to be (winner, phred(ln_pre)) after the
+// thresholds of vanilla_caller.rs:1345-1349; returns false when the literal f64 path must decide.
+template <class M>
+__device__ __forceinline__ bool dominant_position(const TileView<M>& tv, const VoteSmem& S,
+                                                  uint32_t read_begin, uint32_t n_reads,
+                                                  uint32_t pos, uint32_t min_reads,
+                                                  uint32_t min_cons_q, uint32_t fast_qual,
+                                                  Called& out) {
+  if (n_reads > S.nmax2) return false;
+  int32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  bool usable = true;
+  for (uint32_t r = 0; r < n_reads; ++r) {
+    uint64_t d = M::ld64(tv.reads + static_cast<typename M::off_t>(read_begin - tv.read_base + r) * 8u);
+    uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
+    if (pos < len) {
+      typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + pos;
+      uint32_t b = M::ld8(tv.bases + row);
+      uint32_t idx = base_to_index(b);
+      if (b != 'N' && idx < 4u) {
+        uint32_t q = M::ld8(tv.quals + row);
+        q = q > FGB_MAX_PHRED ? FGB_MAX_PHRED : q;
+        int32_t dq = S.dfix[q];
+        usable &= (dq != INT32_MIN);
+        s0 += idx == 0 ? dq : 0; c0 += idx == 0;
+        s1 += idx == 1 ? dq : 0; c1 += idx == 1;
+        s2 += idx == 2 ? dq : 0; c2 += idx == 2;
+        s3 += idx == 3 ? dq : 0; c3 += idx == 3;
+      }
+    }
+  }
+  const uint32_t depth = c0 + c1 + c2 + c3;
+  if (depth == 0) {   // base_builder.rs:392-394 then vanilla_caller.rs:1345 (min_reads >= 1)
+    out.base = 'N'; out.qual = 0; out.depth = 0; out.errors = 0;
+    return true;
+  }
+  if (!usable) return false;
+  // winner over all four lanes (an unobserved base has S = 0) and the runner-up
+  int32_t best = s0, second = INT32_MIN;
+  uint32_t w = 0, cw = c0;
+  auto consider = [&](int32_t sv, uint32_t idx, uint32_t cv) {
+    if (sv > best) { second = best; best = sv; w = idx; cw = cv; }
+    else if (sv > second) { second = sv; }
+  };
+  consider(s1, 1u, c1);
+  consider(s2, 2u, c2);
+  consider(s3, 3u, c3);
+  // every fixed-point term is within half a unit of D[q]*65536; two sums of <= depth terms
+  if (static_cast<int64_t>(best) - second < static_cast<int64_t>(S.g2fix) + 2 * static_cast<int64_t>(depth) + 1)
+    return false;
+  out.depth = depth;
+  out.errors = depth - cw;
+  if (depth < min_reads) { out.base = 'N'; out.qual = 0; }
+  else if (fast_qual < min_cons_q) { out.base = 'N'; out.qual = 2; }
+  else { out.base = (0x54474341u >> (8u * w)) & 0xFFu; out.qual = fast_qual; }
+  return true;
+}
+
+// high bit of each byte set where the byte of x is zero
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {
+  return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+// 0x80 in the low `k` bytes (k = 0..4)
+__device__ __forceinline__ uint32_t low_bytes_mask(uint32_t k) {
+  return k >= 4u ? 0x80808080u : (0x80808080u & ((1u << (8u * k)) - 1u));
+}
+// high bit of each byte set where the byte is one of 'A','C','G','T' (0x41,0x43,0x47,0x54)
+__device__ __forceinline__ uint32_t acgt_bytes(uint32_t x) {
+  uint32_t y = x ^ 0x41414141u;                       // A,C,G,T -> 0x00,0x02,0x06,0x15
+  uint32_t in0246 = zero_bytes(y & 0xF9F9F9F9u);      // {0,2,4,6}
+  uint32_t is4 = zero_bytes(y ^ 0x04040404u);         // 'E'
+  uint32_t isT = zero_bytes(y ^ 0x15151515u);
+  return (in0246 & ~is4) | isT;
+}
+
+// Resolve one undecided position: integer proof first, the literal f64 algorithm otherwise.
+template <class M>
+__device__ __forceinline__ Called resolve_position(const TileView<M>& tv, const VoteSmem& S,
+                                                   uint32_t rb, uint32_t n, uint32_t pos,
+                                                   const VoteArgs& a, LocalStats& ls) {
+  Called c;
+  if (!dominant_position<M>(tv, S, rb, n, pos, a.min_reads, a.min_cons_q, a.fast_qual, c)) {
+    c = exact_position<M>(tv, S, rb, n, pos, a.min_reads, a.min_cons_q, a.fast_qual);
+    ls.exact++;
+  }
+  ls.nocall += (c.base == 'N');
+  return c;
+}
+
+// Votes this warp's share of one tile.  Called by the eight consumer warps; `vt` is the thread's
+// rotating slot (0..kVoteThreads-1): it owns items vt, vt+256, ...
 template <class M>
 __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const Stage& st,
-                                          const TileView<M>& tv, uint32_t* q_count,
+                                          const TileView<M>& tv, uint32_t vt, uint32_t warp,
                                           LocalStats& ls) {
-  const uint32_t tid = threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_units = st.tile.n_units;
   const uint64_t out0 = st.units[0].out_off;
   const uint32_t n_items = static_cast<uint32_t>((st.units[n_units].out_off - out0) >> 2);
   const uint32_t min_reads = a.min_reads, min_cons_q = a.min_cons_q, fast_qual = a.fast_qual;
-  // constant result of a proven-unanimous position after the thresholds of vanilla_caller.rs:1345-1349
+  // constant result of a proven position after the thresholds of vanilla_caller.rs:1345-1349
   const bool fast_masked = fast_qual < min_cons_q;
   const uint32_t fq = fast_masked ? 2u : fast_qual;
+  // planner hint: every unit of the tile has the same number of uchar4 items
+  const uint32_t uni_m = st.tile.flags >> 8;
+  const uint32_t uni_recip = uni_m ? (0xFFFFFFFFu / uni_m + 1u) : 0u;
+  const uint32_t base32 = static_cast<uint32_t>(tv.byte_base);
+  uint32_t* const wqueue = S.queue[warp];
+  uint32_t* const wcount = &S.q_count[warp];
 
   // ---------------- FAST PASS: one thread per uchar4 of output ----------------
-  for (uint32_t item = tid; item < n_items; item += kThreads) {
-    // unit lookup: largest u with start(u) <= item
-    uint32_t lo = 0, hi = n_units;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      uint32_t start = static_cast<uint32_t>((st.units[mid].out_off - out0) >> 2);
-      if (start <= item) lo = mid; else hi = mid;
+  for (uint32_t item = vt; item < n_items; item += kVoteThreads) {
+    uint32_t u;
+    if (uni_m) {
+      u = __umulhi(item, uni_recip);            // exact floor(item / uni_m): 2 <= uni_m <= 4096, item*uni_m < 2^32
+    } else {                                    // largest u with start(u) <= item
+      uint32_t lo = 0, hi = n_units;
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        uint32_t start = static_cast<uint32_t>((st.units[mid].out_off - out0) >> 2);
+        if (start <= item) lo = mid; else hi = mid;
+      }
+      u = lo;
     }
-    const uint32_t u = lo;
     const fgb_unit un = st.units[u];
     const uint32_t rb = un.read_begin;
     const uint32_t n = st.units[u + 1].read_begin - rb;
     const uint32_t cons_len = un.cons_len;
     const uint32_t p0 = (item - static_cast<uint32_t>((un.out_off - out0) >> 2)) << 2;
     const uint64_t o = out0 + (static_cast<uint64_t>(item) << 2);
+    const uint32_t real = cons_len - p0 < 4u ? cons_len - p0 : 4u;   // positions of this item (>= 1)
+    const uint32_t realmask = low_bytes_mask(real);
 
     uint32_t wbase = 0, wqual = 0;           // 4 output bases / quals
-    uint32_t dep[4] = {0, 0, 0, 0}, err[4] = {0, 0, 0, 0};
+    uint32_t d01 = 0, d23 = 0, e01 = 0, e23 = 0;   // 4 x u16 depths / errors
+    ls.positions += real;
 
     if (n == 1) {
       // single-read consensus, vanilla_caller.rs:1285-1316
-      uint64_t d = M::ld64(tv.reads + (rb - tv.read_base) * 8u);
+      uint64_t d = M::ld64(tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u);
       uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
       typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + p0;
       uint32_t wb = 0, wq = 0;
       if (p0 < len) { wb = M::ld32(tv.bases + row); wq = M::ld32(tv.quals + row); }
+      uint32_t dep[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t pos = p0 + j;
@@ -328,87 +442,99 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
           wbase |= ob << (8 * j);
           wqual |= oq << (8 * j);
           dep[j] = od;
-          ls.positions++;
           ls.nocall += (ob == 'N');
         }
       }
+      d01 = dep[0] | (dep[1] << 16);
+      d23 = dep[2] | (dep[3] << 16);
     } else {
       const uint32_t qt = S.qt[n < kQtEntries ? n : kQtEntries - 1];
       const bool fast_ok = (qt <= FGB_MAX_PHRED) && (n >= min_reads) && (n <= 0xFFFFu);
-      uint32_t b0 = 0, diff = 0, okq = 0x80808080u, minlen = 0xFFFFFFFFu;
+      uint32_t fm = 0, b0 = 0;
       if (fast_ok) {
         const uint32_t tsplat = qt * 0x01010101u;
-        typename M::addr_t rd = tv.reads + (rb - tv.read_base) * 8u;
+        typename M::addr_t rd = tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u;
+        uint32_t diff = 0, okq = 0x80808080u, minlen = 0xFFFFFFFFu;
+        {   // reference word: read 0 (if it does not reach p0, minlen vetoes the item anyway)
+          uint64_t d = M::ld64(rd);
+          uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
+          b0 = M::ld32(tv.bases + M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u));
+        }
+#pragma unroll 4
         for (uint32_t r = 0; r < n; ++r) {
           uint64_t d = M::ld64(rd + r * 8u);
-          uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
+          uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
           minlen = len < minlen ? len : minlen;
-          if (len > p0) {
-            typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + p0;
-            uint32_t wb = M::ld32(tv.bases + row);
-            uint32_t wq = M::ld32(tv.quals + row);
-            if (r == 0) b0 = wb;
-            diff |= wb ^ b0;
-            okq &= (wq | 0x80808080u) - tsplat;   // byte high bit survives iff q >= qT (no borrows)
-          }
+          // an uncovered read points at its own first word: harmless, minlen already vetoes
+          typename M::off_t row = M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u);
+          uint32_t wb = M::ld32(tv.bases + row);
+          uint32_t wq = M::ld32(tv.quals + row);
+          diff |= wb ^ b0;
+          okq &= (wq | 0x80808080u) - tsplat;   // byte high bit survives iff q >= qT (no borrows)
         }
+        // per-byte verdict: unanimous & quality-proven & A/C/G/T & covered by every read
+        const uint32_t covered = minlen > p0 ? minlen - p0 : 0u;
+        fm = zero_bytes(diff) & okq & acgt_bytes(b0) & low_bytes_mask(covered) & realmask;
       }
+      // proven positions: constant quality, depth n, no errors
+      const uint32_t fbytes = (fm >> 7) * 0xFFu;
+      wbase = (fast_masked ? 0x4E4E4E4Eu : b0) & fbytes;
+      wqual = (fq * 0x01010101u) & fbytes;
+      d01 = ((fm & 0x80u) ? n : 0u) | ((fm & 0x8000u) ? (n << 16) : 0u);
+      d23 = ((fm & 0x800000u) ? n : 0u) | ((fm & 0x80000000u) ? (n << 16) : 0u);
+      ls.nocall += fast_masked ? __popc(fm) : 0;
+      uint32_t todo = realmask & ~fm;
+      if (todo) {
+        // undecided positions go to this warp's queue (or are resolved in place if it is full)
+        const uint32_t cnt = __popc(todo);
+        uint32_t slot = atomicAdd(wcount, cnt);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t pos = p0 + j;
-        if (pos < cons_len) {
-          uint32_t b = (b0 >> (8 * j)) & 0xFFu;
-          bool fast = fast_ok && pos < minlen && ((diff >> (8 * j)) & 0xFFu) == 0 &&
-                      ((okq >> (8 * j + 7)) & 1u) && is_acgt_upper(b);
-          ls.positions++;
-          if (fast) {
-            wbase |= (fast_masked ? static_cast<uint32_t>('N') : b) << (8 * j);
-            wqual |= fq << (8 * j);
-            dep[j] = n;
-            ls.nocall += fast_masked;
-          } else {
-            uint32_t slot = atomicAdd(q_count, 1u);
-            if (slot < kSlowQueueCap) {
-              S.queue[slot] = (u << 16) | pos;
-            } else {  // queue full: resolve in place (correct, just divergent)
-              Called c = exact_position<M>(tv, S, rb, n, pos, min_reads, min_cons_q, fast_qual);
-              wbase |= c.base << (8 * j);
-              wqual |= c.qual << (8 * j);
-              dep[j] = c.depth;
-              err[j] = c.errors;
-              ls.exact++;
-              ls.nocall += (c.base == 'N');
+        for (int j = 0; j < 4; ++j) {
+          if (todo & (0x80u << (8 * j))) {
+            uint32_t pos = p0 + j;
+            if (slot < kWarpQueueCap) {
+              wqueue[slot] = (u << 16) | pos;
+            } else {
+              Called c = resolve_position<M>(tv, S, rb, n, pos, a, ls);
+              wbase |= (c.base & 0xFFu) << (8 * j);
+              wqual |= (c.qual & 0xFFu) << (8 * j);
+              uint32_t dv = (c.depth & 0xFFFFu) << (16 * (j & 1)), ev = (c.errors & 0xFFFFu) << (16 * (j & 1));
+              if (j < 2) { d01 |= dv; e01 |= ev; } else { d23 |= dv; e23 |= ev; }
             }
+            ++slot;
           }
         }
       }
     }
     *reinterpret_cast<uint32_t*>(a.out_base + o) = wbase;
     *reinterpret_cast<uint32_t*>(a.out_qual + o) = wqual;
-    *reinterpret_cast<uint2*>(a.out_depth + o) = make_uint2(dep[0] | (dep[1] << 16), dep[2] | (dep[3] << 16));
-    *reinterpret_cast<uint2*>(a.out_errors + o) = make_uint2(err[0] | (err[1] << 16), err[2] | (err[3] << 16));
+    *reinterpret_cast<uint2*>(a.out_depth + o) = make_uint2(d01, d23);
+    *reinterpret_cast<uint2*>(a.out_errors + o) = make_uint2(e01, e23);
   }
-  __syncthreads();
+  __syncwarp();
 
-  // ---------------- EXACT PASS: one queued position per thread ----------------
-  uint32_t qn = *q_count;
-  qn = qn < kSlowQueueCap ? qn : kSlowQueueCap;
-  for (uint32_t e = tid; e < qn; e += kThreads) {
-    uint32_t ent = S.queue[e];
+  // ---------------- SLOW PASS: this warp's undecided positions, one per lane ----------------
+  // (a queued position's word was stored above by a lane of this same warp: program order within
+  //  the warp + __syncwarp() orders the byte stores below after it)
+  uint32_t qn = *wcount;
+  qn = qn < kWarpQueueCap ? qn : kWarpQueueCap;
+  for (uint32_t e = lane; e < qn; e += 32) {
+    uint32_t ent = wqueue[e];
     uint32_t u = ent >> 16, pos = ent & 0xFFFFu;
     const fgb_unit un = st.units[u];
     uint32_t n = st.units[u + 1].read_begin - un.read_begin;
-    Called c = exact_position<M>(tv, S, un.read_begin, n, pos, min_reads, min_cons_q, fast_qual);
-    write_called<M>(a, un.out_off + pos, c);
-    ls.exact++;
-    ls.nocall += (c.base == 'N');
+    Called c = resolve_position<M>(tv, S, un.read_begin, n, pos, a, ls);
+    write_called(a, un.out_off + pos, c);
   }
+  __syncwarp();
+  if (lane == 0) *wcount = 0;
 }
 
 __global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   VoteSmem& S = *reinterpret_cast<VoteSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x;
+  const uint32_t warp = tid >> 5;
 
   for (uint32_t i = tid; i < FGB_NTABLE; i += kThreads) {
     S.correct[i] = a.tables->correct[i];
@@ -416,76 +542,87 @@ __global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
   }
   for (uint32_t i = tid; i < 96; i += kThreads) S.single_q[i] = a.tables->single_q[i];
   for (uint32_t i = tid; i < kQtEntries; i += kThreads) S.qt[i] = a.tables->qt[i];
+  for (uint32_t i = tid; i < 96; i += kThreads) S.dfix[i] = a.tables->dfix[i];
+  if (tid < kConsumerWarps) S.q_count[tid] = 0;
   if (tid == 0) {
     S.ln_pre = a.tables->ln_pre;
-    for (int s = 0; s < kStages; ++s) mbar_init(&S.full[s], 1);
-    S.q_count[0] = 0;
-    S.q_count[1] = 0;
+    S.g2fix = a.tables->g2fix;
+    S.nmax2 = a.tables->nmax2;
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&S.full[s], 1);                 // producer's arrive.expect_tx
+      mbar_init(&S.empty[s], kConsumerWarps);   // one arrival per consumer warp
+    }
     fence_mbar_init();
   }
   __syncthreads();
 
-  auto issue = [&](uint64_t t, int s) {   // elected thread only
-    Stage& st = S.st[s];
-    const uint4* gt = reinterpret_cast<const uint4*>(a.tiles + t);
-    uint4 t0 = __ldg(gt), t1 = __ldg(gt + 1);
-    *reinterpret_cast<uint4*>(&st.tile) = t0;
-    *(reinterpret_cast<uint4*>(&st.tile) + 1) = t1;
-    uint64_t byte_begin = (static_cast<uint64_t>(t0.y) << 32) | t0.x;
-    uint32_t byte_len = t0.z, unit_begin = t0.w, n_units = t1.x, read_begin = t1.y,
-             n_reads = t1.z, flags = t1.w;
-    uint32_t units_bytes = (n_units + 1u) * 16u;
-    bool direct = (flags & kTileFlagDirect) != 0;
-    uint32_t rskew = read_begin & 1u;
-    uint32_t rbytes = ((n_reads + rskew + 1u) & ~1u) * 8u;
-    uint32_t tx = units_bytes + (direct ? 0u : 2u * byte_len + rbytes);
-    mbar_arrive_expect_tx(&S.full[s], tx);
-    tma_load_1d(st.units, a.units + unit_begin, units_bytes, &S.full[s]);
-    if (!direct) {
-      if (byte_len) {
-        tma_load_1d(st.bases, a.bases + byte_begin, byte_len, &S.full[s]);
-        tma_load_1d(st.quals, a.quals + byte_begin, byte_len, &S.full[s]);
-      }
-      if (rbytes) tma_load_1d(st.reads, a.reads + (read_begin - rskew), rbytes, &S.full[s]);
-    }
-  };
-
   const uint64_t grid = gridDim.x;
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      uint64_t t = blockIdx.x + static_cast<uint64_t>(s) * grid;
-      if (t < a.n_tiles) issue(t, s);
+
+  if (warp == kConsumerWarps) {
+    // ================= PRODUCER WARP: one elected lane drives the TMA pipeline =================
+    if ((tid & 31u) == 0) {
+      uint32_t k = 0;
+      for (uint64_t t = blockIdx.x; t < a.n_tiles; t += grid, ++k) {
+        const int s = k % kStages;
+        const uint32_t use = k / kStages;
+        if (use > 0) mbar_wait(&S.empty[s], (use - 1u) & 1u);   // consumers released the stage
+        Stage& st = S.st[s];
+        const uint4* gt = reinterpret_cast<const uint4*>(a.tiles + t);
+        uint4 t0 = __ldg(gt), t1 = __ldg(gt + 1);
+        *reinterpret_cast<uint4*>(&st.tile) = t0;
+        *(reinterpret_cast<uint4*>(&st.tile) + 1) = t1;
+        uint64_t byte_begin = (static_cast<uint64_t>(t0.y) << 32) | t0.x;
+        uint32_t byte_len = t0.z, unit_begin = t0.w, n_units = t1.x, read_begin = t1.y,
+                 n_reads = t1.z, flags = t1.w;
+        uint32_t units_bytes = (n_units + 1u) * 16u;
+        bool direct = (flags & kTileFlagDirect) != 0;
+        uint32_t rskew = read_begin & 1u;
+        uint32_t rbytes = ((n_reads + rskew + 1u) & ~1u) * 8u;
+        uint32_t tx = units_bytes + (direct ? 0u : 2u * byte_len + rbytes);
+        mbar_arrive_expect_tx(&S.full[s], tx);
+        tma_load_1d(st.units, a.units + unit_begin, units_bytes, &S.full[s]);
+        if (!direct) {
+          if (byte_len) {
+            tma_load_1d(st.bases, a.bases + byte_begin, byte_len, &S.full[s]);
+            tma_load_1d(st.quals, a.quals + byte_begin, byte_len, &S.full[s]);
+          }
+          if (rbytes) tma_load_1d(st.reads, a.reads + (read_begin - rskew), rbytes, &S.full[s]);
+        }
+      }
     }
+    return;
   }
 
+  // ================= CONSUMER WARPS =================
   LocalStats ls = {0, 0, 0};
   uint64_t n_units_done = 0, n_reads_done = 0;
-  uint32_t k = 0;
+  uint32_t k = 0, rot = 0;
   for (uint64_t t = blockIdx.x; t < a.n_tiles; t += grid, ++k) {
     const int s = k % kStages;
     mbar_wait(&S.full[s], (k / kStages) & 1u);
     Stage& st = S.st[s];
-    uint32_t* qc = &S.q_count[k & 1u];
+    // rotating item assignment: the partial last round of a tile lands on different warps from
+    // tile to tile, so every warp does the same work in the long run
+    const uint32_t vt = (tid - rot) & (kVoteThreads - 1);
+    const uint32_t n_items =
+        static_cast<uint32_t>((st.units[st.tile.n_units].out_off - st.units[0].out_off) >> 2);
     if (st.tile.flags & kTileFlagDirect) {
       TileView<GlMem> tv;
       tv.bases = a.bases; tv.quals = a.quals;
       tv.reads = reinterpret_cast<const uint8_t*>(a.reads + st.tile.read_begin);
       tv.byte_base = 0; tv.read_base = st.tile.read_begin;
-      vote_tile<GlMem>(a, S, st, tv, qc, ls);
+      vote_tile<GlMem>(a, S, st, tv, vt, warp, ls);
     } else {
       TileView<ShMem> tv;
-      tv.bases = smem_u32(st.bases); tv.quals = smem_u32(st.quals);
-      tv.reads = smem_u32(st.reads) + (st.tile.read_begin & 1u) * 8u;
+      tv.bases = st.bases; tv.quals = st.quals;
+      tv.reads = reinterpret_cast<const uint8_t*>(st.reads) + (st.tile.read_begin & 1u) * 8u;
       tv.byte_base = st.tile.byte_begin; tv.read_base = st.tile.read_begin;
-      vote_tile<ShMem>(a, S, st, tv, qc, ls);
+      vote_tile<ShMem>(a, S, st, tv, vt, warp, ls);
     }
     if (tid == 0) { n_units_done += st.tile.n_units; n_reads_done += st.tile.n_reads; }
-    __syncthreads();   // stage s and the queue are free again
-    if (tid == 0) {
-      *qc = 0;
-      uint64_t nt = t + static_cast<uint64_t>(kStages) * grid;
-      if (nt < a.n_tiles) issue(nt, s);
-    }
+    rot = (rot + n_items) & (kVoteThreads - 1);
+    __syncwarp();
+    if ((tid & 31u) == 0) mbar_arrive(&S.empty[s]);   // this warp is done with stage s
   }
 
   // ---- counters: warp-reduce, one atomic per warp ----

@@ -24,7 +24,8 @@
  *            CIGAR-filtered, in reference order (order matters: the f64 Kahan vote is
  *            order-dependent, base_builder.rs:312-324).
  *   bases[], quals[]  two byte columns; read r occupies bytes
- *            [off_r, off_r+len_r) of BOTH columns, off_r % FGB_READ_ALIGN == 0.
+ *            [off_r, off_r+len_r) of BOTH columns, off_r % FGB_READ_ALIGN == 0, len_r >= 1,
+ *            rows ascending and non-overlapping.
  *   reads[r] = FGB_READ_DESC(off_r, len_r); reads of a unit are consecutive.
  *   units[u] = {out_off, read_begin, cons_len}; units[U] is a sentinel
  *            {n_out, n_reads, 0}.  cons_len = min_reads-th longest read
@@ -94,7 +95,8 @@ typedef struct fgb_tile {
   uint32_t n_units;
   uint32_t read_begin;
   uint32_t n_reads;
-  uint32_t flags;       /* reserved, 0                                                        */
+  uint32_t flags;       /* bit0: oversize unit voted straight from HBM; bits 8..31: uchar4 items
+                           per unit when every unit of the tile has the same count (else 0)    */
 } fgb_tile;
 
 typedef struct fgb_batch {
@@ -155,6 +157,13 @@ fgb_status fgb_get_tables(const fgb_handle* h, double* correct, double* err_alt,
 fgb_status fgb_host_tables(uint8_t error_rate_pre_umi, uint8_t error_rate_post_umi,
                            double* correct, double* err_alt, double* ln_pre,
                            uint8_t* single_input_q, uint8_t* qt, uint32_t* fast_qual);
+
+/* Pure host function: the integer "dominant winner" proof tables the kernel uses to skip the f64
+ * path (fgumi_b200/csrc/host_tables.cpp): dfix[96] = round((correct[q]-err_alt[q])*65536) with
+ * INT32_MIN marking unusable qualities, *g2fix the fixed-point gap threshold, *nmax2 the largest
+ * pileup the proof covers.  Exposed so the proof can be tested against the oracle on the CPU. */
+fgb_status fgb_host_proof_tables(uint8_t error_rate_pre_umi, uint8_t error_rate_post_umi,
+                                 int32_t* dfix, int32_t* g2fix, uint32_t* nmax2);
 
 /* ---- batch planning (pure host code, no device needed) -------------------------------- */
 /* Bytes of one column that a tile may span. */

@@ -54,23 +54,64 @@ def test_host_tables_bit_identical_to_oracle(fg, pre, post):
     assert c.tobytes() == oc.tobytes() and e.tobytes() == oe.tobytes()
     assert lp.value == olp and np.array_equal(sq, osq)
     assert fq.value == O.load().orc_ln_prob_to_phred(olp)
-    # the proof table: n identical observations at quality >= qt[n] must clear the 23.0 gap
-    d = oc - oe
-    for n in (1, 2, 3, 8, 100, 255):
+    # the SWAR proof table: n identical observations at quality >= qt[n] are PROVEN to come out
+    # of the reference's call() as (base, phred(ln_pre))
+    for n in (1, 2, 3, 4, 8, 100, 254, 255):
         if qt[n] <= 93:
-            dm = min(d[qt[n]:])
-            assert n * dm > 23.0
-            b, q, _, ll = O.builder_call(pre, post, b"A" * n, [int(qt[n])] * n)
-            assert ll[0] - ll[1] > 23.0 and (b, q) == ("A", fq.value)
+            for q in {int(qt[n]), min(93, int(qt[n]) + 1), 93}:
+                b, qq, _, ll = O.builder_call(pre, post, b"A" * n, [q] * n)
+                assert (b, qq) == ("A", fq.value), (n, q)
+    assert qt[0] == 255
 
 
 def test_fast_path_threshold_defaults(fg):
     lib = fg.lib.load()
     qt = np.zeros(256, np.uint8)
     lib.fgb_host_tables(45, 40, None, None, None, None, qt.ctypes.data, None)
-    assert qt[0] == 255 and qt[1] == 255 and qt[2] == 255   # depth <= 2 can never clear 23
+    assert qt[0] == 255 and qt[1] == 255      # one observation can never dominate
+    assert qt[2] <= 40                        # two Q37+ observations are enough
     assert qt[8] <= 10           # depth 8: every unmasked base (q >= 10) qualifies
     assert qt[3] <= 31
+
+
+def _proof(fg, pre, post):
+    lib = fg.lib.load()
+    dfix = np.zeros(96, np.int32); g2 = C.c_int32(); nmax = C.c_uint32()
+    assert lib.fgb_host_proof_tables(pre, post, dfix.ctypes.data, C.addressof(g2), C.addressof(nmax)) == 0
+    return dfix, g2.value, nmax.value
+
+
+@pytest.mark.parametrize("pre,post", [(45, 40), (50, 50), (30, 20), (60, 60), (93, 93), (20, 45)])
+def test_dominant_winner_proof_against_oracle(fg, pre, post):
+    """Whenever the integer proof fires, the oracle's literal f64 call() must return
+    (winner, phred(ln_pre)).  Random pileups near the decision boundary."""
+    dfix, g2fix, nmax2 = _proof(fg, pre, post)
+    fq = O.load().orc_ln_prob_to_phred(O.tables(pre, post)[2])
+    rng = np.random.default_rng(pre * 100 + post)
+    fired = 0
+    INT_MIN = np.iinfo(np.int32).min
+    assert dfix[0] == INT_MIN          # quality 0 has correct[0] = -inf: never usable
+    for trial in range(6000):
+        n = int(rng.integers(1, 14))
+        if n > nmax2:
+            continue
+        nalt = int(rng.integers(0, max(1, n // 2) + 1))
+        qs = rng.integers(1, 60, size=n)
+        bs = np.array([ord("G")] * (n - nalt) + list(rng.choice([65, 67, 84], size=nalt)), np.uint8)
+        perm = rng.permutation(n)
+        bs, qs = bs[perm], qs[perm]
+        S = {65: 0, 67: 0, 71: 0, 84: 0}
+        cnt = {65: 0, 67: 0, 71: 0, 84: 0}
+        for b, q in zip(bs, qs):
+            S[int(b)] += int(dfix[min(int(q), 93)]); cnt[int(b)] += 1
+        order = sorted(S.items(), key=lambda kv: -kv[1])
+        gap = order[0][1] - order[1][1]
+        if gap >= g2fix + 2 * n + 1:
+            fired += 1
+            b, q, obs, _ = O.builder_call(pre, post, bs.tobytes(), [int(x) for x in qs])
+            assert (ord(b), q) == (order[0][0], fq), (trial, bs, qs, gap, g2fix)
+    if nmax2 >= 13:
+        assert fired > 200
 
 
 def test_create_without_gpu_fails_loudly(fg):
@@ -96,6 +137,9 @@ def test_planner_small_and_empty(fg):
     t = tiles[0]
     assert t["n_units"] == 2 and t["n_reads"] == 6 and t["byte_begin"] == 0
     assert t["byte_len"] % 16 == 0 and t["byte_len"] >= 6 * 40
+    assert t["flags"] >> 8 == 10          # uniform tile: 40-base rows -> 10 uchar4 items per unit
+    b, tiles = _plan(fg, [rows, rows[:2] + [(b"ACGT" * 5, bytes([30] * 20))]], min_reads=3)
+    assert tiles[0]["flags"] >> 8 == 0    # mixed consensus lengths: no hint
 
 
 def test_planner_splits_on_capacity(fg):
@@ -117,10 +161,10 @@ def test_planner_flags_oversize_unit_direct(fg):
     small = [(b"A" * 20, bytes([30] * 20))] * 2
     b, tiles = _plan(fg, [small, big, small])
     assert len(tiles) == 3
-    assert list(tiles["flags"]) == [0, 1, 0]
+    assert list(tiles["flags"] & 1) == [0, 1, 0]
     many = [(b"A" * 4, bytes([30] * 4))] * (fg.lib.load().fgb_tile_max_reads() + 1)
     b, tiles = _plan(fg, [many])
-    assert list(tiles["flags"]) == [1]
+    assert list(tiles["flags"] & 1) == [1]
 
 
 def test_planner_rejects_bad_layout(fg):
