@@ -257,7 +257,7 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
   uint64_t cur_end = 0;   // exclusive end (unaligned) of the open tile's byte range
   uint64_t prev_read_end = 0;
 
-  uint32_t cur_items = 0;     // uchar4 items per unit if uniform so far, 0xFFFFFFFF = mixed
+  uint32_t cur_items = 0;     // 8-position items per unit if uniform so far, 0xFFFFFFFF = mixed
   auto emit = [&]() {
     cur.byte_len = static_cast<uint32_t>(((cur_end + 15u) & ~15ull) - cur.byte_begin);
     if (cur.flags & kTileFlagDirect) { cur.byte_len = 0; }
@@ -275,7 +275,7 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
     if (nx.read_begin < un.read_begin || nx.read_begin > n_reads) return FGB_ERR_LAYOUT;
     uint32_t nr = nx.read_begin - un.read_begin;
     if (un.out_off % FGB_OUT_ALIGN) return FGB_ERR_LAYOUT;
-    if (nx.out_off != un.out_off + ((static_cast<uint64_t>(un.cons_len) + 3u) & ~3ull))
+    if (nx.out_off != un.out_off + ((static_cast<uint64_t>(un.cons_len) + (FGB_OUT_ALIGN - 1u)) & ~static_cast<uint64_t>(FGB_OUT_ALIGN - 1u)))
       return FGB_ERR_LAYOUT;   // output rows are dense, each padded to FGB_OUT_ALIGN
     if (un.cons_len > FGB_MAX_READ_LEN) return FGB_ERR_UNIT_TOO_LARGE;
     if (nr == 0 && un.cons_len != 0) return FGB_ERR_LAYOUT;
@@ -316,7 +316,7 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
         cur.flags |= kTileFlagDirect;   // oversize unit: kernel votes it straight from HBM
     }
     {
-      uint32_t items = (un.cons_len + 3u) >> 2;
+      uint32_t items = (un.cons_len + 7u) >> 3;
       if (cur.n_units == 0) cur_items = items;
       else if (cur_items != items) cur_items = 0xFFFFFFFFu;
     }

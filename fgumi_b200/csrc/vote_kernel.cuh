@@ -14,7 +14,7 @@
 //     complete_tx) as soon as a stage's "empty" mbarrier says all eight CONSUMER warps are done
 //     with it; consumers never meet at a CTA barrier, so a warp that finishes its share of a tile
 //     moves straight on to the next one while HBM streams into the other stage;
-//   * FAST PASS: one thread per 4 consecutive positions (uchar4 words).  Over the depth axis it
+//   * FAST PASS: one thread per 8 consecutive positions (one 64-bit word of each row).  Over the depth axis it
 //     keeps a SWAR "all reads equal the first read" mask and a SWAR "every quality >= qT(n)" mask;
 //     a position that is unanimous over A/C/G/T, covered by every read and passes the quality
 //     mask is PROVEN to take the reference's unanimous fast path (sum of per-read likelihood gaps
@@ -24,7 +24,7 @@
 //     the integer "dominant winner" proof (host_tables.cpp) and only then by the literal algorithm:
 //     sequential, in-order, 4-lane f64 Kahan accumulation from the host-built tables and the f64
 //     call() tail;
-//   * results leave as coalesced uchar4 / ushort4 stores.
+//   * results leave as coalesced 8-byte (bases, quals) and 16-byte (depths, errors) stores.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -106,20 +106,36 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Blocks until the phase with the given parity completes.  `hint_ns` lets the hardware park the
+// thread between probes instead of spinning through issue slots.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t addr = smem_u32(bar);
   uint32_t done;
   do {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(hint_ns)
         : "memory");
   } while (!done);
+}
+// Non-blocking probe of a phase.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes,
@@ -372,8 +388,116 @@ __device__ __forceinline__ Called resolve_position(const TileView<M>& tv, const 
   return c;
 }
 
+// Resolves a warp's queued positions.  The depth axis is split across a GROUP of lanes (8 lanes
+// per position when every queued pileup has <= 8 reads, else the whole warp): each lane classifies
+// its reads and looks up their fixed-point likelihood gaps, a __shfl_xor butterfly sums the four
+// per-base gap sums and counts over the group, and the group leader applies the dominant-winner
+// proof (host_tables.cpp).  Whatever the proof cannot decide runs the literal f64 algorithm.
+template <class M>
+__device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, const Stage& st,
+                                       const TileView<M>& tv, const uint32_t* wqueue, uint32_t qn,
+                                       uint32_t lane, LocalStats& ls) {
+  // group width: warp-uniform
+  uint32_t nmax = 0;
+  for (uint32_t e = lane; e < qn; e += 32) {
+    uint32_t u = wqueue[e] >> 16;
+    uint32_t n = st.units[u + 1].read_begin - st.units[u].read_begin;
+    nmax = n > nmax ? n : nmax;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, nmax, off);
+    nmax = o > nmax ? o : nmax;
+  }
+  const uint32_t G = nmax <= 8u ? 8u : 32u;
+  const uint32_t per_pass = 32u / G;
+  const uint32_t sub = lane & (G - 1u);
+  for (uint32_t e0 = 0; e0 < qn; e0 += per_pass) {
+    const uint32_t e = e0 + lane / G;
+    const bool valid = e < qn;
+    uint32_t u = 0, pos = 0, rb = 0, n = 0;
+    uint64_t out_off = 0;
+    if (valid) {
+      uint32_t ent = wqueue[e];
+      u = ent >> 16; pos = ent & 0xFFFFu;
+      const fgb_unit un = st.units[u];
+      rb = un.read_begin; out_off = un.out_off;
+      n = st.units[u + 1].read_begin - rb;
+    }
+    const bool provable = n <= S.nmax2;
+    int32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    uint32_t c01 = 0, c23 = 0;      // 4 x u16 observation counts; bit 31 of c23 = "unusable quality seen"
+    if (provable) {
+      for (uint32_t r = sub; r < n; r += G) {
+        uint64_t d = M::ld64(tv.reads + static_cast<typename M::off_t>(rb - tv.read_base + r) * 8u);
+        uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
+        if (pos < len) {
+          typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + pos;
+          uint32_t b = M::ld8(tv.bases + row);
+          uint32_t idx = base_to_index(b);
+          if (b != 'N' && idx < 4u) {
+            uint32_t q = M::ld8(tv.quals + row);
+            q = q > FGB_MAX_PHRED ? FGB_MAX_PHRED : q;
+            int32_t dq = S.dfix[q];
+            if (dq == INT32_MIN) { c23 |= 0x80000000u; dq = 0; }
+            s0 += idx == 0 ? dq : 0; s1 += idx == 1 ? dq : 0;
+            s2 += idx == 2 ? dq : 0; s3 += idx == 3 ? dq : 0;
+            c01 += idx == 0 ? 1u : (idx == 1 ? 0x10000u : 0u);
+            c23 += idx == 2 ? 1u : (idx == 3 ? 0x10000u : 0u);
+          }
+        }
+      }
+    }
+    // butterfly over the group (n <= nmax2 <= 1024 keeps every 16-bit count and the flag intact)
+    for (uint32_t off = G >> 1; off > 0; off >>= 1) {
+      s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, off);
+      s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, off);
+      s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, off);
+      s3 += __shfl_xor_sync(0xFFFFFFFFu, s3, off);
+      c01 += __shfl_xor_sync(0xFFFFFFFFu, c01, off);
+      uint32_t o23 = __shfl_xor_sync(0xFFFFFFFFu, c23, off);
+      c23 = ((c23 & 0x7FFFFFFFu) + (o23 & 0x7FFFFFFFu)) | ((c23 | o23) & 0x80000000u);
+    }
+    if (valid && sub == 0) {
+      Called c;
+      bool done = false;
+      if (provable) {
+        const uint32_t c0 = c01 & 0xFFFFu, c1 = c01 >> 16, c2 = c23 & 0xFFFFu, c3 = (c23 >> 16) & 0x7FFFu;
+        const uint32_t depth = c0 + c1 + c2 + c3;
+        if (depth == 0) {   // base_builder.rs:392-394 then vanilla_caller.rs:1345 (min_reads >= 1)
+          c.base = 'N'; c.qual = 0; c.depth = 0; c.errors = 0;
+          done = true;
+        } else if (!(c23 & 0x80000000u)) {
+          int32_t best = s0, second = INT32_MIN;
+          uint32_t w = 0, cw = c0;
+          if (s1 > best) { second = best; best = s1; w = 1; cw = c1; } else if (s1 > second) second = s1;
+          if (s2 > best) { second = best; best = s2; w = 2; cw = c2; } else if (s2 > second) second = s2;
+          if (s3 > best) { second = best; best = s3; w = 3; cw = c3; } else if (s3 > second) second = s3;
+          // every fixed-point term is within half a unit of D[q]*65536; two sums of <= depth terms
+          if (static_cast<int64_t>(best) - second >=
+              static_cast<int64_t>(S.g2fix) + 2 * static_cast<int64_t>(depth) + 1) {
+            c.depth = depth;
+            c.errors = depth - cw;
+            if (depth < a.min_reads) { c.base = 'N'; c.qual = 0; }
+            else if (a.fast_qual < a.min_cons_q) { c.base = 'N'; c.qual = 2; }
+            else { c.base = (0x54474341u >> (8u * w)) & 0xFFu; c.qual = a.fast_qual; }
+            done = true;
+          }
+        }
+      }
+      if (!done) {
+        c = exact_position<M>(tv, S, rb, n, pos, a.min_reads, a.min_cons_q, a.fast_qual);
+        ls.exact++;
+      }
+      ls.nocall += (c.base == 'N');
+      write_called(a, out_off + pos, c);
+    }
+  }
+}
+
 // Votes this warp's share of one tile.  Called by the eight consumer warps; `vt` is the thread's
-// rotating slot (0..kVoteThreads-1): it owns items vt, vt+256, ...
+// rotating slot (0..kVoteThreads-1): it owns items vt, vt+256, ...  An item is 8 consecutive
+// positions of one unit: one 64-bit word of every read's base row and quality row.
 template <class M>
 __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const Stage& st,
                                           const TileView<M>& tv, uint32_t vt, uint32_t warp,
@@ -381,19 +505,19 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_units = st.tile.n_units;
   const uint64_t out0 = st.units[0].out_off;
-  const uint32_t n_items = static_cast<uint32_t>((st.units[n_units].out_off - out0) >> 2);
+  const uint32_t n_items = static_cast<uint32_t>((st.units[n_units].out_off - out0) >> 3);
   const uint32_t min_reads = a.min_reads, min_cons_q = a.min_cons_q, fast_qual = a.fast_qual;
   // constant result of a proven position after the thresholds of vanilla_caller.rs:1345-1349
   const bool fast_masked = fast_qual < min_cons_q;
-  const uint32_t fq = fast_masked ? 2u : fast_qual;
-  // planner hint: every unit of the tile has the same number of uchar4 items
+  const uint32_t fq4 = (fast_masked ? 2u : fast_qual) * 0x01010101u;
+  // planner hint: every unit of the tile has the same number of items
   const uint32_t uni_m = st.tile.flags >> 8;
   const uint32_t uni_recip = uni_m ? (0xFFFFFFFFu / uni_m + 1u) : 0u;
   const uint32_t base32 = static_cast<uint32_t>(tv.byte_base);
   uint32_t* const wqueue = S.queue[warp];
   uint32_t* const wcount = &S.q_count[warp];
 
-  // ---------------- FAST PASS: one thread per uchar4 of output ----------------
+  // ---------------- FAST PASS: one thread per 8 positions ----------------
   for (uint32_t item = vt; item < n_items; item += kVoteThreads) {
     uint32_t u;
     if (uni_m) {
@@ -402,7 +526,7 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
       uint32_t lo = 0, hi = n_units;
       while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
-        uint32_t start = static_cast<uint32_t>((st.units[mid].out_off - out0) >> 2);
+        uint32_t start = static_cast<uint32_t>((st.units[mid].out_off - out0) >> 3);
         if (start <= item) lo = mid; else hi = mid;
       }
       u = lo;
@@ -411,13 +535,13 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
     const uint32_t rb = un.read_begin;
     const uint32_t n = st.units[u + 1].read_begin - rb;
     const uint32_t cons_len = un.cons_len;
-    const uint32_t p0 = (item - static_cast<uint32_t>((un.out_off - out0) >> 2)) << 2;
-    const uint64_t o = out0 + (static_cast<uint64_t>(item) << 2);
-    const uint32_t real = cons_len - p0 < 4u ? cons_len - p0 : 4u;   // positions of this item (>= 1)
-    const uint32_t realmask = low_bytes_mask(real);
+    const uint32_t p0 = (item - static_cast<uint32_t>((un.out_off - out0) >> 3)) << 3;
+    const uint64_t o = out0 + (static_cast<uint64_t>(item) << 3);
+    const uint32_t real = cons_len - p0 < 8u ? cons_len - p0 : 8u;   // positions of this item (>= 1)
+    const uint32_t rm_lo = low_bytes_mask(real), rm_hi = low_bytes_mask(real > 4u ? real - 4u : 0u);
 
-    uint32_t wbase = 0, wqual = 0;           // 4 output bases / quals
-    uint32_t d01 = 0, d23 = 0, e01 = 0, e23 = 0;   // 4 x u16 depths / errors
+    uint32_t wb_lo = 0, wb_hi = 0, wq_lo = 0, wq_hi = 0;   // 8 output bases / quals
+    uint4 dep = make_uint4(0, 0, 0, 0), err = make_uint4(0, 0, 0, 0);   // 8 x u16 each
     ls.positions += real;
 
     if (n == 1) {
@@ -425,40 +549,46 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
       uint64_t d = M::ld64(tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u);
       uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
       typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + p0;
-      uint32_t wb = 0, wq = 0;
-      if (p0 < len) { wb = M::ld32(tv.bases + row); wq = M::ld32(tv.quals + row); }
-      uint32_t dep[4] = {0, 0, 0, 0};
+      uint64_t rbw = 0, rqw = 0;
+      if (p0 < len) { rbw = M::ld64(tv.bases + row); rqw = M::ld64(tv.quals + row); }
+      uint64_t obw = 0, oqw = 0, odw_lo = 0, odw_hi = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         uint32_t pos = p0 + j;
         if (pos < cons_len) {
-          uint32_t b = (wb >> (8 * j)) & 0xFFu, q = (wq >> (8 * j)) & 0xFFu;
+          uint32_t b = static_cast<uint32_t>(rbw >> (8 * j)) & 0xFFu;
+          uint32_t q = static_cast<uint32_t>(rqw >> (8 * j)) & 0xFFu;
           uint32_t ob = 'N', oq = 2, od = 0;
           if (pos < len) {
             uint32_t adj = q < FGB_NTABLE ? S.single_q[q] : 0u;   // `.get(idx).unwrap_or(0)`
             if (adj >= min_cons_q) { ob = b; oq = adj; }
             od = (b != 'N');
           }
-          wbase |= ob << (8 * j);
-          wqual |= oq << (8 * j);
-          dep[j] = od;
+          obw |= static_cast<uint64_t>(ob) << (8 * j);
+          oqw |= static_cast<uint64_t>(oq) << (8 * j);
+          if (j < 4) odw_lo |= static_cast<uint64_t>(od) << (16 * j);
+          else odw_hi |= static_cast<uint64_t>(od) << (16 * (j - 4));
           ls.nocall += (ob == 'N');
         }
       }
-      d01 = dep[0] | (dep[1] << 16);
-      d23 = dep[2] | (dep[3] << 16);
+      wb_lo = static_cast<uint32_t>(obw); wb_hi = static_cast<uint32_t>(obw >> 32);
+      wq_lo = static_cast<uint32_t>(oqw); wq_hi = static_cast<uint32_t>(oqw >> 32);
+      dep = make_uint4(static_cast<uint32_t>(odw_lo), static_cast<uint32_t>(odw_lo >> 32),
+                       static_cast<uint32_t>(odw_hi), static_cast<uint32_t>(odw_hi >> 32));
     } else {
       const uint32_t qt = S.qt[n < kQtEntries ? n : kQtEntries - 1];
       const bool fast_ok = (qt <= FGB_MAX_PHRED) && (n >= min_reads) && (n <= 0xFFFFu);
-      uint32_t fm = 0, b0 = 0;
+      uint32_t fm_lo = 0, fm_hi = 0, b0_lo = 0, b0_hi = 0;
       if (fast_ok) {
         const uint32_t tsplat = qt * 0x01010101u;
         typename M::addr_t rd = tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u;
-        uint32_t diff = 0, okq = 0x80808080u, minlen = 0xFFFFFFFFu;
+        uint32_t diff_lo = 0, diff_hi = 0, okq_lo = 0x80808080u, okq_hi = 0x80808080u;
+        uint32_t minlen = 0xFFFFFFFFu;
         {   // reference word: read 0 (if it does not reach p0, minlen vetoes the item anyway)
           uint64_t d = M::ld64(rd);
           uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
-          b0 = M::ld32(tv.bases + M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u));
+          uint64_t w = M::ld64(tv.bases + M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u));
+          b0_lo = static_cast<uint32_t>(w); b0_hi = static_cast<uint32_t>(w >> 32);
         }
 #pragma unroll 4
         for (uint32_t r = 0; r < n; ++r) {
@@ -467,65 +597,74 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
           minlen = len < minlen ? len : minlen;
           // an uncovered read points at its own first word: harmless, minlen already vetoes
           typename M::off_t row = M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u);
-          uint32_t wb = M::ld32(tv.bases + row);
-          uint32_t wq = M::ld32(tv.quals + row);
-          diff |= wb ^ b0;
-          okq &= (wq | 0x80808080u) - tsplat;   // byte high bit survives iff q >= qT (no borrows)
+          uint64_t wb = M::ld64(tv.bases + row);
+          uint64_t wq = M::ld64(tv.quals + row);
+          diff_lo |= static_cast<uint32_t>(wb) ^ b0_lo;
+          diff_hi |= static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+          // byte high bit survives iff q >= qT (no borrows: every minuend byte is >= 0x80 > qT)
+          okq_lo &= (static_cast<uint32_t>(wq) | 0x80808080u) - tsplat;
+          okq_hi &= (static_cast<uint32_t>(wq >> 32) | 0x80808080u) - tsplat;
         }
         // per-byte verdict: unanimous & quality-proven & A/C/G/T & covered by every read
         const uint32_t covered = minlen > p0 ? minlen - p0 : 0u;
-        fm = zero_bytes(diff) & okq & acgt_bytes(b0) & low_bytes_mask(covered) & realmask;
+        fm_lo = zero_bytes(diff_lo) & okq_lo & acgt_bytes(b0_lo) & low_bytes_mask(covered) & rm_lo;
+        fm_hi = zero_bytes(diff_hi) & okq_hi & acgt_bytes(b0_hi) &
+                low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
       }
       // proven positions: constant quality, depth n, no errors
-      const uint32_t fbytes = (fm >> 7) * 0xFFu;
-      wbase = (fast_masked ? 0x4E4E4E4Eu : b0) & fbytes;
-      wqual = (fq * 0x01010101u) & fbytes;
-      d01 = ((fm & 0x80u) ? n : 0u) | ((fm & 0x8000u) ? (n << 16) : 0u);
-      d23 = ((fm & 0x800000u) ? n : 0u) | ((fm & 0x80000000u) ? (n << 16) : 0u);
-      ls.nocall += fast_masked ? __popc(fm) : 0;
-      uint32_t todo = realmask & ~fm;
-      if (todo) {
+      const uint32_t fb_lo = (fm_lo >> 7) * 0xFFu, fb_hi = (fm_hi >> 7) * 0xFFu;
+      wb_lo = (fast_masked ? 0x4E4E4E4Eu : b0_lo) & fb_lo;
+      wb_hi = (fast_masked ? 0x4E4E4E4Eu : b0_hi) & fb_hi;
+      wq_lo = fq4 & fb_lo;
+      wq_hi = fq4 & fb_hi;
+      const uint32_t nn = n | (n << 16);
+      // expand byte mask pairs to u16 pairs: bytes (0,1) -> dep.x, (2,3) -> dep.y, ...
+      dep.x = nn & (((fb_lo & 0xFFu) * 0x0101u) | ((fb_lo & 0xFF00u) * 0x010100u));
+      dep.y = nn & ((((fb_lo >> 16) & 0xFFu) * 0x0101u) | (((fb_lo >> 16) & 0xFF00u) * 0x010100u));
+      dep.z = nn & (((fb_hi & 0xFFu) * 0x0101u) | ((fb_hi & 0xFF00u) * 0x010100u));
+      dep.w = nn & ((((fb_hi >> 16) & 0xFFu) * 0x0101u) | (((fb_hi >> 16) & 0xFF00u) * 0x010100u));
+      ls.nocall += fast_masked ? (__popc(fm_lo) + __popc(fm_hi)) : 0;
+      const uint32_t todo_lo = rm_lo & ~fm_lo, todo_hi = rm_hi & ~fm_hi;
+      if (todo_lo | todo_hi) {
         // undecided positions go to this warp's queue (or are resolved in place if it is full)
-        const uint32_t cnt = __popc(todo);
-        uint32_t slot = atomicAdd(wcount, cnt);
+        uint32_t slot = atomicAdd(wcount, static_cast<uint32_t>(__popc(todo_lo) + __popc(todo_hi)));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (todo & (0x80u << (8 * j))) {
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t bit = 0x80u << (8 * (j & 3));
+          if ((j < 4 ? todo_lo : todo_hi) & bit) {
             uint32_t pos = p0 + j;
             if (slot < kWarpQueueCap) {
               wqueue[slot] = (u << 16) | pos;
             } else {
               Called c = resolve_position<M>(tv, S, rb, n, pos, a, ls);
-              wbase |= (c.base & 0xFFu) << (8 * j);
-              wqual |= (c.qual & 0xFFu) << (8 * j);
+              uint32_t sb = (c.base & 0xFFu) << (8 * (j & 3)), sq = (c.qual & 0xFFu) << (8 * (j & 3));
+              if (j < 4) { wb_lo |= sb; wq_lo |= sq; } else { wb_hi |= sb; wq_hi |= sq; }
               uint32_t dv = (c.depth & 0xFFFFu) << (16 * (j & 1)), ev = (c.errors & 0xFFFFu) << (16 * (j & 1));
-              if (j < 2) { d01 |= dv; e01 |= ev; } else { d23 |= dv; e23 |= ev; }
+              switch (j >> 1) {
+                case 0: dep.x |= dv; err.x |= ev; break;
+                case 1: dep.y |= dv; err.y |= ev; break;
+                case 2: dep.z |= dv; err.z |= ev; break;
+                default: dep.w |= dv; err.w |= ev; break;
+              }
             }
             ++slot;
           }
         }
       }
     }
-    *reinterpret_cast<uint32_t*>(a.out_base + o) = wbase;
-    *reinterpret_cast<uint32_t*>(a.out_qual + o) = wqual;
-    *reinterpret_cast<uint2*>(a.out_depth + o) = make_uint2(d01, d23);
-    *reinterpret_cast<uint2*>(a.out_errors + o) = make_uint2(e01, e23);
+    *reinterpret_cast<uint2*>(a.out_base + o) = make_uint2(wb_lo, wb_hi);
+    *reinterpret_cast<uint2*>(a.out_qual + o) = make_uint2(wq_lo, wq_hi);
+    *reinterpret_cast<uint4*>(a.out_depth + o) = dep;
+    *reinterpret_cast<uint4*>(a.out_errors + o) = err;
   }
   __syncwarp();
 
-  // ---------------- SLOW PASS: this warp's undecided positions, one per lane ----------------
+  // ---------------- SLOW PASS: this warp's undecided positions ----------------
   // (a queued position's word was stored above by a lane of this same warp: program order within
   //  the warp + __syncwarp() orders the byte stores below after it)
   uint32_t qn = *wcount;
   qn = qn < kWarpQueueCap ? qn : kWarpQueueCap;
-  for (uint32_t e = lane; e < qn; e += 32) {
-    uint32_t ent = wqueue[e];
-    uint32_t u = ent >> 16, pos = ent & 0xFFFFu;
-    const fgb_unit un = st.units[u];
-    uint32_t n = st.units[u + 1].read_begin - un.read_begin;
-    Called c = resolve_position<M>(tv, S, un.read_begin, n, pos, a, ls);
-    write_called(a, un.out_off + pos, c);
-  }
+  if (qn) slow_pass<M>(a, S, st, tv, wqueue, qn, lane, ls);
   __syncwarp();
   if (lane == 0) *wcount = 0;
 }
@@ -565,7 +704,9 @@ __global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
       for (uint64_t t = blockIdx.x; t < a.n_tiles; t += grid, ++k) {
         const int s = k % kStages;
         const uint32_t use = k / kStages;
-        if (use > 0) mbar_wait(&S.empty[s], (use - 1u) & 1u);   // consumers released the stage
+        if (use > 0) {                                          // consumers released the stage
+          mbar_wait(&S.empty[s], (use - 1u) & 1u, 20000u);
+        }
         Stage& st = S.st[s];
         const uint4* gt = reinterpret_cast<const uint4*>(a.tiles + t);
         uint4 t0 = __ldg(gt), t1 = __ldg(gt + 1);
@@ -599,13 +740,13 @@ __global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
   uint32_t k = 0, rot = 0;
   for (uint64_t t = blockIdx.x; t < a.n_tiles; t += grid, ++k) {
     const int s = k % kStages;
-    mbar_wait(&S.full[s], (k / kStages) & 1u);
+    mbar_wait(&S.full[s], (k / kStages) & 1u, 2000u);
     Stage& st = S.st[s];
     // rotating item assignment: the partial last round of a tile lands on different warps from
     // tile to tile, so every warp does the same work in the long run
     const uint32_t vt = (tid - rot) & (kVoteThreads - 1);
     const uint32_t n_items =
-        static_cast<uint32_t>((st.units[st.tile.n_units].out_off - st.units[0].out_off) >> 2);
+        static_cast<uint32_t>((st.units[st.tile.n_units].out_off - st.units[0].out_off) >> 3);
     if (st.tile.flags & kTileFlagDirect) {
       TileView<GlMem> tv;
       tv.bases = a.bases; tv.quals = a.quals;

@@ -20,8 +20,8 @@ FGB_ERR_UNIT_TOO_LARGE = 5
 FGB_ERR_NOMEM = 6
 FGB_ERR_BUSY = 7
 
-FGB_READ_ALIGN = 4
-FGB_OUT_ALIGN = 4
+FGB_READ_ALIGN = 8
+FGB_OUT_ALIGN = 8
 FGB_NCOUNTERS = 8
 COUNTER_NAMES = (
     "units", "positions", "exact_positions", "nocall_positions", "input_reads",

@@ -46,8 +46,8 @@ extern "C" {
 #endif
 
 #define FGB_ABI_VERSION 1
-#define FGB_READ_ALIGN 4u   /* byte alignment of every read row in bases[]/quals[]          */
-#define FGB_OUT_ALIGN 4u    /* element alignment of every unit's output row                 */
+#define FGB_READ_ALIGN 8u   /* byte alignment of every read row in bases[]/quals[]          */
+#define FGB_OUT_ALIGN 8u    /* element alignment of every unit's output row                 */
 #define FGB_MAX_READ_LEN 65535u
 #define FGB_MAX_PHRED 93u   /* phred.rs:28 */
 #define FGB_NTABLE 94u      /* tables are indexed by input quality 0..=93, base_builder.rs:258 */
@@ -95,7 +95,7 @@ typedef struct fgb_tile {
   uint32_t n_units;
   uint32_t read_begin;
   uint32_t n_reads;
-  uint32_t flags;       /* bit0: oversize unit voted straight from HBM; bits 8..31: uchar4 items
+  uint32_t flags;       /* bit0: oversize unit voted straight from HBM; bits 8..31: 8-position items
                            per unit when every unit of the tile has the same count (else 0)    */
 } fgb_tile;
 

@@ -137,7 +137,7 @@ def test_planner_small_and_empty(fg):
     t = tiles[0]
     assert t["n_units"] == 2 and t["n_reads"] == 6 and t["byte_begin"] == 0
     assert t["byte_len"] % 16 == 0 and t["byte_len"] >= 6 * 40
-    assert t["flags"] >> 8 == 10          # uniform tile: 40-base rows -> 10 uchar4 items per unit
+    assert t["flags"] >> 8 == 5           # uniform tile: 40-base rows -> 5 eight-position items per unit
     b, tiles = _plan(fg, [rows, rows[:2] + [(b"ACGT" * 5, bytes([30] * 20))]], min_reads=3)
     assert tiles[0]["flags"] >> 8 == 0    # mixed consensus lengths: no hint
 
@@ -177,14 +177,14 @@ def test_planner_rejects_bad_layout(fg):
                                   batch.n_reads, None, 0, C.byref(n))
     assert plan(b) == 0
     bad = fg.pack_source_reads([[(b"ACGTA", bytes([30] * 5))] * 2], 1)
-    bad.reads[1] = ((int(bad.reads[1]) >> 16) + 1) << 16 | 5      # misaligned row
+    bad.reads[1] = ((int(bad.reads[1]) >> 16) + 4) << 16 | 5      # misaligned row
     assert plan(bad) == fg.lib.FGB_ERR_LAYOUT
     bad = fg.pack_source_reads([[(b"ACGTA", bytes([30] * 5))] * 2], 1)
-    bad.units["out_off"][1] += 4                                   # output rows not dense
+    bad.units["out_off"][1] += 8                                   # output rows not dense
     assert plan(bad) == fg.lib.FGB_ERR_LAYOUT
     bad = fg.pack_source_reads([[(b"ACGTA", bytes([30] * 5))] * 2], 1)
     bad.units["cons_len"][0] = 9                                   # longer than any read
-    bad.units["out_off"][1] = 12
+    bad.units["out_off"][1] = 16
     assert plan(bad) == fg.lib.FGB_ERR_LAYOUT
 
 
