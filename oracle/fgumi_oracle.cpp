@@ -365,6 +365,37 @@ void duplex_combine(const uint8_t* a_bases, const uint8_t* a_quals, const uint16
   }
 }
 
+// duplex_caller.rs:838-1015
+int duplex_consensus_arms(const uint8_t* a_bases, const uint8_t* a_quals, const uint16_t* a_depths,
+                          const uint16_t* a_errors, size_t la, const uint8_t* b_bases,
+                          const uint8_t* b_quals, const uint16_t* b_depths,
+                          const uint16_t* b_errors, size_t lb, const SourceRow* source,
+                          size_t n_source, uint8_t* out_bases, uint8_t* out_quals,
+                          uint16_t* out_errors, size_t* out_len) {
+  size_t len = std::min(la, lb);                                        // :846-849
+  bool a_any = false, b_any = false;                                    // :852-853
+  for (size_t i = 0; i < len; ++i) { a_any |= a_depths[i] > 0; b_any |= b_depths[i] > 0; }
+  if (a_any && !b_any) {                                                // :855-868
+    std::copy(a_bases, a_bases + la, out_bases);
+    std::copy(a_quals, a_quals + la, out_quals);
+    std::copy(a_errors, a_errors + la, out_errors);
+    *out_len = la;
+    return 1;
+  }
+  if (!a_any && b_any) {                                                // :869-882
+    std::copy(b_bases, b_bases + lb, out_bases);
+    std::copy(b_quals, b_quals + lb, out_quals);
+    std::copy(b_errors, b_errors + lb, out_errors);
+    *out_len = lb;
+    return 2;
+  }
+  if (!a_any && !b_any) { *out_len = 0; return 3; }                     // :1013
+  duplex_combine(a_bases, a_quals, a_depths, a_errors, b_bases, b_quals, b_depths, b_errors, len,
+                 source, n_source, out_bases, out_quals, out_errors);
+  *out_len = len;
+  return 0;
+}
+
 // ---- codec_caller.rs -----------------------------------------------------------------------
 // codec_caller.rs:1048-1152
 CodecCombineResult codec_combine_padded(const uint8_t* a_bases, const uint8_t* a_quals,
@@ -444,6 +475,82 @@ void codec_mask_quals(const uint8_t* cons_bases, uint8_t* cons_quals, size_t len
         cons_quals[idx] = std::min<uint8_t>(cons_quals[idx], static_cast<uint8_t>(outer_qual));
     }
   }
+}
+
+// fgumi-dna/src/dna.rs:30-40
+uint8_t complement_base(uint8_t b) {
+  switch (b) {
+    case 'A': case 'a': return 'T';
+    case 'T': case 't': return 'A';
+    case 'C': case 'c': return 'G';
+    case 'G': case 'g': return 'C';
+    default: return b;   // 'N' -> 'N', 'n' -> 'n', anything else unchanged
+  }
+}
+
+// codec_caller.rs:507-520
+SsColumns reverse_complement_ss(const SsColumns& ss) {
+  SsColumns o;
+  size_t n = ss.bases.size();
+  o.bases.resize(n); o.quals.resize(n); o.depths.resize(n); o.errors.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    o.bases[i] = complement_base(ss.bases[n - 1 - i]);   // dna.rs:58-60
+    o.quals[i] = ss.quals[n - 1 - i];
+    o.depths[i] = ss.depths[n - 1 - i];
+    o.errors[i] = ss.errors[n - 1 - i];
+  }
+  return o;
+}
+
+// codec_caller.rs:980-1023
+SsColumns pad_consensus(const SsColumns& ss, size_t new_length, bool pad_left) {
+  size_t cur = ss.bases.size();
+  if (new_length <= cur) return ss;
+  size_t pad = new_length - cur;
+  SsColumns o;
+  auto build = [&](auto& dst, const auto& src, auto fill) {
+    dst.reserve(new_length);
+    if (pad_left) dst.insert(dst.end(), pad, fill);
+    dst.insert(dst.end(), src.begin(), src.end());
+    if (!pad_left) dst.insert(dst.end(), pad, fill);
+  };
+  build(o.bases, ss.bases, NO_CALL_BASE_LOWER);
+  build(o.quals, ss.quals, uint8_t(0));
+  build(o.depths, ss.depths, uint16_t(0));
+  build(o.errors, ss.errors, uint16_t(0));
+  return o;
+}
+
+// codec_caller.rs:721-784 (orient, pad, combine with the gate of :1155-1166, mask, re-orient)
+CodecJobResult codec_job(const SsColumns& ss_r1, const SsColumns& ss_r2, bool r1_is_negative,
+                         bool r2_is_negative, size_t consensus_length, int ss_qual, int outer_qual,
+                         size_t outer_len, size_t max_duplex_disagreements,
+                         double max_duplex_disagreement_rate) {
+  CodecJobResult res;
+  SsColumns r1o = r1_is_negative ? reverse_complement_ss(ss_r1) : ss_r1;   // :746-750
+  SsColumns r2o = r1_is_negative ? ss_r2 : reverse_complement_ss(ss_r2);
+  SsColumns p1 = pad_consensus(r1o, consensus_length, r1_is_negative);     // :752-753
+  SsColumns p2 = pad_consensus(r2o, consensus_length, r2_is_negative);
+  size_t len = p1.bases.size();
+  SsColumns c;
+  c.bases.resize(len); c.quals.resize(len); c.depths.resize(len); c.errors.resize(len);
+  CodecCombineResult cr = codec_combine_padded(p1.bases.data(), p1.quals.data(), p1.depths.data(),
+                                               p1.errors.data(), p2.bases.data(), p2.quals.data(),
+                                               p2.depths.data(), p2.errors.data(), len,
+                                               c.bases.data(), c.quals.data(), c.depths.data(),
+                                               c.errors.data());
+  res.duplex_bases_count = cr.duplex_bases_count;
+  res.duplex_disagreements = cr.duplex_disagreements;
+  if (cr.duplex_bases_count > 0) {   // :1155-1166
+    double rate = static_cast<double>(cr.duplex_disagreements) /
+                  static_cast<double>(cr.duplex_bases_count);
+    if (cr.duplex_disagreements > max_duplex_disagreements) res.status = 1;
+    else if (rate > max_duplex_disagreement_rate) res.status = 2;
+  }
+  codec_mask_quals(c.bases.data(), c.quals.data(), len, p1.bases.data(), p2.bases.data(), ss_qual,
+                   outer_qual, outer_len);                                  // :756
+  res.consensus = r1_is_negative ? reverse_complement_ss(c) : c;            // :757-758
+  return res;
 }
 
 }  // namespace fgoracle

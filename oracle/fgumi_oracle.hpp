@@ -105,6 +105,17 @@ void duplex_combine(const uint8_t* a_bases, const uint8_t* a_quals, const uint16
                     const SourceRow* source, size_t n_source, uint8_t* out_bases,
                     uint8_t* out_quals, uint16_t* out_errors);
 
+// All four arms of duplex_consensus (duplex_caller.rs:838-1015): returns 0 = both strands combined
+// (output length min(la, lb)), 1 = AB only (B has no depth inside the truncated region; output is
+// A at its FULL length, :855-868), 2 = BA only (:869-882), 3 = neither (:1013).  *out_len gets the
+// output length.  out_* must hold max(la, lb) elements.
+int duplex_consensus_arms(const uint8_t* a_bases, const uint8_t* a_quals, const uint16_t* a_depths,
+                          const uint16_t* a_errors, size_t la, const uint8_t* b_bases,
+                          const uint8_t* b_quals, const uint16_t* b_depths,
+                          const uint16_t* b_errors, size_t lb, const SourceRow* source,
+                          size_t n_source, uint8_t* out_bases, uint8_t* out_quals,
+                          uint16_t* out_errors, size_t* out_len);
+
 // ---- codec_caller.rs -----------------------------------------------------------------------
 struct CodecCombineResult {
   size_t duplex_bases_count = 0;     // codec_caller.rs:1046
@@ -123,5 +134,30 @@ CodecCombineResult codec_combine_padded(const uint8_t* a_bases, const uint8_t* a
 void codec_mask_quals(const uint8_t* cons_bases, uint8_t* cons_quals, size_t len,
                       const uint8_t* padded_r1_bases, const uint8_t* padded_r2_bases,
                       int ss_qual, int outer_qual, size_t outer_len);
+
+// fgumi-dna/src/dna.rs:30-40 complement_base and :58-60 reverse_complement
+uint8_t complement_base(uint8_t b);
+
+// One single-strand consensus (codec_caller.rs SingleStrandConsensus: bases/quals/depths/errors).
+struct SsColumns {
+  std::vector<uint8_t> bases, quals;
+  std::vector<uint16_t> depths, errors;
+};
+// reverse_complement_ss, codec_caller.rs:507-520
+SsColumns reverse_complement_ss(const SsColumns& ss);
+// pad_consensus, codec_caller.rs:980-1023
+SsColumns pad_consensus(const SsColumns& ss, size_t new_length, bool pad_left);
+
+struct CodecJobResult {
+  SsColumns consensus;            // after masking and final re-orientation
+  size_t duplex_bases_count = 0;
+  size_t duplex_disagreements = 0;
+  int status = 0;                 // 0 ok, 1 "High duplex disagreement" (:1160), 2 "... rate" (:1163)
+};
+// The orient/pad/combine/mask/re-orient tail of consensus_reads_raw, codec_caller.rs:721-784.
+CodecJobResult codec_job(const SsColumns& ss_r1, const SsColumns& ss_r2, bool r1_is_negative,
+                         bool r2_is_negative, size_t consensus_length, int ss_qual, int outer_qual,
+                         size_t outer_len, size_t max_duplex_disagreements,
+                         double max_duplex_disagreement_rate);
 
 }  // namespace fgoracle

@@ -137,6 +137,19 @@ void orc_duplex_combine(const uint8_t* ab, const uint8_t* aq, const uint16_t* ad
   duplex_combine(ab, aq, ad, ae, bb, bq, bd, be, len, src, rows.size(), ob, oq, oe);
 }
 
+int orc_duplex_job(const uint8_t* ab, const uint8_t* aq, const uint16_t* ad, const uint16_t* ae,
+                   size_t la, const uint8_t* bb, const uint8_t* bq, const uint16_t* bd,
+                   const uint16_t* be, size_t lb, const uint8_t* const* src_bases,
+                   const size_t* src_len, long n_source, uint8_t* ob, uint8_t* oq, uint16_t* oe,
+                   size_t* out_len) {
+  std::vector<SourceRow> rows;
+  for (long i = 0; i < n_source; ++i) rows.push_back(SourceRow{src_bases[i], nullptr, src_len[i]});
+  // duplex_caller.rs:2001-2011: `if source_reads.is_empty() { None } else { Some(..) }`
+  const SourceRow* src = rows.empty() ? nullptr : rows.data();
+  return duplex_consensus_arms(ab, aq, ad, ae, la, bb, bq, bd, be, lb, src, rows.size(), ob, oq, oe,
+                               out_len);
+}
+
 // ---- codec combine ---------------------------------------------------------------------------
 void orc_codec_combine(const uint8_t* ab, const uint8_t* aq, const uint16_t* ad,
                        const uint16_t* ae, const uint8_t* bb, const uint8_t* bq,
@@ -152,6 +165,30 @@ void orc_codec_mask(const uint8_t* cons_bases, uint8_t* cons_quals, size_t len,
                     const uint8_t* r1_bases, const uint8_t* r2_bases, int ss_qual, int outer_qual,
                     size_t outer_len) {
   codec_mask_quals(cons_bases, cons_quals, len, r1_bases, r2_bases, ss_qual, outer_qual, outer_len);
+}
+
+// Full CODEC tail for one molecule.  out_* must hold `consensus_length` elements.
+int orc_codec_job(const uint8_t* ab, const uint8_t* aq, const uint16_t* ad, const uint16_t* ae,
+                  size_t la, const uint8_t* bb, const uint8_t* bq, const uint16_t* bd,
+                  const uint16_t* be, size_t lb, int r1_neg, int r2_neg, size_t cons_len,
+                  int ss_qual, int outer_qual, size_t outer_len, size_t max_dis, double max_rate,
+                  uint8_t* ob, uint8_t* oq, uint16_t* od, uint16_t* oe, uint64_t* duplex_bases,
+                  uint64_t* disagreements) {
+  SsColumns a, b;
+  a.bases.assign(ab, ab + la); a.quals.assign(aq, aq + la);
+  a.depths.assign(ad, ad + la); a.errors.assign(ae, ae + la);
+  b.bases.assign(bb, bb + lb); b.quals.assign(bq, bq + lb);
+  b.depths.assign(bd, bd + lb); b.errors.assign(be, be + lb);
+  CodecJobResult r = codec_job(a, b, r1_neg != 0, r2_neg != 0, cons_len, ss_qual, outer_qual,
+                               outer_len, max_dis, max_rate);
+  size_t n = r.consensus.bases.size();
+  std::memcpy(ob, r.consensus.bases.data(), n);
+  std::memcpy(oq, r.consensus.quals.data(), n);
+  std::memcpy(od, r.consensus.depths.data(), n * 2);
+  std::memcpy(oe, r.consensus.errors.data(), n * 2);
+  if (duplex_bases) *duplex_bases = r.duplex_bases_count;
+  if (disagreements) *disagreements = r.duplex_disagreements;
+  return r.status;
 }
 
 }  // extern "C"

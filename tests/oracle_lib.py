@@ -51,6 +51,13 @@ def load():
     lib.orc_codec_combine.restype = None
     lib.orc_codec_mask.argtypes = [vp, vp, C.c_size_t, vp, vp, C.c_int, C.c_int, C.c_size_t]
     lib.orc_codec_mask.restype = None
+    lib.orc_duplex_job.argtypes = ([vp] * 4 + [C.c_size_t] + [vp] * 4 + [C.c_size_t, vp, vp, C.c_long] +
+                                   [vp] * 4)
+    lib.orc_duplex_job.restype = C.c_int
+    lib.orc_codec_job.argtypes = ([vp] * 4 + [C.c_size_t] + [vp] * 4 + [C.c_size_t, C.c_int, C.c_int,
+                                  C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_double] +
+                                  [vp] * 6)
+    lib.orc_codec_job.restype = C.c_int
     _lib = lib
     return lib
 

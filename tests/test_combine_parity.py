@@ -1,0 +1,220 @@
+"""GPU parity of the strand-combine kernels (K2 duplex, K3 CODEC) through the C-ABI against the
+oracle.  Pure integer work: everything must match bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fg():
+    import __graft_entry__ as graft
+    graft.build()
+    import fgumi_b200
+    return fgumi_b200
+
+
+def _family(rng, depth, length, err=0.05, n_rate=0.03, all_n=False, qlo=5, qhi=41):
+    tmpl = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=length)
+    rows = []
+    for _ in range(depth):
+        b = tmpl.copy()
+        m = rng.random(length) < err
+        b[m] = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(m.sum()))
+        q = rng.integers(qlo, qhi + 1, size=length).astype(np.uint8)
+        nm = rng.random(length) < n_rate
+        if all_n:
+            nm[:] = True
+        b[nm] = ord("N")
+        q[nm] = 2
+        rows.append((b.tobytes(), q.tobytes()))
+    return rows, tmpl
+
+
+def _vote(fg, units, min_cons_q):
+    """Single-strand vote on the GPU (device-resident) + the oracle's SS columns."""
+    import torch
+    batch = fg.pack_source_reads(units, 1)
+    eng = fg.Engine(0, 45, 40, 1, min_cons_q)
+    db = fg.DeviceBatch(batch, "cuda:0")
+    ss = fg.DeviceColumns(batch.n_out, "cuda:0")
+    eng.vote_device(db, ss, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ob, oq, od, oe, _ = O.simplex_batch(batch, 45, 40, 1, min_cons_q)
+    g = ss.to_host()
+    n = batch.n_out
+    for sl in batch.unit_slices():
+        assert np.array_equal(g.base[sl], ob[sl]) and np.array_equal(g.qual[sl], oq[sl])
+        assert np.array_equal(g.depth[sl], od[sl]) and np.array_equal(g.errors[sl], oe[sl])
+    return eng, batch, db, ss, (ob, oq, od, oe)
+
+
+def test_duplex_combine_matches_oracle(fg):
+    import torch
+    rng = np.random.default_rng(31)
+    L = O.load()
+    units = []
+    n_mol = 300
+    for m in range(n_mol):
+        # AB-R1, AB-R2, BA-R1, BA-R2 single-strand families; a few strands carry no coverage at all
+        for k in range(4):
+            depth = int(rng.integers(1, 6))
+            length = int(rng.integers(20, 90))
+            dead = (m % 17 == 3 and k >= 2) or (m % 23 == 5 and k < 2) or (m % 29 == 7)
+            rows, _ = _family(rng, depth, length, all_n=dead)
+            units.append(rows)
+    eng, batch, db, ss, (ob, oq, od, oe) = _vote(fg, units, 2)
+    cons_len = batch.units["cons_len"]
+    out_off = batch.units["out_off"]
+    # duplex R1 = AB-R1 (+) BA-R2, duplex R2 = AB-R2 (+) BA-R1   (duplex_caller.rs:1999-2012)
+    pairs = []
+    for m in range(n_mol):
+        pairs.append((4 * m + 0, 4 * m + 3))
+        pairs.append((4 * m + 1, 4 * m + 2))
+    jobs = np.zeros(len(pairs), dtype=fg.DUPLEX_JOB_DTYPE)
+    off = 0
+    for j, (ua, ub) in enumerate(pairs):
+        jobs[j] = (ua, ub, off)
+        off += (max(int(cons_len[ua]), int(cons_len[ub])) + 7) // 8 * 8
+    n_out = max(off, 8)
+    dev = "cuda:0"
+    tj = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(dev)
+    o_base = torch.zeros(n_out, dtype=torch.uint8, device=dev)
+    o_qual = torch.zeros(n_out, dtype=torch.uint8, device=dev)
+    o_err = torch.zeros(n_out, dtype=torch.int16, device=dev)
+    o_st = torch.full((len(pairs),), 255, dtype=torch.uint8, device=dev)
+    eng.duplex_combine_device(db, ss, tj, len(pairs), o_base, o_qual, o_err, o_st,
+                              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    gb, gq = o_base.cpu().numpy(), o_qual.cpu().numpy()
+    ge, gs = o_err.cpu().numpy().view(np.uint16), o_st.cpu().numpy()
+    assert eng.stats()["combined_jobs"] == len(pairs)
+    eng.close()
+    seen = set()
+    for j, (ua, ub) in enumerate(pairs):
+        la, lb = int(cons_len[ua]), int(cons_len[ub])
+        oa, obo = int(out_off[ua]), int(out_off[ub])
+        rows = units[ua] + units[ub]
+        keep = [np.frombuffer(r[0], np.uint8).copy() for r in rows]
+        ptrs = (C.c_void_p * len(rows))(*[k.ctypes.data for k in keep])
+        lens = (C.c_size_t * len(rows))(*[len(r[0]) for r in rows])
+        cap = max(la, lb, 1)
+        rb = np.zeros(cap, np.uint8); rq = np.zeros(cap, np.uint8); re_ = np.zeros(cap, np.uint16)
+        olen = C.c_size_t()
+        st = L.orc_duplex_job(ob[oa:].ctypes.data, oq[oa:].ctypes.data, od[oa:].ctypes.data,
+                              oe[oa:].ctypes.data, la, ob[obo:].ctypes.data, oq[obo:].ctypes.data,
+                              od[obo:].ctypes.data, oe[obo:].ctypes.data, lb, ptrs, lens, len(rows),
+                              rb.ctypes.data, rq.ctypes.data, re_.ctypes.data, C.addressof(olen))
+        seen.add(st)
+        assert gs[j] == st, (j, gs[j], st)
+        o = int(jobs[j]["out_off"]); n = olen.value
+        assert np.array_equal(gb[o:o + n], rb[:n]), j
+        assert np.array_equal(gq[o:o + n], rq[:n]), j
+        assert np.array_equal(ge[o:o + n], re_[:n]), j
+    assert seen == {0, 1, 2, 3}     # every arm of duplex_consensus was exercised
+
+
+def test_duplex_known_answers(fg):
+    """duplex_caller.rs:2494-2575 through the GPU: single-read strands with min_consensus_base_quality
+    0 keep (base, LUT[q]); the KAT vectors use the raw combine rule, so feed quals whose LUT image is
+    the wanted value."""
+    import torch
+    sq = O.tables(45, 40)[3]
+    inv = {int(v): q for q, v in enumerate(sq)}          # LUT[q] -> q (any preimage)
+    want = [20, 30, 37, 38]
+    qa = bytes(inv[v] for v in want)
+    units = [[(b"ACGT", qa)], [(b"ACGT", qa)], [(b"TGCA", bytes(inv[v] for v in (10, 15, 20, 25)))],
+             [(b"TGCA", qa)]]
+    eng, batch, db, ss, (ob, oq, od, oe) = _vote(fg, units, 0)
+    jobs = np.zeros(3, dtype=fg.DUPLEX_JOB_DTYPE)
+    jobs[0] = (0, 1, 0); jobs[1] = (0, 2, 8); jobs[2] = (0, 3, 16)
+    dev = "cuda:0"
+    tj = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(dev)
+    o_base = torch.zeros(24, dtype=torch.uint8, device=dev)
+    o_qual = torch.zeros(24, dtype=torch.uint8, device=dev)
+    o_err = torch.zeros(24, dtype=torch.int16, device=dev)
+    eng.duplex_combine_device(db, ss, tj, 3, o_base, o_qual, o_err, None,
+                              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    eng.close()
+    gb, gq = o_base.cpu().numpy(), o_qual.cpu().numpy()
+    assert bytes(gb[0:4]) == b"ACGT" and list(gq[0:4]) == [min(93, 2 * v) for v in want]   # agreement
+    assert bytes(gb[8:12]) == b"ACGT" and list(gq[8:12]) == [10, 15, 17, 13]              # higher wins
+    assert bytes(gb[16:20]) == b"NNNN" and list(gq[16:20]) == [2, 2, 2, 2]                # equal quals
+
+
+def test_codec_combine_matches_oracle(fg):
+    import torch
+    rng = np.random.default_rng(41)
+    L = O.load()
+    units, meta = [], []
+    n_mol = 400
+    for m in range(n_mol):
+        k = int(rng.integers(1, 7))
+        l1, l2 = int(rng.integers(12, 70)), int(rng.integers(12, 70))
+        err = 0.3 if m % 11 == 4 else 0.04          # some molecules trip the disagreement gates
+        r1, t1 = _family(rng, k, l1, err=err)
+        # R2 shares sequence context with R1 (reverse complement of an overlapping window)
+        r2, _ = _family(rng, k, l2, err=err)
+        units += [r1, r2]
+        cons_length = max(l1, l2) + int(rng.integers(0, 30))
+        meta.append((bool(rng.integers(0, 2)), cons_length))
+    eng, batch, db, ss, (ob, oq, od, oe) = _vote(fg, units, 0)
+    cons_len = batch.units["cons_len"]; out_off = batch.units["out_off"]
+    jobs = np.zeros(n_mol, dtype=fg.CODEC_JOB_DTYPE)
+    off = 0
+    for m, (r1_neg, clen) in enumerate(meta):
+        la, lb = int(cons_len[2 * m]), int(cons_len[2 * m + 1])
+        r2_neg = not r1_neg                       # FR pair
+        jobs[m]["unit_a"] = 2 * m; jobs[m]["unit_b"] = 2 * m + 1
+        jobs[m]["out_off"] = off; jobs[m]["len"] = clen
+        jobs[m]["rc_a"] = r1_neg; jobs[m]["rc_b"] = not r1_neg; jobs[m]["rc_out"] = r1_neg
+        jobs[m]["pad_a_left"] = clen - la if r1_neg else 0       # pad_consensus(.., r1_is_negative)
+        jobs[m]["pad_b_left"] = clen - lb if r2_neg else 0
+        off += (clen + 7) // 8 * 8
+    for ss_q, outer_q, outer_len, max_dis, max_rate in ((-1, -1, 0, 1 << 30, 1.0), (10, 5, 7, 6, 0.2)):
+        dev = "cuda:0"
+        tj = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(dev)
+        out = fg.DeviceColumns(off, dev)
+        st = torch.full((n_mol,), 255, dtype=torch.uint8, device=dev)
+        dis = torch.zeros(n_mol, dtype=torch.int32, device=dev)
+        dup = torch.zeros(n_mol, dtype=torch.int32, device=dev)
+        cp = fg.lib.FgbCodecParams(ss_q, outer_q, outer_len, min(max_dis, 0xFFFFFFFF), max_rate)
+        eng.stats_reset()
+        eng.codec_combine_device(db, ss, tj, n_mol, cp, out, st, dis, dup,
+                                 torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        g = out.to_host()
+        gs, gdis, gdup = st.cpu().numpy(), dis.cpu().numpy(), dup.cpu().numpy()
+        tot_dup = tot_dis = 0
+        statuses = set()
+        for m, (r1_neg, clen) in enumerate(meta):
+            ua, ub = 2 * m, 2 * m + 1
+            la, lb = int(cons_len[ua]), int(cons_len[ub]); oa, obo = int(out_off[ua]), int(out_off[ub])
+            rb = np.zeros(clen, np.uint8); rq = np.zeros(clen, np.uint8)
+            rd = np.zeros(clen, np.uint16); re_ = np.zeros(clen, np.uint16)
+            nb, nd = C.c_uint64(), C.c_uint64()
+            rs = L.orc_codec_job(ob[oa:].ctypes.data, oq[oa:].ctypes.data, od[oa:].ctypes.data,
+                                 oe[oa:].ctypes.data, la, ob[obo:].ctypes.data, oq[obo:].ctypes.data,
+                                 od[obo:].ctypes.data, oe[obo:].ctypes.data, lb, int(r1_neg),
+                                 int(not r1_neg), clen, ss_q, outer_q, outer_len,
+                                 min(max_dis, 2 ** 62), max_rate, rb.ctypes.data, rq.ctypes.data,
+                                 rd.ctypes.data, re_.ctypes.data, C.addressof(nb), C.addressof(nd))
+            o = int(jobs[m]["out_off"])
+            assert gs[m] == rs, m
+            assert gdis[m] == nd.value and gdup[m] == nb.value, m
+            assert np.array_equal(g.base[o:o + clen], rb), m
+            assert np.array_equal(g.qual[o:o + clen], rq), m
+            assert np.array_equal(g.depth[o:o + clen], rd), m
+            assert np.array_equal(g.errors[o:o + clen], re_), m
+            tot_dup += nb.value; tot_dis += nd.value
+            statuses.add(rs)
+        s = eng.stats()
+        assert s["duplex_bases"] == tot_dup and s["duplex_disagreements"] == tot_dis
+        if max_dis < 100:
+            assert statuses == {0, 1, 2}
+    eng.close()
