@@ -78,7 +78,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -115,18 +115,24 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(mhz)}
 
 
-def cpu_oracle_rate(n_units: int, threads: int, seed: int = 1234):
+def cpu_oracle_rate(n_units: int, threads: int, seed: int = 1234, min_seconds: float = 10.0):
     """Times the CPU oracle (TEST INFRASTRUCTURE used only as the measured baseline) on a sample."""
     import fgumi_b200 as fg
     from fgumi_b200 import synth
     from tests import oracle_lib as O
     b, q = synth.host_pileup(n_units, DEPTH, READ_LEN, ERR, seed=seed)
     batch = fg.pack_uniform(b, q, 1)
-    O.simplex_batch(batch, 45, 40, 1, 2, threads)          # warm (page faults, thread start)
-    t = time.perf_counter()
-    O.simplex_batch(batch, 45, 40, 1, 2, threads)
-    dt = time.perf_counter() - t
-    return n_units / dt, dt
+    outs = O.alloc_outputs(batch)
+    O.simplex_batch(batch, 45, 40, 1, 2, threads, outs)    # warm (page faults, thread start)
+    O.simplex_batch(batch, 45, 40, 1, 2, threads, outs)
+    reps, t = 0, time.perf_counter()
+    while True:                                            # ~10 s of CPU work
+        O.simplex_batch(batch, 45, 40, 1, 2, threads, outs)
+        reps += 1
+        dt = time.perf_counter() - t
+        if dt >= min_seconds or reps >= 2000:
+            break
+    return n_units * reps / dt, dt, reps
 
 
 def run_reference(args):
@@ -134,17 +140,18 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = int(os.environ.get("FGB_REF_SAMPLE_UNITS", "200000"))
+    n = int(os.environ.get("FGB_REF_SAMPLE_UNITS", "400000"))
     import fgumi_b200 as fg
     from fgumi_b200 import synth
     from tests import oracle_lib as O
     b, q = synth.host_pileup(n, DEPTH, READ_LEN, ERR, seed=1234)
     batch = fg.pack_uniform(b, q, 1)
+    outs = O.alloc_outputs(batch)
     for _ in range(args.warmup):
-        O.simplex_batch(batch, 45, 40, 1, 2, threads)
+        O.simplex_batch(batch, 45, 40, 1, 2, threads, outs)
     t = time.perf_counter()
     for _ in range(args.steps):
-        O.simplex_batch(batch, 45, 40, 1, 2, threads)
+        O.simplex_batch(batch, 45, 40, 1, 2, threads, outs)
     dt = time.perf_counter() - t
     v = n * args.steps / dt
     sample = f"{n} families depth {DEPTH} x {READ_LEN} bp per step (same generator as the GPU arm)"
@@ -166,7 +173,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fgumi_b200", choices=["fgumi_b200", "reference"])
     ap.add_argument("--units", type=int, default=int(os.environ.get("FGB_BENCH_UNITS", "10000000")),
@@ -229,6 +236,7 @@ def main():
     clk.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    torch.cuda.nvtx.range_push("fgb_timed")
     ev[0].record()
     for i in range(args.steps):
         step()
@@ -242,6 +250,7 @@ def main():
         ctr = torch.as_tensor(_DevPtr(), device=dev)
         dist.all_reduce(ctr, op=dist.ReduceOp.SUM)
     barrier()
+    torch.cuda.nvtx.range_pop()
     clocks = clk.stop()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
@@ -290,9 +299,11 @@ def main():
         barrier()
         t0 = time.perf_counter()
         esteps = max(3, min(args.steps, 10))
+        torch.cuda.nvtx.range_push("fgb_e2e")
         for _ in range(esteps):
             eng.submit(hb, ho); eng.wait()
         torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
@@ -306,9 +317,9 @@ def main():
 
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
-        v, dtc = cpu_oracle_rate(args.cpu_units, threads)
+        v, dtc, reps = cpu_oracle_rate(args.cpu_units, threads)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_units} families depth {DEPTH} x {READ_LEN} bp, {dtc:.1f} s; "
+               "sample": f"{reps} passes over {args.cpu_units} families depth {DEPTH} x {READ_LEN} bp, {dtc:.1f} s; "
                          "oracle = C++ restatement of fgumi 0.2.0 (no Rust toolchain), "
                          "std::thread over families"}
 

@@ -82,13 +82,17 @@ def tables(pre, post):
     return c, e, lp.value, sq
 
 
-def simplex_batch(batch, pre=45, post=40, min_reads=1, min_cons_q=2, threads=1):
-    """Run the oracle over a PackedBatch; returns (base, qual, depth, errors, cons_len)."""
-    lib = load()
+def alloc_outputs(batch):
     n = max(batch.n_out, 1)
-    ob = np.zeros(n, np.uint8); oq = np.zeros(n, np.uint8)
-    od = np.zeros(n, np.uint16); oe = np.zeros(n, np.uint16)
-    cl = np.zeros(max(batch.n_units, 1), np.uint32)
+    return (np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint16),
+            np.zeros(n, np.uint16), np.zeros(max(batch.n_units, 1), np.uint32))
+
+
+def simplex_batch(batch, pre=45, post=40, min_reads=1, min_cons_q=2, threads=1, outputs=None):
+    """Run the oracle over a PackedBatch; returns (base, qual, depth, errors, cons_len).
+    Pass `outputs=alloc_outputs(batch)` to reuse buffers (timing runs)."""
+    lib = load()
+    ob, oq, od, oe, cl = outputs if outputs is not None else alloc_outputs(batch)
     rc = lib.orc_simplex_batch(batch.n_units, batch.units.ctypes.data, batch.reads.ctypes.data,
                                batch.bases.ctypes.data, batch.quals.ctypes.data, pre, post,
                                min_reads, min_cons_q, ob.ctypes.data, oq.ctypes.data,
