@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfgumi_b200.so")
-SOURCES = ["capi.cu", "host_tables.cpp"]
+SOURCES = ["capi.cu", "host_tables.cpp", "host/vanilla_host.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # no FMA contraction anywhere near the f64 vote (DESIGN.md numerics)
@@ -24,7 +24,7 @@ def _newer(target: str, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps = [os.path.join(dp, f) for dp, _, fs in os.walk(CSRC) for f in fs]
     deps.append(os.path.join(HERE, "..", "include", "fgumi_b200.h"))
     if not force and _newer(OUT, deps):
         return OUT

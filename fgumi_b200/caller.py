@@ -1,0 +1,95 @@
+"""Record-level callers over the C-ABI (fgb_caller_*): the host-side mirror of fgumi's
+`ConsensusCaller` implementations.  Same names and option meaning as the reference
+(crates/fgumi-consensus/src/vanilla_caller.rs:284-341, caller.rs:205-234); groups are queued and
+voted in one GPU batch by `flush()`."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Sequence, Tuple
+
+import numpy as np
+
+from . import lib as _l
+from .engine import VanillaUmiConsensusOptions
+
+
+class ConsensusOutput:
+    """caller.rs:173-178: concatenated `[u32 block_size][BAM record]` bytes + record count."""
+
+    def __init__(self, data: bytes = b"", count: int = 0):
+        self.data, self.count = data, count
+
+
+class VanillaUmiConsensusCaller:
+    """vanilla_caller.rs:344-455 (new) / :1477-1499 (consensus_reads), batched."""
+
+    def __init__(self, read_name_prefix: str, read_group_id: str,
+                 options: VanillaUmiConsensusOptions = VanillaUmiConsensusOptions(), device: int = 0,
+                 tag: bytes = b"MI", cell_tag: bytes = b""):
+        self._lib = _l.load()
+        self._prefix = read_name_prefix.encode()
+        self._rg = read_group_id.encode()
+        o = _l.FgbCallerOptions()
+        o.mode = 0
+        o.error_rate_pre_umi = options.error_rate_pre_umi
+        o.error_rate_post_umi = options.error_rate_post_umi
+        o.min_input_base_quality = options.min_input_base_quality
+        o.min_consensus_base_quality = options.min_consensus_base_quality
+        o.produce_per_base_tags = 1 if options.produce_per_base_tags else 0
+        o.trim = 1 if options.trim else 0
+        o.min_reads = options.min_reads
+        o.tag = tag
+        o.cell_tag = cell_tag if cell_tag else b"\0\0"
+        o.read_name_prefix = self._prefix
+        o.read_group_id = self._rg
+        self._h = C.c_void_p()
+        st = self._lib.fgb_caller_create(device, C.byref(o), C.byref(self._h))
+        if st != _l.FGB_OK:
+            self._h = C.c_void_p()
+            raise _l.FgbError(st, "fgb_caller_create")
+
+    def close(self):
+        if self._h:
+            self._lib.fgb_caller_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int, where: str):
+        if st != _l.FGB_OK:
+            buf = C.create_string_buffer(512)
+            self._lib.fgb_caller_last_error(self._h, buf, 512)
+            raise _l.FgbError(st, where, buf.value.decode(errors="replace"))
+
+    def add_group(self, records: Sequence[bytes]):
+        """Queue one MI group (raw BAM records without the block_size prefix)."""
+        if not records:
+            return
+        blob = b"".join(records)
+        off = np.zeros(len(records) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(r) for r in records])
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        self._check(self._lib.fgb_caller_add_group(self._h, buf.ctypes.data, off.ctypes.data, len(records)),
+                    "fgb_caller_add_group")
+
+    def flush(self) -> ConsensusOutput:
+        data, n, cnt = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.fgb_caller_flush(self._h, C.byref(data), C.byref(n), C.byref(cnt)),
+                    "fgb_caller_flush")
+        raw = C.string_at(data.value, n.value) if n.value else b""
+        return ConsensusOutput(raw, int(cnt.value))
+
+    def consensus_reads_batch(self, groups: Iterable[Sequence[bytes]]) -> ConsensusOutput:
+        for g in groups:
+            self.add_group(g)
+        return self.flush()
+
+    def statistics(self) -> Dict[str, int]:
+        arr = (C.c_uint64 * _l.FGB_NSTATS)()
+        self._check(self._lib.fgb_caller_stats(self._h, arr), "fgb_caller_stats")
+        d = dict(zip(_l.STAT_NAMES, [int(x) for x in arr]))
+        return d

@@ -5,6 +5,7 @@
 // phred.rs:66-346.  Evaluated once per handle with the host libm in f64, so the table bits are the
 // ones the reference's callers hold; the device only ever adds/subtracts these values.
 #include "host_tables.h"
+#include "host_math.h"
 
 #include <cfloat>
 #include <cmath>
@@ -12,47 +13,7 @@
 #include <limits>
 
 namespace fgb {
-namespace {
-
-constexpr double kLn10 = 2.302585092994046;
-constexpr double kLn2 = 0.6931471805599453;
-constexpr double kLnFourThirds = 0.2876820724517809;
-const double kNegInf = -std::numeric_limits<double>::infinity();
-
-inline double ln_err_of_phred(unsigned q) { return -static_cast<double>(q) * kLn10 / 10.0; }  // phred.rs:66
-
-inline double softplus(double x) {  // log(1+e^x), phred.rs:148-158
-  if (x <= -37.0) return std::exp(x);
-  if (x <= 18.0) return std::log1p(std::exp(x));
-  if (x <= 33.3) return x + std::exp(-x);
-  return x;
-}
-
-inline double ln_1m_exp(double x) {  // log(1-e^x), phred.rs:168-182
-  if (x >= 0.0) return kNegInf;
-  return x >= -kLn2 ? std::log(-std::expm1(x)) : std::log1p(-std::exp(x));
-}
-
-inline double ln_add(double a, double b) {  // phred.rs:274-285
-  if (std::isinf(a) && a < 0.0) return b;
-  if (std::isinf(b) && b < 0.0) return a;
-  double lo = b < a ? b : a, hi = b < a ? a : b;
-  return lo + softplus(hi - lo);
-}
-
-inline double ln_sub(double a, double b) {  // phred.rs:188-198
-  if (std::isinf(b) && b < 0.0) return a;
-  if (std::fabs(a - b) < DBL_EPSILON) return kNegInf;
-  return a + ln_1m_exp(b - a);
-}
-
-inline double two_trials(double p, double r) {  // phred.rs:231-251
-  double hi = p < r ? r : p, lo = p < r ? p : r;
-  if (hi - lo >= 6.0) return hi;
-  return ln_sub(ln_add(hi, lo), kLnFourThirds + hi + lo);
-}
-
-}  // namespace
+using namespace hostmath;
 
 unsigned host_ln_prob_to_phred(double ln_prob) {  // phred.rs:119-135
   const double max_as_ln = -93.0 * kLn10 / 10.0;

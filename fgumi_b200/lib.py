@@ -112,6 +112,22 @@ class FgbCodecParams(C.Structure):
     ]
 
 
+class FgbCallerOptions(C.Structure):
+    _fields_ = [
+        ("mode", C.c_uint8), ("error_rate_pre_umi", C.c_uint8), ("error_rate_post_umi", C.c_uint8),
+        ("min_input_base_quality", C.c_uint8), ("min_consensus_base_quality", C.c_uint8),
+        ("produce_per_base_tags", C.c_uint8), ("trim", C.c_uint8), ("reserved0", C.c_uint8),
+        ("min_reads", C.c_uint32), ("tag", C.c_char * 2), ("cell_tag", C.c_char * 2),
+        ("read_name_prefix", C.c_char_p), ("read_group_id", C.c_char_p),
+    ]
+
+
+FGB_NSTATS = 16
+STAT_NAMES = ("total_reads", "consensus_reads", "filtered_reads", "InsufficientReads",
+              "SecondaryOrSupplementary", "ZeroLengthAfterTrimming", "MinorityAlignment",
+              "OrphanConsensus")
+
+
 class FgbCodecOut(C.Structure):
     _fields_ = [("cols", FgbColumns), ("status", C.c_void_p), ("disagreements", C.c_void_p),
                 ("duplex_bases", C.c_void_p)]
@@ -124,6 +140,8 @@ SYMBOLS = (
     "fgb_plan_tiles", "fgb_vote_device", "fgb_submit", "fgb_wait", "fgb_host_alloc",
     "fgb_host_free", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
+    "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
+    "fgb_caller_flush", "fgb_caller_stats",
 )
 
 _lib = None
@@ -198,5 +216,17 @@ def load() -> C.CDLL:
     lib.fgb_stats_reset.restype = C.c_int32
     lib.fgb_launch_count.argtypes = [vp]
     lib.fgb_launch_count.restype = u64
+    lib.fgb_caller_create.argtypes = [C.c_int, C.POINTER(FgbCallerOptions), C.POINTER(vp)]
+    lib.fgb_caller_create.restype = C.c_int32
+    lib.fgb_caller_destroy.argtypes = [vp]
+    lib.fgb_caller_destroy.restype = None
+    lib.fgb_caller_last_error.argtypes = [vp, C.c_char_p, C.c_size_t]
+    lib.fgb_caller_last_error.restype = C.c_size_t
+    lib.fgb_caller_add_group.argtypes = [vp, vp, vp, u32]
+    lib.fgb_caller_add_group.restype = C.c_int32
+    lib.fgb_caller_flush.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+    lib.fgb_caller_flush.restype = C.c_int32
+    lib.fgb_caller_stats.argtypes = [vp, C.POINTER(u64)]
+    lib.fgb_caller_stats.restype = C.c_int32
     _lib = lib
     return lib

@@ -61,7 +61,8 @@ enum {
   FGB_ERR_LAYOUT = 4,        /* batch violates the layout rules above (alignment, ranges)     */
   FGB_ERR_UNIT_TOO_LARGE = 5,/* a single unit exceeds fgb_tile_capacity_bytes()               */
   FGB_ERR_NOMEM = 6,
-  FGB_ERR_BUSY = 7           /* fgb_submit while a previous submit has not been waited on     */
+  FGB_ERR_BUSY = 7,          /* fgb_submit while a previous submit has not been waited on     */
+  FGB_ERR_MISSING_TAG = 8    /* first record of a group lacks the UMI tag (vanilla_caller.rs:1493) */
 };
 
 typedef struct fgb_handle fgb_handle;   /* one per GPU; thread-compatible, not thread-safe    */
@@ -277,6 +278,56 @@ fgb_status fgb_stats_device_ptr(fgb_handle* h, uint64_t** dev_counters);
 fgb_status fgb_stats_reset(fgb_handle* h);
 /* Number of kernel launches this handle has enqueued (for bench.py's gpu_launches). */
 uint64_t fgb_launch_count(const fgb_handle* h);
+
+/* ---- record-level caller: the ConsensusCaller boundary itself --------------------------- */
+/* Mirrors `trait ConsensusCaller` (caller.rs:205-234) for batches of MI groups: raw BAM records in,
+ * a ConsensusOutput byte stream (`[u32 LE block_size][BAM record]...`, caller.rs:173-178) out.
+ * The host side does what the reference's caller does around the vote (filtering, sub-grouping,
+ * mate-overlap clip, source-read preparation, CIGAR filter, min-reads / orphan rules, record and
+ * tag assembly, RX consensus, statistics); the vote itself runs on the GPU through fgb_submit. */
+enum { FGB_MODE_SIMPLEX = 0, FGB_MODE_DUPLEX = 1, FGB_MODE_CODEC = 2 };
+
+typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanilla_caller.rs:284-341 */
+  uint8_t mode;                            /* FGB_MODE_*                                           */
+  uint8_t error_rate_pre_umi;              /* 45 */
+  uint8_t error_rate_post_umi;             /* 40 */
+  uint8_t min_input_base_quality;          /* 10 */
+  uint8_t min_consensus_base_quality;      /* 40 (library) / 2 (CLI)                               */
+  uint8_t produce_per_base_tags;           /* 1  */
+  uint8_t trim;                            /* 0  */
+  uint8_t reserved0;
+  uint32_t min_reads;                      /* 2 (library default); CLI: required -M                */
+  char tag[2];                             /* UMI tag, "MI"                                        */
+  char cell_tag[2];                        /* {0,0} = none                                         */
+  const char* read_name_prefix;            /* consensus read name = "<prefix>:<MI>"                */
+  const char* read_group_id;               /* RG tag value                                         */
+} fgb_caller_options;
+
+enum {   /* ConsensusCallingStats (caller.rs:238-286) as a flat counter array                      */
+  FGB_STAT_TOTAL_READS = 0,
+  FGB_STAT_CONSENSUS_READS = 1,
+  FGB_STAT_FILTERED_READS = 2,
+  FGB_STAT_REJ_INSUFFICIENT_READS = 3,        /* RejectionReason::InsufficientReads              */
+  FGB_STAT_REJ_SECONDARY_SUPPLEMENTARY = 4,   /* ::SecondaryOrSupplementary                      */
+  FGB_STAT_REJ_ZERO_LENGTH = 5,               /* ::ZeroLengthAfterTrimming                       */
+  FGB_STAT_REJ_MINORITY_ALIGNMENT = 6,        /* ::MinorityAlignment                             */
+  FGB_STAT_REJ_ORPHAN_CONSENSUS = 7,          /* ::OrphanConsensus                               */
+  FGB_NSTATS = 16
+};
+
+typedef struct fgb_caller fgb_caller;
+fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_caller** out);
+void fgb_caller_destroy(fgb_caller* c);
+size_t fgb_caller_last_error(const fgb_caller* c, char* buf, size_t buf_len);
+/* consensus_reads() for one MI group: `records` holds n_records raw BAM records (no block_size
+ * prefix) back to back, record i spanning [rec_off[i], rec_off[i+1]).  Groups are queued. */
+fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
+                                uint32_t n_records);
+/* Votes everything queued (one fgb_submit) and returns the concatenated ConsensusOutput of all
+ * groups in input order.  *out_data stays valid until the next flush / destroy. */
+fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* out_len,
+                            uint64_t* out_count);
+fgb_status fgb_caller_stats(const fgb_caller* c, uint64_t stats[FGB_NSTATS]);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,614 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+Record-level restatement (pure Python, small cases only) of the HOST side of fgumi's consensus
+callers: raw BAM record decoding, source-read preparation, CIGAR grouping, the group / orphan rules
+and consensus-record assembly.  The per-position vote itself is delegated to the C++ oracle
+(oracle/liboracle.so).  Only tests/ may import this.  Citations are relative to /root/reference/.
+
+Parity status: the reference has no golden outputs and cannot be built here, so byte-level parity
+with the fgumi binary is "parity unpinned"; this file is checked against the reference's own
+known-answer unit tests where they exist (tests/test_record_oracle_kat.py).
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# ---- fgumi-raw-bam/src/fields.rs:240-265 -------------------------------------------------------
+PAIRED, PROPER_PAIR, UNMAPPED, MATE_UNMAPPED = 0x1, 0x2, 0x4, 0x8
+REVERSE, MATE_REVERSE, FIRST_SEGMENT, LAST_SEGMENT = 0x10, 0x20, 0x40, 0x80
+SECONDARY, QC_FAIL, DUPLICATE, SUPPLEMENTARY = 0x100, 0x200, 0x400, 0x800
+
+BAM_BASE_TO_ASCII = b"=ACMGRSVTWYHKDBN"            # sequence.rs:9-11
+SEQ_CODES = [15] * 256                              # sequence.rs:18-35
+for _i, _b in enumerate(BAM_BASE_TO_ASCII):
+    SEQ_CODES[_b] = _i
+    SEQ_CODES[ord(chr(_b).lower())] = _i
+
+# ops: 0 M,1 I,2 D,3 N,4 S,5 H,6 P,7 =,8 X ; cigar.rs:50-70 (BAM_CIGAR_TYPE = 0x3C1A7)
+def consumes_query(op: int) -> bool:
+    return (0x3C1A7 >> ((op & 0xF) << 1)) & 1 != 0
+
+
+def consumes_ref(op: int) -> bool:
+    return (0x3C1A7 >> ((op & 0xF) << 1)) & 2 != 0
+
+
+class Rec:
+    """RawRecordView, fgumi-raw-bam/src/fields.rs:6-23 + accessors."""
+
+    def __init__(self, b: bytes):
+        self.b = bytes(b)
+        (self.ref_id, self.pos, self.l_read_name, self.mapq, self.bin, self.n_cigar, self.flags,
+         self.l_seq, self.mate_ref_id, self.mate_pos, self.tlen) = struct.unpack_from("<iiBBHHHIiii", self.b, 0)
+
+    @property
+    def name(self) -> bytes:                         # fields.rs:393-396
+        l = self.l_read_name
+        return self.b[32:32 + l - 1] if l > 1 else b""
+
+    def cigar_ops(self) -> List[int]:                # cigar.rs:82-101
+        if self.n_cigar == 0:
+            return []
+        s = 32 + self.l_read_name
+        e = s + 4 * self.n_cigar
+        if e > len(self.b):
+            return []
+        return list(struct.unpack_from("<%dI" % self.n_cigar, self.b, s))
+
+    def seq_offset(self) -> int:                     # fields.rs:488-492
+        return 32 + self.l_read_name + 4 * self.n_cigar
+
+    def sequence(self) -> bytearray:                 # sequence.rs:148-173 (scalar semantics)
+        off = self.seq_offset()
+        out = bytearray(self.l_seq)
+        for i in range(self.l_seq):
+            byte = self.b[off + i // 2]
+            out[i] = BAM_BASE_TO_ASCII[byte >> 4 if i % 2 == 0 else byte & 0xF]
+        return out
+
+    def quals(self) -> bytearray:                    # fields.rs:497-502
+        off = self.seq_offset() + (self.l_seq + 1) // 2
+        return bytearray(self.b[off:off + self.l_seq])
+
+    def aux(self) -> bytes:                          # fields.rs:449-483
+        off = 32 + self.l_read_name + 4 * self.n_cigar + (self.l_seq + 1) // 2 + self.l_seq
+        return self.b[off:] if off <= len(self.b) else b""
+
+    def find_string(self, tag: bytes) -> Optional[bytes]:   # tags.rs:13-48
+        aux = self.aux()
+        p = 0
+        fixed = {ord("A"): 1, ord("c"): 1, ord("C"): 1, ord("s"): 2, ord("S"): 2, ord("i"): 4,
+                 ord("I"): 4, ord("f"): 4}
+        while p + 3 <= len(aux):
+            t, vt = aux[p:p + 2], aux[p + 2]
+            if t == tag:
+                if vt != ord("Z"):
+                    return None
+                end = aux.find(b"\0", p + 3)
+                return None if end < 0 else aux[p + 3:end]
+            if vt in fixed:
+                size = fixed[vt]
+            elif vt in (ord("Z"), ord("H")):
+                end = aux.find(b"\0", p + 3)
+                if end < 0:
+                    break
+                size = end - (p + 3) + 1
+            elif vt == ord("B"):
+                if len(aux) - (p + 3) < 5:
+                    break
+                es = fixed.get(aux[p + 3], 0)
+                if es == 0:
+                    break
+                size = 5 + struct.unpack_from("<I", aux, p + 4)[0] * es
+            else:
+                break
+            p += 3 + size
+        return None
+
+
+# ---- cigar helpers -----------------------------------------------------------------------------
+def reference_length(ops: Sequence[int]) -> int:      # cigar.rs:137-150
+    return sum(op >> 4 for op in ops if consumes_ref(op & 0xF))
+
+
+def simplify_cigar(ops: Sequence[int]) -> List[Tuple[int, int]]:   # noodles_compat.rs:10-55
+    out: List[Tuple[int, int]] = []
+    for raw in ops:
+        ln, t = raw >> 4, raw & 0xF
+        if t > 8:
+            continue
+        kind = 0 if t in (4, 7, 8, 5) else t          # S, =, X, H -> M
+        if out and out[-1][0] == kind:
+            out[-1] = (kind, out[-1][1] + ln)
+        else:
+            out.append((kind, ln))
+    return out
+
+
+def is_cigar_prefix(a, b) -> bool:                    # fgumi-sam clipper.rs:2425-2448
+    if len(a) > len(b):
+        return False
+    last = max(len(a) - 1, 0)
+    for i, (op_a, len_a) in enumerate(a):
+        op_b, len_b = b[i]
+        if op_a != op_b:
+            return False
+        if i == last:
+            if len_a > len_b:
+                return False
+        elif len_a != len_b:
+            return False
+    return True
+
+
+def _parse_leading_clips(cigar: str) -> int:          # cigar.rs:514-536
+    clipped, num_start = 0, 0
+    for i, c in enumerate(cigar):
+        if c.isdigit():
+            continue
+        try:
+            num = int(cigar[num_start:i])
+        except ValueError:
+            num = 0
+        if c in "SH":
+            clipped += num
+            num_start = i + 1
+        else:
+            break
+    return clipped
+
+
+def _parse_ref_len_and_trailing_clips(cigar: str) -> Tuple[int, int]:   # cigar.rs:544-573
+    ref_len = trailing = num_start = 0
+    saw = False
+    for i, c in enumerate(cigar):
+        if c.isdigit():
+            continue
+        try:
+            num = int(cigar[num_start:i])
+        except ValueError:
+            num = 0
+        num_start = i + 1
+        if c in "MDN=X":
+            ref_len += num
+            trailing = 0
+            saw = True
+        elif c in "SH" and saw:
+            trailing += num
+    return ref_len, trailing
+
+
+def is_fr_pair(r: Rec) -> bool:                       # overlap.rs:15-62
+    f = r.flags
+    if not f & PAIRED:
+        return False
+    if f & UNMAPPED or f & MATE_UNMAPPED:
+        return False
+    if r.ref_id != r.mate_ref_id:
+        return False
+    rev, mrev = bool(f & REVERSE), bool(f & MATE_REVERSE)
+    if rev == mrev:
+        return False
+    start = r.pos + 1
+    mstart = r.mate_pos + 1
+    if rev:
+        ref_len = reference_length(r.cigar_ops())
+        end = start + max(ref_len - 1, 0)
+        pos5, neg5 = mstart, end
+    else:
+        pos5, neg5 = start, start + r.tlen
+    return pos5 < neg5
+
+
+def _read_pos_at_ref(ops, start1, target, at_or_past: bool) -> int:   # overlap.rs:148-204
+    ref_pos, read_pos = start1, 0
+    for op in ops:
+        t, ln = op & 0xF, op >> 4
+        if t in (0, 7, 8):
+            for _ in range(ln):
+                read_pos += 1
+                if ref_pos == target:
+                    return read_pos if at_or_past else max(read_pos - 1, 0)
+                ref_pos += 1
+        elif t in (1, 4):
+            read_pos += ln
+        elif t in (2, 3):
+            for _ in range(ln):
+                if ref_pos == target:
+                    return 0
+                ref_pos += 1
+    return 0
+
+
+def num_bases_extending_past_mate(r: Rec) -> int:     # overlap.rs:65-136
+    if not is_fr_pair(r):
+        return 0
+    mc = r.find_string(b"MC")
+    if mc is None:
+        return 0
+    try:
+        mc_s = mc.decode("utf-8")
+    except UnicodeDecodeError:
+        return 0
+    ops = r.cigar_ops()
+    this_pos, m_pos = r.pos + 1, r.mate_pos + 1
+    read_length = sum(op >> 4 for op in ops if consumes_query(op & 0xF))
+    if r.flags & REVERSE:
+        mate_us = m_pos - _parse_leading_clips(mc_s)
+        if this_pos <= mate_us:
+            return _read_pos_at_ref(ops, this_pos, mate_us, False)
+        lead = 0
+        for op in ops:
+            if op & 0xF == 4:
+                lead += op >> 4
+            elif op & 0xF == 5:
+                pass
+            else:
+                break
+        return max(lead - (this_pos - mate_us), 0)
+    ref_len = reference_length(ops)
+    aln_end = this_pos + ref_len - 1
+    rl, tc = _parse_ref_len_and_trailing_clips(mc_s)
+    mate_ue = m_pos + rl + tc - 1
+    if aln_end >= mate_ue:
+        past = _read_pos_at_ref(ops, this_pos, mate_ue, True)
+        return max(read_length - past, 0)
+    trail = 0
+    for op in reversed(ops):
+        if op & 0xF == 4:
+            trail += op >> 4
+        elif op & 0xF == 5:
+            pass
+        else:
+            break
+    return max(trail - (mate_ue - aln_end), 0)
+
+
+# ---- fgumi-dna/src/dna.rs:30-60 ----------------------------------------------------------------
+_COMP = {ord("A"): ord("T"), ord("a"): ord("T"), ord("T"): ord("A"), ord("t"): ord("A"),
+         ord("C"): ord("G"), ord("c"): ord("G"), ord("G"): ord("C"), ord("g"): ord("C")}
+
+
+def reverse_complement(seq: bytes) -> bytearray:
+    return bytearray(_COMP.get(b, b) for b in reversed(seq))
+
+
+# ---- vanilla_caller.rs --------------------------------------------------------------------------
+@dataclass
+class VanillaOptions:                                 # vanilla_caller.rs:284-341
+    tag: bytes = b"MI"
+    error_rate_pre_umi: int = 45
+    error_rate_post_umi: int = 40
+    min_input_base_quality: int = 10
+    min_reads: int = 2
+    produce_per_base_tags: bool = True
+    trim: bool = False
+    min_consensus_base_quality: int = 40
+    cell_tag: Optional[bytes] = None
+
+
+@dataclass
+class SourceRead:                                     # vanilla_caller.rs:129-146
+    original_idx: int
+    bases: bytearray
+    quals: bytearray
+    simplified_cigar: list
+    flags: int
+
+
+def find_quality_trim_point(quals: Sequence[int], trim_qual: int) -> int:   # vanilla_caller.rs:780-804
+    length = len(quals)
+    if trim_qual < 1 or length == 0:
+        return 0
+    score = max_score = 0
+    trim_point = length
+    for i in range(length - 1, -1, -1):
+        score += trim_qual - quals[i]
+        if score < 0:
+            break
+        if score > max_score:
+            max_score = score
+            trim_point = i
+    return trim_point
+
+
+def truncate_simplified_cigar(cigar, query_length: int):     # vanilla_caller.rs:816-851
+    result, remaining = [], query_length
+    for kind, ln in cigar:
+        if remaining == 0:
+            break
+        if kind in (0, 1, 4, 7, 8):
+            take = min(ln, remaining)
+            result.append((kind, take))
+            remaining -= take
+        else:
+            result.append((kind, ln))
+    return result
+
+
+def create_source_read(r: Rec, idx: int, mate_clip: int, opt: VanillaOptions) -> Optional[SourceRead]:
+    """vanilla_caller.rs:863-955"""
+    neg = bool(r.flags & REVERSE)
+    min_bq = opt.min_input_base_quality
+    bases, quals = r.sequence(), r.quals()
+    read_len = len(bases)
+    if len(quals) == 0 or len(quals) != read_len:
+        return None
+    if all(q == 0xFF for q in quals):
+        return None
+    if neg:
+        bases = reverse_complement(bases)
+        quals = bytearray(reversed(quals))
+    trim_to = find_quality_trim_point(quals, min_bq) if opt.trim else read_len
+    for i in range(trim_to):
+        if quals[i] < min_bq:
+            bases[i] = ord("N")
+            quals[i] = 2
+    clip_position = max(read_len - mate_clip, 0)
+    final_len = min(clip_position, trim_to)
+    while final_len > 0 and bases[final_len - 1] == ord("N"):
+        final_len -= 1
+    if final_len == 0:
+        return None
+    bases, quals = bases[:final_len], quals[:final_len]
+    simp = simplify_cigar(r.cigar_ops())
+    if neg:
+        simp = list(reversed(simp))
+    simp = truncate_simplified_cigar(simp, final_len)
+    return SourceRead(idx, bases, quals, simp, r.flags)
+
+
+_KIND_ORD = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5, 6: 6, 7: 7, 8: 8}
+
+
+def _cmp_cigar(a, b) -> int:                          # vanilla_caller.rs:77-105
+    for (ka, la), (kb, lb) in zip(a, b):
+        if la != lb:
+            return -1 if la < lb else 1
+        if _KIND_ORD[ka] != _KIND_ORD[kb]:
+            return -1 if _KIND_ORD[ka] < _KIND_ORD[kb] else 1
+    return (len(a) > len(b)) - (len(a) < len(b))
+
+
+def select_most_common_alignment_group(indexed) -> List[int]:     # vanilla_caller.rs:47-119
+    if len(indexed) < 2:
+        return [i for i, _, _ in indexed]
+    groups: List[Tuple[list, List[int]]] = []
+    for idx, _len, cigar in indexed:
+        found = False
+        for gc, members in groups:
+            if is_cigar_prefix(cigar, gc):
+                members.append(idx)
+                found = True
+        if not found:
+            groups.append((list(cigar), [idx]))
+    # Iterator::max_by returns the LAST maximum; key: size asc, then cmp_cigar(b, a)
+    best = None
+    for g in groups:
+        if best is None:
+            best = g
+            continue
+        c = (len(g[1]) > len(best[1])) - (len(g[1]) < len(best[1]))
+        if c == 0:
+            c = _cmp_cigar(best[0], g[0])             # cmp(g, best) = cmp_cigar(best.cigar, g.cigar)
+        if c >= 0:
+            best = g
+    return list(best[1]) if best else []
+
+
+def filter_by_alignment(srs: List[SourceRead]):       # vanilla_caller.rs:961-1013
+    if len(srs) < 2:
+        return srs, 0
+    indexed = [(i, len(sr.bases), sr.simplified_cigar) for i, sr in enumerate(srs)]
+    indexed.sort(key=lambda t: -t[1])                 # stable sort, descending length
+    keep = set(select_most_common_alignment_group(indexed))
+    kept = [sr for i, sr in enumerate(srs) if i in keep]
+    return kept, len(srs) - len(keep)
+
+
+# ---- simple_umi.rs ------------------------------------------------------------------------------
+def consensus_umis(umis: List[str], vote) -> str:     # simple_umi.rs:65-122, 236-245
+    if not umis:
+        return ""
+    if len(umis) == 1:
+        return umis[0]
+    first = umis[0]
+    n = len(first)
+    assert all(len(s) == n for s in umis)
+    out = []
+    for i in range(n):
+        col = [s[i] for s in umis]
+        dna = [c for c in col if c.upper() in "ACGTN"]
+        if len(dna) == len(col):
+            b, _q = vote(90, 90, "".join(col).encode(), [20] * len(col))
+            out.append(b)
+        elif not dna:
+            assert all(c == first[i] for c in col)
+            out.append(first[i])
+        else:
+            raise AssertionError("mix of DNA and non-DNA characters")
+    return "".join(out)
+
+
+# ---- raw-bam builder.rs / tags.rs encoders -------------------------------------------------------
+def pack_sequence(bases: bytes) -> bytes:             # sequence.rs:183-209
+    out = bytearray()
+    for i in range(0, len(bases) - 1, 2):
+        out.append((SEQ_CODES[bases[i]] << 4) | SEQ_CODES[bases[i + 1]])
+    if len(bases) % 2:
+        out.append(SEQ_CODES[bases[-1]] << 4)
+    return bytes(out)
+
+
+def tag_string(tag: bytes, v: bytes) -> bytes:        # tags.rs:512-519
+    return tag + b"Z" + v + b"\0"
+
+
+def tag_int(tag: bytes, v: int) -> bytes:             # tags.rs:533-553
+    if -128 <= v <= 127:
+        return tag + b"c" + struct.pack("<b", v)
+    if 0 <= v <= 255:
+        return tag + b"C" + struct.pack("<B", v)
+    if 0 <= v <= 65535:
+        return tag + b"S" + struct.pack("<H", v)
+    if -32768 <= v <= 32767:
+        return tag + b"s" + struct.pack("<h", v)
+    return tag + b"i" + struct.pack("<i", v)
+
+
+def tag_float(tag: bytes, v) -> bytes:                # tags.rs:557-563
+    return tag + b"f" + struct.pack("<f", v)
+
+
+def tag_i16_array(tag: bytes, vals) -> bytes:         # tags.rs:573-586
+    return tag + b"Bs" + struct.pack("<I", len(vals)) + struct.pack("<%dh" % len(vals), *vals)
+
+
+def tag_phred33(tag: bytes, quals) -> bytes:          # tags.rs:656-667
+    return tag + b"Z" + bytes(min(q + 33, 255) for q in quals) + b"\0"
+
+
+def unmapped_record(name: bytes, flag: int, bases: bytes, quals: bytes) -> bytearray:   # builder.rs:90-142
+    assert len(name) < 255
+    out = bytearray(struct.pack("<iiBBHHHIiii", -1, -1, len(name) + 1, 0, 4680, 0, flag, len(bases),
+                                -1, -1, 0))
+    out += name + b"\0"
+    out += pack_sequence(bases)
+    out += bytes(quals) if (quals or not bases) else b"\xff" * len(bases)
+    return out
+
+
+def with_block_size(rec: bytes) -> bytes:             # builder.rs:224-230
+    return struct.pack("<I", len(rec)) + bytes(rec)
+
+
+# ---- the simplex caller -------------------------------------------------------------------------
+@dataclass
+class Stats:                                          # caller.rs:238-286
+    total_reads: int = 0
+    consensus_reads: int = 0
+    filtered_reads: int = 0
+    rejections: Dict[str, int] = field(default_factory=dict)
+
+    def reject(self, reason: str, n: int):
+        self.filtered_reads += n
+        self.rejections[reason] = self.rejections.get(reason, 0) + n
+
+
+class VanillaCallerOracle:
+    """VanillaUmiConsensusCaller::consensus_reads, vanilla_caller.rs:1042-1499."""
+
+    def __init__(self, prefix: str, rg: str, opt: VanillaOptions, vote_fn, builder_fn):
+        self.prefix, self.rg, self.opt = prefix, rg, opt
+        self.stats = Stats()
+        self.vote = vote_fn           # (rows, opt) -> (bases, quals, depths, errors)
+        self.builder_call = builder_fn
+
+    def consensus_reads(self, records: List[bytes]) -> Tuple[bytes, int]:
+        if not records:
+            return b"", 0
+        recs = [Rec(b) for b in records]
+        umi = recs[0].find_string(self.opt.tag)
+        if umi is None:
+            raise ValueError("Missing UMI tag")
+        return self._process_group(umi.decode("utf-8", "replace"), recs)
+
+    def _process_group(self, umi: str, recs: List[Rec]):
+        st, opt = self.stats, self.opt
+        st.total_reads += len(recs)
+        reads = [r for r in recs if not (r.flags & SECONDARY) and not (r.flags & SUPPLEMENTARY)]
+        if len(recs) - len(reads):
+            st.reject("SecondaryOrSupplementary", len(recs) - len(reads))
+        if not reads:
+            return b"", 0
+        if len(reads) < opt.min_reads:
+            st.reject("InsufficientReads", len(reads))
+            return b"", 0
+        frag = [r for r in reads if not r.flags & PAIRED]
+        r1 = [r for r in reads if r.flags & PAIRED and r.flags & FIRST_SEGMENT]
+        r2 = [r for r in reads if r.flags & PAIRED and not r.flags & FIRST_SEGMENT and r.flags & LAST_SEGMENT]
+        out, count = bytearray(), 0
+        ok, _, rec = self._subgroup(umi, "Fragment", frag)
+        if ok:
+            st.consensus_reads += 1
+            out += rec
+            count += 1
+        ok1, n1, rec1 = self._subgroup(umi, "R1", r1)
+        ok2, n2, rec2 = self._subgroup(umi, "R2", r2)
+        if ok1 and ok2:
+            st.consensus_reads += 2
+            out += rec1 + rec2
+            count += 2
+        elif ok1:
+            st.reject("OrphanConsensus", n1)
+        elif ok2:
+            st.reject("OrphanConsensus", n2)
+        return bytes(out), count
+
+    def _subgroup(self, umi: str, read_type: str, group: List[Rec]):
+        st, opt = self.stats, self.opt
+        if not group:
+            return False, 0, b""
+        if len(group) < opt.min_reads:
+            st.reject("InsufficientReads", len(group))
+            return False, 0, b""
+        clips = [num_bases_extending_past_mate(r) for r in group]
+        srs, zero = [], 0
+        for i, (r, c) in enumerate(zip(group, clips)):
+            sr = create_source_read(r, i, c, opt)
+            if sr is None:
+                zero += 1
+            else:
+                srs.append(sr)
+        if zero:
+            st.reject("ZeroLengthAfterTrimming", zero)
+        if len(srs) < opt.min_reads:
+            if srs:
+                st.reject("InsufficientReads", len(srs))
+            return False, 0, b""
+        srs, n_rej = filter_by_alignment(srs)
+        if n_rej:
+            st.reject("MinorityAlignment", n_rej)
+        if len(srs) < opt.min_reads:
+            if srs:
+                st.reject("InsufficientReads", len(srs))
+            return False, 0, b""
+        bases, quals, depths, errors = self.vote([(bytes(s.bases), bytes(s.quals)) for s in srs], opt)
+        raws = [group[s.original_idx] for s in srs]
+        return True, len(srs), self._record(umi, read_type, raws, bases, quals, depths, errors)
+
+    def _record(self, umi, read_type, raws, bases, quals, depths, errors) -> bytes:
+        """build_consensus_record_into, vanilla_caller.rs:1365-1473"""
+        opt = self.opt
+        name = f"{self.prefix}:{umi}".encode()
+        flag = UNMAPPED
+        if read_type == "R1":
+            flag |= PAIRED | FIRST_SEGMENT | MATE_UNMAPPED
+        elif read_type == "R2":
+            flag |= PAIRED | LAST_SEGMENT | MATE_UNMAPPED
+        rec = unmapped_record(name, flag, bases, quals)
+        rec += tag_string(b"RG", self.rg.encode())
+        max_d = max(depths) if len(depths) else 0
+        min_d = min(depths) if len(depths) else 0
+        tot_e, tot_d = int(sum(int(e) for e in errors)), int(sum(int(d) for d in depths))
+        # `total_errors as f32 / total_depth as f32`
+        rate = (np.float32(tot_e) / np.float32(tot_d)) if tot_d > 0 else np.float32(0.0)
+        rec += tag_int(b"cD", int(max_d)) + tag_int(b"cM", int(min_d)) + tag_float(b"cE", rate)
+        if opt.produce_per_base_tags:
+            rec += tag_i16_array(b"cd", [min(int(d), 32767) for d in depths])
+            rec += tag_i16_array(b"ce", [min(int(e), 32767) for e in errors])
+        rec += tag_string(b"MI", umi.encode())
+        if opt.cell_tag is not None and raws:
+            v = raws[0].find_string(opt.cell_tag)
+            if v is not None:
+                rec += tag_string(opt.cell_tag, v)
+        umis = [r.find_string(b"RX") for r in raws]
+        umis = [u.decode("utf-8", "replace") for u in umis if u is not None]
+        if umis:
+            rx = consensus_umis(umis, lambda pre, post, b, q: self.builder_call(pre, post, b, q)[:2])
+            rec += tag_string(b"RX", rx.encode())
+        return with_block_size(rec)
