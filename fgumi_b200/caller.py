@@ -20,7 +20,18 @@ class ConsensusOutput:
         self.data, self.count = data, count
 
 
-class VanillaUmiConsensusCaller:
+class _Caller:
+    """Shared plumbing over fgb_caller_* (add_group / flush / statistics)."""
+
+    def _create(self, o: "_l.FgbCallerOptions", device: int):
+        self._h = C.c_void_p()
+        st = self._lib.fgb_caller_create(device, C.byref(o), C.byref(self._h))
+        if st != _l.FGB_OK:
+            self._h = C.c_void_p()
+            raise _l.FgbError(st, "fgb_caller_create")
+
+
+class VanillaUmiConsensusCaller(_Caller):
     """vanilla_caller.rs:344-455 (new) / :1477-1499 (consensus_reads), batched."""
 
     def __init__(self, read_name_prefix: str, read_group_id: str,
@@ -42,11 +53,7 @@ class VanillaUmiConsensusCaller:
         o.cell_tag = cell_tag if cell_tag else b"\0\0"
         o.read_name_prefix = self._prefix
         o.read_group_id = self._rg
-        self._h = C.c_void_p()
-        st = self._lib.fgb_caller_create(device, C.byref(o), C.byref(self._h))
-        if st != _l.FGB_OK:
-            self._h = C.c_void_p()
-            raise _l.FgbError(st, "fgb_caller_create")
+        self._create(o, device)
 
     def close(self):
         if self._h:
@@ -93,3 +100,29 @@ class VanillaUmiConsensusCaller:
         self._check(self._lib.fgb_caller_stats(self._h, arr), "fgb_caller_stats")
         d = dict(zip(_l.STAT_NAMES, [int(x) for x in arr]))
         return d
+
+
+class DuplexConsensusCaller(VanillaUmiConsensusCaller):
+    """DuplexConsensusCaller::new (duplex_caller.rs:358-434): min_reads = (total, xy, yx)."""
+
+    def __init__(self, read_name_prefix: str, read_group_id: str, min_reads=(1, 1, 1),
+                 error_rate_pre_umi: int = 45, error_rate_post_umi: int = 40,
+                 min_input_base_quality: int = 10, produce_per_base_tags: bool = True,
+                 trim: bool = False, device: int = 0, cell_tag: bytes = b""):
+        self._lib = _l.load()
+        self._prefix = read_name_prefix.encode()
+        self._rg = read_group_id.encode()
+        o = _l.FgbCallerOptions()
+        o.mode = 1
+        o.error_rate_pre_umi = error_rate_pre_umi
+        o.error_rate_post_umi = error_rate_post_umi
+        o.min_input_base_quality = min_input_base_quality
+        o.min_consensus_base_quality = 2
+        o.produce_per_base_tags = 1 if produce_per_base_tags else 0
+        o.trim = 1 if trim else 0
+        o.min_reads, o.min_xy_reads, o.min_yx_reads = min_reads
+        o.tag = b"MI"
+        o.cell_tag = cell_tag if cell_tag else b"\0\0"
+        o.read_name_prefix = self._prefix
+        o.read_group_id = self._rg
+        self._create(o, device)

@@ -1,0 +1,662 @@
+// Record-level callers behind fgb_caller_* (product code): the host side of fgumi's
+// VanillaUmiConsensusCaller and DuplexConsensusCaller, re-shaped for GPU batches.
+//
+//   add_group()  everything the reference does BEFORE the vote, per MI group, packing the surviving
+//                SourceRead rows into the SoA batch of include/fgumi_b200.h:
+//                  simplex  vanilla_caller.rs:1042-1227 (process_group / process_subgroup)
+//                  duplex   duplex_caller.rs:576-630 (strand partition), :1719-1942 (process_group)
+//   flush()      one vote (+ strand combine) on the GPU for everything packed, then the record
+//                assembly, in input order:
+//                  simplex  vanilla_caller.rs:1365-1473 (build_consensus_record_into)
+//                  duplex   duplex_caller.rs:1944-2202 (arm selection, min-reads re-check) and
+//                           :1048-1285 (duplex_read_into)
+// There is no CPU vote here: without a device, fgb_caller_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/fgumi_b200.h"
+#include "bam.h"
+#include "prep.h"
+
+using namespace fgb;
+using namespace fgb::prep;
+
+namespace {
+
+enum ReadType : uint8_t { kFragment = 0, kR1 = 1, kR2 = 2 };
+
+struct UnitMeta {                    // simplex: one per packed unit
+  uint8_t read_type;
+  std::string umi;
+  std::vector<std::string> rx;       // RX values of the surviving reads, in order
+  bool has_cell = false;
+  std::string cell;
+};
+
+struct RxSource {                    // duplex: one surviving raw read's RX + FIRST_SEGMENT flag
+  std::string rx;
+  bool first;
+};
+
+struct Molecule {                    // duplex: one MI group that reached the vote
+  std::string base_mi;
+  uint32_t n_input = 0;              // a_records.len() + b_records.len() (for rejections)
+  bool has_cell = false;
+  std::string cell;
+  // unit index of AB-R1, AB-R2, BA-R1, BA-R2 (UINT32_MAX = absent)
+  uint32_t unit[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  std::vector<RxSource> rx[4];       // RX sources per sub-family
+  int32_t job[2] = {-1, -1};         // duplex combine jobs (R1, R2) when all four are present
+  uint8_t pattern = 0;               // 0 full duplex, 1 AB only, 2 BA only
+};
+
+}  // namespace
+
+struct fgb_caller {
+  fgb_caller_options opt{};
+  std::string prefix, rg;
+  fgb_handle* h = nullptr;
+  UmiBuilder umi_builder;
+  PrepOptions prep_opt;
+  uint64_t stats[FGB_NSTATS] = {0};
+  Packer pack;
+  std::vector<UnitMeta> metas;           // simplex
+  std::vector<Molecule> molecules;       // duplex
+  std::vector<fgb_duplex_job> jobs;      // duplex
+  uint64_t n_duplex_out = 0;
+  std::vector<uint8_t> out;              // output of the last flush
+  uint64_t out_count = 0;
+  std::string last_error;
+  std::vector<uint32_t> ops;             // scratch
+};
+
+namespace {
+
+void reject(fgb_caller* c, int reason, uint64_t n) {
+  c->stats[FGB_STAT_FILTERED_READS] += n;
+  c->stats[reason] += n;
+}
+
+bool get_string_tag(const View& v, const char tag[2], std::string* out) {
+  const uint8_t* val; size_t n;
+  if (!bam::find_string_tag(v, tag, &val, &n)) return false;
+  out->assign(reinterpret_cast<const char*>(val), n);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// simplex
+// ------------------------------------------------------------------------------------------------
+struct Prepared {
+  bool ok = false;
+  size_t surviving = 0;
+  std::vector<SourceRead> srs;
+  std::vector<uint32_t> rec_idx;   // indices (into the group's records) of the surviving reads
+};
+
+// process_subgroup up to the vote, vanilla_caller.rs:1124-1227
+void prepare_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::vector<uint32_t>& members,
+                      Prepared* p) {
+  p->ok = false; p->surviving = 0; p->srs.clear(); p->rec_idx.clear();
+  const size_t min_reads = c->opt.min_reads;
+  if (members.empty()) return;
+  if (members.size() < min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, members.size()); return; }
+  size_t zero = 0;
+  for (uint32_t k = 0; k < members.size(); ++k) {
+    const View& v = recs[members[k]];
+    bam::cigar_ops(v, &c->ops);
+    size_t clip = bam::num_bases_extending_past_mate(v, c->ops);
+    SourceRead sr;
+    if (make_source_read(c->prep_opt, v, k, clip, &c->ops, &sr)) p->srs.push_back(std::move(sr));
+    else ++zero;
+  }
+  if (zero) reject(c, FGB_STAT_REJ_ZERO_LENGTH, zero);
+  if (p->srs.size() < min_reads) {
+    if (!p->srs.empty()) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, p->srs.size());
+    return;
+  }
+  size_t minority = filter_by_alignment(&p->srs);
+  if (minority) reject(c, FGB_STAT_REJ_MINORITY_ALIGNMENT, minority);
+  if (p->srs.size() < min_reads) {
+    if (!p->srs.empty()) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, p->srs.size());
+    return;
+  }
+  p->ok = true;
+  p->surviving = p->srs.size();
+  for (auto& sr : p->srs) p->rec_idx.push_back(members[sr.original_idx]);
+}
+
+void pack_simplex_unit(fgb_caller* c, const std::vector<View>& recs, const Prepared& p, uint8_t read_type,
+                       const std::string& umi) {
+  c->pack.add_unit(p.srs, c->opt.min_reads);
+  UnitMeta m;
+  m.read_type = read_type;
+  m.umi = umi;
+  std::string s;
+  for (uint32_t ri : p.rec_idx) if (get_string_tag(recs[ri], "RX", &s)) m.rx.push_back(s);
+  if (c->opt.cell_tag[0] && !p.rec_idx.empty()) m.has_cell = get_string_tag(recs[p.rec_idx[0]], c->opt.cell_tag, &m.cell);
+  c->metas.push_back(std::move(m));
+}
+
+// consensus_reads for one MI group (vanilla_caller.rs:1477-1499 + process_group :1042-1114).
+fgb_status add_group_simplex(fgb_caller* c, const std::vector<View>& recs) {
+  const uint32_t n_records = static_cast<uint32_t>(recs.size());
+  std::string umi;
+  if (!get_string_tag(recs[0], c->opt.tag, &umi)) {   // vanilla_caller.rs:1493-1496
+    c->last_error = std::string("Missing UMI tag '") + c->opt.tag[0] + c->opt.tag[1] + "'";
+    return FGB_ERR_MISSING_TAG;
+  }
+  c->stats[FGB_STAT_TOTAL_READS] += n_records;
+  std::vector<uint32_t> kept;
+  for (uint32_t i = 0; i < n_records; ++i) {
+    uint16_t f = recs[i].flags();
+    if (!(f & bam::kSecondary) && !(f & bam::kSupplementary)) kept.push_back(i);
+  }
+  if (kept.size() != n_records) reject(c, FGB_STAT_REJ_SECONDARY_SUPPLEMENTARY, n_records - kept.size());
+  if (kept.empty()) return FGB_OK;
+  if (kept.size() < c->opt.min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, kept.size()); return FGB_OK; }
+  std::vector<uint32_t> frag, r1, r2;
+  for (uint32_t i : kept) {   // subgroup_reads, vanilla_caller.rs:1018-1039
+    uint16_t f = recs[i].flags();
+    if (!(f & bam::kPaired)) frag.push_back(i);
+    else if (f & bam::kFirst) r1.push_back(i);
+    else if (f & bam::kLast) r2.push_back(i);
+  }
+  Prepared pf, p1, p2;
+  prepare_subgroup(c, recs, frag, &pf);
+  if (pf.ok) { pack_simplex_unit(c, recs, pf, kFragment, umi); c->stats[FGB_STAT_CONSENSUS_READS] += 1; }
+  prepare_subgroup(c, recs, r1, &p1);
+  prepare_subgroup(c, recs, r2, &p2);
+  if (p1.ok && p2.ok) {   // orphan rule, vanilla_caller.rs:1089-1108
+    pack_simplex_unit(c, recs, p1, kR1, umi);
+    pack_simplex_unit(c, recs, p2, kR2, umi);
+    c->stats[FGB_STAT_CONSENSUS_READS] += 2;
+  } else if (p1.ok) {
+    reject(c, FGB_STAT_REJ_ORPHAN_CONSENSUS, p1.surviving);
+  } else if (p2.ok) {
+    reject(c, FGB_STAT_REJ_ORPHAN_CONSENSUS, p2.surviving);
+  }
+  return FGB_OK;
+}
+
+float error_rate(uint64_t errors, uint64_t depth) {
+  return depth > 0 ? static_cast<float>(errors) / static_cast<float>(depth) : 0.0f;
+}
+
+fgb_status append_rx(fgb_caller* c, bam::Writer* w, const std::vector<std::string>& umis) {
+  if (umis.empty()) return FGB_OK;
+  std::string rx;
+  if (!consensus_umis(c->umi_builder, umis, &rx)) {
+    c->last_error = "RX values of a family have different lengths or mix DNA and non-DNA characters";
+    return FGB_ERR_INVALID_ARG;   // the reference panics here (simple_umi.rs:78-116)
+  }
+  w->str("RX", rx.data(), rx.size());
+  return FGB_OK;
+}
+
+fgb_status flush_simplex(fgb_caller* c) {
+  const uint64_t U = c->pack.units.size();
+  if (!U) return FGB_OK;
+  uint64_t n_bytes, R;
+  c->pack.seal(&n_bytes, &R);
+  uint64_t n_tiles = 0;
+  fgb_status st = fgb_plan_tiles(c->pack.units.data(), U, c->pack.reads.data(), R, nullptr, 0, &n_tiles);
+  if (st != FGB_OK) { c->last_error = "fgb_plan_tiles failed"; return st; }
+  std::vector<fgb_tile> tiles(n_tiles ? n_tiles : 1);
+  if ((st = fgb_plan_tiles(c->pack.units.data(), U, c->pack.reads.data(), R, tiles.data(), n_tiles, &n_tiles)) != FGB_OK) return st;
+  const uint64_t no = c->pack.n_out;
+  std::vector<uint8_t> ob(no + 8), oq(no + 8);
+  std::vector<uint16_t> od(no + 8), oe(no + 8);
+  fgb_batch b;
+  b.n_units = U; b.n_reads = R; b.n_bytes = n_bytes; b.n_out = no; b.n_tiles = n_tiles;
+  b.bases = c->pack.bases.data(); b.quals = c->pack.quals.data(); b.reads = c->pack.reads.data();
+  b.units = c->pack.units.data(); b.tiles = tiles.data();
+  fgb_columns cols{ob.data(), oq.data(), od.data(), oe.data()};
+  st = fgb_submit(c->h, &b, &cols);
+  if (st == FGB_OK) st = fgb_wait(c->h);
+  if (st != FGB_OK) {
+    char buf[256];
+    fgb_last_error(c->h, buf, sizeof(buf));
+    c->last_error = buf;
+    return st;
+  }
+  // ---- build_consensus_record_into, vanilla_caller.rs:1365-1473 ----
+  bam::Writer w(&c->out);
+  for (uint64_t i = 0; i < U; ++i) {
+    const fgb_unit& u = c->pack.units[i];
+    const UnitMeta& m = c->metas[i];
+    const uint32_t L = u.cons_len;
+    const uint8_t* bases = ob.data() + u.out_off;
+    const uint8_t* quals = oq.data() + u.out_off;
+    const uint16_t* depths = od.data() + u.out_off;
+    const uint16_t* errors = oe.data() + u.out_off;
+    uint16_t flag = bam::kUnmapped;
+    if (m.read_type == kR1) flag |= bam::kPaired | bam::kFirst | bam::kMateUnmapped;
+    else if (m.read_type == kR2) flag |= bam::kPaired | bam::kLast | bam::kMateUnmapped;
+    std::string name = c->prefix + ":" + m.umi;
+    if (name.size() >= 255) { c->last_error = "read name too long"; return FGB_ERR_INVALID_ARG; }
+    w.begin(name, flag, bases, quals, L);
+    w.str("RG", c->rg.data(), c->rg.size());
+    uint32_t max_d = 0, min_d = L ? 0xFFFFFFFFu : 0;
+    uint64_t tot_e = 0, tot_d = 0;
+    for (uint32_t k = 0; k < L; ++k) {
+      max_d = std::max<uint32_t>(max_d, depths[k]);
+      min_d = std::min<uint32_t>(min_d, depths[k]);
+      tot_e += errors[k];
+      tot_d += depths[k];
+    }
+    w.integer("cD", static_cast<int32_t>(max_d));
+    w.integer("cM", static_cast<int32_t>(min_d));
+    w.real("cE", error_rate(tot_e, tot_d));
+    if (c->opt.produce_per_base_tags) {
+      w.i16_array("cd", depths, L);
+      w.i16_array("ce", errors, L);
+    }
+    w.str("MI", m.umi.data(), m.umi.size());
+    if (m.has_cell) w.str(c->opt.cell_tag, m.cell.data(), m.cell.size());
+    if ((st = append_rx(c, &w, m.rx)) != FGB_OK) return st;
+    w.end();
+    ++c->out_count;
+  }
+  return FGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// duplex
+// ------------------------------------------------------------------------------------------------
+bool paired_r1(const View& v) { return (v.flags() & bam::kPaired) && (v.flags() & bam::kFirst); }
+bool paired_r2(const View& v) { return (v.flags() & bam::kPaired) && (v.flags() & bam::kLast); }
+
+// has_minimum_number_of_reads / duplex_consensus_has_minimum_reads, duplex_caller.rs:731-769
+bool min_reads_ok(const fgb_caller* c, size_t na, size_t nb) {
+  size_t xy = na >= nb ? na : nb, yx = na >= nb ? nb : na;
+  return c->opt.min_reads <= xy + yx && c->opt.min_xy_reads <= xy && c->opt.min_yx_reads <= yx;
+}
+
+bool all_same_strand(const std::vector<View>& recs, const std::vector<uint32_t>& a,
+                     const std::vector<uint32_t>& b) {
+  bool have = false, rev = false;
+  for (const auto* grp : {&a, &b})
+    for (uint32_t i : *grp) {
+      bool r = recs[i].flags() & bam::kReverse;
+      if (!have) { have = true; rev = r; }
+      else if (r != rev) return false;
+    }
+  return true;
+}
+
+// duplex_caller.rs:2206-2250 (consensus_reads) + :576-630 + process_group :1719-1942
+fgb_status add_group_duplex(fgb_caller* c, const std::vector<View>& recs) {
+  const uint32_t n = static_cast<uint32_t>(recs.size());
+  c->stats[FGB_STAT_TOTAL_READS] += n;
+  std::vector<uint32_t> a, b;
+  std::string base_mi, mi;
+  bool have_mi = false;
+  for (uint32_t i = 0; i < n; ++i) {   // partition_records_by_strand
+    if (!get_string_tag(recs[i], "MI", &mi)) {
+      c->last_error = "read is missing the MI tag (duplex requires 'group --strategy paired' input)";
+      return FGB_ERR_MISSING_TAG;
+    }
+    if (!have_mi) { base_mi = mi.size() >= 2 ? mi.substr(0, mi.size() - 2) : mi; have_mi = true; }
+    if (mi.size() >= 2 && mi[mi.size() - 2] == '/' && mi.back() == 'A') a.push_back(i);
+    else if (mi.size() >= 2 && mi[mi.size() - 2] == '/' && mi.back() == 'B') b.push_back(i);
+    else {
+      c->last_error = "MI tag '" + mi + "' has no /A or /B suffix (duplex requires paired grouping)";
+      return FGB_ERR_INVALID_ARG;
+    }
+  }
+  if (a.empty() && b.empty()) return FGB_OK;
+  const uint64_t n_input = a.size() + b.size();
+  size_t na = 0, nb = 0;
+  for (uint32_t i : a) na += paired_r1(recs[i]);
+  for (uint32_t i : b) nb += paired_r1(recs[i]);
+  if (!min_reads_ok(c, na, nb)) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, n_input); return FGB_OK; }
+  Molecule m;
+  m.base_mi = base_mi;
+  m.n_input = static_cast<uint32_t>(n_input);
+  if (c->opt.cell_tag[0]) {
+    const View& first = !a.empty() ? recs[a[0]] : recs[b[0]];
+    m.has_cell = get_string_tag(first, c->opt.cell_tag, &m.cell);
+  }
+  std::vector<uint32_t> ab_r1, ab_r2, ba_r1, ba_r2;
+  for (uint32_t i : a) { if (paired_r1(recs[i])) ab_r1.push_back(i); if (paired_r2(recs[i])) ab_r2.push_back(i); }
+  for (uint32_t i : b) { if (paired_r1(recs[i])) ba_r1.push_back(i); if (paired_r2(recs[i])) ba_r2.push_back(i); }
+  if (!a.empty() && !b.empty()) {   // strand-orientation sanity, duplex_caller.rs:1799-1823
+    if (!all_same_strand(recs, ab_r1, ba_r2) || !all_same_strand(recs, ab_r2, ba_r1)) {
+      reject(c, FGB_STAT_REJ_POTENTIAL_COLLISION, n_input);
+      return FGB_OK;
+    }
+  }
+  // X = AB-R1 + BA-R2, Y = AB-R2 + BA-R1: pooled CIGAR filter, then split back (:1844-1892)
+  auto pooled = [&](const std::vector<uint32_t>& p, const std::vector<uint32_t>& q,
+                    std::vector<uint32_t>* raws, std::vector<SourceRead>* srs) {
+    raws->clear(); srs->clear();
+    raws->insert(raws->end(), p.begin(), p.end());
+    raws->insert(raws->end(), q.begin(), q.end());
+    for (uint32_t k = 0; k < raws->size(); ++k) {
+      const View& v = recs[(*raws)[k]];
+      bam::cigar_ops(v, &c->ops);
+      size_t clip = bam::num_bases_extending_past_mate(v, c->ops);
+      SourceRead sr;
+      if (make_source_read(c->prep_opt, v, k, clip, &c->ops, &sr)) srs->push_back(std::move(sr));
+    }
+    filter_by_alignment(srs);   // MinorityAlignment is counted by the ss caller, not the duplex stats
+  };
+  std::vector<uint32_t> x_raws, y_raws;
+  std::vector<SourceRead> fx, fy;
+  pooled(ab_r1, ba_r2, &x_raws, &fx);
+  pooled(ab_r2, ba_r1, &y_raws, &fy);
+  std::vector<SourceRead> grp[4];   // AB-R1, AB-R2, BA-R1, BA-R2
+  std::vector<uint32_t> grp_raw[4];
+  for (auto& sr : fx) { int g = (sr.flags & bam::kFirst) ? 0 : 3; grp_raw[g].push_back(x_raws[sr.original_idx]); grp[g].push_back(std::move(sr)); }
+  for (auto& sr : fy) { int g = (sr.flags & bam::kFirst) ? 2 : 1; grp_raw[g].push_back(y_raws[sr.original_idx]); grp[g].push_back(std::move(sr)); }
+  const bool have[4] = {!grp[0].empty(), !grp[1].empty(), !grp[2].empty(), !grp[3].empty()};
+  // consensus_call succeeds iff the group is non-empty (min_reads = 1); arm selection :1986-2190
+  if (have[0] && have[1] && have[2] && have[3]) m.pattern = 0;
+  else if (have[0] && have[1] && !have[2] && !have[3] && c->opt.min_yx_reads == 0) m.pattern = 1;
+  else if (!have[0] && !have[1] && have[2] && have[3] && c->opt.min_yx_reads == 0) m.pattern = 2;
+  else { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, n_input); return FGB_OK; }
+  std::string rx;
+  for (int g = 0; g < 4; ++g) {
+    if (!have[g]) continue;
+    m.unit[g] = c->pack.add_unit(grp[g], 1);
+    for (uint32_t ri : grp_raw[g])
+      if (get_string_tag(recs[ri], "RX", &rx)) m.rx[g].push_back(RxSource{rx, (recs[ri].flags() & bam::kFirst) != 0});
+  }
+  if (m.pattern == 0) {
+    auto add_job = [&](uint32_t ua, uint32_t ub) {
+      fgb_duplex_job j;
+      j.unit_a = ua; j.unit_b = ub; j.out_off = c->n_duplex_out;
+      uint32_t cap = std::max(c->pack.units[ua].cons_len, c->pack.units[ub].cons_len);
+      c->n_duplex_out += round_up(cap, FGB_OUT_ALIGN);
+      c->jobs.push_back(j);
+      return static_cast<int32_t>(c->jobs.size() - 1);
+    };
+    m.job[0] = add_job(m.unit[0], m.unit[3]);   // duplex R1 = AB-R1 (+) BA-R2, :1999-2004
+    m.job[1] = add_job(m.unit[1], m.unit[2]);   // duplex R2 = AB-R2 (+) BA-R1, :2008-2012
+  }
+  c->molecules.push_back(std::move(m));
+  return FGB_OK;
+}
+
+// One strand's columns as seen by duplex_read_into (ab_consensus / ba_consensus).
+struct Strand {
+  const uint8_t* bases = nullptr;
+  const uint8_t* quals = nullptr;
+  const uint16_t* depths = nullptr;
+  const uint16_t* errors = nullptr;
+  uint32_t len = 0;
+  bool present = false;
+};
+
+struct DuplexRead {
+  const uint8_t* bases; const uint8_t* quals; const uint16_t* errors; uint32_t len;
+  Strand ab, ba;
+};
+
+uint32_t max_depth(const Strand& s) {
+  uint32_t m = 0;
+  for (uint32_t i = 0; i < s.len; ++i) m = std::max<uint32_t>(m, s.depths[i]);
+  return m;
+}
+
+// duplex_read_into, duplex_caller.rs:1048-1285 (methylation off)
+fgb_status write_duplex_record(fgb_caller* c, bam::Writer* w, const DuplexRead& d, bool r1,
+                               const Molecule& m, const std::vector<RxSource>& src_a,
+                               const std::vector<RxSource>& src_b) {
+  uint16_t flag = bam::kUnmapped | bam::kPaired | bam::kMateUnmapped | (r1 ? bam::kFirst : bam::kLast);
+  std::string name = c->prefix + ":" + m.base_mi;
+  if (name.size() >= 255) { c->last_error = "read name too long"; return FGB_ERR_INVALID_ARG; }
+  w->begin(name, flag, d.bases, d.quals, d.len);
+  w->str("MI", m.base_mi.data(), m.base_mi.size());
+  if (m.has_cell) w->str(c->opt.cell_tag, m.cell.data(), m.cell.size());
+  w->str("RG", c->rg.data(), c->rg.size());
+  auto metrics = [](const Strand& s, int32_t* mx, int32_t* mn, float* er) {
+    *mx = 0; *mn = 0; *er = 0.0f;
+    if (!s.present) return;
+    uint32_t lo = s.len ? 0xFFFFFFFFu : 0, hi = 0;
+    uint64_t td = 0, te = 0;
+    for (uint32_t i = 0; i < s.len; ++i) {
+      hi = std::max<uint32_t>(hi, s.depths[i]); lo = std::min<uint32_t>(lo, s.depths[i]);
+      td += s.depths[i]; te += s.errors[i];
+    }
+    *mx = static_cast<int32_t>(hi); *mn = static_cast<int32_t>(lo); *er = error_rate(te, td);
+  };
+  int32_t mx, mn; float er;
+  metrics(d.ab, &mx, &mn, &er);
+  w->integer("aD", mx); w->real("aE", er); w->integer("aM", mn);
+  if (c->opt.produce_per_base_tags) {
+    w->str("ac", d.ab.bases, d.ab.len);
+    w->i16_array("ad", d.ab.depths, d.ab.len);
+    w->i16_array("ae", d.ab.errors, d.ab.len);
+    w->phred33("aq", d.ab.quals, d.ab.len);
+  }
+  metrics(d.ba, &mx, &mn, &er);
+  w->integer("bD", mx); w->real("bE", er); w->integer("bM", mn);
+  if (c->opt.produce_per_base_tags && d.ba.present) {
+    w->str("bc", d.ba.bases, d.ba.len);
+    w->i16_array("bd", d.ba.depths, d.ba.len);
+    w->i16_array("be", d.ba.errors, d.ba.len);
+    w->phred33("bq", d.ba.quals, d.ba.len);
+  }
+  int32_t cmx = 0, cmn = d.len ? 0x7FFFFFFF : 0;
+  uint64_t td = 0, te = 0;
+  for (uint32_t i = 0; i < d.len; ++i) {
+    int32_t v = (i < d.ab.len ? d.ab.depths[i] : 0) + ((d.ba.present && i < d.ba.len) ? d.ba.depths[i] : 0);
+    cmx = std::max(cmx, v); cmn = std::min(cmn, v);
+    td += static_cast<uint64_t>(v); te += d.errors[i];
+  }
+  w->integer("cD", cmx); w->real("cE", error_rate(te, td)); w->integer("cM", cmn);
+  // RX: orientation-aware reversal of the '-'-separated halves, :1187-1211
+  std::vector<std::string> umis;
+  auto collect = [&](const std::vector<RxSource>& src) {
+    for (const auto& s : src) {
+      if (s.first == r1) { umis.push_back(s.rx); continue; }
+      std::vector<std::string> parts;
+      size_t start = 0;
+      for (;;) {
+        size_t p = s.rx.find('-', start);
+        if (p == std::string::npos) { parts.push_back(s.rx.substr(start)); break; }
+        parts.push_back(s.rx.substr(start, p - start));
+        start = p + 1;
+      }
+      std::string rev;
+      for (size_t k = parts.size(); k-- > 0;) { rev += parts[k]; if (k) rev += '-'; }
+      umis.push_back(rev);
+    }
+  };
+  collect(src_a);
+  collect(src_b);
+  fgb_status st = append_rx(c, w, umis);
+  if (st != FGB_OK) return st;
+  w->end();
+  ++c->out_count;
+  return FGB_OK;
+}
+
+fgb_status flush_duplex(fgb_caller* c) {
+  const uint64_t U = c->pack.units.size();
+  if (!U) return FGB_OK;
+  uint64_t n_bytes, R;
+  c->pack.seal(&n_bytes, &R);
+  uint64_t n_tiles = 0;
+  fgb_status st = fgb_plan_tiles(c->pack.units.data(), U, c->pack.reads.data(), R, nullptr, 0, &n_tiles);
+  if (st != FGB_OK) { c->last_error = "fgb_plan_tiles failed"; return st; }
+  std::vector<fgb_tile> tiles(n_tiles ? n_tiles : 1);
+  if ((st = fgb_plan_tiles(c->pack.units.data(), U, c->pack.reads.data(), R, tiles.data(), n_tiles, &n_tiles)) != FGB_OK) return st;
+  const uint64_t no = c->pack.n_out, nd = c->n_duplex_out;
+  std::vector<uint8_t> sb(no + 8), sq(no + 8), db(nd + 8), dq(nd + 8), dst(c->jobs.size() + 1);
+  std::vector<uint16_t> sd(no + 8), se(no + 8), de(nd + 8);
+  fgb_batch b;
+  b.n_units = U; b.n_reads = R; b.n_bytes = n_bytes; b.n_out = no; b.n_tiles = n_tiles;
+  b.bases = c->pack.bases.data(); b.quals = c->pack.quals.data(); b.reads = c->pack.reads.data();
+  b.units = c->pack.units.data(); b.tiles = tiles.data();
+  fgb_columns ss{sb.data(), sq.data(), sd.data(), se.data()};
+  fgb_duplex_out dout{db.data(), dq.data(), de.data(), dst.data()};
+  st = fgb_duplex_submit(c->h, &b, &ss, c->jobs.data(), c->jobs.size(), nd, &dout);
+  if (st != FGB_OK) {
+    char buf[256];
+    fgb_last_error(c->h, buf, sizeof(buf));
+    c->last_error = buf;
+    return st;
+  }
+  auto strand_of = [&](uint32_t unit, uint32_t len) {
+    Strand s;
+    const fgb_unit& u = c->pack.units[unit];
+    s.bases = sb.data() + u.out_off; s.quals = sq.data() + u.out_off;
+    s.depths = sd.data() + u.out_off; s.errors = se.data() + u.out_off;
+    s.len = len; s.present = true;
+    return s;
+  };
+  bam::Writer w(&c->out);
+  for (const Molecule& m : c->molecules) {
+    DuplexRead d[2];
+    bool ok = true;
+    if (m.pattern == 0) {
+      const uint32_t ua[2] = {m.unit[0], m.unit[1]}, ub[2] = {m.unit[3], m.unit[2]};
+      for (int k = 0; k < 2 && ok; ++k) {
+        const fgb_duplex_job& j = c->jobs[m.job[k]];
+        const uint32_t la = c->pack.units[ua[k]].cons_len, lb = c->pack.units[ub[k]].cons_len;
+        const uint8_t status = dst[m.job[k]];
+        DuplexRead& r = d[k];
+        r.bases = db.data() + j.out_off; r.quals = dq.data() + j.out_off; r.errors = de.data() + j.out_off;
+        if (status == FGB_DUPLEX_BOTH) {            // ab/ba truncated to the duplex length, :972-991
+          r.len = std::min(la, lb);
+          r.ab = strand_of(ua[k], r.len); r.ba = strand_of(ub[k], r.len);
+        } else if (status == FGB_DUPLEX_A_ONLY) {   // :855-868
+          r.len = la; r.ab = strand_of(ua[k], la); r.ba = Strand();
+        } else if (status == FGB_DUPLEX_B_ONLY) {   // :869-882 (is_ba_only: BA sits in the ab slot)
+          r.len = lb; r.ab = strand_of(ub[k], lb); r.ba = Strand();
+        } else {
+          ok = false;                               // duplex_consensus returned None
+        }
+      }
+      if (ok) {   // duplex_consensus_has_minimum_reads on both reads, :2036-2047
+        for (int k = 0; k < 2; ++k)
+          if (!min_reads_ok(c, max_depth(d[k].ab), d[k].ba.present ? max_depth(d[k].ba) : 0)) ok = false;
+      }
+      if (!ok) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, m.n_input); continue; }
+      if ((st = write_duplex_record(c, &w, d[0], true, m, m.rx[0], m.rx[3])) != FGB_OK) return st;
+      if ((st = write_duplex_record(c, &w, d[1], false, m, m.rx[1], m.rx[2])) != FGB_OK) return st;
+      c->stats[FGB_STAT_CONSENSUS_READS] += 1;
+    } else {
+      // single-strand molecule (min_yx_reads == 0): duplex_consensus(Some, None) keeps the strand
+      // only if it has depth somewhere (:852-853)
+      const uint32_t u1 = m.pattern == 1 ? m.unit[0] : m.unit[3];   // R1 from AB-R1 / BA-R2
+      const uint32_t u2 = m.pattern == 1 ? m.unit[1] : m.unit[2];   // R2 from AB-R2 / BA-R1
+      const uint32_t us[2] = {u1, u2};
+      for (int k = 0; k < 2 && ok; ++k) {
+        Strand s = strand_of(us[k], c->pack.units[us[k]].cons_len);
+        if (max_depth(s) == 0) { ok = false; break; }
+        d[k].bases = s.bases; d[k].quals = s.quals; d[k].errors = s.errors; d[k].len = s.len;
+        d[k].ab = s; d[k].ba = Strand();
+      }
+      if (!ok) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, m.n_input); continue; }
+      static const std::vector<RxSource> kNone;
+      if (m.pattern == 1) {
+        if ((st = write_duplex_record(c, &w, d[0], true, m, m.rx[0], kNone)) != FGB_OK) return st;
+        if ((st = write_duplex_record(c, &w, d[1], false, m, m.rx[1], kNone)) != FGB_OK) return st;
+      } else {
+        if ((st = write_duplex_record(c, &w, d[0], true, m, kNone, m.rx[3])) != FGB_OK) return st;
+        if ((st = write_duplex_record(c, &w, d[1], false, m, kNone, m.rx[2])) != FGB_OK) return st;
+      }
+      c->stats[FGB_STAT_CONSENSUS_READS] += 1;
+    }
+  }
+  return FGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_caller** out) {
+  if (!opt || !out || !opt->read_name_prefix || !opt->read_group_id) return FGB_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (opt->mode != FGB_MODE_SIMPLEX && opt->mode != FGB_MODE_DUPLEX) return FGB_ERR_INVALID_ARG;
+  if (opt->mode == FGB_MODE_SIMPLEX && opt->min_reads == 0) return FGB_ERR_INVALID_ARG;
+  if (opt->mode == FGB_MODE_DUPLEX &&
+      (opt->min_xy_reads > opt->min_reads || opt->min_yx_reads > opt->min_xy_reads))
+    return FGB_ERR_INVALID_ARG;   // "min-reads values must be specified high to low", duplex_caller.rs:385-395
+  std::unique_ptr<fgb_caller> c(new fgb_caller());
+  c->opt = *opt;
+  c->prefix = opt->read_name_prefix;
+  c->rg = opt->read_group_id;
+  c->opt.read_name_prefix = nullptr;
+  c->opt.read_group_id = nullptr;
+  c->prep_opt.min_input_base_quality = opt->min_input_base_quality;
+  c->prep_opt.trim = opt->trim != 0;
+  fgb_params p;
+  p.error_rate_pre_umi = opt->error_rate_pre_umi;
+  p.error_rate_post_umi = opt->error_rate_post_umi;
+  p.reserved0 = 0;
+  if (opt->mode == FGB_MODE_SIMPLEX) {
+    p.min_consensus_base_quality = opt->min_consensus_base_quality;
+    p.min_reads = opt->min_reads;
+  } else {   // single-strand caller of the duplex caller, duplex_caller.rs:397-412
+    p.min_consensus_base_quality = 2;
+    p.min_reads = 1;
+  }
+  fgb_status st = fgb_create(device, &p, &c->h);
+  if (st != FGB_OK) return st;
+  *out = c.release();
+  return FGB_OK;
+}
+
+void fgb_caller_destroy(fgb_caller* c) {
+  if (!c) return;
+  fgb_destroy(c->h);
+  delete c;
+}
+
+size_t fgb_caller_last_error(const fgb_caller* c, char* buf, size_t buf_len) {
+  if (!c) return 0;
+  if (buf && buf_len) {
+    size_t n = std::min(buf_len - 1, c->last_error.size());
+    std::memcpy(buf, c->last_error.data(), n);
+    buf[n] = 0;
+  }
+  return c->last_error.size();
+}
+
+fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
+                                uint32_t n_records) {
+  if (!c || (n_records && (!records || !rec_off))) return FGB_ERR_INVALID_ARG;
+  if (n_records == 0) return FGB_OK;
+  std::vector<View> recs;
+  recs.reserve(n_records);
+  for (uint32_t i = 0; i < n_records; ++i) {
+    size_t len = static_cast<size_t>(rec_off[i + 1] - rec_off[i]);
+    if (len < 32) { c->last_error = "BAM record shorter than its fixed header"; return FGB_ERR_INVALID_ARG; }
+    recs.emplace_back(records + rec_off[i], len);
+    if (recs.back().aux_off() > len) { c->last_error = "truncated BAM record"; return FGB_ERR_INVALID_ARG; }
+  }
+  return c->opt.mode == FGB_MODE_DUPLEX ? add_group_duplex(c, recs) : add_group_simplex(c, recs);
+}
+
+fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* out_len,
+                            uint64_t* out_count) {
+  if (!c || !out_data || !out_len || !out_count) return FGB_ERR_INVALID_ARG;
+  c->out.clear();
+  c->out_count = 0;
+  fgb_status st = c->opt.mode == FGB_MODE_DUPLEX ? flush_duplex(c) : flush_simplex(c);
+  c->pack.clear(); c->metas.clear(); c->molecules.clear(); c->jobs.clear();
+  c->n_duplex_out = 0;
+  if (st != FGB_OK) return st;
+  *out_data = c->out.data();
+  *out_len = c->out.size();
+  *out_count = c->out_count;
+  return FGB_OK;
+}
+
+fgb_status fgb_caller_stats(const fgb_caller* c, uint64_t stats[FGB_NSTATS]) {
+  if (!c || !stats) return FGB_ERR_INVALID_ARG;
+  std::memcpy(stats, c->stats, sizeof(c->stats));
+  return FGB_OK;
+}
+
+}  // extern "C"

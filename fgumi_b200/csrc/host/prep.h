@@ -1,0 +1,260 @@
+// Shared host-side preparation code of the record-level callers (product code, header-only):
+// source-read creation, CIGAR grouping, RX consensus and the SoA batch packer.
+//
+// Behavioural spec (reference = /root/reference/crates/fgumi-consensus/src/):
+//   vanilla_caller.rs:47-119    select_most_common_alignment_group
+//   vanilla_caller.rs:780-804   find_quality_trim_point
+//   vanilla_caller.rs:863-955   create_source_read
+//   vanilla_caller.rs:961-1013  filter_source_reads_by_alignment
+//   vanilla_caller.rs:1269-1277 consensus length = min_reads-th longest read
+//   simple_umi.rs:36-134,236-245  SimpleConsensusCaller / consensus_umis
+#pragma once
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../../include/fgumi_b200.h"
+#include "../host_math.h"
+#include "../host_tables.h"
+#include "bam.h"
+
+namespace fgb {
+namespace prep {
+
+using bam::View;
+
+inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+struct PrepOptions {
+  uint8_t min_input_base_quality = 10;
+  bool trim = false;
+};
+
+struct SourceRead {
+  uint32_t original_idx = 0;
+  uint16_t flags = 0;
+  std::vector<uint8_t> bases, quals;
+  bam::SimpleCigar cigar;
+};
+
+// Host ConsensusBaseBuilder for the RX (UMI) consensus only (simple_umi.rs:36-134): f64, literal.
+struct UmiBuilder {
+  HostTables t;
+  UmiBuilder() { build_host_tables(90, 90, &t); }   // simple_umi.rs:13-19 defaults (90, 90, Q20)
+  // One column of characters, all DNA (A/C/G/T/N, any case); returns the called base.
+  uint8_t call(const std::vector<uint8_t>& col) const {
+    using namespace hostmath;
+    double ll[4] = {0, 0, 0, 0}, kc[4] = {0, 0, 0, 0};
+    uint32_t obs[4] = {0, 0, 0, 0};
+    const double c = t.correct[20], e = t.err_alt[20];
+    for (uint8_t ch : col) {
+      int idx;
+      switch (ch) {
+        case 'A': case 'a': idx = 0; break;
+        case 'C': case 'c': idx = 1; break;
+        case 'G': case 'g': idx = 2; break;
+        case 'T': case 't': idx = 3; break;
+        default: idx = -1;
+      }
+      if (idx < 0) continue;   // 'N' is ignored by add(), base_builder.rs:300
+      for (int i = 0; i < 4; ++i) {   // base_builder.rs:312-324
+        double v = i == idx ? c : e;
+        double y = v - kc[i];
+        double s = ll[i] + y;
+        kc[i] = (s - ll[i]) - y;
+        ll[i] = s;
+      }
+      obs[idx]++;
+    }
+    const uint32_t depth = obs[0] + obs[1] + obs[2] + obs[3];
+    if (depth == 0) return 'N';
+    int kinds = (obs[0] != 0) + (obs[1] != 0) + (obs[2] != 0) + (obs[3] != 0);
+    static const char kB[5] = "ACGT";
+    if (kinds == 1) {
+      int w = obs[0] ? 0 : obs[1] ? 1 : obs[2] ? 2 : 3;
+      if (ll[w] - ll[(w + 1) % 4] > 23.0) return kB[w];
+    }
+    double mx = kNegInf;
+    int mi = -1;
+    bool tie = false;
+    for (int i = 0; i < 4; ++i) {   // base_builder.rs:413-431
+      if (ll[i] > mx) { mx = ll[i]; mi = i; tie = false; }
+      else if (ll[i] == mx) tie = true;
+      else if (ll[i] < mx && std::fabs(ll[i] - mx) <= DBL_EPSILON) tie = true;
+    }
+    if (tie || mi < 0) return 'N';
+    return kB[mi];
+  }
+};
+
+
+// find_quality_trim_point, vanilla_caller.rs:780-804
+inline size_t quality_trim_point(const std::vector<uint8_t>& q, uint8_t trim_qual) {
+  size_t length = q.size();
+  if (trim_qual < 1 || length == 0) return 0;
+  int32_t score = 0, max_score = 0;
+  size_t trim_point = length;
+  for (size_t i = length; i-- > 0;) {
+    score += static_cast<int32_t>(trim_qual) - static_cast<int32_t>(q[i]);
+    if (score < 0) break;
+    if (score > max_score) { max_score = score; trim_point = i; }
+  }
+  return trim_point;
+}
+
+
+// create_source_read, vanilla_caller.rs:863-955
+inline bool make_source_read(const PrepOptions& opt, const View& v, uint32_t idx, size_t mate_clip,
+                             std::vector<uint32_t>* ops, SourceRead* sr) {
+  const bool neg = v.flags() & bam::kReverse;
+  const uint8_t min_bq = opt.min_input_base_quality;
+  bam::decode_sequence(v, &sr->bases);
+  const uint32_t read_len = v.l_seq();
+  if (read_len == 0 || v.qual_off() + read_len > v.n) return false;
+  sr->quals.assign(v.b + v.qual_off(), v.b + v.qual_off() + read_len);
+  bool all_ff = true;
+  for (uint8_t q : sr->quals) if (q != 0xFF) { all_ff = false; break; }
+  if (all_ff) return false;
+  if (neg) {
+    std::reverse(sr->bases.begin(), sr->bases.end());
+    for (auto& b : sr->bases) b = bam::complement(b);
+    std::reverse(sr->quals.begin(), sr->quals.end());
+  }
+  const size_t trim_to = opt.trim ? quality_trim_point(sr->quals, min_bq) : read_len;
+  for (size_t i = 0; i < trim_to; ++i)
+    if (sr->quals[i] < min_bq) { sr->bases[i] = 'N'; sr->quals[i] = 2; }
+  const size_t clip_position = read_len > mate_clip ? read_len - mate_clip : 0;
+  size_t final_len = std::min(clip_position, trim_to);
+  while (final_len > 0 && sr->bases[final_len - 1] == 'N') --final_len;
+  if (final_len == 0) return false;
+  sr->bases.resize(final_len);
+  sr->quals.resize(final_len);
+  bam::cigar_ops(v, ops);
+  bam::simplify_cigar(*ops, &sr->cigar);
+  if (neg) std::reverse(sr->cigar.begin(), sr->cigar.end());
+  bam::truncate_cigar(&sr->cigar, final_len);
+  sr->original_idx = idx;
+  sr->flags = v.flags();
+  return true;
+}
+
+
+// filter_source_reads_by_alignment + select_most_common_alignment_group, vanilla_caller.rs:47-119,961-1013
+inline size_t filter_by_alignment(std::vector<SourceRead>* srs) {
+  const size_t n = srs->size();
+  if (n < 2) return 0;
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    return (*srs)[a].bases.size() > (*srs)[b].bases.size();
+  });
+  struct Group { const bam::SimpleCigar* cigar; std::vector<uint32_t> members; };
+  std::vector<Group> groups;
+  for (uint32_t idx : order) {
+    const bam::SimpleCigar& cg = (*srs)[idx].cigar;
+    bool found = false;
+    for (auto& g : groups)
+      if (bam::is_cigar_prefix(cg, *g.cigar)) { g.members.push_back(idx); found = true; }   // no break (fgbio)
+    if (!found) groups.push_back(Group{&cg, {idx}});
+  }
+  // Iterator::max_by keeps the LAST maximum: larger group wins, then the smaller CIGAR
+  const Group* best = nullptr;
+  for (const auto& g : groups) {
+    if (!best) { best = &g; continue; }
+    int cmp = g.members.size() < best->members.size() ? -1 : (g.members.size() > best->members.size() ? 1 : 0);
+    if (cmp == 0) cmp = bam::cmp_cigar(*best->cigar, *g.cigar);
+    if (cmp >= 0) best = &g;
+  }
+  std::vector<char> keep(n, 0);
+  for (uint32_t i : best->members) keep[i] = 1;
+  size_t kept = 0;
+  for (char k : keep) kept += k;
+  std::vector<SourceRead> out;
+  out.reserve(kept);
+  for (size_t i = 0; i < n; ++i) if (keep[i]) out.push_back(std::move((*srs)[i]));
+  srs->swap(out);
+  return n - kept;
+}
+
+
+// consensus_umis, simple_umi.rs:65-122,236-245.  Returns false for the reference's panics
+// (length mismatch, DNA / non-DNA mix).
+inline bool consensus_umis(const UmiBuilder& builder, const std::vector<std::string>& umis, std::string* out) {
+  out->clear();
+  if (umis.empty()) return true;
+  if (umis.size() == 1) { *out = umis[0]; return true; }
+  const std::string& first = umis[0];
+  for (const auto& s : umis) if (s.size() != first.size()) return false;
+  auto is_dna = [](uint8_t ch) {
+    switch (ch) { case 'A': case 'C': case 'G': case 'T': case 'N':
+                  case 'a': case 'c': case 'g': case 't': case 'n': return true; default: return false; }
+  };
+  std::vector<uint8_t> col(umis.size());
+  for (size_t i = 0; i < first.size(); ++i) {
+    size_t non_dna = 0;
+    for (size_t k = 0; k < umis.size(); ++k) {
+      col[k] = static_cast<uint8_t>(umis[k][i]);
+      if (!is_dna(col[k])) {
+        ++non_dna;
+        if (col[k] != static_cast<uint8_t>(first[i])) return false;
+      }
+    }
+    if (non_dna == 0) out->push_back(static_cast<char>(builder.call(col)));
+    else if (non_dna == umis.size()) out->push_back(first[i]);
+    else return false;
+  }
+  return true;
+}
+
+
+// The packed SoA batch of include/fgumi_b200.h, grown unit by unit.
+struct Packer {
+  std::vector<uint8_t> bases, quals;
+  std::vector<uint64_t> reads;
+  std::vector<fgb_unit> units;
+  uint64_t n_out = 0;
+  // Appends one unit (its SourceRead rows); returns the unit index.
+  uint32_t add_unit(const std::vector<SourceRead>& srs, size_t min_reads) {
+    fgb_unit u;
+    u.out_off = n_out;
+    u.read_begin = static_cast<uint32_t>(reads.size());
+    std::vector<size_t> lens;
+    for (const auto& sr : srs) {
+      size_t off = bases.size();
+      size_t len = sr.bases.size();
+      reads.push_back(FGB_READ_DESC(off, len));
+      bases.insert(bases.end(), sr.bases.begin(), sr.bases.end());
+      quals.insert(quals.end(), sr.quals.begin(), sr.quals.end());
+      size_t pad = round_up(len, FGB_READ_ALIGN) - len;
+      bases.insert(bases.end(), pad, 0);
+      quals.insert(quals.end(), pad, 0);
+      lens.push_back(len);
+    }
+    std::sort(lens.begin(), lens.end(), std::greater<size_t>());
+    u.cons_len = static_cast<uint32_t>(lens[min_reads - 1]);   // vanilla_caller.rs:1269-1277
+    units.push_back(u);
+    n_out += round_up(u.cons_len, FGB_OUT_ALIGN);
+    return static_cast<uint32_t>(units.size() - 1);
+  }
+  // Seals the batch (sentinel unit, 16-byte column padding, descriptor padding).
+  void seal(uint64_t* n_bytes, uint64_t* n_reads) {
+    fgb_unit sentinel;
+    sentinel.out_off = n_out;
+    sentinel.read_begin = static_cast<uint32_t>(reads.size());
+    sentinel.cons_len = 0;
+    units.push_back(sentinel);
+    *n_bytes = bases.size();
+    bases.resize(round_up(bases.size() + 1, 16), 0);
+    quals.resize(bases.size(), 0);
+    *n_reads = reads.size();
+    reads.resize(reads.size() + 2, 0);
+  }
+  void clear() { bases.clear(); quals.clear(); reads.clear(); units.clear(); n_out = 0; }
+};
+
+}  // namespace prep
+}  // namespace fgb

@@ -19,6 +19,7 @@ FGB_ERR_LAYOUT = 4
 FGB_ERR_UNIT_TOO_LARGE = 5
 FGB_ERR_NOMEM = 6
 FGB_ERR_BUSY = 7
+FGB_ERR_MISSING_TAG = 8
 
 FGB_READ_ALIGN = 8
 FGB_OUT_ALIGN = 8
@@ -117,7 +118,8 @@ class FgbCallerOptions(C.Structure):
         ("mode", C.c_uint8), ("error_rate_pre_umi", C.c_uint8), ("error_rate_post_umi", C.c_uint8),
         ("min_input_base_quality", C.c_uint8), ("min_consensus_base_quality", C.c_uint8),
         ("produce_per_base_tags", C.c_uint8), ("trim", C.c_uint8), ("reserved0", C.c_uint8),
-        ("min_reads", C.c_uint32), ("tag", C.c_char * 2), ("cell_tag", C.c_char * 2),
+        ("min_reads", C.c_uint32), ("min_xy_reads", C.c_uint32), ("min_yx_reads", C.c_uint32),
+        ("tag", C.c_char * 2), ("cell_tag", C.c_char * 2),
         ("read_name_prefix", C.c_char_p), ("read_group_id", C.c_char_p),
     ]
 
@@ -125,7 +127,7 @@ class FgbCallerOptions(C.Structure):
 FGB_NSTATS = 16
 STAT_NAMES = ("total_reads", "consensus_reads", "filtered_reads", "InsufficientReads",
               "SecondaryOrSupplementary", "ZeroLengthAfterTrimming", "MinorityAlignment",
-              "OrphanConsensus")
+              "OrphanConsensus", "PotentialCollision")
 
 
 class FgbCodecOut(C.Structure):
@@ -140,7 +142,7 @@ SYMBOLS = (
     "fgb_plan_tiles", "fgb_vote_device", "fgb_submit", "fgb_wait", "fgb_host_alloc",
     "fgb_host_free", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
-    "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
+    "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats",
 )
 
@@ -208,6 +210,12 @@ def load() -> C.CDLL:
                                              u64, C.POINTER(FgbCodecParams),
                                              C.POINTER(FgbCodecOut), vp]
     lib.fgb_codec_combine_device.restype = C.c_int32
+    lib.fgb_duplex_submit.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), vp, u64, u64,
+                                      C.POINTER(FgbDuplexOut)]
+    lib.fgb_duplex_submit.restype = C.c_int32
+    lib.fgb_codec_submit.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), vp, u64,
+                                     C.POINTER(FgbCodecParams), u64, C.POINTER(FgbCodecOut)]
+    lib.fgb_codec_submit.restype = C.c_int32
     lib.fgb_stats.argtypes = [vp, C.POINTER(u64)]
     lib.fgb_stats.restype = C.c_int32
     lib.fgb_stats_device_ptr.argtypes = [vp, C.POINTER(vp)]

@@ -269,6 +269,18 @@ fgb_status fgb_codec_combine_device(fgb_handle* h, const fgb_batch* in, const fg
                                     const fgb_codec_params* cp, const fgb_codec_out* out,
                                     void* stream);
 
+/* Host-buffer forms of vote + strand combine (what the duplex / CODEC callers use): every pointer
+ * is a HOST pointer.  One shot and synchronous: the batch is copied to the device, voted, combined,
+ * and BOTH the single-strand columns (`ss_out`, needed for the ac/ad/ae/aq, bc/bd/be/bq tags) and the
+ * combined columns are copied back before the call returns.  n_*_out = elements in each combined
+ * output column. */
+fgb_status fgb_duplex_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss_out,
+                             const fgb_duplex_job* jobs, uint64_t n_jobs, uint64_t n_duplex_out,
+                             const fgb_duplex_out* out);
+fgb_status fgb_codec_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss_out,
+                            const fgb_codec_job* jobs, uint64_t n_jobs, const fgb_codec_params* cp,
+                            uint64_t n_codec_out, const fgb_codec_out* out);
+
 /* ---- statistics, K4 -------------------------------------------------------------------- */
 /* Synchronises the handle's streams and copies the device counters (cumulative). */
 fgb_status fgb_stats(fgb_handle* h, uint64_t counters[FGB_NCOUNTERS]);
@@ -296,7 +308,11 @@ typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanill
   uint8_t produce_per_base_tags;           /* 1  */
   uint8_t trim;                            /* 0  */
   uint8_t reserved0;
-  uint32_t min_reads;                      /* 2 (library default); CLI: required -M                */
+  uint32_t min_reads;                      /* simplex: -M (per-position depth gate too); duplex:
+                                              min total reads (duplex_caller.rs:358-395)           */
+  uint32_t min_xy_reads;                   /* duplex only: min reads of the better-covered strand  */
+  uint32_t min_yx_reads;                   /* duplex only: min reads of the other strand; 0 allows
+                                              single-strand molecules                              */
   char tag[2];                             /* UMI tag, "MI"                                        */
   char cell_tag[2];                        /* {0,0} = none                                         */
   const char* read_name_prefix;            /* consensus read name = "<prefix>:<MI>"                */
@@ -312,6 +328,7 @@ enum {   /* ConsensusCallingStats (caller.rs:238-286) as a flat counter array   
   FGB_STAT_REJ_ZERO_LENGTH = 5,               /* ::ZeroLengthAfterTrimming                       */
   FGB_STAT_REJ_MINORITY_ALIGNMENT = 6,        /* ::MinorityAlignment                             */
   FGB_STAT_REJ_ORPHAN_CONSENSUS = 7,          /* ::OrphanConsensus                               */
+  FGB_STAT_REJ_POTENTIAL_COLLISION = 8,       /* ::PotentialCollision (duplex_caller.rs:1799-1823) */
   FGB_NSTATS = 16
 };
 

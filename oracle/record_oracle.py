@@ -612,3 +612,242 @@ class VanillaCallerOracle:
             rx = consensus_umis(umis, lambda pre, post, b, q: self.builder_call(pre, post, b, q)[:2])
             rec += tag_string(b"RX", rx.encode())
         return with_block_size(rec)
+
+
+# =================================================================================================
+# Duplex caller — crates/fgumi-consensus/src/duplex_caller.rs
+# =================================================================================================
+@dataclass
+class SsCons:                                          # VanillaConsensusRead, vanilla_caller.rs:152-176
+    bases: bytes
+    quals: bytes
+    depths: list
+    errors: list
+    source_rows: list                                  # [(bases, quals)] of the SourceReads used
+
+
+@dataclass
+class DuplexCons:                                      # DuplexConsensusRead
+    bases: bytes
+    quals: bytes
+    errors: list
+    ab: SsCons
+    ba: Optional[SsCons]
+    is_ba_only: bool = False
+
+
+class DuplexCallerOracle:
+    """DuplexConsensusCaller::consensus_reads, duplex_caller.rs:2206-2250 + process_group :1719-2202."""
+
+    def __init__(self, prefix: str, rg: str, min_reads=(1, 1, 1), pre=45, post=40, min_input_q=10,
+                 per_base=True, trim=False, cell_tag: Optional[bytes] = None, vote_fn=None,
+                 builder_fn=None, duplex_job_fn=None):
+        self.prefix, self.rg = prefix, rg
+        self.min_total, self.min_xy, self.min_yx = min_reads
+        self.per_base, self.cell_tag = per_base, cell_tag
+        # ss_options, duplex_caller.rs:397-412: min_reads 1, min_consensus_base_quality MIN_PHRED
+        self.ss_opt = VanillaOptions(error_rate_pre_umi=pre, error_rate_post_umi=post,
+                                     min_input_base_quality=min_input_q, min_reads=1,
+                                     produce_per_base_tags=per_base, trim=trim,
+                                     min_consensus_base_quality=2, cell_tag=cell_tag)
+        self.vote, self.builder_call, self.duplex_job = vote_fn, builder_fn, duplex_job_fn
+        self.stats = Stats()
+
+    # ---- consensus_reads :2206-2250 + partition_records_by_strand :576-630 ----
+    def consensus_reads(self, records: List[bytes]) -> Tuple[bytes, int]:
+        self.stats.total_reads += len(records)
+        if not records:
+            return b"", 0
+        recs = [Rec(b) for b in records]
+        base_mi, a, b = None, [], []
+        for r in recs:
+            mi = r.find_string(b"MI")
+            if mi is None:
+                raise ValueError("missing MI tag")
+            if base_mi is None:
+                base_mi = (mi[:-2] if len(mi) >= 2 else mi).decode("utf-8", "replace")
+            if len(mi) >= 2 and mi[-2:] == b"/A":
+                a.append(r)
+            elif len(mi) >= 2 and mi[-2:] == b"/B":
+                b.append(r)
+            else:
+                raise ValueError("MI tag without /A or /B suffix")
+        return self._process_group(base_mi, a, b)
+
+    @staticmethod
+    def _r1(r):
+        return bool(r.flags & PAIRED) and bool(r.flags & FIRST_SEGMENT)
+
+    @staticmethod
+    def _r2(r):
+        return bool(r.flags & PAIRED) and bool(r.flags & LAST_SEGMENT)
+
+    def _min_ok(self, na, nb):                         # :731-749 / :753-769
+        xy, yx = (na, nb) if na >= nb else (nb, na)
+        return self.min_total <= xy + yx and self.min_xy <= xy and self.min_yx <= yx
+
+    def _consensus_call(self, srs: List[SourceRead]) -> Optional[SsCons]:   # vanilla_caller.rs:628-668
+        if not srs or len(srs) < self.ss_opt.min_reads:
+            return None
+        rows = [(bytes(s.bases), bytes(s.quals)) for s in srs]
+        b, q, d, e = self.vote(rows, self.ss_opt)
+        return SsCons(b, q, d, e, rows)
+
+    def _duplex_consensus(self, a: Optional[SsCons], b: Optional[SsCons], with_sources: bool):
+        """duplex_consensus :838-1015 via the C++ oracle's arms."""
+        if a is not None and b is not None:
+            src = (a.source_rows + b.source_rows) if with_sources else []
+            st, ob, oq, oe = self.duplex_job(a, b, src)
+            if st == 0:
+                n = len(ob)
+                ab = SsCons(a.bases[:n], a.quals[:n], a.depths[:n], a.errors[:n], [])
+                ba = SsCons(b.bases[:n], b.quals[:n], b.depths[:n], b.errors[:n], [])
+                return DuplexCons(ob, oq, oe, ab, ba, False)
+            if st == 1:
+                return DuplexCons(a.bases, a.quals, list(a.errors), a, None, False)
+            if st == 2:
+                return DuplexCons(b.bases, b.quals, list(b.errors), b, None, True)
+            return None
+        one, ba_only = (a, False) if a is not None else (b, True)
+        if one is None:
+            return None
+        # len = own length; the strand is kept only if it has depth somewhere (:852-853)
+        if not any(d > 0 for d in one.depths):
+            return None
+        return DuplexCons(one.bases, one.quals, list(one.errors), one, None, ba_only)
+
+    def _process_group(self, base_mi: str, a: List[Rec], b: List[Rec]):
+        st = self.stats
+        if not a and not b:
+            return b"", 0
+        na = sum(1 for r in a if self._r1(r))
+        nb = sum(1 for r in b if self._r1(r))
+        if not self._min_ok(na, nb):
+            st.reject("InsufficientReads", len(a) + len(b))
+            return b"", 0
+        cell = None
+        if self.cell_tag is not None:
+            first = a[0] if a else (b[0] if b else None)
+            if first is not None:
+                v = first.find_string(self.cell_tag)
+                cell = v if v is not None else None
+        ab_r1 = [r for r in a if self._r1(r)]; ab_r2 = [r for r in a if self._r2(r)]
+        ba_r1 = [r for r in b if self._r1(r)]; ba_r2 = [r for r in b if self._r2(r)]
+
+        def same_strand(rs):
+            return len({bool(r.flags & REVERSE) for r in rs}) <= 1
+        if a and b:
+            if not same_strand(ab_r1 + ba_r2) or not same_strand(ab_r2 + ba_r1):
+                st.reject("PotentialCollision", len(a) + len(b))
+                return b"", 0
+        x_raws, y_raws = ab_r1 + ba_r2, ab_r2 + ba_r1
+
+        def sources(raws):
+            out = []
+            for i, r in enumerate(raws):
+                sr = create_source_read(r, i, num_bases_extending_past_mate(r), self.ss_opt)
+                if sr is not None:
+                    out.append(sr)
+            return out
+        fx, _ = filter_by_alignment(sources(x_raws))
+        fy, _ = filter_by_alignment(sources(y_raws))
+        f_ab_r1 = [s for s in fx if s.flags & FIRST_SEGMENT]
+        f_ba_r2 = [s for s in fx if not s.flags & FIRST_SEGMENT]
+        f_ab_r2 = [s for s in fy if not s.flags & FIRST_SEGMENT]
+        f_ba_r1 = [s for s in fy if s.flags & FIRST_SEGMENT]
+        raws_ab_r1 = [x_raws[s.original_idx] for s in f_ab_r1]
+        raws_ba_r2 = [x_raws[s.original_idx] for s in f_ba_r2]
+        raws_ab_r2 = [y_raws[s.original_idx] for s in f_ab_r2]
+        raws_ba_r1 = [y_raws[s.original_idx] for s in f_ba_r1]
+        c_ab_r1, c_ab_r2 = self._consensus_call(f_ab_r1), self._consensus_call(f_ab_r2)
+        c_ba_r1, c_ba_r2 = self._consensus_call(f_ba_r1), self._consensus_call(f_ba_r2)
+        out = bytearray()
+        pattern = (c_ab_r1 is not None, c_ab_r2 is not None, c_ba_r1 is not None, c_ba_r2 is not None)
+        if pattern == (True, True, True, True):
+            d1 = self._duplex_consensus(c_ab_r1, c_ba_r2, True)       # :1999-2004
+            d2 = self._duplex_consensus(c_ab_r2, c_ba_r1, True)       # :2008-2012
+            if d1 is not None and d2 is not None:
+                if self._cons_min_ok(d1) and self._cons_min_ok(d2):
+                    out += self._record(d1, "R1", base_mi, raws_ab_r1, raws_ba_r2, True, cell)
+                    out += self._record(d2, "R2", base_mi, raws_ab_r2, raws_ba_r1, False, cell)
+                    st.consensus_reads += 1
+                    return bytes(out), 2
+                st.reject("InsufficientReads", len(a) + len(b))
+                return b"", 0
+        elif pattern == (True, True, False, False):
+            if self.min_yx == 0:
+                d1 = self._duplex_consensus(c_ab_r1, None, False)
+                d2 = self._duplex_consensus(c_ab_r2, None, False)
+                if d1 is not None and d2 is not None:
+                    out += self._record(d1, "R1", base_mi, raws_ab_r1, [], True, cell)
+                    out += self._record(d2, "R2", base_mi, raws_ab_r2, [], False, cell)
+                    st.consensus_reads += 1
+                    return bytes(out), 2
+        elif pattern == (False, False, True, True):
+            if self.min_yx == 0:
+                d1 = self._duplex_consensus(None, c_ba_r2, False)
+                d2 = self._duplex_consensus(None, c_ba_r1, False)
+                if d1 is not None and d2 is not None:
+                    out += self._record(d1, "R1", base_mi, [], raws_ba_r2, True, cell)
+                    out += self._record(d2, "R2", base_mi, [], raws_ba_r1, False, cell)
+                    st.consensus_reads += 1
+                    return bytes(out), 2
+        st.reject("InsufficientReads", len(a) + len(b))
+        return b"", 0
+
+    def _cons_min_ok(self, d: DuplexCons) -> bool:     # :753-769
+        na = max(d.ab.depths) if len(d.ab.depths) else 0
+        nb = (max(d.ba.depths) if len(d.ba.depths) else 0) if d.ba is not None else 0
+        return self._min_ok(int(na), int(nb))
+
+    def _record(self, d: DuplexCons, read_type, umi, raws_a, raws_b, first_of_pair, cell) -> bytes:
+        """duplex_read_into :1048-1285 (methylation off)."""
+        flag = UNMAPPED | PAIRED | MATE_UNMAPPED | (FIRST_SEGMENT if read_type == "R1" else LAST_SEGMENT)
+        rec = unmapped_record(f"{self.prefix}:{umi}".encode(), flag, d.bases, d.quals)
+        rec += tag_string(b"MI", umi.encode())
+        if self.cell_tag is not None and cell is not None:
+            rec += tag_string(self.cell_tag, cell)
+        rec += tag_string(b"RG", self.rg.encode())
+
+        def strand_metrics(s: Optional[SsCons]):
+            if s is None:
+                return 0, 0, np.float32(0.0)
+            mx = int(max(s.depths)) if len(s.depths) else 0
+            mn = int(min(s.depths)) if len(s.depths) else 0
+            td, te = int(sum(int(x) for x in s.depths)), int(sum(int(x) for x in s.errors))
+            return mx, mn, (np.float32(te) / np.float32(td)) if td > 0 else np.float32(0.0)
+        amx, amn, aer = strand_metrics(d.ab)
+        rec += tag_int(b"aD", amx) + tag_float(b"aE", aer) + tag_int(b"aM", amn)
+        if self.per_base:
+            rec += tag_string(b"ac", d.ab.bases)
+            rec += tag_i16_array(b"ad", [min(int(x), 32767) for x in d.ab.depths])
+            rec += tag_i16_array(b"ae", [min(int(x), 32767) for x in d.ab.errors])
+            rec += tag_phred33(b"aq", d.ab.quals)
+        bmx, bmn, ber = strand_metrics(d.ba)
+        rec += tag_int(b"bD", bmx) + tag_float(b"bE", ber) + tag_int(b"bM", bmn)
+        if self.per_base and d.ba is not None:
+            rec += tag_string(b"bc", d.ba.bases)
+            rec += tag_i16_array(b"bd", [min(int(x), 32767) for x in d.ba.depths])
+            rec += tag_i16_array(b"be", [min(int(x), 32767) for x in d.ba.errors])
+            rec += tag_phred33(b"bq", d.ba.quals)
+        n = len(d.bases)
+        comb = [(int(d.ab.depths[i]) if i < len(d.ab.depths) else 0) +
+                (int(d.ba.depths[i]) if (d.ba is not None and i < len(d.ba.depths)) else 0) for i in range(n)]
+        cmx, cmn = (max(comb) if comb else 0), (min(comb) if comb else 0)
+        td, te = sum(comb), int(sum(int(x) for x in d.errors))
+        cer = (np.float32(te) / np.float32(td)) if td > 0 else np.float32(0.0)
+        rec += tag_int(b"cD", cmx) + tag_float(b"cE", cer) + tag_int(b"cM", cmn)
+        umis = []
+        for r in list(raws_a) + list(raws_b):
+            rx = r.find_string(b"RX")
+            if rx is None:
+                continue
+            s = rx.decode("utf-8", "replace")
+            if bool(r.flags & FIRST_SEGMENT) == first_of_pair:
+                umis.append(s)
+            else:
+                umis.append("-".join(reversed(s.split("-"))))
+        if umis:
+            rx = consensus_umis(umis, lambda pre, post, b, q: self.builder_call(pre, post, b, q)[:2])
+            rec += tag_string(b"RX", rx.encode())
+        return with_block_size(rec)

@@ -164,3 +164,132 @@ def test_missing_umi_tag_is_an_error():
         c.add_group([make_record(seq=b"ACGT")])
     assert ei.value.status == fg.lib.FGB_ERR_MISSING_TAG
     c.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# duplex
+# ---------------------------------------------------------------------------------------------------
+def duplex_job_fn(a, b, src_rows):
+    """duplex_consensus arms through the C++ oracle."""
+    import ctypes as C
+    L = O.load()
+    arr8 = lambda x: np.frombuffer(bytes(x), np.uint8).copy()
+    arr16 = lambda x: np.array(list(x), np.uint16)
+    A = [arr8(a.bases), arr8(a.quals), arr16(a.depths), arr16(a.errors)]
+    B = [arr8(b.bases), arr8(b.quals), arr16(b.depths), arr16(b.errors)]
+    keep = [np.frombuffer(r[0], np.uint8).copy() for r in src_rows]
+    ptrs = (C.c_void_p * max(len(keep), 1))(*[k.ctypes.data for k in keep])
+    lens = (C.c_size_t * max(len(keep), 1))(*[len(k) for k in keep])
+    cap = max(len(a.bases), len(b.bases), 1)
+    ob = np.zeros(cap, np.uint8); oq = np.zeros(cap, np.uint8); oe = np.zeros(cap, np.uint16)
+    n = C.c_size_t()
+    st = L.orc_duplex_job(*[x.ctypes.data for x in A], len(a.bases), *[x.ctypes.data for x in B], len(b.bases),
+                          ptrs, lens, len(keep), ob.ctypes.data, oq.ctypes.data, oe.ctypes.data, C.addressof(n))
+    return st, bytes(ob[:n.value]), bytes(oq[:n.value]), list(oe[:n.value])
+
+
+def random_duplex_groups(rng, n_groups, L=50):
+    groups = []
+    for g in range(n_groups):
+        tmpl = ACGT[rng.integers(0, 4, size=3 * L)].tobytes()
+        insert = int(rng.integers(L, 3 * L))
+        n_ab, n_ba = int(rng.integers(0, 5)), int(rng.integers(0, 5))
+        if rng.random() < 0.1:
+            n_ba = 0
+        rx_a, rx_b = b"AAC-GGT", b"GGT-AAC"
+        recs = []
+        collide = rng.random() < 0.05
+        for strand, n in (("A", n_ab), ("B", n_ba)):
+            for d in range(n):
+                def mutate(seq, all_n=False):
+                    s = np.frombuffer(seq, np.uint8).copy()
+                    m = rng.random(len(s)) < 0.04
+                    s[m] = ACGT[rng.integers(0, 4, size=int(m.sum()))]
+                    if all_n:
+                        s[:] = ord("N")
+                    return s.tobytes()
+                q = lambda: rng.integers(8, 41, size=L).astype(np.uint8).tobytes()
+                mi = b"%d/%s" % (g, strand.encode())
+                name = b"m%d%s%d" % (g, strand.encode(), d)
+                fwd, rev = tmpl[:L], tmpl[insert - L:insert]
+                p1, p2 = 500, 500 + insert - L
+                # AB: R1 forward at p1, R2 reverse at p2.  BA: R1 reverse at p2, R2 forward at p1.
+                r1_fwd = (strand == "A")
+                if collide and strand == "B" and d == 0:
+                    r1_fwd = True
+                dead = (g % 13 == 5 and strand == "B")       # a strand whose bases are all N
+                tags = [(b"MI", "Z", mi), (b"RX", "Z", rx_a if strand == "A" else rx_b)]
+                if rng.random() < 0.5:
+                    tags.append((b"CB", "Z", b"CELL"))
+                for which in ("R1", "R2"):
+                    if rng.random() < 0.08:
+                        continue                               # drop a mate now and then
+                    is_fwd = r1_fwd if which == "R1" else not r1_fwd
+                    fl = P | (F1 if which == "R1" else F2) | (MREV if is_fwd else REV)
+                    seq = mutate(fwd if is_fwd else rev, dead)
+                    pos, mpos = (p1, p2) if is_fwd else (p2, p1)
+                    recs.append(make_record(name=name, flags=fl, pos=pos, mate_ref_id=0, mate_pos=mpos,
+                                            tlen=insert if is_fwd else -insert, seq=seq, quals=q(),
+                                            tags=tags + [(b"MC", "Z", b"%dM" % L)]))
+        if recs:
+            groups.append(recs)
+    return groups
+
+
+@pytest.mark.parametrize("min_reads,per_base", [((1, 1, 0), True), ((1, 1, 1), True), ((3, 2, 1), False),
+                                                ((2, 1, 0), True)])
+def test_duplex_caller_bytes_match_oracle(min_reads, per_base):
+    import fgumi_b200 as fg
+    rng = np.random.default_rng(7 + sum(min_reads))
+    groups = random_duplex_groups(rng, 220)
+    caller = fg.DuplexConsensusCaller("fgumi", "A", min_reads=min_reads, produce_per_base_tags=per_base,
+                                      device=0, cell_tag=b"CB")
+    got = caller.consensus_reads_batch(groups)
+    gstats = caller.statistics()
+    caller.close()
+    oracle = R.DuplexCallerOracle("fgumi", "A", min_reads=min_reads, per_base=per_base, cell_tag=b"CB",
+                                  vote_fn=vote_fn, builder_fn=O.builder_call, duplex_job_fn=duplex_job_fn)
+    want, count = bytearray(), 0
+    for g in groups:
+        d, n = oracle.consensus_reads(g)
+        want += d
+        count += n
+    assert got.count == count
+    if got.data != bytes(want):
+        a, b = parse_records(got.data), parse_records(bytes(want))
+        for i, (x, y) in enumerate(zip(a, b)):
+            assert x == y, (i, x, y)
+    assert got.data == bytes(want)
+    s = oracle.stats
+    assert gstats["total_reads"] == s.total_reads and gstats["consensus_reads"] == s.consensus_reads
+    assert gstats["filtered_reads"] == s.filtered_reads
+    assert gstats["InsufficientReads"] == s.rejections.get("InsufficientReads", 0)
+    assert gstats["PotentialCollision"] == s.rejections.get("PotentialCollision", 0)
+    assert count >= 40 and s.rejections.get("PotentialCollision", 0) > 0
+    recs = parse_records(got.data)
+    assert recs[0]["tag_order"][:3] in ([b"MI", b"CB", b"RG"], [b"MI", b"RG", b"aD"])
+    if min_reads[2] == 0:
+        assert any(b"bc" not in r["tags"] for r in recs)      # single-strand molecules were emitted
+
+
+def test_duplex_known_answer_end_to_end():
+    """duplex_caller.rs:3368-3405: a 4-read molecule (AB pair + BA pair) gives 2 duplex records."""
+    import fgumi_b200 as fg
+    L = 20
+    seq, rc = b"ACGTACGTACGTACGTACGT", b"ACGTACGTACGTACGTACGT"
+    def rd(name, mi, first, fwd):
+        fl = P | (F1 if first else F2) | (MREV if fwd else REV)
+        return make_record(name=name, flags=fl, pos=100 if fwd else 200, mate_ref_id=0, mate_pos=200 if fwd else 100,
+                           tlen=120 if fwd else -120, seq=seq, quals=[30] * L,
+                           tags=[(b"MI", "Z", mi), (b"RX", "Z", b"ACG-TTA"), (b"MC", "Z", b"20M")])
+    grp = [rd(b"a", b"1/A", True, True), rd(b"a", b"1/A", False, False),
+           rd(b"b", b"1/B", True, False), rd(b"b", b"1/B", False, True)]
+    c = fg.DuplexConsensusCaller("fgumi", "A", min_reads=(1, 1, 1))
+    out = c.consensus_reads_batch([grp])
+    st = c.statistics()
+    c.close()
+    recs = parse_records(out.data)
+    assert out.count == 2 and [r["flags"] for r in recs] == [0x4D, 0x8D]
+    assert recs[0]["name"] == b"fgumi:1" and recs[0]["tags"][b"MI"] == b"1"
+    assert recs[0]["tags"][b"aD"] == 1 and recs[0]["tags"][b"bD"] == 1 and recs[0]["tags"][b"cD"] == 2
+    assert st["consensus_reads"] == 1 and st["total_reads"] == 4
