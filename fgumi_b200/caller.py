@@ -126,3 +126,38 @@ class DuplexConsensusCaller(VanillaUmiConsensusCaller):
         o.read_name_prefix = self._prefix
         o.read_group_id = self._rg
         self._create(o, device)
+
+
+class CodecConsensusCaller(VanillaUmiConsensusCaller):
+    """CodecConsensusCaller::new (codec_caller.rs:306-370) with CodecConsensusOptions (:99-166).
+    `max_reads_per_strand` (seeded down-sampling) is not offered; None is the reference default."""
+
+    def __init__(self, read_name_prefix: str, read_group_id: str, min_reads_per_strand: int = 1,
+                 min_duplex_length: int = 1, error_rate_pre_umi: int = 45, error_rate_post_umi: int = 40,
+                 single_strand_qual=None, outer_bases_qual=None, outer_bases_length: int = 5,
+                 max_duplex_disagreements=None, max_duplex_disagreement_rate: float = 1.0,
+                 produce_per_base_tags: bool = False, device: int = 0, cell_tag: bytes = b""):
+        self._lib = _l.load()
+        self._prefix = read_name_prefix.encode()
+        self._rg = read_group_id.encode()
+        o = _l.FgbCallerOptions()
+        o.mode = 2
+        o.error_rate_pre_umi = error_rate_pre_umi
+        o.error_rate_post_umi = error_rate_post_umi
+        o.min_input_base_quality = 10            # carried by the options, unused on this path
+        o.min_consensus_base_quality = 0
+        o.produce_per_base_tags = 1 if produce_per_base_tags else 0
+        o.trim = 0
+        o.min_reads = min_reads_per_strand
+        o.min_duplex_length = min_duplex_length
+        o.codec.single_strand_qual = -1 if single_strand_qual is None else single_strand_qual
+        o.codec.outer_bases_qual = -1 if outer_bases_qual is None else outer_bases_qual
+        o.codec.outer_bases_length = outer_bases_length
+        o.codec.max_duplex_disagreements = 0xFFFFFFFF if max_duplex_disagreements is None \
+            else max_duplex_disagreements
+        o.codec.max_duplex_disagreement_rate = max_duplex_disagreement_rate
+        o.tag = b"MI"
+        o.cell_tag = cell_tag if cell_tag else b"\0\0"
+        o.read_name_prefix = self._prefix
+        o.read_group_id = self._rg
+        self._create(o, device)

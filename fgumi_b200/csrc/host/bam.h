@@ -260,6 +260,126 @@ inline size_t num_bases_extending_past_mate(const View& v, const std::vector<uin
   return trail > gap ? trail - gap : 0;
 }
 
+
+// ---- virtual CIGAR clipping (cigar.rs:337-841) and ref->query mapping (cigar.rs:412-457) ----
+inline uint32_t enc_op(uint32_t type, size_t len) { return (static_cast<uint32_t>(len) << 4) | type; }
+inline bool consumes_read(uint32_t t) { return t == 0 || t == 1 || t == 7 || t == 8; }
+
+// Existing leading (from_start) or trailing H then S clips; returns how many ops they span.
+inline size_t existing_clips(const std::vector<uint32_t>& ops, bool from_start, size_t* hard, size_t* soft) {
+  *hard = 0; *soft = 0;
+  size_t skip = 0;
+  const size_t n = ops.size();
+  auto at = [&](size_t k) { return from_start ? ops[k] : ops[n - 1 - k]; };
+  while (skip < n && (at(skip) & 0xF) == 5) { *hard += at(skip) >> 4; ++skip; }
+  while (skip < n && (at(skip) & 0xF) == 4) { *soft += at(skip) >> 4; ++skip; }
+  return skip;
+}
+
+// clip_cigar_ops_raw: returns the clipped ops; *ref_consumed = reference bases removed at the start.
+inline std::vector<uint32_t> clip_cigar_ops(const std::vector<uint32_t>& ops, size_t clip_amount,
+                                            bool from_start, size_t* ref_consumed) {
+  *ref_consumed = 0;
+  if (clip_amount == 0 || ops.empty()) return ops;
+  const size_t n = ops.size();
+  size_t existing = 0;
+  for (size_t k = 0; k < n; ++k) {
+    uint32_t op = from_start ? ops[k] : ops[n - 1 - k];
+    if ((op & 0xF) == 4 || (op & 0xF) == 5) existing += op >> 4; else break;
+  }
+  size_t hard, soft;
+  const size_t skip = existing_clips(ops, from_start, &hard, &soft);
+  std::vector<uint32_t> res;
+  if (clip_amount <= existing) {   // upgrade_clipping_raw: soft clips become hard, alignment unchanged
+    size_t up = std::min(soft, clip_amount > hard ? clip_amount - hard : 0);
+    if (from_start) {
+      res.push_back(enc_op(5, hard + up));
+      if (soft - up > 0) res.push_back(enc_op(4, soft - up));
+      res.insert(res.end(), ops.begin() + skip, ops.end());
+    } else {
+      res.assign(ops.begin(), ops.end() - skip);
+      if (soft - up > 0) res.push_back(enc_op(4, soft - up));
+      res.push_back(enc_op(5, hard + up));
+    }
+    return res;
+  }
+  const size_t want = clip_amount - existing;
+  size_t read_clipped = 0, ref_clipped = 0;
+  std::vector<uint32_t> new_ops;
+  if (from_start) {   // clip_cigar_start_raw
+    size_t idx = skip;
+    while (idx < n) {
+      uint32_t op = ops[idx], t = op & 0xF; size_t ln = op >> 4;
+      if (read_clipped == want && new_ops.empty() && t == 2) { ref_clipped += ln; ++idx; continue; }
+      if (read_clipped >= want) break;
+      bool is_read = consumes_read(t), is_ref = consumes_ref(t);
+      if (is_read && ln > want - read_clipped) {
+        if (t == 1) read_clipped += ln;
+        else {
+          size_t rem = want - read_clipped;
+          read_clipped += rem;
+          if (is_ref) ref_clipped += rem;
+          new_ops.push_back(enc_op(t, ln - rem));
+        }
+      } else {
+        if (is_read) read_clipped += ln;
+        if (is_ref) ref_clipped += ln;
+      }
+      ++idx;
+    }
+    res.push_back(enc_op(5, hard + soft + read_clipped));
+    res.insert(res.end(), new_ops.begin(), new_ops.end());
+    res.insert(res.end(), ops.begin() + idx, ops.end());
+    *ref_consumed = ref_clipped;
+    return res;
+  }
+  // clip_cigar_end_raw
+  size_t idx = n - skip;
+  while (idx > 0) {
+    uint32_t op = ops[idx - 1], t = op & 0xF; size_t ln = op >> 4;
+    if (read_clipped == want && new_ops.empty() && t == 2) { --idx; continue; }
+    if (read_clipped >= want) break;
+    bool is_read = consumes_read(t);
+    if (is_read && ln > want - read_clipped) {
+      if (t == 1) read_clipped += ln;
+      else {
+        size_t rem = want - read_clipped;
+        read_clipped += rem;
+        new_ops.push_back(enc_op(t, ln - rem));
+      }
+    } else if (is_read) {
+      read_clipped += ln;
+    }
+    --idx;
+  }
+  res.assign(ops.begin(), ops.begin() + idx);
+  res.insert(res.end(), new_ops.rbegin(), new_ops.rend());
+  res.push_back(enc_op(5, hard + soft + read_clipped));
+  return res;
+}
+
+// read_pos_at_ref_pos_raw: 1-based query position at a 1-based reference position; false = None.
+inline bool read_pos_at_ref_pos(const std::vector<uint32_t>& ops, size_t alignment_start, size_t ref_pos,
+                                bool last_base_if_deleted, size_t* out) {
+  if (ref_pos < alignment_start) return false;
+  size_t ref_off = 0, q_off = 0;
+  for (uint32_t op : ops) {
+    uint32_t t = op & 0xF; size_t ln = op >> 4;
+    size_t op_ref_start = alignment_start + ref_off;
+    if (consumes_ref(t)) {
+      size_t op_ref_end = op_ref_start + ln - 1;
+      if (ref_pos >= op_ref_start && ref_pos <= op_ref_end && ln > 0) {
+        if (consumes_query(t)) { *out = q_off + (ref_pos - op_ref_start) + 1; return true; }
+        if (last_base_if_deleted) { *out = q_off > 0 ? q_off : 1; return true; }
+        return false;
+      }
+      ref_off += ln;
+    }
+    if (consumes_query(t)) q_off += ln;
+  }
+  return false;
+}
+
 // ---- simplified CIGAR ----
 using SimpleCigar = std::vector<std::pair<uint8_t, uint32_t>>;   // (kind 0..8, length)
 
@@ -365,6 +485,10 @@ struct Writer {
   void i16_array(const char t[2], const uint16_t* v, uint32_t n) {   // values clamp to i16::MAX
     tag(t, 'B'); out->push_back('s'); le<uint32_t>(n);
     for (uint32_t i = 0; i < n; ++i) le<int16_t>(static_cast<int16_t>(v[i] > 32767 ? 32767 : v[i]));
+  }
+  void i16_array_wrap(const char t[2], const uint16_t* v, uint32_t n) {   // `as i16` (wrapping)
+    tag(t, 'B'); out->push_back('s'); le<uint32_t>(n);
+    for (uint32_t i = 0; i < n; ++i) le<int16_t>(static_cast<int16_t>(v[i]));
   }
   void phred33(const char t[2], const uint8_t* q, uint32_t n) {
     tag(t, 'Z');

@@ -54,6 +54,18 @@ struct Molecule {                    // duplex: one MI group that reached the vo
   uint8_t pattern = 0;               // 0 full duplex, 1 AB only, 2 BA only
 };
 
+struct CodecMolecule {               // CODEC: one MI group that reached the vote
+  bool has_umi = false;
+  std::string umi;
+  uint32_t unit_r1 = 0, unit_r2 = 0;
+  uint32_t job = 0;
+  bool r1_negative = false;
+  uint32_t cons_len = 0;
+  bool has_cell = false;
+  std::string cell;
+  std::vector<std::string> rx;       // RX of ALL records of the group (codec_caller.rs:1340-1349)
+};
+
 }  // namespace
 
 struct fgb_caller {
@@ -68,6 +80,10 @@ struct fgb_caller {
   std::vector<Molecule> molecules;       // duplex
   std::vector<fgb_duplex_job> jobs;      // duplex
   uint64_t n_duplex_out = 0;
+  std::vector<CodecMolecule> codec_molecules;   // CODEC
+  std::vector<fgb_codec_job> codec_jobs;
+  uint64_t n_codec_out = 0;
+  uint64_t consensus_counter = 0;        // codec_caller.rs:1236
   std::vector<uint8_t> out;              // output of the last flush
   uint64_t out_count = 0;
   std::string last_error;
@@ -570,6 +586,337 @@ fgb_status flush_duplex(fgb_caller* c) {
   return FGB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CODEC
+// ------------------------------------------------------------------------------------------------
+struct ClippedInfo {                 // ClippedRecordInfo, codec_caller.rs
+  uint32_t raw_idx;
+  size_t clip_amount;
+  bool clip_from_start;
+  size_t clipped_seq_len;
+  std::vector<uint32_t> clipped_cigar;
+  size_t adjusted_pos;
+  uint16_t flags;
+};
+
+// build_clipped_info, codec_caller.rs:817-851
+ClippedInfo clipped_info(fgb_caller* c, const View& v, uint32_t idx) {
+  ClippedInfo ci;
+  bam::cigar_ops(v, &c->ops);
+  ci.clip_amount = bam::num_bases_extending_past_mate(v, c->ops);
+  ci.raw_idx = idx;
+  ci.flags = v.flags();
+  ci.clip_from_start = v.flags() & bam::kReverse;
+  size_t ref_consumed = 0;
+  ci.clipped_cigar = bam::clip_cigar_ops(c->ops, ci.clip_amount, ci.clip_from_start, &ref_consumed);
+  ci.clipped_seq_len = v.l_seq() > ci.clip_amount ? v.l_seq() - ci.clip_amount : 0;
+  ci.adjusted_pos = static_cast<size_t>(v.pos() + 1) + (ci.clip_from_start ? ref_consumed : 0);
+  return ci;
+}
+
+// filter_to_most_common_alignment_raw, codec_caller.rs:867-909
+void codec_filter(fgb_caller* c, std::vector<ClippedInfo>* infos) {
+  if (infos->size() < 2) return;
+  std::vector<SourceRead> proxy(infos->size());   // reuse the shared grouping on (length, cigar)
+  for (size_t i = 0; i < infos->size(); ++i) {
+    bam::simplify_cigar((*infos)[i].clipped_cigar, &proxy[i].cigar);
+    if ((*infos)[i].flags & bam::kReverse) std::reverse(proxy[i].cigar.begin(), proxy[i].cigar.end());
+    proxy[i].bases.resize((*infos)[i].clipped_seq_len);
+    proxy[i].original_idx = static_cast<uint32_t>(i);
+  }
+  size_t rejected = filter_by_alignment(&proxy);
+  if (rejected) reject(c, FGB_STAT_REJ_MINORITY_ALIGNMENT, rejected);
+  std::vector<ClippedInfo> kept;
+  for (auto& p : proxy) kept.push_back(std::move((*infos)[p.original_idx]));
+  infos->swap(kept);
+}
+
+// to_source_read_for_codec_raw, codec_caller.rs:414-469 (no masking, no trimming)
+void codec_source_read(const View& v, const ClippedInfo& ci, SourceRead* sr) {
+  bam::decode_sequence(v, &sr->bases);
+  const uint32_t l = v.l_seq();
+  sr->quals.assign(v.b + v.qual_off(), v.b + v.qual_off() + l);
+  size_t clip = std::min<size_t>(ci.clip_amount, sr->bases.size());
+  if (clip > 0) {
+    if (ci.clip_from_start) {
+      sr->bases.erase(sr->bases.begin(), sr->bases.begin() + clip);
+      sr->quals.erase(sr->quals.begin(), sr->quals.begin() + clip);
+    } else {
+      sr->bases.resize(sr->bases.size() - clip);
+      sr->quals.resize(sr->quals.size() - clip);
+    }
+  }
+  if (v.flags() & bam::kReverse) {
+    std::reverse(sr->bases.begin(), sr->bases.end());
+    for (auto& b : sr->bases) b = bam::complement(b);
+    std::reverse(sr->quals.begin(), sr->quals.end());
+  }
+  sr->flags = v.flags();
+}
+
+bool strict_utf8_string_tag(const View& v, const char tag[2], std::string* out) {
+  const uint8_t* val; size_t n;
+  if (!bam::find_string_tag(v, tag, &val, &n)) return false;
+  if (!bam::valid_utf8(val, n)) return false;   // String::from_utf8(..).ok()
+  out->assign(reinterpret_cast<const char*>(val), n);
+  return true;
+}
+
+// consensus_reads_raw up to the vote, codec_caller.rs:531-745
+fgb_status add_group_codec(fgb_caller* c, const std::vector<View>& recs) {
+  const uint32_t n = static_cast<uint32_t>(recs.size());
+  c->stats[FGB_STAT_TOTAL_READS] += n;
+  CodecMolecule m;
+  m.has_umi = get_string_tag(recs[0], "MI", &m.umi);
+  std::vector<uint32_t> paired;
+  size_t frag = 0;
+  std::vector<uint32_t> ops;
+  for (uint32_t i = 0; i < n; ++i) {   // phase 1
+    const uint16_t f = recs[i].flags();
+    if (!(f & bam::kPaired)) { ++frag; continue; }
+    if (f & (bam::kSecondary | bam::kSupplementary | bam::kUnmapped)) continue;
+    bam::cigar_ops(recs[i], &ops);
+    if (!bam::is_fr_pair(recs[i], ops)) continue;
+    paired.push_back(i);
+  }
+  if (frag) reject(c, FGB_STAT_REJ_FRAGMENT_READ, frag);
+  if (paired.empty()) return FGB_OK;
+  // phase 2: pair by read name in first-seen order
+  struct NameGroup { const uint8_t* name; size_t len; std::vector<uint32_t> idx; };
+  std::vector<NameGroup> groups;
+  for (uint32_t i : paired) {
+    const uint8_t* nm = recs[i].b + 32;
+    size_t ln = recs[i].l_read_name() > 1 ? recs[i].l_read_name() - 1 : 0;
+    bool found = false;
+    for (auto& g : groups)
+      if (g.len == ln && std::memcmp(g.name, nm, ln) == 0) { g.idx.push_back(i); found = true; break; }
+    if (!found) groups.push_back(NameGroup{nm, ln, {i}});
+  }
+  std::vector<ClippedInfo> r1s, r2s;
+  for (auto& g : groups) {
+    if (g.idx.size() != 2) continue;
+    uint32_t i1 = g.idx[0], i2 = g.idx[1];
+    if (!(recs[i1].flags() & bam::kFirst)) std::swap(i1, i2);
+    r1s.push_back(clipped_info(c, recs[i1], i1));
+    r2s.push_back(clipped_info(c, recs[i2], i2));
+  }
+  if (r1s.empty()) return FGB_OK;
+  const size_t min_reads = c->opt.min_reads;
+  if (r1s.size() < min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, r1s.size() + r2s.size()); return FGB_OK; }
+  codec_filter(c, &r1s);   // phase 3
+  codec_filter(c, &r2s);
+  if (r1s.empty() || r2s.empty()) return FGB_OK;
+  if (r1s.size() < min_reads || r2s.size() < min_reads) {
+    reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, r1s.size() + r2s.size());
+    return FGB_OK;
+  }
+  // phase 4: overlap / phase on the longest R1 and R2 (first maximum wins)
+  auto longest = [](const std::vector<ClippedInfo>& v) {
+    const ClippedInfo* best = nullptr;
+    int32_t best_len = 0;
+    for (const auto& ci : v) {
+      int32_t rl = bam::reference_length(ci.clipped_cigar);
+      if (!best || rl > best_len) { best = &ci; best_len = rl; }
+    }
+    return best;
+  };
+  const ClippedInfo* l1 = longest(r1s);
+  const ClippedInfo* l2 = longest(r2s);
+  const bool r1_neg = l1->flags & bam::kReverse;
+  const ClippedInfo* lpos = r1_neg ? l2 : l1;
+  const ClippedInfo* lneg = r1_neg ? l1 : l2;
+  const size_t neg_start = lneg->adjusted_pos, pos_start = lpos->adjusted_pos;
+  const int32_t prl = bam::reference_length(lpos->clipped_cigar);
+  const size_t pos_ref_len = prl > 0 ? static_cast<size_t>(prl) : 0;
+  const size_t pos_end = pos_start + (pos_ref_len > 0 ? pos_ref_len - 1 : 0);
+  const size_t ov_start = neg_start, ov_end = pos_end;
+  const int64_t duplex_length = static_cast<int64_t>(ov_end) - static_cast<int64_t>(ov_start) + 1;
+  const uint64_t n_pairs = r1s.size() + r2s.size();
+  if (duplex_length < static_cast<int64_t>(c->opt.min_duplex_length)) {
+    reject(c, FGB_STAT_REJ_INSUFFICIENT_OVERLAP, n_pairs);
+    return FGB_OK;
+  }
+  size_t a, b, cc, d;
+  bool ok = bam::read_pos_at_ref_pos(l1->clipped_cigar, l1->adjusted_pos, ov_start, true, &a) &&
+            bam::read_pos_at_ref_pos(l2->clipped_cigar, l2->adjusted_pos, ov_start, true, &b) &&
+            bam::read_pos_at_ref_pos(l1->clipped_cigar, l1->adjusted_pos, ov_end, true, &cc) &&
+            bam::read_pos_at_ref_pos(l2->clipped_cigar, l2->adjusted_pos, ov_end, true, &d);
+  if (!ok || (static_cast<int64_t>(a) - static_cast<int64_t>(b)) != (static_cast<int64_t>(cc) - static_cast<int64_t>(d))) {
+    reject(c, FGB_STAT_REJ_INDEL_ERROR, n_pairs);
+    return FGB_OK;
+  }
+  const bool r2_neg = l2->flags & bam::kReverse;
+  size_t pp, nn;
+  if (!bam::read_pos_at_ref_pos(lpos->clipped_cigar, lpos->adjusted_pos, ov_end, false, &pp) ||
+      !bam::read_pos_at_ref_pos(lneg->clipped_cigar, lneg->adjusted_pos, ov_end, false, &nn)) {
+    reject(c, FGB_STAT_REJ_INDEL_ERROR, n_pairs);
+    return FGB_OK;
+  }
+  const size_t cons_len = pp + lneg->clipped_seq_len - nn;
+  // phase 5: the two single-strand units.  Their consensus length (min_reads = 1 -> longest row)
+  // is known now, so the `consensus_length < ss length` rejection (:738-744) happens here.
+  std::vector<SourceRead> s1(r1s.size()), s2(r2s.size());
+  size_t len1 = 0, len2 = 0;
+  for (size_t i = 0; i < r1s.size(); ++i) { codec_source_read(recs[r1s[i].raw_idx], r1s[i], &s1[i]); len1 = std::max(len1, s1[i].bases.size()); }
+  for (size_t i = 0; i < r2s.size(); ++i) { codec_source_read(recs[r2s[i].raw_idx], r2s[i], &s2[i]); len2 = std::max(len2, s2[i].bases.size()); }
+  for (const auto& sr : s1) if (sr.bases.empty()) { c->last_error = "CODEC read fully clipped"; return FGB_ERR_INVALID_ARG; }
+  for (const auto& sr : s2) if (sr.bases.empty()) { c->last_error = "CODEC read fully clipped"; return FGB_ERR_INVALID_ARG; }
+  if (cons_len < len1 || cons_len < len2) { reject(c, FGB_STAT_REJ_INDEL_ERROR, n_pairs); return FGB_OK; }
+  if (cons_len > FGB_MAX_READ_LEN) { c->last_error = "CODEC consensus longer than 65535"; return FGB_ERR_UNIT_TOO_LARGE; }
+  m.unit_r1 = c->pack.add_unit(s1, 1);
+  m.unit_r2 = c->pack.add_unit(s2, 1);
+  m.r1_negative = r1_neg;
+  m.cons_len = static_cast<uint32_t>(cons_len);
+  fgb_codec_job j;
+  std::memset(&j, 0, sizeof(j));
+  j.unit_a = m.unit_r1; j.unit_b = m.unit_r2;
+  j.out_off = c->n_codec_out;
+  j.len = m.cons_len;
+  j.rc_a = r1_neg; j.rc_b = !r1_neg; j.rc_out = r1_neg;            // :746-750, :757-758
+  j.pad_a_left = r1_neg ? static_cast<uint32_t>(cons_len - len1) : 0;   // pad_consensus(.., r1_is_negative)
+  j.pad_b_left = r2_neg ? static_cast<uint32_t>(cons_len - len2) : 0;
+  c->n_codec_out += round_up(cons_len, FGB_OUT_ALIGN);
+  m.job = static_cast<uint32_t>(c->codec_jobs.size());
+  c->codec_jobs.push_back(j);
+  if (c->opt.cell_tag[0]) {   // first source read with a non-empty cell barcode, :1322-1332
+    auto scan = [&](const std::vector<ClippedInfo>& v) {
+      for (const auto& ci : v) {
+        if (m.has_cell) return;
+        std::string val;
+        if (get_string_tag(recs[ci.raw_idx], c->opt.cell_tag, &val) && !val.empty()) { m.has_cell = true; m.cell = val; }
+      }
+    };
+    scan(r1s); scan(r2s);
+  }
+  std::string rx;
+  for (uint32_t i = 0; i < n; ++i) if (strict_utf8_string_tag(recs[i], "RX", &rx)) m.rx.push_back(rx);
+  c->codec_molecules.push_back(std::move(m));
+  return FGB_OK;
+}
+
+// One padded, oriented single strand as the record builder sees it (ss_for_ac / ss_for_bc).
+struct PaddedStrand {
+  std::vector<uint8_t> bases, quals;
+  std::vector<uint16_t> depths, errors;
+};
+
+// reverse_complement_ss + pad_consensus (+ reverse_complement_ss again when R1 is negative),
+// codec_caller.rs:507-520, 980-1023, 760-766
+void padded_strand(const uint8_t* b, const uint8_t* q, const uint16_t* d, const uint16_t* e, uint32_t len,
+                   bool rc_first, uint32_t pad_left, uint32_t total, bool rc_again, PaddedStrand* out) {
+  out->bases.assign(total, 'n'); out->quals.assign(total, 0);
+  out->depths.assign(total, 0); out->errors.assign(total, 0);
+  for (uint32_t i = 0; i < len; ++i) {
+    uint32_t s = rc_first ? len - 1 - i : i;
+    out->bases[pad_left + i] = rc_first ? bam::complement(b[s]) : b[s];
+    out->quals[pad_left + i] = q[s]; out->depths[pad_left + i] = d[s]; out->errors[pad_left + i] = e[s];
+  }
+  if (rc_again) {
+    std::reverse(out->bases.begin(), out->bases.end());
+    for (auto& x : out->bases) x = bam::complement(x);
+    std::reverse(out->quals.begin(), out->quals.end());
+    std::reverse(out->depths.begin(), out->depths.end());
+    std::reverse(out->errors.begin(), out->errors.end());
+  }
+}
+
+fgb_status flush_codec(fgb_caller* c) {
+  const uint64_t U = c->pack.units.size();
+  if (!U) return FGB_OK;
+  uint64_t n_bytes, R;
+  c->pack.seal(&n_bytes, &R);
+  uint64_t n_tiles = 0;
+  fgb_status st = fgb_plan_tiles(c->pack.units.data(), U, c->pack.reads.data(), R, nullptr, 0, &n_tiles);
+  if (st != FGB_OK) { c->last_error = "fgb_plan_tiles failed"; return st; }
+  std::vector<fgb_tile> tiles(n_tiles ? n_tiles : 1);
+  if ((st = fgb_plan_tiles(c->pack.units.data(), U, c->pack.reads.data(), R, tiles.data(), n_tiles, &n_tiles)) != FGB_OK) return st;
+  const uint64_t no = c->pack.n_out, nc = c->n_codec_out, nj = c->codec_jobs.size();
+  std::vector<uint8_t> sb(no + 8), sq(no + 8), cb(nc + 8), cq(nc + 8), cst(nj + 1);
+  std::vector<uint16_t> sd(no + 8), se(no + 8), cd(nc + 8), ce(nc + 8);
+  std::vector<uint32_t> dis(nj + 1), dup(nj + 1);
+  fgb_batch b;
+  b.n_units = U; b.n_reads = R; b.n_bytes = n_bytes; b.n_out = no; b.n_tiles = n_tiles;
+  b.bases = c->pack.bases.data(); b.quals = c->pack.quals.data(); b.reads = c->pack.reads.data();
+  b.units = c->pack.units.data(); b.tiles = tiles.data();
+  fgb_columns ss{sb.data(), sq.data(), sd.data(), se.data()};
+  fgb_codec_out cout;
+  cout.cols = fgb_columns{cb.data(), cq.data(), cd.data(), ce.data()};
+  cout.status = cst.data(); cout.disagreements = dis.data(); cout.duplex_bases = dup.data();
+  st = fgb_codec_submit(c->h, &b, &ss, c->codec_jobs.data(), nj, &c->opt.codec, nc, &cout);
+  if (st != FGB_OK) {
+    char buf[256];
+    fgb_last_error(c->h, buf, sizeof(buf));
+    c->last_error = buf;
+    return st;
+  }
+  bam::Writer w(&c->out);
+  PaddedStrand sa, sbb;
+  for (const CodecMolecule& m : c->codec_molecules) {
+    const fgb_codec_job& j = c->codec_jobs[m.job];
+    if (dup[m.job] > 0) {   // counted before the gate, codec_caller.rs:1155-1158
+      c->stats[FGB_STAT_DUPLEX_BASES] += dup[m.job];
+      c->stats[FGB_STAT_DUPLEX_DISAGREEMENTS] += dis[m.job];
+    }
+    if (cst[m.job] != FGB_CODEC_OK) continue;   // "High duplex disagreement": the group is dropped
+    const fgb_unit& u1 = c->pack.units[m.unit_r1];
+    const fgb_unit& u2 = c->pack.units[m.unit_r2];
+    const uint32_t L = m.cons_len;
+    padded_strand(sb.data() + u1.out_off, sq.data() + u1.out_off, sd.data() + u1.out_off, se.data() + u1.out_off,
+                  u1.cons_len, j.rc_a, j.pad_a_left, L, m.r1_negative, &sa);
+    padded_strand(sb.data() + u2.out_off, sq.data() + u2.out_off, sd.data() + u2.out_off, se.data() + u2.out_off,
+                  u2.cons_len, j.rc_b, j.pad_b_left, L, m.r1_negative, &sbb);
+    // build_output_record_into, codec_caller.rs:1226-1368
+    ++c->consensus_counter;
+    std::string name = c->prefix + ":" + (m.has_umi ? m.umi : std::to_string(c->consensus_counter));
+    if (name.size() >= 255) { c->last_error = "read name too long"; return FGB_ERR_INVALID_ARG; }
+    const uint8_t* bases = cb.data() + j.out_off;
+    const uint8_t* quals = cq.data() + j.out_off;
+    const uint16_t* errors = ce.data() + j.out_off;
+    w.begin(name, bam::kUnmapped, bases, quals, L);
+    w.str("RG", c->rg.data(), c->rg.size());
+    if (m.has_umi) w.str("MI", m.umi.data(), m.umi.size());
+    int32_t tmax = 0, tmin = L ? 0x7FFFFFFF : 0;
+    int64_t tbases = 0; uint64_t terr = 0;
+    for (uint32_t i = 0; i < L; ++i) {
+      int32_t t = static_cast<int32_t>(sa.depths[i]) + static_cast<int32_t>(sbb.depths[i]);
+      tmax = std::max(tmax, t); tmin = std::min(tmin, t); tbases += t; terr += errors[i];
+    }
+    w.integer("cD", tmax); w.integer("cM", tmin);
+    w.real("cE", tbases > 0 ? static_cast<float>(terr) / static_cast<float>(static_cast<int32_t>(tbases)) : 0.0f);
+    auto strand_tags = [&](const PaddedStrand& s, const char* dt, const char* mt, const char* et) {
+      int32_t mx = 0, mn = L ? 0x7FFFFFFF : 0;
+      uint64_t te = 0, tb = 0;
+      for (uint32_t i = 0; i < L; ++i) {
+        mx = std::max<int32_t>(mx, s.depths[i]); mn = std::min<int32_t>(mn, s.depths[i]);
+        te += s.errors[i]; tb += s.depths[i];
+      }
+      w.integer(dt, mx); w.integer(mt, mn); w.real(et, error_rate(te, tb));
+    };
+    strand_tags(sa, "aD", "aM", "aE");
+    strand_tags(sbb, "bD", "bM", "bE");
+    if (c->opt.produce_per_base_tags) {   // `d as i16`: wrapping, not clamping (:1299-1309)
+      w.i16_array_wrap("ad", sa.depths.data(), L); w.i16_array_wrap("bd", sbb.depths.data(), L);
+      w.i16_array_wrap("ae", sa.errors.data(), L); w.i16_array_wrap("be", sbb.errors.data(), L);
+      w.str("ac", sa.bases.data(), L); w.str("bc", sbb.bases.data(), L);
+      w.phred33("aq", sa.quals.data(), L); w.phred33("bq", sbb.quals.data(), L);
+    }
+    if (m.has_cell) w.str(c->opt.cell_tag, m.cell.data(), m.cell.size());
+    if (!m.rx.empty()) {
+      std::string rx;
+      if (!consensus_umis(c->umi_builder, m.rx, &rx)) {
+        c->last_error = "RX values of a family have different lengths or mix DNA and non-DNA characters";
+        return FGB_ERR_INVALID_ARG;
+      }
+      if (!rx.empty()) w.str("RX", rx.data(), rx.size());
+    }
+    w.end();
+    ++c->out_count;
+    c->stats[FGB_STAT_CONSENSUS_READS] += 1;
+  }
+  return FGB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -577,8 +924,8 @@ extern "C" {
 fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_caller** out) {
   if (!opt || !out || !opt->read_name_prefix || !opt->read_group_id) return FGB_ERR_INVALID_ARG;
   *out = nullptr;
-  if (opt->mode != FGB_MODE_SIMPLEX && opt->mode != FGB_MODE_DUPLEX) return FGB_ERR_INVALID_ARG;
-  if (opt->mode == FGB_MODE_SIMPLEX && opt->min_reads == 0) return FGB_ERR_INVALID_ARG;
+  if (opt->mode > FGB_MODE_CODEC) return FGB_ERR_INVALID_ARG;
+  if (opt->mode != FGB_MODE_DUPLEX && opt->min_reads == 0) return FGB_ERR_INVALID_ARG;
   if (opt->mode == FGB_MODE_DUPLEX &&
       (opt->min_xy_reads > opt->min_reads || opt->min_yx_reads > opt->min_xy_reads))
     return FGB_ERR_INVALID_ARG;   // "min-reads values must be specified high to low", duplex_caller.rs:385-395
@@ -597,8 +944,11 @@ fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_call
   if (opt->mode == FGB_MODE_SIMPLEX) {
     p.min_consensus_base_quality = opt->min_consensus_base_quality;
     p.min_reads = opt->min_reads;
-  } else {   // single-strand caller of the duplex caller, duplex_caller.rs:397-412
+  } else if (opt->mode == FGB_MODE_DUPLEX) {   // single-strand caller of the duplex caller, duplex_caller.rs:397-412
     p.min_consensus_base_quality = 2;
+    p.min_reads = 1;
+  } else {   // single-strand caller of the CODEC caller, codec_caller.rs:326-339
+    p.min_consensus_base_quality = 0;
     p.min_reads = 1;
   }
   fgb_status st = fgb_create(device, &p, &c->h);
@@ -635,7 +985,9 @@ fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uin
     recs.emplace_back(records + rec_off[i], len);
     if (recs.back().aux_off() > len) { c->last_error = "truncated BAM record"; return FGB_ERR_INVALID_ARG; }
   }
-  return c->opt.mode == FGB_MODE_DUPLEX ? add_group_duplex(c, recs) : add_group_simplex(c, recs);
+  if (c->opt.mode == FGB_MODE_DUPLEX) return add_group_duplex(c, recs);
+  if (c->opt.mode == FGB_MODE_CODEC) return add_group_codec(c, recs);
+  return add_group_simplex(c, recs);
 }
 
 fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* out_len,
@@ -643,9 +995,11 @@ fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* o
   if (!c || !out_data || !out_len || !out_count) return FGB_ERR_INVALID_ARG;
   c->out.clear();
   c->out_count = 0;
-  fgb_status st = c->opt.mode == FGB_MODE_DUPLEX ? flush_duplex(c) : flush_simplex(c);
+  fgb_status st = c->opt.mode == FGB_MODE_DUPLEX ? flush_duplex(c)
+                  : c->opt.mode == FGB_MODE_CODEC ? flush_codec(c) : flush_simplex(c);
   c->pack.clear(); c->metas.clear(); c->molecules.clear(); c->jobs.clear();
-  c->n_duplex_out = 0;
+  c->codec_molecules.clear(); c->codec_jobs.clear();
+  c->n_duplex_out = 0; c->n_codec_out = 0;
   if (st != FGB_OK) return st;
   *out_data = c->out.data();
   *out_len = c->out.size();

@@ -121,13 +121,15 @@ class FgbCallerOptions(C.Structure):
         ("min_reads", C.c_uint32), ("min_xy_reads", C.c_uint32), ("min_yx_reads", C.c_uint32),
         ("tag", C.c_char * 2), ("cell_tag", C.c_char * 2),
         ("read_name_prefix", C.c_char_p), ("read_group_id", C.c_char_p),
+        ("min_duplex_length", C.c_uint32), ("reserved1", C.c_uint32), ("codec", FgbCodecParams),
     ]
 
 
 FGB_NSTATS = 16
 STAT_NAMES = ("total_reads", "consensus_reads", "filtered_reads", "InsufficientReads",
               "SecondaryOrSupplementary", "ZeroLengthAfterTrimming", "MinorityAlignment",
-              "OrphanConsensus", "PotentialCollision")
+              "OrphanConsensus", "PotentialCollision", "FragmentRead", "InsufficientOverlap",
+              "IndelErrorBetweenStrands", "duplex_bases", "duplex_disagreements")
 
 
 class FgbCodecOut(C.Structure):

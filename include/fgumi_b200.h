@@ -317,6 +317,10 @@ typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanill
   char cell_tag[2];                        /* {0,0} = none                                         */
   const char* read_name_prefix;            /* consensus read name = "<prefix>:<MI>"                */
   const char* read_group_id;               /* RG tag value                                         */
+  /* CODEC only (CodecConsensusOptions, codec_caller.rs:99-166): min_reads = min_reads_per_strand */
+  uint32_t min_duplex_length;              /* 1 */
+  uint32_t reserved1;
+  fgb_codec_params codec;                  /* single_strand_qual / outer_bases_* / disagreement gates */
 } fgb_caller_options;
 
 enum {   /* ConsensusCallingStats (caller.rs:238-286) as a flat counter array                      */
@@ -329,6 +333,11 @@ enum {   /* ConsensusCallingStats (caller.rs:238-286) as a flat counter array   
   FGB_STAT_REJ_MINORITY_ALIGNMENT = 6,        /* ::MinorityAlignment                             */
   FGB_STAT_REJ_ORPHAN_CONSENSUS = 7,          /* ::OrphanConsensus                               */
   FGB_STAT_REJ_POTENTIAL_COLLISION = 8,       /* ::PotentialCollision (duplex_caller.rs:1799-1823) */
+  FGB_STAT_REJ_FRAGMENT_READ = 9,             /* ::FragmentRead (codec_caller.rs:564-566)        */
+  FGB_STAT_REJ_INSUFFICIENT_OVERLAP = 10,     /* ::InsufficientOverlap (codec_caller.rs:688-694) */
+  FGB_STAT_REJ_INDEL_ERROR = 11,              /* ::IndelErrorBetweenStrands (:697-737)           */
+  FGB_STAT_DUPLEX_BASES = 12,                 /* consensus_duplex_bases_emitted (:1157)          */
+  FGB_STAT_DUPLEX_DISAGREEMENTS = 13,         /* duplex_disagreement_base_count (:1158)          */
   FGB_NSTATS = 16
 };
 

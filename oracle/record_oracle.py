@@ -851,3 +851,414 @@ class DuplexCallerOracle:
             rx = consensus_umis(umis, lambda pre, post, b, q: self.builder_call(pre, post, b, q)[:2])
             rec += tag_string(b"RX", rx.encode())
         return with_block_size(rec)
+
+
+# =================================================================================================
+# CODEC caller — crates/fgumi-consensus/src/codec_caller.rs
+# =================================================================================================
+def _enc(op_type: int, ln: int) -> int:
+    return (ln << 4) | op_type
+
+
+def _consumes_read(t: int) -> bool:                    # cigar.rs:75-77 (M, I, =, X)
+    return t in (0, 1, 7, 8)
+
+
+def _upgrade_clipping(ops, clip_amount, from_start):   # cigar.rs:579-655
+    if from_start:
+        hard = soft = skip = 0
+        for op in ops:
+            if op & 0xF == 5:
+                hard += op >> 4; skip += 1
+            else:
+                break
+        for op in ops[skip:]:
+            if op & 0xF == 4:
+                soft += op >> 4; skip += 1
+            else:
+                break
+        up = min(soft, max(clip_amount - hard, 0))
+        res = [_enc(5, hard + up)]
+        if soft - up > 0:
+            res.append(_enc(4, soft - up))
+        return res + list(ops[skip:]), 0
+    hard = soft = skip = 0
+    for op in reversed(ops):
+        if op & 0xF == 5:
+            hard += op >> 4; skip += 1
+        else:
+            break
+    end_idx = len(ops) - skip
+    for op in reversed(ops[:end_idx]):
+        if op & 0xF == 4:
+            soft += op >> 4; skip += 1
+        else:
+            break
+    up = min(soft, max(clip_amount - hard, 0))
+    res = list(ops[:len(ops) - skip])
+    if soft - up > 0:
+        res.append(_enc(4, soft - up))
+    res.append(_enc(5, hard + up))
+    return res, 0
+
+
+def _clip_start(ops, clip_amount):                     # cigar.rs:658-757
+    hard = soft = skip = 0
+    for op in ops:
+        if op & 0xF == 5:
+            hard += op >> 4; skip += 1
+        else:
+            break
+    for op in ops[skip:]:
+        if op & 0xF == 4:
+            soft += op >> 4; skip += 1
+        else:
+            break
+    post = list(ops[skip:])
+    read_clipped = ref_clipped = 0
+    new_ops, idx = [], 0
+    while idx < len(post):
+        op = post[idx]; t, ln = op & 0xF, op >> 4
+        if read_clipped == clip_amount and not new_ops and t == 2:
+            ref_clipped += ln; idx += 1
+            continue
+        if read_clipped >= clip_amount:
+            break
+        is_read, is_ref = _consumes_read(t), consumes_ref(t)
+        if is_read and ln > clip_amount - read_clipped:
+            if t == 1:
+                read_clipped += ln
+            else:
+                rem_clip = clip_amount - read_clipped
+                read_clipped += rem_clip
+                if is_ref:
+                    ref_clipped += rem_clip
+                new_ops.append(_enc(t, ln - rem_clip))
+        else:
+            if is_read:
+                read_clipped += ln
+            if is_ref:
+                ref_clipped += ln
+        idx += 1
+    new_ops += post[idx:]
+    return [_enc(5, hard + soft + read_clipped)] + new_ops, ref_clipped
+
+
+def _clip_end(ops, clip_amount):                       # cigar.rs:760-841
+    hard = soft = skip = 0
+    for op in reversed(ops):
+        if op & 0xF == 5:
+            hard += op >> 4; skip += 1
+        else:
+            break
+    end_idx = len(ops) - skip
+    for op in reversed(ops[:end_idx]):
+        if op & 0xF == 4:
+            soft += op >> 4; skip += 1
+        else:
+            break
+    post = list(ops[:len(ops) - skip])
+    read_clipped = 0
+    new_ops, idx = [], len(post)
+    while idx > 0:
+        op = post[idx - 1]; t, ln = op & 0xF, op >> 4
+        if read_clipped == clip_amount and not new_ops and t == 2:
+            idx -= 1
+            continue
+        if read_clipped >= clip_amount:
+            break
+        is_read = _consumes_read(t)
+        if is_read and ln > clip_amount - read_clipped:
+            if t == 1:
+                read_clipped += ln
+            else:
+                rem_clip = clip_amount - read_clipped
+                read_clipped += rem_clip
+                new_ops.append(_enc(t, ln - rem_clip))
+        elif is_read:
+            read_clipped += ln
+        idx -= 1
+    res = post[:idx] + list(reversed(new_ops))
+    res.append(_enc(5, hard + soft + read_clipped))
+    return res, 0
+
+
+def clip_cigar_ops(ops, clip_amount, from_start):      # cigar.rs:355-397
+    if clip_amount == 0 or not ops:
+        return list(ops), 0
+    seq = ops if from_start else list(reversed(ops))
+    existing = 0
+    for op in seq:
+        if op & 0xF in (4, 5):
+            existing += op >> 4
+        else:
+            break
+    if clip_amount <= existing:
+        return _upgrade_clipping(list(ops), clip_amount, from_start)
+    extra = clip_amount - existing
+    return _clip_start(list(ops), extra) if from_start else _clip_end(list(ops), extra)
+
+
+def read_pos_at_ref_pos(ops, alignment_start, ref_pos, return_last_if_deleted):   # cigar.rs:412-457
+    if ref_pos < alignment_start:
+        return None
+    ref_off = q_off = 0
+    for op in ops:
+        t, ln = op & 0xF, op >> 4
+        op_ref_start = alignment_start + ref_off
+        if consumes_ref(t):
+            op_ref_end = op_ref_start + ln - 1
+            if op_ref_start <= ref_pos <= op_ref_end:
+                if consumes_query(t):
+                    return q_off + (ref_pos - op_ref_start) + 1
+                if return_last_if_deleted:
+                    return q_off if q_off > 0 else 1
+                return None
+        if consumes_ref(t):
+            ref_off += ln
+        if consumes_query(t):
+            q_off += ln
+    return None
+
+
+@dataclass
+class ClippedInfo:                                     # codec_caller.rs ClippedRecordInfo
+    raw_idx: int
+    clip_amount: int
+    clip_from_start: bool
+    clipped_seq_len: int
+    clipped_cigar: list
+    adjusted_pos: int
+    flags: int
+
+
+class CodecCallerOracle:
+    """CodecConsensusCaller::consensus_reads_raw, codec_caller.rs:531-814."""
+
+    def __init__(self, prefix, rg, min_reads_per_strand=1, min_duplex_length=1, pre=45, post=40,
+                 ss_qual=None, outer_qual=None, outer_len=5, max_dis=None, max_rate=1.0,
+                 per_base=False, cell_tag=None, vote_fn=None, builder_fn=None, codec_job_fn=None):
+        self.prefix, self.rg = prefix, rg
+        self.min_reads, self.min_duplex_length = min_reads_per_strand, min_duplex_length
+        self.ss_qual, self.outer_qual, self.outer_len = ss_qual, outer_qual, outer_len
+        self.max_dis, self.max_rate = max_dis, max_rate
+        self.per_base, self.cell_tag = per_base, cell_tag
+        # ss_options :326-339: min_reads 1, min_consensus_base_quality 0, trim false
+        self.ss_opt = VanillaOptions(error_rate_pre_umi=pre, error_rate_post_umi=post, min_reads=1,
+                                     min_consensus_base_quality=0)
+        self.vote, self.builder_call, self.codec_job = vote_fn, builder_fn, codec_job_fn
+        self.total_input_reads = self.consensus_reads_generated = self.reads_filtered = 0
+        self.duplex_bases = self.duplex_disagreements = 0
+        self.rejections: Dict[str, int] = {}
+        self.counter = 0
+
+    def _reject(self, n, reason):
+        self.rejections[reason] = self.rejections.get(reason, 0) + n
+        self.reads_filtered += n
+
+    @staticmethod
+    def _clipped_info(r: Rec, idx: int, clip: int) -> ClippedInfo:     # :817-851
+        from_start = bool(r.flags & REVERSE)
+        cig, ref_consumed = clip_cigar_ops(r.cigar_ops(), clip, from_start)
+        adj = (r.pos + 1) + (ref_consumed if from_start else 0)
+        return ClippedInfo(idx, clip, from_start, max(r.l_seq - clip, 0), cig, adj, r.flags)
+
+    def _filter(self, infos: List[ClippedInfo]) -> List[ClippedInfo]:  # :867-909
+        if len(infos) < 2:
+            return infos
+        indexed = []
+        for i, inf in enumerate(infos):
+            c = simplify_cigar(inf.clipped_cigar)
+            if inf.flags & REVERSE:
+                c = list(reversed(c))
+            indexed.append((i, inf.clipped_seq_len, c))
+        indexed.sort(key=lambda t: -t[1])
+        best = set(select_most_common_alignment_group(indexed))
+        rej = len(infos) - len(best)
+        if rej:
+            self._reject(rej, "MinorityAlignment")
+        return [inf for i, inf in enumerate(infos) if i in best]
+
+    @staticmethod
+    def _source_row(r: Rec, inf: ClippedInfo):          # to_source_read_for_codec_raw :414-469
+        bases, quals = r.sequence(), r.quals()
+        clip = min(inf.clip_amount, len(bases))
+        if clip > 0:
+            if inf.clip_from_start:
+                bases, quals = bases[clip:], quals[clip:]
+            else:
+                bases, quals = bases[:len(bases) - clip], quals[:len(quals) - clip]
+        if r.flags & REVERSE:
+            bases = reverse_complement(bases)
+            quals = bytearray(reversed(quals))
+        return bytes(bases), bytes(quals)
+
+    def consensus_reads(self, records: List[bytes]) -> Tuple[bytes, int]:
+        self.total_input_reads += len(records)
+        if not records:
+            return b"", 0
+        recs = [Rec(b) for b in records]
+        umi = recs[0].find_string(b"MI")
+        umi = umi.decode("utf-8", "replace") if umi is not None else None
+        paired, frag = [], 0
+        for i, r in enumerate(recs):                    # phase 1 :545-561
+            if not r.flags & PAIRED:
+                frag += 1
+                continue
+            if r.flags & (SECONDARY | SUPPLEMENTARY | UNMAPPED):
+                continue
+            if not is_fr_pair(r):
+                continue
+            paired.append(i)
+        if frag:
+            self._reject(frag, "FragmentRead")
+        if not paired:
+            return b"", 0
+        by_name: Dict[bytes, List[int]] = {}
+        order = []
+        for i in paired:                                # phase 2 :572-611
+            nm = recs[i].name
+            if nm not in by_name:
+                order.append(nm)
+            by_name.setdefault(nm, []).append(i)
+        r1s, r2s = [], []
+        for nm in order:
+            idxs = by_name[nm]
+            if len(idxs) != 2:
+                continue
+            i1, i2 = (idxs[0], idxs[1]) if recs[idxs[0]].flags & FIRST_SEGMENT else (idxs[1], idxs[0])
+            r1s.append(self._clipped_info(recs[i1], i1, num_bases_extending_past_mate(recs[i1])))
+            r2s.append(self._clipped_info(recs[i2], i2, num_bases_extending_past_mate(recs[i2])))
+        if not r1s:
+            return b"", 0
+        if len(r1s) < self.min_reads:
+            self._reject(len(r1s) + len(r2s), "InsufficientReads")
+            return b"", 0
+        r1s, r2s = self._filter(r1s), self._filter(r2s)   # phase 3
+        if not r1s or not r2s:
+            return b"", 0
+        if len(r1s) < self.min_reads or len(r2s) < self.min_reads:
+            self._reject(len(r1s) + len(r2s), "InsufficientReads")
+            return b"", 0
+
+        def longest(infos):                             # `.iter().rev().max_by_key(..)`: first max wins
+            best = None
+            for inf in infos:
+                rl = reference_length(inf.clipped_cigar)
+                if best is None or rl > best[0]:
+                    best = (rl, inf)
+            return best[1]
+        l1, l2 = longest(r1s), longest(r2s)
+        r1_neg = bool(l1.flags & REVERSE)
+        lpos, lneg = (l2, l1) if r1_neg else (l1, l2)
+        neg_start, pos_start = lneg.adjusted_pos, lpos.adjusted_pos
+        pos_ref_len = reference_length(lpos.clipped_cigar)
+        pos_end = pos_start + max(pos_ref_len - 1, 0)
+        ov_start, ov_end = neg_start, pos_end
+        if ov_end - ov_start + 1 < self.min_duplex_length:
+            self._reject(len(r1s) + len(r2s), "InsufficientOverlap")
+            return b"", 0
+        a = read_pos_at_ref_pos(l1.clipped_cigar, l1.adjusted_pos, ov_start, True)   # :911-946
+        b = read_pos_at_ref_pos(l2.clipped_cigar, l2.adjusted_pos, ov_start, True)
+        c = read_pos_at_ref_pos(l1.clipped_cigar, l1.adjusted_pos, ov_end, True)
+        d = read_pos_at_ref_pos(l2.clipped_cigar, l2.adjusted_pos, ov_end, True)
+        if None in (a, b, c, d) or (a - b) != (c - d):
+            self._reject(len(r1s) + len(r2s), "IndelErrorBetweenStrands")
+            return b"", 0
+        r2_neg = bool(l2.flags & REVERSE)
+        pp = read_pos_at_ref_pos(lpos.clipped_cigar, lpos.adjusted_pos, ov_end, False)   # :949-968
+        nn = read_pos_at_ref_pos(lneg.clipped_cigar, lneg.adjusted_pos, ov_end, False)
+        if pp is None or nn is None:
+            self._reject(len(r1s) + len(r2s), "IndelErrorBetweenStrands")
+            return b"", 0
+        cons_len = pp + lneg.clipped_seq_len - nn
+        rows1 = [self._source_row(recs[i.raw_idx], i) for i in r1s]
+        rows2 = [self._source_row(recs[i.raw_idx], i) for i in r2s]
+        ss1 = self.vote(rows1, self.ss_opt)
+        ss2 = self.vote(rows2, self.ss_opt)
+        if cons_len < len(ss1[0]) or cons_len < len(ss2[0]):
+            self._reject(len(r1s) + len(r2s), "IndelErrorBetweenStrands")
+            return b"", 0
+        res = self.codec_job(ss1, ss2, r1_neg, r2_neg, cons_len, self)
+        self.duplex_bases += res["duplex_bases"] if res["duplex_bases"] > 0 else 0
+        self.duplex_disagreements += res["disagreements"] if res["duplex_bases"] > 0 else 0
+        if res["status"] != 0:
+            return b"", 0                                 # bail!("High duplex disagreement..") -> dropped
+        raws = [recs[i.raw_idx] for i in r1s] + [recs[i.raw_idx] for i in r2s]
+        rec = self._record(res, umi, raws, recs)
+        self.consensus_reads_generated += 1
+        return rec, 1
+
+    def _record(self, res, umi, source_raws, all_recs) -> bytes:          # :1226-1368
+        self.counter += 1
+        name = f"{self.prefix}:{umi}" if umi is not None else f"{self.prefix}:{self.counter}"
+        cons, ac, bc = res["consensus"], res["ss_for_ac"], res["ss_for_bc"]
+        rec = unmapped_record(name.encode(), UNMAPPED, cons[0], cons[1])
+        rec += tag_string(b"RG", self.rg.encode())
+        if umi is not None:
+            rec += tag_string(b"MI", umi.encode())
+        tot = [int(x) + int(y) for x, y in zip(ac[2], bc[2])]
+        tmax, tmin = (max(tot) if tot else 0), (min(tot) if tot else 0)
+        terr, tbases = int(sum(int(e) for e in cons[3])), sum(tot)
+        rec += tag_int(b"cD", tmax) + tag_int(b"cM", tmin)
+        rec += tag_float(b"cE", (np.float32(terr) / np.float32(tbases)) if tbases > 0 else np.float32(0))
+
+        def strand(s):
+            mx = max((int(d) for d in s[2]), default=0)
+            mn = min((int(d) for d in s[2]), default=0)
+            te, tb = sum(int(e) for e in s[3]), sum(int(d) for d in s[2])
+            return mx, mn, (np.float32(te) / np.float32(tb)) if tb > 0 else np.float32(0)
+        for pre, s in ((b"a", ac), (b"b", bc)):
+            mx, mn, er = strand(s)
+            rec += tag_int(pre + b"D", mx) + tag_int(pre + b"M", mn) + tag_float(pre + b"E", er)
+        if self.per_base:
+            wrap = lambda v: ((int(v) + 32768) % 65536) - 32768     # `d as i16`
+            rec += tag_i16_array(b"ad", [wrap(d) for d in ac[2]]) + tag_i16_array(b"bd", [wrap(d) for d in bc[2]])
+            rec += tag_i16_array(b"ae", [wrap(e) for e in ac[3]]) + tag_i16_array(b"be", [wrap(e) for e in bc[3]])
+            rec += tag_string(b"ac", ac[0]) + tag_string(b"bc", bc[0])
+            rec += tag_phred33(b"aq", ac[1]) + tag_phred33(b"bq", bc[1])
+        if self.cell_tag is not None:
+            for r in source_raws:
+                v = r.find_string(self.cell_tag)
+                if v is not None and len(v) > 0:
+                    rec += tag_string(self.cell_tag, v)
+                    break
+        umis = []
+        for r in all_recs:
+            v = r.find_string(b"RX")
+            if v is None:
+                continue
+            try:
+                umis.append(v.decode("utf-8"))
+            except UnicodeDecodeError:
+                pass
+        if umis:
+            rx = consensus_umis(umis, lambda pre, post, b, q: self.builder_call(pre, post, b, q)[:2])
+            if rx:
+                rec += tag_string(b"RX", rx.encode())
+        return with_block_size(rec)
+
+
+def _rc_ss(s):                                         # reverse_complement_ss, codec_caller.rs:507-520
+    return (bytes(reverse_complement(s[0])), bytes(reversed(s[1])), list(reversed(s[2])), list(reversed(s[3])))
+
+
+def _pad_ss(s, new_len, left):                         # pad_consensus, codec_caller.rs:980-1023
+    cur = len(s[0])
+    if new_len <= cur:
+        return s
+    n = new_len - cur
+    pb, pq, pd, pe = b"n" * n, bytes(n), [0] * n, [0] * n
+    if left:
+        return (pb + s[0], pq + s[1], pd + list(s[2]), pe + list(s[3]))
+    return (s[0] + pb, s[1] + pq, list(s[2]) + pd, list(s[3]) + pe)
+
+
+def codec_strands(ss1, ss2, r1_neg, r2_neg, cons_len):
+    """codec_caller.rs:746-766: oriented+padded single strands and the ac/bc views of them."""
+    ss1 = (bytes(ss1[0]), bytes(ss1[1]), list(ss1[2]), list(ss1[3]))
+    ss2 = (bytes(ss2[0]), bytes(ss2[1]), list(ss2[2]), list(ss2[3]))
+    o1, o2 = (_rc_ss(ss1), ss2) if r1_neg else (ss1, _rc_ss(ss2))
+    p1, p2 = _pad_ss(o1, cons_len, r1_neg), _pad_ss(o2, cons_len, r2_neg)
+    ac, bc = (_rc_ss(p1), _rc_ss(p2)) if r1_neg else (p1, p2)
+    return p1, p2, ac, bc

@@ -293,3 +293,138 @@ def test_duplex_known_answer_end_to_end():
     assert recs[0]["name"] == b"fgumi:1" and recs[0]["tags"][b"MI"] == b"1"
     assert recs[0]["tags"][b"aD"] == 1 and recs[0]["tags"][b"bD"] == 1 and recs[0]["tags"][b"cD"] == 2
     assert st["consensus_reads"] == 1 and st["total_reads"] == 4
+
+
+# ------------------------------------------------------------------------------------------------
+# CODEC (codec_caller.rs:531-814)
+# ------------------------------------------------------------------------------------------------
+def random_codec_groups(rng, n_groups, L=40):
+    from tests.test_codec_oracle_kat import create_fr_pair, M, I, D, S
+    groups = []
+    shapes1 = [[(M, L)], [(S, 4), (M, L - 4)], [(M, 6), (D, 2), (M, L - 6)], [(M, 5), (I, 1), (M, L - 6)]]
+    shapes2 = [[(M, L)], [(M, L - 5), (S, 5)], [(M, L - 6), (D, 3), (M, 6)], [(M, L - 8), (I, 2), (M, 6)]]
+    for g in range(n_groups):
+        start1 = int(rng.integers(1, 150))
+        start2 = start1 + int(rng.integers(0, L + 6))        # sometimes past R1's end: no overlap
+        c1 = shapes1[int(rng.integers(0, 4))] if rng.random() < 0.4 else shapes1[0]
+        c2 = shapes2[int(rng.integers(0, 4))] if rng.random() < 0.4 else shapes2[0]
+        r1_rev = rng.random() < 0.4                            # R1 on the negative strand
+        n_pairs = int(rng.integers(1, 5))
+        noisy = rng.random() < 0.25
+        recs = []
+        for d in range(n_pairs):
+            cc1, cc2 = c1, c2
+            if n_pairs > 2 and d == n_pairs - 1 and rng.random() < 0.5:
+                cc1 = shapes1[2] if c1 is not shapes1[2] else shapes1[0]   # a minority alignment
+            def edit(s1, s2):
+                out = []
+                for s in (s1, s2):
+                    a = np.frombuffer(s, np.uint8).copy()
+                    m = rng.random(len(a)) < (0.25 if noisy else 0.03)
+                    a[m] = ACGT[rng.integers(0, 4, size=int(m.sum()))]
+                    if rng.random() < 0.1:
+                        a[int(rng.integers(0, len(a)))] = ord("N")
+                    out.append(a.tobytes())
+                return out
+            mi = None if g % 17 == 3 else b"%d" % g
+            if r1_rev:      # R1 is the right-hand, reverse mate
+                pair = create_fr_pair(b"p%d_%d" % (g, d), start2, start1, 30, cc2, cc1, mi=mi or b"x",
+                                      rx=b"ACG-TTA" if rng.random() < 0.9 else None, rev1=True, rev2=False,
+                                      seq_edit=edit, ref_oriented=True)
+            else:
+                pair = create_fr_pair(b"p%d_%d" % (g, d), start1, start2, 30, cc1, cc2, mi=mi or b"x",
+                                      rx=b"ACG-TTA" if rng.random() < 0.9 else None, seq_edit=edit,
+                                      ref_oriented=True)
+            # random per-base qualities + optional MC / CB tags are appended by re-building the records
+            out = []
+            for raw in pair:
+                r = R.Rec(raw)
+                q = rng.integers(5, 41, size=r.l_seq).astype(np.uint8).tobytes()
+                raw = bytearray(raw)
+                qo = r.seq_offset() + (r.l_seq + 1) // 2
+                raw[qo:qo + r.l_seq] = q
+                if mi is None:                                  # strip the MI tag (first tag: MI:Z:x\0)
+                    t = qo + r.l_seq
+                    assert raw[t:t + 3] == b"MIZ"
+                    del raw[t:t + 5]
+                if rng.random() < 0.5:
+                    raw += b"CBZCELL%d\0" % (g % 3)
+                out.append(bytes(raw))
+            if rng.random() < 0.07:
+                out = out[:1]                                    # a lone mate
+            recs += out
+        if rng.random() < 0.1:
+            recs.append(make_record(name=b"frag%d" % g, flags=0, pos=start1, seq=b"ACGTACGTAC",
+                                    tags=[(b"MI", "Z", b"%d" % g)]))
+        if rng.random() < 0.05:
+            recs = list(reversed(recs))
+        groups.append(recs)
+    return groups
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [
+    dict(),
+    dict(min_reads_per_strand=2, per_base=True),
+    dict(min_duplex_length=20, ss_qual=4, outer_qual=7, outer_len=6, per_base=True),
+    dict(max_dis=3, max_rate=0.2, per_base=False),
+])
+def test_codec_caller_bytes_match_oracle(kw):
+    import fgumi_b200 as fg
+    from tests.test_codec_oracle_kat import codec_job_fn
+    rng = np.random.default_rng(100 + len(kw))
+    groups = random_codec_groups(rng, 260)
+    caller = fg.CodecConsensusCaller(
+        "codec", "RG1", min_reads_per_strand=kw.get("min_reads_per_strand", 1),
+        min_duplex_length=kw.get("min_duplex_length", 1), single_strand_qual=kw.get("ss_qual"),
+        outer_bases_qual=kw.get("outer_qual"), outer_bases_length=kw.get("outer_len", 5),
+        max_duplex_disagreements=kw.get("max_dis"), max_duplex_disagreement_rate=kw.get("max_rate", 1.0),
+        produce_per_base_tags=kw.get("per_base", False), device=0, cell_tag=b"CB")
+    got = caller.consensus_reads_batch(groups)
+    gstats = caller.statistics()
+    caller.close()
+    oracle = R.CodecCallerOracle("codec", "RG1", vote_fn=vote_fn, builder_fn=O.builder_call,
+                                 codec_job_fn=codec_job_fn, cell_tag=b"CB", **kw)
+    want, count = bytearray(), 0
+    for g in groups:
+        d, n = oracle.consensus_reads(g)
+        want += d
+        count += n
+    assert got.count == count
+    if got.data != bytes(want):
+        a, b = parse_records(got.data), parse_records(bytes(want))
+        for i, (x, y) in enumerate(zip(a, b)):
+            assert x == y, (i, x, y)
+    assert got.data == bytes(want)
+    assert gstats["total_reads"] == oracle.total_input_reads
+    assert gstats["consensus_reads"] == oracle.consensus_reads_generated
+    assert gstats["filtered_reads"] == oracle.reads_filtered
+    for k in ("FragmentRead", "InsufficientReads", "MinorityAlignment", "InsufficientOverlap",
+              "IndelErrorBetweenStrands"):
+        assert gstats[k] == oracle.rejections.get(k, 0), k
+    assert gstats["duplex_bases"] == oracle.duplex_bases
+    assert gstats["duplex_disagreements"] == oracle.duplex_disagreements
+    assert count >= 60
+    assert oracle.rejections.get("InsufficientOverlap", 0) > 0 and oracle.rejections.get("FragmentRead", 0) > 0
+
+
+@pytest.mark.gpu
+def test_codec_known_answers_through_the_gpu_caller():
+    """codec_caller.rs:2190-2231, 2593-2681, 2768-2803 through fgb_caller_* in CODEC mode."""
+    import fgumi_b200 as fg
+    from tests.test_codec_oracle_kat import create_fr_pair, simple_pair, REF, M, D, S
+    c = fg.CodecConsensusCaller("codec", "RG1")
+    out = c.consensus_reads_batch([
+        simple_pair(ref_oriented=True),
+        create_fr_pair(b"read1", 1, 11, 35, [(M, 30)], [(M, 25), (D, 5), (M, 5)]),
+        create_fr_pair(b"read1", 1, 11, 35, [(S, 5), (M, 25)], [(M, 25), (S, 5)]),
+        create_fr_pair(b"read1", 1, 11, 35, [(M, 30)], [(M, 19), (D, 2), (M, 11)]),
+        create_fr_pair(b"read1", 100, 135, 35, [(M, 30)], [(M, 30)], rev1=True, rev2=False),
+    ])
+    st = c.statistics()
+    c.close()
+    recs = parse_records(out.data)
+    assert out.count == 3 and [len(r["bases"]) for r in recs] == [40, 40, 45]
+    assert recs[0]["bases"] == REF[:40] and recs[0]["name"] == b"codec:hi" and recs[0]["flags"] == 4
+    assert recs[0]["tags"][b"RX"] == b"ACC-TGA" and recs[0]["tags"][b"cD"] == 2
+    assert st["IndelErrorBetweenStrands"] == 2 and st["total_reads"] == 10 and st["consensus_reads"] == 3
