@@ -36,7 +36,7 @@ class VanillaUmiConsensusCaller(_Caller):
 
     def __init__(self, read_name_prefix: str, read_group_id: str,
                  options: VanillaUmiConsensusOptions = VanillaUmiConsensusOptions(), device: int = 0,
-                 tag: bytes = b"MI", cell_tag: bytes = b""):
+                 tag: bytes = b"MI", cell_tag: bytes = b"", consensus_call_overlapping_bases: bool = False):
         self._lib = _l.load()
         self._prefix = read_name_prefix.encode()
         self._rg = read_group_id.encode()
@@ -48,6 +48,7 @@ class VanillaUmiConsensusCaller(_Caller):
         o.min_consensus_base_quality = options.min_consensus_base_quality
         o.produce_per_base_tags = 1 if options.produce_per_base_tags else 0
         o.trim = 1 if options.trim else 0
+        o.consensus_call_overlapping_bases = 1 if consensus_call_overlapping_bases else 0
         o.min_reads = options.min_reads
         o.tag = tag
         o.cell_tag = cell_tag if cell_tag else b"\0\0"
@@ -108,12 +109,14 @@ class DuplexConsensusCaller(VanillaUmiConsensusCaller):
     def __init__(self, read_name_prefix: str, read_group_id: str, min_reads=(1, 1, 1),
                  error_rate_pre_umi: int = 45, error_rate_post_umi: int = 40,
                  min_input_base_quality: int = 10, produce_per_base_tags: bool = True,
-                 trim: bool = False, device: int = 0, cell_tag: bytes = b""):
+                 trim: bool = False, device: int = 0, cell_tag: bytes = b"",
+                 consensus_call_overlapping_bases: bool = False):
         self._lib = _l.load()
         self._prefix = read_name_prefix.encode()
         self._rg = read_group_id.encode()
         o = _l.FgbCallerOptions()
         o.mode = 1
+        o.consensus_call_overlapping_bases = 1 if consensus_call_overlapping_bases else 0
         o.error_rate_pre_umi = error_rate_pre_umi
         o.error_rate_post_umi = error_rate_post_umi
         o.min_input_base_quality = min_input_base_quality
@@ -161,3 +164,21 @@ class CodecConsensusCaller(VanillaUmiConsensusCaller):
         o.read_name_prefix = self._prefix
         o.read_group_id = self._rg
         self._create(o, device)
+
+
+def apply_overlapping_consensus(records: Sequence[bytes], agreement: int = 0, disagreement: int = 0):
+    """apply_overlapping_consensus (overlapping.rs:625-667) on one MI group.  Returns the rewritten
+    records and (overlapping_bases, bases_agreeing, bases_disagreeing, bases_corrected)."""
+    lib = _l.load()
+    if not records:
+        return [], (0, 0, 0, 0)
+    blob = np.frombuffer(b"".join(records), dtype=np.uint8).copy()
+    off = np.zeros(len(records) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(r) for r in records])
+    stats = np.zeros(4, dtype=np.uint64)
+    st = lib.fgb_overlap_apply_group(blob.ctypes.data, off.ctypes.data, len(records), agreement, disagreement,
+                                     stats.ctypes.data)
+    if st != _l.FGB_OK:
+        raise _l.FgbError(st, "fgb_overlap_apply_group")
+    out = [blob[int(off[i]):int(off[i + 1])].tobytes() for i in range(len(records))]
+    return out, tuple(int(x) for x in stats)

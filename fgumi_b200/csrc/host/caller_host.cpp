@@ -20,6 +20,7 @@
 
 #include "../../../include/fgumi_b200.h"
 #include "bam.h"
+#include "overlap.h"
 #include "prep.h"
 
 using namespace fgb;
@@ -88,6 +89,8 @@ struct fgb_caller {
   uint64_t out_count = 0;
   std::string last_error;
   std::vector<uint32_t> ops;             // scratch
+  overlap::Caller overlap{overlap::kAgreeConsensus, overlap::kDisagreeConsensus};   // simplex.rs:384-387
+  std::vector<uint8_t> group_copy;       // mutable copy of a group for the overlap pre-pass
 };
 
 namespace {
@@ -926,6 +929,8 @@ fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_call
   *out = nullptr;
   if (opt->mode > FGB_MODE_CODEC) return FGB_ERR_INVALID_ARG;
   if (opt->mode != FGB_MODE_DUPLEX && opt->min_reads == 0) return FGB_ERR_INVALID_ARG;
+  if (opt->mode == FGB_MODE_CODEC && opt->consensus_call_overlapping_bases)
+    return FGB_ERR_INVALID_ARG;   // "CODEC does not support overlapping consensus", commands/codec.rs:257
   if (opt->mode == FGB_MODE_DUPLEX &&
       (opt->min_xy_reads > opt->min_reads || opt->min_yx_reads > opt->min_xy_reads))
     return FGB_ERR_INVALID_ARG;   // "min-reads values must be specified high to low", duplex_caller.rs:385-395
@@ -985,6 +990,14 @@ fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uin
     recs.emplace_back(records + rec_off[i], len);
     if (recs.back().aux_off() > len) { c->last_error = "truncated BAM record"; return FGB_ERR_INVALID_ARG; }
   }
+  if (c->opt.consensus_call_overlapping_bases) {   // simplex.rs:395-398, duplex.rs:464-467
+    const uint64_t base = rec_off[0], total = rec_off[n_records] - base;
+    c->group_copy.assign(records + base, records + base + total);
+    std::vector<uint64_t> off(n_records + 1);
+    for (uint32_t i = 0; i <= n_records; ++i) off[i] = rec_off[i] - base;
+    c->overlap.apply_group(c->group_copy.data(), off.data(), n_records);
+    for (uint32_t i = 0; i < n_records; ++i) recs[i] = View(c->group_copy.data() + off[i], off[i + 1] - off[i]);
+  }
   if (c->opt.mode == FGB_MODE_DUPLEX) return add_group_duplex(c, recs);
   if (c->opt.mode == FGB_MODE_CODEC) return add_group_codec(c, recs);
   return add_group_simplex(c, recs);
@@ -1007,9 +1020,30 @@ fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* o
   return FGB_OK;
 }
 
+fgb_status fgb_overlap_apply_group(uint8_t* records, const uint64_t* rec_off, uint32_t n_records,
+                                   uint8_t agreement, uint8_t disagreement, uint64_t stats[4]) {
+  if (agreement > 2 || disagreement > 2 || (n_records && (!records || !rec_off))) return FGB_ERR_INVALID_ARG;
+  for (uint32_t i = 0; i < n_records; ++i) {
+    if (rec_off[i + 1] < rec_off[i] + 32) return FGB_ERR_INVALID_ARG;
+    View v(records + rec_off[i], rec_off[i + 1] - rec_off[i]);
+    if (v.aux_off() > v.n) return FGB_ERR_INVALID_ARG;
+  }
+  overlap::Caller oc(static_cast<overlap::Agreement>(agreement), static_cast<overlap::Disagreement>(disagreement));
+  oc.apply_group(records, rec_off, n_records);
+  if (stats) {
+    stats[0] += oc.stats.overlapping_bases; stats[1] += oc.stats.bases_agreeing;
+    stats[2] += oc.stats.bases_disagreeing; stats[3] += oc.stats.bases_corrected;
+  }
+  return FGB_OK;
+}
+
 fgb_status fgb_caller_stats(const fgb_caller* c, uint64_t stats[FGB_NSTATS]) {
   if (!c || !stats) return FGB_ERR_INVALID_ARG;
   std::memcpy(stats, c->stats, sizeof(c->stats));
+  stats[FGB_STAT_OVERLAP_BASES] = c->overlap.stats.overlapping_bases;
+  stats[FGB_STAT_OVERLAP_AGREEING] = c->overlap.stats.bases_agreeing;
+  stats[FGB_STAT_OVERLAP_DISAGREEING] = c->overlap.stats.bases_disagreeing;
+  stats[FGB_STAT_OVERLAP_CORRECTED] = c->overlap.stats.bases_corrected;
   return FGB_OK;
 }
 

@@ -117,7 +117,8 @@ class FgbCallerOptions(C.Structure):
     _fields_ = [
         ("mode", C.c_uint8), ("error_rate_pre_umi", C.c_uint8), ("error_rate_post_umi", C.c_uint8),
         ("min_input_base_quality", C.c_uint8), ("min_consensus_base_quality", C.c_uint8),
-        ("produce_per_base_tags", C.c_uint8), ("trim", C.c_uint8), ("reserved0", C.c_uint8),
+        ("produce_per_base_tags", C.c_uint8), ("trim", C.c_uint8),
+        ("consensus_call_overlapping_bases", C.c_uint8),
         ("min_reads", C.c_uint32), ("min_xy_reads", C.c_uint32), ("min_yx_reads", C.c_uint32),
         ("tag", C.c_char * 2), ("cell_tag", C.c_char * 2),
         ("read_name_prefix", C.c_char_p), ("read_group_id", C.c_char_p),
@@ -125,11 +126,12 @@ class FgbCallerOptions(C.Structure):
     ]
 
 
-FGB_NSTATS = 16
+FGB_NSTATS = 24
 STAT_NAMES = ("total_reads", "consensus_reads", "filtered_reads", "InsufficientReads",
               "SecondaryOrSupplementary", "ZeroLengthAfterTrimming", "MinorityAlignment",
               "OrphanConsensus", "PotentialCollision", "FragmentRead", "InsufficientOverlap",
-              "IndelErrorBetweenStrands", "duplex_bases", "duplex_disagreements")
+              "IndelErrorBetweenStrands", "duplex_bases", "duplex_disagreements", "overlapping_bases",
+              "overlap_bases_agreeing", "overlap_bases_disagreeing", "overlap_bases_corrected")
 
 
 class FgbCodecOut(C.Structure):
@@ -145,7 +147,7 @@ SYMBOLS = (
     "fgb_host_free", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
-    "fgb_caller_flush", "fgb_caller_stats",
+    "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group",
 )
 
 _lib = None
@@ -238,5 +240,7 @@ def load() -> C.CDLL:
     lib.fgb_caller_flush.restype = C.c_int32
     lib.fgb_caller_stats.argtypes = [vp, C.POINTER(u64)]
     lib.fgb_caller_stats.restype = C.c_int32
+    lib.fgb_overlap_apply_group.argtypes = [vp, vp, C.c_uint32, C.c_uint8, C.c_uint8, vp]
+    lib.fgb_overlap_apply_group.restype = C.c_int32
     _lib = lib
     return lib

@@ -307,7 +307,9 @@ typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanill
   uint8_t min_consensus_base_quality;      /* 40 (library) / 2 (CLI)                               */
   uint8_t produce_per_base_tags;           /* 1  */
   uint8_t trim;                            /* 0  */
-  uint8_t reserved0;
+  uint8_t consensus_call_overlapping_bases;/* 1 in the CLI (--consensus-call-overlapping-bases,
+                                              commands/common.rs:347-356): run the R1/R2 overlap
+                                              pre-pass on each group first; simplex/duplex only   */
   uint32_t min_reads;                      /* simplex: -M (per-position depth gate too); duplex:
                                               min total reads (duplex_caller.rs:358-395)           */
   uint32_t min_xy_reads;                   /* duplex only: min reads of the better-covered strand  */
@@ -338,8 +340,23 @@ enum {   /* ConsensusCallingStats (caller.rs:238-286) as a flat counter array   
   FGB_STAT_REJ_INDEL_ERROR = 11,              /* ::IndelErrorBetweenStrands (:697-737)           */
   FGB_STAT_DUPLEX_BASES = 12,                 /* consensus_duplex_bases_emitted (:1157)          */
   FGB_STAT_DUPLEX_DISAGREEMENTS = 13,         /* duplex_disagreement_base_count (:1158)          */
-  FGB_NSTATS = 16
+  FGB_STAT_OVERLAP_BASES = 14,                /* CorrectionStats (overlapping.rs:42-77)          */
+  FGB_STAT_OVERLAP_AGREEING = 15,
+  FGB_STAT_OVERLAP_DISAGREEING = 16,
+  FGB_STAT_OVERLAP_CORRECTED = 17,
+  FGB_NSTATS = 24
 };
+
+/* ---- overlapping-bases pre-pass (OverlappingBasesConsensusCaller, overlapping.rs:79-337) ---- */
+enum { FGB_OVERLAP_AGREE_CONSENSUS = 0, FGB_OVERLAP_AGREE_MAX_QUAL = 1, FGB_OVERLAP_AGREE_PASS_THROUGH = 2 };
+enum { FGB_OVERLAP_DISAGREE_CONSENSUS = 0, FGB_OVERLAP_DISAGREE_MASK_BOTH = 1,
+       FGB_OVERLAP_DISAGREE_MASK_LOWER_QUAL = 2 };
+/* apply_overlapping_consensus (overlapping.rs:625-667) on one MI group, IN PLACE: primary R1/R2
+ * records with the same name are paired and the bases they align to the same reference position
+ * are co-called (sequence nibbles and qualities rewritten).  stats[4] += {overlapping_bases,
+ * bases_agreeing, bases_disagreeing, bases_corrected}.  Host-only; needs no handle. */
+fgb_status fgb_overlap_apply_group(uint8_t* records, const uint64_t* rec_off, uint32_t n_records,
+                                   uint8_t agreement, uint8_t disagreement, uint64_t stats[4]);
 
 typedef struct fgb_caller fgb_caller;
 fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_caller** out);

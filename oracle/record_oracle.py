@@ -1262,3 +1262,186 @@ def codec_strands(ss1, ss2, r1_neg, r2_neg, cons_len):
     p1, p2 = _pad_ss(o1, cons_len, r1_neg), _pad_ss(o2, cons_len, r2_neg)
     ac, bc = (_rc_ss(p1), _rc_ss(p2)) if r1_neg else (p1, p2)
     return p1, p2, ac, bc
+
+
+# =================================================================================================
+# Overlapping-bases pre-pass (crates/fgumi-consensus/src/overlapping.rs)
+# =================================================================================================
+AGREE_CONSENSUS, AGREE_MAX_QUAL, AGREE_PASS_THROUGH = 0, 1, 2          # AgreementStrategy :20-28
+DISAGREE_CONSENSUS, DISAGREE_MASK_BOTH, DISAGREE_MASK_LOWER = 0, 1, 2  # DisagreementStrategy :31-39
+
+
+class _ReadAndRefPosIterator:
+    """ReadAndRefPosIterator, overlapping.rs:382-553 (1-based read and reference positions)."""
+
+    def __init__(self, rec: Rec, rec_start, rec_end, mate_start, mate_end):    # :411-449
+        self.ops = [(op & 0xF, op >> 4) for op in rec.cigar_ops()]
+        min_ref, max_ref = max(rec_start, mate_start), min(rec_end, mate_end)
+        self.start_read_pos, self.end_read_pos = 1, rec.l_seq
+        self.start_ref_pos, self.end_ref_pos = max(rec_start, min_ref), min(rec_end, max_ref)
+        self.cur_read_pos, self.cur_ref_pos = 1, rec_start
+        self.element_index = self.in_elem_offset = 0
+        self._skip_to_start()
+
+    def _on_target(self):                                                # :452-460
+        if self.element_index >= len(self.ops):
+            return 0
+        k, n = self.ops[self.element_index]
+        return n if k in (0, 2, 3, 7, 8) else 0
+
+    def _on_query(self):                                                 # :463-471
+        if self.element_index >= len(self.ops):
+            return 0
+        k, n = self.ops[self.element_index]
+        return n if k in (0, 1, 4, 7, 8) else 0
+
+    def _is_alignment(self):                                             # :474-481
+        return self.element_index < len(self.ops) and self.ops[self.element_index][0] in (0, 7, 8)
+
+    def _skip_to_start(self):                                            # :484-499
+        while self.element_index < len(self.ops):
+            ref_end = self.cur_ref_pos + self._on_target() - 1
+            read_end = self.cur_read_pos + self._on_query() - 1
+            if ref_end >= self.start_ref_pos and read_end >= self.start_read_pos:
+                break
+            self.cur_ref_pos += self._on_target()
+            self.cur_read_pos += self._on_query()
+            self.element_index += 1
+        self._skip_non_aligned()
+
+    def _skip_non_aligned(self):                                         # :502-521
+        self.in_elem_offset = 0
+        while self.element_index < len(self.ops) and not self._is_alignment():
+            self.cur_ref_pos += self._on_target()
+            self.cur_read_pos += self._on_query()
+            self.element_index += 1
+        if self.element_index < len(self.ops) and (self.cur_ref_pos < self.start_ref_pos or
+                                                   self.cur_read_pos < self.start_read_pos):
+            off = max(self.start_ref_pos - self.cur_ref_pos, self.start_read_pos - self.cur_read_pos)
+            self.in_elem_offset = off
+            self.cur_ref_pos += off
+            self.cur_read_pos += off
+
+    def next(self):                                                      # :531-559
+        if self.element_index < len(self.ops):
+            if self.in_elem_offset >= self.ops[self.element_index][1]:
+                self.element_index += 1
+                self._skip_non_aligned()
+        if (self.element_index >= len(self.ops) or self.cur_read_pos > self.end_read_pos or
+                self.cur_ref_pos > self.end_ref_pos):
+            return None
+        pos = (self.cur_read_pos - 1, self.cur_ref_pos)
+        self.cur_read_pos += 1
+        self.cur_ref_pos += 1
+        self.in_elem_offset += 1
+        return pos
+
+
+def _set_base(rec: bytearray, seq_off: int, i: int, base: int):          # sequence.rs:53-61
+    code = b"=ACMGRSVTWYHKDBN".find(bytes([base]))
+    code = 15 if code < 0 else code
+    j = seq_off + i // 2
+    rec[j] = ((code << 4) | (rec[j] & 0x0F)) if i % 2 == 0 else ((rec[j] & 0xF0) | code)
+
+
+class OverlappingOracle:
+    """OverlappingBasesConsensusCaller (overlapping.rs:79-337) + apply_overlapping_consensus (:625)."""
+
+    def __init__(self, agreement=AGREE_CONSENSUS, disagreement=DISAGREE_CONSENSUS):
+        self.agreement, self.disagreement = agreement, disagreement
+        self.overlapping_bases = self.bases_agreeing = self.bases_disagreeing = self.bases_corrected = 0
+
+    def stats(self):
+        return (self.overlapping_bases, self.bases_agreeing, self.bases_disagreeing, self.bases_corrected)
+
+    def call(self, r1: bytearray, r2: bytearray) -> bool:                # :236-337
+        v1, v2 = Rec(bytes(r1)), Rec(bytes(r2))
+        if (v1.flags & UNMAPPED) or (v2.flags & UNMAPPED) or v1.ref_id != v2.ref_id:
+            return False
+
+        def span(v):                                                     # cigar.rs:314-335
+            if v.pos < 0:
+                return None
+            rl = reference_length(v.cigar_ops())
+            return (v.pos + 1, v.pos + rl) if rl != 0 else None
+        s1, s2 = span(v1), span(v2)
+        if s1 is None or s2 is None:
+            return False
+        it1 = _ReadAndRefPosIterator(v1, s1[0], s1[1], s2[0], s2[1])
+        it2 = _ReadAndRefPosIterator(v2, s2[0], s2[1], s1[0], s1[1])
+        pairs = []                                                       # merge walk :586-617
+        a, b = it1.next(), it2.next()
+        while a is not None and b is not None:
+            if a[1] < b[1]:
+                a = it1.next()
+            elif a[1] > b[1]:
+                b = it2.next()
+            else:
+                pairs.append((a[0], b[0]))
+                a, b = it1.next(), it2.next()
+        if not pairs:
+            return False
+        seq1, seq2 = v1.sequence(), v2.sequence()
+        q1, q2 = v1.quals(), v2.quals()
+        modified = False
+        nocall = (ord("N"), ord("n"), ord("."))
+        for o1, o2 in pairs:
+            b1, b2 = seq1[o1], seq2[o2]
+            if b1 in nocall or b2 in nocall:
+                continue
+            self.overlapping_bases += 1
+            x, y = q1[o1], q2[o2]
+            if b1 == b2:
+                self.bases_agreeing += 1
+                if self.agreement == AGREE_PASS_THROUGH:
+                    continue
+                nq = min(x + y, 93) if self.agreement == AGREE_CONSENSUS else max(x, y)
+                q1[o1] = q2[o2] = nq
+                if nq != x or nq != y:
+                    self.bases_corrected += 1
+                    modified = True
+            else:
+                self.bases_disagreeing += 1
+                modified = True
+                if self.disagreement == DISAGREE_CONSENSUS:
+                    if x == y:
+                        cb, cq = ord("N"), 2
+                    elif x > y:
+                        cb, cq = b1, max(x - y, 2)
+                    else:
+                        cb, cq = b2, max(y - x, 2)
+                    seq1[o1] = seq2[o2] = cb
+                    q1[o1] = q2[o2] = cq
+                    self.bases_corrected += 2
+                elif self.disagreement == DISAGREE_MASK_BOTH or x == y:
+                    seq1[o1] = seq2[o2] = ord("N")
+                    q1[o1] = q2[o2] = 2
+                    self.bases_corrected += 2
+                elif x < y:
+                    seq1[o1], q1[o1] = ord("N"), 2
+                    self.bases_corrected += 1
+                else:
+                    seq2[o2], q2[o2] = ord("N"), 2
+                    self.bases_corrected += 1
+        if modified:
+            for rec, v, seq, q in ((r1, v1, seq1, q1), (r2, v2, seq2, q2)):
+                so = v.seq_offset()
+                for i, base in enumerate(seq):
+                    _set_base(rec, so, i, base)
+                qo = so + (v.l_seq + 1) // 2
+                rec[qo:qo + len(q)] = q
+        return True
+
+    def apply(self, records: List[bytearray]):                           # :625-667
+        pairs: Dict[bytes, List[Optional[int]]] = {}
+        for idx, raw in enumerate(records):
+            v = Rec(bytes(raw))
+            if v.flags & (SECONDARY | SUPPLEMENTARY):
+                continue
+            if v.flags & FIRST_SEGMENT:
+                pairs.setdefault(v.name, [None, None])[0] = idx
+            elif v.flags & LAST_SEGMENT:
+                pairs.setdefault(v.name, [None, None])[1] = idx
+        for i1, i2 in pairs.values():
+            if i1 is not None and i2 is not None:
+                self.call(records[i1], records[i2])
