@@ -84,12 +84,27 @@ class TorchBatch:
                            self.units.data_ptr(), self.tiles.data_ptr())
 
 
-def _gen_rows(torch, dev, gen, depths_t, L, Lp, error_rate, out_b, out_q, row0, chunk_units):
+def _hashed_templates(torch, dev, template_ids, L, seed):
+    """Template base codes as a stateless hash of (seed, template id, position): units that share a
+    template id share a template, independent of how the batch is chunked."""
+    x = template_ids.to(dev, torch.int64)[:, None] * 1_000_003 + torch.arange(L, device=dev)[None, :]
+    x = x + seed * 7_919
+    x = (x ^ (x >> 30)) * -4658895280553007687      # splitmix64 constants (int64 arithmetic wraps)
+    x = (x ^ (x >> 27)) * -7723592293110705685
+    x = x ^ (x >> 31)
+    return (x >> 40) & 3
+
+
+def _gen_rows(torch, dev, gen, depths_t, L, Lp, error_rate, out_b, out_q, row0, chunk_units,
+              template_ids=None, seed=0):
     """Fill rows [row0, row0 + sum(depths)) of the [R, Lp] byte matrices for one chunk of units."""
     U = depths_t.numel()
     acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
     curve = torch.from_numpy(_base_quality_curve(L)).to(dev, torch.float32)
-    tmpl_code = torch.randint(0, 4, (U, L), device=dev, generator=gen, dtype=torch.int64)
+    if template_ids is None:
+        tmpl_code = torch.randint(0, 4, (U, L), device=dev, generator=gen, dtype=torch.int64)
+    else:
+        tmpl_code = _hashed_templates(torch, dev, template_ids, L, seed)
     unit_of_row = torch.repeat_interleave(torch.arange(U, device=dev), depths_t)
     R = unit_of_row.numel()
     code = tmpl_code[unit_of_row]                                   # [R, L]
@@ -131,7 +146,8 @@ def make_descriptors(depths: np.ndarray, L: int = 150, min_reads: int = 1) -> Pa
 
 
 def device_batch(torch, device, depths: np.ndarray, L: int = 150, error_rate: float = 1e-3,
-                 seed: int = 42, min_reads: int = 1, chunk_rows: int = 2_000_000) -> TorchBatch:
+                 seed: int = 42, min_reads: int = 1, chunk_rows: int = 2_000_000,
+                 template_ids: np.ndarray = None) -> TorchBatch:
     """Build a batch with per-unit depths `depths` (fixed or ragged), all reads of length L,
     directly in device memory.  Host keeps only the (small) unit/read/tile descriptors."""
     depths = np.asarray(depths, dtype=np.int64)
@@ -154,7 +170,9 @@ def device_batch(torch, device, depths: np.ndarray, L: int = 150, error_rate: fl
         u1 = int(np.searchsorted(read_begin, read_begin[u0] + chunk_rows, side="right")) - 1
         u1 = max(u0 + 1, min(U, u1))
         d = torch.from_numpy(depths[u0:u1]).to(dev)
-        _gen_rows(torch, dev, gen, d, L, Lp, error_rate, bmat, qmat, int(read_begin[u0]), u1 - u0)
+        tid = None if template_ids is None else torch.from_numpy(
+            np.ascontiguousarray(template_ids[u0:u1]).astype(np.int64))
+        _gen_rows(torch, dev, gen, d, L, Lp, error_rate, bmat, qmat, int(read_begin[u0]), u1 - u0, tid, seed)
         u0 = u1
     to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
     tiles = host.tiles if len(host.tiles) else np.zeros(1, dtype=TILE_DTYPE)
