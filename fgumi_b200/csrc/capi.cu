@@ -258,11 +258,22 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
   uint64_t prev_read_end = 0;
 
   uint32_t cur_items = 0;     // 8-position items per unit if uniform so far, 0xFFFFFFFF = mixed
+  bool regular = false;       // open tile: equal-length rows packed at stride round_up(len, 8)
+  uint32_t reg_len = 0;
+  uint64_t reg_next = 0;      // where the next row must start for the tile to stay regular
+  uint32_t max_reads_in_unit = 0;
   auto emit = [&]() {
     cur.byte_len = static_cast<uint32_t>(((cur_end + 15u) & ~15ull) - cur.byte_begin);
     if (cur.flags & kTileFlagDirect) { cur.byte_len = 0; }
-    if (cur_items != 0xFFFFFFFFu && cur_items >= 2 && cur_items <= 4096)   // umulhi exactness
-      cur.flags |= cur_items << 8;    // hint: unit index = item / cur_items
+    const bool uniform = cur_items != 0xFFFFFFFFu && cur_items >= 2 && cur_items <= 4096;   // umulhi exactness
+    if (uniform) cur.flags |= cur_items << 8;    // hint: unit index = item / cur_items
+    if (!(cur.flags & kTileFlagDirect)) {
+      if (regular && uniform && cur.n_reads > 0) {
+        cur.flags |= kTileFlagRegular;
+        if (FGB_READ_OFF(reads[cur.read_begin]) != cur.byte_begin) cur.flags |= kTileFlagSkew8;
+      }
+      if (max_reads_in_unit <= 8) cur.flags |= kTileFlagShallow;
+    }
     if (out && nt < cap) out[nt] = cur;
     ++nt;
     open = false;
@@ -314,7 +325,20 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
       uint64_t span = ((ue + 15u) & ~15ull) - cur.byte_begin;
       if (span > kTileCapBytes || nr + (cur.read_begin & 1u) > kTileMaxReads)
         cur.flags |= kTileFlagDirect;   // oversize unit: kernel votes it straight from HBM
+      regular = nr > 0;
+      reg_len = nr ? FGB_READ_LEN(reads[un.read_begin]) : 0;
+      reg_next = ub;
+      max_reads_in_unit = 0;
     }
+    if (regular) {   // still regular with this unit?
+      const uint64_t stride = (static_cast<uint64_t>(reg_len) + 7u) & ~7ull;
+      if (nr == 0 || un.cons_len != reg_len) regular = false;
+      for (uint32_t r = un.read_begin; regular && r < nx.read_begin; ++r) {
+        if (FGB_READ_LEN(reads[r]) != reg_len || FGB_READ_OFF(reads[r]) != reg_next) regular = false;
+        reg_next += stride;
+      }
+    }
+    max_reads_in_unit = std::max(max_reads_in_unit, nr);
     {
       uint32_t items = (un.cons_len + 7u) >> 3;
       if (cur.n_units == 0) cur_items = items;

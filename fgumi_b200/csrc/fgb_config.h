@@ -17,5 +17,10 @@ constexpr uint32_t kWarpQueueCap = 96;     // undecided positions buffered per w
 constexpr uint32_t kQtEntries = 256;       // fast-path quality threshold table, indexed by min(n,255)
 
 constexpr uint32_t kTileFlagDirect = 1u;   // unit too large for a stage: kernel reads it from HBM
+constexpr uint32_t kTileFlagRegular = 2u;  // all reads one length L, rows back to back at stride
+                                           // round_up(L,8), every unit calls L positions (L > 8)
+constexpr uint32_t kTileFlagSkew8 = 4u;    // regular tiles: first row starts 8 bytes into the stage
+constexpr uint32_t kTileFlagShallow = 8u;  // no unit of the tile has more than 8 reads
+// bits 8..31: items (8-position words) per unit when uniform over the tile (2..4096), else 0
 
 }  // namespace fgb

@@ -397,19 +397,23 @@ template <class M>
 __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, const Stage& st,
                                        const TileView<M>& tv, const uint32_t* wqueue, uint32_t qn,
                                        uint32_t lane, LocalStats& ls) {
-  // group width: warp-uniform
-  uint32_t nmax = 0;
-  for (uint32_t e = lane; e < qn; e += 32) {
-    uint32_t u = wqueue[e] >> 16;
-    uint32_t n = st.units[u + 1].read_begin - st.units[u].read_begin;
-    nmax = n > nmax ? n : nmax;
-  }
+  // group width (warp-uniform): 8 lanes per position when the planner saw no unit deeper than 8
+  // reads in this tile, else look at the queued units
+  uint32_t G = 8u;
+  if (!(st.tile.flags & kTileFlagShallow)) {
+    uint32_t nmax = 0;
+    for (uint32_t e = lane; e < qn; e += 32) {
+      uint32_t u = wqueue[e] >> 16;
+      uint32_t n = st.units[u + 1].read_begin - st.units[u].read_begin;
+      nmax = n > nmax ? n : nmax;
+    }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, nmax, off);
-    nmax = o > nmax ? o : nmax;
+    for (int off = 16; off > 0; off >>= 1) {
+      uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, nmax, off);
+      nmax = o > nmax ? o : nmax;
+    }
+    G = nmax <= 8u ? 8u : 32u;
   }
-  const uint32_t G = nmax <= 8u ? 8u : 32u;
   const uint32_t per_pass = 32u / G;
   const uint32_t sub = lane & (G - 1u);
   for (uint32_t e0 = 0; e0 < qn; e0 += per_pass) {
@@ -498,7 +502,11 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
 // Votes this warp's share of one tile.  Called by the eight consumer warps; `vt` is the thread's
 // rotating slot (0..kVoteThreads-1): it owns items vt, vt+256, ...  An item is 8 consecutive
 // positions of one unit: one 64-bit word of every read's base row and quality row.
-template <class M>
+//
+// Regular tiles (planner flag): every read of the tile has the same length L, rows are packed back
+// to back at stride round_up(L, 8) and every unit calls L positions.  The read descriptors are then
+// redundant for the scan: read r of the tile starts at word (r - tile.read_begin) * m, m = stride/8.
+template <class M, bool Regular>
 __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const Stage& st,
                                           const TileView<M>& tv, uint32_t vt, uint32_t warp,
                                           LocalStats& ls) {
@@ -507,6 +515,11 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
   const uint64_t out0 = st.units[0].out_off;
   const uint32_t n_items = static_cast<uint32_t>((st.units[n_units].out_off - out0) >> 3);
   const uint32_t min_reads = a.min_reads, min_cons_q = a.min_cons_q, fast_qual = a.fast_qual;
+  // regular-tile constants
+  const uint32_t reg_len = st.units[0].cons_len;
+  const uint32_t reg_tail = reg_len - (((reg_len + 7u) >> 3) - 1u) * 8u;      // positions in a row's last word
+  const uint32_t reg_tl_lo = low_bytes_mask(reg_tail), reg_tl_hi = low_bytes_mask(reg_tail > 4u ? reg_tail - 4u : 0u);
+  const uint32_t reg_row0 = (st.tile.flags & kTileFlagSkew8) ? 8u : 0u;        // first row inside the stage
   // constant result of a proven position after the thresholds of vanilla_caller.rs:1345-1349
   const bool fast_masked = fast_qual < min_cons_q;
   const uint32_t fq4 = (fast_masked ? 2u : fast_qual) * 0x01010101u;
@@ -520,7 +533,7 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
   // ---------------- FAST PASS: one thread per 8 positions ----------------
   for (uint32_t item = vt; item < n_items; item += kVoteThreads) {
     uint32_t u;
-    if (uni_m) {
+    if (Regular || uni_m) {
       u = __umulhi(item, uni_recip);            // exact floor(item / uni_m): 2 <= uni_m <= 4096, item*uni_m < 2^32
     } else {                                    // largest u with start(u) <= item
       uint32_t lo = 0, hi = n_units;
@@ -535,20 +548,40 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
     const uint32_t rb = un.read_begin;
     const uint32_t n = st.units[u + 1].read_begin - rb;
     const uint32_t cons_len = un.cons_len;
-    const uint32_t p0 = (item - static_cast<uint32_t>((un.out_off - out0) >> 3)) << 3;
     const uint64_t o = out0 + (static_cast<uint64_t>(item) << 3);
-    const uint32_t real = cons_len - p0 < 8u ? cons_len - p0 : 8u;   // positions of this item (>= 1)
-    const uint32_t rm_lo = low_bytes_mask(real), rm_hi = low_bytes_mask(real > 4u ? real - 4u : 0u);
+    uint32_t p0, real, rm_lo, rm_hi;
+    uint32_t reg_word = 0;                      // regular tiles: word index of read 0's word in the stage
+    if (Regular) {
+      const uint32_t w = item - u * uni_m;
+      const bool last = w + 1u == uni_m;
+      p0 = w << 3;
+      real = last ? reg_tail : 8u;
+      rm_lo = last ? reg_tl_lo : 0x80808080u;
+      rm_hi = last ? reg_tl_hi : 0x80808080u;
+      reg_word = (rb - st.tile.read_begin) * uni_m + w;
+    } else {
+      p0 = (item - static_cast<uint32_t>((un.out_off - out0) >> 3)) << 3;
+      real = cons_len - p0 < 8u ? cons_len - p0 : 8u;   // positions of this item (>= 1)
+      rm_lo = low_bytes_mask(real); rm_hi = low_bytes_mask(real > 4u ? real - 4u : 0u);
+    }
 
     uint32_t wb_lo = 0, wb_hi = 0, wq_lo = 0, wq_hi = 0;   // 8 output bases / quals
     uint4 dep = make_uint4(0, 0, 0, 0), err = make_uint4(0, 0, 0, 0);   // 8 x u16 each
+    uint32_t todo_lo = 0, todo_hi = 0;          // positions left for in-place resolution (queue overflow)
     ls.positions += real;
 
     if (n == 1) {
       // single-read consensus, vanilla_caller.rs:1285-1316
-      uint64_t d = M::ld64(tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u);
-      uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
-      typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + p0;
+      uint32_t len;
+      typename M::off_t row;
+      if (Regular) {
+        len = reg_len;
+        row = reg_row0 + reg_word * 8u;
+      } else {
+        uint64_t d = M::ld64(tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u);
+        len = static_cast<uint32_t>(d & 0xFFFFu);
+        row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + p0;
+      }
       uint64_t rbw = 0, rqw = 0;
       if (p0 < len) { rbw = M::ld64(tv.bases + row); rqw = M::ld64(tv.quals + row); }
       uint64_t obw = 0, oqw = 0, odw_lo = 0, odw_hi = 0;
@@ -581,35 +614,56 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
       uint32_t fm_lo = 0, fm_hi = 0, b0_lo = 0, b0_hi = 0;
       if (fast_ok) {
         const uint32_t tsplat = qt * 0x01010101u;
-        typename M::addr_t rd = tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u;
         uint32_t diff_lo = 0, diff_hi = 0, okq_lo = 0x80808080u, okq_hi = 0x80808080u;
-        uint32_t minlen = 0xFFFFFFFFu;
-        {   // reference word: read 0 (if it does not reach p0, minlen vetoes the item anyway)
-          uint64_t d = M::ld64(rd);
-          uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
-          uint64_t w = M::ld64(tv.bases + M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u));
-          b0_lo = static_cast<uint32_t>(w); b0_hi = static_cast<uint32_t>(w >> 32);
-        }
+        if (Regular) {
+          // every read covers the item: walk the rows at a constant stride, no descriptors
+          typename M::addr_t pb = tv.bases + reg_row0 + reg_word * 8u;
+          const uint32_t step = uni_m * 8u;
+          {
+            uint64_t w = M::ld64(pb);
+            b0_lo = static_cast<uint32_t>(w); b0_hi = static_cast<uint32_t>(w >> 32);
+          }
 #pragma unroll 4
-        for (uint32_t r = 0; r < n; ++r) {
-          uint64_t d = M::ld64(rd + r * 8u);
-          uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
-          minlen = len < minlen ? len : minlen;
-          // an uncovered read points at its own first word: harmless, minlen already vetoes
-          typename M::off_t row = M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u);
-          uint64_t wb = M::ld64(tv.bases + row);
-          uint64_t wq = M::ld64(tv.quals + row);
-          diff_lo |= static_cast<uint32_t>(wb) ^ b0_lo;
-          diff_hi |= static_cast<uint32_t>(wb >> 32) ^ b0_hi;
-          // byte high bit survives iff q >= qT (no borrows: every minuend byte is >= 0x80 > qT)
-          okq_lo &= (static_cast<uint32_t>(wq) | 0x80808080u) - tsplat;
-          okq_hi &= (static_cast<uint32_t>(wq >> 32) | 0x80808080u) - tsplat;
+          for (uint32_t r = 0; r < n; ++r, pb += step) {
+            uint64_t wb = M::ld64(pb);
+            uint64_t wq = M::ld64(pb + kTileCapBytes);      // quality column sits kTileCapBytes above
+            diff_lo |= static_cast<uint32_t>(wb) ^ b0_lo;
+            diff_hi |= static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+            okq_lo &= (static_cast<uint32_t>(wq) | 0x80808080u) - tsplat;
+            okq_hi &= (static_cast<uint32_t>(wq >> 32) | 0x80808080u) - tsplat;
+          }
+          fm_lo = zero_bytes(diff_lo) & okq_lo & acgt_bytes(b0_lo) & rm_lo;
+          fm_hi = zero_bytes(diff_hi) & okq_hi & acgt_bytes(b0_hi) & rm_hi;
+        } else {
+          typename M::addr_t rd = tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u;
+          uint32_t minlen = 0xFFFFFFFFu;
+          {   // reference word: read 0 (if it does not reach p0, minlen vetoes the item anyway)
+            uint64_t d = M::ld64(rd);
+            uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
+            uint64_t w = M::ld64(tv.bases + M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u));
+            b0_lo = static_cast<uint32_t>(w); b0_hi = static_cast<uint32_t>(w >> 32);
+          }
+#pragma unroll 4
+          for (uint32_t r = 0; r < n; ++r) {
+            uint64_t d = M::ld64(rd + r * 8u);
+            uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
+            minlen = len < minlen ? len : minlen;
+            // an uncovered read points at its own first word: harmless, minlen already vetoes
+            typename M::off_t row = M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u);
+            uint64_t wb = M::ld64(tv.bases + row);
+            uint64_t wq = M::ld64(tv.quals + row);
+            diff_lo |= static_cast<uint32_t>(wb) ^ b0_lo;
+            diff_hi |= static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+            // byte high bit survives iff q >= qT (no borrows: every minuend byte is >= 0x80 > qT)
+            okq_lo &= (static_cast<uint32_t>(wq) | 0x80808080u) - tsplat;
+            okq_hi &= (static_cast<uint32_t>(wq >> 32) | 0x80808080u) - tsplat;
+          }
+          // per-byte verdict: unanimous & quality-proven & A/C/G/T & covered by every read
+          const uint32_t covered = minlen > p0 ? minlen - p0 : 0u;
+          fm_lo = zero_bytes(diff_lo) & okq_lo & acgt_bytes(b0_lo) & low_bytes_mask(covered) & rm_lo;
+          fm_hi = zero_bytes(diff_hi) & okq_hi & acgt_bytes(b0_hi) &
+                  low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
         }
-        // per-byte verdict: unanimous & quality-proven & A/C/G/T & covered by every read
-        const uint32_t covered = minlen > p0 ? minlen - p0 : 0u;
-        fm_lo = zero_bytes(diff_lo) & okq_lo & acgt_bytes(b0_lo) & low_bytes_mask(covered) & rm_lo;
-        fm_hi = zero_bytes(diff_hi) & okq_hi & acgt_bytes(b0_hi) &
-                low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
       }
       // proven positions: constant quality, depth n, no errors
       const uint32_t fb_lo = (fm_lo >> 7) * 0xFFu, fb_hi = (fm_hi >> 7) * 0xFFu;
@@ -619,43 +673,42 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
       wq_hi = fq4 & fb_hi;
       const uint32_t nn = n | (n << 16);
       // expand byte mask pairs to u16 pairs: bytes (0,1) -> dep.x, (2,3) -> dep.y, ...
-      dep.x = nn & (((fb_lo & 0xFFu) * 0x0101u) | ((fb_lo & 0xFF00u) * 0x010100u));
-      dep.y = nn & ((((fb_lo >> 16) & 0xFFu) * 0x0101u) | (((fb_lo >> 16) & 0xFF00u) * 0x010100u));
-      dep.z = nn & (((fb_hi & 0xFFu) * 0x0101u) | ((fb_hi & 0xFF00u) * 0x010100u));
-      dep.w = nn & ((((fb_hi >> 16) & 0xFFu) * 0x0101u) | (((fb_hi >> 16) & 0xFF00u) * 0x010100u));
+      dep.x = nn & __byte_perm(fb_lo, 0u, 0x1100u);
+      dep.y = nn & __byte_perm(fb_lo, 0u, 0x3322u);
+      dep.z = nn & __byte_perm(fb_hi, 0u, 0x1100u);
+      dep.w = nn & __byte_perm(fb_hi, 0u, 0x3322u);
       ls.nocall += fast_masked ? (__popc(fm_lo) + __popc(fm_hi)) : 0;
-      const uint32_t todo_lo = rm_lo & ~fm_lo, todo_hi = rm_hi & ~fm_hi;
+      todo_lo = rm_lo & ~fm_lo; todo_hi = rm_hi & ~fm_hi;
       if (todo_lo | todo_hi) {
-        // undecided positions go to this warp's queue (or are resolved in place if it is full)
-        uint32_t slot = atomicAdd(wcount, static_cast<uint32_t>(__popc(todo_lo) + __popc(todo_hi)));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t bit = 0x80u << (8 * (j & 3));
-          if ((j < 4 ? todo_lo : todo_hi) & bit) {
-            uint32_t pos = p0 + j;
-            if (slot < kWarpQueueCap) {
-              wqueue[slot] = (u << 16) | pos;
-            } else {
-              Called c = resolve_position<M>(tv, S, rb, n, pos, a, ls);
-              uint32_t sb = (c.base & 0xFFu) << (8 * (j & 3)), sq = (c.qual & 0xFFu) << (8 * (j & 3));
-              if (j < 4) { wb_lo |= sb; wq_lo |= sq; } else { wb_hi |= sb; wq_hi |= sq; }
-              uint32_t dv = (c.depth & 0xFFFFu) << (16 * (j & 1)), ev = (c.errors & 0xFFFFu) << (16 * (j & 1));
-              switch (j >> 1) {
-                case 0: dep.x |= dv; err.x |= ev; break;
-                case 1: dep.y |= dv; err.y |= ev; break;
-                case 2: dep.z |= dv; err.z |= ev; break;
-                default: dep.w |= dv; err.w |= ev; break;
-              }
-            }
-            ++slot;
-          }
+        // undecided positions go to this warp's queue; if it is full they are resolved in place,
+        // after the item's words have been stored (below)
+        const uint32_t cnt = static_cast<uint32_t>(__popc(todo_lo) + __popc(todo_hi));
+        uint32_t slot = atomicAdd(wcount, cnt);
+        const uint32_t ent = (u << 16) | p0;
+        uint32_t keep_lo = 0, keep_hi = 0;
+        for (uint32_t t = todo_lo; t; t &= t - 1u, ++slot) {
+          if (slot < kWarpQueueCap) wqueue[slot] = ent + ((__ffs(t) - 1) >> 3);
+          else keep_lo |= t & (0u - t);
         }
+        for (uint32_t t = todo_hi; t; t &= t - 1u, ++slot) {
+          if (slot < kWarpQueueCap) wqueue[slot] = ent + 4u + ((__ffs(t) - 1) >> 3);
+          else keep_hi |= t & (0u - t);
+        }
+        todo_lo = keep_lo; todo_hi = keep_hi;
       }
     }
     *reinterpret_cast<uint2*>(a.out_base + o) = make_uint2(wb_lo, wb_hi);
     *reinterpret_cast<uint2*>(a.out_qual + o) = make_uint2(wq_lo, wq_hi);
     *reinterpret_cast<uint4*>(a.out_depth + o) = dep;
     *reinterpret_cast<uint4*>(a.out_errors + o) = err;
+    if (todo_lo | todo_hi) {                    // rare: the warp queue overflowed
+      for (uint32_t j = 0; j < 8u; ++j) {
+        if ((j < 4u ? todo_lo >> (8u * j) : todo_hi >> (8u * (j - 4u))) & 0x80u) {
+          Called c = resolve_position<M>(tv, S, rb, n, p0 + j, a, ls);
+          write_called(a, o + j, c);
+        }
+      }
+    }
   }
   __syncwarp();
 
@@ -752,13 +805,14 @@ __global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
       tv.bases = a.bases; tv.quals = a.quals;
       tv.reads = reinterpret_cast<const uint8_t*>(a.reads + st.tile.read_begin);
       tv.byte_base = 0; tv.read_base = st.tile.read_begin;
-      vote_tile<GlMem>(a, S, st, tv, vt, warp, ls);
+      vote_tile<GlMem, false>(a, S, st, tv, vt, warp, ls);
     } else {
       TileView<ShMem> tv;
       tv.bases = st.bases; tv.quals = st.quals;
       tv.reads = reinterpret_cast<const uint8_t*>(st.reads) + (st.tile.read_begin & 1u) * 8u;
       tv.byte_base = st.tile.byte_begin; tv.read_base = st.tile.read_begin;
-      vote_tile<ShMem>(a, S, st, tv, vt, warp, ls);
+      if (st.tile.flags & kTileFlagRegular) vote_tile<ShMem, true>(a, S, st, tv, vt, warp, ls);
+      else vote_tile<ShMem, false>(a, S, st, tv, vt, warp, ls);
     }
     if (tid == 0) { n_units_done += st.tile.n_units; n_reads_done += st.tile.n_reads; }
     rot = (rot + n_items) & (kVoteThreads - 1);
