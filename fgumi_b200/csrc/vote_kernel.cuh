@@ -70,6 +70,7 @@ struct __align__(16) Stage {
   uint64_t reads[kTileMaxReads + 2];
   fgb_unit units[kTileMaxUnits + 1];
   fgb_tile tile;
+  uint32_t aux[4];   // written by the producer: [0] = 2^32 / items-per-unit + 1 (uniform tiles), [1] = items
 };
 
 struct __align__(128) VoteSmem {
@@ -393,31 +394,15 @@ __device__ __forceinline__ Called resolve_position(const TileView<M>& tv, const 
 // its reads and looks up their fixed-point likelihood gaps, a __shfl_xor butterfly sums the four
 // per-base gap sums and counts over the group, and the group leader applies the dominant-winner
 // proof (host_tables.cpp).  Whatever the proof cannot decide runs the literal f64 algorithm.
-template <class M>
-__device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, const Stage& st,
-                                       const TileView<M>& tv, const uint32_t* wqueue, uint32_t qn,
-                                       uint32_t lane, LocalStats& ls) {
-  // group width (warp-uniform): 8 lanes per position when the planner saw no unit deeper than 8
-  // reads in this tile, else look at the queued units
-  uint32_t G = 8u;
-  if (!(st.tile.flags & kTileFlagShallow)) {
-    uint32_t nmax = 0;
-    for (uint32_t e = lane; e < qn; e += 32) {
-      uint32_t u = wqueue[e] >> 16;
-      uint32_t n = st.units[u + 1].read_begin - st.units[u].read_begin;
-      nmax = n > nmax ? n : nmax;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, nmax, off);
-      nmax = o > nmax ? o : nmax;
-    }
-    G = nmax <= 8u ? 8u : 32u;
-  }
-  const uint32_t per_pass = 32u / G;
+template <class M, uint32_t G>
+__device__ __forceinline__ void slow_pass_g(const VoteArgs& a, const VoteSmem& S, const Stage& st,
+                                            const TileView<M>& tv, const uint32_t* wqueue, uint32_t qn,
+                                            uint32_t lane, LocalStats& ls) {
+  constexpr uint32_t per_pass = 32u / G;
+  constexpr uint32_t gshift = G == 8u ? 3u : 5u;
   const uint32_t sub = lane & (G - 1u);
   for (uint32_t e0 = 0; e0 < qn; e0 += per_pass) {
-    const uint32_t e = e0 + lane / G;
+    const uint32_t e = e0 + (lane >> gshift);
     const bool valid = e < qn;
     uint32_t u = 0, pos = 0, rb = 0, n = 0;
     uint64_t out_off = 0;
@@ -438,9 +423,10 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
         if (pos < len) {
           typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + pos;
           uint32_t b = M::ld8(tv.bases + row);
-          uint32_t idx = base_to_index(b);
-          if (b != 'N' && idx < 4u) {
-            uint32_t q = M::ld8(tv.quals + row);
+          uint32_t q = M::ld8(tv.quals + row);
+          if (is_acgt_upper(b & 0xDFu)) {       // A,C,G,T in either case; 'N' and the rest are skipped
+            const uint32_t x = (b >> 1) & 3u;   // A 0, C 1, T 2, G 3
+            const uint32_t idx = x ^ (x >> 1);  // A 0, C 1, G 2, T 3
             q = q > FGB_MAX_PHRED ? FGB_MAX_PHRED : q;
             int32_t dq = S.dfix[q];
             if (dq == INT32_MIN) { c23 |= 0x80000000u; dq = 0; }
@@ -453,6 +439,7 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
       }
     }
     // butterfly over the group (n <= nmax2 <= 1024 keeps every 16-bit count and the flag intact)
+#pragma unroll
     for (uint32_t off = G >> 1; off > 0; off >>= 1) {
       s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, off);
       s1 += __shfl_xor_sync(0xFFFFFFFFu, s1, off);
@@ -499,6 +486,31 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
   }
 }
 
+// Group width (warp-uniform): 8 lanes per position when no queued pileup is deeper than 8 reads
+// (the planner's shallow-tile hint answers that without looking), else the whole warp.
+template <class M>
+__device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, const Stage& st,
+                                          const TileView<M>& tv, const uint32_t* wqueue, uint32_t qn,
+                                          uint32_t lane, LocalStats& ls) {
+  bool shallow = (st.tile.flags & kTileFlagShallow) != 0;
+  if (!shallow) {
+    uint32_t nmax = 0;
+    for (uint32_t e = lane; e < qn; e += 32) {
+      uint32_t u = wqueue[e] >> 16;
+      uint32_t n = st.units[u + 1].read_begin - st.units[u].read_begin;
+      nmax = n > nmax ? n : nmax;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, nmax, off);
+      nmax = o > nmax ? o : nmax;
+    }
+    shallow = nmax <= 8u;
+  }
+  if (shallow) slow_pass_g<M, 8u>(a, S, st, tv, wqueue, qn, lane, ls);
+  else slow_pass_g<M, 32u>(a, S, st, tv, wqueue, qn, lane, ls);
+}
+
 // Votes this warp's share of one tile.  Called by the eight consumer warps; `vt` is the thread's
 // rotating slot (0..kVoteThreads-1): it owns items vt, vt+256, ...  An item is 8 consecutive
 // positions of one unit: one 64-bit word of every read's base row and quality row.
@@ -509,11 +521,10 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
 template <class M, bool Regular>
 __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const Stage& st,
                                           const TileView<M>& tv, uint32_t vt, uint32_t warp,
-                                          LocalStats& ls) {
+                                          uint32_t n_items, LocalStats& ls) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_units = st.tile.n_units;
   const uint64_t out0 = st.units[0].out_off;
-  const uint32_t n_items = static_cast<uint32_t>((st.units[n_units].out_off - out0) >> 3);
   const uint32_t min_reads = a.min_reads, min_cons_q = a.min_cons_q, fast_qual = a.fast_qual;
   // regular-tile constants
   const uint32_t reg_len = st.units[0].cons_len;
@@ -525,7 +536,7 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
   const uint32_t fq4 = (fast_masked ? 2u : fast_qual) * 0x01010101u;
   // planner hint: every unit of the tile has the same number of items
   const uint32_t uni_m = st.tile.flags >> 8;
-  const uint32_t uni_recip = uni_m ? (0xFFFFFFFFu / uni_m + 1u) : 0u;
+  const uint32_t uni_recip = st.aux[0];
   const uint32_t base32 = static_cast<uint32_t>(tv.byte_base);
   uint32_t* const wqueue = S.queue[warp];
   uint32_t* const wcount = &S.q_count[warp];
@@ -748,13 +759,15 @@ __global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
   }
   __syncthreads();
 
-  const uint64_t grid = gridDim.x;
+  const uint32_t grid = gridDim.x;
+  const uint32_t n_tiles = static_cast<uint32_t>(a.n_tiles);   // < 2^32: fgb_plan_tiles bounds n_units
 
   if (warp == kConsumerWarps) {
     // ================= PRODUCER WARP: one elected lane drives the TMA pipeline =================
     if ((tid & 31u) == 0) {
       uint32_t k = 0;
-      for (uint64_t t = blockIdx.x; t < a.n_tiles; t += grid, ++k) {
+      uint64_t n_units_done = 0, n_reads_done = 0;
+      for (uint32_t t = blockIdx.x; t < n_tiles; t += grid, ++k) {
         const int s = k % kStages;
         const uint32_t use = k / kStages;
         if (use > 0) {                                          // consumers released the stage
@@ -773,6 +786,10 @@ __global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
         uint32_t rskew = read_begin & 1u;
         uint32_t rbytes = ((n_reads + rskew + 1u) & ~1u) * 8u;
         uint32_t tx = units_bytes + (direct ? 0u : 2u * byte_len + rbytes);
+        const uint32_t uni_m = flags >> 8;     // per-tile constants every consumer lane would otherwise derive
+        st.aux[0] = uni_m ? 0xFFFFFFFFu / uni_m + 1u : 0u;
+        st.aux[1] = uni_m * n_units;
+        n_units_done += n_units; n_reads_done += n_reads;
         mbar_arrive_expect_tx(&S.full[s], tx);
         tma_load_1d(st.units, a.units + unit_begin, units_bytes, &S.full[s]);
         if (!direct) {
@@ -783,38 +800,39 @@ __global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
           if (rbytes) tma_load_1d(st.reads, a.reads + (read_begin - rskew), rbytes, &S.full[s]);
         }
       }
+      if (n_units_done) atomicAdd(a.counters + FGB_CTR_UNITS, static_cast<unsigned long long>(n_units_done));
+      if (n_reads_done) atomicAdd(a.counters + FGB_CTR_INPUT_READS, static_cast<unsigned long long>(n_reads_done));
     }
     return;
   }
 
   // ================= CONSUMER WARPS =================
   LocalStats ls = {0, 0, 0};
-  uint64_t n_units_done = 0, n_reads_done = 0;
   uint32_t k = 0, rot = 0;
-  for (uint64_t t = blockIdx.x; t < a.n_tiles; t += grid, ++k) {
+  for (uint32_t t = blockIdx.x; t < n_tiles; t += grid, ++k) {
     const int s = k % kStages;
     mbar_wait(&S.full[s], (k / kStages) & 1u, 2000u);
     Stage& st = S.st[s];
     // rotating item assignment: the partial last round of a tile lands on different warps from
     // tile to tile, so every warp does the same work in the long run
     const uint32_t vt = (tid - rot) & (kVoteThreads - 1);
-    const uint32_t n_items =
-        static_cast<uint32_t>((st.units[st.tile.n_units].out_off - st.units[0].out_off) >> 3);
+    uint32_t n_items = st.aux[1];
+    if (n_items == 0)
+      n_items = static_cast<uint32_t>((st.units[st.tile.n_units].out_off - st.units[0].out_off) >> 3);
     if (st.tile.flags & kTileFlagDirect) {
       TileView<GlMem> tv;
       tv.bases = a.bases; tv.quals = a.quals;
       tv.reads = reinterpret_cast<const uint8_t*>(a.reads + st.tile.read_begin);
       tv.byte_base = 0; tv.read_base = st.tile.read_begin;
-      vote_tile<GlMem, false>(a, S, st, tv, vt, warp, ls);
+      vote_tile<GlMem, false>(a, S, st, tv, vt, warp, n_items, ls);
     } else {
       TileView<ShMem> tv;
       tv.bases = st.bases; tv.quals = st.quals;
       tv.reads = reinterpret_cast<const uint8_t*>(st.reads) + (st.tile.read_begin & 1u) * 8u;
       tv.byte_base = st.tile.byte_begin; tv.read_base = st.tile.read_begin;
-      if (st.tile.flags & kTileFlagRegular) vote_tile<ShMem, true>(a, S, st, tv, vt, warp, ls);
-      else vote_tile<ShMem, false>(a, S, st, tv, vt, warp, ls);
+      if (st.tile.flags & kTileFlagRegular) vote_tile<ShMem, true>(a, S, st, tv, vt, warp, n_items, ls);
+      else vote_tile<ShMem, false>(a, S, st, tv, vt, warp, n_items, ls);
     }
-    if (tid == 0) { n_units_done += st.tile.n_units; n_reads_done += st.tile.n_reads; }
     rot = (rot + n_items) & (kVoteThreads - 1);
     __syncwarp();
     if ((tid & 31u) == 0) mbar_arrive(&S.empty[s]);   // this warp is done with stage s
@@ -832,10 +850,6 @@ __global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
     if (v0) atomicAdd(a.counters + FGB_CTR_POSITIONS, static_cast<unsigned long long>(v0));
     if (v1) atomicAdd(a.counters + FGB_CTR_EXACT_POSITIONS, static_cast<unsigned long long>(v1));
     if (v2) atomicAdd(a.counters + FGB_CTR_NOCALL_POSITIONS, static_cast<unsigned long long>(v2));
-  }
-  if (tid == 0) {
-    if (n_units_done) atomicAdd(a.counters + FGB_CTR_UNITS, static_cast<unsigned long long>(n_units_done));
-    if (n_reads_done) atomicAdd(a.counters + FGB_CTR_INPUT_READS, static_cast<unsigned long long>(n_reads_done));
   }
 }
 
