@@ -11,6 +11,7 @@ OUT = os.path.join(HERE, "libfgumi_b200.so")
 SOURCES = ["capi.cu", "host_tables.cpp", "host/caller_host.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-maxrregcount=112",      # vote_kernel: 2 CTAs x 288 threads x 112 regs = 64512 <= 65536 per SM
     "-fmad=false",            # no FMA contraction anywhere near the f64 vote (DESIGN.md numerics)
     "-Xcompiler", "-fPIC", "-shared",
 ]

@@ -733,7 +733,7 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
   if (lane == 0) *wcount = 0;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) vote_kernel(const VoteArgs a) {
+__global__ void __launch_bounds__(kThreads) vote_kernel(const VoteArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   VoteSmem& S = *reinterpret_cast<VoteSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x;
