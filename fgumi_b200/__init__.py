@@ -4,7 +4,7 @@ The product is libfgumi_b200.so (hand-written sm_100a CUDA behind the C-ABI in
 include/fgumi_b200.h).  This package is the thin host-side mirror of that boundary.
 """
 from .engine import (Engine, PackedBatch, HostColumns, DeviceBatch, DeviceColumns,  # noqa: F401
-                     VanillaUmiConsensusOptions, pack_source_reads, pack_uniform, plan_tiles,
+                     VanillaUmiConsensusOptions, pack_source_reads, pack_uniform, plan_tiles, pack8_encode,
                      consensus_length, UNIT_DTYPE, TILE_DTYPE, DUPLEX_JOB_DTYPE, CODEC_JOB_DTYPE)
 from . import lib  # noqa: F401
 from .caller import VanillaUmiConsensusCaller, DuplexConsensusCaller, CodecConsensusCaller, ConsensusOutput, apply_overlapping_consensus  # noqa: F401

@@ -15,6 +15,7 @@
 #include "combine_kernels.cuh"
 #include "fgb_config.h"
 #include "host_tables.h"
+#include "unpack_kernels.cuh"
 #include "vote_kernel.cuh"
 
 using namespace fgb;
@@ -35,6 +36,8 @@ struct Slot {
   cudaStream_t stream = nullptr;
   uint8_t* bases = nullptr;
   uint8_t* quals = nullptr;
+  uint8_t* packed = nullptr;     // PACK8 transfer column (fgb_submit_pack8)
+  uint64_t cap_packed = 0;
   uint64_t* reads = nullptr;
   fgb_unit* units = nullptr;
   fgb_tile* tiles = nullptr;
@@ -122,6 +125,8 @@ const char* fgb_strerror(fgb_status s) {
     case FGB_ERR_UNIT_TOO_LARGE: return "unit exceeds the supported size";
     case FGB_ERR_NOMEM: return "out of memory";
     case FGB_ERR_BUSY: return "a previous fgb_submit has not been waited on";
+    case FGB_ERR_MISSING_TAG: return "first record of the group has no UMI tag";
+    case FGB_ERR_NOT_ENCODABLE: return "observation outside the PACK8 alphabet";
     default: return "unknown status";
   }
 }
@@ -197,7 +202,7 @@ void fgb_destroy(fgb_handle* h) {
   for (int s = 0; s < kSlots; ++s) {
     Slot& sl = h->slots[s];
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
-    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.reads); cudaFree(sl.units);
+    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.reads); cudaFree(sl.units);
     cudaFree(sl.tiles); cudaFree(sl.out_base); cudaFree(sl.out_qual); cudaFree(sl.out_depth);
     cudaFree(sl.out_errors);
   }
@@ -373,11 +378,16 @@ fgb_status fgb_host_alloc(void** p, size_t bytes) {
 }
 void fgb_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out) {
+}  // extern "C"
+
+namespace {
+enum class HostFormat { kBytes, kPack8 };
+
+fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* out, HostFormat fmt) {
   if (!h || !in || !out) return FGB_ERR_INVALID_ARG;
   if (h->submit_pending) return FGB_ERR_BUSY;
   if (in->n_tiles == 0) return FGB_OK;
-  if (!in->tiles || !in->units || !in->reads || !in->bases || !in->quals || !out->base ||
+  if (!in->tiles || !in->units || !in->reads || !in->bases || (fmt == HostFormat::kBytes && !in->quals) || !out->base ||
       !out->qual || !out->depth || !out->errors)
     return FGB_ERR_INVALID_ARG;
   FGB_CUDA(h, cudaSetDevice(h->device));
@@ -432,8 +442,23 @@ fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out
     if ((st = ensure(h, &sl.out_errors, &c3, o1 - o0 + 4)) != FGB_OK) return st;
 
     cudaStream_t s = sl.stream;
-    FGB_CUDA(h, cudaMemcpyAsync(sl.bases, in->bases + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
-    FGB_CUDA(h, cudaMemcpyAsync(sl.quals, in->quals + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
+    if (fmt == HostFormat::kPack8) {
+      if ((st = ensure(h, &sl.packed, &sl.cap_packed, nbytes + 16)) != FGB_OK) return st;
+      FGB_CUDA(h, cudaMemcpyAsync(sl.packed, in->bases + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
+      const uint64_t n16 = (valid_bytes + 15u) >> 4;   // byte0 is 16-aligned; slack bytes are in the buffers
+      if (n16) {
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n16 + 255u) / 256u,
+                                                                       static_cast<uint64_t>(h->sm_count) * 16u));
+        unpack8_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(sl.packed),
+                                            reinterpret_cast<uint4*>(sl.bases),
+                                            reinterpret_cast<uint4*>(sl.quals), n16);
+        h->launches++;
+        FGB_CUDA(h, cudaGetLastError());
+      }
+    } else {
+      FGB_CUDA(h, cudaMemcpyAsync(sl.bases, in->bases + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
+      FGB_CUDA(h, cudaMemcpyAsync(sl.quals, in->quals + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
+    }
     FGB_CUDA(h, cudaMemcpyAsync(sl.reads, in->reads + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, s));
     FGB_CUDA(h, cudaMemcpyAsync(sl.units, in->units + u0, (u1 - u0 + 1) * sizeof(fgb_unit),
                                 cudaMemcpyHostToDevice, s));
@@ -464,6 +489,44 @@ fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out
     ++chunk;
   }
   return FGB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out) {
+  return submit_impl(h, in, out, HostFormat::kBytes);
+}
+
+fgb_status fgb_submit_pack8(fgb_handle* h, const fgb_batch* in, const fgb_columns* out) {
+  return submit_impl(h, in, out, HostFormat::kPack8);
+}
+
+fgb_status fgb_pack8_encode(const uint8_t* bases, const uint8_t* quals, uint64_t n, uint8_t* out) {
+  if (n && (!bases || !quals || !out)) return FGB_ERR_INVALID_ARG;
+  static const uint8_t kCode[256] = {   // 0..3 = A,C,G,T; 4 = N; 5 = padding (0); 255 = not encodable
+#define X 255
+      5, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, 0, X, 1, X, X, X, 2, X, X, X, X, X, X, 4, X, X, X, X, X, 3, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X,
+      X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X, X
+#undef X
+  };
+  uint32_t bad = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint32_t c = kCode[bases[i]], q = quals[i];
+    uint32_t v;
+    if (c < 4u) { v = (c << 6) | q; bad |= q > 61u; }
+    else if (c == 4u) { v = 0x3Eu; bad |= q != 2u; }
+    else if (c == 5u) { v = 0u; bad |= q != 0u; }
+    else { v = 0u; bad = 1u; }
+    out[i] = static_cast<uint8_t>(v);
+  }
+  return bad ? FGB_ERR_NOT_ENCODABLE : FGB_OK;
 }
 
 fgb_status fgb_wait(fgb_handle* h) {

@@ -135,6 +135,20 @@ def pack_uniform(bases: np.ndarray, quals: np.ndarray, min_reads: int = 1) -> Pa
     return PackedBatch(fb, fq, reads, uarr, U, n_reads, n_bytes, U * Lo)
 
 
+def pack8_encode(bases: np.ndarray, quals: np.ndarray) -> Optional[np.ndarray]:
+    """fgb_pack8_encode over a (bases, quals) column pair; None when the batch is not encodable
+    (IUPAC / lower-case bases, N with a quality other than 2, quality above 61)."""
+    lib = _l.load()
+    n = int(bases.size)
+    out = np.empty(n, dtype=np.uint8)
+    st = lib.fgb_pack8_encode(bases.ctypes.data, quals.ctypes.data, n, out.ctypes.data)
+    if st == _l.FGB_ERR_NOT_ENCODABLE:
+        return None
+    if st != _l.FGB_OK:
+        raise _l.FgbError(st, "fgb_pack8_encode")
+    return out
+
+
 def plan_tiles(batch: PackedBatch) -> np.ndarray:
     """fgb_plan_tiles: greedy segmentation of the batch into shared-memory tiles."""
     lib = _l.load()
@@ -277,6 +291,19 @@ class Engine:
         c = _l.FgbColumns(out.base.ctypes.data, out.qual.ctypes.data, out.depth.ctypes.data,
                           out.errors.ctypes.data)
         self._check(self._lib.fgb_submit(self._h, C.byref(b), C.byref(c)), "fgb_submit")
+
+    def submit_pack8(self, batch: PackedBatch, packed: np.ndarray, out: HostColumns):
+        """fgb_submit_pack8: `packed` is the one-byte-per-observation column of `batch`
+        (see pack8_encode); half the host->device bytes of submit()."""
+        if batch.tiles is None:
+            plan_tiles(batch)
+        self._keep = (batch, packed, out)
+        b = _l.FgbBatch(batch.n_units, batch.n_reads, batch.n_bytes, batch.n_out, len(batch.tiles),
+                        packed.ctypes.data, None, batch.reads.ctypes.data,
+                        batch.units.ctypes.data, batch.tiles.ctypes.data)
+        c = _l.FgbColumns(out.base.ctypes.data, out.qual.ctypes.data, out.depth.ctypes.data,
+                          out.errors.ctypes.data)
+        self._check(self._lib.fgb_submit_pack8(self._h, C.byref(b), C.byref(c)), "fgb_submit_pack8")
 
     def wait(self):
         self._check(self._lib.fgb_wait(self._h), "fgb_wait")

@@ -20,6 +20,7 @@ FGB_ERR_UNIT_TOO_LARGE = 5
 FGB_ERR_NOMEM = 6
 FGB_ERR_BUSY = 7
 FGB_ERR_MISSING_TAG = 8
+FGB_ERR_NOT_ENCODABLE = 9
 
 FGB_READ_ALIGN = 8
 FGB_OUT_ALIGN = 8
@@ -147,7 +148,8 @@ SYMBOLS = (
     "fgb_host_free", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
-    "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group",
+    "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
+    "fgb_submit_pack8",
 )
 
 _lib = None
@@ -242,5 +244,9 @@ def load() -> C.CDLL:
     lib.fgb_caller_stats.restype = C.c_int32
     lib.fgb_overlap_apply_group.argtypes = [vp, vp, C.c_uint32, C.c_uint8, C.c_uint8, vp]
     lib.fgb_overlap_apply_group.restype = C.c_int32
+    lib.fgb_pack8_encode.argtypes = [vp, vp, u64, vp]
+    lib.fgb_pack8_encode.restype = C.c_int32
+    lib.fgb_submit_pack8.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns)]
+    lib.fgb_submit_pack8.restype = C.c_int32
     _lib = lib
     return lib

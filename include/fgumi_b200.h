@@ -62,7 +62,8 @@ enum {
   FGB_ERR_UNIT_TOO_LARGE = 5,/* a single unit exceeds fgb_tile_capacity_bytes()               */
   FGB_ERR_NOMEM = 6,
   FGB_ERR_BUSY = 7,          /* fgb_submit while a previous submit has not been waited on     */
-  FGB_ERR_MISSING_TAG = 8    /* first record of a group lacks the UMI tag (vanilla_caller.rs:1493) */
+  FGB_ERR_MISSING_TAG = 8,   /* first record of a group lacks the UMI tag (vanilla_caller.rs:1493) */
+  FGB_ERR_NOT_ENCODABLE = 9  /* fgb_pack8_encode: an observation outside the PACK8 alphabet     */
 };
 
 typedef struct fgb_handle fgb_handle;   /* one per GPU; thread-compatible, not thread-safe    */
@@ -191,6 +192,20 @@ fgb_status fgb_vote_device(fgb_handle* h, const fgb_batch* in, const fgb_columns
  * columns are complete.  The caller owns all host buffers and must keep them alive until
  * fgb_wait() returns. */
 fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out);
+
+/* ---- compact transfer formats (the PCIe link bounds end-to-end throughput) ------------------
+ * PACK8: ONE byte per observation of a prepared SourceRead row instead of a base byte and a quality
+ * byte: bits 7..6 = A,C,G,T (0..3), bits 5..0 = quality 0..61; 0x3E = (N, Q2), the masked base of
+ * create_source_read (vanilla_caller.rs:908-916).  Row offsets and lengths are those of the
+ * two-column layout, so units/reads/tiles are unchanged.  fgb_pack8_encode converts n bytes of a
+ * (bases, quals) column pair; FGB_ERR_NOT_ENCODABLE (nothing useful in `out`) when a row holds a
+ * lower-case or IUPAC base, an N whose quality is not 2, or a quality above 61 -- such batches go
+ * through fgb_submit.  Row padding bytes (base 0, quality 0) are accepted and encode as 0x00. */
+fgb_status fgb_pack8_encode(const uint8_t* bases, const uint8_t* quals, uint64_t n, uint8_t* out);
+/* fgb_submit with `in->bases` holding the PACK8 column (in->quals is ignored): the column is
+ * copied host->device and expanded to the two byte columns by an unpack kernel in front of the
+ * vote.  Same chunking, ordering and completion rules as fgb_submit. */
+fgb_status fgb_submit_pack8(fgb_handle* h, const fgb_batch* in, const fgb_columns* out);
 fgb_status fgb_wait(fgb_handle* h);
 
 /* Pinned host allocation helpers (cudaHostAlloc / cudaFreeHost). */

@@ -192,3 +192,14 @@ def test_consensus_length_rule(fg):
     assert fg.consensus_length([10, 8, 6], 1) == 10
     assert fg.consensus_length([6, 10, 8], 2) == 8
     assert fg.consensus_length([6, 10, 8], 3) == 6
+
+
+def test_pack8_encode_alphabet(fg):
+    """PACK8 host encoder: A,C,G,T with q <= 61, (N, 2) and zero padding encode; anything else is
+    reported as not encodable."""
+    b = np.frombuffer(b"ACGTN\0", np.uint8).copy()
+    q = np.array([0, 61, 30, 7, 2, 0], np.uint8)
+    p = fg.pack8_encode(b, q)
+    assert p.tolist() == [0, (1 << 6) | 61, (2 << 6) | 30, (3 << 6) | 7, 0x3E, 0]
+    for bad_b, bad_q in ((b"a", 30), (b"R", 30), (b"N", 10), (b"A", 62), (b"\0", 1)):
+        assert fg.pack8_encode(np.frombuffer(bad_b, np.uint8).copy(), np.array([bad_q], np.uint8)) is None

@@ -198,3 +198,37 @@ def test_multi_chunk_submit(fg):
     quals = np.tile(quals, (reps, 1, 1))
     st = check(fg, fg.pack_uniform(bases, quals, 1), threads=8)
     assert st["units"] == 4000 * reps
+
+
+def test_pack8_submit_matches_byte_submit(fg):
+    """PACK8 transfer format: same results as the two-column submit, half the H2D bytes."""
+    rng = np.random.default_rng(88)
+    units = []
+    for _ in range(3000):
+        depth = int(rng.integers(1, 12))
+        L = int(rng.integers(5, 200))
+        rows = []
+        for _ in range(depth):
+            ln = int(rng.integers(max(1, L - 20), L + 1))
+            b = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=ln)
+            q = rng.integers(0, 62, size=ln).astype(np.uint8)
+            m = rng.random(ln) < 0.05
+            b[m] = ord("N"); q[m] = 2
+            rows.append((b.tobytes(), q.tobytes()))
+        units.append(rows)
+    batch = fg.pack_source_reads(units, 1)
+    packed = fg.pack8_encode(batch.bases, batch.quals)
+    assert packed is not None and packed.size == batch.bases.size
+    eng = fg.Engine(0, 45, 40, 1, 2)
+    want = eng.vote(batch)
+    got = fg.HostColumns.alloc(batch.n_out)
+    eng.submit_pack8(batch, packed, got)
+    eng.wait()
+    eng.close()
+    for sl in batch.unit_slices():
+        assert np.array_equal(got.base[sl], want.base[sl]) and np.array_equal(got.qual[sl], want.qual[sl])
+        assert np.array_equal(got.depth[sl], want.depth[sl]) and np.array_equal(got.errors[sl], want.errors[sl])
+    # and against the oracle directly
+    ob, oq, od, oe, _ = O.simplex_batch(batch, 45, 40, 1, 2)
+    for sl in batch.unit_slices():
+        assert np.array_equal(got.base[sl], ob[sl]) and np.array_equal(got.qual[sl], oq[sl])
