@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -29,8 +30,8 @@ static_assert(offsetof(Stage, quals) % 16 == 0 && offsetof(Stage, reads) % 16 ==
 
 namespace {
 
-constexpr int kSlots = 2;                        // chunk pipeline depth of fgb_submit
-constexpr uint64_t kChunkColumnBytes = 96ull << 20;  // per-column bytes per chunk
+constexpr int kSlots = 4;                        // max chunk pipeline depth of fgb_submit
+constexpr uint64_t kChunkColumnBytes = 96ull << 20;  // default per-column bytes per chunk
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -61,6 +62,8 @@ struct fgb_handle {
   std::string last_error;
   Slot slots[kSlots];
   bool submit_pending = false;
+  int n_slots = 2;                                  // FGB_SUBMIT_SLOTS (1..kSlots)
+  uint64_t chunk_bytes = kChunkColumnBytes;         // FGB_SUBMIT_CHUNK_MB
 };
 
 namespace {
@@ -159,6 +162,9 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   if (!h) return FGB_ERR_NOMEM;
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  if (const char* e = std::getenv("FGB_SUBMIT_SLOTS")) h->n_slots = std::max(1, std::min(kSlots, std::atoi(e)));
+  if (const char* e = std::getenv("FGB_SUBMIT_CHUNK_MB"))
+    h->chunk_bytes = static_cast<uint64_t>(std::max(1, std::atoi(e))) << 20;
   h->params = *params;
   build_host_tables(params->error_rate_pre_umi, params->error_rate_post_umi, &h->host_tables);
 
@@ -413,7 +419,7 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
         end = tl.byte_begin + tl.byte_len;
       }
       end = std::max(end, byte1);
-      if (t1 > t0 && end - byte0 > kChunkColumnBytes) break;
+      if (t1 > t0 && end - byte0 > h->chunk_bytes) break;
       byte1 = end;
       ++t1;
     }
@@ -426,7 +432,7 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
     const uint64_t nbytes = byte1 - byte0;
     const uint64_t valid_bytes = std::min(byte1, in->n_bytes) - std::min(byte0, in->n_bytes);
 
-    Slot& sl = h->slots[chunk % kSlots];
+    Slot& sl = h->slots[chunk % h->n_slots];
     // In-stream order makes slot reuse safe: chunk c+kSlots queues behind chunk c's D2H.
     fgb_status st;
     uint64_t cap2 = sl.cap_bytes;
