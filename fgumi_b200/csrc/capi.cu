@@ -39,6 +39,10 @@ struct Slot {
   uint8_t* quals = nullptr;
   uint8_t* packed = nullptr;     // PACK8 transfer column (fgb_submit_pack8)
   uint64_t cap_packed = 0;
+  uint8_t* seq4 = nullptr;       // BAM4 transfer columns (fgb_submit_bam4)
+  uint8_t* qraw = nullptr;
+  fgb_raw_read* rawreads = nullptr;
+  uint64_t cap_seq4 = 0, cap_qraw = 0, cap_rawreads = 0;
   uint64_t* reads = nullptr;
   fgb_unit* units = nullptr;
   fgb_tile* tiles = nullptr;
@@ -208,7 +212,7 @@ void fgb_destroy(fgb_handle* h) {
   for (int s = 0; s < kSlots; ++s) {
     Slot& sl = h->slots[s];
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
-    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.reads); cudaFree(sl.units);
+    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.seq4); cudaFree(sl.qraw); cudaFree(sl.rawreads); cudaFree(sl.reads); cudaFree(sl.units);
     cudaFree(sl.tiles); cudaFree(sl.out_base); cudaFree(sl.out_qual); cudaFree(sl.out_depth);
     cudaFree(sl.out_errors);
   }
@@ -387,13 +391,46 @@ void fgb_host_free(void* p) { if (p) cudaFreeHost(p); }
 }  // extern "C"
 
 namespace {
-enum class HostFormat { kBytes, kPack8 };
+enum class HostFormat { kBytes, kPack8, kBam4 };
 
-fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* out, HostFormat fmt) {
+fgb_status launch_unpack_bam4(fgb_handle* h, const Bam4Args& a, cudaStream_t s) {
+  const uint64_t n = a.read_end - a.read_begin;
+  if (n == 0) return FGB_OK;
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + 7u) / 8u, static_cast<uint64_t>(h->sm_count) * 16u));
+  unpack_bam4_kernel<<<grid, 256, 0, s>>>(a);
+  h->launches++;
+  FGB_CUDA(h, cudaGetLastError());
+  return FGB_OK;
+}
+
+// Layout rules of fgb_raw_columns (checked once per submit, O(reads)).
+fgb_status check_raw(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw) {
+  if (!raw || !raw->seq4 || !raw->quals_raw || !raw->raw_reads) return FGB_ERR_INVALID_ARG;
+  uint64_t prev_end = 0;
+  for (uint64_t r = 0; r < in->n_reads; ++r) {
+    const fgb_raw_read& rr = raw->raw_reads[r];
+    if ((rr.src_off & 1u) || rr.src_off < prev_end || rr.src_off + rr.raw_len > raw->n_raw ||
+        FGB_READ_LEN(in->reads[r]) > rr.raw_len) {
+      h->last_error = "fgb_raw_columns: raw spans must be even-aligned, ascending, inside the columns and at least as long as their rows";
+      return FGB_ERR_LAYOUT;
+    }
+    prev_end = rr.src_off + rr.raw_len;
+  }
+  return FGB_OK;
+}
+
+fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* out, HostFormat fmt,
+                       const fgb_raw_columns* raw = nullptr) {
   if (!h || !in || !out) return FGB_ERR_INVALID_ARG;
   if (h->submit_pending) return FGB_ERR_BUSY;
   if (in->n_tiles == 0) return FGB_OK;
-  if (!in->tiles || !in->units || !in->reads || !in->bases || (fmt == HostFormat::kBytes && !in->quals) || !out->base ||
+  if (fmt == HostFormat::kBam4) {
+    if (!in->reads) return FGB_ERR_INVALID_ARG;
+    fgb_status rs = check_raw(h, in, raw);
+    if (rs != FGB_OK) return rs;
+  }
+  if (!in->tiles || !in->units || !in->reads || (fmt != HostFormat::kBam4 && !in->bases) ||
+      (fmt == HostFormat::kBytes && !in->quals) || !out->base ||
       !out->qual || !out->depth || !out->errors)
     return FGB_ERR_INVALID_ARG;
   FGB_CUDA(h, cudaSetDevice(h->device));
@@ -461,6 +498,22 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
         h->launches++;
         FGB_CUDA(h, cudaGetLastError());
       }
+    } else if (fmt == HostFormat::kBam4) {
+      // raw span of this chunk's reads (ascending by construction), origin aligned down to 32 bases
+      const uint64_t rf = first.read_begin, rl = r1;           // absolute read range [rf, rl)
+      if (rl > rf) {
+        const uint64_t a0 = raw->raw_reads[rf].src_off & ~31ull;
+        const uint64_t a1 = raw->raw_reads[rl - 1].src_off + raw->raw_reads[rl - 1].raw_len;
+        const uint64_t nraw = a1 - a0;
+        if ((st = ensure(h, &sl.seq4, &sl.cap_seq4, nraw / 2 + 16)) != FGB_OK) return st;
+        if ((st = ensure(h, &sl.qraw, &sl.cap_qraw, nraw + 16)) != FGB_OK) return st;
+        if ((st = ensure(h, &sl.rawreads, &sl.cap_rawreads, rl - rf + 1)) != FGB_OK) return st;
+        FGB_CUDA(h, cudaMemcpyAsync(sl.seq4, raw->seq4 + a0 / 2, (nraw + 1) / 2, cudaMemcpyHostToDevice, s));
+        FGB_CUDA(h, cudaMemcpyAsync(sl.qraw, raw->quals_raw + a0, nraw, cudaMemcpyHostToDevice, s));
+        FGB_CUDA(h, cudaMemcpyAsync(sl.rawreads, raw->raw_reads + rf, (rl - rf) * sizeof(fgb_raw_read),
+                                    cudaMemcpyHostToDevice, s));
+      }
+      // (the layout descriptors are uploaded below; the unpack launch follows them)
     } else {
       FGB_CUDA(h, cudaMemcpyAsync(sl.bases, in->bases + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
       FGB_CUDA(h, cudaMemcpyAsync(sl.quals, in->quals + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
@@ -485,6 +538,20 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
     dc.qual = sl.out_qual - o0;
     dc.depth = sl.out_depth - o0;
     dc.errors = sl.out_errors - o0;
+    if (fmt == HostFormat::kBam4 && r1 > first.read_begin) {
+      const uint64_t rf = first.read_begin;
+      const uint64_t a0 = raw->raw_reads[rf].src_off & ~31ull;
+      Bam4Args ua;
+      ua.seq4 = sl.seq4 - a0 / 2;
+      ua.quals_raw = sl.qraw - a0;
+      ua.raw_reads = sl.rawreads - rf;
+      ua.reads = db.reads;
+      ua.bases = const_cast<uint8_t*>(db.bases);
+      ua.quals = const_cast<uint8_t*>(db.quals);
+      ua.read_begin = rf; ua.read_end = r1;
+      ua.min_q = raw->min_input_base_quality;
+      if ((st = launch_unpack_bam4(h, ua, s)) != FGB_OK) return st;
+    }
     if ((st = launch_vote(h, db, dc, s)) != FGB_OK) return st;
     const uint64_t no = o1 - o0;
     FGB_CUDA(h, cudaMemcpyAsync(out->base + o0, sl.out_base, no, cudaMemcpyDeviceToHost, s));
@@ -506,6 +573,25 @@ fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out
 
 fgb_status fgb_submit_pack8(fgb_handle* h, const fgb_batch* in, const fgb_columns* out) {
   return submit_impl(h, in, out, HostFormat::kPack8);
+}
+
+fgb_status fgb_submit_bam4(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,
+                           const fgb_columns* out) {
+  return submit_impl(h, in, out, HostFormat::kBam4, raw);
+}
+
+fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,
+                                  uint8_t* bases, uint8_t* quals, void* stream) {
+  if (!h || !in || !raw || !bases || !quals || !in->reads || !raw->seq4 || !raw->quals_raw ||
+      !raw->raw_reads)
+    return FGB_ERR_INVALID_ARG;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  Bam4Args ua;
+  ua.seq4 = raw->seq4; ua.quals_raw = raw->quals_raw; ua.raw_reads = raw->raw_reads;
+  ua.reads = in->reads; ua.bases = bases; ua.quals = quals;
+  ua.read_begin = 0; ua.read_end = in->n_reads;
+  ua.min_q = raw->min_input_base_quality;
+  return launch_unpack_bam4(h, ua, static_cast<cudaStream_t>(stream));
 }
 
 fgb_status fgb_pack8_encode(const uint8_t* bases, const uint8_t* quals, uint64_t n, uint8_t* out) {

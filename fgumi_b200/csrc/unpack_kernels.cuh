@@ -47,3 +47,63 @@ __global__ void __launch_bounds__(256) unpack8_kernel(const uint4* __restrict__ 
 }
 
 }  // namespace fgb
+
+namespace fgb {
+
+struct Bam4Args {
+  const uint8_t* seq4;          // biased: nibble i of the batch lives in seq4[i >> 1] (high nibble first)
+  const uint8_t* quals_raw;     // biased: quals_raw[i]
+  const fgb_raw_read* raw_reads;   // biased: raw_reads[r] for absolute read index r
+  const uint64_t* reads;        // layout descriptors (off << 16 | final_len), biased the same way
+  uint8_t* bases;               // byte columns being built (biased by the chunk origin)
+  uint8_t* quals;
+  uint64_t read_begin, read_end;   // absolute read range of this launch
+  uint32_t min_q;               // min_input_base_quality (0 = no masking)
+};
+
+// One warp per read, lanes over the row's 64-bit words.  Output position p of the row comes from
+// raw base p (forward strand) or raw_len-1-p complemented (reverse strand) of the kept raw span
+// (vanilla_caller.rs:893-898); q < min_q turns the observation into (N, Q2) (:908-916).
+__global__ void __launch_bounds__(256) unpack_bam4_kernel(const Bam4Args a) {
+  // "=ACMGRSVTWYHKDBN" and its complement (A<->T, C<->G, everything else unchanged; fgumi-dna dna.rs:30-60)
+  __shared__ uint8_t lut[32];
+  if (threadIdx.x < 32) {
+    const char* f = "=ACMGRSVTWYHKDBN";
+    const char* c = "=TGMCRSVAWYHKDBN";
+    lut[threadIdx.x] = static_cast<uint8_t>(threadIdx.x < 16 ? f[threadIdx.x] : c[threadIdx.x - 16]);
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t r = a.read_begin + ((static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+       r < a.read_end; r += warps) {
+    const fgb_raw_read rr = a.raw_reads[r];
+    const uint64_t d = a.reads[r];
+    const uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
+    const uint64_t off = d >> 16;
+    const bool rev = rr.flags & 1u;
+    const uint8_t* tab = lut + (rev ? 16 : 0);
+    const uint32_t words = (len + 7u) >> 3;
+    for (uint32_t w = lane; w < words; w += 32u) {
+      uint64_t wb = 0, wq = 0;
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) {
+        const uint32_t p = w * 8u + j;
+        if (p < len) {
+          const uint64_t i = rr.src_off + (rev ? rr.raw_len - 1u - p : p);
+          const uint32_t byte = __ldg(a.seq4 + (i >> 1));
+          const uint32_t nib = (i & 1u) ? (byte & 15u) : (byte >> 4);
+          uint32_t b = tab[nib];
+          uint32_t q = __ldg(a.quals_raw + i);
+          if (q < a.min_q) { b = 'N'; q = 2u; }
+          wb |= static_cast<uint64_t>(b) << (8u * j);
+          wq |= static_cast<uint64_t>(q) << (8u * j);
+        }
+      }
+      *reinterpret_cast<uint64_t*>(a.bases + off + w * 8u) = wb;
+      *reinterpret_cast<uint64_t*>(a.quals + off + w * 8u) = wq;
+    }
+  }
+}
+
+}  // namespace fgb

@@ -135,6 +135,63 @@ def pack_uniform(bases: np.ndarray, quals: np.ndarray, min_reads: int = 1) -> Pa
     return PackedBatch(fb, fq, reads, uarr, U, n_reads, n_bytes, U * Lo)
 
 
+RAW_READ_DTYPE = np.dtype([("src_off", "<u8"), ("raw_len", "<u4"), ("flags", "<u4")])
+assert RAW_READ_DTYPE.itemsize == 16
+_NIBBLE = np.full(256, 15, dtype=np.uint8)
+for _i, _c in enumerate(b"=ACMGRSVTWYHKDBN"):
+    _NIBBLE[_c] = _i
+    _NIBBLE[ord(chr(_c).lower())] = _i
+
+
+@dataclass
+class RawColumns:
+    """fgb_raw_columns: the records' 4-bit sequence + raw qualities, and one fgb_raw_read per row."""
+    seq4: np.ndarray
+    quals_raw: np.ndarray
+    raw_reads: np.ndarray
+    n_raw: int
+    min_input_base_quality: int
+
+    def struct(self) -> "_l.FgbRawColumns":
+        return _l.FgbRawColumns(self.n_raw, self.seq4.ctypes.data, self.quals_raw.ctypes.data,
+                                self.raw_reads.ctypes.data, self.min_input_base_quality)
+
+
+def pack_raw_reads(units, min_reads: int, min_input_base_quality: int):
+    """units: [[(seq ASCII bytes, raw quals bytes, reverse: bool, row_len: int), ...], ...] where
+    (seq, quals) is the KEPT raw span of the record and row_len the SourceRead length the host
+    computed (vanilla_caller.rs:899-927).  Returns (layout PackedBatch without columns, RawColumns)."""
+    lens = [[r[3] for r in u] for u in units]
+    layout = pack_source_reads([[(b"\0" * n, b"\0" * n) for n in ul] for ul in lens], min_reads)
+    layout.bases = None
+    layout.quals = None
+    R = layout.n_reads
+    rr = np.zeros(R + 1, dtype=RAW_READ_DTYPE)
+    seqs, quals = [], []
+    off = 0
+    k = 0
+    for u in units:
+        for seq, q, rev, _ in u:
+            n = len(seq)
+            assert len(q) == n
+            rr[k] = (off, n, 1 if rev else 0)
+            pad = (-n) % 8                       # spans start on even (here 8-aligned) indices
+            seqs.append(np.frombuffer(seq, np.uint8)); quals.append(np.frombuffer(q, np.uint8))
+            if pad:
+                seqs.append(np.zeros(pad, np.uint8)); quals.append(np.zeros(pad, np.uint8))
+            off += n + pad
+            k += 1
+    allseq = np.concatenate(seqs) if seqs else np.zeros(0, np.uint8)
+    allq = np.concatenate(quals) if quals else np.zeros(0, np.uint8)
+    nib = _NIBBLE[allseq]
+    if nib.size % 2:
+        nib = np.concatenate([nib, np.zeros(1, np.uint8)])
+    seq4 = ((nib[0::2] << 4) | nib[1::2]).astype(np.uint8)
+    seq4 = np.concatenate([seq4, np.zeros(32, np.uint8)])
+    allq = np.concatenate([allq, np.zeros(32, np.uint8)])
+    return layout, RawColumns(seq4, allq, rr, off, min_input_base_quality)
+
+
 def pack8_encode(bases: np.ndarray, quals: np.ndarray) -> Optional[np.ndarray]:
     """fgb_pack8_encode over a (bases, quals) column pair; None when the batch is not encodable
     (IUPAC / lower-case bases, N with a quality other than 2, quality above 61)."""
@@ -304,6 +361,20 @@ class Engine:
         c = _l.FgbColumns(out.base.ctypes.data, out.qual.ctypes.data, out.depth.ctypes.data,
                           out.errors.ctypes.data)
         self._check(self._lib.fgb_submit_pack8(self._h, C.byref(b), C.byref(c)), "fgb_submit_pack8")
+
+    def submit_bam4(self, layout: PackedBatch, raw: "RawColumns", out: HostColumns):
+        """fgb_submit_bam4: rows are built on the device from the 4-bit sequence + raw qualities."""
+        if layout.tiles is None:
+            plan_tiles(layout)
+        self._keep = (layout, raw, out)
+        b = _l.FgbBatch(layout.n_units, layout.n_reads, layout.n_bytes, layout.n_out, len(layout.tiles),
+                        None, None, layout.reads.ctypes.data, layout.units.ctypes.data,
+                        layout.tiles.ctypes.data)
+        c = _l.FgbColumns(out.base.ctypes.data, out.qual.ctypes.data, out.depth.ctypes.data,
+                          out.errors.ctypes.data)
+        r = raw.struct()
+        self._check(self._lib.fgb_submit_bam4(self._h, C.byref(b), C.byref(r), C.byref(c)),
+                    "fgb_submit_bam4")
 
     def wait(self):
         self._check(self._lib.fgb_wait(self._h), "fgb_wait")

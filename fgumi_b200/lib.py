@@ -104,6 +104,12 @@ class FgbCodecJob(C.Structure):
     ]
 
 
+class FgbRawColumns(C.Structure):
+    _fields_ = [("n_raw", C.c_uint64), ("seq4", C.c_void_p), ("quals_raw", C.c_void_p),
+                ("raw_reads", C.c_void_p), ("min_input_base_quality", C.c_uint8),
+                ("reserved", C.c_uint8 * 7)]
+
+
 class FgbCodecParams(C.Structure):
     _fields_ = [
         ("single_strand_qual", C.c_int32),
@@ -149,7 +155,7 @@ SYMBOLS = (
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
-    "fgb_submit_pack8",
+    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device",
 )
 
 _lib = None
@@ -248,5 +254,9 @@ def load() -> C.CDLL:
     lib.fgb_pack8_encode.restype = C.c_int32
     lib.fgb_submit_pack8.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns)]
     lib.fgb_submit_pack8.restype = C.c_int32
+    lib.fgb_submit_bam4.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbRawColumns), C.POINTER(FgbColumns)]
+    lib.fgb_submit_bam4.restype = C.c_int32
+    lib.fgb_unpack_bam4_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbRawColumns), vp, vp, vp]
+    lib.fgb_unpack_bam4_device.restype = C.c_int32
     _lib = lib
     return lib

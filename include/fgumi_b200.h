@@ -206,6 +206,41 @@ fgb_status fgb_pack8_encode(const uint8_t* bases, const uint8_t* quals, uint64_t
  * copied host->device and expanded to the two byte columns by an unpack kernel in front of the
  * vote.  Same chunking, ordering and completion rules as fgb_submit. */
 fgb_status fgb_submit_pack8(fgb_handle* h, const fgb_batch* in, const fgb_columns* out);
+
+/* BAM4: the records' own payload -- 4-bit packed sequence (raw-bam sequence.rs:9-35) and raw quality
+ * bytes -- plus what the host decided per read.  The device does the per-base part of
+ * create_source_read (vanilla_caller.rs:893-916): decode, orientation (reverse-complement and
+ * reversed qualities for a reverse-strand read) and the min-input-quality mask, writing the
+ * SourceRead rows straight into the HBM columns the vote reads.  The host keeps the per-read
+ * decisions: which reads survive, the kept raw span (CODEC's virtual clip, codec_caller.rs:414-469)
+ * and the row length after quality trim / mate-overlap clip / trailing-N strip (:899-927).
+ * 1.5 bytes per raw base cross the link instead of 2 per row byte. */
+typedef struct fgb_raw_read {    /* 16 bytes; entry r belongs to read r of the batch (fgb_batch.reads[r]) */
+  uint64_t src_off;              /* index of the first kept raw base in the raw columns; even           */
+  uint32_t raw_len;              /* kept raw bases (l_seq unless clipped in raw coordinates)            */
+  uint32_t flags;                /* FGB_RAW_REVERSE                                                     */
+} fgb_raw_read;
+enum { FGB_RAW_REVERSE = 1 };
+
+typedef struct fgb_raw_columns {
+  uint64_t n_raw;                /* raw bases in the columns                                            */
+  const uint8_t* seq4;           /* (n_raw + 1) / 2 bytes, base i in the high (i even) / low nibble     */
+  const uint8_t* quals_raw;      /* n_raw bytes                                                         */
+  const fgb_raw_read* raw_reads; /* n_reads entries; src_off ascending, spans not overlapping;
+                                    reads[r] length <= raw_reads[r].raw_len                             */
+  uint8_t min_input_base_quality;/* 0 = no masking (CODEC)                                              */
+  uint8_t reserved[7];
+} fgb_raw_columns;
+
+/* fgb_submit for a batch whose rows are built on the device: `in` carries units / reads / tiles /
+ * n_* as usual (row offsets and lengths describe the rows to build), in->bases and in->quals are
+ * ignored.  Same chunking, ordering and completion rules as fgb_submit. */
+fgb_status fgb_submit_bam4(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,
+                           const fgb_columns* out);
+/* Device-resident variant of the unpack step alone (multi-kernel flows, tests): all pointers of
+ * `in`, `raw` and the row columns are device pointers; enqueues one kernel on `stream`. */
+fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,
+                                  uint8_t* bases, uint8_t* quals, void* stream);
 fgb_status fgb_wait(fgb_handle* h);
 
 /* Pinned host allocation helpers (cudaHostAlloc / cudaFreeHost). */

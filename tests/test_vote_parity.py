@@ -232,3 +232,70 @@ def test_pack8_submit_matches_byte_submit(fg):
     ob, oq, od, oe, _ = O.simplex_batch(batch, 45, 40, 1, 2)
     for sl in batch.unit_slices():
         assert np.array_equal(got.base[sl], ob[sl]) and np.array_equal(got.qual[sl], oq[sl])
+
+
+def test_bam4_submit_builds_source_reads_on_device(fg):
+    """BAM4 transfer format: the device decodes the 4-bit sequence, orients the read
+    and applies the min-input-quality mask of create_source_read (vanilla_caller.rs:893-916); the
+    result must equal a vote over rows prepared by the record oracle's create_source_read."""
+    from oracle import record_oracle as R
+    from tests.bam_builder import make_record
+    rng = np.random.default_rng(99)
+    alphabet = np.frombuffer(b"ACGTACGTACGTACGTNRYM=", np.uint8)
+    opt = R.VanillaOptions(min_reads=1, min_input_base_quality=12, trim=False)
+    raw_units, row_units = [], []
+    for _ in range(2500):
+        depth = int(rng.integers(1, 10))
+        L = int(rng.integers(8, 180))
+        ru, ou = [], []
+        for _ in range(depth):
+            ln = int(rng.integers(max(1, L - 15), L + 1))
+            seq = alphabet[rng.integers(0, alphabet.size, size=ln)].tobytes()
+            q = rng.integers(2, 45, size=ln).astype(np.uint8).tobytes()
+            rev = bool(rng.integers(0, 2))
+            clip = int(rng.integers(0, 6)) if rng.random() < 0.3 else 0
+            rec = R.Rec(make_record(name=b"r", flags=R.REVERSE if rev else 0, pos=10, seq=seq, quals=q))
+            sr = R.create_source_read(rec, 0, clip, opt)
+            if sr is None:
+                continue
+            ru.append((seq, q, rev, len(sr.bases)))
+            ou.append((bytes(sr.bases), bytes(sr.quals)))
+        if ru:
+            raw_units.append(ru); row_units.append(ou)
+    layout, raw = fg.pack_raw_reads(raw_units, 1, opt.min_input_base_quality)
+    eng = fg.Engine(0, 45, 40, 1, 2)
+    got = fg.HostColumns.alloc(layout.n_out)
+    eng.submit_bam4(layout, raw, got)
+    eng.wait()
+    want_batch = fg.pack_source_reads(row_units, 1)
+    assert np.array_equal(want_batch.units["out_off"], layout.units["out_off"])
+    ob, oq, od, oe, _ = O.simplex_batch(want_batch, 45, 40, 1, 2)
+    for sl in want_batch.unit_slices():
+        assert np.array_equal(got.base[sl], ob[sl]) and np.array_equal(got.qual[sl], oq[sl])
+        assert np.array_equal(got.depth[sl], od[sl]) and np.array_equal(got.errors[sl], oe[sl])
+    # CODEC-style rows: a clipped raw span, orientation only, no masking (codec_caller.rs:414-469)
+    raw_units, row_units = [], []
+    for _ in range(600):
+        ru, ou = [], []
+        for _ in range(int(rng.integers(1, 6))):
+            ln = int(rng.integers(10, 120))
+            seq = alphabet[rng.integers(0, 4, size=ln)].tobytes()
+            q = rng.integers(2, 45, size=ln).astype(np.uint8).tobytes()
+            rev = bool(rng.integers(0, 2))
+            a = int(rng.integers(0, 4)) * 2                 # kept span starts on an even raw index
+            b = ln - int(rng.integers(0, 5))
+            ks, kq = seq[a:b], q[a:b]
+            ru.append((ks, kq, rev, len(ks)))
+            rows_b = bytes(R.reverse_complement(ks)) if rev else ks
+            ou.append((rows_b, kq[::-1] if rev else kq))
+        raw_units.append(ru); row_units.append(ou)
+    layout, raw = fg.pack_raw_reads(raw_units, 1, 0)
+    got = fg.HostColumns.alloc(layout.n_out)
+    eng.submit_bam4(layout, raw, got)
+    eng.wait()
+    eng.close()
+    want_batch = fg.pack_source_reads(row_units, 1)
+    ob, oq, od, oe, _ = O.simplex_batch(want_batch, 45, 40, 1, 2)
+    for sl in want_batch.unit_slices():
+        assert np.array_equal(got.base[sl], ob[sl]) and np.array_equal(got.qual[sl], oq[sl])
+        assert np.array_equal(got.depth[sl], od[sl]) and np.array_equal(got.errors[sl], oe[sl])
