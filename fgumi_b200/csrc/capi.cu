@@ -39,6 +39,9 @@ struct Slot {
   uint8_t* quals = nullptr;
   uint8_t* packed = nullptr;     // PACK8 transfer column (fgb_submit_pack8)
   uint64_t cap_packed = 0;
+  uint8_t* out_depth8 = nullptr; // narrow outputs (FGB_OUT_U8)
+  uint8_t* out_errors8 = nullptr;
+  uint64_t cap_out8 = 0;
   uint8_t* seq4 = nullptr;       // BAM4 transfer columns (fgb_submit_bam4)
   uint8_t* qraw = nullptr;
   fgb_raw_read* rawreads = nullptr;
@@ -212,7 +215,7 @@ void fgb_destroy(fgb_handle* h) {
   for (int s = 0; s < kSlots; ++s) {
     Slot& sl = h->slots[s];
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
-    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.seq4); cudaFree(sl.qraw); cudaFree(sl.rawreads); cudaFree(sl.reads); cudaFree(sl.units);
+    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.out_depth8); cudaFree(sl.out_errors8); cudaFree(sl.seq4); cudaFree(sl.qraw); cudaFree(sl.rawreads); cudaFree(sl.reads); cudaFree(sl.units);
     cudaFree(sl.tiles); cudaFree(sl.out_base); cudaFree(sl.out_qual); cudaFree(sl.out_depth);
     cudaFree(sl.out_errors);
   }
@@ -403,38 +406,59 @@ fgb_status launch_unpack_bam4(fgb_handle* h, const Bam4Args& a, cudaStream_t s) 
   return FGB_OK;
 }
 
-// Layout rules of fgb_raw_columns (checked once per submit, O(reads)).
-fgb_status check_raw(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw) {
-  if (!raw || !raw->seq4 || !raw->quals_raw || !raw->raw_reads) return FGB_ERR_INVALID_ARG;
-  uint64_t prev_end = 0;
-  for (uint64_t r = 0; r < in->n_reads; ++r) {
+// Layout rules of fgb_raw_columns for reads [r0, r1); `*prev_end` carries the end of the previous
+// span across calls.  Checked chunk by chunk so that the O(reads) pass overlaps the copies in flight.
+fgb_status check_raw(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw, uint64_t r0,
+                     uint64_t r1, uint64_t* prev_end) {
+  uint64_t pe = *prev_end;
+  uint32_t bad = 0;
+  for (uint64_t r = r0; r < r1; ++r) {
     const fgb_raw_read& rr = raw->raw_reads[r];
-    if ((rr.src_off & 1u) || rr.src_off < prev_end || rr.src_off + rr.raw_len > raw->n_raw ||
-        FGB_READ_LEN(in->reads[r]) > rr.raw_len) {
-      h->last_error = "fgb_raw_columns: raw spans must be even-aligned, ascending, inside the columns and at least as long as their rows";
-      return FGB_ERR_LAYOUT;
-    }
-    prev_end = rr.src_off + rr.raw_len;
+    bad |= static_cast<uint32_t>(rr.src_off & 1u) | (rr.src_off < pe) |
+           (rr.src_off + rr.raw_len > raw->n_raw) | (FGB_READ_LEN(in->reads[r]) > rr.raw_len);
+    pe = rr.src_off + rr.raw_len;
+  }
+  *prev_end = pe;
+  if (bad) {
+    h->last_error = "fgb_raw_columns: raw spans must be even-aligned, ascending, inside the columns and at least as long as their rows";
+    return FGB_ERR_LAYOUT;
   }
   return FGB_OK;
 }
 
 fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* out, HostFormat fmt,
-                       const fgb_raw_columns* raw = nullptr) {
+                       const fgb_raw_columns* raw = nullptr, bool narrow = false) {
   if (!h || !in || !out) return FGB_ERR_INVALID_ARG;
   if (h->submit_pending) return FGB_ERR_BUSY;
   if (in->n_tiles == 0) return FGB_OK;
-  if (fmt == HostFormat::kBam4) {
-    if (!in->reads) return FGB_ERR_INVALID_ARG;
-    fgb_status rs = check_raw(h, in, raw);
-    if (rs != FGB_OK) return rs;
+  if (narrow) {
+    if (!in->units) return FGB_ERR_INVALID_ARG;
+    for (uint64_t u = 0; u < in->n_units; ++u)
+      if (in->units[u + 1].read_begin - in->units[u].read_begin > 255u) {
+        h->last_error = "FGB_OUT_U8 needs every unit to have at most 255 reads";
+        return FGB_ERR_INVALID_ARG;
+      }
   }
+  if (fmt == HostFormat::kBam4 &&
+      (!in->reads || !raw || !raw->seq4 || !raw->quals_raw || !raw->raw_reads))
+    return FGB_ERR_INVALID_ARG;
+  uint64_t raw_prev_end = 0;
   if (!in->tiles || !in->units || !in->reads || (fmt != HostFormat::kBam4 && !in->bases) ||
       (fmt == HostFormat::kBytes && !in->quals) || !out->base ||
       !out->qual || !out->depth || !out->errors)
     return FGB_ERR_INVALID_ARG;
   FGB_CUDA(h, cudaSetDevice(h->device));
   h->submit_pending = true;
+  // Any early return below leaves copies in flight that target the caller's buffers: drain them and
+  // clear the pending flag so the handle stays usable.
+  struct Guard {
+    fgb_handle* h; bool ok = false;
+    ~Guard() {
+      if (ok) return;
+      for (int i = 0; i < kSlots; ++i) if (h->slots[i].stream) cudaStreamSynchronize(h->slots[i].stream);
+      h->submit_pending = false;
+    }
+  } guard{h};
 
   const fgb_tile* T = in->tiles;
   uint64_t t0 = 0;
@@ -501,6 +525,7 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
     } else if (fmt == HostFormat::kBam4) {
       // raw span of this chunk's reads (ascending by construction), origin aligned down to 32 bases
       const uint64_t rf = first.read_begin, rl = r1;           // absolute read range [rf, rl)
+      if ((st = check_raw(h, in, raw, rf, rl, &raw_prev_end)) != FGB_OK) return st;
       if (rl > rf) {
         const uint64_t a0 = raw->raw_reads[rf].src_off & ~31ull;
         const uint64_t a1 = raw->raw_reads[rl - 1].src_off + raw->raw_reads[rl - 1].raw_len;
@@ -556,11 +581,31 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
     const uint64_t no = o1 - o0;
     FGB_CUDA(h, cudaMemcpyAsync(out->base + o0, sl.out_base, no, cudaMemcpyDeviceToHost, s));
     FGB_CUDA(h, cudaMemcpyAsync(out->qual + o0, sl.out_qual, no, cudaMemcpyDeviceToHost, s));
-    FGB_CUDA(h, cudaMemcpyAsync(out->depth + o0, sl.out_depth, no * 2, cudaMemcpyDeviceToHost, s));
-    FGB_CUDA(h, cudaMemcpyAsync(out->errors + o0, sl.out_errors, no * 2, cudaMemcpyDeviceToHost, s));
+    if (narrow) {
+      uint64_t c8 = sl.cap_out8;
+      if ((st = ensure(h, &sl.out_depth8, &sl.cap_out8, no + 16)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.out_errors8, &c8, no + 16)) != FGB_OK) return st;
+      const uint64_t n8 = (no + 7u) >> 3;   // output rows are padded to 8 elements
+      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n8 + 255u) / 256u,
+                                                                     static_cast<uint64_t>(h->sm_count) * 16u));
+      narrow_u16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(sl.out_depth),
+                                             reinterpret_cast<const uint4*>(sl.out_errors),
+                                             reinterpret_cast<uint2*>(sl.out_depth8),
+                                             reinterpret_cast<uint2*>(sl.out_errors8), n8);
+      h->launches++;
+      FGB_CUDA(h, cudaGetLastError());
+      FGB_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out->depth) + o0, sl.out_depth8, no,
+                                  cudaMemcpyDeviceToHost, s));
+      FGB_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(out->errors) + o0, sl.out_errors8, no,
+                                  cudaMemcpyDeviceToHost, s));
+    } else {
+      FGB_CUDA(h, cudaMemcpyAsync(out->depth + o0, sl.out_depth, no * 2, cudaMemcpyDeviceToHost, s));
+      FGB_CUDA(h, cudaMemcpyAsync(out->errors + o0, sl.out_errors, no * 2, cudaMemcpyDeviceToHost, s));
+    }
     t0 = t1;
     ++chunk;
   }
+  guard.ok = true;
   return FGB_OK;
 }
 }  // namespace
@@ -578,6 +623,14 @@ fgb_status fgb_submit_pack8(fgb_handle* h, const fgb_batch* in, const fgb_column
 fgb_status fgb_submit_bam4(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,
                            const fgb_columns* out) {
   return submit_impl(h, in, out, HostFormat::kBam4, raw);
+}
+
+fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out,
+                         const fgb_submit_options* opt) {
+  if (!opt || opt->input_format > FGB_IN_BAM4 || opt->output_format > FGB_OUT_U8) return FGB_ERR_INVALID_ARG;
+  const HostFormat f = opt->input_format == FGB_IN_PACK8 ? HostFormat::kPack8
+                       : opt->input_format == FGB_IN_BAM4 ? HostFormat::kBam4 : HostFormat::kBytes;
+  return submit_impl(h, in, out, f, opt->raw, opt->output_format == FGB_OUT_U8);
 }
 
 fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,

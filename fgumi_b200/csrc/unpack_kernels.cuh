@@ -106,4 +106,17 @@ __global__ void __launch_bounds__(256) unpack_bam4_kernel(const Bam4Args a) {
   }
 }
 
+// Output narrowing in front of the device->host copy: 8 u16 -> 8 u8 per thread and column.
+__global__ void __launch_bounds__(256) narrow_u16_kernel(const uint4* __restrict__ depth16,
+                                                         const uint4* __restrict__ errors16,
+                                                         uint2* __restrict__ depth8,
+                                                         uint2* __restrict__ errors8, uint64_t n8) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const uint4 d = depth16[i], e = errors16[i];
+    depth8[i] = make_uint2(__byte_perm(d.x, d.y, 0x6420u), __byte_perm(d.z, d.w, 0x6420u));
+    errors8[i] = make_uint2(__byte_perm(e.x, e.y, 0x6420u), __byte_perm(e.z, e.w, 0x6420u));
+  }
+}
+
 }  // namespace fgb

@@ -376,6 +376,29 @@ class Engine:
         self._check(self._lib.fgb_submit_bam4(self._h, C.byref(b), C.byref(r), C.byref(c)),
                     "fgb_submit_bam4")
 
+    def submit_ex(self, batch: PackedBatch, out: HostColumns, packed: Optional[np.ndarray] = None,
+                  raw: Optional["RawColumns"] = None, narrow: bool = False):
+        """fgb_submit_ex: input format chosen by what is passed (packed -> PACK8, raw -> BAM4, else the
+        two byte columns); narrow=True makes out.depth / out.errors uint8 columns."""
+        if batch.tiles is None:
+            plan_tiles(batch)
+        self._keep = (batch, packed, raw, out)
+        fmt = _l.FGB_IN_PACK8 if packed is not None else _l.FGB_IN_BAM4 if raw is not None else _l.FGB_IN_BYTES
+        bases = packed.ctypes.data if packed is not None else (batch.bases.ctypes.data if fmt == _l.FGB_IN_BYTES else None)
+        quals = batch.quals.ctypes.data if fmt == _l.FGB_IN_BYTES else None
+        b = _l.FgbBatch(batch.n_units, batch.n_reads, batch.n_bytes, batch.n_out, len(batch.tiles),
+                        bases, quals, batch.reads.ctypes.data, batch.units.ctypes.data,
+                        batch.tiles.ctypes.data)
+        if narrow:
+            assert out.depth.dtype == np.uint8 and out.errors.dtype == np.uint8
+        c = _l.FgbColumns(out.base.ctypes.data, out.qual.ctypes.data, out.depth.ctypes.data,
+                          out.errors.ctypes.data)
+        rs = raw.struct() if raw is not None else None
+        o = _l.FgbSubmitOptions(fmt, _l.FGB_OUT_U8 if narrow else _l.FGB_OUT_U16,
+                                C.cast(C.pointer(rs), C.c_void_p) if rs is not None else None)
+        self._keep = self._keep + (rs,)
+        self._check(self._lib.fgb_submit_ex(self._h, C.byref(b), C.byref(c), C.byref(o)), "fgb_submit_ex")
+
     def wait(self):
         self._check(self._lib.fgb_wait(self._h), "fgb_wait")
         self._keep = None

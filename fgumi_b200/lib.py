@@ -110,6 +110,14 @@ class FgbRawColumns(C.Structure):
                 ("reserved", C.c_uint8 * 7)]
 
 
+class FgbSubmitOptions(C.Structure):
+    _fields_ = [("input_format", C.c_uint32), ("output_format", C.c_uint32), ("raw", C.c_void_p)]
+
+
+FGB_IN_BYTES, FGB_IN_PACK8, FGB_IN_BAM4 = 0, 1, 2
+FGB_OUT_U16, FGB_OUT_U8 = 0, 1
+
+
 class FgbCodecParams(C.Structure):
     _fields_ = [
         ("single_strand_qual", C.c_int32),
@@ -155,7 +163,7 @@ SYMBOLS = (
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
-    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device",
+    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex",
 )
 
 _lib = None
@@ -258,5 +266,7 @@ def load() -> C.CDLL:
     lib.fgb_submit_bam4.restype = C.c_int32
     lib.fgb_unpack_bam4_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbRawColumns), vp, vp, vp]
     lib.fgb_unpack_bam4_device.restype = C.c_int32
+    lib.fgb_submit_ex.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), C.POINTER(FgbSubmitOptions)]
+    lib.fgb_submit_ex.restype = C.c_int32
     _lib = lib
     return lib

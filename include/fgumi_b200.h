@@ -237,6 +237,20 @@ typedef struct fgb_raw_columns {
  * ignored.  Same chunking, ordering and completion rules as fgb_submit. */
 fgb_status fgb_submit_bam4(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,
                            const fgb_columns* out);
+/* The general form: any input format, optionally NARROW outputs.  With FGB_OUT_U8, out->depth and
+ * out->errors are treated as uint8_t columns of n_out elements (cast the pointers): the link then
+ * carries 4 instead of 6 bytes per consensus position.  Allowed only when no unit has more than
+ * 255 reads (FGB_ERR_INVALID_ARG otherwise); the record builder widens to i16 for the cd/ce tags. */
+enum { FGB_IN_BYTES = 0, FGB_IN_PACK8 = 1, FGB_IN_BAM4 = 2 };
+enum { FGB_OUT_U16 = 0, FGB_OUT_U8 = 1 };
+typedef struct fgb_submit_options {
+  uint32_t input_format;           /* FGB_IN_*  */
+  uint32_t output_format;          /* FGB_OUT_* */
+  const fgb_raw_columns* raw;      /* FGB_IN_BAM4 only */
+} fgb_submit_options;
+fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out,
+                         const fgb_submit_options* opt);
+
 /* Device-resident variant of the unpack step alone (multi-kernel flows, tests): all pointers of
  * `in`, `raw` and the row columns are device pointers; enqueues one kernel on `stream`. */
 fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,

@@ -299,3 +299,36 @@ def test_bam4_submit_builds_source_reads_on_device(fg):
     for sl in want_batch.unit_slices():
         assert np.array_equal(got.base[sl], ob[sl]) and np.array_equal(got.qual[sl], oq[sl])
         assert np.array_equal(got.depth[sl], od[sl]) and np.array_equal(got.errors[sl], oe[sl])
+
+
+def test_submit_ex_narrow_outputs(fg):
+    """fgb_submit_ex with FGB_OUT_U8: depth / errors arrive as u8 columns and equal the u16 ones; a
+    unit deeper than 255 reads is refused."""
+    rng = np.random.default_rng(123)
+    units = []
+    for _ in range(1500):
+        depth = int(rng.integers(1, 30))
+        L = int(rng.integers(10, 160))
+        rows = []
+        for _ in range(depth):
+            b = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=L)
+            q = rng.integers(2, 45, size=L).astype(np.uint8)
+            rows.append((b.tobytes(), q.tobytes()))
+        units.append(rows)
+    batch = fg.pack_source_reads(units, 1)
+    eng = fg.Engine(0, 45, 40, 1, 2)
+    want = eng.vote(batch)
+    n = batch.n_out
+    for packed in (None, fg.pack8_encode(batch.bases, batch.quals)):
+        got = fg.HostColumns(np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.full(n, 255, np.uint8),
+                             np.full(n, 255, np.uint8))
+        eng.submit_ex(batch, got, packed=packed, narrow=True)
+        eng.wait()
+        for sl in batch.unit_slices():
+            assert np.array_equal(got.base[sl], want.base[sl]) and np.array_equal(got.qual[sl], want.qual[sl])
+            assert np.array_equal(got.depth[sl], want.depth[sl]) and np.array_equal(got.errors[sl], want.errors[sl])
+    deep = fg.pack_source_reads([[(b"ACGT", bytes([30] * 4))] * 256], 1)
+    out = fg.HostColumns(np.zeros(8, np.uint8), np.zeros(8, np.uint8), np.zeros(8, np.uint8), np.zeros(8, np.uint8))
+    with pytest.raises(fg.lib.FgbError):
+        eng.submit_ex(deep, out, narrow=True)
+    eng.close()
