@@ -20,6 +20,29 @@ class ConsensusOutput:
         self.data, self.count = data, count
 
 
+class ConsensusFilter:
+    """`fgumi filter` options for single-strand consensus reads (commands/filter.rs:100-160):
+    -M min_reads, -E max_read_error_rate, -e max_base_error_rate, -N min_base_quality,
+    -q min_mean_base_quality, -n max_no_call_fraction (>= 1.0 = absolute count)."""
+
+    def __init__(self, min_reads: int = 1, max_read_error_rate: float = 0.025,
+                 max_base_error_rate: float = 0.1, min_base_quality=None, min_mean_base_quality=None,
+                 max_no_call_fraction: float = 0.2):
+        self.min_reads, self.max_read_error_rate = min_reads, max_read_error_rate
+        self.max_base_error_rate, self.min_base_quality = max_base_error_rate, min_base_quality
+        self.min_mean_base_quality, self.max_no_call_fraction = min_mean_base_quality, max_no_call_fraction
+
+    def fill(self, fp: "_l.FgbFilterParams"):
+        fp.min_reads = self.min_reads
+        fp.min_base_quality = -1 if self.min_base_quality is None else self.min_base_quality
+        fp.max_read_error_rate = self.max_read_error_rate
+        fp.max_base_error_rate = self.max_base_error_rate
+        fp.min_mean_base_quality = -1.0 if self.min_mean_base_quality is None else self.min_mean_base_quality
+        fp.max_no_call_fraction = self.max_no_call_fraction
+        fp.per_base_tags = 1
+        return fp
+
+
 class _Caller:
     """Shared plumbing over fgb_caller_* (add_group / flush / statistics)."""
 
@@ -36,7 +59,8 @@ class VanillaUmiConsensusCaller(_Caller):
 
     def __init__(self, read_name_prefix: str, read_group_id: str,
                  options: VanillaUmiConsensusOptions = VanillaUmiConsensusOptions(), device: int = 0,
-                 tag: bytes = b"MI", cell_tag: bytes = b"", consensus_call_overlapping_bases: bool = False):
+                 tag: bytes = b"MI", cell_tag: bytes = b"", consensus_call_overlapping_bases: bool = False,
+                 filter: "ConsensusFilter" = None):
         self._lib = _l.load()
         self._prefix = read_name_prefix.encode()
         self._rg = read_group_id.encode()
@@ -49,6 +73,9 @@ class VanillaUmiConsensusCaller(_Caller):
         o.produce_per_base_tags = 1 if options.produce_per_base_tags else 0
         o.trim = 1 if options.trim else 0
         o.consensus_call_overlapping_bases = 1 if consensus_call_overlapping_bases else 0
+        if filter is not None:           # `fgumi simplex | fgumi filter` in one pass
+            o.filter_enabled = 1
+            filter.fill(o.filter)
         o.min_reads = options.min_reads
         o.tag = tag
         o.cell_tag = cell_tag if cell_tag else b"\0\0"

@@ -15,6 +15,7 @@
 #include "../../include/fgumi_b200.h"
 #include "combine_kernels.cuh"
 #include "fgb_config.h"
+#include "filter_kernel.cuh"
 #include "host_tables.h"
 #include "unpack_kernels.cuh"
 #include "vote_kernel.cuh"
@@ -39,6 +40,9 @@ struct Slot {
   uint8_t* quals = nullptr;
   uint8_t* packed = nullptr;     // PACK8 transfer column (fgb_submit_pack8)
   uint64_t cap_packed = 0;
+  uint8_t* unit_status = nullptr;   // filter epilogue results
+  uint32_t* unit_masked = nullptr;
+  uint64_t cap_ustat = 0, cap_umask = 0;
   uint8_t* out_depth8 = nullptr; // narrow outputs (FGB_OUT_U8)
   uint8_t* out_errors8 = nullptr;
   uint64_t cap_out8 = 0;
@@ -69,6 +73,8 @@ struct fgb_handle {
   std::string last_error;
   Slot slots[kSlots];
   bool submit_pending = false;
+  uint16_t* d_emax = nullptr;                       // filter: per-depth error-count limit
+  double emax_rate = -1.0;                          // the max_base_error_rate d_emax was built for
   int n_slots = 2;                                  // FGB_SUBMIT_SLOTS (1..kSlots)
   uint64_t chunk_bytes = kChunkColumnBytes;         // FGB_SUBMIT_CHUNK_MB
 };
@@ -215,12 +221,13 @@ void fgb_destroy(fgb_handle* h) {
   for (int s = 0; s < kSlots; ++s) {
     Slot& sl = h->slots[s];
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
-    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.out_depth8); cudaFree(sl.out_errors8); cudaFree(sl.seq4); cudaFree(sl.qraw); cudaFree(sl.rawreads); cudaFree(sl.reads); cudaFree(sl.units);
+    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.unit_status); cudaFree(sl.unit_masked); cudaFree(sl.out_depth8); cudaFree(sl.out_errors8); cudaFree(sl.seq4); cudaFree(sl.qraw); cudaFree(sl.rawreads); cudaFree(sl.reads); cudaFree(sl.units);
     cudaFree(sl.tiles); cudaFree(sl.out_base); cudaFree(sl.out_qual); cudaFree(sl.out_depth);
     cudaFree(sl.out_errors);
   }
   cudaFree(h->d_tables);
   cudaFree(h->d_counters);
+  cudaFree(h->d_emax);
   delete h;
 }
 
@@ -396,6 +403,58 @@ void fgb_host_free(void* p) { if (p) cudaFreeHost(p); }
 namespace {
 enum class HostFormat { kBytes, kPack8, kBam4 };
 
+// emax[d] = largest error count e (<= d) with (double)e / (double)d <= rate, i.e. exactly the
+// positions mask_bases keeps (`errors / depth > max_base_error_rate` masks, filter.rs:681-684).
+// Built with the same f64 division the reference performs; e -> e/d is monotone, so bisect.
+fgb_status ensure_emax(fgb_handle* h, double rate, cudaStream_t s) {
+  if (h->d_emax && h->emax_rate == rate) return FGB_OK;
+  std::vector<uint16_t> t(65536, 0);
+  for (uint32_t d = 1; d < 65536; ++d) {
+    uint32_t lo = 0, hi = d;           // invariant: lo passes (0/d = 0 <= rate unless rate < 0)
+    if (!(0.0 / static_cast<double>(d) > rate)) {
+      while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (static_cast<double>(mid) / static_cast<double>(d) > rate) hi = mid - 1; else lo = mid;
+      }
+      t[d] = static_cast<uint16_t>(lo);
+    } else {
+      t[d] = 0;                        // negative rate: even zero errors would be masked; the kernel's
+    }                                  // `e > emax` cannot express that, fgb_filter_* rejects rate < 0
+  }
+  if (!h->d_emax) FGB_CUDA(h, cudaMalloc(&h->d_emax, 65536 * sizeof(uint16_t)));
+  FGB_CUDA(h, cudaStreamSynchronize(s));   // the table may still be in use by an earlier launch
+  FGB_CUDA(h, cudaMemcpy(h->d_emax, t.data(), 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  h->emax_rate = rate;
+  return FGB_OK;
+}
+
+bool filter_params_ok(const fgb_filter_params* fp) {
+  return fp && fp->max_base_error_rate >= 0.0 && fp->max_no_call_fraction >= 0.0 &&
+         fp->min_base_quality <= 255 && fp->min_base_quality >= -1;
+}
+
+fgb_status launch_filter(fgb_handle* h, const fgb_unit* units, uint64_t u0, uint64_t u1,
+                         const fgb_columns& cols, const fgb_filter_params& fp, uint8_t* status,
+                         uint32_t* masked, cudaStream_t s) {
+  if (u1 <= u0) return FGB_OK;
+  FilterArgs a;
+  a.units = units; a.unit_begin = u0; a.unit_end = u1;
+  a.base = cols.base; a.qual = cols.qual; a.depth = cols.depth; a.errors = cols.errors;
+  a.emax = h->d_emax; a.status = status; a.masked = masked; a.counters = h->d_counters;
+  a.min_reads = fp.min_reads;
+  a.min_base_quality = fp.min_base_quality < 0 ? 0u : static_cast<uint32_t>(fp.min_base_quality);
+  a.per_base_tags = fp.per_base_tags;
+  a.max_read_error_rate = fp.max_read_error_rate;
+  a.min_mean_base_quality = fp.min_mean_base_quality;
+  a.max_no_call_fraction = fp.max_no_call_fraction;
+  const uint64_t n = u1 - u0;
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + 7u) / 8u, static_cast<uint64_t>(h->sm_count) * 16u));
+  filter_simplex_kernel<<<grid, 256, 0, s>>>(a);
+  h->launches++;
+  FGB_CUDA(h, cudaGetLastError());
+  return FGB_OK;
+}
+
 fgb_status launch_unpack_bam4(fgb_handle* h, const Bam4Args& a, cudaStream_t s) {
   const uint64_t n = a.read_end - a.read_begin;
   if (n == 0) return FGB_OK;
@@ -427,10 +486,20 @@ fgb_status check_raw(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* 
 }
 
 fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* out, HostFormat fmt,
-                       const fgb_raw_columns* raw = nullptr, bool narrow = false) {
+                       const fgb_raw_columns* raw = nullptr, bool narrow = false,
+                       const fgb_submit_options* opt = nullptr) {
   if (!h || !in || !out) return FGB_ERR_INVALID_ARG;
   if (h->submit_pending) return FGB_ERR_BUSY;
   if (in->n_tiles == 0) return FGB_OK;
+  const fgb_filter_params* fp = opt ? opt->filter : nullptr;
+  if (fp) {
+    if (!filter_params_ok(fp) || !opt->unit_status) return FGB_ERR_INVALID_ARG;
+    FGB_CUDA(h, cudaSetDevice(h->device));
+    for (int i = 0; i < kSlots; ++i)     // the table is shared by every slot stream
+      if (h->slots[i].stream) FGB_CUDA(h, cudaStreamSynchronize(h->slots[i].stream));
+    fgb_status es = ensure_emax(h, fp->max_base_error_rate, h->slots[0].stream);
+    if (es != FGB_OK) return es;
+  }
   if (narrow) {
     if (!in->units) return FGB_ERR_INVALID_ARG;
     for (uint64_t u = 0; u < in->n_units; ++u)
@@ -578,6 +647,16 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
       if ((st = launch_unpack_bam4(h, ua, s)) != FGB_OK) return st;
     }
     if ((st = launch_vote(h, db, dc, s)) != FGB_OK) return st;
+    if (fp) {
+      if ((st = ensure(h, &sl.unit_status, &sl.cap_ustat, u1 - u0 + 16)) != FGB_OK) return st;
+      if (opt->unit_masked && (st = ensure(h, &sl.unit_masked, &sl.cap_umask, u1 - u0 + 16)) != FGB_OK) return st;
+      if ((st = launch_filter(h, db.units, u0, u1, dc, *fp, sl.unit_status,
+                              opt->unit_masked ? sl.unit_masked : nullptr, s)) != FGB_OK) return st;
+      FGB_CUDA(h, cudaMemcpyAsync(opt->unit_status + u0, sl.unit_status, u1 - u0, cudaMemcpyDeviceToHost, s));
+      if (opt->unit_masked)
+        FGB_CUDA(h, cudaMemcpyAsync(opt->unit_masked + u0, sl.unit_masked, (u1 - u0) * 4,
+                                    cudaMemcpyDeviceToHost, s));
+    }
     const uint64_t no = o1 - o0;
     FGB_CUDA(h, cudaMemcpyAsync(out->base + o0, sl.out_base, no, cudaMemcpyDeviceToHost, s));
     FGB_CUDA(h, cudaMemcpyAsync(out->qual + o0, sl.out_qual, no, cudaMemcpyDeviceToHost, s));
@@ -630,7 +709,20 @@ fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* 
   if (!opt || opt->input_format > FGB_IN_BAM4 || opt->output_format > FGB_OUT_U8) return FGB_ERR_INVALID_ARG;
   const HostFormat f = opt->input_format == FGB_IN_PACK8 ? HostFormat::kPack8
                        : opt->input_format == FGB_IN_BAM4 ? HostFormat::kBam4 : HostFormat::kBytes;
-  return submit_impl(h, in, out, f, opt->raw, opt->output_format == FGB_OUT_U8);
+  return submit_impl(h, in, out, f, opt->raw, opt->output_format == FGB_OUT_U8, opt);
+}
+
+fgb_status fgb_filter_simplex_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* cols,
+                                     const fgb_filter_params* fp, uint8_t* unit_status,
+                                     uint32_t* unit_masked, void* stream) {
+  if (!h || !in || !cols || !unit_status || !filter_params_ok(fp)) return FGB_ERR_INVALID_ARG;
+  if (in->n_units == 0) return FGB_OK;
+  if (!in->units || !cols->base || !cols->qual || !cols->depth || !cols->errors) return FGB_ERR_INVALID_ARG;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  fgb_status st = ensure_emax(h, fp->max_base_error_rate, s);
+  if (st != FGB_OK) return st;
+  return launch_filter(h, in->units, 0, in->n_units, *cols, *fp, unit_status, unit_masked, s);
 }
 
 fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,

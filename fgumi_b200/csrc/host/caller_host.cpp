@@ -235,7 +235,21 @@ fgb_status flush_simplex(fgb_caller* c) {
   b.bases = c->pack.bases.data(); b.quals = c->pack.quals.data(); b.reads = c->pack.reads.data();
   b.units = c->pack.units.data(); b.tiles = tiles.data();
   fgb_columns cols{ob.data(), oq.data(), od.data(), oe.data()};
-  st = fgb_submit(c->h, &b, &cols);
+  std::vector<uint8_t> fstatus;
+  std::vector<uint32_t> fmasked;
+  if (c->opt.filter_enabled) {   // `fgumi filter` as an epilogue of the vote (commands/filter.rs:738-905)
+    fstatus.assign(U + 1, FGB_FILTER_PASS);
+    fmasked.assign(U + 1, 0);
+    fgb_filter_params fp = c->opt.filter;
+    fp.per_base_tags = c->opt.produce_per_base_tags;
+    fgb_submit_options so;
+    std::memset(&so, 0, sizeof(so));
+    so.input_format = FGB_IN_BYTES; so.output_format = FGB_OUT_U16;
+    so.filter = &fp; so.unit_status = fstatus.data(); so.unit_masked = fmasked.data();
+    st = fgb_submit_ex(c->h, &b, &cols, &so);
+  } else {
+    st = fgb_submit(c->h, &b, &cols);
+  }
   if (st == FGB_OK) st = fgb_wait(c->h);
   if (st != FGB_OK) {
     char buf[256];
@@ -243,9 +257,27 @@ fgb_status flush_simplex(fgb_caller* c) {
     c->last_error = buf;
     return st;
   }
+  // Template rule (commands/filter.rs:640-672): reads that share a name -- here the consecutive units
+  // of one MI -- are emitted only if every one of them passed.
+  std::vector<char> emit(U, 1);
+  if (c->opt.filter_enabled) {
+    for (uint64_t i = 0; i < U;) {
+      uint64_t j = i;
+      bool pass = true;
+      while (j < U && c->metas[j].umi == c->metas[i].umi) { pass = pass && fstatus[j] == FGB_FILTER_PASS; ++j; }
+      for (uint64_t k = i; k < j; ++k) {
+        emit[k] = pass;
+        c->stats[FGB_STAT_FILTER_RECORDS] += 1;
+        c->stats[FGB_STAT_FILTER_BASES_MASKED] += fmasked[k];
+        if (pass) c->stats[FGB_STAT_FILTER_PASSED] += 1;
+      }
+      i = j;
+    }
+  }
   // ---- build_consensus_record_into, vanilla_caller.rs:1365-1473 ----
   bam::Writer w(&c->out);
   for (uint64_t i = 0; i < U; ++i) {
+    if (!emit[i]) continue;
     const fgb_unit& u = c->pack.units[i];
     const UnitMeta& m = c->metas[i];
     const uint32_t L = u.cons_len;
@@ -929,6 +961,7 @@ fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_call
   *out = nullptr;
   if (opt->mode > FGB_MODE_CODEC) return FGB_ERR_INVALID_ARG;
   if (opt->mode != FGB_MODE_DUPLEX && opt->min_reads == 0) return FGB_ERR_INVALID_ARG;
+  if (opt->filter_enabled && opt->mode != FGB_MODE_SIMPLEX) return FGB_ERR_INVALID_ARG;
   if (opt->mode == FGB_MODE_CODEC && opt->consensus_call_overlapping_bases)
     return FGB_ERR_INVALID_ARG;   // "CODEC does not support overlapping consensus", commands/codec.rs:257
   if (opt->mode == FGB_MODE_DUPLEX &&
@@ -1035,6 +1068,20 @@ fgb_status fgb_overlap_apply_group(uint8_t* records, const uint64_t* rec_off, ui
     stats[2] += oc.stats.bases_disagreeing; stats[3] += oc.stats.bases_corrected;
   }
   return FGB_OK;
+}
+
+uint32_t fgb_struct_size(uint32_t id) {
+  switch (id) {
+    case 0: return sizeof(fgb_caller_options);
+    case 1: return sizeof(fgb_filter_params);
+    case 2: return sizeof(fgb_submit_options);
+    case 3: return sizeof(fgb_raw_columns);
+    case 4: return sizeof(fgb_raw_read);
+    case 5: return sizeof(fgb_batch);
+    case 6: return sizeof(fgb_codec_params);
+    case 7: return sizeof(fgb_params);
+    default: return 0;
+  }
 }
 
 fgb_status fgb_caller_stats(const fgb_caller* c, uint64_t stats[FGB_NSTATS]) {

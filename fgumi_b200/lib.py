@@ -24,10 +24,11 @@ FGB_ERR_NOT_ENCODABLE = 9
 
 FGB_READ_ALIGN = 8
 FGB_OUT_ALIGN = 8
-FGB_NCOUNTERS = 8
+FGB_NCOUNTERS = 12
 COUNTER_NAMES = (
     "units", "positions", "exact_positions", "nocall_positions", "input_reads",
     "duplex_bases", "duplex_disagreements", "combined_jobs",
+    "filter_records", "filter_passed", "filter_bases_masked",
 )
 
 FGB_DUPLEX_BOTH, FGB_DUPLEX_A_ONLY, FGB_DUPLEX_B_ONLY, FGB_DUPLEX_NONE = 0, 1, 2, 3
@@ -110,8 +111,20 @@ class FgbRawColumns(C.Structure):
                 ("reserved", C.c_uint8 * 7)]
 
 
+class FgbFilterParams(C.Structure):
+    _fields_ = [("min_reads", C.c_uint32), ("min_base_quality", C.c_int32),
+                ("max_read_error_rate", C.c_double), ("max_base_error_rate", C.c_double),
+                ("min_mean_base_quality", C.c_double), ("max_no_call_fraction", C.c_double),
+                ("per_base_tags", C.c_uint8), ("reserved", C.c_uint8 * 7)]
+
+
 class FgbSubmitOptions(C.Structure):
-    _fields_ = [("input_format", C.c_uint32), ("output_format", C.c_uint32), ("raw", C.c_void_p)]
+    _fields_ = [("input_format", C.c_uint32), ("output_format", C.c_uint32), ("raw", C.c_void_p),
+                ("filter", C.c_void_p), ("unit_status", C.c_void_p), ("unit_masked", C.c_void_p)]
+
+
+FGB_FILTER_PASS, FGB_FILTER_INSUFFICIENT_READS, FGB_FILTER_EXCESSIVE_ERROR_RATE = 0, 1, 2
+FGB_FILTER_LOW_MEAN_QUALITY, FGB_FILTER_TOO_MANY_NO_CALLS, FGB_FILTER_NO_RECORD = 3, 4, 255
 
 
 FGB_IN_BYTES, FGB_IN_PACK8, FGB_IN_BAM4 = 0, 1, 2
@@ -138,6 +151,7 @@ class FgbCallerOptions(C.Structure):
         ("tag", C.c_char * 2), ("cell_tag", C.c_char * 2),
         ("read_name_prefix", C.c_char_p), ("read_group_id", C.c_char_p),
         ("min_duplex_length", C.c_uint32), ("reserved1", C.c_uint32), ("codec", FgbCodecParams),
+        ("filter_enabled", C.c_uint8), ("reserved2", C.c_uint8 * 7), ("filter", FgbFilterParams),
     ]
 
 
@@ -146,7 +160,8 @@ STAT_NAMES = ("total_reads", "consensus_reads", "filtered_reads", "InsufficientR
               "SecondaryOrSupplementary", "ZeroLengthAfterTrimming", "MinorityAlignment",
               "OrphanConsensus", "PotentialCollision", "FragmentRead", "InsufficientOverlap",
               "IndelErrorBetweenStrands", "duplex_bases", "duplex_disagreements", "overlapping_bases",
-              "overlap_bases_agreeing", "overlap_bases_disagreeing", "overlap_bases_corrected")
+              "overlap_bases_agreeing", "overlap_bases_disagreeing", "overlap_bases_corrected",
+              "filter_records", "filter_passed", "filter_bases_masked")
 
 
 class FgbCodecOut(C.Structure):
@@ -163,7 +178,7 @@ SYMBOLS = (
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
-    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex",
+    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size",
 )
 
 _lib = None
@@ -268,5 +283,10 @@ def load() -> C.CDLL:
     lib.fgb_unpack_bam4_device.restype = C.c_int32
     lib.fgb_submit_ex.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), C.POINTER(FgbSubmitOptions)]
     lib.fgb_submit_ex.restype = C.c_int32
+    lib.fgb_filter_simplex_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns),
+                                              C.POINTER(FgbFilterParams), vp, vp, vp]
+    lib.fgb_filter_simplex_device.restype = C.c_int32
+    lib.fgb_struct_size.argtypes = [C.c_uint32]
+    lib.fgb_struct_size.restype = C.c_uint32
     _lib = lib
     return lib

@@ -134,7 +134,10 @@ enum {
   FGB_CTR_DUPLEX_BASES = 5,     /* codec_caller.rs:1157 consensus_duplex_bases_emitted        */
   FGB_CTR_DUPLEX_DISAGREE = 6,  /* codec_caller.rs:1158 duplex_disagreement_base_count        */
   FGB_CTR_COMBINED = 7,         /* strand-combine jobs processed                              */
-  FGB_NCOUNTERS = 8
+  FGB_CTR_FILTER_RECORDS = 8,   /* consensus reads seen by the filter epilogue                */
+  FGB_CTR_FILTER_PASSED = 9,    /* ... that passed every read-level gate                      */
+  FGB_CTR_FILTER_BASES_MASKED = 10, /* bases newly masked to N by the filter                  */
+  FGB_NCOUNTERS = 12
 };
 
 /* ---- lifecycle ------------------------------------------------------------------------ */
@@ -241,12 +244,44 @@ fgb_status fgb_submit_bam4(fgb_handle* h, const fgb_batch* in, const fgb_raw_col
  * out->errors are treated as uint8_t columns of n_out elements (cast the pointers): the link then
  * carries 4 instead of 6 bytes per consensus position.  Allowed only when no unit has more than
  * 255 reads (FGB_ERR_INVALID_ARG otherwise); the record builder widens to i16 for the cd/ce tags. */
+/* ---- consensus filter epilogue (single-strand reads) ----------------------------------------
+ * What `fgumi filter` applies to a simplex consensus read, run on the columns right after the vote:
+ * mask_bases (filter.rs:655-696), filter_read on the cD / cE the caller derives (filter.rs:453-471,
+ * caller.rs:322-329), then the mean-quality and no-call gates (commands/filter.rs:909-929). */
+typedef struct fgb_filter_params {      /* FilterThresholds (filter.rs:31-40) + command options   */
+  uint32_t min_reads;                   /* -M: per-base depth gate and per-read cD gate            */
+  int32_t min_base_quality;             /* -N; -1 = none                                           */
+  double max_read_error_rate;           /* -E                                                      */
+  double max_base_error_rate;           /* -e                                                      */
+  double min_mean_base_quality;         /* -q; negative = none                                     */
+  double max_no_call_fraction;          /* -n; >= 1.0 is an absolute count (commands/filter.rs:921) */
+  uint8_t per_base_tags;                /* 0: the read would carry no cd/ce arrays, so every base
+                                           has depth 0 for the mask (filter.rs:677)               */
+  uint8_t reserved[7];
+} fgb_filter_params;
+enum {                                  /* per-unit result                                         */
+  FGB_FILTER_PASS = 0,
+  FGB_FILTER_INSUFFICIENT_READS = 1,    /* FilterResult::InsufficientReads                         */
+  FGB_FILTER_EXCESSIVE_ERROR_RATE = 2,  /* FilterResult::ExcessiveErrorRate                        */
+  FGB_FILTER_LOW_MEAN_QUALITY = 3,
+  FGB_FILTER_TOO_MANY_NO_CALLS = 4,
+  FGB_FILTER_NO_RECORD = 255            /* unit without a consensus read (cons_len 0)              */
+};
+/* Device-resident form: masks `cols` in place for the units of `in`, writes one status byte (and
+ * optionally the newly-masked count) per unit.  All pointers are device pointers. */
+fgb_status fgb_filter_simplex_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* cols,
+                                     const fgb_filter_params* fp, uint8_t* unit_status,
+                                     uint32_t* unit_masked, void* stream);
+
 enum { FGB_IN_BYTES = 0, FGB_IN_PACK8 = 1, FGB_IN_BAM4 = 2 };
 enum { FGB_OUT_U16 = 0, FGB_OUT_U8 = 1 };
 typedef struct fgb_submit_options {
   uint32_t input_format;           /* FGB_IN_*  */
   uint32_t output_format;          /* FGB_OUT_* */
   const fgb_raw_columns* raw;      /* FGB_IN_BAM4 only */
+  const fgb_filter_params* filter; /* non-NULL: run the filter epilogue before the copy back      */
+  uint8_t* unit_status;            /* host, n_units bytes (required with `filter`)                */
+  uint32_t* unit_masked;           /* host, n_units words, may be NULL                            */
 } fgb_submit_options;
 fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out,
                          const fgb_submit_options* opt);
@@ -387,6 +422,12 @@ typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanill
   uint32_t min_duplex_length;              /* 1 */
   uint32_t reserved1;
   fgb_codec_params codec;                  /* single_strand_qual / outer_bases_* / disagreement gates */
+  /* simplex only: `fgumi simplex | fgumi filter` in one pass (template mode, commands/filter.rs:
+   * 614-697): consensus reads are masked on the device and a template -- the fragment / R1 / R2
+   * reads of one MI -- is emitted only if all of its reads pass. */
+  uint8_t filter_enabled;
+  uint8_t reserved2[7];
+  fgb_filter_params filter;                /* filter.per_base_tags is set from produce_per_base_tags */
 } fgb_caller_options;
 
 enum {   /* ConsensusCallingStats (caller.rs:238-286) as a flat counter array                      */
@@ -408,6 +449,9 @@ enum {   /* ConsensusCallingStats (caller.rs:238-286) as a flat counter array   
   FGB_STAT_OVERLAP_AGREEING = 15,
   FGB_STAT_OVERLAP_DISAGREEING = 16,
   FGB_STAT_OVERLAP_CORRECTED = 17,
+  FGB_STAT_FILTER_RECORDS = 18,               /* consensus reads seen by the filter               */
+  FGB_STAT_FILTER_PASSED = 19,                /* reads emitted (whole templates that passed)      */
+  FGB_STAT_FILTER_BASES_MASKED = 20,
   FGB_NSTATS = 24
 };
 
@@ -435,6 +479,11 @@ fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uin
 fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* out_len,
                             uint64_t* out_count);
 fgb_status fgb_caller_stats(const fgb_caller* c, uint64_t stats[FGB_NSTATS]);
+
+/* sizeof() of the ABI structs as this library was compiled, so a binding can check its own layout:
+ * 0 fgb_caller_options, 1 fgb_filter_params, 2 fgb_submit_options, 3 fgb_raw_columns,
+ * 4 fgb_raw_read, 5 fgb_batch, 6 fgb_codec_params, 7 fgb_params; 0 for an unknown id. */
+uint32_t fgb_struct_size(uint32_t id);
 
 #ifdef __cplusplus
 }

@@ -1445,3 +1445,142 @@ class OverlappingOracle:
         for i1, i2 in pairs.values():
             if i1 is not None and i2 is not None:
                 self.call(records[i1], records[i2])
+
+
+# =================================================================================================
+# Consensus filter (crates/fgumi-consensus/src/filter.rs + src/lib/commands/filter.rs), simplex reads
+# =================================================================================================
+def _aux_tags(aux: bytes):
+    """Walk BAM aux data -> {tag: (type, value)}; B arrays -> (subtype, [values])."""
+    out, p = {}, 0
+    fixed = {"A": ("<c", 1), "c": ("<b", 1), "C": ("<B", 1), "s": ("<h", 2), "S": ("<H", 2),
+             "i": ("<i", 4), "I": ("<I", 4), "f": ("<f", 4)}
+    while p + 3 <= len(aux):
+        tag, vt = bytes(aux[p:p + 2]), chr(aux[p + 2])
+        p += 3
+        if vt in fixed:
+            fmt, n = fixed[vt]
+            out[tag] = (vt, struct.unpack_from(fmt, aux, p)[0])
+            p += n
+        elif vt in "ZH":
+            e = aux.index(b"\0", p)
+            out[tag] = (vt, bytes(aux[p:e]))
+            p = e + 1
+        elif vt == "B":
+            st = chr(aux[p])
+            (cnt,) = struct.unpack_from("<I", aux, p + 1)
+            fmt, n = fixed[st]
+            out[tag] = ("B" + st, list(struct.unpack_from("<%d%s" % (cnt, fmt[1]), aux, p + 5)))
+            p += 5 + cnt * n
+        else:
+            break
+    return out
+
+
+@dataclass
+class FilterThresholds:                                  # filter.rs:31-40
+    min_reads: int = 1
+    max_read_error_rate: float = 1.0
+    max_base_error_rate: float = 1.0
+
+
+FILTER_PASS, FILTER_INSUFFICIENT_READS, FILTER_EXCESSIVE_ERROR_RATE = 0, 1, 2
+
+
+def filter_read(aux: bytes, th: FilterThresholds) -> int:          # filter.rs:453-471
+    tags = _aux_tags(aux)
+    cd = tags.get(b"cD")
+    if cd is not None and cd[0] in "cCsSiI" and cd[1] < th.min_reads:
+        return FILTER_INSUFFICIENT_READS
+    ce = tags.get(b"cE")
+    if ce is not None and ce[0] == "f" and float(np.float32(ce[1])) > th.max_read_error_rate:
+        return FILTER_EXCESSIVE_ERROR_RATE
+    return FILTER_PASS
+
+
+def compute_read_stats(rec: bytes) -> Tuple[int, float]:            # filter.rs:565-590
+    r = Rec(bytes(rec))
+    seq, q = r.sequence(), r.quals()
+    n_count = sum(1 for b in seq if b == ord("N"))
+    qs = sum(int(x) for b, x in zip(seq, q) if b != ord("N"))
+    non_n = len(seq) - n_count
+    return n_count, (qs / non_n if non_n else 0.0)
+
+
+def mask_bases(rec: bytearray, th: FilterThresholds, min_base_quality: Optional[int]) -> int:   # filter.rs:655-696
+    r = Rec(bytes(rec))
+    tags = _aux_tags(r.aux())
+    cd = tags.get(b"cd")
+    ce = tags.get(b"ce")
+    cdv = [v & 0xFFFF for v in cd[1]] if cd is not None and cd[0].startswith("B") else None   # array_tag_to_vec_u16
+    cev = [v & 0xFFFF for v in ce[1]] if ce is not None and ce[0].startswith("B") else None
+    so = r.seq_offset()
+    qo = so + (r.l_seq + 1) // 2
+    seq = r.sequence()
+    masked = 0
+    for i in range(r.l_seq):
+        depth = cdv[i] if cdv is not None and i < len(cdv) else 0
+        errors = cev[i] if cev is not None and i < len(cev) else 0
+        qual = rec[qo + i]
+        should = ((min_base_quality is not None and qual < min_base_quality) or depth < th.min_reads or
+                  (depth > 0 and (float(errors) / float(depth)) > th.max_base_error_rate))
+        if should:
+            if seq[i] != ord("N"):
+                masked += 1
+            _set_base(rec, so, i, ord("N"))                 # mask_base: nibble 15
+            rec[qo + i] = 2
+    return masked
+
+
+def check_no_call_and_quality(rec: bytes, min_mean_qual: Optional[float], max_no_call_frac: float) -> bool:
+    """commands/filter.rs:909-929"""
+    no_calls, mean_q = compute_read_stats(rec)
+    if min_mean_qual is not None and mean_q < min_mean_qual:
+        return False
+    n = Rec(bytes(rec)).l_seq
+    if max_no_call_frac >= 1.0:
+        return float(no_calls) <= max_no_call_frac
+    frac = no_calls / n if n > 0 else 0.0
+    return frac <= max_no_call_frac
+
+
+class SimplexFilterOracle:
+    """`fgumi filter` on single-strand consensus records, template mode
+    (commands/filter.rs:614-697, 738-905): mask bases, then read-level checks; a template (records
+    sharing a name, consecutive) is kept only if all of its primary records pass."""
+
+    def __init__(self, th: FilterThresholds, min_base_quality: Optional[int] = None,
+                 min_mean_base_quality: Optional[float] = None, max_no_call_fraction: float = 0.2):
+        self.th, self.min_bq = th, min_base_quality
+        self.min_mean, self.max_nc = min_mean_base_quality, max_no_call_fraction
+        self.total = self.passed = self.bases_masked = 0
+
+    def process_record(self, rec: bytearray) -> bool:
+        self.bases_masked += mask_bases(rec, self.th, self.min_bq)
+        if filter_read(Rec(bytes(rec)).aux(), self.th) != FILTER_PASS:
+            return False
+        return check_no_call_and_quality(bytes(rec), self.min_mean, self.max_nc)
+
+    def filter_stream(self, data: bytes) -> Tuple[bytes, int]:
+        recs, p = [], 0
+        while p < len(data):
+            (n,) = struct.unpack_from("<I", data, p)
+            recs.append(bytearray(data[p + 4:p + 4 + n]))
+            p += 4 + n
+        out, kept, i = bytearray(), 0, 0
+        while i < len(recs):
+            j = i
+            name = Rec(bytes(recs[i])).name
+            while j < len(recs) and Rec(bytes(recs[j])).name == name:
+                j += 1
+            passes = []
+            for k in range(i, j):
+                self.total += 1
+                passes.append(self.process_record(recs[k]))
+            if all(passes):                                  # all records here are primary
+                for k in range(i, j):
+                    out += with_block_size(bytes(recs[k]))
+                    kept += 1
+                    self.passed += 1
+            i = j
+        return bytes(out), kept

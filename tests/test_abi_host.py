@@ -40,6 +40,12 @@ def test_struct_sizes_match_header(fg):
     assert C.sizeof(l.FgbParams) == 8
     assert C.sizeof(l.FgbDuplexJob) == 16 and C.sizeof(l.FgbCodecJob) == 32
     assert C.sizeof(l.FgbCodecParams) == 24
+    lib = l.load()
+    for i, t in enumerate((l.FgbCallerOptions, l.FgbFilterParams, l.FgbSubmitOptions, l.FgbRawColumns,
+                           None, l.FgbBatch, l.FgbCodecParams, l.FgbParams)):
+        if t is not None:
+            assert lib.fgb_struct_size(i) == C.sizeof(t), (i, t)
+    assert lib.fgb_struct_size(4) == 16 and lib.fgb_struct_size(99) == 0
 
 
 @pytest.mark.parametrize("pre,post", [(45, 40), (50, 50), (93, 93), (93, 10), (30, 20), (10, 45)])
