@@ -1,0 +1,92 @@
+"""Device-resident throughput of the duplex (K1 + K2) and CODEC (K1 + K3) pipelines at BASELINE sizes
+(configs 3 and 4), with algorithmic bytes per SURVEY §8d.  Reference numbers for DESIGN.md; the
+driver's bench line stays the simplex config.  usage: python scripts/bench_modes.py [scale]"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import fgumi_b200 as fg
+from fgumi_b200 import synth
+
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+DEV, L = "cuda:0", 150
+Lo = (L + 7) // 8 * 8
+peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+
+
+def timed(fn, n=8):
+    fn(); torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record()
+    for i in range(n):
+        fn(); ev[i + 1].record()
+    torch.cuda.synchronize()
+    return float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(n)]))
+
+
+def duplex():
+    M = int(5_000_000 * scale); U = 4 * M
+    depths = np.full(U, 4, dtype=np.int64)
+    m = np.arange(M, dtype=np.int64)
+    tid = np.empty(U, dtype=np.int64)
+    tid[0::4], tid[3::4], tid[1::4], tid[2::4] = 2 * m, 2 * m, 2 * m + 1, 2 * m + 1
+    tb = synth.device_batch(torch, DEV, depths, L, 1e-3, seed=43, template_ids=tid)
+    eng = fg.Engine(0, 45, 40, 1, 2)
+    ss = fg.DeviceColumns(tb.host.n_out, DEV)
+    jobs = np.zeros(2 * M, dtype=fg.DUPLEX_JOB_DTYPE)
+    jobs["unit_a"][0::2], jobs["unit_b"][0::2] = 4 * m, 4 * m + 3
+    jobs["unit_a"][1::2], jobs["unit_b"][1::2] = 4 * m + 1, 4 * m + 2
+    jobs["out_off"] = np.arange(2 * M, dtype=np.uint64) * np.uint64(Lo)
+    tj = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(DEV)
+    n_out = 2 * M * Lo
+    ob = torch.zeros(n_out, dtype=torch.uint8, device=DEV); oq = torch.zeros_like(ob)
+    oe = torch.zeros(n_out, dtype=torch.int16, device=DEV)
+    st = torch.zeros(2 * M, dtype=torch.uint8, device=DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    t1 = timed(lambda: eng.vote_device(tb, ss, s))
+    t2 = timed(lambda: eng.duplex_combine_device(tb, ss, tj, 2 * M, ob, oq, oe, st, s))
+    k1_bytes = U * (2 * 4 * L + 6 * L + 8 * 5 + 8)
+    k2_bytes = 2 * M * (2 * 6 * L + 4 * L + 2 * 8 * L + 16)     # 2 SS columns in, (base, qual, errors) out, 8 source rows re-read
+    eng.close()
+    return {"molecules": M, "k1_ms": t1, "k2_ms": t2, "molecules_per_s": M / ((t1 + t2) * 1e-3),
+            "k1_gbs": k1_bytes / t1 / 1e6, "k2_gbs": k2_bytes / t2 / 1e6,
+            "k1_frac": k1_bytes / t1 / 1e6 / peak, "k2_frac": k2_bytes / t2 / 1e6 / peak}
+
+
+def codec():
+    M = int(2_000_000 * scale)
+    rng = np.random.default_rng(44)
+    k = rng.integers(2, 21, size=M)
+    depths = np.repeat(k, 2).astype(np.int64)
+    tb = synth.device_batch(torch, DEV, depths, L, 1e-3, seed=44)
+    eng = fg.Engine(0, 45, 40, 1, 0)
+    ss = fg.DeviceColumns(tb.host.n_out, DEV)
+    insert = np.clip(np.round(rng.normal(300, 50, size=M)), L, 2 * L).astype(np.int64)
+    Lc_pad = (insert + 7) // 8 * 8
+    jobs = np.zeros(M, dtype=fg.CODEC_JOB_DTYPE)
+    r1n = rng.random(M) < 0.5
+    jobs["unit_a"], jobs["unit_b"] = 2 * np.arange(M), 2 * np.arange(M) + 1
+    jobs["out_off"][1:] = np.cumsum(Lc_pad)[:-1]
+    jobs["len"] = insert
+    jobs["rc_a"], jobs["rc_b"], jobs["rc_out"] = r1n, ~r1n, r1n
+    jobs["pad_a_left"] = np.where(r1n, insert - L, 0)
+    jobs["pad_b_left"] = np.where(~r1n, insert - L, 0)
+    tj = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(DEV)
+    out = fg.DeviceColumns(int(Lc_pad.sum()), DEV)
+    st = torch.zeros(M, dtype=torch.uint8, device=DEV)
+    dis = torch.zeros(M, dtype=torch.int32, device=DEV); dup = torch.zeros_like(dis)
+    cp = fg.lib.FgbCodecParams(-1, -1, 5, 0xFFFFFFFF, 1.0)
+    s = torch.cuda.current_stream().cuda_stream
+    t1 = timed(lambda: eng.vote_device(tb, ss, s))
+    t3 = timed(lambda: eng.codec_combine_device(tb, ss, tj, M, cp, out, st, dis, dup, s))
+    R = int(depths.sum())
+    k1_bytes = R * 2 * L + 2 * M * 6 * L + 8 * (R + 2 * M) + 16 * M
+    k3_bytes = M * 2 * 6 * L + int(insert.sum()) * 6 + 32 * M
+    eng.close()
+    return {"molecules": M, "k1_ms": t1, "k3_ms": t3, "molecules_per_s": M / ((t1 + t3) * 1e-3),
+            "k1_gbs": k1_bytes / t1 / 1e6, "k3_gbs": k3_bytes / t3 / 1e6,
+            "k1_frac": k1_bytes / t1 / 1e6 / peak, "k3_frac": k3_bytes / t3 / 1e6 / peak}
+
+
+print(json.dumps({"duplex_config3": duplex()}))
+torch.cuda.empty_cache()
+print(json.dumps({"codec_config4": codec()}))
