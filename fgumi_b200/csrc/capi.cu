@@ -201,6 +201,7 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   std::memcpy(dt.dfix, h->host_tables.dfix, sizeof(dt.dfix));
   dt.g2fix = h->host_tables.g2fix;
   dt.nmax2 = h->host_tables.nmax2;
+  std::memcpy(dt.pair_q, h->host_tables.pair_q, sizeof(dt.pair_q));
   if ((e = cudaMemcpy(h->d_tables, &dt, sizeof(dt), cudaMemcpyHostToDevice)) != cudaSuccess)
     return fail(e, "cudaMemcpy tables");
   if ((e = cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * FGB_NCOUNTERS)) != cudaSuccess)

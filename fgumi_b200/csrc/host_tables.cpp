@@ -25,6 +25,39 @@ unsigned host_ln_prob_to_phred(double ln_prob) {  // phred.rs:119-135
   return static_cast<unsigned>(p);
 }
 
+namespace {
+// base_builder.rs:295-458 for two observations of base index 0 with qualities q1, q2 (in that
+// order): the 4-lane Kahan accumulation, the unanimous fast path and the full call().
+unsigned pair_quality(const HostTables& t, unsigned q1, unsigned q2) {
+  double ll[4] = {0.0, 0.0, 0.0, 0.0}, kc[4] = {0.0, 0.0, 0.0, 0.0};
+  const unsigned qs[2] = {q1, q2};
+  for (unsigned q : qs) {
+    for (int i = 0; i < 4; ++i) {                       // :312-324
+      const double v = i == 0 ? t.correct[q] : t.err_alt[q];
+      const double y = v - kc[i];
+      const double s = ll[i] + y;
+      kc[i] = (s - ll[i]) - y;
+      ll[i] = s;
+    }
+  }
+  if (ll[0] - ll[1] > 23.0) return t.fast_qual;         // :338-379 (one observed base)
+  const double ln_sum = ln_add_array4(ll);              // :401-457
+  double mx = -std::numeric_limits<double>::infinity();
+  int mi = -1;
+  bool tie = false;
+  for (int i = 0; i < 4; ++i) {
+    const double v = ll[i];
+    if (v > mx) { mx = v; mi = i; tie = false; }
+    else if (v == mx) tie = true;
+    else if (v < mx && std::fabs(v - mx) <= DBL_EPSILON) tie = true;
+  }
+  if (tie || mi != 0) return 255;                       // cannot happen for finite tables; be literal
+  const double post = mx - ln_sum;
+  const double err = ln_1m_exp(post);
+  return host_ln_prob_to_phred(two_trials(t.ln_pre, err));
+}
+}  // namespace
+
 void build_host_tables(unsigned pre, unsigned post, HostTables* t) {
   const double ln_post = ln_err_of_phred(post);
   const double ln3 = std::log(3.0);
@@ -42,6 +75,11 @@ void build_host_tables(unsigned pre, unsigned post, HostTables* t) {
     t->single_q[q] = static_cast<uint8_t>(v > 93 ? 93 : v);
   }
   t->single_q[94] = t->single_q[95] = 0;
+
+  for (unsigned q1 = 0; q1 < 94; ++q1)
+    for (unsigned q2 = 0; q2 < 94; ++q2)
+      t->pair_q[q1 * 94 + q2] =
+          (q1 == 0 || q2 == 0) ? 255 : static_cast<uint8_t>(pair_quality(*t, q1, q2));
 
   // ---- Proof tables (DESIGN.md "exactness") ------------------------------------------------------
   // Let D[q] = correct[q] - err_alt[q] and, for one position, S_b = sum of D[q_i] over the

@@ -16,6 +16,10 @@ struct HostTables {
   int32_t g2fix;         // ceil(G2 * 65536)
   uint32_t nmax2;        // proof valid for pileups of at most this many observations (0 = off)
   double g2;             // G2 in nats
+  // Unanimous two-read pileups: pair_q[q1 * 94 + q2] = the quality base_builder's add/add/call
+  // sequence yields for two observations of one base with qualities q1 then q2 (before the
+  // min-consensus-quality threshold); 255 = not tabulated (quality 0), evaluate literally.
+  uint8_t pair_q[94 * 94];
 };
 
 void build_host_tables(unsigned pre, unsigned post, HostTables* t);

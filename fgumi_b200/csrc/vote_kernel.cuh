@@ -44,6 +44,7 @@ struct DeviceTables {
   int32_t dfix[96];             // fixed-point likelihood gaps (host_tables.cpp), INT32_MIN = unusable
   int32_t g2fix;                // dominant-winner threshold, fixed point
   uint32_t nmax2;               // dominant-winner proof valid up to this many observations
+  uint8_t pair_q[94 * 94];      // unanimous two-read pileups: quality by (q1, q2); 255 = literal path
 };
 
 struct VoteArgs {
@@ -87,6 +88,7 @@ struct __align__(128) VoteSmem {
   int32_t dfix[96];
   int32_t g2fix;
   uint32_t nmax2;
+  const uint8_t* pair_q;        // DeviceTables::pair_q (global memory, L1-resident)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -206,11 +208,43 @@ struct Called {
 };
 
 // The literal per-position algorithm (vanilla_caller.rs:1319-1355 + base_builder.rs:295-458).
+//
+// Two-read units take a shortcut first: when both reads cover the position, agree on an A/C/G/T base
+// and have tabulated qualities, the result is the host-evaluated outcome of the reference's
+// add/add/call sequence (host_tables.cpp pair_quality).  Shallow pileups rarely reach the
+// dominant-winner gap, so without the table every position of a two-read unit would run the f64
+// path.  The shortcut lives here, out of line, so the vote loop's register allocation is untouched.
+// Bit 31 of the returned depth flags a result of the f64 algorithm (diagnostic counter).
+constexpr uint32_t kLiteralFlag = 0x80000000u;
+
 template <class M>
 __device__ __noinline__ Called exact_position(const TileView<M>& tv, const VoteSmem& S,
                                               uint32_t read_begin, uint32_t n_reads,
                                               uint32_t pos, uint32_t min_reads,
                                               uint32_t min_cons_q, uint32_t fast_qual) {
+  if (n_reads == 2u) {
+    const uint64_t d0 = M::ld64(tv.reads + static_cast<typename M::off_t>(read_begin - tv.read_base) * 8u);
+    const uint64_t d1 = M::ld64(tv.reads + static_cast<typename M::off_t>(read_begin - tv.read_base + 1u) * 8u);
+    if (pos < (static_cast<uint32_t>(d0) & 0xFFFFu) && pos < (static_cast<uint32_t>(d1) & 0xFFFFu)) {
+      const typename M::off_t r0 = static_cast<typename M::off_t>((d0 >> 16) - tv.byte_base) + pos;
+      const typename M::off_t r1 = static_cast<typename M::off_t>((d1 >> 16) - tv.byte_base) + pos;
+      const uint32_t i0 = base_to_index(M::ld8(tv.bases + r0));
+      if (i0 < 4u && i0 == base_to_index(M::ld8(tv.bases + r1))) {
+        uint32_t qa = M::ld8(tv.quals + r0), qb = M::ld8(tv.quals + r1);
+        qa = qa > FGB_MAX_PHRED ? FGB_MAX_PHRED : qa;
+        qb = qb > FGB_MAX_PHRED ? FGB_MAX_PHRED : qb;
+        const uint32_t cq = __ldg(S.pair_q + qa * 94u + qb);
+        if (cq != 255u) {
+          Called o;
+          o.depth = 2; o.errors = 0;
+          if (2u < min_reads) { o.base = 'N'; o.qual = 0; }                 // vanilla_caller.rs:1345-1349
+          else if (cq < min_cons_q) { o.base = 'N'; o.qual = 2; }
+          else { o.base = (0x54474341u >> (8u * i0)) & 0xFFu; o.qual = cq; }
+          return o;
+        }
+      }
+    }
+  }
   double ll[4] = {0.0, 0.0, 0.0, 0.0};   // LN_ONE
   double kc[4] = {0.0, 0.0, 0.0, 0.0};   // Kahan compensations
   uint64_t cnt = 0;                      // 4 x u16 observation counters
@@ -280,7 +314,7 @@ __device__ __noinline__ Called exact_position(const TileView<M>& tv, const VoteS
     }
   }
   Called out;
-  out.depth = depth;
+  out.depth = depth | kLiteralFlag;
   out.errors = (depth - nobs_call) & 0xFFFFu;                 // vanilla_caller.rs:1341
   if (depth < min_reads) { out.base = 'N'; out.qual = 0; }    // :1345-1346
   else if (cqual < min_cons_q) { out.base = 'N'; out.qual = 2; }  // :1347-1348
@@ -383,7 +417,8 @@ __device__ __forceinline__ Called resolve_position(const TileView<M>& tv, const 
   Called c;
   if (!dominant_position<M>(tv, S, rb, n, pos, a.min_reads, a.min_cons_q, a.fast_qual, c)) {
     c = exact_position<M>(tv, S, rb, n, pos, a.min_reads, a.min_cons_q, a.fast_qual);
-    ls.exact++;
+    ls.exact += c.depth >> 31;
+    c.depth &= ~kLiteralFlag;
   }
   ls.nocall += (c.base == 'N');
   return c;
@@ -478,7 +513,8 @@ __device__ __forceinline__ void slow_pass_g(const VoteArgs& a, const VoteSmem& S
       }
       if (!done) {
         c = exact_position<M>(tv, S, rb, n, pos, a.min_reads, a.min_cons_q, a.fast_qual);
-        ls.exact++;
+        ls.exact += c.depth >> 31;
+        c.depth &= ~kLiteralFlag;
       }
       ls.nocall += (c.base == 'N');
       write_called(a, out_off + pos, c);
@@ -751,6 +787,7 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteArgs a) {
     S.ln_pre = a.tables->ln_pre;
     S.g2fix = a.tables->g2fix;
     S.nmax2 = a.tables->nmax2;
+    S.pair_q = a.tables->pair_q;
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&S.full[s], 1);                 // producer's arrive.expect_tx
       mbar_init(&S.empty[s], kConsumerWarps);   // one arrival per consumer warp

@@ -87,6 +87,54 @@ def codec():
             "k1_frac": k1_bytes / t1 / 1e6 / peak, "k3_frac": k3_bytes / t3 / 1e6 / peak}
 
 
+def aux_kernels():
+    """K0 (PACK8 / BAM4 unpack) and K4 (filter epilogue) on 4 M depth-8 families, device resident."""
+    import ctypes as C
+    U = int(4_000_000 * scale)
+    depths = np.full(U, 8, dtype=np.int64)
+    tb = synth.device_batch(torch, DEV, depths, L, 1e-3, seed=42)
+    eng = fg.Engine(0, 45, 40, 1, 2)
+    lib = eng._lib
+    out = fg.DeviceColumns(tb.host.n_out, DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    eng.vote_device(tb, out, s)
+    nb = tb.host.n_bytes
+    # BAM4: treat the generated rows as forward-strand raw reads
+    nibtab = torch.full((256,), 15, dtype=torch.uint8, device=DEV)
+    for i, ch in enumerate(b"=ACMGRSVTWYHKDBN"):
+        nibtab[ch] = i
+    nib = nibtab[tb.bases[:nb].long()]
+    seq4 = ((nib[0::2] << 4) | nib[1::2]).contiguous()
+    R = tb.host.n_reads
+    rr = np.zeros(R + 1, dtype=fg.RAW_READ_DTYPE)
+    rr["src_off"][:R] = np.arange(R, dtype=np.uint64) * np.uint64(Lo)
+    rr["raw_len"][:R] = L
+    rrd = torch.from_numpy(rr.view(np.uint8).reshape(-1)).to(DEV)
+    b2 = torch.zeros(nb + 64, dtype=torch.uint8, device=DEV); q2 = torch.zeros_like(b2)
+    raw = fg.lib.FgbRawColumns(nb, seq4.data_ptr(), tb.quals.data_ptr(), rrd.data_ptr(), 10)
+    bs = tb.struct()
+    def bam4():
+        assert lib.fgb_unpack_bam4_device(eng._h, C.byref(bs), C.byref(raw), C.c_void_p(b2.data_ptr()),
+                                          C.c_void_p(q2.data_ptr()), C.c_void_p(s)) == 0
+    t_b4 = timed(bam4)
+    assert torch.equal(b2[:nb].view(-1, Lo)[:, :L], tb.bases[:nb].view(-1, Lo)[:, :L])
+    b4_bytes = R * (L // 2 + L + 16 + 8 + 2 * L)
+    # K4 on the voted columns
+    fp = fg.lib.FgbFilterParams(2, 20, 0.05, 0.2, 30.0, 0.2, 1)
+    status = torch.zeros(U, dtype=torch.uint8, device=DEV)
+    cs = out.struct()
+    def filt():
+        assert lib.fgb_filter_simplex_device(eng._h, C.byref(bs), C.byref(cs), C.byref(fp),
+                                             C.c_void_p(status.data_ptr()), None, C.c_void_p(s)) == 0
+    t_f = timed(filt)
+    f_bytes = U * (6 * L + 16 + 1)        # read 4 columns, (masked positions are rare) + status
+    eng.close()
+    return {"units": U, "bam4_ms": t_b4, "bam4_gbs": b4_bytes / t_b4 / 1e6, "bam4_frac": b4_bytes / t_b4 / 1e6 / peak,
+            "filter_ms": t_f, "filter_gbs": f_bytes / t_f / 1e6, "filter_frac": f_bytes / t_f / 1e6 / peak}
+
+
+print(json.dumps({"aux_kernels": aux_kernels()}))
+torch.cuda.empty_cache()
 print(json.dumps({"duplex_config3": duplex()}))
 torch.cuda.empty_cache()
 print(json.dumps({"codec_config4": codec()}))
