@@ -298,7 +298,7 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
         cur.flags |= kTileFlagRegular;
         if (FGB_READ_OFF(reads[cur.read_begin]) != cur.byte_begin) cur.flags |= kTileFlagSkew8;
       }
-      if (max_reads_in_unit <= 8) cur.flags |= kTileFlagShallow;
+      if (max_reads_in_unit <= 64) cur.flags |= kTileFlagShallow;
     }
     if (out && nt < cap) out[nt] = cur;
     ++nt;

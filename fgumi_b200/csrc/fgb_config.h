@@ -20,7 +20,7 @@ constexpr uint32_t kTileFlagDirect = 1u;   // unit too large for a stage: kernel
 constexpr uint32_t kTileFlagRegular = 2u;  // all reads one length L, rows back to back at stride
                                            // round_up(L,8), every unit calls L positions (L > 8)
 constexpr uint32_t kTileFlagSkew8 = 4u;    // regular tiles: first row starts 8 bytes into the stage
-constexpr uint32_t kTileFlagShallow = 8u;  // no unit of the tile has more than 8 reads
+constexpr uint32_t kTileFlagShallow = 8u;  // no unit of the tile has more than 64 reads
 // bits 8..31: items (8-position words) per unit when uniform over the tile (2..4096), else 0
 
 }  // namespace fgb

@@ -522,8 +522,9 @@ __device__ __forceinline__ void slow_pass_g(const VoteArgs& a, const VoteSmem& S
   }
 }
 
-// Group width (warp-uniform): 8 lanes per position when no queued pileup is deeper than 8 reads
-// (the planner's shallow-tile hint answers that without looking), else the whole warp.
+// Group width (warp-uniform): 8 lanes per position (each lane strides the depth axis by 8) when no
+// queued pileup is deeper than 64 reads -- the planner's shallow-tile hint answers that without
+// looking -- else the whole warp per position.
 template <class M>
 __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, const Stage& st,
                                           const TileView<M>& tv, const uint32_t* wqueue, uint32_t qn,
@@ -541,7 +542,7 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
       uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, nmax, off);
       nmax = o > nmax ? o : nmax;
     }
-    shallow = nmax <= 8u;
+    shallow = nmax <= 64u;
   }
   if (shallow) slow_pass_g<M, 8u>(a, S, st, tv, wqueue, qn, lane, ls);
   else slow_pass_g<M, 32u>(a, S, st, tv, wqueue, qn, lane, ls);
