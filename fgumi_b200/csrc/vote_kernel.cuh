@@ -207,6 +207,67 @@ struct Called {
   uint32_t base, qual, depth, errors;
 };
 
+// Certified single-precision evaluation of the call() tail (base_builder.rs:433-457) for a position
+// with a unique winner.  With d_b = ll[b] - ll[w] (exact f64 differences, then rounded to f32) the
+// posterior error is s / (1 + s), s = sum_b e^(d_b): every term is positive, so there is no
+// cancellation and OUR value of s carries < 1e-4 relative error (argument rounding, exp/log
+// approximation).  The REFERENCE's value does not: it forms ln_sum by folding `x + exp(-x)` terms
+// (phred.rs:148-158, 307-330) and subtracts, which leaves an absolute rounding noise of a few
+// ulp(max |ll|) on s -- negligible for s >= 1e-9, a percent at s ~ 1e-12 (reachable with a pre-UMI
+// error rate near Q93).  So the tail is evaluated at both ends of the interval that contains the
+// reference's s, and the result is accepted only if both ends take the same branch of
+// ln_error_prob_two_trials (its `p1 - p2 >= 6` shortcut, phred.rs:238, is a discontinuity) and floor
+// to the same quality (phred.rs:126) with 2e-3 phred to spare.  Anything else -- and any non-finite
+// likelihood -- is left to the literal f64 tail, which replays the reference's operations exactly.
+__device__ __forceinline__ bool tail_phred(float err, float lp, float* x, int* branch) {
+  const float p1 = fmaxf(lp, err), p2 = fminf(lp, err);
+  const float diff = p1 - p2;
+  if (!(fabsf(diff - 6.0f) > 2.0e-3f)) return false;      // too close to the shortcut (or NaN)
+  float fin;
+  if (diff >= 6.0f) {
+    if (p1 == lp) { *branch = 0; *x = 0.0f; return true; }   // ln_pre passes through: phred(ln_pre)
+    *branch = 1; fin = err;
+  } else {
+    *branch = 2; fin = p1 + log1pf(__expf(p2 - p1) - 1.3333334f * __expf(p2));
+  }
+  *x = fin * -4.3429446f + 0.001f;                         // -10 / ln(10)
+  return *x == *x;
+}
+__device__ __forceinline__ float clamp_floor_phred(float x) {
+  return x >= 94.0f ? 93.0f : (x < 2.0f ? 2.0f : floorf(x));
+}
+__device__ __forceinline__ bool certified_quality(const double (&ll)[4], int mi, double mx, double ln_pre,
+                                                  uint32_t fast_qual, uint32_t* q_out) {
+  float s = 0.0f;
+  double maxabs = fabs(mx);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i == mi) continue;
+    const double d = __dsub_rn(ll[i], mx);
+    // a -inf likelihood (quality-0 observation) makes the reference's ln_sum_exp_array return -inf
+    // outright (phred.rs:318-320): that quirk, and NaN, belong to the literal tail
+    if (!(d <= 0.0) || !(d > -1.0e300)) return false;
+    maxabs = fmax(maxabs, fabs(ll[i]));
+    if (d > -100.0) s += __expf(static_cast<float>(d));
+  }
+  if (!(maxabs < 1.0e300)) return false;
+  const float lp = static_cast<float>(ln_pre);
+  const float noise = static_cast<float>(maxabs * 1.8e-15);   // 8 ulp(max |ll|) on the reference's s
+  const float s_hi = (s + noise) * 1.0001f;
+  const float s_lo = fmaxf(s - noise, 0.0f) * 0.9999f;
+  float x_lo, x_hi;
+  int b_lo, b_hi;
+  if (!tail_phred(__logf(s_hi) - log1pf(s_hi), lp, &x_lo, &b_lo)) return false;   // more error, lower quality
+  const float err_lo = s_lo > 0.0f ? __logf(s_lo) - log1pf(s_lo) : -CUDART_INF_F;
+  if (!tail_phred(err_lo, lp, &x_hi, &b_hi)) return false;
+  if (b_lo != b_hi) return false;
+  if (b_lo == 0) { *q_out = fast_qual; return true; }
+  const float qa = clamp_floor_phred(x_lo - 2.0e-3f), qb = clamp_floor_phred(x_hi + 2.0e-3f);
+  if (qa != qb) return false;
+  *q_out = static_cast<uint32_t>(qa);
+  return true;
+}
+
 // The literal per-position algorithm (vanilla_caller.rs:1319-1355 + base_builder.rs:295-458).
 //
 // Two-read units take a shortcut first: when both reads cover the position, agree on an A/C/G/T base
@@ -277,6 +338,7 @@ __device__ __noinline__ Called exact_position(const TileView<M>& tv, const VoteS
   uint32_t depth = (n0 + n1 + n2 + n3) & 0xFFFFu;             // contributions(): u16 sum
   uint32_t cbase = 'N', cqual = 2;                            // base_builder.rs:392-394
   uint32_t nobs_call = 0;
+  uint32_t literal = 0;                                       // set when the f64 tail decided
   if (depth != 0) {
     uint32_t kinds = (n0 != 0) + (n1 != 0) + (n2 != 0) + (n3 != 0);
     bool done = false;
@@ -292,7 +354,8 @@ __device__ __noinline__ Called exact_position(const TileView<M>& tv, const VoteS
       }
     }
     if (!done) {                                              // base_builder.rs:401-457
-      double ln_sum = dm::ln_sum_exp_array4(ll);
+      // argmax and tie rule first: pure comparisons (the reference evaluates ln_sum before them;
+      // the order is immaterial)
       double mx = -CUDART_INF;
       int mi = -1;
       bool tie = false;
@@ -304,17 +367,24 @@ __device__ __noinline__ Called exact_position(const TileView<M>& tv, const VoteS
         else if (v < mx) { if (fabs(__dsub_rn(v, mx)) <= dm::kEps) tie = true; }
       }
       if (!(tie || mi < 0)) {
-        double post = __dsub_rn(mx, ln_sum);
-        double err = dm::ln_one_minus_exp(post);
-        double fin = dm::ln_error_prob_two_trials(S.ln_pre, err);
+        uint32_t q;
+        if (certified_quality(ll, mi, mx, S.ln_pre, fast_qual, &q)) {
+          cqual = q;
+        } else {
+          double ln_sum = dm::ln_sum_exp_array4(ll);
+          double post = __dsub_rn(mx, ln_sum);
+          double err = dm::ln_one_minus_exp(post);
+          double fin = dm::ln_error_prob_two_trials(S.ln_pre, err);
+          cqual = dm::ln_prob_to_phred(fin);
+          literal = kLiteralFlag;
+        }
         cbase = (0x54474341u >> (8 * mi)) & 0xFFu;
-        cqual = dm::ln_prob_to_phred(fin);
         nobs_call = mi == 0 ? n0 : mi == 1 ? n1 : mi == 2 ? n2 : n3;
       }
     }
   }
   Called out;
-  out.depth = depth | kLiteralFlag;
+  out.depth = depth | literal;
   out.errors = (depth - nobs_call) & 0xFFFFu;                 // vanilla_caller.rs:1341
   if (depth < min_reads) { out.base = 'N'; out.qual = 0; }    // :1345-1346
   else if (cqual < min_cons_q) { out.base = 'N'; out.qual = 2; }  // :1347-1348
