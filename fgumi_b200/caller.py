@@ -60,7 +60,7 @@ class VanillaUmiConsensusCaller(_Caller):
     def __init__(self, read_name_prefix: str, read_group_id: str,
                  options: VanillaUmiConsensusOptions = VanillaUmiConsensusOptions(), device: int = 0,
                  tag: bytes = b"MI", cell_tag: bytes = b"", consensus_call_overlapping_bases: bool = False,
-                 filter: "ConsensusFilter" = None):
+                 filter: "ConsensusFilter" = None, n_threads: int = 1):
         self._lib = _l.load()
         self._prefix = read_name_prefix.encode()
         self._rg = read_group_id.encode()
@@ -73,6 +73,7 @@ class VanillaUmiConsensusCaller(_Caller):
         o.produce_per_base_tags = 1 if options.produce_per_base_tags else 0
         o.trim = 1 if options.trim else 0
         o.consensus_call_overlapping_bases = 1 if consensus_call_overlapping_bases else 0
+        o.n_threads = n_threads
         if filter is not None:           # `fgumi simplex | fgumi filter` in one pass
             o.filter_enabled = 1
             filter.fill(o.filter)
@@ -111,6 +112,21 @@ class VanillaUmiConsensusCaller(_Caller):
         self._check(self._lib.fgb_caller_add_group(self._h, buf.ctypes.data, off.ctypes.data, len(records)),
                     "fgb_caller_add_group")
 
+    def add_groups(self, groups: Sequence[Sequence[bytes]]):
+        """Queue many MI groups with one call (fgb_caller_add_groups); the per-group host work runs
+        on `n_threads` threads when the caller was created with n_threads > 1."""
+        groups = [g for g in groups if g]
+        if not groups:
+            return
+        recs = [r for g in groups for r in g]
+        blob = np.frombuffer(b"".join(recs), dtype=np.uint8)
+        off = np.zeros(len(recs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(r) for r in recs])
+        grp = np.zeros(len(groups) + 1, dtype=np.uint64)
+        grp[1:] = np.cumsum([len(g) for g in groups])
+        self._check(self._lib.fgb_caller_add_groups(self._h, blob.ctypes.data, off.ctypes.data, grp.ctypes.data,
+                                                    len(groups)), "fgb_caller_add_groups")
+
     def flush(self) -> ConsensusOutput:
         data, n, cnt = C.c_void_p(), C.c_uint64(), C.c_uint64()
         self._check(self._lib.fgb_caller_flush(self._h, C.byref(data), C.byref(n), C.byref(cnt)),
@@ -137,12 +153,13 @@ class DuplexConsensusCaller(VanillaUmiConsensusCaller):
                  error_rate_pre_umi: int = 45, error_rate_post_umi: int = 40,
                  min_input_base_quality: int = 10, produce_per_base_tags: bool = True,
                  trim: bool = False, device: int = 0, cell_tag: bytes = b"",
-                 consensus_call_overlapping_bases: bool = False):
+                 consensus_call_overlapping_bases: bool = False, n_threads: int = 1):
         self._lib = _l.load()
         self._prefix = read_name_prefix.encode()
         self._rg = read_group_id.encode()
         o = _l.FgbCallerOptions()
         o.mode = 1
+        o.n_threads = n_threads
         o.consensus_call_overlapping_bases = 1 if consensus_call_overlapping_bases else 0
         o.error_rate_pre_umi = error_rate_pre_umi
         o.error_rate_post_umi = error_rate_post_umi
@@ -166,12 +183,14 @@ class CodecConsensusCaller(VanillaUmiConsensusCaller):
                  min_duplex_length: int = 1, error_rate_pre_umi: int = 45, error_rate_post_umi: int = 40,
                  single_strand_qual=None, outer_bases_qual=None, outer_bases_length: int = 5,
                  max_duplex_disagreements=None, max_duplex_disagreement_rate: float = 1.0,
-                 produce_per_base_tags: bool = False, device: int = 0, cell_tag: bytes = b""):
+                 produce_per_base_tags: bool = False, device: int = 0, cell_tag: bytes = b"",
+                 n_threads: int = 1):
         self._lib = _l.load()
         self._prefix = read_name_prefix.encode()
         self._rg = read_group_id.encode()
         o = _l.FgbCallerOptions()
         o.mode = 2
+        o.n_threads = n_threads
         o.error_rate_pre_umi = error_rate_pre_umi
         o.error_rate_post_umi = error_rate_post_umi
         o.min_input_base_quality = 10            # carried by the options, unused on this path

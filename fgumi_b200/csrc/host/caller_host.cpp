@@ -16,6 +16,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/fgumi_b200.h"
@@ -91,6 +92,7 @@ struct fgb_caller {
   std::vector<uint32_t> ops;             // scratch
   overlap::Caller overlap{overlap::kAgreeConsensus, overlap::kDisagreeConsensus};   // simplex.rs:384-387
   std::vector<uint8_t> group_copy;       // mutable copy of a group for the overlap pre-pass
+  std::vector<std::unique_ptr<fgb_caller>> workers;   // per-thread prep state of fgb_caller_add_groups (no GPU handle)
 };
 
 namespace {
@@ -275,43 +277,76 @@ fgb_status flush_simplex(fgb_caller* c) {
     }
   }
   // ---- build_consensus_record_into, vanilla_caller.rs:1365-1473 ----
-  bam::Writer w(&c->out);
-  for (uint64_t i = 0; i < U; ++i) {
-    if (!emit[i]) continue;
-    const fgb_unit& u = c->pack.units[i];
-    const UnitMeta& m = c->metas[i];
-    const uint32_t L = u.cons_len;
-    const uint8_t* bases = ob.data() + u.out_off;
-    const uint8_t* quals = oq.data() + u.out_off;
-    const uint16_t* depths = od.data() + u.out_off;
-    const uint16_t* errors = oe.data() + u.out_off;
-    uint16_t flag = bam::kUnmapped;
-    if (m.read_type == kR1) flag |= bam::kPaired | bam::kFirst | bam::kMateUnmapped;
-    else if (m.read_type == kR2) flag |= bam::kPaired | bam::kLast | bam::kMateUnmapped;
-    std::string name = c->prefix + ":" + m.umi;
-    if (name.size() >= 255) { c->last_error = "read name too long"; return FGB_ERR_INVALID_ARG; }
-    w.begin(name, flag, bases, quals, L);
-    w.str("RG", c->rg.data(), c->rg.size());
-    uint32_t max_d = 0, min_d = L ? 0xFFFFFFFFu : 0;
-    uint64_t tot_e = 0, tot_d = 0;
-    for (uint32_t k = 0; k < L; ++k) {
-      max_d = std::max<uint32_t>(max_d, depths[k]);
-      min_d = std::min<uint32_t>(min_d, depths[k]);
-      tot_e += errors[k];
-      tot_d += depths[k];
+  // Records are independent: with n_threads > 1 contiguous unit ranges are assembled into per-thread
+  // buffers and concatenated in order.
+  auto assemble = [&](uint64_t i0, uint64_t i1, std::vector<uint8_t>* dst, uint64_t* count,
+                      std::string* err) -> fgb_status {
+    bam::Writer w(dst);
+    std::string rx;
+    for (uint64_t i = i0; i < i1; ++i) {
+      if (!emit[i]) continue;
+      const fgb_unit& u = c->pack.units[i];
+      const UnitMeta& m = c->metas[i];
+      const uint32_t L = u.cons_len;
+      const uint8_t* bases = ob.data() + u.out_off;
+      const uint8_t* quals = oq.data() + u.out_off;
+      const uint16_t* depths = od.data() + u.out_off;
+      const uint16_t* errors = oe.data() + u.out_off;
+      uint16_t flag = bam::kUnmapped;
+      if (m.read_type == kR1) flag |= bam::kPaired | bam::kFirst | bam::kMateUnmapped;
+      else if (m.read_type == kR2) flag |= bam::kPaired | bam::kLast | bam::kMateUnmapped;
+      std::string name = c->prefix + ":" + m.umi;
+      if (name.size() >= 255) { *err = "read name too long"; return FGB_ERR_INVALID_ARG; }
+      w.begin(name, flag, bases, quals, L);
+      w.str("RG", c->rg.data(), c->rg.size());
+      uint32_t max_d = 0, min_d = L ? 0xFFFFFFFFu : 0;
+      uint64_t tot_e = 0, tot_d = 0;
+      for (uint32_t k = 0; k < L; ++k) {
+        max_d = std::max<uint32_t>(max_d, depths[k]);
+        min_d = std::min<uint32_t>(min_d, depths[k]);
+        tot_e += errors[k];
+        tot_d += depths[k];
+      }
+      w.integer("cD", static_cast<int32_t>(max_d));
+      w.integer("cM", static_cast<int32_t>(min_d));
+      w.real("cE", error_rate(tot_e, tot_d));
+      if (c->opt.produce_per_base_tags) {
+        w.i16_array("cd", depths, L);
+        w.i16_array("ce", errors, L);
+      }
+      w.str("MI", m.umi.data(), m.umi.size());
+      if (m.has_cell) w.str(c->opt.cell_tag, m.cell.data(), m.cell.size());
+      if (!m.rx.empty()) {
+        if (!consensus_umis(c->umi_builder, m.rx, &rx)) {   // the reference panics here (simple_umi.rs:78-116)
+          *err = "RX values of a family have different lengths or mix DNA and non-DNA characters";
+          return FGB_ERR_INVALID_ARG;
+        }
+        w.str("RX", rx.data(), rx.size());
+      }
+      w.end();
+      ++*count;
     }
-    w.integer("cD", static_cast<int32_t>(max_d));
-    w.integer("cM", static_cast<int32_t>(min_d));
-    w.real("cE", error_rate(tot_e, tot_d));
-    if (c->opt.produce_per_base_tags) {
-      w.i16_array("cd", depths, L);
-      w.i16_array("ce", errors, L);
-    }
-    w.str("MI", m.umi.data(), m.umi.size());
-    if (m.has_cell) w.str(c->opt.cell_tag, m.cell.data(), m.cell.size());
-    if ((st = append_rx(c, &w, m.rx)) != FGB_OK) return st;
-    w.end();
-    ++c->out_count;
+    return FGB_OK;
+  };
+  const uint32_t T = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint32_t>(c->opt.n_threads, 1u), (U + 255) / 256));
+  if (T <= 1) {
+    std::string err;
+    st = assemble(0, U, &c->out, &c->out_count, &err);
+    if (st != FGB_OK) c->last_error = err;
+    return st;
+  }
+  std::vector<std::vector<uint8_t>> bufs(T);
+  std::vector<uint64_t> counts(T, 0);
+  std::vector<std::string> errs(T);
+  std::vector<fgb_status> sts(T, FGB_OK);
+  std::vector<std::thread> th;
+  for (uint32_t t = 0; t < T; ++t)
+    th.emplace_back([&, t]() { sts[t] = assemble(U * t / T, U * (t + 1) / T, &bufs[t], &counts[t], &errs[t]); });
+  for (auto& x : th) x.join();
+  for (uint32_t t = 0; t < T; ++t) {
+    if (sts[t] != FGB_OK) { c->last_error = errs[t]; return sts[t]; }
+    c->out.insert(c->out.end(), bufs[t].begin(), bufs[t].end());
+    c->out_count += counts[t];
   }
   return FGB_OK;
 }
@@ -1034,6 +1069,100 @@ fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uin
   if (c->opt.mode == FGB_MODE_DUPLEX) return add_group_duplex(c, recs);
   if (c->opt.mode == FGB_MODE_CODEC) return add_group_codec(c, recs);
   return add_group_simplex(c, recs);
+}
+
+}  // extern "C"
+
+namespace {
+
+// Appends everything a worker queued to the parent, in order, fixing up the offsets and indices that
+// are relative to the worker's own batch.
+void merge_worker(fgb_caller* c, fgb_caller* w) {
+  const uint64_t byte_base = c->pack.bases.size();
+  const uint32_t read_base = static_cast<uint32_t>(c->pack.reads.size());
+  const uint32_t unit_base = static_cast<uint32_t>(c->pack.units.size());
+  const uint64_t out_base = c->pack.n_out;
+  c->pack.bases.insert(c->pack.bases.end(), w->pack.bases.begin(), w->pack.bases.end());
+  c->pack.quals.insert(c->pack.quals.end(), w->pack.quals.begin(), w->pack.quals.end());
+  for (uint64_t d : w->pack.reads) c->pack.reads.push_back(FGB_READ_DESC(FGB_READ_OFF(d) + byte_base, FGB_READ_LEN(d)));
+  for (fgb_unit u : w->pack.units) { u.out_off += out_base; u.read_begin += read_base; c->pack.units.push_back(u); }
+  c->pack.n_out += w->pack.n_out;
+  for (auto& m : w->metas) c->metas.push_back(std::move(m));
+  // duplex
+  const int32_t job_base = static_cast<int32_t>(c->jobs.size());
+  for (fgb_duplex_job j : w->jobs) { j.unit_a += unit_base; j.unit_b += unit_base; j.out_off += c->n_duplex_out; c->jobs.push_back(j); }
+  c->n_duplex_out += w->n_duplex_out;
+  for (auto& m : w->molecules) {
+    for (auto& u : m.unit) if (u != 0xFFFFFFFFu) u += unit_base;
+    for (auto& j : m.job) if (j >= 0) j += job_base;
+    c->molecules.push_back(std::move(m));
+  }
+  // CODEC
+  const uint32_t cjob_base = static_cast<uint32_t>(c->codec_jobs.size());
+  for (fgb_codec_job j : w->codec_jobs) { j.unit_a += unit_base; j.unit_b += unit_base; j.out_off += c->n_codec_out; c->codec_jobs.push_back(j); }
+  c->n_codec_out += w->n_codec_out;
+  for (auto& m : w->codec_molecules) { m.unit_r1 += unit_base; m.unit_r2 += unit_base; m.job += cjob_base; c->codec_molecules.push_back(std::move(m)); }
+  for (int i = 0; i < FGB_NSTATS; ++i) c->stats[i] += w->stats[i];
+  c->overlap.stats.overlapping_bases += w->overlap.stats.overlapping_bases;
+  c->overlap.stats.bases_agreeing += w->overlap.stats.bases_agreeing;
+  c->overlap.stats.bases_disagreeing += w->overlap.stats.bases_disagreeing;
+  c->overlap.stats.bases_corrected += w->overlap.stats.bases_corrected;
+  w->pack.clear(); w->metas.clear(); w->molecules.clear(); w->jobs.clear();
+  w->codec_molecules.clear(); w->codec_jobs.clear();
+  w->n_duplex_out = 0; w->n_codec_out = 0;
+  std::memset(w->stats, 0, sizeof(w->stats));
+  w->overlap.stats = overlap::Stats();
+}
+
+}  // namespace
+
+extern "C" {
+
+fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
+                                 const uint64_t* group_rec, uint64_t n_groups) {
+  if (!c || (n_groups && (!records || !rec_off || !group_rec))) return FGB_ERR_INVALID_ARG;
+  if (n_groups == 0) return FGB_OK;
+  const uint64_t n_rec = group_rec[n_groups] - group_rec[0];
+  uint32_t T = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint32_t>(c->opt.n_threads, 1u), (n_groups + 63) / 64));
+  auto run = [&](fgb_caller* dst, uint64_t g0, uint64_t g1, uint64_t* bad_group) -> fgb_status {
+    for (uint64_t g = g0; g < g1; ++g) {
+      const uint64_t r0 = group_rec[g], r1 = group_rec[g + 1];
+      if (r1 < r0 || r1 - r0 > 0xFFFFFFFFull) { dst->last_error = "bad group_rec table"; *bad_group = g; return FGB_ERR_INVALID_ARG; }
+      fgb_status st = fgb_caller_add_group(dst, records, rec_off + r0, static_cast<uint32_t>(r1 - r0));
+      if (st != FGB_OK) { *bad_group = g; return st; }
+    }
+    return FGB_OK;
+  };
+  if (T <= 1) { uint64_t bg = 0; return run(c, 0, n_groups, &bg); }
+  while (c->workers.size() < T) {
+    std::unique_ptr<fgb_caller> w(new fgb_caller());
+    w->opt = c->opt; w->prefix = c->prefix; w->rg = c->rg; w->prep_opt = c->prep_opt;
+    w->h = nullptr;                    // workers only prepare; the vote happens in the parent's flush
+    c->workers.push_back(std::move(w));
+  }
+  // contiguous ranges balanced by record count
+  std::vector<uint64_t> cut(T + 1, n_groups);
+  cut[0] = 0;
+  for (uint32_t t = 1; t < T; ++t) {
+    const uint64_t target = group_rec[0] + n_rec * t / T;
+    cut[t] = static_cast<uint64_t>(std::lower_bound(group_rec, group_rec + n_groups, target) - group_rec);
+    if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+  }
+  std::vector<fgb_status> sts(T, FGB_OK);
+  std::vector<uint64_t> bad(T, 0);
+  std::vector<std::thread> th;
+  for (uint32_t t = 0; t < T; ++t)
+    th.emplace_back([&, t]() { sts[t] = run(c->workers[t].get(), cut[t], cut[t + 1], &bad[t]); });
+  for (auto& x : th) x.join();
+  for (uint32_t t = 0; t < T; ++t) {
+    if (sts[t] != FGB_OK) {           // report the first failing group in input order; drop the partial work
+      c->last_error = c->workers[t]->last_error;
+      for (auto& w : c->workers) { fgb_caller scratch; merge_worker(&scratch, w.get()); }
+      return sts[t];
+    }
+  }
+  for (uint32_t t = 0; t < T; ++t) merge_worker(c, c->workers[t].get());
+  return FGB_OK;
 }
 
 fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* out_len,

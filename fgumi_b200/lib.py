@@ -151,7 +151,8 @@ class FgbCallerOptions(C.Structure):
         ("tag", C.c_char * 2), ("cell_tag", C.c_char * 2),
         ("read_name_prefix", C.c_char_p), ("read_group_id", C.c_char_p),
         ("min_duplex_length", C.c_uint32), ("reserved1", C.c_uint32), ("codec", FgbCodecParams),
-        ("filter_enabled", C.c_uint8), ("reserved2", C.c_uint8 * 7), ("filter", FgbFilterParams),
+        ("filter_enabled", C.c_uint8), ("reserved2", C.c_uint8 * 3), ("n_threads", C.c_uint32),
+        ("filter", FgbFilterParams),
     ]
 
 
@@ -178,7 +179,7 @@ SYMBOLS = (
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
-    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size",
+    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups",
 )
 
 _lib = None
@@ -286,6 +287,8 @@ def load() -> C.CDLL:
     lib.fgb_filter_simplex_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns),
                                               C.POINTER(FgbFilterParams), vp, vp, vp]
     lib.fgb_filter_simplex_device.restype = C.c_int32
+    lib.fgb_caller_add_groups.argtypes = [vp, vp, vp, vp, u64]
+    lib.fgb_caller_add_groups.restype = C.c_int32
     lib.fgb_struct_size.argtypes = [C.c_uint32]
     lib.fgb_struct_size.restype = C.c_uint32
     _lib = lib

@@ -426,7 +426,9 @@ typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanill
    * 614-697): consensus reads are masked on the device and a template -- the fragment / R1 / R2
    * reads of one MI -- is emitted only if all of its reads pass. */
   uint8_t filter_enabled;
-  uint8_t reserved2[7];
+  uint8_t reserved2[3];
+  uint32_t n_threads;                      /* host threads for fgb_caller_add_groups and the record
+                                              assembly of flush; 0 or 1 = the calling thread only  */
   fgb_filter_params filter;                /* filter.per_base_tags is set from produce_per_base_tags */
 } fgb_caller_options;
 
@@ -474,6 +476,14 @@ size_t fgb_caller_last_error(const fgb_caller* c, char* buf, size_t buf_len);
  * prefix) back to back, record i spanning [rec_off[i], rec_off[i+1]).  Groups are queued. */
 fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
                                 uint32_t n_records);
+/* The same for many groups at once: group g holds records [group_rec[g], group_rec[g+1]) of the
+ * rec_off table (n_groups + 1 entries in group_rec, group_rec[n_groups] + 1 entries in rec_off).
+ * With options.n_threads > 1 the per-group host work (filtering, source-read preparation, CIGAR
+ * grouping, ...) runs on that many threads over contiguous ranges of groups and the results are
+ * merged in input order, so the output is identical to calling fgb_caller_add_group in a loop.  This
+ * is the reference's "one caller per worker" (simplex.rs:574) folded behind one call. */
+fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
+                                 const uint64_t* group_rec, uint64_t n_groups);
 /* Votes everything queued (one fgb_submit) and returns the concatenated ConsensusOutput of all
  * groups in input order.  *out_data stays valid until the next flush / destroy. */
 fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* out_len,
