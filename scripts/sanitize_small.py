@@ -1,0 +1,45 @@
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import fgumi_b200 as fg
+from tests import oracle_lib as O
+
+rng = np.random.default_rng(5)
+units = []
+for i in range(1500):
+    depth = int(rng.integers(1, 14))
+    L = int(rng.integers(3, 170))
+    rows = []
+    for _ in range(depth):
+        ln = int(rng.integers(max(1, L - 9), L + 1))
+        b = rng.choice(np.frombuffer(b"ACGTN", np.uint8), p=[.24, .24, .24, .24, .04], size=ln)
+        q = rng.integers(2, 45, size=ln).astype(np.uint8)
+        q[b == ord("N")] = 2
+        rows.append((b.tobytes(), q.tobytes()))
+    units.append(rows)
+units.append([(b"ACGT" * 6000, bytes([30] * 24000))] * 3)        # oversize unit: direct path
+batch = fg.pack_source_reads(units, 1)
+eng = fg.Engine(0, 45, 40, 1, 2)
+want = O.simplex_batch(batch, 45, 40, 1, 2)
+got = eng.vote(batch)
+n = batch.n_out
+assert np.array_equal(got.base[:n], want[0][:n]) and np.array_equal(got.qual[:n], want[1][:n])
+packed = fg.pack8_encode(batch.bases, batch.quals)
+out8 = fg.HostColumns(np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint8), np.zeros(n, np.uint8))
+eng.submit_ex(batch, out8, packed=packed, narrow=True); eng.wait()
+assert np.array_equal(out8.base, got.base[:n])
+# filter epilogue through the caller, duplex and codec callers
+from tests.test_caller_parity import random_groups, random_duplex_groups, random_codec_groups
+c = fg.VanillaUmiConsensusCaller("f", "A", fg.VanillaUmiConsensusOptions(min_reads=1, min_consensus_base_quality=2),
+                                 filter=fg.ConsensusFilter(min_reads=2, max_read_error_rate=0.1, max_base_error_rate=0.2, min_base_quality=10),
+                                 consensus_call_overlapping_bases=True, n_threads=3)
+c.add_groups(random_groups(rng, 60)); c.flush(); c.close()
+c = fg.DuplexConsensusCaller("f", "A", min_reads=(1, 1, 0)); c.consensus_reads_batch(random_duplex_groups(rng, 60)); c.close()
+c = fg.CodecConsensusCaller("c", "R"); c.consensus_reads_batch(random_codec_groups(rng, 60)); c.close()
+# BAM4
+layout, raw = fg.pack_raw_reads([[(b"ACGTNACGTACGTTTGA", bytes(range(5, 22)), bool(i & 1), 17 - (i % 3))] * (1 + i % 4) for i in range(200)], 1, 10)
+o = fg.HostColumns.alloc(layout.n_out)
+eng.submit_bam4(layout, raw, o); eng.wait()
+eng.close()
+print("sanitize run ok")
