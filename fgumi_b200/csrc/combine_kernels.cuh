@@ -67,6 +67,75 @@ __global__ void __launch_bounds__(kCombineThreads) duplex_combine_kernel(const D
       status = FGB_DUPLEX_BOTH;
       const uint32_t ra0 = ua.read_begin, ra1 = a.units[job.unit_a + 1].read_begin;
       const uint32_t rb0 = ub.read_begin, rb1 = a.units[job.unit_b + 1].read_begin;
+      // Word path: 8 positions per lane with byte-parallel arithmetic.  Needs 8-aligned rows (the
+      // layout rule for inputs; job.out_off is the caller's) and per-position error counts that fit
+      // a byte.  Everything else takes the position-by-position loop below.
+      const bool words = ((ua.out_off | ub.out_off | job.out_off) & 7u) == 0 &&
+                         (ra1 - ra0) + (rb1 - rb0) <= 255u;
+      if (words) {
+        for (uint32_t base0 = 0; base0 < len; base0 += 256u) {
+          const uint32_t p0 = base0 + lane * 8u;
+          const bool active = p0 < len;
+          uint2 ab2 = make_uint2(0, 0), bb2 = ab2, aq2 = ab2, bq2 = ab2;
+          if (active) {
+            ab2 = *reinterpret_cast<const uint2*>(a.ss_base + ua.out_off + p0);
+            bb2 = *reinterpret_cast<const uint2*>(a.ss_base + ub.out_off + p0);
+            aq2 = *reinterpret_cast<const uint2*>(a.ss_qual + ua.out_off + p0);
+            bq2 = *reinterpret_cast<const uint2*>(a.ss_qual + ub.out_off + p0);
+          }
+          uint32_t ob[2], oq[2], rawb[2], cnt[2] = {0u, 0u};
+          const uint32_t abw[2] = {ab2.x, ab2.y}, bbw[2] = {bb2.x, bb2.y};
+          const uint32_t aqw[2] = {aq2.x, aq2.y}, bqw[2] = {bq2.x, bq2.y};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t eq = __vcmpeq4(abw[h], bbw[h]);                    // :912-927, bytewise
+            const uint32_t sum = __vminu4(__vaddus4(aqw[h], bqw[h]), 0x5D5D5D5Du);
+            const uint32_t dif = __vminu4(__vabsdiffu4(aqw[h], bqw[h]), 0x5D5D5D5Du);
+            const uint32_t rq = __vmaxu4((eq & sum) | (~eq & dif), 0x02020202u);   // cap_quality; equal-quality dissent -> 2
+            const uint32_t b_wins = ~eq & __vcmpgtu4(bqw[h], aqw[h]);
+            rawb[h] = (bbw[h] & b_wins) | (abw[h] & ~b_wins);
+            const uint32_t mask = __vcmpeq4(abw[h], 0x4E4E4E4Eu) | __vcmpeq4(bbw[h], 0x4E4E4E4Eu) |
+                                  __vcmpeq4(rq, 0x02020202u);                 // :930-935
+            ob[h] = (0x4E4E4E4Eu & mask) | (rawb[h] & ~mask);
+            oq[h] = (0x02020202u & mask) | (rq & ~mask);
+          }
+          // :943-951 exact error recount against the pooled source reads (AB rows then BA rows)
+          // descriptors are fetched 32 at a time, one per lane, and broadcast by shuffle, so the row
+          // loads of a chunk are independent of each other (all lanes take part in the shuffles)
+          auto recount_word = [&](uint64_t d) {
+            const uint32_t rl = static_cast<uint32_t>(d & 0xFFFFu);
+            if (active && rl > p0) {
+              const uint2 sb = *reinterpret_cast<const uint2*>(a.bases + (d >> 16) + p0);
+              const uint32_t cov = rl - p0;                                   // covered positions of this word
+              const uint32_t c0 = cov >= 4u ? 0xFFFFFFFFu : ((1u << (8u * cov)) - 1u);
+              const uint32_t c1 = cov >= 8u ? 0xFFFFFFFFu : (cov > 4u ? ((1u << (8u * (cov - 4u))) - 1u) : 0u);
+              const uint32_t sw[2] = {sb.x, sb.y}, cw[2] = {c0, c1};
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t ne = ~__vcmpeq4(sw[h], rawb[h]) & ~__vcmpeq4(sw[h], 0x4E4E4E4Eu) & cw[h];
+                cnt[h] += ne & 0x01010101u;
+              }
+            }
+          };
+          const uint32_t na = ra1 - ra0, nr = na + (rb1 - rb0);
+          for (uint32_t c0 = 0; c0 < nr; c0 += 32u) {
+            const uint32_t k = c0 + lane;
+            const uint64_t mine = k < nr ? a.reads[k < na ? ra0 + k : rb0 + (k - na)] : 0ull;
+            const uint32_t m = nr - c0 < 32u ? nr - c0 : 32u;
+#pragma unroll 4
+            for (uint32_t r = 0; r < m; ++r) recount_word(__shfl_sync(0xFFFFFFFFu, mine, r));
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) cnt[h] &= ~__vcmpeq4(rawb[h], 0x4E4E4E4Eu);   // raw base N: no recount
+          if (active) {
+            *reinterpret_cast<uint2*>(a.out_base + job.out_off + p0) = make_uint2(ob[0], ob[1]);
+            *reinterpret_cast<uint2*>(a.out_qual + job.out_off + p0) = make_uint2(oq[0], oq[1]);
+            *reinterpret_cast<uint4*>(a.out_errors + job.out_off + p0) =
+                make_uint4(__byte_perm(cnt[0], 0u, 0x4140u), __byte_perm(cnt[0], 0u, 0x4342u),
+                           __byte_perm(cnt[1], 0u, 0x4140u), __byte_perm(cnt[1], 0u, 0x4342u));
+          }
+        }
+      } else {
       for (uint32_t i = lane; i < len; i += 32) {
         uint32_t a_base = a.ss_base[ua.out_off + i], b_base = a.ss_base[ub.out_off + i];
         int32_t a_qual = a.ss_qual[ua.out_off + i], b_qual = a.ss_qual[ub.out_off + i];
@@ -98,6 +167,7 @@ __global__ void __launch_bounds__(kCombineThreads) duplex_combine_kernel(const D
         a.out_base[job.out_off + i] = mask ? 'N' : static_cast<uint8_t>(raw_base);
         a.out_qual[job.out_off + i] = mask ? 2 : static_cast<uint8_t>(raw_qual);
         a.out_errors[job.out_off + i] = static_cast<uint16_t>(nerr);
+      }
       }
     } else if (a_any || b_any) {
       // :855-882 single-strand passthrough keeps the FULL length of the surviving strand
