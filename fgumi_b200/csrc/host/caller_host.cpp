@@ -15,6 +15,9 @@
 #include <cmath>
 #include <cstring>
 #include <memory>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <thread>
 #include <vector>
@@ -93,6 +96,13 @@ struct fgb_caller {
   overlap::Caller overlap{overlap::kAgreeConsensus, overlap::kDisagreeConsensus};   // simplex.rs:384-387
   std::vector<uint8_t> group_copy;       // mutable copy of a group for the overlap pre-pass
   std::vector<std::unique_ptr<fgb_caller>> workers;   // per-thread prep state of fgb_caller_add_groups (no GPU handle)
+  // flush scratch that outlives a flush, so steady-state flushes neither page-fault nor zero-fill:
+  std::vector<std::vector<uint8_t>> tbufs;   // per-thread record buffers (capacity kept)
+  uint8_t* joined = nullptr;                 // concatenated output of a threaded flush (malloc, grow-only)
+  size_t joined_cap = 0, joined_len = 0;
+  bool out_is_joined = false;
+  void* pinned[4] = {nullptr, nullptr, nullptr, nullptr};   // consensus columns, page-locked (fgb_host_alloc)
+  size_t pinned_cap = 0;                     // capacity in elements (same for the four columns)
 };
 
 namespace {
@@ -219,9 +229,23 @@ fgb_status append_rx(fgb_caller* c, bam::Writer* w, const std::vector<std::strin
   return FGB_OK;
 }
 
+// FGB_CALLER_TRACE=1 prints the phases of a flush to stderr (diagnostics only).
+struct PhaseTrace {
+  bool on = std::getenv("FGB_CALLER_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "fgb_caller flush: %-22s %8.2f ms\n", what,
+                 std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 fgb_status flush_simplex(fgb_caller* c) {
   const uint64_t U = c->pack.units.size();
   if (!U) return FGB_OK;
+  PhaseTrace trace;
   uint64_t n_bytes, R;
   c->pack.seal(&n_bytes, &R);
   uint64_t n_tiles = 0;
@@ -230,8 +254,21 @@ fgb_status flush_simplex(fgb_caller* c) {
   std::vector<fgb_tile> tiles(n_tiles ? n_tiles : 1);
   if ((st = fgb_plan_tiles(c->pack.units.data(), U, c->pack.reads.data(), R, tiles.data(), n_tiles, &n_tiles)) != FGB_OK) return st;
   const uint64_t no = c->pack.n_out;
-  std::vector<uint8_t> ob(no + 8), oq(no + 8);
-  std::vector<uint16_t> od(no + 8), oe(no + 8);
+  trace.mark("seal + plan");
+  if (c->pinned_cap < no + 8) {              // grow-only page-locked columns: no zero-fill, fast D2H
+    for (void*& p : c->pinned) { fgb_host_free(p); p = nullptr; }
+    c->pinned_cap = 0;
+    const size_t cap = (no + 8) + (no + 8) / 4;
+    const size_t bytes[4] = {cap, cap, cap * 2, cap * 2};
+    for (int i = 0; i < 4; ++i)
+      if (fgb_host_alloc(&c->pinned[i], bytes[i]) != FGB_OK) { c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM; }
+    c->pinned_cap = cap;
+  }
+  struct Col8 { uint8_t* p; uint8_t* data() const { return p; } };
+  struct Col16 { uint16_t* p; uint16_t* data() const { return p; } };
+  const Col8 ob{static_cast<uint8_t*>(c->pinned[0])}, oq{static_cast<uint8_t*>(c->pinned[1])};
+  const Col16 od{static_cast<uint16_t*>(c->pinned[2])}, oe{static_cast<uint16_t*>(c->pinned[3])};
+  trace.mark("output buffers");
   fgb_batch b;
   b.n_units = U; b.n_reads = R; b.n_bytes = n_bytes; b.n_out = no; b.n_tiles = n_tiles;
   b.bases = c->pack.bases.data(); b.quals = c->pack.quals.data(); b.reads = c->pack.reads.data();
@@ -259,6 +296,7 @@ fgb_status flush_simplex(fgb_caller* c) {
     c->last_error = buf;
     return st;
   }
+  trace.mark("submit + wait");
   // Template rule (commands/filter.rs:640-672): reads that share a name -- here the consecutive units
   // of one MI -- are emitted only if every one of them passed.
   std::vector<char> emit(U, 1);
@@ -335,19 +373,43 @@ fgb_status flush_simplex(fgb_caller* c) {
     if (st != FGB_OK) c->last_error = err;
     return st;
   }
-  std::vector<std::vector<uint8_t>> bufs(T);
+  if (c->tbufs.size() < T) c->tbufs.resize(T);
   std::vector<uint64_t> counts(T, 0);
   std::vector<std::string> errs(T);
   std::vector<fgb_status> sts(T, FGB_OK);
-  std::vector<std::thread> th;
-  for (uint32_t t = 0; t < T; ++t)
-    th.emplace_back([&, t]() { sts[t] = assemble(U * t / T, U * (t + 1) / T, &bufs[t], &counts[t], &errs[t]); });
-  for (auto& x : th) x.join();
+  {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < T; ++t)
+      th.emplace_back([&, t]() {
+        c->tbufs[t].clear();
+        sts[t] = assemble(U * t / T, U * (t + 1) / T, &c->tbufs[t], &counts[t], &errs[t]);
+      });
+    for (auto& x : th) x.join();
+  }
+  trace.mark("assemble (threads)");
+  size_t total = 0;
+  std::vector<size_t> at(T, 0);
   for (uint32_t t = 0; t < T; ++t) {
     if (sts[t] != FGB_OK) { c->last_error = errs[t]; return sts[t]; }
-    c->out.insert(c->out.end(), bufs[t].begin(), bufs[t].end());
+    at[t] = total;
+    total += c->tbufs[t].size();
     c->out_count += counts[t];
   }
+  if (c->joined_cap < total) {
+    std::free(c->joined);
+    c->joined_cap = total + total / 4 + 64;
+    c->joined = static_cast<uint8_t*>(std::malloc(c->joined_cap));
+    if (!c->joined) { c->joined_cap = 0; c->last_error = "out of memory"; return FGB_ERR_NOMEM; }
+  }
+  {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < T; ++t)
+      th.emplace_back([&, t]() { if (!c->tbufs[t].empty()) std::memcpy(c->joined + at[t], c->tbufs[t].data(), c->tbufs[t].size()); });
+    for (auto& x : th) x.join();
+  }
+  c->joined_len = total;
+  c->out_is_joined = true;
+  trace.mark("concatenate");
   return FGB_OK;
 }
 
@@ -1032,6 +1094,8 @@ fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_call
 
 void fgb_caller_destroy(fgb_caller* c) {
   if (!c) return;
+  for (void* p : c->pinned) fgb_host_free(p);
+  std::free(c->joined);
   fgb_destroy(c->h);
   delete c;
 }
@@ -1170,14 +1234,15 @@ fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* o
   if (!c || !out_data || !out_len || !out_count) return FGB_ERR_INVALID_ARG;
   c->out.clear();
   c->out_count = 0;
+  c->out_is_joined = false;
   fgb_status st = c->opt.mode == FGB_MODE_DUPLEX ? flush_duplex(c)
                   : c->opt.mode == FGB_MODE_CODEC ? flush_codec(c) : flush_simplex(c);
   c->pack.clear(); c->metas.clear(); c->molecules.clear(); c->jobs.clear();
   c->codec_molecules.clear(); c->codec_jobs.clear();
   c->n_duplex_out = 0; c->n_codec_out = 0;
   if (st != FGB_OK) return st;
-  *out_data = c->out.data();
-  *out_len = c->out.size();
+  *out_data = c->out_is_joined ? c->joined : c->out.data();
+  *out_len = c->out_is_joined ? c->joined_len : c->out.size();
   *out_count = c->out_count;
   return FGB_OK;
 }
