@@ -209,3 +209,76 @@ def test_pack8_encode_alphabet(fg):
     assert p.tolist() == [0, (1 << 6) | 61, (2 << 6) | 30, (3 << 6) | 7, 0x3E, 0]
     for bad_b, bad_q in ((b"a", 30), (b"R", 30), (b"N", 10), (b"A", 62), (b"\0", 1)):
         assert fg.pack8_encode(np.frombuffer(bad_b, np.uint8).copy(), np.array([bad_q], np.uint8)) is None
+
+
+def _brute_force_hints(batch, t):
+    """What the tile hint bits must say, straight from their definitions (fgb_config.h)."""
+    u0, nu = int(t["unit_begin"]), int(t["n_units"])
+    units, reads = batch.units, batch.reads
+    lens, offs, per_unit = [], [], []
+    for u in range(u0, u0 + nu):
+        rb, re = int(units["read_begin"][u]), int(units["read_begin"][u + 1])
+        per_unit.append(re - rb)
+        for r in range(rb, re):
+            lens.append(int(reads[r]) & 0xFFFF)
+            offs.append(int(reads[r]) >> 16)
+    cons = [int(units["cons_len"][u]) for u in range(u0, u0 + nu)]
+    items = {(c + 7) // 8 for c in cons}
+    uniform = len(items) == 1 and 2 <= next(iter(items)) <= 4096
+    regular = False
+    if lens and uniform and all(n > 0 for n in per_unit):
+        L = lens[0]
+        stride = (L + 7) // 8 * 8
+        regular = (all(x == L for x in lens) and all(c == L for c in cons) and
+                   all(o == offs[0] + i * stride for i, o in enumerate(offs)))
+    shallow = max(per_unit) <= 64
+    return uniform, regular, shallow, (offs[0] != int(t["byte_begin"])) if lens else False
+
+
+def test_planner_hint_bits_match_their_definitions(fg):
+    """Property test: on random layouts (uniform, ragged, gapped, deep) every hint bit the planner sets
+    -- regular, first-row skew, shallow, uniform items -- equals its brute-force definition, and the
+    tiles cover every unit exactly once within the capacity limits."""
+    lib = fg.lib.load()
+    cap, max_u, max_r = lib.fgb_tile_capacity_bytes(), lib.fgb_tile_max_units(), lib.fgb_tile_max_reads()
+    rng = np.random.default_rng(77)
+    seen = {"regular": 0, "irregular": 0, "skew": 0, "deep": 0}
+    for trial in range(120):
+        style = trial % 4
+        units = []
+        for _ in range(int(rng.integers(1, 260))):
+            if style == 0:                       # one length everywhere
+                L, depth = 150, int(rng.integers(1, 12))
+                rows = [(b"A" * L, bytes([30] * L))] * depth
+            elif style == 1:                     # ragged
+                depth = int(rng.integers(1, 10))
+                rows = [(b"C" * n, bytes([30] * n)) for n in rng.integers(1, 90, size=depth)]
+            elif style == 2:                     # uniform length but an occasional short read
+                L, depth = int(rng.integers(9, 60)), int(rng.integers(1, 6))
+                rows = [(b"G" * L, bytes([30] * L))] * depth
+                if rng.random() < 0.05:
+                    rows = rows + [(b"G" * (L - 1), bytes([30] * (L - 1)))]
+            else:                                # deep units
+                L, depth = 40, int(rng.integers(1, 130))
+                rows = [(b"T" * L, bytes([30] * L))] * depth
+            units.append(rows)
+        batch = fg.pack_source_reads(units, 1)
+        tiles = fg.plan_tiles(batch)
+        assert int(tiles["n_units"].sum()) == batch.n_units
+        assert np.array_equal(tiles["unit_begin"], np.concatenate([[0], np.cumsum(tiles["n_units"])[:-1]]))
+        for t in tiles:
+            fl = int(t["flags"])
+            direct = fl & 1
+            if not direct:
+                assert t["byte_len"] <= cap and t["n_units"] <= max_u and t["n_reads"] + (int(t["read_begin"]) & 1) <= max_r
+            uniform, regular, shallow, skew = _brute_force_hints(batch, t)
+            assert ((fl >> 8) != 0) == uniform, (trial, fl)
+            if not direct:
+                assert bool(fl & 2) == regular, (trial, fl)
+                assert bool(fl & 8) == shallow, (trial, fl)
+                if regular:
+                    assert bool(fl & 4) == skew, (trial, fl)
+                    seen["skew"] += skew
+                seen["regular" if regular else "irregular"] += 1
+                seen["deep"] += not shallow
+    assert all(v > 0 for v in seen.values()), seen
