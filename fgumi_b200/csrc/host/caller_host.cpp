@@ -414,6 +414,70 @@ fgb_status flush_simplex(fgb_caller* c) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// threaded record assembly (duplex, CODEC)
+// ------------------------------------------------------------------------------------------------
+void ensure_workers(fgb_caller* c, uint32_t T) {
+  while (c->workers.size() < T) {
+    std::unique_ptr<fgb_caller> w(new fgb_caller());
+    w->opt = c->opt; w->prefix = c->prefix; w->rg = c->rg; w->prep_opt = c->prep_opt;
+    w->h = nullptr;                    // workers prepare and assemble; the vote happens in the parent
+    c->workers.push_back(std::move(w));
+  }
+}
+
+// Runs body(ctx, i0, i1) over [0, n): on the caller itself when one thread is enough, else on worker
+// contexts (own record buffer, counters, error text) over contiguous ranges; buffers are joined in
+// order, counters summed, and the first error in input order wins.
+template <class Body>
+fgb_status parallel_records(fgb_caller* c, uint64_t n, uint64_t min_per_thread, Body body) {
+  const uint32_t T = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint32_t>(c->opt.n_threads, 1u),
+                                                               (n + min_per_thread - 1) / min_per_thread));
+  if (T <= 1) return body(c, static_cast<uint64_t>(0), n);
+  ensure_workers(c, T);
+  std::vector<fgb_status> sts(T, FGB_OK);
+  {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < T; ++t)
+      th.emplace_back([&, t]() {
+        fgb_caller* w = c->workers[t].get();
+        w->out.clear(); w->out_count = 0; w->last_error.clear();
+        sts[t] = body(w, n * t / T, n * (t + 1) / T);
+      });
+    for (auto& x : th) x.join();
+  }
+  size_t total = 0;
+  std::vector<size_t> at(T, 0);
+  fgb_status first = FGB_OK;
+  for (uint32_t t = 0; t < T; ++t) {
+    fgb_caller* w = c->workers[t].get();
+    if (first == FGB_OK && sts[t] != FGB_OK) { first = sts[t]; c->last_error = w->last_error; }
+    at[t] = total;
+    total += w->out.size();
+    c->out_count += w->out_count;
+    for (int i = 0; i < FGB_NSTATS; ++i) { c->stats[i] += w->stats[i]; w->stats[i] = 0; }
+  }
+  if (first != FGB_OK) return first;
+  if (c->joined_cap < total) {
+    std::free(c->joined);
+    c->joined_cap = total + total / 4 + 64;
+    c->joined = static_cast<uint8_t*>(std::malloc(c->joined_cap));
+    if (!c->joined) { c->joined_cap = 0; c->last_error = "out of memory"; return FGB_ERR_NOMEM; }
+  }
+  {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < T; ++t)
+      th.emplace_back([&, t]() {
+        const auto& o = c->workers[t]->out;
+        if (!o.empty()) std::memcpy(c->joined + at[t], o.data(), o.size());
+      });
+    for (auto& x : th) x.join();
+  }
+  c->joined_len = total;
+  c->out_is_joined = true;
+  return FGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // duplex
 // ------------------------------------------------------------------------------------------------
 bool paired_r1(const View& v) { return (v.flags() & bam::kPaired) && (v.flags() & bam::kFirst); }
@@ -660,8 +724,13 @@ fgb_status flush_duplex(fgb_caller* c) {
     s.len = len; s.present = true;
     return s;
   };
-  bam::Writer w(&c->out);
-  for (const Molecule& m : c->molecules) {
+  return parallel_records(c, c->molecules.size(), 128, [&](fgb_caller* ctx, uint64_t m0, uint64_t m1) -> fgb_status {
+  // `ctx` owns the record buffer, the counters and the error text of this range; the voted columns,
+  // jobs and molecules are the parent's (read-only here)
+  fgb_status st = FGB_OK;
+  bam::Writer w(&ctx->out);
+  for (uint64_t mi = m0; mi < m1; ++mi) {
+    const Molecule& m = c->molecules[mi];
     DuplexRead d[2];
     bool ok = true;
     if (m.pattern == 0) {
@@ -685,12 +754,12 @@ fgb_status flush_duplex(fgb_caller* c) {
       }
       if (ok) {   // duplex_consensus_has_minimum_reads on both reads, :2036-2047
         for (int k = 0; k < 2; ++k)
-          if (!min_reads_ok(c, max_depth(d[k].ab), d[k].ba.present ? max_depth(d[k].ba) : 0)) ok = false;
+          if (!min_reads_ok(ctx, max_depth(d[k].ab), d[k].ba.present ? max_depth(d[k].ba) : 0)) ok = false;
       }
-      if (!ok) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, m.n_input); continue; }
-      if ((st = write_duplex_record(c, &w, d[0], true, m, m.rx[0], m.rx[3])) != FGB_OK) return st;
-      if ((st = write_duplex_record(c, &w, d[1], false, m, m.rx[1], m.rx[2])) != FGB_OK) return st;
-      c->stats[FGB_STAT_CONSENSUS_READS] += 1;
+      if (!ok) { reject(ctx, FGB_STAT_REJ_INSUFFICIENT_READS, m.n_input); continue; }
+      if ((st = write_duplex_record(ctx, &w, d[0], true, m, m.rx[0], m.rx[3])) != FGB_OK) return st;
+      if ((st = write_duplex_record(ctx, &w, d[1], false, m, m.rx[1], m.rx[2])) != FGB_OK) return st;
+      ctx->stats[FGB_STAT_CONSENSUS_READS] += 1;
     } else {
       // single-strand molecule (min_yx_reads == 0): duplex_consensus(Some, None) keeps the strand
       // only if it has depth somewhere (:852-853)
@@ -703,19 +772,20 @@ fgb_status flush_duplex(fgb_caller* c) {
         d[k].bases = s.bases; d[k].quals = s.quals; d[k].errors = s.errors; d[k].len = s.len;
         d[k].ab = s; d[k].ba = Strand();
       }
-      if (!ok) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, m.n_input); continue; }
+      if (!ok) { reject(ctx, FGB_STAT_REJ_INSUFFICIENT_READS, m.n_input); continue; }
       static const std::vector<RxSource> kNone;
       if (m.pattern == 1) {
-        if ((st = write_duplex_record(c, &w, d[0], true, m, m.rx[0], kNone)) != FGB_OK) return st;
-        if ((st = write_duplex_record(c, &w, d[1], false, m, m.rx[1], kNone)) != FGB_OK) return st;
+        if ((st = write_duplex_record(ctx, &w, d[0], true, m, m.rx[0], kNone)) != FGB_OK) return st;
+        if ((st = write_duplex_record(ctx, &w, d[1], false, m, m.rx[1], kNone)) != FGB_OK) return st;
       } else {
-        if ((st = write_duplex_record(c, &w, d[0], true, m, kNone, m.rx[3])) != FGB_OK) return st;
-        if ((st = write_duplex_record(c, &w, d[1], false, m, kNone, m.rx[2])) != FGB_OK) return st;
+        if ((st = write_duplex_record(ctx, &w, d[0], true, m, kNone, m.rx[3])) != FGB_OK) return st;
+        if ((st = write_duplex_record(ctx, &w, d[1], false, m, kNone, m.rx[2])) != FGB_OK) return st;
       }
-      c->stats[FGB_STAT_CONSENSUS_READS] += 1;
+      ctx->stats[FGB_STAT_CONSENSUS_READS] += 1;
     }
   }
   return FGB_OK;
+  });
 }
 
 
@@ -982,13 +1052,23 @@ fgb_status flush_codec(fgb_caller* c) {
     c->last_error = buf;
     return st;
   }
-  bam::Writer w(&c->out);
+  // the record counter behind `prefix:<n>` names (codec_caller.rs:1236-1242) counts emitted records in
+  // input order: number the survivors up front so that ranges can be assembled independently
+  const uint64_t NM = c->codec_molecules.size();
+  std::vector<uint64_t> ordinal(NM + 1, 0);
+  for (uint64_t i = 0; i < NM; ++i)
+    ordinal[i + 1] = ordinal[i] + (cst[c->codec_molecules[i].job] == FGB_CODEC_OK);
+  const uint64_t counter0 = c->consensus_counter;
+  c->consensus_counter += ordinal[NM];
+  return parallel_records(c, NM, 128, [&](fgb_caller* ctx, uint64_t m0, uint64_t m1) -> fgb_status {
+  bam::Writer w(&ctx->out);
   PaddedStrand sa, sbb;
-  for (const CodecMolecule& m : c->codec_molecules) {
+  for (uint64_t mi = m0; mi < m1; ++mi) {
+    const CodecMolecule& m = c->codec_molecules[mi];
     const fgb_codec_job& j = c->codec_jobs[m.job];
     if (dup[m.job] > 0) {   // counted before the gate, codec_caller.rs:1155-1158
-      c->stats[FGB_STAT_DUPLEX_BASES] += dup[m.job];
-      c->stats[FGB_STAT_DUPLEX_DISAGREEMENTS] += dis[m.job];
+      ctx->stats[FGB_STAT_DUPLEX_BASES] += dup[m.job];
+      ctx->stats[FGB_STAT_DUPLEX_DISAGREEMENTS] += dis[m.job];
     }
     if (cst[m.job] != FGB_CODEC_OK) continue;   // "High duplex disagreement": the group is dropped
     const fgb_unit& u1 = c->pack.units[m.unit_r1];
@@ -999,9 +1079,8 @@ fgb_status flush_codec(fgb_caller* c) {
     padded_strand(sb.data() + u2.out_off, sq.data() + u2.out_off, sd.data() + u2.out_off, se.data() + u2.out_off,
                   u2.cons_len, j.rc_b, j.pad_b_left, L, m.r1_negative, &sbb);
     // build_output_record_into, codec_caller.rs:1226-1368
-    ++c->consensus_counter;
-    std::string name = c->prefix + ":" + (m.has_umi ? m.umi : std::to_string(c->consensus_counter));
-    if (name.size() >= 255) { c->last_error = "read name too long"; return FGB_ERR_INVALID_ARG; }
+    std::string name = c->prefix + ":" + (m.has_umi ? m.umi : std::to_string(counter0 + ordinal[mi] + 1));
+    if (name.size() >= 255) { ctx->last_error = "read name too long"; return FGB_ERR_INVALID_ARG; }
     const uint8_t* bases = cb.data() + j.out_off;
     const uint8_t* quals = cq.data() + j.out_off;
     const uint16_t* errors = ce.data() + j.out_off;
@@ -1037,16 +1116,17 @@ fgb_status flush_codec(fgb_caller* c) {
     if (!m.rx.empty()) {
       std::string rx;
       if (!consensus_umis(c->umi_builder, m.rx, &rx)) {
-        c->last_error = "RX values of a family have different lengths or mix DNA and non-DNA characters";
+        ctx->last_error = "RX values of a family have different lengths or mix DNA and non-DNA characters";
         return FGB_ERR_INVALID_ARG;
       }
       if (!rx.empty()) w.str("RX", rx.data(), rx.size());
     }
     w.end();
-    ++c->out_count;
-    c->stats[FGB_STAT_CONSENSUS_READS] += 1;
+    ++ctx->out_count;
+    ctx->stats[FGB_STAT_CONSENSUS_READS] += 1;
   }
   return FGB_OK;
+  });
 }
 
 }  // namespace
@@ -1198,12 +1278,7 @@ fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const ui
     return FGB_OK;
   };
   if (T <= 1) { uint64_t bg = 0; return run(c, 0, n_groups, &bg); }
-  while (c->workers.size() < T) {
-    std::unique_ptr<fgb_caller> w(new fgb_caller());
-    w->opt = c->opt; w->prefix = c->prefix; w->rg = c->rg; w->prep_opt = c->prep_opt;
-    w->h = nullptr;                    // workers only prepare; the vote happens in the parent's flush
-    c->workers.push_back(std::move(w));
-  }
+  ensure_workers(c, T);
   // contiguous ranges balanced by record count
   std::vector<uint64_t> cut(T + 1, n_groups);
   cut[0] = 0;
