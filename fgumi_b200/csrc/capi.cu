@@ -73,6 +73,8 @@ struct fgb_handle {
   std::string last_error;
   Slot slots[kSlots];
   bool submit_pending = false;
+  uint32_t* d_bad = nullptr;                        // BAM4: set by the unpack kernel on a bad raw span
+  bool bam4_pending = false;
   uint16_t* d_emax = nullptr;                       // filter: per-depth error-count limit
   double emax_rate = -1.0;                          // the max_base_error_rate d_emax was built for
   int n_slots = 2;                                  // FGB_SUBMIT_SLOTS (1..kSlots)
@@ -229,6 +231,7 @@ void fgb_destroy(fgb_handle* h) {
   cudaFree(h->d_tables);
   cudaFree(h->d_counters);
   cudaFree(h->d_emax);
+  cudaFree(h->d_bad);
   delete h;
 }
 
@@ -456,33 +459,19 @@ fgb_status launch_filter(fgb_handle* h, const fgb_unit* units, uint64_t u0, uint
   return FGB_OK;
 }
 
-fgb_status launch_unpack_bam4(fgb_handle* h, const Bam4Args& a, cudaStream_t s) {
+fgb_status launch_unpack_bam4(fgb_handle* h, Bam4Args a, cudaStream_t s) {
   const uint64_t n = a.read_end - a.read_begin;
   if (n == 0) return FGB_OK;
+  if (!h->d_bad) {
+    FGB_CUDA(h, cudaMalloc(&h->d_bad, sizeof(uint32_t)));
+    FGB_CUDA(h, cudaMemset(h->d_bad, 0, sizeof(uint32_t)));
+  }
+  a.bad = h->d_bad;
+  h->bam4_pending = true;
   const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + 7u) / 8u, static_cast<uint64_t>(h->sm_count) * 16u));
   unpack_bam4_kernel<<<grid, 256, 0, s>>>(a);
   h->launches++;
   FGB_CUDA(h, cudaGetLastError());
-  return FGB_OK;
-}
-
-// Layout rules of fgb_raw_columns for reads [r0, r1); `*prev_end` carries the end of the previous
-// span across calls.  Checked chunk by chunk so that the O(reads) pass overlaps the copies in flight.
-fgb_status check_raw(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw, uint64_t r0,
-                     uint64_t r1, uint64_t* prev_end) {
-  uint64_t pe = *prev_end;
-  uint32_t bad = 0;
-  for (uint64_t r = r0; r < r1; ++r) {
-    const fgb_raw_read& rr = raw->raw_reads[r];
-    bad |= static_cast<uint32_t>(rr.src_off & 1u) | (rr.src_off < pe) |
-           (rr.src_off + rr.raw_len > raw->n_raw) | (FGB_READ_LEN(in->reads[r]) > rr.raw_len);
-    pe = rr.src_off + rr.raw_len;
-  }
-  *prev_end = pe;
-  if (bad) {
-    h->last_error = "fgb_raw_columns: raw spans must be even-aligned, ascending, inside the columns and at least as long as their rows";
-    return FGB_ERR_LAYOUT;
-  }
   return FGB_OK;
 }
 
@@ -512,7 +501,7 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
   if (fmt == HostFormat::kBam4 &&
       (!in->reads || !raw || !raw->seq4 || !raw->quals_raw || !raw->raw_reads))
     return FGB_ERR_INVALID_ARG;
-  uint64_t raw_prev_end = 0;
+
   if (!in->tiles || !in->units || !in->reads || (fmt != HostFormat::kBam4 && !in->bases) ||
       (fmt == HostFormat::kBytes && !in->quals) || !out->base ||
       !out->qual || !out->depth || !out->errors)
@@ -595,10 +584,13 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
     } else if (fmt == HostFormat::kBam4) {
       // raw span of this chunk's reads (ascending by construction), origin aligned down to 32 bases
       const uint64_t rf = first.read_begin, rl = r1;           // absolute read range [rf, rl)
-      if ((st = check_raw(h, in, raw, rf, rl, &raw_prev_end)) != FGB_OK) return st;
       if (rl > rf) {
         const uint64_t a0 = raw->raw_reads[rf].src_off & ~31ull;
         const uint64_t a1 = raw->raw_reads[rl - 1].src_off + raw->raw_reads[rl - 1].raw_len;
+        if (a1 < a0 || a1 > raw->n_raw) {
+          h->last_error = "fgb_raw_columns: raw spans must ascend with the reads and stay inside the columns";
+          return FGB_ERR_LAYOUT;
+        }
         const uint64_t nraw = a1 - a0;
         if ((st = ensure(h, &sl.seq4, &sl.cap_seq4, nraw / 2 + 16)) != FGB_OK) return st;
         if ((st = ensure(h, &sl.qraw, &sl.cap_qraw, nraw + 16)) != FGB_OK) return st;
@@ -644,6 +636,8 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
       ua.bases = const_cast<uint8_t*>(db.bases);
       ua.quals = const_cast<uint8_t*>(db.quals);
       ua.read_begin = rf; ua.read_end = r1;
+      ua.raw_lo = a0;
+      ua.raw_hi = raw->raw_reads[r1 - 1].src_off + raw->raw_reads[r1 - 1].raw_len;
       ua.min_q = raw->min_input_base_quality;
       if ((st = launch_unpack_bam4(h, ua, s)) != FGB_OK) return st;
     }
@@ -736,6 +730,7 @@ fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_
   ua.seq4 = raw->seq4; ua.quals_raw = raw->quals_raw; ua.raw_reads = raw->raw_reads;
   ua.reads = in->reads; ua.bases = bases; ua.quals = quals;
   ua.read_begin = 0; ua.read_end = in->n_reads;
+  ua.raw_lo = 0; ua.raw_hi = raw->n_raw;
   ua.min_q = raw->min_input_base_quality;
   return launch_unpack_bam4(h, ua, static_cast<cudaStream_t>(stream));
 }
@@ -772,6 +767,16 @@ fgb_status fgb_wait(fgb_handle* h) {
   h->submit_pending = false;
   FGB_CUDA(h, cudaSetDevice(h->device));
   for (int s = 0; s < kSlots; ++s) FGB_CUDA(h, cudaStreamSynchronize(h->slots[s].stream));
+  if (h->bam4_pending) {               // the unpack kernel validates the raw spans where it reads them
+    h->bam4_pending = false;
+    uint32_t bad = 0;
+    FGB_CUDA(h, cudaMemcpy(&bad, h->d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+    if (bad) {
+      FGB_CUDA(h, cudaMemset(h->d_bad, 0, sizeof(uint32_t)));
+      h->last_error = "fgb_raw_columns: a raw span is odd-aligned, runs past the columns or is shorter than its row";
+      return FGB_ERR_LAYOUT;
+    }
+  }
   return FGB_OK;
 }
 

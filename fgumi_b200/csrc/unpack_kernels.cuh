@@ -58,6 +58,8 @@ struct Bam4Args {
   uint8_t* bases;               // byte columns being built (biased by the chunk origin)
   uint8_t* quals;
   uint64_t read_begin, read_end;   // absolute read range of this launch
+  uint64_t raw_lo, raw_hi;      // raw index range [raw_lo, raw_hi) that is resident (bounds check)
+  uint32_t* bad;                // set to 1 when a raw span breaks the layout rules (read is skipped)
   uint32_t min_q;               // min_input_base_quality (0 = no masking)
 };
 
@@ -81,6 +83,11 @@ __global__ void __launch_bounds__(256) unpack_bam4_kernel(const Bam4Args a) {
     const uint64_t d = a.reads[r];
     const uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
     const uint64_t off = d >> 16;
+    // layout rules of fgb_raw_columns, checked where the data is touched (no host pass over the reads)
+    if ((rr.src_off & 1u) || rr.src_off < a.raw_lo || rr.src_off + rr.raw_len > a.raw_hi || len > rr.raw_len) {
+      if (lane == 0) atomicOr(a.bad, 1u);
+      continue;
+    }
     const bool rev = rr.flags & 1u;
     const uint8_t* tab = lut + (rev ? 16 : 0);
     const uint32_t words = (len + 7u) >> 3;

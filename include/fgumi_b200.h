@@ -229,8 +229,11 @@ typedef struct fgb_raw_columns {
   uint64_t n_raw;                /* raw bases in the columns                                            */
   const uint8_t* seq4;           /* (n_raw + 1) / 2 bytes, base i in the high (i even) / low nibble     */
   const uint8_t* quals_raw;      /* n_raw bytes                                                         */
-  const fgb_raw_read* raw_reads; /* n_reads entries; src_off ascending, spans not overlapping;
-                                    reads[r] length <= raw_reads[r].raw_len                             */
+  const fgb_raw_read* raw_reads; /* n_reads entries in read order (chunks are cut along it, so spans
+                                    should ascend); src_off even, inside the columns, and
+                                    reads[r] length <= raw_len -- checked on the device where the
+                                    span is read: a violation skips the read and makes the next
+                                    fgb_wait return FGB_ERR_LAYOUT                                      */
   uint8_t min_input_base_quality;/* 0 = no masking (CODEC)                                              */
   uint8_t reserved[7];
 } fgb_raw_columns;

@@ -366,3 +366,22 @@ def test_small_depth_dissent_stress(fg, pre, post):
     assert np.array_equal(got.depth[:n], od[:n]) and np.array_equal(got.errors[:n], oe[:n])
     # the certified tail decides almost everything the proofs leave open
     assert st["exact_positions"] < 0.05 * st["positions"]
+
+
+def test_bam4_bad_raw_span_is_reported_at_wait(fg):
+    """A raw span that runs past the columns is caught by the unpack kernel (the read is skipped) and
+    surfaces as FGB_ERR_LAYOUT from the next fgb_wait; the handle stays usable."""
+    units = [[(b"ACGTACGTAC", bytes([30] * 10), False, 10)] * 3 for _ in range(50)]
+    layout, raw = fg.pack_raw_reads(units, 1, 10)
+    eng = fg.Engine(0, 45, 40, 1, 2)
+    out = fg.HostColumns.alloc(layout.n_out)
+    raw.raw_reads["raw_len"][7] = 4          # shorter than its 10-base row
+    eng.submit_bam4(layout, raw, out)
+    with pytest.raises(fg.lib.FgbError) as ei:
+        eng.wait()
+    assert ei.value.status == fg.lib.FGB_ERR_LAYOUT
+    raw.raw_reads["raw_len"][7] = 10
+    eng.submit_bam4(layout, raw, out)
+    eng.wait()
+    assert bytes(out.base[:10]) == b"ACGTACGTAC"
+    eng.close()
