@@ -375,3 +375,85 @@ def test_codec_combine_rules():  # codec_caller.rs:1068-1149
     assert d == [5, 5, 5, 5, 3, 2, 0, 2]
     assert e == [0, 1 + 2, 1 + 3, 0 + 2, 1, 0, 0, 0]
     assert nb == 4 and nd == 3
+
+
+# ------------------------------------------------------------------ more of duplex_caller.rs
+def _duplex_cols(ab, aq, ad, ae, bb, bq, bd, be, n_source=-1):
+    """duplex_combine with explicit depth / error columns (approximate error branch by default)."""
+    L = O.load()
+    n = min(len(ab), len(bb))
+    A = [np.frombuffer(ab, np.uint8).copy(), np.array(aq, np.uint8), np.array(ad, np.uint16), np.array(ae, np.uint16)]
+    B = [np.frombuffer(bb, np.uint8).copy(), np.array(bq, np.uint8), np.array(bd, np.uint16), np.array(be, np.uint16)]
+    ob = np.zeros(n, np.uint8); oq = np.zeros(n, np.uint8); oe = np.zeros(n, np.uint16)
+    L.orc_duplex_combine(*[x.ctypes.data for x in A], *[x.ctypes.data for x in B], n, None, None, n_source,
+                         ob.ctypes.data, oq.ctypes.data, oe.ctypes.data)
+    return bytes(ob), list(oq), list(oe)
+
+
+def _duplex_arms(ab, aq, ad, ae, bb, bq, bd, be):
+    """duplex_consensus(Some/None, Some/None, None): status, bases, quals, errors."""
+    L = O.load()
+    la, lb = len(ab), len(bb)
+    A = [np.frombuffer(ab, np.uint8).copy(), np.array(aq, np.uint8), np.array(ad, np.uint16), np.array(ae, np.uint16)]
+    B = [np.frombuffer(bb, np.uint8).copy(), np.array(bq, np.uint8), np.array(bd, np.uint16), np.array(be, np.uint16)]
+    cap = max(la, lb, 1)
+    ob = np.zeros(cap, np.uint8); oq = np.zeros(cap, np.uint8); oe = np.zeros(cap, np.uint16)
+    n = C.c_size_t()
+    st = L.orc_duplex_job(*[x.ctypes.data for x in A], la, *[x.ctypes.data for x in B], lb, None, None, 0,
+                          ob.ctypes.data, oq.ctypes.data, oe.ctypes.data, C.addressof(n))
+    return st, bytes(ob[:n.value]), list(oq[:n.value]), list(oe[:n.value])
+
+
+def test_duplex_n_bases_and_mixed():                 # :2659-2686, :2968-3001
+    b, q, _ = _duplex(b"ANAA", [20] * 4, b"AANA", [20] * 4)
+    assert b == b"ANNA" and q[1] == 2 and q[2] == 2
+    b, q, _ = _duplex(b"ANGT", [30] * 4, b"TNCG", [25] * 4)
+    assert b == b"ANGT" and q == [5, 2, 5, 5]
+
+
+def test_duplex_quality_capping_and_threshold():     # :2714-2766, :3003-3031
+    assert _duplex(b"AAA", [50, 60, 93], b"AAA", [50, 60, 93])[1] == [93, 93, 93]
+    b, q, _ = _duplex(b"ACGT", [5, 4, 3, 10], b"TGCA", [3, 2, 2, 8])     # differences of 2, 2, 1, 2 all mask
+    assert b == b"NNNN" and q == [2, 2, 2, 2]
+    b, q, _ = _duplex(b"AAAA", [25] * 4, b"TTTT", [25] * 4)
+    assert b == b"NNNN" and q == [2, 2, 2, 2]
+    assert _duplex(b"AAAA", [45] * 4, b"AAAA", [20] * 4)[1] == [65] * 4  # :2768-2808 deep vs shallow strand
+
+
+def test_duplex_consensus_arms():                    # :4300-4337, :4702-4731, :5112-5173
+    # (a strand that is None never reaches the combine here: the host emits the survivor directly;
+    #  what the arms function decides is the "no coverage inside the truncated region" rule, :852-882)
+    st, b, q, e = _duplex_arms(b"ACGTAC", [30] * 6, [5] * 6, [0] * 6, b"ACGT", [25] * 4, [4] * 4, [0] * 4)
+    assert st == 0 and len(b) == 4 and len(q) == 4                       # both: truncated to the shorter strand
+    st, b, q, e = _duplex_arms(b"ACGTAC", [30] * 6, [0, 0, 0, 0, 5, 5], [0] * 6, b"TGCA", [25] * 4, [4] * 4, [0] * 4)
+    assert st == 2 and b == b"TGCA"                                      # AB has no depth in [0,4): BA only
+    st, b, q, e = _duplex_arms(b"AC", [30, 30], [0, 0], [0, 0], b"AC", [30, 30], [5, 5], [0, 0])
+    assert st == 2 and b == b"AC" and q == [30, 30]
+    st, b, q, e = _duplex_arms(b"ACGT", [30, 31, 32, 33], [5] * 4, [0, 1, 0, 1], b"TTTT", [9] * 4, [0] * 4, [0] * 4)
+    assert st == 1 and (b, q, e) == (b"ACGT", [30, 31, 32, 33], [0, 1, 0, 1])   # AB only: passes through whole
+    st, b, q, e = _duplex_arms(b"AC", [30, 30], [0, 0], [0, 0], b"AC", [30, 30], [0, 0], [0, 0])
+    assert st == 3 and b == b""                                          # neither strand has coverage: None
+    st, b, q, e = _duplex_arms(b"NA", [30, 30], [5, 5], [0, 0], b"AN", [30, 30], [5, 5], [0, 0])
+    assert st == 0 and b == b"NN"                                        # N in either strand masks
+
+
+def test_duplex_error_approximation():               # :4339-4406, :5015-5078
+    _, _, e = _duplex_cols(b"ACGT", [30] * 4, [5] * 4, [1, 0, 2, 0], b"ACGT", [25] * 4, [4] * 4, [0, 1, 0, 2])
+    assert e == [1, 1, 2, 2]                                             # agreement: errors add
+    b, _, e = _duplex_cols(b"AT", [30, 40], [5, 5], [1, 2], b"AC", [25, 30], [4, 4], [0, 1])
+    assert b == b"AT" and e[1] == 5                                      # a wins: a_err + (b_depth - b_err)
+
+
+def test_cap_quality_and_is_error_semantics():       # :4481-4501
+    # cap_quality through the combine: sums clamp at 93, differences at 2
+    assert _duplex(b"A", [93], b"A", [93])[1] == [93] and _duplex(b"A", [3], b"C", [2])[1] == [2]
+    # is_error: N on either side is not an error (exact recount against source rows)
+    L = O.load()
+    ab = np.frombuffer(b"AN", np.uint8).copy(); q = np.array([30, 30], np.uint8)
+    d = np.array([2, 2], np.uint16); z = np.zeros(2, np.uint16)
+    rows = [np.frombuffer(b"TN", np.uint8).copy(), np.frombuffer(b"AA", np.uint8).copy()]
+    ptrs = (C.c_void_p * 2)(*[r.ctypes.data for r in rows]); lens = (C.c_size_t * 2)(2, 2)
+    ob = np.zeros(2, np.uint8); oq = np.zeros(2, np.uint8); oe = np.zeros(2, np.uint16)
+    L.orc_duplex_combine(ab.ctypes.data, q.ctypes.data, d.ctypes.data, z.ctypes.data, ab.ctypes.data, q.ctypes.data,
+                         d.ctypes.data, z.ctypes.data, 2, ptrs, lens, 2, ob.ctypes.data, oq.ctypes.data, oe.ctypes.data)
+    assert list(oe) == [1, 0]        # 'T' vs consensus 'A' counts; source 'N' does not; consensus N counts nothing

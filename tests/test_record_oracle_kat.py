@@ -203,3 +203,68 @@ def test_rx_consensus_and_cell_barcode():
     rec, = parse_records(c.consensus_reads(reads)[0])
     assert rec["tags"][b"RX"] == b"ACGT-TTTT" and rec["tags"][b"CB"] == b"CELL1"
     assert rec["tag_order"] == [b"RG", b"cD", b"cM", b"cE", b"cd", b"ce", b"MI", b"CB", b"RX"]
+
+
+# ---- further ports of the reference's caller tests -------------------------------------------
+def test_more_source_read_cases():
+    # FF pair: no mate-overlap clip (:3021-3057)
+    r = make_record(flags=P | F1, pos=10, mate_ref_id=0, mate_pos=0, tlen=50, seq=b"A" * 50,
+                    tags=[(b"MC", "Z", b"50M")])
+    sr, clip = sr_of(r, min_input_base_quality=2)
+    assert clip == 0 and len(sr.bases) == 50
+    # FR pair whose reads carry the same insertion: nothing to clip (:3061-3094)
+    r = make_record(flags=P | F1 | MREV, pos=0, mate_ref_id=0, mate_pos=0, tlen=80, seq=b"A" * 100,
+                    cigar="40M20I40M", tags=[(b"MC", "Z", b"40M20I40M")])
+    sr, clip = sr_of(r, min_input_base_quality=2)
+    assert len(sr.bases) == 100
+    # quality trim + mask together: "AGC" survives (:3923-3957)
+    sr, _ = sr_of(make_record(seq=b"AGCACGACGT", quals=[30, 30, 30, 2, 5, 2, 3, 20, 2, 6]),
+                  min_input_base_quality=15, trim=True)
+    assert bytes(sr.bases) == b"AGC"
+
+
+def test_read_can_join_several_cigar_groups():               # :3593-3642
+    kept, rej = R.filter_by_alignment(_srs(["50M"] * 2 + ["40M1I9M"] * 3) +
+                                      [R.create_source_read(R.Rec(make_record(seq=b"A" * 40, cigar="40M")), 5, 0,
+                                                            R.VanillaOptions(min_input_base_quality=2))])
+    assert len(kept) == 4 and 5 in [k.original_idx for k in kept]       # the 40M prefix read rides with 40M1I9M
+
+
+def test_groups_pairs_and_missing_mate_cigar():
+    def frag_u(name, umi):
+        return frag(name, b"GATTACA", [30] * 7, umi)
+    # one consensus per call, two calls for two UMI groups (:3773-3809)
+    c = make_caller(min_reads=1, min_input_base_quality=2)
+    assert c.consensus_reads([frag_u(b"a", b"G1"), frag_u(b"b", b"G1")])[1] == 1
+    assert c.consensus_reads([frag_u(b"c", b"G2"), frag_u(b"d", b"G2")])[1] == 1
+    assert c.stats.consensus_reads == 2
+    # a pair without MC tags still gives R1 + R2 (:3999-4053)
+    r1 = make_record(name=b"READ1", flags=P | F1 | MREV, pos=0, mate_ref_id=0, mate_pos=99, tlen=109, seq=b"A" * 10,
+                     tags=[(b"MI", "Z", b"GATTACA")])
+    r2 = make_record(name=b"READ1", flags=P | F2 | REV, pos=99, mate_ref_id=0, mate_pos=0, tlen=-109, seq=b"A" * 10,
+                     tags=[(b"MI", "Z", b"GATTACA")])
+    c = make_caller(min_reads=1, min_input_base_quality=2)
+    assert c.consensus_reads([r1, r2])[1] == 2
+
+
+def test_rx_consensus_uses_surviving_reads_only():           # :4058-4154
+    def rd(name, cigar, rx):
+        return make_record(name=name, pos=0, seq=b"A" * 10, cigar=cigar, tags=[(b"MI", "Z", b"AAA"), (b"RX", "Z", rx)])
+    c = make_caller(min_reads=1, min_input_base_quality=2)
+    data, n = c.consensus_reads([rd(b"READ1", "10M", b"TTT"), rd(b"READ2", "5M5D5M", b"ATT"),
+                                 rd(b"READ3", "10M", b"TAT"), rd(b"READ4", "4M2I4M", b"TTA")])
+    rec, = parse_records(data)
+    assert n == 1 and rec["tags"][b"RX"] == b"TNT"          # TTT + TAT; the two minority alignments do not vote
+
+
+def test_orphan_when_r1_fails_and_r2_succeeds():             # :4500-4640 (mirror of :4340)
+    def pair(i):
+        r1 = make_record(name=b"q%d" % i, flags=P | F1 | MREV, pos=100, mate_ref_id=0, mate_pos=300, tlen=250,
+                         seq=b"ACGTACGTAC", tags=[(b"MI", "Z", b"U"), (b"MC", "Z", b"10M")])
+        r2 = make_record(name=b"q%d" % i, flags=P | F2 | REV, pos=300, mate_ref_id=0, mate_pos=100, tlen=-250,
+                         seq=b"TTGCATTGCA", tags=[(b"MI", "Z", b"U"), (b"MC", "Z", b"10M")])
+        return [r1, r2]
+    c = make_caller(min_reads=2, min_consensus_base_quality=2)
+    data, n = c.consensus_reads(pair(0) + [pair(1)[1]])          # two R2s, one R1
+    assert n == 0 and data == b""
+    assert c.stats.rejections == {"InsufficientReads": 1, "OrphanConsensus": 2} and c.stats.filtered_reads == 3
