@@ -268,3 +268,22 @@ def test_orphan_when_r1_fails_and_r2_succeeds():             # :4500-4640 (mirro
     data, n = c.consensus_reads(pair(0) + [pair(1)[1]])          # two R2s, one R1
     assert n == 0 and data == b""
     assert c.stats.rejections == {"InsufficientReads": 1, "OrphanConsensus": 2} and c.stats.filtered_reads == 3
+
+
+# ---- consensus_umis / SimpleConsensusCaller, simple_umi.rs:257-372 (ports of fgbio's SimpleConsensusCallerTest)
+def test_simple_consensus_caller_kats():
+    cu = lambda umis: R.consensus_umis(list(umis), lambda pre, post, b, q: O.builder_call(pre, post, b, q)[:2])
+    assert cu(["A", "A"]) == "A" and cu(["GATTACA", "GATTACA"]) == "GATTACA"                    # :290-297
+    assert cu(["A", "C", "G", "T"]) == "N"                                                       # :300-312 tie
+    assert cu(["A", "C", "C", "C"]) == "C" and cu(["C", "C", "C", "A"]) == "C"
+    assert cu(["GATTACA"] * 3 + ["NNNNNNN"]) == "GATTACA"                                        # Ns do not vote
+    assert cu(["GATT-ACA"] * 3) == "GATT-ACA" and cu(["XGAT", "XGAT"]) == "XGAT" and cu(["GATY", "GATY"]) == "GATY"
+    assert cu(["AACC", "CCAA"]) == "NNNN"                                                        # :436-448
+    assert cu(["ACGT", "ACGT", "CAGT"]) == "ACGT" and cu(["ACGT"] * 3 + ["ACGG"]) == "ACGT"      # :392-400, :451-462
+    assert cu([]) == "" and cu(["ACGT"]) == "ACGT"                                               # :236-245
+    for bad in (["A", "AC"], ["GATT-ACA", "GATT-ACA", "GATTAACA"], ["GATT-ACA", "GATT+ACA"]):    # the panics :257-287
+        try:
+            cu(bad)
+        except AssertionError:
+            continue
+        raise AssertionError("expected a failure for %r" % (bad,))
