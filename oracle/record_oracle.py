@@ -1080,6 +1080,22 @@ class CodecCallerOracle:
         return [inf for i, inf in enumerate(infos) if i in best]
 
     @staticmethod
+    def check_overlap_phase(r1: ClippedInfo, r2: ClippedInfo, ov_start: int, ov_end: int) -> bool:   # :911-946
+        a = read_pos_at_ref_pos(r1.clipped_cigar, r1.adjusted_pos, ov_start, True)
+        b = read_pos_at_ref_pos(r2.clipped_cigar, r2.adjusted_pos, ov_start, True)
+        c = read_pos_at_ref_pos(r1.clipped_cigar, r1.adjusted_pos, ov_end, True)
+        d = read_pos_at_ref_pos(r2.clipped_cigar, r2.adjusted_pos, ov_end, True)
+        return None not in (a, b, c, d) and (a - b) == (c - d)
+
+    @staticmethod
+    def compute_consensus_length(pos: ClippedInfo, neg: ClippedInfo, ov_end: int) -> Optional[int]:   # :949-968
+        pp = read_pos_at_ref_pos(pos.clipped_cigar, pos.adjusted_pos, ov_end, False)
+        nn = read_pos_at_ref_pos(neg.clipped_cigar, neg.adjusted_pos, ov_end, False)
+        if pp is None or nn is None:
+            return None
+        return pp + neg.clipped_seq_len - nn
+
+    @staticmethod
     def _source_row(r: Rec, inf: ClippedInfo):          # to_source_read_for_codec_raw :414-469
         bases, quals = r.sequence(), r.quals()
         clip = min(inf.clip_amount, len(bases))
@@ -1158,20 +1174,14 @@ class CodecCallerOracle:
         if ov_end - ov_start + 1 < self.min_duplex_length:
             self._reject(len(r1s) + len(r2s), "InsufficientOverlap")
             return b"", 0
-        a = read_pos_at_ref_pos(l1.clipped_cigar, l1.adjusted_pos, ov_start, True)   # :911-946
-        b = read_pos_at_ref_pos(l2.clipped_cigar, l2.adjusted_pos, ov_start, True)
-        c = read_pos_at_ref_pos(l1.clipped_cigar, l1.adjusted_pos, ov_end, True)
-        d = read_pos_at_ref_pos(l2.clipped_cigar, l2.adjusted_pos, ov_end, True)
-        if None in (a, b, c, d) or (a - b) != (c - d):
+        if not self.check_overlap_phase(l1, l2, ov_start, ov_end):
             self._reject(len(r1s) + len(r2s), "IndelErrorBetweenStrands")
             return b"", 0
         r2_neg = bool(l2.flags & REVERSE)
-        pp = read_pos_at_ref_pos(lpos.clipped_cigar, lpos.adjusted_pos, ov_end, False)   # :949-968
-        nn = read_pos_at_ref_pos(lneg.clipped_cigar, lneg.adjusted_pos, ov_end, False)
-        if pp is None or nn is None:
+        cons_len = self.compute_consensus_length(lpos, lneg, ov_end)
+        if cons_len is None:
             self._reject(len(r1s) + len(r2s), "IndelErrorBetweenStrands")
             return b"", 0
-        cons_len = pp + lneg.clipped_seq_len - nn
         rows1 = [self._source_row(recs[i.raw_idx], i) for i in r1s]
         rows2 = [self._source_row(recs[i.raw_idx], i) for i in r2s]
         ss1 = self.vote(rows1, self.ss_opt)

@@ -264,3 +264,133 @@ def test_read_pos_at_ref_pos():                      # :3258-3370, :3916-3950
     assert f(cig, 100, 100, False) == 4
     cig = enc([(H, 5), (M, 10)])
     assert f(cig, 100, 100, False) == 1
+
+
+# ---- more helper KATs (create_test_paired_read based) ----
+def paired_read(name, seq, qual, first, rev, mate_rev, start, cig):
+    """create_test_paired_read, codec_caller.rs:1618-1704: 1-based start, 200 bp insert, MI tag."""
+    flags = P | (F1 if first else F2) | (REV if rev else 0) | (MREV if mate_rev else 0)
+    ref_len = sum(n for k, n in cig if k in (M, D, N_, 7, 8))
+    if rev:
+        mate1, tlen = max(start - 200 + ref_len, 1), -200
+    else:
+        mate1, tlen = max(start + 200 - ref_len, 1), 200
+    return make_record(name=name, flags=flags, pos=start - 1, mapq=60, cigar=enc(cig), seq=seq,
+                       quals=bytes(qual), mate_ref_id=0, mate_pos=mate1 - 1, tlen=tlen,
+                       tags=[(b"MI", "Z", b"UMI123")])
+
+
+def infos(recs):
+    """The test-only wrappers of codec_caller.rs:1477-1530 build ClippedRecordInfo with clip 0."""
+    return [R.CodecCallerOracle._clipped_info(R.Rec(b), i, 0) for i, b in enumerate(recs)]
+
+
+def test_is_fr_pair():                                # :1707-1751
+    assert R.is_fr_pair(R.Rec(paired_read(b"read1", b"ACGT", b"####", True, False, True, 100, [(M, 4)])))
+    assert R.is_fr_pair(R.Rec(paired_read(b"read1", b"ACGT", b"####", True, True, False, 100, [(M, 4)])))
+    assert not R.is_fr_pair(R.Rec(paired_read(b"read1", b"ACGT", b"####", True, False, False, 100, [(M, 4)])))
+
+
+def test_filter_to_most_common_alignment():           # :1754-1990
+    def run(reads):
+        o = make_codec_oracle()
+        inf = infos(reads)
+        kept = o._filter(inf)
+        return o, [reads[k.raw_idx] for k in kept]
+    mk = lambda nm, cig, seq=b"ACGT", rev=False: paired_read(nm, seq, b"#" * len(seq), True, rev, not rev, 100, cig)
+    # three 4M reads and one with a deletion -> the odd one is dropped (:1754-1814)
+    o, kept = run([mk(b"r1", [(M, 4)]), mk(b"r2", [(M, 4)]), mk(b"r3", [(M, 4)]),
+                   mk(b"r4", [(M, 2), (D, 1), (M, 2)])])
+    assert len(kept) == 3 and o.rejections == {"MinorityAlignment": 1}
+    # 2 x 4M against 2 x 3M1D1M: the tie goes to the smaller CIGAR, 3 < 4 (:1817-1908)
+    o, kept = run([mk(b"r1_4M", [(M, 4)]), mk(b"r2_4M", [(M, 4)]),
+                   mk(b"r3_del", [(M, 3), (D, 1), (M, 1)]), mk(b"r4_del", [(M, 3), (D, 1), (M, 1)])])
+    assert [R.Rec(k).name for k in kept] == [b"r3_del", b"r4_del"]
+    assert o.rejections == {"MinorityAlignment": 2} and o.reads_filtered == 2
+    # negative-strand reads compare their REVERSED cigars: 3M1I2M -> 2M1I3M wins (:1910-1990)
+    a, b = [(M, 3), (I, 1), (M, 2)], [(M, 2), (I, 1), (M, 3)]
+    o, kept = run([mk(b"r1_groupA", a, b"ACGTAC", True), mk(b"r2_groupA", a, b"ACGTAC", True),
+                   mk(b"r3_groupB", b, b"ACGTAC", True), mk(b"r4_groupB", b, b"ACGTAC", True)])
+    assert [R.Rec(k).name for k in kept] == [b"r1_groupA", b"r2_groupA"]
+    assert o.rejections == {"MinorityAlignment": 2}
+    # the same two groups on the forward strand: group B's 2M.. is the smaller one
+    o, kept = run([mk(b"r1_groupA", a, b"ACGTAC"), mk(b"r2_groupA", a, b"ACGTAC"),
+                   mk(b"r3_groupB", b, b"ACGTAC"), mk(b"r4_groupB", b, b"ACGTAC")])
+    assert [R.Rec(k).name for k in kept] == [b"r3_groupB", b"r4_groupB"]
+
+
+def test_to_source_read_for_codec():                  # :2980-3100
+    row = R.CodecCallerOracle._source_row
+    ci = R.CodecCallerOracle._clipped_info
+    fwd = R.Rec(paired_read(b"read1", b"ACGT", [30, 31, 32, 33], True, False, True, 100, [(M, 4)]))
+    assert row(fwd, ci(fwd, 0, 0)) == (b"ACGT", bytes([30, 31, 32, 33]))
+    rev = R.Rec(paired_read(b"read1", b"ACGT", [30, 31, 32, 33], True, True, False, 100, [(M, 4)]))
+    assert row(rev, ci(rev, 1, 0)) == (b"ACGT", bytes([33, 32, 31, 30]))
+    rev = R.Rec(paired_read(b"read1", b"AACC", [10, 20, 30, 40], True, True, False, 100, [(M, 4)]))
+    assert row(rev, ci(rev, 2, 0)) == (b"GGTT", bytes([40, 30, 20, 10]))
+    # clipping at or beyond the read length leaves an empty source read, from either end
+    for clip, from_start in ((10, False), (10, True), (4, False)):
+        inf = ci(fwd, 0, 0)
+        inf.clip_amount, inf.clip_from_start = clip, from_start
+        assert row(fwd, inf) == (b"", b"")
+
+
+def test_check_overlap_phase():                       # :3371-3437, :3952-4000
+    f = R.CodecCallerOracle.check_overlap_phase
+    a30, q30 = b"A" * 30, [30] * 30
+    r1 = paired_read(b"read1", a30, q30, True, False, True, 100, [(M, 30)])
+    r2 = paired_read(b"read2", a30, q30, False, True, False, 110, [(M, 30)])
+    assert f(*infos([r1, r2]), 110, 129)
+    r2 = paired_read(b"read2", a30, q30, False, True, False, 100, [(M, 15), (D, 5), (M, 15)])
+    assert f(*infos([r1, r2]), 100, 129) is False      # runs; 1-1 != 30-25
+    a50 = b"A" * 50
+    r1 = make_record(name=b"r1", flags=0, pos=99, cigar=enc([(M, 50)]), seq=a50, quals=bytes([30] * 50))
+    r2 = make_record(name=b"r2", flags=0, pos=119, cigar=enc([(M, 50)]), seq=a50, quals=bytes([30] * 50))
+    assert f(*infos([r1, r2]), 120, 149)
+    r2 = make_record(name=b"r2", flags=0, pos=119, cigar=enc([(M, 15), (D, 2), (M, 33)]), seq=b"A" * 48,
+                     quals=bytes([30] * 48))
+    assert not f(*infos([r1, r2]), 120, 149)
+
+
+def test_compute_codec_consensus_length():            # :3748-3817
+    f = R.CodecCallerOracle.compute_consensus_length
+    a30, q30 = b"A" * 30, [30] * 30
+    pos = paired_read(b"pos", a30, q30, True, False, True, 100, [(M, 30)])
+    neg = paired_read(b"neg", a30, q30, False, True, False, 110, [(M, 30)])
+    assert f(*infos([pos, neg]), 129) == 40            # 30 + 30 - 20
+    pos = paired_read(b"pos", a30, q30, True, False, True, 100, [(M, 15), (D, 5), (M, 15)])
+    neg = paired_read(b"neg", a30, q30, False, True, False, 100, [(M, 30)])
+    assert f(*infos([pos, neg]), 116) is None          # 116 falls inside the deletion
+
+
+def test_pad_and_reverse_complement_ss():             # :3439-3523, :3632-3659
+    ss = (b"ACGT", bytes([30, 31, 32, 33]), [5, 6, 7, 8], [0, 1, 0, 1])
+    p = R._pad_ss(ss, 8, False)
+    assert p[0] == b"ACGTnnnn" and p[1][4:] == bytes(4) and p[2][4:] == [0] * 4 and p[3][4:] == [0] * 4
+    p = R._pad_ss(ss, 8, True)
+    assert p[0] == b"nnnnACGT" and p[1][:4] == bytes(4) and p[2][:4] == [0] * 4 and p[2][4:] == [5, 6, 7, 8]
+    assert R._pad_ss(ss, 4, False) == ss and R._pad_ss(ss, 2, False) == ss
+    rc = R._rc_ss((b"ACGT", bytes([10, 20, 30, 40]), [1, 2, 3, 4], [5, 6, 7, 8]))
+    assert rc == (b"ACGT", bytes([40, 30, 20, 10]), [4, 3, 2, 1], [8, 7, 6, 5])
+    assert R._rc_ss((b"AACC", bytes(4), [0] * 4, [0] * 4))[0] == b"GGTT"
+
+
+def test_mask_consensus_quals_query_based():          # :3526-3575 through the C++ oracle
+    L = O.load()
+    cons_b = np.frombuffer(b"ACGT", np.uint8).copy()
+    cons_q = np.full(4, 30, np.uint8)
+    r1 = np.frombuffer(b"NCGT", np.uint8).copy()
+    r2 = np.frombuffer(b"ACGN", np.uint8).copy()
+    L.orc_codec_mask(cons_b.ctypes.data, cons_q.ctypes.data, 4, r1.ctypes.data, r2.ctypes.data, 10, -1, 5)
+    assert cons_q.tolist() == [10, 30, 30, 10]
+    # lowercase padding is NOT a no-call for this check (NO_CALL_BASE is b'N', :1195-1198)
+    cons_q[:] = 30
+    r1 = np.frombuffer(b"nCGT", np.uint8).copy()
+    L.orc_codec_mask(cons_b.ctypes.data, cons_q.ctypes.data, 4, r1.ctypes.data, r2.ctypes.data, 10, -1, 5)
+    assert cons_q.tolist() == [30, 30, 30, 10]
+    # outer-bases masking takes the min with the outer quality on both ends (:1206-1211)
+    cons_b = np.frombuffer(b"ACGTACGT", np.uint8).copy()
+    cons_q = np.array([30, 3, 30, 30, 30, 30, 30, 30], np.uint8)
+    r = np.frombuffer(b"ACGTACGT", np.uint8).copy()
+    L.orc_codec_mask(cons_b.ctypes.data, cons_q.ctypes.data, 8, r.ctypes.data, r.ctypes.data, -1, 5, 2)
+    assert cons_q.tolist() == [5, 3, 30, 30, 30, 30, 5, 5]
