@@ -13,7 +13,10 @@ constexpr int kStages = 2;
 constexpr uint32_t kTileCapBytes = 20480;  // per column per stage
 constexpr uint32_t kTileMaxReads = 512;    // read descriptors per stage (8 B each)
 constexpr uint32_t kTileMaxUnits = 127;    // unit descriptors per stage (16 B each, +1 sentinel)
-constexpr uint32_t kWarpQueueCap = 96;     // undecided positions buffered per warp per tile
+#ifndef FGB_WARP_QUEUE_CAP
+#define FGB_WARP_QUEUE_CAP 96
+#endif
+constexpr uint32_t kWarpQueueCap = FGB_WARP_QUEUE_CAP;     // undecided positions buffered per warp per tile
 constexpr uint32_t kQtEntries = 256;       // fast-path quality threshold table, indexed by min(n,255)
 
 constexpr uint32_t kTileFlagDirect = 1u;   // unit too large for a stage: kernel reads it from HBM

@@ -198,9 +198,16 @@ __device__ __forceinline__ bool is_acgt_upper(uint32_t b) {
   return t < 32u && ((0x0010008Au >> t) & 1u);
 }
 // BASE_TO_INDEX, base_builder.rs:204-215 (case-insensitive A,C,G,T -> 0..3, else 4)
+// Branch-free: a compare chain here becomes data-dependent branches, and lanes that split on the
+// base do not reconverge before the end of the out-of-line resolver.
 __device__ __forceinline__ uint32_t base_to_index(uint32_t b) {
-  uint32_t u = b & 0xDFu;
+  const uint32_t u = b & 0xDFu;
+#ifdef FGB_B2I_BRANCHY
   return u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : u == 'T' ? 3u : 4u;
+#else
+  const uint32_t x = (u >> 1) & 3u;            // A 0, C 1, T 2, G 3
+  return is_acgt_upper(u) ? (x ^ (x >> 1)) : 4u;
+#endif
 }
 
 struct Called {
@@ -614,8 +621,28 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
     }
     shallow = nmax <= 64u;
   }
-  if (shallow) slow_pass_g<M, 8u>(a, S, st, tv, wqueue, qn, lane, ls);
-  else slow_pass_g<M, 32u>(a, S, st, tv, wqueue, qn, lane, ls);
+#ifndef FGB_SLOW_PER_LANE
+#define FGB_SLOW_PER_LANE 1
+#endif
+#ifndef FGB_LANE_MIN_QUEUE
+#define FGB_LANE_MIN_QUEUE 24u
+#endif
+  if (shallow && (!FGB_SLOW_PER_LANE || qn < FGB_LANE_MIN_QUEUE)) {
+    slow_pass_g<M, 8u>(a, S, st, tv, wqueue, qn, lane, ls);
+  } else if (shallow) {
+    // one lane per queued position: with at most 64 reads the depth loop is short, and 32 positions
+    // per pass beat splitting each pileup over a group of lanes
+    for (uint32_t e = lane; e < qn; e += 32u) {
+      const uint32_t ent = wqueue[e];
+      const uint32_t u = ent >> 16, pos = ent & 0xFFFFu;
+      const fgb_unit un = st.units[u];
+      const Called c = resolve_position<M>(tv, S, un.read_begin, st.units[u + 1].read_begin - un.read_begin,
+                                           pos, a, ls);
+      write_called(a, un.out_off + pos, c);
+    }
+  } else {
+    slow_pass_g<M, 32u>(a, S, st, tv, wqueue, qn, lane, ls);
+  }
 }
 
 // Votes this warp's share of one tile.  Called by the eight consumer warps; `vt` is the thread's

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfgumi_b200.so")
+LIB_PATH = os.environ.get("FGUMI_B200_LIB") or os.path.join(_HERE, "libfgumi_b200.so")   # override: kernel A/B runs
 
 FGB_OK = 0
 FGB_ERR_INVALID_ARG = 1

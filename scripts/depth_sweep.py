@@ -6,9 +6,13 @@ import fgumi_b200 as fg
 from fgumi_b200 import synth
 U = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 minq = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-for spec in ("1", "2", "3", "4", "6", "8", "12", "16", "20", "mixed2-20"):
+SPECS = sys.argv[3].split(",") if len(sys.argv) > 3 else ("1", "2", "3", "4", "6", "8", "12", "16", "20", "mixed2-20", "zipf1-100")
+for spec in SPECS:
     if spec.startswith("mixed"):
         depths = np.repeat(np.random.default_rng(1).integers(2, 21, size=U // 2), 2).astype(np.int64)
+    elif spec.startswith("zipf"):      # BASELINE config 5: P(d) ~ 1/d on 1..100
+        w = 1.0 / np.arange(1, 101)
+        depths = np.random.default_rng(2).choice(np.arange(1, 101), size=U // 4, p=w / w.sum()).astype(np.int64)
     else:
         depths = np.full(U, int(spec), dtype=np.int64)
     tb = synth.device_batch(torch, "cuda:0", depths, 150, 1e-3, seed=7)
