@@ -8,10 +8,15 @@ import fgumi_b200 as fg
 from fgumi_b200 import synth
 
 units = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-depth = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+depth = sys.argv[2] if len(sys.argv) > 2 else "8"
 launches = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 eng = fg.Engine(0, 45, 40, 1, 2)
-tb = synth.device_batch(torch, "cuda:0", np.full(units, depth, np.int64), 150, 1e-3, seed=42)
+if depth.startswith("zipf"):        # BASELINE config 5: P(d) ~ 1/d on 1..100
+    w = 1.0 / np.arange(1, 101)
+    depths = np.random.default_rng(2).choice(np.arange(1, 101), size=units, p=w / w.sum()).astype(np.int64)
+else:
+    depths = np.full(units, int(depth), np.int64)
+tb = synth.device_batch(torch, "cuda:0", depths, 150, 1e-3, seed=42)
 out = fg.DeviceColumns(tb.host.n_out, "cuda:0")
 b, c = tb.struct(), out.struct()
 lib = fg.lib.load()
