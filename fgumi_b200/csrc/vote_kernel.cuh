@@ -621,9 +621,6 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
     }
     shallow = nmax <= 64u;
   }
-#ifndef FGB_DEEP_SPREAD_ITEMS
-#define FGB_DEEP_SPREAD_ITEMS 64u
-#endif
 #ifndef FGB_SLOW_PER_LANE
 #define FGB_SLOW_PER_LANE 1
 #endif
@@ -953,17 +950,10 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteArgs a) {
     Stage& st = S.st[s];
     // rotating item assignment: the partial last round of a tile lands on different warps from
     // tile to tile, so every warp does the same work in the long run
-    uint32_t vt = (tid - rot) & (kVoteThreads - 1);
+    const uint32_t vt = (tid - rot) & (kVoteThreads - 1);
     uint32_t n_items = st.aux[1];
     if (n_items == 0)
       n_items = static_cast<uint32_t>((st.units[st.tile.n_units].out_off - st.units[0].out_off) >> 3);
-#ifndef FGB_NO_DEEP_SPREAD
-    // A tile with this few items holds a handful of deep units.  Consecutive items then go to
-    // different warps (warp w, lane l takes item 8 l + w) instead of consecutive lanes, so that a
-    // unit's undecided positions are spread over all eight warp queues rather than resolved by the
-    // one warp that happened to own the unit.
-    if (n_items <= FGB_DEEP_SPREAD_ITEMS) vt = ((tid & 31u) << 3) | warp;
-#endif
     if (st.tile.flags & kTileFlagDirect) {
       TileView<GlMem> tv;
       tv.bases = a.bases; tv.quals = a.quals;

@@ -165,6 +165,28 @@ def test_zipf_depths(fg):
     check(fg, fg.pack_source_reads(units, 1))
 
 
+def test_deep_units_between_shallow_ones(fg):
+    """Deep units (32-100 reads: tiles of a few dozen items, the whole-warp resolver) interleaved with
+    shallow ones: regular and ragged, heavy dissent (long warp queues), Ns, low qualities, min_reads
+    gates."""
+    from fgumi_b200 import synth
+    rng = np.random.default_rng(31)
+    units = []
+    for d, err in ((40, 1e-3), (3, 1e-2), (100, 5e-3), (33, 0.2), (1, 0.0), (64, 1e-3), (65, 0.05), (32, 0.0), (31, 0.01)):
+        b, q = synth.host_pileup(1, d, 150, err, seed=int(rng.integers(1 << 30)))
+        units.append([(b[0, r].tobytes(), q[0, r].tobytes()) for r in range(d)])
+    batch = fg.pack_source_reads(units, 1)
+    check(fg, batch)
+    check(fg, batch, device_path=True)
+    ragged = _ragged_units(rng, 60, 90, 1, 170)
+    ragged = [u for u in ragged if len(u) >= 20]
+    check(fg, fg.pack_source_reads(ragged, 1))
+    check(fg, fg.pack_source_reads(ragged, 25), min_reads=25, min_cons_q=20)
+    odd = _ragged_units(rng, 30, 80, 30, 60, alphabet=b"ACGTNacgtRY.", qlo=0, qhi=120)
+    odd = [u for u in odd if len(u) >= 32]
+    check(fg, fg.pack_source_reads(odd, 1))
+
+
 def test_oversize_units_take_direct_path(fg):
     """Units too big for a shared-memory stage are voted straight from HBM."""
     from fgumi_b200 import synth
