@@ -43,6 +43,41 @@ class ConsensusFilter:
         return fp
 
 
+class DuplexConsensusFilter:
+    """`fgumi filter` options for duplex consensus reads: each of min_reads, max_read_error_rate and
+    max_base_error_rate takes one to three values for the [duplex, AB, BA] tiers, missing ones filled
+    from the last (filter.rs:20-28, 237-330); AB is the stricter strand tier, BA the lenient one."""
+
+    def __init__(self, min_reads=(1,), max_read_error_rate=(0.025,), max_base_error_rate=(0.1,),
+                 min_base_quality=None, min_mean_base_quality=None, max_no_call_fraction: float = 0.2,
+                 require_single_strand_agreement: bool = False):
+        three = lambda v: (list(v) + [list(v)[-1]] * 3)[:3]
+        self.min_reads, self.max_read_error_rate = three(min_reads), three(max_read_error_rate)
+        self.max_base_error_rate = three(max_base_error_rate)
+        self.min_base_quality, self.min_mean_base_quality = min_base_quality, min_mean_base_quality
+        self.max_no_call_fraction, self.require_ss = max_no_call_fraction, require_single_strand_agreement
+
+    def fill(self, fp: "_l.FgbDuplexFilterParams"):
+        ConsensusFilter(self.min_reads[0], self.max_read_error_rate[0], self.max_base_error_rate[0],
+                        self.min_base_quality, self.min_mean_base_quality, self.max_no_call_fraction).fill(fp.cc)
+        fp.ab_min_reads, fp.ba_min_reads = self.min_reads[1], self.min_reads[2]
+        fp.ab_max_read_error_rate, fp.ba_max_read_error_rate = self.max_read_error_rate[1], self.max_read_error_rate[2]
+        fp.ab_max_base_error_rate, fp.ba_max_base_error_rate = self.max_base_error_rate[1], self.max_base_error_rate[2]
+        fp.require_ss_agreement = 1 if self.require_ss else 0
+        return fp
+
+    def apply(self, record: bytearray):
+        """One assembled record through fgb_filter_record (host code): returns (status, newly masked)."""
+        lib = _l.load()
+        fp = self.fill(_l.FgbDuplexFilterParams())
+        buf = (C.c_uint8 * len(record)).from_buffer(record)
+        masked, status = C.c_uint32(), C.c_uint8()
+        st = lib.fgb_filter_record(C.addressof(buf), len(record), C.byref(fp), C.addressof(masked), C.addressof(status))
+        if st != _l.FGB_OK:
+            raise _l.FgbError(st, "fgb_filter_record")
+        return status.value, masked.value
+
+
 class _Caller:
     """Shared plumbing over fgb_caller_* (add_group / flush / statistics)."""
 
@@ -153,12 +188,16 @@ class DuplexConsensusCaller(VanillaUmiConsensusCaller):
                  error_rate_pre_umi: int = 45, error_rate_post_umi: int = 40,
                  min_input_base_quality: int = 10, produce_per_base_tags: bool = True,
                  trim: bool = False, device: int = 0, cell_tag: bytes = b"",
-                 consensus_call_overlapping_bases: bool = False, n_threads: int = 1):
+                 consensus_call_overlapping_bases: bool = False, n_threads: int = 1,
+                 filter: "DuplexConsensusFilter" = None):
         self._lib = _l.load()
         self._prefix = read_name_prefix.encode()
         self._rg = read_group_id.encode()
         o = _l.FgbCallerOptions()
         o.mode = 1
+        if filter is not None:           # `fgumi duplex | fgumi filter` in one pass
+            o.filter_enabled = 1
+            filter.fill(o.duplex_filter)
         o.n_threads = n_threads
         o.consensus_call_overlapping_bases = 1 if consensus_call_overlapping_bases else 0
         o.error_rate_pre_umi = error_rate_pre_umi

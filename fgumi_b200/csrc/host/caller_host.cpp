@@ -26,6 +26,7 @@
 #include "bam.h"
 #include "overlap.h"
 #include "prep.h"
+#include "record_filter.h"
 
 using namespace fgb;
 using namespace fgb::prep;
@@ -690,6 +691,24 @@ fgb_status write_duplex_record(fgb_caller* c, bam::Writer* w, const DuplexRead& 
   return FGB_OK;
 }
 
+// `fgumi duplex | fgumi filter`, template mode (commands/filter.rs:640-672): the two records of the
+// molecule start at `mark` in ctx->out; both are masked, and both are dropped unless both pass.
+void filter_duplex_template(fgb_caller* ctx, size_t mark) {
+  bool pass = true;
+  size_t p = mark;
+  while (p + 4 <= ctx->out.size()) {
+    const uint32_t bs = bam::rd32(ctx->out.data() + p);
+    uint32_t masked = 0;
+    const int st = rfilter::filter_record(ctx->out.data() + p + 4, bs, ctx->opt.duplex_filter, &masked);
+    ctx->stats[FGB_STAT_FILTER_RECORDS] += 1;
+    ctx->stats[FGB_STAT_FILTER_BASES_MASKED] += masked;
+    if (st != FGB_FILTER_PASS) pass = false;
+    p += 4 + static_cast<size_t>(bs);
+  }
+  if (pass) ctx->stats[FGB_STAT_FILTER_PASSED] += 2;
+  else { ctx->out.resize(mark); ctx->out_count -= 2; }
+}
+
 fgb_status flush_duplex(fgb_caller* c) {
   const uint64_t U = c->pack.units.size();
   if (!U) return FGB_OK;
@@ -757,9 +776,11 @@ fgb_status flush_duplex(fgb_caller* c) {
           if (!min_reads_ok(ctx, max_depth(d[k].ab), d[k].ba.present ? max_depth(d[k].ba) : 0)) ok = false;
       }
       if (!ok) { reject(ctx, FGB_STAT_REJ_INSUFFICIENT_READS, m.n_input); continue; }
+      const size_t mark = ctx->out.size();
       if ((st = write_duplex_record(ctx, &w, d[0], true, m, m.rx[0], m.rx[3])) != FGB_OK) return st;
       if ((st = write_duplex_record(ctx, &w, d[1], false, m, m.rx[1], m.rx[2])) != FGB_OK) return st;
       ctx->stats[FGB_STAT_CONSENSUS_READS] += 1;
+      if (c->opt.filter_enabled) filter_duplex_template(ctx, mark);
     } else {
       // single-strand molecule (min_yx_reads == 0): duplex_consensus(Some, None) keeps the strand
       // only if it has depth somewhere (:852-853)
@@ -774,6 +795,7 @@ fgb_status flush_duplex(fgb_caller* c) {
       }
       if (!ok) { reject(ctx, FGB_STAT_REJ_INSUFFICIENT_READS, m.n_input); continue; }
       static const std::vector<RxSource> kNone;
+      const size_t mark = ctx->out.size();
       if (m.pattern == 1) {
         if ((st = write_duplex_record(ctx, &w, d[0], true, m, m.rx[0], kNone)) != FGB_OK) return st;
         if ((st = write_duplex_record(ctx, &w, d[1], false, m, m.rx[1], kNone)) != FGB_OK) return st;
@@ -782,6 +804,7 @@ fgb_status flush_duplex(fgb_caller* c) {
         if ((st = write_duplex_record(ctx, &w, d[1], false, m, kNone, m.rx[2])) != FGB_OK) return st;
       }
       ctx->stats[FGB_STAT_CONSENSUS_READS] += 1;
+      if (c->opt.filter_enabled) filter_duplex_template(ctx, mark);
     }
   }
   return FGB_OK;
@@ -1138,7 +1161,19 @@ fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_call
   *out = nullptr;
   if (opt->mode > FGB_MODE_CODEC) return FGB_ERR_INVALID_ARG;
   if (opt->mode != FGB_MODE_DUPLEX && opt->min_reads == 0) return FGB_ERR_INVALID_ARG;
-  if (opt->filter_enabled && opt->mode != FGB_MODE_SIMPLEX) return FGB_ERR_INVALID_ARG;
+  if (opt->filter_enabled && opt->mode == FGB_MODE_CODEC) return FGB_ERR_INVALID_ARG;
+  if (opt->filter_enabled && opt->mode == FGB_MODE_DUPLEX) {
+    const fgb_duplex_filter_params& f = opt->duplex_filter;
+    const double rates[] = {f.cc.max_read_error_rate, f.cc.max_base_error_rate, f.ab_max_read_error_rate,
+                            f.ab_max_base_error_rate, f.ba_max_read_error_rate, f.ba_max_base_error_rate};
+    for (double r : rates) if (!(r >= 0.0 && r <= 1.0)) return FGB_ERR_INVALID_ARG;     // commands/filter.rs:975-1000
+    if (!(f.cc.max_no_call_fraction >= 0.0) || f.cc.min_base_quality > 255 || f.cc.min_base_quality < -1)
+      return FGB_ERR_INVALID_ARG;
+    // stringency order (commands/filter.rs:965-972): min-reads ba <= ab <= cc, error rates ab <= ba
+    if (f.ba_min_reads > f.ab_min_reads || f.ab_min_reads > f.cc.min_reads ||
+        f.ab_max_read_error_rate > f.ba_max_read_error_rate || f.ab_max_base_error_rate > f.ba_max_base_error_rate)
+      return FGB_ERR_INVALID_ARG;
+  }
   if (opt->mode == FGB_MODE_CODEC && opt->consensus_call_overlapping_bases)
     return FGB_ERR_INVALID_ARG;   // "CODEC does not support overlapping consensus", commands/codec.rs:257
   if (opt->mode == FGB_MODE_DUPLEX &&
@@ -1339,6 +1374,17 @@ fgb_status fgb_overlap_apply_group(uint8_t* records, const uint64_t* rec_off, ui
   return FGB_OK;
 }
 
+fgb_status fgb_filter_record(uint8_t* record, size_t len, const fgb_duplex_filter_params* p,
+                             uint32_t* masked, uint8_t* status) {
+  if (!record || !p || !status || len < 32) return FGB_ERR_INVALID_ARG;
+  const bam::View v(record, len);
+  if (!v.cigar_in_bounds() || v.aux_off() > len) return FGB_ERR_LAYOUT;
+  uint32_t m = 0;
+  *status = static_cast<uint8_t>(rfilter::filter_record(record, len, *p, &m));
+  if (masked) *masked = m;
+  return FGB_OK;
+}
+
 uint32_t fgb_struct_size(uint32_t id) {
   switch (id) {
     case 0: return sizeof(fgb_caller_options);
@@ -1349,6 +1395,7 @@ uint32_t fgb_struct_size(uint32_t id) {
     case 5: return sizeof(fgb_batch);
     case 6: return sizeof(fgb_codec_params);
     case 7: return sizeof(fgb_params);
+    case 8: return sizeof(fgb_duplex_filter_params);
     default: return 0;
   }
 }

@@ -118,6 +118,13 @@ class FgbFilterParams(C.Structure):
                 ("per_base_tags", C.c_uint8), ("reserved", C.c_uint8 * 7)]
 
 
+class FgbDuplexFilterParams(C.Structure):
+    _fields_ = [("cc", FgbFilterParams), ("ab_min_reads", C.c_uint32), ("ba_min_reads", C.c_uint32),
+                ("ab_max_read_error_rate", C.c_double), ("ba_max_read_error_rate", C.c_double),
+                ("ab_max_base_error_rate", C.c_double), ("ba_max_base_error_rate", C.c_double),
+                ("require_ss_agreement", C.c_uint8), ("reserved", C.c_uint8 * 7)]
+
+
 class FgbSubmitOptions(C.Structure):
     _fields_ = [("input_format", C.c_uint32), ("output_format", C.c_uint32), ("raw", C.c_void_p),
                 ("filter", C.c_void_p), ("unit_status", C.c_void_p), ("unit_masked", C.c_void_p)]
@@ -152,7 +159,7 @@ class FgbCallerOptions(C.Structure):
         ("read_name_prefix", C.c_char_p), ("read_group_id", C.c_char_p),
         ("min_duplex_length", C.c_uint32), ("reserved1", C.c_uint32), ("codec", FgbCodecParams),
         ("filter_enabled", C.c_uint8), ("reserved2", C.c_uint8 * 3), ("n_threads", C.c_uint32),
-        ("filter", FgbFilterParams),
+        ("filter", FgbFilterParams), ("duplex_filter", FgbDuplexFilterParams),
     ]
 
 
@@ -179,7 +186,7 @@ SYMBOLS = (
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
-    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups",
+    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups", "fgb_filter_record",
 )
 
 _lib = None
@@ -287,6 +294,8 @@ def load() -> C.CDLL:
     lib.fgb_filter_simplex_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns),
                                               C.POINTER(FgbFilterParams), vp, vp, vp]
     lib.fgb_filter_simplex_device.restype = C.c_int32
+    lib.fgb_filter_record.argtypes = [vp, C.c_size_t, C.POINTER(FgbDuplexFilterParams), vp, vp]
+    lib.fgb_filter_record.restype = C.c_int32
     lib.fgb_caller_add_groups.argtypes = [vp, vp, vp, vp, u64]
     lib.fgb_caller_add_groups.restype = C.c_int32
     lib.fgb_struct_size.argtypes = [C.c_uint32]

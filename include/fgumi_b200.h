@@ -270,6 +270,30 @@ enum {                                  /* per-unit result                      
   FGB_FILTER_TOO_MANY_NO_CALLS = 4,
   FGB_FILTER_NO_RECORD = 255            /* unit without a consensus read (cons_len 0)              */
 };
+/* `fgumi filter` on DUPLEX consensus reads: three tiers of thresholds (filter.rs:120-215) -- `cc` for
+ * the final consensus, `ab` (the stricter tier) for the better strand of each metric, `ba` for the
+ * worse one -- and optional single-strand agreement masking (filter.rs:702-806).  `cc` also carries
+ * the options shared with the simplex filter (min_base_quality, min_mean_base_quality,
+ * max_no_call_fraction; per_base_tags is ignored: the record says what it carries). */
+typedef struct fgb_duplex_filter_params {
+  fgb_filter_params cc;
+  uint32_t ab_min_reads;
+  uint32_t ba_min_reads;
+  double ab_max_read_error_rate;
+  double ba_max_read_error_rate;
+  double ab_max_base_error_rate;
+  double ba_max_base_error_rate;
+  uint8_t require_ss_agreement;         /* --require-single-strand-agreement                       */
+  uint8_t reserved[7];
+} fgb_duplex_filter_params;
+/* One assembled consensus record (BAM bytes without the block_size word) through the filter, on the
+ * host: masks bases in place (sequence nibble -> N, quality -> 2), then applies the read-level gates
+ * (filter_duplex_read filter.rs:477-557 when the record has aD / bD, else filter_read :453-471; then
+ * commands/filter.rs:909-929).  *status = FGB_FILTER_*, *masked = bases newly masked.  Pure host
+ * code: no device needed. */
+fgb_status fgb_filter_record(uint8_t* record, size_t len, const fgb_duplex_filter_params* p,
+                             uint32_t* masked, uint8_t* status);
+
 /* Device-resident form: masks `cols` in place for the units of `in`, writes one status byte (and
  * optionally the newly-masked count) per unit.  All pointers are device pointers. */
 fgb_status fgb_filter_simplex_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* cols,
@@ -433,6 +457,8 @@ typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanill
   uint32_t n_threads;                      /* host threads for fgb_caller_add_groups and the record
                                               assembly of flush; 0 or 1 = the calling thread only  */
   fgb_filter_params filter;                /* filter.per_base_tags is set from produce_per_base_tags */
+  fgb_duplex_filter_params duplex_filter;  /* duplex mode with filter_enabled: `fgumi duplex | fgumi
+                                              filter`, template mode, on the assembled records     */
 } fgb_caller_options;
 
 enum {   /* ConsensusCallingStats (caller.rs:238-286) as a flat counter array                      */

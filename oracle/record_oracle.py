@@ -1517,13 +1517,25 @@ def compute_read_stats(rec: bytes) -> Tuple[int, float]:            # filter.rs:
     return n_count, (qs / non_n if non_n else 0.0)
 
 
+def _array_u16(v):
+    """array_tag_to_vec_u16 / array_tag_element_u16, raw-bam tags.rs:479-506: unsigned 8/16-bit elements
+    as they are, signed ones clamped at 0, every other element type reads as 0."""
+    if v is None or not v[0].startswith("B"):
+        return None
+    st = v[0][1]
+    if st in "CS":
+        return [int(x) for x in v[1]]
+    if st in "cs":
+        return [max(int(x), 0) for x in v[1]]
+    return [0] * len(v[1])
+
+
 def mask_bases(rec: bytearray, th: FilterThresholds, min_base_quality: Optional[int]) -> int:   # filter.rs:655-696
     r = Rec(bytes(rec))
     tags = _aux_tags(r.aux())
     cd = tags.get(b"cd")
     ce = tags.get(b"ce")
-    cdv = [v & 0xFFFF for v in cd[1]] if cd is not None and cd[0].startswith("B") else None   # array_tag_to_vec_u16
-    cev = [v & 0xFFFF for v in ce[1]] if ce is not None and ce[0].startswith("B") else None
+    cdv, cev = _array_u16(cd), _array_u16(ce)
     so = r.seq_offset()
     qo = so + (r.l_seq + 1) // 2
     seq = r.sequence()
@@ -1594,3 +1606,131 @@ class SimplexFilterOracle:
                     self.passed += 1
             i = j
         return bytes(out), kept
+
+
+# ---- duplex consensus reads (filter.rs:443-447, 477-557, 621-639, 702-806) ----------------------
+def is_duplex_consensus(aux: bytes) -> bool:                        # filter.rs:443-446
+    tags = _aux_tags(aux)
+    return b"aD" in tags or b"bD" in tags
+
+
+def _find_int(tags, tag):                                           # bam_fields::find_int_tag: any integer type
+    v = tags.get(tag)
+    return int(v[1]) if v is not None and v[0] in "cCsSiI" else None
+
+
+def _find_float(tags, tag):                                         # bam_fields::find_float_tag: 'f' only
+    v = tags.get(tag)
+    return float(np.float32(v[1])) if v is not None and v[0] == "f" else None
+
+
+def filter_duplex_read(aux: bytes, cc: FilterThresholds, ab: FilterThresholds, ba: FilterThresholds) -> int:
+    """filter.rs:477-557.  `ab` is the stricter tier (checked against the better strand of each
+    metric), `ba` the lenient one (checked against the worse strand)."""
+    r = filter_read(aux, cc)
+    if r != FILTER_PASS:
+        return r
+    tags = _aux_tags(aux)
+    a_d = _find_int(tags, b"aD")
+    a_d = a_d if a_d is not None else _find_int(tags, b"aM")
+    b_d = _find_int(tags, b"bD")
+    b_d = b_d if b_d is not None else _find_int(tags, b"bM")
+    a_e, b_e = _find_float(tags, b"aE"), _find_float(tags, b"bE")
+    if a_d is not None and b_d is not None:
+        worst_d, best_d = (a_d, b_d) if a_d < b_d else (b_d, a_d)
+    elif a_d is not None:
+        worst_d, best_d = 0, a_d
+    elif b_d is not None:
+        worst_d, best_d = 0, b_d
+    else:
+        return FILTER_PASS
+    if a_e is not None and b_e is not None:
+        best_e, worst_e = (a_e, b_e) if a_e < b_e else (b_e, a_e)
+    elif a_e is not None:
+        best_e = worst_e = a_e
+    elif b_e is not None:
+        best_e = worst_e = b_e
+    else:
+        best_e = worst_e = 0.0
+    U64 = (1 << 64) - 1                       # `(depth as usize) < min_reads`: a negative tag value wraps
+    if (best_d & U64) < ab.min_reads:
+        return FILTER_INSUFFICIENT_READS
+    if best_e > ab.max_read_error_rate:
+        return FILTER_EXCESSIVE_ERROR_RATE
+    if (worst_d & U64) < ba.min_reads:
+        return FILTER_INSUFFICIENT_READS
+    if worst_e > ba.max_read_error_rate:
+        return FILTER_EXCESSIVE_ERROR_RATE
+    return FILTER_PASS
+
+
+def _string_or_u8_array(tags, tag):                                 # filter.rs:621-639
+    v = tags.get(tag)
+    if v is None:
+        return None
+    if v[0] == "Z":
+        return bytes(v[1])
+    if v[0] in ("BC", "Bc"):
+        return bytes(x & 0xFF for x in v[1])
+    return None
+
+
+def mask_duplex_bases(rec: bytearray, cc: FilterThresholds, ab: FilterThresholds, ba: FilterThresholds,
+                      min_base_quality: Optional[int], require_ss_agreement: bool) -> int:   # filter.rs:702-806
+    r = Rec(bytes(rec))
+    tags = _aux_tags(r.aux())
+
+    ad, ae, bd, be = (_array_u16(tags.get(t)) for t in (b"ad", b"ae", b"bd", b"be"))
+    ac = _string_or_u8_array(tags, b"ac") if require_ss_agreement else None
+    bc = _string_or_u8_array(tags, b"bc") if require_ss_agreement else None
+    so = r.seq_offset()
+    qo = so + (r.l_seq + 1) // 2
+    seq = r.sequence()
+    get = lambda v, i: v[i] if v is not None and i < len(v) else 0
+    masked = 0
+    for i in range(r.l_seq):
+        if seq[i] == ord("N"):                                      # is_base_n: already masked
+            continue
+        a_d, b_d, a_e, b_e = get(ad, i), get(bd, i), get(ae, i), get(be, i)
+        best_d, worst_d = max(a_d, b_d), min(a_d, b_d)
+        a_r = float(a_e) / float(a_d) if a_d > 0 else 0.0
+        b_r = float(b_e) / float(b_d) if b_d > 0 else 0.0
+        best_r, worst_r = min(a_r, b_r), max(a_r, b_r)
+        tot_d = a_d + b_d
+        tot_r = float(a_e + b_e) / float(tot_d) if tot_d > 0 else 0.0
+        qual = rec[qo + i]
+        should = ((min_base_quality is not None and qual < min_base_quality) or
+                  tot_d < cc.min_reads or tot_r > cc.max_base_error_rate or
+                  best_d < ab.min_reads or best_r > ab.max_base_error_rate or
+                  worst_d < ba.min_reads or worst_r > ba.max_base_error_rate)
+        ss_dis = False
+        if require_ss_agreement and a_d > 0 and b_d > 0:
+            ab_b = ac[i] if ac is not None and i < len(ac) else ord("N")
+            bb_b = bc[i] if bc is not None and i < len(bc) else ord("N")
+            ss_dis = ab_b != bb_b
+        if should or ss_dis:
+            masked += 1
+            _set_base(rec, so, i, ord("N"))
+            rec[qo + i] = 2
+    return masked
+
+
+class DuplexFilterOracle(SimplexFilterOracle):
+    """`fgumi filter` on duplex consensus records (commands/filter.rs:770-793, 949-968): duplex
+    masking with the CC / AB / BA tiers, then the duplex read-level gates and the shared mean-quality
+    and no-call checks.  Records without aD/bD tags take the single-strand path with the CC tier
+    (`effective_single_strand_thresholds`, filter.rs:217-219)."""
+
+    def __init__(self, cc: FilterThresholds, ab: FilterThresholds, ba: FilterThresholds,
+                 min_base_quality: Optional[int] = None, min_mean_base_quality: Optional[float] = None,
+                 max_no_call_fraction: float = 0.2, require_ss_agreement: bool = False):
+        super().__init__(cc, min_base_quality, min_mean_base_quality, max_no_call_fraction)
+        self.ab, self.ba, self.ss_agree = ab, ba, require_ss_agreement
+
+    def process_record(self, rec: bytearray) -> bool:
+        if not is_duplex_consensus(Rec(bytes(rec)).aux()):
+            return super().process_record(rec)
+        self.bases_masked += mask_duplex_bases(rec, self.th, self.ab, self.ba, self.min_bq, self.ss_agree)
+        if filter_duplex_read(Rec(bytes(rec)).aux(), self.th, self.ab, self.ba) != FILTER_PASS:
+            return False
+        return check_no_call_and_quality(bytes(rec), self.min_mean, self.max_nc)

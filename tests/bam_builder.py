@@ -52,6 +52,8 @@ def make_record(name=b"r", flags=0, ref_id=0, pos=0, mapq=60, cigar=None, mate_r
             rec += b"f" + struct.pack("<f", val)
         elif typ == "Bs":
             rec += b"Bs" + struct.pack("<I", len(val)) + struct.pack("<%dh" % len(val), *val)
+        elif typ == "BC":
+            rec += b"BC" + struct.pack("<I", len(val)) + bytes(val)
         else:
             raise ValueError(typ)
     return bytes(rec)
