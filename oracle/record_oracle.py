@@ -658,7 +658,11 @@ class DuplexCallerOracle:
         self.stats.total_reads += len(records)
         if not records:
             return b"", 0
-        recs = [Rec(b) for b in records]
+        base_mi, a, b = self.partition_records_by_strand([Rec(b) for b in records])
+        return self._process_group(base_mi, a, b)
+
+    @staticmethod
+    def partition_records_by_strand(recs):               # :576-630
         base_mi, a, b = None, [], []
         for r in recs:
             mi = r.find_string(b"MI")
@@ -672,7 +676,11 @@ class DuplexCallerOracle:
                 b.append(r)
             else:
                 raise ValueError("MI tag without /A or /B suffix")
-        return self._process_group(base_mi, a, b)
+        return base_mi, a, b
+
+    @staticmethod
+    def are_all_same_strand(rs) -> bool:                 # :771-780 (empty and single: true)
+        return len({bool(r.flags & REVERSE) for r in rs}) <= 1
 
     @staticmethod
     def _r1(r):
@@ -734,8 +742,7 @@ class DuplexCallerOracle:
         ab_r1 = [r for r in a if self._r1(r)]; ab_r2 = [r for r in a if self._r2(r)]
         ba_r1 = [r for r in b if self._r1(r)]; ba_r2 = [r for r in b if self._r2(r)]
 
-        def same_strand(rs):
-            return len({bool(r.flags & REVERSE) for r in rs}) <= 1
+        same_strand = self.are_all_same_strand
         if a and b:
             if not same_strand(ab_r1 + ba_r2) or not same_strand(ab_r2 + ba_r1):
                 st.reject("PotentialCollision", len(a) + len(b))
@@ -802,7 +809,9 @@ class DuplexCallerOracle:
 
     def _record(self, d: DuplexCons, read_type, umi, raws_a, raws_b, first_of_pair, cell) -> bytes:
         """duplex_read_into :1048-1285 (methylation off)."""
-        flag = UNMAPPED | PAIRED | MATE_UNMAPPED | (FIRST_SEGMENT if read_type == "R1" else LAST_SEGMENT)
+        flag = UNMAPPED                                   # :1064-1076: a fragment carries no pair flags
+        if read_type in ("R1", "R2"):
+            flag |= PAIRED | MATE_UNMAPPED | (FIRST_SEGMENT if read_type == "R1" else LAST_SEGMENT)
         rec = unmapped_record(f"{self.prefix}:{umi}".encode(), flag, d.bases, d.quals)
         rec += tag_string(b"MI", umi.encode())
         if self.cell_tag is not None and cell is not None:

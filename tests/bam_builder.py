@@ -48,6 +48,8 @@ def make_record(name=b"r", flags=0, ref_id=0, pos=0, mapq=60, cigar=None, mate_r
             rec += b"i" + struct.pack("<i", val)
         elif typ == "C":
             rec += b"C" + struct.pack("<B", val)
+        elif typ in ("c", "s", "S", "I"):
+            rec += typ.encode() + struct.pack({"c": "<b", "s": "<h", "S": "<H", "I": "<I"}[typ], val)
         elif typ == "f":
             rec += b"f" + struct.pack("<f", val)
         elif typ == "Bs":

@@ -248,3 +248,23 @@ def test_duplex_caller_with_filter(fopt, min_reads, threads):
     assert st["filter_records"] == flt.total and st["filter_passed"] == flt.passed
     assert st["filter_bases_masked"] == flt.bases_masked
     assert 0 < flt.passed < flt.total and flt.bases_masked > 0
+
+
+def test_int_tag_variants():                          # duplex_caller.rs:4734-4780, raw-bam tags.rs:118-150
+    """Every BAM integer type reads as an integer tag; a float or a missing tag does not -- in the
+    oracle and in the product's host filter (cD feeds the CC min-reads gate)."""
+    import fgumi_b200 as fg
+    for typ, val in (("c", 42), ("C", 200), ("s", 1000), ("S", 50000), ("i", 100000), ("I", 200000)):
+        rec = bytearray(make_record(name=b"r", flags=4, ref_id=-1, pos=-1, cigar=[], seq=b"AC", quals=[30, 30],
+                                    tags=[(b"cD", typ, val)]))
+        tags = R._aux_tags(R.Rec(bytes(rec)).aux())
+        assert R._find_int(tags, b"cD") == val
+        for mr, want in ((val, fg.lib.FGB_FILTER_PASS), (val + 1, fg.lib.FGB_FILTER_INSUFFICIENT_READS)):
+            f = fg.DuplexConsensusFilter((mr, 0, 0), (1.0,), (1.0,), None, None, 1.0)
+            # per-base masks see depth 0 < min_reads: every base is masked, but the read gate is cD's
+            assert R.filter_read(R.Rec(bytes(rec)).aux(), T(mr, 1.0, 1.0)) == want
+            status, _ = f.apply(bytearray(rec))
+            assert (status == fg.lib.FGB_FILTER_INSUFFICIENT_READS) == (want == fg.lib.FGB_FILTER_INSUFFICIENT_READS)
+    rec = make_record(name=b"r", flags=4, ref_id=-1, pos=-1, cigar=[], seq=b"AC", quals=[30, 30], tags=[(b"cD", "f", 1.5)])
+    tags = R._aux_tags(R.Rec(bytes(rec)).aux())
+    assert R._find_int(tags, b"cD") is None and R._find_int(tags, b"aD") is None
