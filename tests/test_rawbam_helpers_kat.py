@@ -1,0 +1,160 @@
+"""Pins the oracle's restatement of the raw-BAM helpers on the path -- FR-pair detection and the
+mate-overlap clip (crates/fgumi-raw-bam/src/overlap.rs), CIGAR arithmetic (cigar.rs) and CIGAR
+simplification (noodles_compat.rs) -- against the reference's own unit tests for them.  CPU only."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import record_oracle as R           # noqa: E402
+from tests.bam_builder import make_record, encode_op   # noqa: E402
+
+P, F1, F2, REV, MREV, UNM, MUNM = (R.PAIRED, R.FIRST_SEGMENT, R.LAST_SEGMENT, R.REVERSE, R.MATE_REVERSE,
+                                   R.UNMAPPED, R.MATE_UNMAPPED)
+M, I, D, N_, S, H, PAD, EQ, X = range(9)
+
+
+def ops(*cig):
+    return [encode_op(k, n) for k, n in cig]
+
+
+def bam(tid, pos, flag, cigar, seq_len, mate_tid, mate_pos, tlen=0, mc=None):
+    """make_bam_bytes / make_bam_bytes_with_tlen, raw-bam testutil.rs:187-259"""
+    tags = [(b"MC", "Z", mc)] if mc is not None else []
+    return R.Rec(make_record(name=b"rea", flags=flag, ref_id=tid, pos=pos, mapq=0, cigar=cigar, mate_ref_id=mate_tid,
+                             mate_pos=mate_pos, tlen=tlen, seq=b"A" * seq_len, quals=[0] * seq_len, tags=tags))
+
+
+def test_is_fr_pair_raw():                            # overlap.rs:260-405
+    c10 = ops((M, 10))
+    assert not R.is_fr_pair(bam(0, 100, 0, c10, 10, 0, 200))
+    assert not R.is_fr_pair(bam(0, 100, P | UNM, c10, 10, 0, 200))
+    assert not R.is_fr_pair(bam(0, 100, P | MUNM, c10, 10, -1, -1))
+    assert not R.is_fr_pair(bam(0, 100, P | MREV, c10, 10, 1, 200))          # different references
+    assert not R.is_fr_pair(bam(0, 100, P, c10, 10, 0, 200))                 # FF
+    assert not R.is_fr_pair(bam(0, 100, P | REV | MREV, c10, 10, 0, 200))    # RR
+    assert R.is_fr_pair(bam(0, 100, P | MREV, c10, 10, 0, 200, tlen=200))
+    assert R.is_fr_pair(bam(0, 100, P | REV, c10, 10, 0, 100, tlen=-10))
+    assert not R.is_fr_pair(bam(0, 200, P | MREV, c10, 10, 0, 100, tlen=-100))   # RF
+
+
+def test_bases_past_and_before_ref_pos():             # overlap.rs:411-535
+    past = lambda c, s, t: R._read_pos_at_ref(c, s, t, True)       # compute_bases_past_ref_pos
+    before = lambda c, s, t: R._read_pos_at_ref(c, s, t, False)    # compute_bases_before_ref_pos
+    c10, ins, dele, sc = ops((M, 10)), ops((M, 5), (I, 3), (M, 5)), ops((M, 5), (D, 3), (M, 5)), ops((S, 3), (M, 10))
+    assert [past(c10, 100, t) for t in (105, 100, 109, 110)] == [6, 1, 10, 0]
+    assert past(ins, 100, 107) == 11 and past(dele, 100, 106) == 0 and past(sc, 100, 102) == 6
+    assert [before(c10, 100, t) for t in (105, 100, 110)] == [5, 0, 0]
+    assert before(ins, 100, 107) == 10 and before(dele, 100, 106) == 0 and before(sc, 100, 102) == 5
+
+
+def test_num_bases_extending_past_mate_raw():         # overlap.rs:540-780, 826-880
+    f = R.num_bases_extending_past_mate
+    c10, c20 = ops((M, 10)), ops((M, 20))
+    assert f(bam(0, 100, 0, c10, 10, 0, 200)) == 0
+    assert f(bam(0, 100, P | UNM | MREV, c10, 10, 0, 200)) == 0
+    assert f(bam(0, 100, P | MUNM | MREV, c10, 10, -1, -1)) == 0
+    assert f(bam(0, 100, P, c10, 10, 0, 200, mc=b"10M")) == 0                 # same strand
+    assert f(bam(0, 100, P | MREV, c10, 10, 1, 200, mc=b"10M")) == 0          # different references
+    assert f(bam(0, 100, P | MREV, c10, 10, 0, 200, tlen=110)) == 0           # no MC tag
+    assert f(bam(0, 100, P | MREV, c20, 20, 0, 105, tlen=20, mc=b"10M")) == 5       # forward read past the mate's end
+    assert f(bam(0, 100, P | MREV, c10, 10, 0, 200, tlen=110, mc=b"10M")) == 0
+    assert f(bam(0, 100, P | REV, c20, 20, 0, 105, mc=b"10M")) == 5                # reverse read before the mate's start
+    assert f(bam(0, 200, P | REV, c10, 10, 0, 100, mc=b"10M")) == 0
+    assert f(bam(0, 110, P | REV, ops((S, 3), (M, 10)), 13, 0, 105, mc=b"10M")) == 0
+    assert f(bam(0, 100, P | MREV, ops((M, 10), (S, 3)), 13, 0, 200, tlen=110, mc=b"10M")) == 0
+    # regression (SRR6109273 MI=807): opposite strands but RF orientation -> no clipping
+    assert f(bam(0, 11_576_620, P | MREV | F1, ops((M, 145), (S, 124)), 269, 0, 11_576_412, tlen=-28, mc=b"87S182M")) == 0
+    assert f(bam(0, 11_576_412, P | REV | F2, ops((S, 87), (M, 182)), 269, 0, 11_576_620, tlen=28, mc=b"145M124S")) == 0
+
+
+def test_soft_clip_gaps_reach_into_the_clip():        # overlap.rs:105-134 (the saturating_sub arms), :787-822
+    """The leading / trailing soft-clip counters skip hard clips; a gap smaller than the clip leaves
+    the difference to be clipped."""
+    f = R.num_bases_extending_past_mate
+    # reverse read 3H5S10M starting 2 bases after the mate's unclipped start: 5 - 2 = 3
+    assert f(bam(0, 107, P | REV, ops((H, 3), (S, 5), (M, 10)), 15, 0, 105, mc=b"10M")) == 3
+    # forward read 10M5S3H ending 2 bases before the mate's unclipped end: 5 - 2 = 3
+    assert f(bam(0, 100, P | MREV, ops((M, 10), (S, 5), (H, 3)), 15, 0, 102, tlen=12, mc=b"10M")) == 3
+
+
+def test_clip_cigar_ops_raw():                        # cigar.rs:1656-1893
+    f = R.clip_cigar_ops
+    assert f(ops((M, 10)), 0, True) == (ops((M, 10)), 0)
+    assert f([], 5, True) == ([], 0)
+    assert f(ops((S, 5), (M, 10)), 3, True) == (ops((H, 3), (S, 2), (M, 10)), 0)        # upgrade path
+    assert f(ops((M, 10), (S, 5)), 3, False) == (ops((M, 10), (S, 2), (H, 3)), 0)
+    assert f(ops((M, 10)), 3, True) == (ops((H, 3), (M, 7)), 3)
+    assert f(ops((M, 10)), 3, False) == (ops((M, 7), (H, 3)), 0)
+    assert f(ops((S, 2), (M, 10)), 5, True) == (ops((H, 5), (M, 7)), 3)                 # past the existing clip
+    assert f(ops((M, 10), (S, 2)), 5, False) == (ops((M, 7), (H, 5)), 0)
+    assert f(ops((M, 10), (I, 3), (M, 5)), 10, True) == (ops((H, 10), (I, 3), (M, 5)), 10)
+    assert f(ops((M, 5), (D, 2), (M, 10)), 5, True) == (ops((H, 5), (M, 10)), 7)        # deletion at the boundary
+    assert f(ops((M, 10), (D, 2), (M, 5)), 5, False) == (ops((M, 10), (H, 5)), 0)
+    assert f(ops((M, 10)), 4, True) == (ops((H, 4), (M, 6)), 4)
+    assert f(ops((M, 10)), 4, False) == (ops((M, 6), (H, 4)), 0)
+    assert f(ops((M, 5), (I, 3), (M, 5)), 6, True) == (ops((H, 8), (M, 5)), 5)          # insertion eaten whole
+    assert f(ops((EQ, 5), (X, 3)), 4, True) == (ops((H, 4), (EQ, 1), (X, 3)), 4)
+    assert f(ops((M, 10)), 10, True) == (ops((H, 10)), 10)
+    assert f(ops((M, 10)), 10, False) == (ops((H, 10)), 0)
+    cx = ops((S, 3), (M, 10), (I, 2), (M, 5), (S, 4))
+    assert f(cx, 8, True) == (ops((H, 8), (M, 5), (I, 2), (M, 5), (S, 4)), 5)
+    assert f(cx, 8, False) == (ops((S, 3), (M, 10), (I, 2), (M, 1), (H, 8)), 0)
+
+
+def test_upgrade_and_edge_clipping_raw():             # cigar.rs:1896-2045
+    up = R._upgrade_clipping
+    assert up(ops((S, 5), (M, 10)), 3, True) == (ops((H, 3), (S, 2), (M, 10)), 0)
+    assert up(ops((H, 2), (S, 5), (M, 10)), 4, True) == (ops((H, 4), (S, 3), (M, 10)), 0)
+    assert up(ops((S, 5), (M, 10)), 5, True) == (ops((H, 5), (M, 10)), 0)
+    assert up(ops((H, 3), (S, 5), (M, 10)), 3, True) == (ops((H, 3), (S, 5), (M, 10)), 0)
+    assert up(ops((M, 10), (S, 5)), 3, False) == (ops((M, 10), (S, 2), (H, 3)), 0)
+    assert up(ops((M, 10), (S, 5), (H, 2)), 5, False) == (ops((M, 10), (S, 2), (H, 5)), 0)
+    assert up(ops((M, 10), (S, 5)), 5, False) == (ops((M, 10), (H, 5)), 0)
+    assert R._clip_start(ops((H, 3), (M, 10)), 2) == (ops((H, 5), (M, 8)), 2)
+    assert R._clip_end(ops((M, 10), (H, 3)), 2) == (ops((M, 8), (H, 5)), 0)
+    assert R._clip_start(ops((I, 3), (M, 10)), 1) == (ops((H, 3), (M, 10)), 0)
+    assert R._clip_end(ops((M, 10), (I, 3)), 1) == (ops((M, 10), (H, 3)), 0)
+
+
+def test_read_pos_at_ref_pos_raw():                   # cigar.rs:1286-1345, 2050-2086
+    f = R.read_pos_at_ref_pos
+    c10 = ops((M, 10))
+    assert [f(c10, 100, t, False) for t in (100, 102, 105, 109)] == [1, 3, 6, 10]
+    assert f(c10, 100, 99, False) is None and f(c10, 100, 110, False) is None
+    dele = ops((M, 5), (D, 3), (M, 5))
+    assert f(dele, 100, 106, False) is None and f(dele, 100, 106, True) == 5
+    ins = ops((M, 5), (I, 3), (M, 5))
+    assert f(ins, 100, 104, False) == 5 and f(ins, 100, 105, False) == 9
+    assert f(ops((S, 3), (M, 10)), 100, 100, False) == 4
+    assert f(ops((D, 2), (M, 5)), 100, 100, True) == 1           # deletion first: no earlier base, reports 1
+
+
+def test_mc_string_parsers_and_reference_length():    # cigar.rs:1366-1460
+    assert [R._parse_leading_clips(s) for s in ("5S10M", "3H5S10M", "10M", "5S3H")] == [5, 8, 0, 8]
+    g = R._parse_ref_len_and_trailing_clips
+    assert g("10M5S") == (10, 5) and g("5S10M2I3D5M3S2H") == (18, 5) and g("5S3H") == (0, 0) and g("10=3X") == (13, 0)
+    assert R.reference_length(ops((M, 50))) == 50
+    assert R.reference_length(ops((M, 10), (D, 3), (M, 5), (N_, 2), (M, 8))) == 28
+    assert R.reference_length(ops((M, 10), (I, 5), (M, 10))) == 20
+
+
+def test_simplify_cigar_from_raw():                   # noodles_compat.rs:294-392
+    f = R.simplify_cigar
+    assert f(ops((S, 5), (M, 10), (I, 3), (M, 5), (S, 4))) == [(M, 15), (I, 3), (M, 9)]
+    assert f(ops((EQ, 5), (X, 3), (D, 2), (EQ, 4))) == [(M, 8), (D, 2), (M, 4)]
+    assert f([]) == []
+    assert f(ops((H, 5), (M, 10), (H, 5))) == [(M, 20)]
+    assert f(ops((H, 2), (S, 3), (M, 5), (I, 2), (M, 3), (D, 1), (M, 4), (S, 4), (H, 1))) == \
+        [(M, 10), (I, 2), (M, 3), (D, 1), (M, 9)]
+    assert f(ops((M, 5), (N_, 3), (M, 5))) == [(M, 5), (N_, 3), (M, 5)]
+    assert f(ops((S, 10))) == [(M, 10)]
+
+
+def test_sequence_packing():                          # sequence.rs:530-570, 684-740
+    pk = R.pack_sequence
+    assert pk(b"") == b"" and pk(b"ACGT") == bytes([0x12, 0x48]) and pk(b"ACG") == bytes([0x12, 0x40])
+    assert pk(b"T") == bytes([0x80]) and pk(b"NN") == bytes([0xFF])
+    assert pk(b"ACGTACGTACGTACGTA") == bytes([0x12, 0x48] * 4 + [0x10])
+    for seq in (b"ACGT", b"ACG", b"NNNN", b"T"):
+        r = R.Rec(make_record(name=b"rd", flags=0, ref_id=0, pos=0, cigar=[], seq=seq, quals=[0] * len(seq)))
+        assert bytes(r.sequence()) == seq
