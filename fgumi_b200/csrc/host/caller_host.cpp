@@ -1374,6 +1374,58 @@ fgb_status fgb_overlap_apply_group(uint8_t* records, const uint64_t* rec_off, ui
   return FGB_OK;
 }
 
+int fgb_host_is_fr_pair(const uint8_t* record, size_t len) {
+  if (!record || len < 32) return 0;
+  const bam::View v(record, len);
+  if (!v.cigar_in_bounds()) return 0;
+  std::vector<uint32_t> ops;
+  bam::cigar_ops(v, &ops);
+  return bam::is_fr_pair(v, ops) ? 1 : 0;
+}
+
+uint32_t fgb_host_num_bases_extending_past_mate(const uint8_t* record, size_t len) {
+  if (!record || len < 32) return 0;
+  const bam::View v(record, len);
+  if (!v.cigar_in_bounds() || v.aux_off() > len) return 0;
+  std::vector<uint32_t> ops;
+  bam::cigar_ops(v, &ops);
+  return static_cast<uint32_t>(bam::num_bases_extending_past_mate(v, ops));
+}
+
+fgb_status fgb_host_clip_cigar_ops(const uint32_t* ops, uint32_t n_ops, uint32_t clip_amount, int from_start,
+                                   uint32_t* out_ops, uint32_t* out_n, uint32_t* ref_consumed) {
+  if ((n_ops && !ops) || !out_ops || !out_n) return FGB_ERR_INVALID_ARG;
+  const std::vector<uint32_t> in(ops, ops + n_ops);
+  size_t rc = 0;
+  const std::vector<uint32_t> res = bam::clip_cigar_ops(in, clip_amount, from_start != 0, &rc);
+  if (res.size() > static_cast<size_t>(n_ops) + 2) return FGB_ERR_LAYOUT;
+  std::copy(res.begin(), res.end(), out_ops);
+  *out_n = static_cast<uint32_t>(res.size());
+  if (ref_consumed) *ref_consumed = static_cast<uint32_t>(rc);
+  return FGB_OK;
+}
+
+int fgb_host_read_pos_at_ref_pos(const uint32_t* ops, uint32_t n_ops, uint64_t alignment_start,
+                                 uint64_t ref_pos, int return_last_base_if_deleted, uint64_t* read_pos) {
+  if ((n_ops && !ops) || !read_pos) return 0;
+  const std::vector<uint32_t> in(ops, ops + n_ops);
+  size_t out = 0;
+  if (!bam::read_pos_at_ref_pos(in, alignment_start, ref_pos, return_last_base_if_deleted != 0, &out)) return 0;
+  *read_pos = out;
+  return 1;
+}
+
+fgb_status fgb_host_simplify_cigar(const uint32_t* ops, uint32_t n_ops, uint8_t* out_kinds, uint32_t* out_lens,
+                                   uint32_t* out_n) {
+  if ((n_ops && (!ops || !out_kinds || !out_lens)) || !out_n) return FGB_ERR_INVALID_ARG;
+  const std::vector<uint32_t> in(ops, ops + n_ops);
+  bam::SimpleCigar sc;
+  bam::simplify_cigar(in, &sc);
+  for (size_t i = 0; i < sc.size(); ++i) { out_kinds[i] = sc[i].first; out_lens[i] = sc[i].second; }
+  *out_n = static_cast<uint32_t>(sc.size());
+  return FGB_OK;
+}
+
 fgb_status fgb_filter_record(uint8_t* record, size_t len, const fgb_duplex_filter_params* p,
                              uint32_t* masked, uint8_t* status) {
   if (!record || !p || !status || len < 32) return FGB_ERR_INVALID_ARG;

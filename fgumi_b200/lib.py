@@ -186,7 +186,8 @@ SYMBOLS = (
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
-    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups", "fgb_filter_record",
+    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups", "fgb_filter_record", "fgb_host_is_fr_pair",
+    "fgb_host_num_bases_extending_past_mate", "fgb_host_clip_cigar_ops", "fgb_host_read_pos_at_ref_pos", "fgb_host_simplify_cigar",
 )
 
 _lib = None
@@ -296,6 +297,16 @@ def load() -> C.CDLL:
     lib.fgb_filter_simplex_device.restype = C.c_int32
     lib.fgb_filter_record.argtypes = [vp, C.c_size_t, C.POINTER(FgbDuplexFilterParams), vp, vp]
     lib.fgb_filter_record.restype = C.c_int32
+    lib.fgb_host_is_fr_pair.argtypes = [vp, C.c_size_t]
+    lib.fgb_host_is_fr_pair.restype = C.c_int
+    lib.fgb_host_num_bases_extending_past_mate.argtypes = [vp, C.c_size_t]
+    lib.fgb_host_num_bases_extending_past_mate.restype = u32
+    lib.fgb_host_clip_cigar_ops.argtypes = [vp, u32, u32, C.c_int, vp, vp, vp]
+    lib.fgb_host_clip_cigar_ops.restype = C.c_int32
+    lib.fgb_host_read_pos_at_ref_pos.argtypes = [vp, u32, u64, u64, C.c_int, vp]
+    lib.fgb_host_read_pos_at_ref_pos.restype = C.c_int
+    lib.fgb_host_simplify_cigar.argtypes = [vp, u32, vp, vp, vp]
+    lib.fgb_host_simplify_cigar.restype = C.c_int32
     lib.fgb_caller_add_groups.argtypes = [vp, vp, vp, vp, u64]
     lib.fgb_caller_add_groups.restype = C.c_int32
     lib.fgb_struct_size.argtypes = [C.c_uint32]

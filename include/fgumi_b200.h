@@ -286,6 +286,23 @@ typedef struct fgb_duplex_filter_params {
   uint8_t require_ss_agreement;         /* --require-single-strand-agreement                       */
   uint8_t reserved[7];
 } fgb_duplex_filter_params;
+/* ---- raw-record helpers of the host prep (pure host code, no device needed) ------------------ */
+/* The reference exposes these from fgumi-raw-bam; the callers use them for every source read, and
+ * they are exported so a host integration -- and the CPU test-suite -- can call the same code.
+ *   fgb_host_is_fr_pair                     overlap.rs:15-62   is_fr_pair_raw
+ *   fgb_host_num_bases_extending_past_mate  overlap.rs:65-136  num_bases_extending_past_mate_raw
+ *   fgb_host_clip_cigar_ops                 cigar.rs:355-397   clip_cigar_ops_raw; out_ops holds n_ops + 2
+ *   fgb_host_read_pos_at_ref_pos            cigar.rs:412-457   read_pos_at_ref_pos_raw; returns 0 = None
+ *   fgb_host_simplify_cigar                 noodles_compat.rs:10-55; out_kinds / out_lens hold n_ops   */
+int fgb_host_is_fr_pair(const uint8_t* record, size_t len);
+uint32_t fgb_host_num_bases_extending_past_mate(const uint8_t* record, size_t len);
+fgb_status fgb_host_clip_cigar_ops(const uint32_t* ops, uint32_t n_ops, uint32_t clip_amount, int from_start,
+                                   uint32_t* out_ops, uint32_t* out_n, uint32_t* ref_consumed);
+int fgb_host_read_pos_at_ref_pos(const uint32_t* ops, uint32_t n_ops, uint64_t alignment_start,
+                                 uint64_t ref_pos, int return_last_base_if_deleted, uint64_t* read_pos);
+fgb_status fgb_host_simplify_cigar(const uint32_t* ops, uint32_t n_ops, uint8_t* out_kinds, uint32_t* out_lens,
+                                   uint32_t* out_n);
+
 /* One assembled consensus record (BAM bytes without the block_size word) through the filter, on the
  * host: masks bases in place (sequence nibble -> N, quality -> 2), then applies the read-level gates
  * (filter_duplex_read filter.rs:477-557 when the record has aD / bD, else filter_read :453-471; then

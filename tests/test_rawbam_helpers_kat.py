@@ -1,8 +1,11 @@
 """Pins the oracle's restatement of the raw-BAM helpers on the path -- FR-pair detection and the
 mate-overlap clip (crates/fgumi-raw-bam/src/overlap.rs), CIGAR arithmetic (cigar.rs) and CIGAR
-simplification (noodles_compat.rs) -- against the reference's own unit tests for them.  CPU only."""
+simplification (noodles_compat.rs) -- against the reference's own unit tests for them -- and, where the product's host code exports the same
+helper through the C-ABI (fgb_host_*), runs the same cases against the product.  CPU only."""
 import os
 import sys
+
+import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import record_oracle as R           # noqa: E402
@@ -17,6 +20,66 @@ def ops(*cig):
     return [encode_op(k, n) for k, n in cig]
 
 
+class _Oracle:
+    """oracle/record_oracle.py"""
+    is_fr_pair = staticmethod(R.is_fr_pair)
+    num_bases_extending_past_mate = staticmethod(R.num_bases_extending_past_mate)
+    clip_cigar_ops = staticmethod(R.clip_cigar_ops)
+    read_pos_at_ref_pos = staticmethod(R.read_pos_at_ref_pos)
+    simplify_cigar = staticmethod(R.simplify_cigar)
+
+
+class _Product:
+    """The same helpers of the product's host code (fgumi_b200/csrc/host/bam.h) through the C-ABI."""
+
+    @staticmethod
+    def _lib():
+        import fgumi_b200 as fg
+        return fg.lib.load()
+
+    @staticmethod
+    def _u32(v):
+        import ctypes as C
+        return (C.c_uint32 * max(len(v), 1))(*v)
+
+    @classmethod
+    def is_fr_pair(cls, r):
+        return bool(cls._lib().fgb_host_is_fr_pair(bytes(r.b), len(r.b)))
+
+    @classmethod
+    def num_bases_extending_past_mate(cls, r):
+        return cls._lib().fgb_host_num_bases_extending_past_mate(bytes(r.b), len(r.b))
+
+    @classmethod
+    def clip_cigar_ops(cls, o, clip, from_start):
+        import ctypes as C
+        out, n, rc = (C.c_uint32 * (len(o) + 2))(), C.c_uint32(), C.c_uint32()
+        a = cls._u32(o)
+        assert cls._lib().fgb_host_clip_cigar_ops(C.addressof(a), len(o), clip, int(from_start), C.addressof(out),
+                                                  C.addressof(n), C.addressof(rc)) == 0
+        return list(out[:n.value]), rc.value
+
+    @classmethod
+    def read_pos_at_ref_pos(cls, o, start, ref_pos, last):
+        import ctypes as C
+        out = C.c_uint64()
+        a = cls._u32(o)
+        ok = cls._lib().fgb_host_read_pos_at_ref_pos(C.addressof(a), len(o), start, ref_pos, int(last), C.addressof(out))
+        return out.value if ok else None
+
+    @classmethod
+    def simplify_cigar(cls, o):
+        import ctypes as C
+        kinds, lens, n = (C.c_uint8 * max(len(o), 1))(), (C.c_uint32 * max(len(o), 1))(), C.c_uint32()
+        a = cls._u32(o)
+        assert cls._lib().fgb_host_simplify_cigar(C.addressof(a), len(o), C.addressof(kinds), C.addressof(lens),
+                                                  C.addressof(n)) == 0
+        return [(int(kinds[i]), int(lens[i])) for i in range(n.value)]
+
+
+IMPLS = pytest.mark.parametrize("impl", [_Oracle, _Product], ids=["oracle", "product-host"])
+
+
 def bam(tid, pos, flag, cigar, seq_len, mate_tid, mate_pos, tlen=0, mc=None):
     """make_bam_bytes / make_bam_bytes_with_tlen, raw-bam testutil.rs:187-259"""
     tags = [(b"MC", "Z", mc)] if mc is not None else []
@@ -24,17 +87,19 @@ def bam(tid, pos, flag, cigar, seq_len, mate_tid, mate_pos, tlen=0, mc=None):
                              mate_pos=mate_pos, tlen=tlen, seq=b"A" * seq_len, quals=[0] * seq_len, tags=tags))
 
 
-def test_is_fr_pair_raw():                            # overlap.rs:260-405
+@IMPLS
+def test_is_fr_pair_raw(impl):                        # overlap.rs:260-405
     c10 = ops((M, 10))
-    assert not R.is_fr_pair(bam(0, 100, 0, c10, 10, 0, 200))
-    assert not R.is_fr_pair(bam(0, 100, P | UNM, c10, 10, 0, 200))
-    assert not R.is_fr_pair(bam(0, 100, P | MUNM, c10, 10, -1, -1))
-    assert not R.is_fr_pair(bam(0, 100, P | MREV, c10, 10, 1, 200))          # different references
-    assert not R.is_fr_pair(bam(0, 100, P, c10, 10, 0, 200))                 # FF
-    assert not R.is_fr_pair(bam(0, 100, P | REV | MREV, c10, 10, 0, 200))    # RR
-    assert R.is_fr_pair(bam(0, 100, P | MREV, c10, 10, 0, 200, tlen=200))
-    assert R.is_fr_pair(bam(0, 100, P | REV, c10, 10, 0, 100, tlen=-10))
-    assert not R.is_fr_pair(bam(0, 200, P | MREV, c10, 10, 0, 100, tlen=-100))   # RF
+    R_is_fr_pair = impl.is_fr_pair
+    assert not R_is_fr_pair(bam(0, 100, 0, c10, 10, 0, 200))
+    assert not R_is_fr_pair(bam(0, 100, P | UNM, c10, 10, 0, 200))
+    assert not R_is_fr_pair(bam(0, 100, P | MUNM, c10, 10, -1, -1))
+    assert not R_is_fr_pair(bam(0, 100, P | MREV, c10, 10, 1, 200))          # different references
+    assert not R_is_fr_pair(bam(0, 100, P, c10, 10, 0, 200))                 # FF
+    assert not R_is_fr_pair(bam(0, 100, P | REV | MREV, c10, 10, 0, 200))    # RR
+    assert R_is_fr_pair(bam(0, 100, P | MREV, c10, 10, 0, 200, tlen=200))
+    assert R_is_fr_pair(bam(0, 100, P | REV, c10, 10, 0, 100, tlen=-10))
+    assert not R_is_fr_pair(bam(0, 200, P | MREV, c10, 10, 0, 100, tlen=-100))   # RF
 
 
 def test_bases_past_and_before_ref_pos():             # overlap.rs:411-535
@@ -47,8 +112,9 @@ def test_bases_past_and_before_ref_pos():             # overlap.rs:411-535
     assert before(ins, 100, 107) == 10 and before(dele, 100, 106) == 0 and before(sc, 100, 102) == 5
 
 
-def test_num_bases_extending_past_mate_raw():         # overlap.rs:540-780, 826-880
-    f = R.num_bases_extending_past_mate
+@IMPLS
+def test_num_bases_extending_past_mate_raw(impl):     # overlap.rs:540-780, 826-880
+    f = impl.num_bases_extending_past_mate
     c10, c20 = ops((M, 10)), ops((M, 20))
     assert f(bam(0, 100, 0, c10, 10, 0, 200)) == 0
     assert f(bam(0, 100, P | UNM | MREV, c10, 10, 0, 200)) == 0
@@ -67,18 +133,20 @@ def test_num_bases_extending_past_mate_raw():         # overlap.rs:540-780, 826-
     assert f(bam(0, 11_576_412, P | REV | F2, ops((S, 87), (M, 182)), 269, 0, 11_576_620, tlen=28, mc=b"145M124S")) == 0
 
 
-def test_soft_clip_gaps_reach_into_the_clip():        # overlap.rs:105-134 (the saturating_sub arms), :787-822
+@IMPLS
+def test_soft_clip_gaps_reach_into_the_clip(impl):    # overlap.rs:105-134 (the saturating_sub arms), :787-822
     """The leading / trailing soft-clip counters skip hard clips; a gap smaller than the clip leaves
     the difference to be clipped."""
-    f = R.num_bases_extending_past_mate
+    f = impl.num_bases_extending_past_mate
     # reverse read 3H5S10M starting 2 bases after the mate's unclipped start: 5 - 2 = 3
     assert f(bam(0, 107, P | REV, ops((H, 3), (S, 5), (M, 10)), 15, 0, 105, mc=b"10M")) == 3
     # forward read 10M5S3H ending 2 bases before the mate's unclipped end: 5 - 2 = 3
     assert f(bam(0, 100, P | MREV, ops((M, 10), (S, 5), (H, 3)), 15, 0, 102, tlen=12, mc=b"10M")) == 3
 
 
-def test_clip_cigar_ops_raw():                        # cigar.rs:1656-1893
-    f = R.clip_cigar_ops
+@IMPLS
+def test_clip_cigar_ops_raw(impl):                    # cigar.rs:1656-1893
+    f = impl.clip_cigar_ops
     assert f(ops((M, 10)), 0, True) == (ops((M, 10)), 0)
     assert f([], 5, True) == ([], 0)
     assert f(ops((S, 5), (M, 10)), 3, True) == (ops((H, 3), (S, 2), (M, 10)), 0)        # upgrade path
@@ -116,8 +184,9 @@ def test_upgrade_and_edge_clipping_raw():             # cigar.rs:1896-2045
     assert R._clip_end(ops((M, 10), (I, 3)), 1) == (ops((M, 10), (H, 3)), 0)
 
 
-def test_read_pos_at_ref_pos_raw():                   # cigar.rs:1286-1345, 2050-2086
-    f = R.read_pos_at_ref_pos
+@IMPLS
+def test_read_pos_at_ref_pos_raw(impl):               # cigar.rs:1286-1345, 2050-2086
+    f = impl.read_pos_at_ref_pos
     c10 = ops((M, 10))
     assert [f(c10, 100, t, False) for t in (100, 102, 105, 109)] == [1, 3, 6, 10]
     assert f(c10, 100, 99, False) is None and f(c10, 100, 110, False) is None
@@ -138,8 +207,9 @@ def test_mc_string_parsers_and_reference_length():    # cigar.rs:1366-1460
     assert R.reference_length(ops((M, 10), (I, 5), (M, 10))) == 20
 
 
-def test_simplify_cigar_from_raw():                   # noodles_compat.rs:294-392
-    f = R.simplify_cigar
+@IMPLS
+def test_simplify_cigar_from_raw(impl):               # noodles_compat.rs:294-392
+    f = impl.simplify_cigar
     assert f(ops((S, 5), (M, 10), (I, 3), (M, 5), (S, 4))) == [(M, 15), (I, 3), (M, 9)]
     assert f(ops((EQ, 5), (X, 3), (D, 2), (EQ, 4))) == [(M, 8), (D, 2), (M, 4)]
     assert f([]) == []
