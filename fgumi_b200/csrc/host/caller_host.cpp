@@ -1374,6 +1374,52 @@ fgb_status fgb_overlap_apply_group(uint8_t* records, const uint64_t* rec_off, ui
   return FGB_OK;
 }
 
+fgb_status fgb_host_source_reads(const uint8_t* records, const uint64_t* rec_off, uint32_t n_records,
+                                 uint8_t min_input_base_quality, int trim, uint8_t* out_bases,
+                                 uint8_t* out_quals, uint64_t* row_off, uint32_t* orig_idx,
+                                 uint32_t* n_rows, uint32_t* n_minority) {
+  if (!n_rows || !row_off || (n_records && (!records || !rec_off || !out_bases || !out_quals || !orig_idx)))
+    return FGB_ERR_INVALID_ARG;
+  prep::PrepOptions po;
+  po.min_input_base_quality = min_input_base_quality;
+  po.trim = trim != 0;
+  std::vector<prep::SourceRead> srs;
+  std::vector<uint32_t> ops;
+  for (uint32_t i = 0; i < n_records; ++i) {
+    if (rec_off[i + 1] < rec_off[i] || rec_off[i + 1] - rec_off[i] < 32) return FGB_ERR_LAYOUT;
+    const View v(records + rec_off[i], rec_off[i + 1] - rec_off[i]);
+    if (!v.cigar_in_bounds() || v.aux_off() > v.n) return FGB_ERR_LAYOUT;
+    bam::cigar_ops(v, &ops);
+    const size_t clip = bam::num_bases_extending_past_mate(v, ops);
+    prep::SourceRead sr;
+    if (prep::make_source_read(po, v, i, clip, &ops, &sr)) srs.push_back(std::move(sr));
+  }
+  const size_t minority = prep::filter_by_alignment(&srs);
+  uint64_t off = 0;
+  for (size_t r = 0; r < srs.size(); ++r) {
+    row_off[r] = off;
+    std::memcpy(out_bases + off, srs[r].bases.data(), srs[r].bases.size());
+    std::memcpy(out_quals + off, srs[r].quals.data(), srs[r].quals.size());
+    orig_idx[r] = srs[r].original_idx;
+    off += srs[r].bases.size();
+  }
+  row_off[srs.size()] = off;
+  *n_rows = static_cast<uint32_t>(srs.size());
+  if (n_minority) *n_minority = static_cast<uint32_t>(minority);
+  return FGB_OK;
+}
+
+fgb_status fgb_host_consensus_umis(const char* const* umis, uint32_t n, char* out, size_t cap) {
+  if ((n && !umis) || !out || !cap) return FGB_ERR_INVALID_ARG;
+  static const prep::UmiBuilder builder;
+  std::vector<std::string> v;
+  for (uint32_t i = 0; i < n; ++i) { if (!umis[i]) return FGB_ERR_INVALID_ARG; v.emplace_back(umis[i]); }
+  std::string res;
+  if (!prep::consensus_umis(builder, v, &res) || res.size() + 1 > cap) return FGB_ERR_INVALID_ARG;
+  std::memcpy(out, res.c_str(), res.size() + 1);
+  return FGB_OK;
+}
+
 int fgb_host_is_fr_pair(const uint8_t* record, size_t len) {
   if (!record || len < 32) return 0;
   const bam::View v(record, len);

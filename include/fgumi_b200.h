@@ -294,6 +294,21 @@ typedef struct fgb_duplex_filter_params {
  *   fgb_host_clip_cigar_ops                 cigar.rs:355-397   clip_cigar_ops_raw; out_ops holds n_ops + 2
  *   fgb_host_read_pos_at_ref_pos            cigar.rs:412-457   read_pos_at_ref_pos_raw; returns 0 = None
  *   fgb_host_simplify_cigar                 noodles_compat.rs:10-55; out_kinds / out_lens hold n_ops   */
+/*   fgb_host_source_reads   the simplex sub-group prep: for each record (the rec_off convention of
+ *                           fgb_caller_add_group) the mate-overlap clip and create_source_read
+ *                           (vanilla_caller.rs:863-955), then filter_source_reads_by_alignment
+ *                           (:961-1013).  Writes the surviving rows back to back into out_bases /
+ *                           out_quals (capacity: the sum of the records' l_seq), row r at
+ *                           [row_off[r], row_off[r+1]), its record index in orig_idx[r]; *n_rows rows,
+ *                           *n_minority reads dropped by the CIGAR filter.
+ *   fgb_host_consensus_umis simple_umi.rs:65-122, 236-245; umis = n NUL-terminated strings; returns
+ *                           FGB_ERR_INVALID_ARG where the reference panics (unequal lengths, DNA mixed
+ *                           with other characters) or when `cap` is too small                          */
+fgb_status fgb_host_source_reads(const uint8_t* records, const uint64_t* rec_off, uint32_t n_records,
+                                 uint8_t min_input_base_quality, int trim, uint8_t* out_bases,
+                                 uint8_t* out_quals, uint64_t* row_off, uint32_t* orig_idx,
+                                 uint32_t* n_rows, uint32_t* n_minority);
+fgb_status fgb_host_consensus_umis(const char* const* umis, uint32_t n, char* out, size_t cap);
 int fgb_host_is_fr_pair(const uint8_t* record, size_t len);
 uint32_t fgb_host_num_bases_extending_past_mate(const uint8_t* record, size_t len);
 fgb_status fgb_host_clip_cigar_ops(const uint32_t* ops, uint32_t n_ops, uint32_t clip_amount, int from_start,

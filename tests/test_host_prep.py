@@ -1,0 +1,91 @@
+"""The product's host prep (fgumi_b200/csrc/host/prep.h) through the C-ABI, on the CPU: source-read
+preparation + CIGAR filter against the oracle on random MI groups, and the UMI consensus against the
+reference's SimpleConsensusCaller tests (simple_umi.rs:257-462).  No GPU needed."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import record_oracle as R           # noqa: E402
+from tests import oracle_lib as O               # noqa: E402
+
+
+def product_source_reads(records, min_q, trim):
+    import fgumi_b200 as fg
+    lib = fg.lib.load()
+    blob = b"".join(records)
+    off = np.zeros(len(records) + 1, np.uint64)
+    off[1:] = np.cumsum([len(r) for r in records])
+    cap = sum(R.Rec(r).l_seq for r in records) + 1
+    ob, oq = np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+    row_off, orig = np.zeros(len(records) + 1, np.uint64), np.zeros(max(len(records), 1), np.uint32)
+    n_rows, n_min = C.c_uint32(), C.c_uint32()
+    buf = np.frombuffer(blob, np.uint8) if blob else np.zeros(1, np.uint8)
+    st = lib.fgb_host_source_reads(buf.ctypes.data, off.ctypes.data, len(records), min_q, int(trim), ob.ctypes.data,
+                                   oq.ctypes.data, row_off.ctypes.data, orig.ctypes.data, C.addressof(n_rows),
+                                   C.addressof(n_min))
+    assert st == 0
+    rows = [(bytes(ob[int(row_off[r]):int(row_off[r + 1])]), bytes(oq[int(row_off[r]):int(row_off[r + 1])]), int(orig[r]))
+            for r in range(n_rows.value)]
+    return rows, n_min.value
+
+
+@pytest.mark.parametrize("min_q,trim", [(10, False), (20, True), (2, False)])
+def test_source_reads_and_cigar_filter_match_oracle(min_q, trim):
+    from tests.test_caller_parity import random_groups
+    rng = np.random.default_rng(4242 + min_q)
+    opt = R.VanillaOptions(min_input_base_quality=min_q, trim=trim)
+    n_rows = n_rejected = n_clipped = 0
+    for group in random_groups(rng, 250):
+        recs = [R.Rec(b) for b in group]
+        srs = []
+        for i, r in enumerate(recs):
+            clip = R.num_bases_extending_past_mate(r)
+            n_clipped += clip > 0
+            sr = R.create_source_read(r, i, clip, opt)
+            if sr is not None:
+                srs.append(sr)
+        kept, minority = R.filter_by_alignment(srs)
+        want = [(bytes(s.bases), bytes(s.quals), s.original_idx) for s in kept]
+        got, got_minority = product_source_reads(group, min_q, trim)
+        assert got == want and got_minority == minority
+        n_rows += len(want)
+        n_rejected += minority
+    assert n_rows > 500 and n_rejected > 0 and n_clipped > 0
+
+
+def test_consensus_umis_kats():                       # simple_umi.rs:257-462, through the product
+    import fgumi_b200 as fg
+    lib = fg.lib.load()
+
+    def cu(umis):
+        arr = (C.c_char_p * max(len(umis), 1))(*[u.encode() for u in umis])
+        out = C.create_string_buffer(256)
+        st = lib.fgb_host_consensus_umis(arr, len(umis), out, 256)
+        return out.value.decode() if st == 0 else None
+    assert cu(["A", "A"]) == "A" and cu(["GATTACA", "GATTACA"]) == "GATTACA"
+    assert cu(["A", "C", "G", "T"]) == "N"
+    assert cu(["A", "C", "C", "C"]) == "C" and cu(["C", "C", "C", "A"]) == "C"
+    assert cu(["GATTACA"] * 3 + ["NNNNNNN"]) == "GATTACA"
+    assert cu(["GATT-ACA"] * 3) == "GATT-ACA" and cu(["XGAT", "XGAT"]) == "XGAT" and cu(["GATY", "GATY"]) == "GATY"
+    assert cu(["AACC", "CCAA"]) == "NNNN"
+    assert cu(["ACGT", "ACGT", "CAGT"]) == "ACGT" and cu(["ACGT"] * 3 + ["ACGG"]) == "ACGT"
+    assert cu([]) == "" and cu(["ACGT"]) == "ACGT"
+    for bad in (["A", "AC"], ["GATT-ACA", "GATT-ACA", "GATTAACA"], ["GATT-ACA", "GATT+ACA"]):
+        assert cu(bad) is None                         # where the reference panics
+    # and against the oracle on random UMI sets
+    rng = np.random.default_rng(99)
+    vote = lambda pre, post, b, q: O.builder_call(pre, post, b, q)[:2]
+    for _ in range(300):
+        n, ln = int(rng.integers(1, 9)), int(rng.integers(1, 12))
+        true = rng.choice(list("ACGT"), size=ln)
+        umis = []
+        for _k in range(n):
+            u = true.copy()
+            m = rng.random(ln) < 0.2
+            u[m] = rng.choice(list("ACGTNacgt"), size=int(m.sum()))
+            umis.append("".join(u))
+        assert cu(umis) == R.consensus_umis(list(umis), vote)
