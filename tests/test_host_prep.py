@@ -89,3 +89,103 @@ def test_consensus_umis_kats():                       # simple_umi.rs:257-462, t
             u[m] = rng.choice(list("ACGTNacgt"), size=int(m.sum()))
             umis.append("".join(u))
         assert cu(umis) == R.consensus_umis(list(umis), vote)
+
+
+def test_malformed_records_do_not_crash_the_host_helpers():
+    """Truncated and bit-flipped records through every record-taking host entry point: any status is
+    acceptable, a crash or an out-of-bounds read (the test process dying) is not."""
+    import fgumi_b200 as fg
+    from tests.test_caller_parity import random_groups
+    lib = fg.lib.load()
+    rng = np.random.default_rng(7)
+    fp = fg.DuplexConsensusFilter((2, 1, 1), (0.1,), (0.2,), 10, 20.0, 0.3, True).fill(fg.lib.FgbDuplexFilterParams())
+    groups = random_groups(rng, 40)
+    n_calls = 0
+    for group in groups:
+        for rec in group[:3]:
+            for _ in range(12):
+                b = bytearray(rec)
+                mode = int(rng.integers(0, 4))
+                if mode == 0:
+                    b = b[:int(rng.integers(0, len(b)))]                       # truncate anywhere
+                elif mode == 1:
+                    for k in rng.integers(0, len(b), size=3):                  # flip bytes (header, cigar, aux)
+                        b[int(k)] = int(rng.integers(0, 256))
+                elif mode == 2:
+                    b[12:14] = int(rng.integers(0, 65536)).to_bytes(2, "little")   # n_cigar_op
+                else:
+                    b[16:20] = int(rng.integers(0, 1 << 20)).to_bytes(4, "little")   # l_seq
+                if len(b) == 0:
+                    continue
+                buf = (C.c_uint8 * len(b)).from_buffer(b)
+                lib.fgb_host_is_fr_pair(C.addressof(buf), len(b))
+                lib.fgb_host_num_bases_extending_past_mate(C.addressof(buf), len(b))
+                masked, status = C.c_uint32(), C.c_uint8()
+                lib.fgb_filter_record(C.addressof(buf), len(b), C.byref(fp), C.addressof(masked), C.addressof(status))
+                off = np.array([0, len(b)], np.uint64)
+                cap = max(int.from_bytes(bytes(b[16:20]), "little"), 1) if len(b) >= 20 else 1
+                if cap <= (1 << 20):
+                    ob, oq = np.zeros(cap + 8, np.uint8), np.zeros(cap + 8, np.uint8)
+                    ro, oi = np.zeros(2, np.uint64), np.zeros(1, np.uint32)
+                    nr, nm = C.c_uint32(), C.c_uint32()
+                    lib.fgb_host_source_reads(C.addressof(buf), off.ctypes.data, 1, 10, 0, ob.ctypes.data, oq.ctypes.data,
+                                              ro.ctypes.data, oi.ctypes.data, C.addressof(nr), C.addressof(nm))
+                n_calls += 1
+    assert n_calls > 1000
+
+
+def _mutations(rng, rec, n):
+    out = []
+    for _ in range(n):
+        b = bytearray(rec)
+        mode = int(rng.integers(0, 5))
+        if mode == 0:
+            b = b[:int(rng.integers(0, len(b)))]
+        elif mode == 1:
+            for k in rng.integers(0, len(b), size=3):
+                b[int(k)] = int(rng.integers(0, 256))
+        elif mode == 2:
+            b[12:14] = int(rng.integers(0, 65536)).to_bytes(2, "little")
+        elif mode == 3:
+            b[16:20] = int(rng.integers(0, 1 << 12)).to_bytes(4, "little")
+        else:
+            b[8] = int(rng.integers(0, 256))                                   # l_read_name
+        out.append(bytes(b))
+    return out
+
+
+def test_host_helpers_under_asan(tmp_path):
+    """The header-only host helpers (bam.h, prep.h, record_filter.h) compiled with AddressSanitizer and
+    UBSan into a small harness (tests/native/host_fuzz.cpp) and run over ~10 k valid, truncated and
+    corrupted records held in exact-size heap blocks: any out-of-bounds access aborts the harness."""
+    import shutil
+    import struct
+    import subprocess
+    from tests.test_caller_parity import random_groups, random_duplex_groups
+    from tests.test_duplex_filter import _random_record
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host_fuzz"
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                        "-o", str(exe), os.path.join(root, "tests", "native", "host_fuzz.cpp"),
+                        os.path.join(root, "fgumi_b200", "csrc", "host_tables.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rng = np.random.default_rng(11)
+    recs = []
+    for group in random_groups(rng, 60) + random_duplex_groups(rng, 20):
+        for rec in group:
+            recs.append(bytes(rec))
+            recs.extend(_mutations(rng, rec, 6))
+    for _ in range(300):                                   # consensus records with per-base / strand tags
+        rec = bytes(_random_record(rng))
+        recs.append(rec)
+        recs.extend(_mutations(rng, rec, 6))
+    path = tmp_path / "records.bin"
+    with open(path, "wb") as f:
+        for rec in recs:
+            f.write(struct.pack("<I", len(rec)) + rec)
+    r = subprocess.run([str(exe), str(path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
+    assert r.stdout.startswith("records %d " % len(recs)) and len(recs) > 5000
