@@ -162,6 +162,31 @@ class VanillaUmiConsensusCaller(_Caller):
         self._check(self._lib.fgb_caller_add_groups(self._h, blob.ctypes.data, off.ctypes.data, grp.ctypes.data,
                                                     len(groups)), "fgb_caller_add_groups")
 
+    def pending(self) -> Dict[str, object]:
+        """What is queued for the next flush (fgb_caller_pending), copied out: per unit the list of
+        (bases, quals) source rows and cons_len, plus the duplex / CODEC jobs.  Works on a planning-only
+        caller (device=FGB_DEVICE_NONE) too."""
+        from .engine import UNIT_DTYPE, DUPLEX_JOB_DTYPE, CODEC_JOB_DTYPE
+        b = _l.FgbBatch()
+        dj, cj, ndj, ncj = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.fgb_caller_pending(self._h, C.byref(b), C.addressof(dj), C.addressof(ndj),
+                                                 C.addressof(cj), C.addressof(ncj)), "fgb_caller_pending")
+        arr = lambda ptr, n, dt: (np.frombuffer(C.string_at(ptr, int(n) * np.dtype(dt).itemsize), dtype=dt).copy()
+                                  if n else np.zeros(0, dt))
+        units = arr(b.units, b.n_units, UNIT_DTYPE)
+        reads = arr(b.reads, b.n_reads, np.uint64)
+        bases, quals = arr(b.bases, b.n_bytes, np.uint8), arr(b.quals, b.n_bytes, np.uint8)
+        ends = list(units["read_begin"][1:]) + [int(b.n_reads)]
+        out_units = []
+        for u in range(len(units)):
+            rows = []
+            for r in range(int(units["read_begin"][u]), int(ends[u])):
+                off, ln = int(reads[r]) >> 16, int(reads[r]) & 0xFFFF
+                rows.append((bytes(bases[off:off + ln]), bytes(quals[off:off + ln])))
+            out_units.append({"rows": rows, "cons_len": int(units["cons_len"][u])})
+        return {"units": out_units, "duplex_jobs": arr(dj.value, ndj.value, DUPLEX_JOB_DTYPE),
+                "codec_jobs": arr(cj.value, ncj.value, CODEC_JOB_DTYPE), "n_out": int(b.n_out)}
+
     def flush(self) -> ConsensusOutput:
         data, n, cnt = C.c_void_p(), C.c_uint64(), C.c_uint64()
         self._check(self._lib.fgb_caller_flush(self._h, C.byref(data), C.byref(n), C.byref(cnt)),

@@ -1201,9 +1201,31 @@ fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_call
     p.min_consensus_base_quality = 0;
     p.min_reads = 1;
   }
-  fgb_status st = fgb_create(device, &p, &c->h);
-  if (st != FGB_OK) return st;
+  if (device != FGB_DEVICE_NONE) {       // FGB_DEVICE_NONE: planning only, flush refuses (no CPU fallback)
+    fgb_status st = fgb_create(device, &p, &c->h);
+    if (st != FGB_OK) return st;
+  }
   *out = c.release();
+  return FGB_OK;
+}
+
+fgb_status fgb_caller_pending(const fgb_caller* c, fgb_batch* batch, const fgb_duplex_job** duplex_jobs,
+                              uint64_t* n_duplex_jobs, const fgb_codec_job** codec_jobs,
+                              uint64_t* n_codec_jobs) {
+  if (!c || !batch) return FGB_ERR_INVALID_ARG;
+  std::memset(batch, 0, sizeof(*batch));
+  batch->n_units = c->pack.units.size();
+  batch->n_reads = c->pack.reads.size();
+  batch->n_bytes = c->pack.bases.size();
+  batch->n_out = c->pack.n_out;
+  batch->bases = c->pack.bases.data();
+  batch->quals = c->pack.quals.data();
+  batch->reads = c->pack.reads.data();
+  batch->units = c->pack.units.data();
+  if (duplex_jobs) *duplex_jobs = c->jobs.data();
+  if (n_duplex_jobs) *n_duplex_jobs = c->jobs.size();
+  if (codec_jobs) *codec_jobs = c->codec_jobs.data();
+  if (n_codec_jobs) *n_codec_jobs = c->codec_jobs.size();
   return FGB_OK;
 }
 
@@ -1345,6 +1367,10 @@ fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* o
   c->out.clear();
   c->out_count = 0;
   c->out_is_joined = false;
+  if (!c->h) {
+    c->last_error = "planning-only caller (FGB_DEVICE_NONE): flushing needs a GPU, there is no CPU fallback";
+    return FGB_ERR_NO_DEVICE;
+  }
   fgb_status st = c->opt.mode == FGB_MODE_DUPLEX ? flush_duplex(c)
                   : c->opt.mode == FGB_MODE_CODEC ? flush_codec(c) : flush_simplex(c);
   c->pack.clear(); c->metas.clear(); c->molecules.clear(); c->jobs.clear();

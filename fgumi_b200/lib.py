@@ -130,6 +130,7 @@ class FgbSubmitOptions(C.Structure):
                 ("filter", C.c_void_p), ("unit_status", C.c_void_p), ("unit_masked", C.c_void_p)]
 
 
+FGB_DEVICE_NONE = -1      # fgb_caller_create: planning-only caller (no engine, flush refuses)
 FGB_FILTER_PASS, FGB_FILTER_INSUFFICIENT_READS, FGB_FILTER_EXCESSIVE_ERROR_RATE = 0, 1, 2
 FGB_FILTER_LOW_MEAN_QUALITY, FGB_FILTER_TOO_MANY_NO_CALLS, FGB_FILTER_NO_RECORD = 3, 4, 255
 
@@ -187,7 +188,7 @@ SYMBOLS = (
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
     "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups", "fgb_filter_record", "fgb_host_is_fr_pair",
-    "fgb_host_num_bases_extending_past_mate", "fgb_host_clip_cigar_ops", "fgb_host_read_pos_at_ref_pos", "fgb_host_simplify_cigar", "fgb_host_source_reads", "fgb_host_consensus_umis",
+    "fgb_host_num_bases_extending_past_mate", "fgb_host_clip_cigar_ops", "fgb_host_read_pos_at_ref_pos", "fgb_host_simplify_cigar", "fgb_host_source_reads", "fgb_host_consensus_umis", "fgb_caller_pending",
 )
 
 _lib = None
@@ -311,6 +312,8 @@ def load() -> C.CDLL:
     lib.fgb_host_source_reads.restype = C.c_int32
     lib.fgb_host_consensus_umis.argtypes = [vp, u32, vp, C.c_size_t]
     lib.fgb_host_consensus_umis.restype = C.c_int32
+    lib.fgb_caller_pending.argtypes = [vp, C.POINTER(FgbBatch), vp, vp, vp, vp]
+    lib.fgb_caller_pending.restype = C.c_int32
     lib.fgb_caller_add_groups.argtypes = [vp, vp, vp, vp, u64]
     lib.fgb_caller_add_groups.restype = C.c_int32
     lib.fgb_struct_size.argtypes = [C.c_uint32]

@@ -1,0 +1,131 @@
+"""The host half of the three record-level callers WITHOUT a GPU: a planning-only caller
+(fgb_caller_create(FGB_DEVICE_NONE)) runs the product's group rules and source-read preparation and
+queues the packed batch; per MI group its units (source rows in order, consensus length) must equal
+what the oracle caller hands to its vote hook, and flushing must fail loudly (no CPU fallback)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import record_oracle as R           # noqa: E402
+from tests import oracle_lib as O               # noqa: E402
+from tests.test_record_oracle_kat import vote_fn   # noqa: E402
+from tests.test_caller_parity import random_groups, random_duplex_groups, random_codec_groups, duplex_job_fn   # noqa: E402
+from tests.test_codec_oracle_kat import codec_job_fn   # noqa: E402
+
+
+class Capture:
+    """Wraps the oracle's vote hook and records the row lists it is called with."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, rows, opt):
+        self.calls.append(([(bytes(b), bytes(q)) for b, q in rows], opt.min_reads))
+        return vote_fn(rows, opt)
+
+
+def _cons_len(rows, min_reads):
+    return sorted((len(b) for b, _ in rows), reverse=True)[min_reads - 1]
+
+
+def _compare_groups(fg, product, oracle_call, cap, groups, unordered=False, orphans=None):
+    """`orphans`: callable returning the oracle's running OrphanConsensus count.  The simplex oracle
+    votes R1 / R2 sub-groups one by one and only then drops a pair whose mate has no consensus; the
+    product knows that at planning time and does not queue the lone sub-group -- so its units may be
+    a subsequence of the oracle's vote calls, with the difference explained by orphan rejections."""
+    n_units = n_skipped = 0
+    for g in groups:
+        cap.calls.clear()
+        o0 = orphans() if orphans else 0
+        n_out = oracle_call(g)
+        before = len(product.pending()["units"])
+        product.add_group(g)
+        units = product.pending()["units"][before:]
+        want = [(rows, _cons_len(rows, mr)) for rows, mr in cap.calls]
+        got = [(u["rows"], u["cons_len"]) for u in units]
+        if unordered:
+            key = lambda t: (t[1], t[0])
+            got, want = sorted(got, key=key), sorted(want, key=key)
+        if orphans and len(got) < len(want):
+            it = iter(want)
+            assert all(any(x == y for y in it) for x in got), "units are not a subsequence of the oracle's calls"
+            assert orphans() > o0
+            n_skipped += len(want) - len(got)
+        elif unordered and len(got) < len(want):
+            # duplex / CODEC: the oracle votes strand by strand and may only then find that the molecule
+            # cannot be completed; the product sees that while planning and queues nothing for it
+            assert got == [] and n_out == 0, (len(got), len(want), n_out)
+            n_skipped += len(want)
+        else:
+            assert got == want
+        n_units += len(got)
+    return n_units, n_skipped
+
+
+def test_planning_only_caller_refuses_to_flush():
+    import fgumi_b200 as fg
+    c = fg.VanillaUmiConsensusCaller("fgumi", "A", device=fg.lib.FGB_DEVICE_NONE)
+    c.add_group(random_groups(np.random.default_rng(1), 3)[0])
+    with pytest.raises(fg.lib.FgbError) as e:
+        c.flush()
+    assert e.value.status == fg.lib.FGB_ERR_NO_DEVICE
+    c.close()
+
+
+@pytest.mark.parametrize("min_reads,trim,overlap", [(1, False, False), (2, True, False), (1, False, True)])
+def test_simplex_host_prep_matches_oracle(min_reads, trim, overlap):
+    import fgumi_b200 as fg
+    rng = np.random.default_rng(31 + min_reads)
+    groups = random_groups(rng, 200)
+    cap = Capture()
+    oracle = R.VanillaCallerOracle("fgumi", "A", R.VanillaOptions(min_reads=min_reads, trim=trim), cap, O.builder_call)
+    ov = R.OverlappingOracle() if overlap else None
+
+    def call(g):
+        if ov is not None:
+            recs = [bytearray(r) for r in g]
+            ov.apply(recs)
+            g = [bytes(r) for r in recs]
+        oracle.consensus_reads(g)
+    opts = fg.VanillaUmiConsensusOptions(min_reads=min_reads, trim=trim)
+    c = fg.VanillaUmiConsensusCaller("fgumi", "A", opts, device=fg.lib.FGB_DEVICE_NONE,
+                                     consensus_call_overlapping_bases=overlap)
+    n, skipped = _compare_groups(fg, c, call, cap, groups,
+                                 orphans=lambda: oracle.stats.rejections.get("OrphanConsensus", 0))
+    st = c.statistics()
+    c.close()
+    assert n > 150 and skipped > 0 and st["total_reads"] == sum(len(g) for g in groups)
+
+
+@pytest.mark.parametrize("min_reads", [(1, 1, 1), (2, 1, 0), (3, 2, 1)])
+def test_duplex_host_prep_matches_oracle(min_reads):
+    import fgumi_b200 as fg
+    rng = np.random.default_rng(77 + sum(min_reads))
+    groups = random_duplex_groups(rng, 150)
+    cap = Capture()
+    oracle = R.DuplexCallerOracle("fgumi", "A", min_reads=min_reads, per_base=True, vote_fn=cap,
+                                  builder_fn=O.builder_call, duplex_job_fn=duplex_job_fn)
+    c = fg.DuplexConsensusCaller("fgumi", "A", min_reads=min_reads, device=fg.lib.FGB_DEVICE_NONE)
+    n, _ = _compare_groups(fg, c, lambda g: oracle.consensus_reads(g)[1], cap, groups, unordered=True)
+    pend = c.pending()
+    st = c.statistics()
+    c.close()
+    assert n > 200 and len(pend["duplex_jobs"]) > 50
+    assert st["total_reads"] == oracle.stats.total_reads
+    assert st["PotentialCollision"] == oracle.stats.rejections.get("PotentialCollision", 0) > 0
+
+
+def test_codec_host_prep_matches_oracle():
+    import fgumi_b200 as fg
+    rng = np.random.default_rng(5)
+    groups = random_codec_groups(rng, 150)
+    cap = Capture()
+    oracle = R.CodecCallerOracle("fgumi", "A", vote_fn=cap, builder_fn=O.builder_call, codec_job_fn=codec_job_fn)
+    c = fg.CodecConsensusCaller("fgumi", "A", device=fg.lib.FGB_DEVICE_NONE)
+    n, _ = _compare_groups(fg, c, lambda g: oracle.consensus_reads(g)[1], cap, groups, unordered=True)
+    pend = c.pending()
+    c.close()
+    assert n > 100 and len(pend["codec_jobs"]) * 2 == n
