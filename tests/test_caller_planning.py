@@ -129,3 +129,32 @@ def test_codec_host_prep_matches_oracle():
     pend = c.pending()
     c.close()
     assert n > 100 and len(pend["codec_jobs"]) * 2 == n
+
+
+@pytest.mark.parametrize("mode", ["simplex", "duplex", "codec"])
+def test_threaded_add_groups_queues_the_same_batch(mode):
+    """fgb_caller_add_groups on several host threads (worker sub-callers merged in input order) must
+    queue exactly what group-by-group calls on one thread queue: units, rows, jobs and counters."""
+    import fgumi_b200 as fg
+    rng = np.random.default_rng(12)
+    if mode == "simplex":
+        groups = random_groups(rng, 300)
+        mk = lambda t: fg.VanillaUmiConsensusCaller("fgumi", "A", device=fg.lib.FGB_DEVICE_NONE, n_threads=t,
+                                                    consensus_call_overlapping_bases=True)
+    elif mode == "duplex":
+        groups = random_duplex_groups(rng, 200)
+        mk = lambda t: fg.DuplexConsensusCaller("fgumi", "A", min_reads=(1, 1, 0), device=fg.lib.FGB_DEVICE_NONE, n_threads=t)
+    else:
+        groups = random_codec_groups(rng, 200)
+        mk = lambda t: fg.CodecConsensusCaller("fgumi", "A", device=fg.lib.FGB_DEVICE_NONE, n_threads=t)
+    one = mk(1)
+    for g in groups:
+        one.add_group(g)
+    many = mk(5)
+    many.add_groups(groups)
+    a, b = one.pending(), many.pending()
+    sa, sb = one.statistics(), many.statistics()
+    one.close(); many.close()
+    assert a["units"] == b["units"] and a["n_out"] == b["n_out"] and len(a["units"]) > 100
+    assert np.array_equal(a["duplex_jobs"], b["duplex_jobs"]) and np.array_equal(a["codec_jobs"], b["codec_jobs"])
+    assert sa == sb
