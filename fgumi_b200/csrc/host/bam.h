@@ -395,20 +395,20 @@ inline void simplify_cigar(const std::vector<uint32_t>& ops, SimpleCigar* out) {
 }
 
 inline void truncate_cigar(SimpleCigar* c, size_t query_len) {   // vanilla_caller.rs:816-851
-  SimpleCigar r;
-  size_t remaining = query_len;
-  for (auto& e : *c) {
+  size_t remaining = query_len, w = 0;                           // in place: elements only shrink
+  for (size_t i = 0; i < c->size(); ++i) {
     if (remaining == 0) break;
-    bool q = e.first == 0 || e.first == 1 || e.first == 4 || e.first == 7 || e.first == 8;
+    auto e = (*c)[i];
+    const bool q = e.first == 0 || e.first == 1 || e.first == 4 || e.first == 7 || e.first == 8;
     if (q) {
-      uint32_t take = e.second < remaining ? e.second : static_cast<uint32_t>(remaining);
-      r.emplace_back(e.first, take);
+      const uint32_t take = e.second < remaining ? e.second : static_cast<uint32_t>(remaining);
+      (*c)[w++] = {e.first, take};
       remaining -= take;
     } else {
-      r.push_back(e);
+      (*c)[w++] = e;
     }
   }
-  c->swap(r);
+  c->resize(w);
 }
 
 inline bool is_cigar_prefix(const SimpleCigar& a, const SimpleCigar& b) {

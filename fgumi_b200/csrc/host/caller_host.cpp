@@ -72,6 +72,14 @@ struct CodecMolecule {               // CODEC: one MI group that reached the vot
   std::vector<std::string> rx;       // RX of ALL records of the group (codec_caller.rs:1340-1349)
 };
 
+struct Prepared {
+  bool ok = false;
+  size_t surviving = 0;
+  size_t n = 0;                    // live elements of `srs`; the rest is a pool whose buffers are reused
+  std::vector<SourceRead> srs;
+  std::vector<uint32_t> rec_idx;   // indices (into the group's records) of the surviving reads
+};
+
 }  // namespace
 
 struct fgb_caller {
@@ -94,6 +102,8 @@ struct fgb_caller {
   uint64_t out_count = 0;
   std::string last_error;
   std::vector<uint32_t> ops;             // scratch
+  Prepared prepared[3];                  // simplex: fragment / R1 / R2 sub-groups, buffers reused across groups
+  std::vector<uint32_t> scratch_idx[4];  // simplex: kept / fragment / R1 / R2 record indices
   overlap::Caller overlap{overlap::kAgreeConsensus, overlap::kDisagreeConsensus};   // simplex.rs:384-387
   std::vector<uint8_t> group_copy;       // mutable copy of a group for the overlap pre-pass
   std::vector<std::unique_ptr<fgb_caller>> workers;   // per-thread prep state of fgb_caller_add_groups (no GPU handle)
@@ -123,17 +133,10 @@ bool get_string_tag(const View& v, const char tag[2], std::string* out) {
 // ------------------------------------------------------------------------------------------------
 // simplex
 // ------------------------------------------------------------------------------------------------
-struct Prepared {
-  bool ok = false;
-  size_t surviving = 0;
-  std::vector<SourceRead> srs;
-  std::vector<uint32_t> rec_idx;   // indices (into the group's records) of the surviving reads
-};
-
 // process_subgroup up to the vote, vanilla_caller.rs:1124-1227
 void prepare_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::vector<uint32_t>& members,
                       Prepared* p) {
-  p->ok = false; p->surviving = 0; p->srs.clear(); p->rec_idx.clear();
+  p->ok = false; p->surviving = 0; p->n = 0; p->rec_idx.clear();
   const size_t min_reads = c->opt.min_reads;
   if (members.empty()) return;
   if (members.size() < min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, members.size()); return; }
@@ -142,33 +145,35 @@ void prepare_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::v
     const View& v = recs[members[k]];
     bam::cigar_ops(v, &c->ops);
     size_t clip = bam::num_bases_extending_past_mate(v, c->ops);
-    SourceRead sr;
-    if (make_source_read(c->prep_opt, v, k, clip, &c->ops, &sr)) p->srs.push_back(std::move(sr));
+    if (p->n == p->srs.size()) p->srs.emplace_back();
+    if (make_source_read(c->prep_opt, v, k, clip, &c->ops, &p->srs[p->n])) ++p->n;
     else ++zero;
   }
   if (zero) reject(c, FGB_STAT_REJ_ZERO_LENGTH, zero);
-  if (p->srs.size() < min_reads) {
-    if (!p->srs.empty()) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, p->srs.size());
+  if (p->n < min_reads) {
+    if (p->n) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, p->n);
     return;
   }
-  size_t minority = filter_by_alignment(&p->srs);
-  if (minority) reject(c, FGB_STAT_REJ_MINORITY_ALIGNMENT, minority);
-  if (p->srs.size() < min_reads) {
-    if (!p->srs.empty()) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, p->srs.size());
+  const size_t kept = filter_by_alignment_n(&p->srs, p->n);
+  if (kept != p->n) reject(c, FGB_STAT_REJ_MINORITY_ALIGNMENT, p->n - kept);
+  p->n = kept;
+  if (p->n < min_reads) {
+    if (p->n) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, p->n);
     return;
   }
   p->ok = true;
-  p->surviving = p->srs.size();
-  for (auto& sr : p->srs) p->rec_idx.push_back(members[sr.original_idx]);
+  p->surviving = p->n;
+  for (size_t i = 0; i < p->n; ++i) p->rec_idx.push_back(members[p->srs[i].original_idx]);
 }
 
 void pack_simplex_unit(fgb_caller* c, const std::vector<View>& recs, const Prepared& p, uint8_t read_type,
                        const std::string& umi) {
-  c->pack.add_unit(p.srs, c->opt.min_reads);
+  c->pack.add_unit(p.srs, p.n, c->opt.min_reads);
   UnitMeta m;
   m.read_type = read_type;
   m.umi = umi;
   std::string s;
+  m.rx.reserve(p.rec_idx.size());
   for (uint32_t ri : p.rec_idx) if (get_string_tag(recs[ri], "RX", &s)) m.rx.push_back(s);
   if (c->opt.cell_tag[0] && !p.rec_idx.empty()) m.has_cell = get_string_tag(recs[p.rec_idx[0]], c->opt.cell_tag, &m.cell);
   c->metas.push_back(std::move(m));
@@ -183,7 +188,8 @@ fgb_status add_group_simplex(fgb_caller* c, const std::vector<View>& recs) {
     return FGB_ERR_MISSING_TAG;
   }
   c->stats[FGB_STAT_TOTAL_READS] += n_records;
-  std::vector<uint32_t> kept;
+  std::vector<uint32_t>&kept = c->scratch_idx[0], &frag = c->scratch_idx[1], &r1 = c->scratch_idx[2], &r2 = c->scratch_idx[3];
+  kept.clear(); frag.clear(); r1.clear(); r2.clear();
   for (uint32_t i = 0; i < n_records; ++i) {
     uint16_t f = recs[i].flags();
     if (!(f & bam::kSecondary) && !(f & bam::kSupplementary)) kept.push_back(i);
@@ -191,14 +197,13 @@ fgb_status add_group_simplex(fgb_caller* c, const std::vector<View>& recs) {
   if (kept.size() != n_records) reject(c, FGB_STAT_REJ_SECONDARY_SUPPLEMENTARY, n_records - kept.size());
   if (kept.empty()) return FGB_OK;
   if (kept.size() < c->opt.min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, kept.size()); return FGB_OK; }
-  std::vector<uint32_t> frag, r1, r2;
   for (uint32_t i : kept) {   // subgroup_reads, vanilla_caller.rs:1018-1039
     uint16_t f = recs[i].flags();
     if (!(f & bam::kPaired)) frag.push_back(i);
     else if (f & bam::kFirst) r1.push_back(i);
     else if (f & bam::kLast) r2.push_back(i);
   }
-  Prepared pf, p1, p2;
+  Prepared &pf = c->prepared[0], &p1 = c->prepared[1], &p2 = c->prepared[2];   // pooled across groups
   prepare_subgroup(c, recs, frag, &pf);
   if (pf.ok) { pack_simplex_unit(c, recs, pf, kFragment, umi); c->stats[FGB_STAT_CONSENSUS_READS] += 1; }
   prepare_subgroup(c, recs, r1, &p1);

@@ -107,29 +107,72 @@ inline size_t quality_trim_point(const std::vector<uint8_t>& q, uint8_t trim_qua
 }
 
 
-// create_source_read, vanilla_caller.rs:863-955
+// create_source_read, vanilla_caller.rs:863-955.
+// One fused pass: the reference decodes the 4-bit sequence, reverse-complements negative-strand reads,
+// masks low qualities, clips and strips trailing Ns in separate sweeps; only the first
+// min(read_len - mate_clip, trim_to) oriented positions can survive, so only those are produced, each
+// straight from its nibble (a second 16-entry table decodes AND complements) and quality byte.
 inline bool make_source_read(const PrepOptions& opt, const View& v, uint32_t idx, size_t mate_clip,
                              std::vector<uint32_t>* ops, SourceRead* sr) {
+  static const char kFwd[17] = "=ACMGRSVTWYHKDBN";     // sequence.rs nibble codes
+  static const char kRev[17] = "=TGMCRSVAWYHKDBN";     // ... complemented (A<->T, C<->G, rest unchanged)
   const bool neg = v.flags() & bam::kReverse;
   const uint8_t min_bq = opt.min_input_base_quality;
-  bam::decode_sequence(v, &sr->bases);
   const uint32_t read_len = v.l_seq();
   if (read_len == 0 || v.qual_off() + read_len > v.n) return false;
-  sr->quals.assign(v.b + v.qual_off(), v.b + v.qual_off() + read_len);
+  const uint8_t* s = v.b + v.seq_off();
+  const uint8_t* q = v.b + v.qual_off();
   bool all_ff = true;
-  for (uint8_t q : sr->quals) if (q != 0xFF) { all_ff = false; break; }
-  if (all_ff) return false;
-  if (neg) {
-    std::reverse(sr->bases.begin(), sr->bases.end());
-    for (auto& b : sr->bases) b = bam::complement(b);
-    std::reverse(sr->quals.begin(), sr->quals.end());
+  for (uint32_t i = 0; i < read_len; ++i) if (q[i] != 0xFF) { all_ff = false; break; }
+  if (all_ff) return false;                                  // missing qualities
+  size_t trim_to = read_len;
+  if (opt.trim) {                                            // needs the oriented qualities as a whole
+    static thread_local std::vector<uint8_t> oriented;
+    if (neg) oriented.assign(std::reverse_iterator<const uint8_t*>(q + read_len), std::reverse_iterator<const uint8_t*>(q));
+    else oriented.assign(q, q + read_len);
+    trim_to = quality_trim_point(oriented, min_bq);
   }
-  const size_t trim_to = opt.trim ? quality_trim_point(sr->quals, min_bq) : read_len;
-  for (size_t i = 0; i < trim_to; ++i)
-    if (sr->quals[i] < min_bq) { sr->bases[i] = 'N'; sr->quals[i] = 2; }
   const size_t clip_position = read_len > mate_clip ? read_len - mate_clip : 0;
-  size_t final_len = std::min(clip_position, trim_to);
-  while (final_len > 0 && sr->bases[final_len - 1] == 'N') --final_len;
+  const size_t bound = std::min(clip_position, trim_to);
+  if (bound == 0) return false;                              // nothing can survive (final_len == 0 below)
+  sr->bases.resize(bound);
+  sr->quals.resize(bound);
+  uint8_t* __restrict ob = sr->bases.data();
+  uint8_t* __restrict oq = sr->quals.data();
+  // a pair table decodes one packed byte (two bases) per step, complemented and swapped for
+  // negative-strand reads; then a (reversed) copy of the qualities and a compare-and-blend pass that
+  // the compiler vectorises
+  struct PairTables {
+    uint16_t fwd[256], rev[256];
+    PairTables() {
+      for (int b = 0; b < 256; ++b) {
+        const uint8_t f[2] = {static_cast<uint8_t>(kFwd[b >> 4]), static_cast<uint8_t>(kFwd[b & 15])};
+        const uint8_t r[2] = {static_cast<uint8_t>(kRev[b & 15]), static_cast<uint8_t>(kRev[b >> 4])};
+        std::memcpy(&fwd[b], f, 2);
+        std::memcpy(&rev[b], r, 2);
+      }
+    }
+  };
+  static const PairTables kPairs;
+  if (!neg) {
+    const size_t n2 = bound >> 1;
+    for (size_t k = 0; k < n2; ++k) std::memcpy(ob + 2 * k, &kPairs.fwd[s[k]], 2);
+    if (bound & 1) ob[bound - 1] = static_cast<uint8_t>(kFwd[s[bound >> 1] >> 4]);
+    std::memcpy(oq, q, bound);
+  } else {
+    size_t i = 0, j = read_len - 1;                        // oriented position i is record position j
+    if (bound > 0 && !(j & 1)) { ob[0] = static_cast<uint8_t>(kRev[s[j >> 1] >> 4]); i = 1; --j; }
+    for (; i + 2 <= bound; i += 2, j -= 2) std::memcpy(ob + i, &kPairs.rev[s[j >> 1]], 2);   // j odd: (low, high) nibble
+    if (i < bound) ob[i] = static_cast<uint8_t>(kRev[s[j >> 1] & 15]);
+    std::reverse_copy(q + (read_len - bound), q + read_len, oq);
+  }
+  for (size_t i = 0; i < bound; ++i) {
+    const bool low = oq[i] < min_bq;
+    ob[i] = low ? static_cast<uint8_t>('N') : ob[i];
+    oq[i] = low ? static_cast<uint8_t>(2) : oq[i];
+  }
+  size_t final_len = bound;
+  while (final_len > 0 && ob[final_len - 1] == 'N') --final_len;
   if (final_len == 0) return false;
   sr->bases.resize(final_len);
   sr->quals.resize(final_len);
@@ -144,39 +187,58 @@ inline bool make_source_read(const PrepOptions& opt, const View& v, uint32_t idx
 
 
 // filter_source_reads_by_alignment + select_most_common_alignment_group, vanilla_caller.rs:47-119,961-1013
-inline size_t filter_by_alignment(std::vector<SourceRead>* srs) {
-  const size_t n = srs->size();
-  if (n < 2) return 0;
-  std::vector<uint32_t> order(n);
+// over the first `n` elements of `srs`: the kept reads are moved to the front in their original order
+// (by swapping, so every element keeps its buffers for reuse) and their number is returned.
+inline size_t filter_by_alignment_n(std::vector<SourceRead>* srs, size_t n) {
+  if (n < 2) return n;
+  static thread_local std::vector<uint32_t> order;
+  order.resize(n);
   for (uint32_t i = 0; i < n; ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
     return (*srs)[a].bases.size() > (*srs)[b].bases.size();
   });
   struct Group { const bam::SimpleCigar* cigar; std::vector<uint32_t> members; };
-  std::vector<Group> groups;
+  static thread_local std::vector<Group> groups;
+  size_t n_groups = 0;
   for (uint32_t idx : order) {
     const bam::SimpleCigar& cg = (*srs)[idx].cigar;
     bool found = false;
-    for (auto& g : groups)
-      if (bam::is_cigar_prefix(cg, *g.cigar)) { g.members.push_back(idx); found = true; }   // no break (fgbio)
-    if (!found) groups.push_back(Group{&cg, {idx}});
+    for (size_t g = 0; g < n_groups; ++g)
+      if (bam::is_cigar_prefix(cg, *groups[g].cigar)) { groups[g].members.push_back(idx); found = true; }   // no break (fgbio)
+    if (!found) {
+      if (n_groups == groups.size()) groups.emplace_back();
+      groups[n_groups].cigar = &cg;
+      groups[n_groups].members.assign(1, idx);
+      ++n_groups;
+    }
   }
   // Iterator::max_by keeps the LAST maximum: larger group wins, then the smaller CIGAR
   const Group* best = nullptr;
-  for (const auto& g : groups) {
+  for (size_t gi = 0; gi < n_groups; ++gi) {
+    const Group& g = groups[gi];
     if (!best) { best = &g; continue; }
     int cmp = g.members.size() < best->members.size() ? -1 : (g.members.size() > best->members.size() ? 1 : 0);
     if (cmp == 0) cmp = bam::cmp_cigar(*best->cigar, *g.cigar);
     if (cmp >= 0) best = &g;
   }
-  std::vector<char> keep(n, 0);
+  if (best->members.size() == n) return n;                  // the common case: nothing to drop
+  static thread_local std::vector<char> keep;
+  keep.assign(n, 0);
   for (uint32_t i : best->members) keep[i] = 1;
-  size_t kept = 0;
-  for (char k : keep) kept += k;
-  std::vector<SourceRead> out;
-  out.reserve(kept);
-  for (size_t i = 0; i < n; ++i) if (keep[i]) out.push_back(std::move((*srs)[i]));
-  srs->swap(out);
+  size_t w = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (!keep[i]) continue;
+    if (w != i) { std::swap((*srs)[w], (*srs)[i]); std::swap(keep[w], keep[i]); }
+    ++w;
+  }
+  return w;
+}
+
+// Vector form: drops the minority reads, returns how many were dropped.
+inline size_t filter_by_alignment(std::vector<SourceRead>* srs) {
+  const size_t n = srs->size();
+  const size_t kept = filter_by_alignment_n(srs, n);
+  srs->resize(kept);
   return n - kept;
 }
 
@@ -218,20 +280,24 @@ struct Packer {
   std::vector<fgb_unit> units;
   uint64_t n_out = 0;
   // Appends one unit (its SourceRead rows); returns the unit index.
-  uint32_t add_unit(const std::vector<SourceRead>& srs, size_t min_reads) {
+  uint32_t add_unit(const std::vector<SourceRead>& srs, size_t min_reads) { return add_unit(srs, srs.size(), min_reads); }
+  // ... the first `n` elements of `srs`
+  uint32_t add_unit(const std::vector<SourceRead>& srs, size_t n, size_t min_reads) {
     fgb_unit u;
     u.out_off = n_out;
     u.read_begin = static_cast<uint32_t>(reads.size());
-    std::vector<size_t> lens;
-    for (const auto& sr : srs) {
-      size_t off = bases.size();
-      size_t len = sr.bases.size();
+    static thread_local std::vector<size_t> lens;
+    lens.clear();
+    for (size_t k = 0; k < n; ++k) {
+      const SourceRead& sr = srs[k];
+      const size_t off = bases.size();
+      const size_t len = sr.bases.size();
       reads.push_back(FGB_READ_DESC(off, len));
-      bases.insert(bases.end(), sr.bases.begin(), sr.bases.end());
-      quals.insert(quals.end(), sr.quals.begin(), sr.quals.end());
-      size_t pad = round_up(len, FGB_READ_ALIGN) - len;
-      bases.insert(bases.end(), pad, 0);
-      quals.insert(quals.end(), pad, 0);
+      const size_t padded = round_up(len, FGB_READ_ALIGN);
+      bases.resize(off + padded, 0);                         // value-initialised: the padding is zero
+      quals.resize(off + padded, 0);
+      std::memcpy(bases.data() + off, sr.bases.data(), len);
+      std::memcpy(quals.data() + off, sr.quals.data(), len);
       lens.push_back(len);
     }
     std::sort(lens.begin(), lens.end(), std::greater<size_t>());
