@@ -48,9 +48,9 @@ __global__ void __launch_bounds__(256) filter_simplex_kernel(const FilterArgs a)
       uint32_t b = a.base[o], q = a.qual[o];
       const uint32_t d = a.depth[o], e = a.errors[o];
       maxd = d > maxd ? d : maxd; td += d; te += e;
-      // the filter reads cd / ce back from the record, where the caller stored them as i16 (a value
-      // above 32767 wraps negative) and array_tag_element_u16 clamps negatives to 0 (raw-bam tags.rs:487-490)
-      const uint32_t dt = (a.per_base_tags && d < 32768u) ? d : 0u, et = (a.per_base_tags && e < 32768u) ? e : 0u;
+      // the filter reads cd / ce back from the record, where the simplex caller stored them clamped to
+      // i16::MAX (vanilla_caller.rs:1410-1412)
+      const uint32_t dt = a.per_base_tags ? (d < 32767u ? d : 32767u) : 0u, et = a.per_base_tags ? (e < 32767u ? e : 32767u) : 0u;
       const bool mask = q < a.min_base_quality || dt < a.min_reads || (dt > 0u && et > a.emax[dt]);
       if (mask) {
         newly += (b != 'N');

@@ -458,6 +458,7 @@ struct Writer {
       default: return 15;
     }
   }
+  struct CodeTable { uint8_t t[256]; CodeTable() { for (int b = 0; b < 256; ++b) t[b] = code(static_cast<uint8_t>(b)); } };
   void begin(const std::string& name, uint16_t flag, const uint8_t* bases, const uint8_t* quals, uint32_t l) {
     start = out->size();
     le<uint32_t>(0);                       // block_size, patched in end()
@@ -468,9 +469,14 @@ struct Writer {
     le<int32_t>(-1); le<int32_t>(-1); le<int32_t>(0);
     put(name.data(), name.size());
     out->push_back(0);
-    for (uint32_t i = 0; i + 1 < l; i += 2) out->push_back(static_cast<uint8_t>((code(bases[i]) << 4) | code(bases[i + 1])));
-    if (l & 1) out->push_back(static_cast<uint8_t>(code(bases[l - 1]) << 4));
-    put(quals, l);
+    // packed sequence + qualities: sized once, written in place
+    static const CodeTable kCodes;
+    const size_t o = out->size(), nb = (static_cast<size_t>(l) + 1) / 2;
+    out->resize(o + nb + l);
+    uint8_t* p = out->data() + o;
+    for (uint32_t i = 0; i + 1 < l; i += 2) p[i >> 1] = static_cast<uint8_t>((kCodes.t[bases[i]] << 4) | kCodes.t[bases[i + 1]]);
+    if (l & 1) p[l >> 1] = static_cast<uint8_t>(kCodes.t[bases[l - 1]] << 4);
+    if (l) std::memcpy(p + nb, quals, l);
   }
   void tag(const char t[2], char type) { out->push_back(t[0]); out->push_back(t[1]); out->push_back(type); }
   void str(const char t[2], const void* v, size_t n) { tag(t, 'Z'); put(v, n); out->push_back(0); }
@@ -482,18 +488,22 @@ struct Writer {
     else { tag(t, 'i'); le<int32_t>(v); }
   }
   void real(const char t[2], float v) { tag(t, 'f'); le<float>(v); }
+  uint8_t* grow(size_t n) { const size_t o = out->size(); out->resize(o + n); return out->data() + o; }
   void i16_array(const char t[2], const uint16_t* v, uint32_t n) {   // values clamp to i16::MAX
     tag(t, 'B'); out->push_back('s'); le<uint32_t>(n);
-    for (uint32_t i = 0; i < n; ++i) le<int16_t>(static_cast<int16_t>(v[i] > 32767 ? 32767 : v[i]));
+    uint8_t* p = grow(2 * static_cast<size_t>(n));
+    for (uint32_t i = 0; i < n; ++i) { const uint16_t x = v[i] > 32767 ? 32767 : v[i]; std::memcpy(p + 2 * i, &x, 2); }
   }
-  void i16_array_wrap(const char t[2], const uint16_t* v, uint32_t n) {   // `as i16` (wrapping)
+  void i16_array_wrap(const char t[2], const uint16_t* v, uint32_t n) {   // `as i16` (wrapping): same bits
     tag(t, 'B'); out->push_back('s'); le<uint32_t>(n);
-    for (uint32_t i = 0; i < n; ++i) le<int16_t>(static_cast<int16_t>(v[i]));
+    uint8_t* p = grow(2 * static_cast<size_t>(n));
+    if (n) std::memcpy(p, v, 2 * static_cast<size_t>(n));
   }
   void phred33(const char t[2], const uint8_t* q, uint32_t n) {
     tag(t, 'Z');
-    for (uint32_t i = 0; i < n; ++i) out->push_back(static_cast<uint8_t>(q[i] > 222 ? 255 : q[i] + 33));
-    out->push_back(0);
+    uint8_t* p = grow(static_cast<size_t>(n) + 1);
+    for (uint32_t i = 0; i < n; ++i) p[i] = static_cast<uint8_t>(q[i] > 222 ? 255 : q[i] + 33);
+    p[n] = 0;
   }
   void end() {
     uint32_t bs = static_cast<uint32_t>(out->size() - start - 4);

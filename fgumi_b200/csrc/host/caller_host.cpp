@@ -248,6 +248,46 @@ struct PhaseTrace {
   }
 };
 
+// build_consensus_record_into, vanilla_caller.rs:1365-1473: one simplex consensus record from its columns.
+fgb_status write_simplex_record(const fgb_caller* c, bam::Writer* wp, const UnitMeta& m, uint32_t L,
+                                const uint8_t* bases, const uint8_t* quals, const uint16_t* depths,
+                                const uint16_t* errors, std::string* rx_scratch, std::string* err) {
+  bam::Writer& w = *wp;
+  std::string& rx = *rx_scratch;
+  uint16_t flag = bam::kUnmapped;
+  if (m.read_type == kR1) flag |= bam::kPaired | bam::kFirst | bam::kMateUnmapped;
+  else if (m.read_type == kR2) flag |= bam::kPaired | bam::kLast | bam::kMateUnmapped;
+  std::string name = c->prefix + ":" + m.umi;
+  if (name.size() >= 255) { *err = "read name too long"; return FGB_ERR_INVALID_ARG; }
+  w.begin(name, flag, bases, quals, L);
+  w.str("RG", c->rg.data(), c->rg.size());
+  uint32_t max_d = 0, min_d = L ? 0xFFFFFFFFu : 0;
+  uint64_t tot_e = 0, tot_d = 0;
+  for (uint32_t k = 0; k < L; ++k) {
+    max_d = std::max<uint32_t>(max_d, depths[k]);
+    min_d = std::min<uint32_t>(min_d, depths[k]);
+    tot_e += errors[k];
+    tot_d += depths[k];
+  }
+  w.integer("cD", static_cast<int32_t>(max_d));
+  w.integer("cM", static_cast<int32_t>(min_d));
+  w.real("cE", error_rate(tot_e, tot_d));
+  if (c->opt.produce_per_base_tags) {
+    w.i16_array("cd", depths, L);
+    w.i16_array("ce", errors, L);
+  }
+  w.str("MI", m.umi.data(), m.umi.size());
+  if (m.has_cell) w.str(c->opt.cell_tag, m.cell.data(), m.cell.size());
+  if (!m.rx.empty()) {
+    if (!consensus_umis(c->umi_builder, m.rx, &rx)) {   // the reference panics here (simple_umi.rs:78-116)
+      *err = "RX values of a family have different lengths or mix DNA and non-DNA characters";
+      return FGB_ERR_INVALID_ARG;
+    }
+    w.str("RX", rx.data(), rx.size());
+  }
+  return FGB_OK;
+}
+
 fgb_status flush_simplex(fgb_caller* c) {
   const uint64_t U = c->pack.units.size();
   if (!U) return FGB_OK;
@@ -331,42 +371,9 @@ fgb_status flush_simplex(fgb_caller* c) {
       if (!emit[i]) continue;
       const fgb_unit& u = c->pack.units[i];
       const UnitMeta& m = c->metas[i];
-      const uint32_t L = u.cons_len;
-      const uint8_t* bases = ob.data() + u.out_off;
-      const uint8_t* quals = oq.data() + u.out_off;
-      const uint16_t* depths = od.data() + u.out_off;
-      const uint16_t* errors = oe.data() + u.out_off;
-      uint16_t flag = bam::kUnmapped;
-      if (m.read_type == kR1) flag |= bam::kPaired | bam::kFirst | bam::kMateUnmapped;
-      else if (m.read_type == kR2) flag |= bam::kPaired | bam::kLast | bam::kMateUnmapped;
-      std::string name = c->prefix + ":" + m.umi;
-      if (name.size() >= 255) { *err = "read name too long"; return FGB_ERR_INVALID_ARG; }
-      w.begin(name, flag, bases, quals, L);
-      w.str("RG", c->rg.data(), c->rg.size());
-      uint32_t max_d = 0, min_d = L ? 0xFFFFFFFFu : 0;
-      uint64_t tot_e = 0, tot_d = 0;
-      for (uint32_t k = 0; k < L; ++k) {
-        max_d = std::max<uint32_t>(max_d, depths[k]);
-        min_d = std::min<uint32_t>(min_d, depths[k]);
-        tot_e += errors[k];
-        tot_d += depths[k];
-      }
-      w.integer("cD", static_cast<int32_t>(max_d));
-      w.integer("cM", static_cast<int32_t>(min_d));
-      w.real("cE", error_rate(tot_e, tot_d));
-      if (c->opt.produce_per_base_tags) {
-        w.i16_array("cd", depths, L);
-        w.i16_array("ce", errors, L);
-      }
-      w.str("MI", m.umi.data(), m.umi.size());
-      if (m.has_cell) w.str(c->opt.cell_tag, m.cell.data(), m.cell.size());
-      if (!m.rx.empty()) {
-        if (!consensus_umis(c->umi_builder, m.rx, &rx)) {   // the reference panics here (simple_umi.rs:78-116)
-          *err = "RX values of a family have different lengths or mix DNA and non-DNA characters";
-          return FGB_ERR_INVALID_ARG;
-        }
-        w.str("RX", rx.data(), rx.size());
-      }
+      fgb_status rs = write_simplex_record(c, &w, m, u.cons_len, ob.data() + u.out_off, oq.data() + u.out_off,
+                                           od.data() + u.out_off, oe.data() + u.out_off, &rx, err);
+      if (rs != FGB_OK) return rs;
       w.end();
       ++*count;
     }
@@ -1437,6 +1444,36 @@ fgb_status fgb_host_source_reads(const uint8_t* records, const uint64_t* rec_off
   row_off[srs.size()] = off;
   *n_rows = static_cast<uint32_t>(srs.size());
   if (n_minority) *n_minority = static_cast<uint32_t>(minority);
+  return FGB_OK;
+}
+
+fgb_status fgb_host_simplex_record(const char* read_name_prefix, const char* read_group_id, const char* umi,
+                                   uint8_t read_type, int produce_per_base_tags, const uint8_t* bases,
+                                   const uint8_t* quals, const uint16_t* depths, const uint16_t* errors,
+                                   uint32_t len, const char cell_tag[2], const char* cell,
+                                   const char* const* rx, uint32_t n_rx, uint8_t* out, size_t cap,
+                                   size_t* out_len) {
+  if (!read_name_prefix || !read_group_id || !umi || read_type > 2 || !out || !out_len ||
+      (len && (!bases || !quals || !depths || !errors)) || (n_rx && !rx))
+    return FGB_ERR_INVALID_ARG;
+  fgb_caller c;
+  c.prefix = read_name_prefix;
+  c.rg = read_group_id;
+  c.opt.produce_per_base_tags = produce_per_base_tags ? 1 : 0;
+  UnitMeta m;
+  m.read_type = read_type == 0 ? kFragment : (read_type == 1 ? kR1 : kR2);
+  m.umi = umi;
+  if (cell_tag && cell) { c.opt.cell_tag[0] = cell_tag[0]; c.opt.cell_tag[1] = cell_tag[1]; m.has_cell = true; m.cell = cell; }
+  for (uint32_t i = 0; i < n_rx; ++i) { if (!rx[i]) return FGB_ERR_INVALID_ARG; m.rx.emplace_back(rx[i]); }
+  std::vector<uint8_t> buf;
+  bam::Writer w(&buf);
+  std::string scratch, err;
+  fgb_status st = write_simplex_record(&c, &w, m, len, bases, quals, depths, errors, &scratch, &err);
+  if (st != FGB_OK) return st;
+  w.end();
+  if (buf.size() > cap) return FGB_ERR_INVALID_ARG;
+  std::memcpy(out, buf.data(), buf.size());
+  *out_len = buf.size();
   return FGB_OK;
 }
 

@@ -309,6 +309,17 @@ fgb_status fgb_host_source_reads(const uint8_t* records, const uint64_t* rec_off
                                  uint8_t* out_quals, uint64_t* row_off, uint32_t* orig_idx,
                                  uint32_t* n_rows, uint32_t* n_minority);
 fgb_status fgb_host_consensus_umis(const char* const* umis, uint32_t n, char* out, size_t cap);
+/*   fgb_host_simplex_record  build_consensus_record_into (vanilla_caller.rs:1365-1473): the BAM record
+ *                           (block_size word included) of one simplex consensus read from its four
+ *                           columns.  read_type 0 fragment, 1 R1, 2 R2; cell_tag / cell may be NULL; rx =
+ *                           n_rx NUL-terminated RX values of the source reads.  The record assembly of
+ *                           fgb_caller_flush calls the same code.                                       */
+fgb_status fgb_host_simplex_record(const char* read_name_prefix, const char* read_group_id, const char* umi,
+                                   uint8_t read_type, int produce_per_base_tags, const uint8_t* bases,
+                                   const uint8_t* quals, const uint16_t* depths, const uint16_t* errors,
+                                   uint32_t len, const char cell_tag[2], const char* cell,
+                                   const char* const* rx, uint32_t n_rx, uint8_t* out, size_t cap,
+                                   size_t* out_len);
 int fgb_host_is_fr_pair(const uint8_t* record, size_t len);
 uint32_t fgb_host_num_bases_extending_past_mate(const uint8_t* record, size_t len);
 fgb_status fgb_host_clip_cigar_ops(const uint32_t* ops, uint32_t n_ops, uint32_t clip_amount, int from_start,

@@ -189,3 +189,50 @@ def test_host_helpers_under_asan(tmp_path):
     r = subprocess.run([str(exe), str(path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
     assert r.stdout.startswith("records %d " % len(recs)) and len(recs) > 5000
+
+
+def test_simplex_record_builder_matches_oracle():
+    """fgb_host_simplex_record (the code the flush's record assembly runs) against the oracle's
+    build_consensus_record_into restatement: odd and even lengths, every base code, depths / errors
+    beyond i16, integer tag widths, cell and RX tags."""
+    import fgumi_b200 as fg
+    from tests.bam_builder import make_record
+    lib = fg.lib.load()
+    rng = np.random.default_rng(808)
+    for trial in range(300):
+        L = int(rng.integers(1, 200))
+        bases = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=L))
+        quals = rng.integers(2, 94, size=L).astype(np.uint8)
+        hi = int(rng.choice([5, 200, 40000, 65535]))
+        depths = rng.integers(0, hi + 1, size=L).astype(np.uint16)
+        errors = np.minimum(rng.integers(0, hi + 1, size=L), depths).astype(np.uint16)
+        per_base = bool(rng.random() < 0.7)
+        read_type = int(rng.integers(0, 3))
+        umi = "%d" % int(rng.integers(0, 10 ** int(rng.integers(1, 9))))
+        cell = b"CELL%d" % trial if rng.random() < 0.5 else None
+        n_rx = int(rng.integers(0, 6))
+        rx_true = "".join(rng.choice(list("ACGT"), size=6)) + "-" + "".join(rng.choice(list("ACGT"), size=6))
+        rxs = []
+        for _ in range(n_rx):
+            u = list(rx_true)
+            if rng.random() < 0.3:
+                u[int(rng.integers(0, 6))] = str(rng.choice(list("ACGTN")))
+            rxs.append("".join(u))
+        # oracle: the caller's record builder fed with raw records that carry the RX / cell tags
+        opt = R.VanillaOptions(produce_per_base_tags=per_base, cell_tag=b"CB" if cell else None)
+        o = R.VanillaCallerOracle("fgumi", "grp", opt, None, O.builder_call)
+        raws = [R.Rec(make_record(name=b"r", seq=b"A", quals=[30],
+                                  tags=[(b"RX", "Z", x.encode())] + ([(b"CB", "Z", cell)] if cell else []))) for x in rxs]
+        if cell and not raws:                         # the cell tag is read from the first source read
+            raws = [R.Rec(make_record(name=b"r", seq=b"A", quals=[30], tags=[(b"CB", "Z", cell)]))]
+        want = o._record(umi, ("Fragment", "R1", "R2")[read_type], raws, bases, bytes(quals), list(depths), list(errors))
+        rx_arr = (C.c_char_p * max(n_rx, 1))(*[x.encode() for x in rxs])
+        out = np.zeros(4 * L + 4096, np.uint8)
+        n = C.c_size_t()
+        b8 = np.frombuffer(bases, np.uint8)
+        st = lib.fgb_host_simplex_record(b"fgumi", b"grp", umi.encode(), read_type, int(per_base), b8.ctypes.data,
+                                         quals.ctypes.data, depths.ctypes.data, errors.ctypes.data, L,
+                                         b"CB" if cell else None, cell, rx_arr, n_rx, out.ctypes.data, len(out),
+                                         C.addressof(n))
+        assert st == 0
+        assert bytes(out[:n.value]) == want, trial
