@@ -158,3 +158,40 @@ def test_threaded_add_groups_queues_the_same_batch(mode):
     assert a["units"] == b["units"] and a["n_out"] == b["n_out"] and len(a["units"]) > 100
     assert np.array_equal(a["duplex_jobs"], b["duplex_jobs"]) and np.array_equal(a["codec_jobs"], b["codec_jobs"])
     assert sa == sb
+
+
+@pytest.mark.parametrize("sanitizer", ["address,undefined", "thread"])
+def test_host_caller_under_sanitizers(tmp_path, sanitizer):
+    """caller_host.cpp itself compiled with ASan+UBSan, and with TSan, into tests/native/caller_plan.cpp:
+    planning-only callers of the three modes over random MI groups, one thread against six, two rounds
+    (pooled buffers reused); the harness also compares the two queued batches byte for byte."""
+    import shutil
+    import struct
+    import subprocess
+    import fgumi_b200 as fg
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "fgumi_b200")
+    fg.lib.load()                                   # the engine symbols come from the built library
+    exe = tmp_path / "caller_plan"
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=" + sanitizer, "-fno-sanitize-recover=all",
+                        "-o", str(exe), os.path.join(root, "tests", "native", "caller_plan.cpp"),
+                        os.path.join(libdir, "csrc", "host", "caller_host.cpp"),
+                        os.path.join(libdir, "csrc", "host_tables.cpp"),
+                        "-L" + libdir, "-lfgumi_b200", "-Wl,-rpath," + libdir, "-lpthread"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rng = np.random.default_rng(2)
+    for mode, groups in ((0, random_groups(rng, 150)), (1, random_duplex_groups(rng, 80)), (2, random_codec_groups(rng, 80))):
+        path = tmp_path / ("groups%d.bin" % mode)
+        with open(path, "wb") as f:
+            f.write(struct.pack("<II", mode, len(groups)))
+            for g in groups:
+                f.write(struct.pack("<I", len(g)))
+                for rec in g:
+                    f.write(struct.pack("<I", len(rec)) + bytes(rec))
+        env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", TSAN_OPTIONS="halt_on_error=1")
+        r = subprocess.run([str(exe), str(path), "6"], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0 and r.stdout.startswith("ok units"), (mode, r.returncode, r.stdout[-300:], r.stderr[-3000:])
