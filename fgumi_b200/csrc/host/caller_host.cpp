@@ -1288,6 +1288,10 @@ fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uin
 
 namespace {
 
+// Below this many column bytes the serial merge is cheaper than starting threads for it
+// (FGB_PARALLEL_MERGE_BYTES overrides: tests set it to 0 to exercise the threaded merge on small inputs).
+const size_t kParallelMergeBytes = []() { const char* e = std::getenv("FGB_PARALLEL_MERGE_BYTES"); return e ? static_cast<size_t>(std::strtoull(e, nullptr, 10)) : (size_t{4} << 20); }();
+
 // Appends everything a worker queued to the parent, in order, fixing up the offsets and indices that
 // are relative to the worker's own batch.
 void merge_worker(fgb_caller* c, fgb_caller* w) {
@@ -1325,6 +1329,93 @@ void merge_worker(fgb_caller* c, fgb_caller* w) {
   w->n_duplex_out = 0; w->n_codec_out = 0;
   std::memset(w->stats, 0, sizeof(w->stats));
   w->overlap.stats = overlap::Stats();
+}
+
+// merge_worker for all workers at once, with the big copies on the workers' own threads: the parent's
+// containers are sized once (the byte columns without zero-fill), every worker then writes its slice at
+// a precomputed offset with the same fix-ups merge_worker applies.  Byte-identical to the serial merge.
+void merge_workers_parallel(fgb_caller* c, uint32_t T) {
+  struct Base { size_t bytes, reads, units, metas, jobs, mols, cjobs, cmols; uint64_t out, dout, cout; };
+  std::vector<Base> b(T + 1);
+  b[0] = Base{c->pack.bases.size(), c->pack.reads.size(), c->pack.units.size(), c->metas.size(), c->jobs.size(),
+              c->molecules.size(), c->codec_jobs.size(), c->codec_molecules.size(), c->pack.n_out,
+              c->n_duplex_out, c->n_codec_out};
+  for (uint32_t t = 0; t < T; ++t) {
+    const fgb_caller* w = c->workers[t].get();
+    b[t + 1] = Base{b[t].bytes + w->pack.bases.size(), b[t].reads + w->pack.reads.size(), b[t].units + w->pack.units.size(),
+                    b[t].metas + w->metas.size(), b[t].jobs + w->jobs.size(), b[t].mols + w->molecules.size(),
+                    b[t].cjobs + w->codec_jobs.size(), b[t].cmols + w->codec_molecules.size(),
+                    b[t].out + w->pack.n_out, b[t].dout + w->n_duplex_out, b[t].cout + w->n_codec_out};
+  }
+  c->pack.bases.resize(b[T].bytes);
+  c->pack.quals.resize(b[T].bytes);
+  c->pack.reads.resize(b[T].reads);
+  c->pack.units.resize(b[T].units);
+  c->metas.resize(b[T].metas);
+  c->jobs.resize(b[T].jobs);
+  c->molecules.resize(b[T].mols);
+  c->codec_jobs.resize(b[T].cjobs);
+  c->codec_molecules.resize(b[T].cmols);
+  auto copy_one = [&](uint32_t t) {
+    fgb_caller* w = c->workers[t].get();
+    const Base& o = b[t];
+    if (!w->pack.bases.empty()) {
+      std::memcpy(c->pack.bases.data() + o.bytes, w->pack.bases.data(), w->pack.bases.size());
+      std::memcpy(c->pack.quals.data() + o.bytes, w->pack.quals.data(), w->pack.quals.size());
+    }
+    for (size_t i = 0; i < w->pack.reads.size(); ++i) {
+      const uint64_t d = w->pack.reads[i];
+      c->pack.reads[o.reads + i] = FGB_READ_DESC(FGB_READ_OFF(d) + o.bytes, FGB_READ_LEN(d));
+    }
+    for (size_t i = 0; i < w->pack.units.size(); ++i) {
+      fgb_unit u = w->pack.units[i];
+      u.out_off += o.out; u.read_begin += static_cast<uint32_t>(o.reads);
+      c->pack.units[o.units + i] = u;
+    }
+    for (size_t i = 0; i < w->metas.size(); ++i) c->metas[o.metas + i] = std::move(w->metas[i]);
+    for (size_t i = 0; i < w->jobs.size(); ++i) {
+      fgb_duplex_job j = w->jobs[i];
+      j.unit_a += static_cast<uint32_t>(o.units); j.unit_b += static_cast<uint32_t>(o.units); j.out_off += o.dout;
+      c->jobs[o.jobs + i] = j;
+    }
+    for (size_t i = 0; i < w->molecules.size(); ++i) {
+      Molecule& m = w->molecules[i];
+      for (auto& u : m.unit) if (u != 0xFFFFFFFFu) u += static_cast<uint32_t>(o.units);
+      for (auto& j : m.job) if (j >= 0) j += static_cast<int32_t>(o.jobs);
+      c->molecules[o.mols + i] = std::move(m);
+    }
+    for (size_t i = 0; i < w->codec_jobs.size(); ++i) {
+      fgb_codec_job j = w->codec_jobs[i];
+      j.unit_a += static_cast<uint32_t>(o.units); j.unit_b += static_cast<uint32_t>(o.units); j.out_off += o.cout;
+      c->codec_jobs[o.cjobs + i] = j;
+    }
+    for (size_t i = 0; i < w->codec_molecules.size(); ++i) {
+      CodecMolecule& m = w->codec_molecules[i];
+      m.unit_r1 += static_cast<uint32_t>(o.units); m.unit_r2 += static_cast<uint32_t>(o.units);
+      m.job += static_cast<uint32_t>(o.cjobs);
+      c->codec_molecules[o.cmols + i] = std::move(m);
+    }
+  };
+  std::vector<std::thread> th;
+  for (uint32_t t = 1; t < T; ++t) th.emplace_back(copy_one, t);
+  copy_one(0);
+  for (auto& x : th) x.join();
+  c->pack.n_out = b[T].out;
+  c->n_duplex_out = b[T].dout;
+  c->n_codec_out = b[T].cout;
+  for (uint32_t t = 0; t < T; ++t) {          // counters, then reset the worker like merge_worker does
+    fgb_caller* w = c->workers[t].get();
+    for (int i = 0; i < FGB_NSTATS; ++i) c->stats[i] += w->stats[i];
+    c->overlap.stats.overlapping_bases += w->overlap.stats.overlapping_bases;
+    c->overlap.stats.bases_agreeing += w->overlap.stats.bases_agreeing;
+    c->overlap.stats.bases_disagreeing += w->overlap.stats.bases_disagreeing;
+    c->overlap.stats.bases_corrected += w->overlap.stats.bases_corrected;
+    w->pack.clear(); w->metas.clear(); w->molecules.clear(); w->jobs.clear();
+    w->codec_molecules.clear(); w->codec_jobs.clear();
+    w->n_duplex_out = 0; w->n_codec_out = 0;
+    std::memset(w->stats, 0, sizeof(w->stats));
+    w->overlap.stats = overlap::Stats();
+  }
 }
 
 }  // namespace
@@ -1369,7 +1460,10 @@ fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const ui
       return sts[t];
     }
   }
-  for (uint32_t t = 0; t < T; ++t) merge_worker(c, c->workers[t].get());
+  size_t worker_bytes = 0;
+  for (uint32_t t = 0; t < T; ++t) worker_bytes += c->workers[t]->pack.bases.size();
+  if (worker_bytes >= kParallelMergeBytes) merge_workers_parallel(c, T);
+  else for (uint32_t t = 0; t < T; ++t) merge_worker(c, c->workers[t].get());
   return FGB_OK;
 }
 

@@ -273,9 +273,19 @@ inline bool consensus_umis(const UmiBuilder& builder, const std::vector<std::str
 }
 
 
+// Allocator whose resize() leaves new elements uninitialised (the two byte columns are always
+// overwritten right after they grow; zero-filling 100 MB per batch first would cost as much as the copy).
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInitAlloc<U>; };
+  template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+using ByteColumn = std::vector<uint8_t, DefaultInitAlloc<uint8_t>>;
+
 // The packed SoA batch of include/fgumi_b200.h, grown unit by unit.
 struct Packer {
-  std::vector<uint8_t> bases, quals;
+  ByteColumn bases, quals;
   std::vector<uint64_t> reads;
   std::vector<fgb_unit> units;
   uint64_t n_out = 0;

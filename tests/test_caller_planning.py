@@ -164,7 +164,8 @@ def test_threaded_add_groups_queues_the_same_batch(mode):
 def test_host_caller_under_sanitizers(tmp_path, sanitizer):
     """caller_host.cpp itself compiled with ASan+UBSan, and with TSan, into tests/native/caller_plan.cpp:
     planning-only callers of the three modes over random MI groups, one thread against six, two rounds
-    (pooled buffers reused); the harness also compares the two queued batches byte for byte."""
+    (pooled buffers reused), with the serial and with the threaded merge of the worker batches; the harness
+    also compares the two queued batches byte for byte."""
     import shutil
     import struct
     import subprocess
@@ -192,6 +193,9 @@ def test_host_caller_under_sanitizers(tmp_path, sanitizer):
                 f.write(struct.pack("<I", len(g)))
                 for rec in g:
                     f.write(struct.pack("<I", len(rec)) + bytes(rec))
-        env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", TSAN_OPTIONS="halt_on_error=1")
-        r = subprocess.run([str(exe), str(path), "6"], capture_output=True, text=True, timeout=600, env=env)
-        assert r.returncode == 0 and r.stdout.startswith("ok units"), (mode, r.returncode, r.stdout[-300:], r.stderr[-3000:])
+        for merge_bytes in ("0", str(1 << 40)):     # threaded merge of the worker batches / serial merge
+            env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", TSAN_OPTIONS="halt_on_error=1",
+                       FGB_PARALLEL_MERGE_BYTES=merge_bytes)
+            r = subprocess.run([str(exe), str(path), "6"], capture_output=True, text=True, timeout=600, env=env)
+            assert r.returncode == 0 and r.stdout.startswith("ok units"), (mode, merge_bytes, r.returncode,
+                                                                          r.stdout[-300:], r.stderr[-3000:])
