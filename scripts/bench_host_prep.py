@@ -36,3 +36,21 @@ for overlap in (False, True):
             best = max(best, len(recs) / dt / 1e6)
             c.close()
         print(f"simplex{'+overlap' if overlap else ''} threads {T}: {best:.2f} M input reads/s")
+
+# duplex and CODEC planning throughput (random MI groups of the parity tests, 150 bp)
+from tests.test_caller_parity import random_duplex_groups, random_codec_groups
+for name, gen, mk in (("duplex", random_duplex_groups, lambda: fg.DuplexConsensusCaller("fgumi", "A", min_reads=(1, 1, 0), device=fg.lib.FGB_DEVICE_NONE)),
+                      ("codec", random_codec_groups, lambda: fg.CodecConsensusCaller("fgumi", "A", device=fg.lib.FGB_DEVICE_NONE))):
+    groups = gen(np.random.default_rng(5), 1500, L=150)
+    recs = [r for g in groups for r in g]
+    blob = np.frombuffer(b"".join(recs), np.uint8)
+    off = np.zeros(len(recs) + 1, dtype=np.uint64); off[1:] = np.cumsum([len(r) for r in recs])
+    grp = np.zeros(len(groups) + 1, dtype=np.uint64); grp[1:] = np.cumsum([len(g) for g in groups])
+    best = 0.0
+    for rep in range(3):
+        c = mk()
+        t0 = time.perf_counter()
+        assert c._lib.fgb_caller_add_groups(c._h, blob.ctypes.data, off.ctypes.data, grp.ctypes.data, len(groups)) == 0
+        best = max(best, len(recs) / (time.perf_counter() - t0) / 1e6)
+        c.close()
+    print(f"{name} threads 1: {best:.2f} M input reads/s ({len(recs)} reads, {len(recs) / len(groups):.1f} per group)")

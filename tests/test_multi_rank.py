@@ -85,3 +85,26 @@ def test_two_rank_gloo_shards_match_single_process(tmp_path):
     assert np.array_equal(c0, c1)                    # every rank holds the global sums
     assert c0[0] == full.n_units and c0[1] == int(cl.sum()) and c0[3] == full.n_reads
     assert c0[2] == int((ob[:full.n_out] == ord("N")).sum())
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on host cores only: one JSON line with the contract's keys
+    (impl, metric, value, unit, cpu_baseline, e2e with zero transfer bytes ...) and a positive rate."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FGB_REF_SAMPLE_UNITS="20000")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["warmup"] >= 3 and d["higher_is_better"] is True
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    meta = json.load(open(os.path.join(root, "BASELINE.json")))
+    assert d["metric"].split(" (")[0] in meta["metric"]
