@@ -871,23 +871,30 @@ void codec_filter(fgb_caller* c, std::vector<ClippedInfo>* infos) {
 
 // to_source_read_for_codec_raw, codec_caller.rs:414-469 (no masking, no trimming)
 void codec_source_read(const View& v, const ClippedInfo& ci, SourceRead* sr) {
-  bam::decode_sequence(v, &sr->bases);
-  const uint32_t l = v.l_seq();
-  sr->quals.assign(v.b + v.qual_off(), v.b + v.qual_off() + l);
-  size_t clip = std::min<size_t>(ci.clip_amount, sr->bases.size());
-  if (clip > 0) {
-    if (ci.clip_from_start) {
-      sr->bases.erase(sr->bases.begin(), sr->bases.begin() + clip);
-      sr->quals.erase(sr->quals.begin(), sr->quals.begin() + clip);
-    } else {
-      sr->bases.resize(sr->bases.size() - clip);
-      sr->quals.resize(sr->quals.size() - clip);
+  // to_source_read_for_codec_raw, codec_caller.rs:414-469: decode, drop the virtual clip from one end,
+  // reverse-complement negative-strand reads -- produced in one pass over the kept record positions
+  const size_t l = v.l_seq();
+  const size_t clip = std::min<size_t>(ci.clip_amount, l);
+  const size_t lo = ci.clip_from_start ? clip : 0, hi = ci.clip_from_start ? l : l - clip;
+  const size_t n = hi - lo;
+  sr->bases.resize(n);
+  sr->quals.resize(n);
+  const uint8_t* s = v.b + v.seq_off();
+  const uint8_t* q = v.b + v.qual_off();
+  if (!(v.flags() & bam::kReverse)) {
+    for (size_t i = 0; i < n; ++i) {
+      const size_t j = lo + i;
+      const uint8_t byte = s[j >> 1];
+      sr->bases[i] = static_cast<uint8_t>(prep::kFwd[(j & 1) ? (byte & 0xF) : (byte >> 4)]);
     }
-  }
-  if (v.flags() & bam::kReverse) {
-    std::reverse(sr->bases.begin(), sr->bases.end());
-    for (auto& b : sr->bases) b = bam::complement(b);
-    std::reverse(sr->quals.begin(), sr->quals.end());
+    if (n) std::memcpy(sr->quals.data(), q + lo, n);
+  } else {
+    for (size_t i = 0; i < n; ++i) {
+      const size_t j = hi - 1 - i;
+      const uint8_t byte = s[j >> 1];
+      sr->bases[i] = static_cast<uint8_t>(prep::kRev[(j & 1) ? (byte & 0xF) : (byte >> 4)]);
+    }
+    std::reverse_copy(q + lo, q + hi, sr->quals.begin());
   }
   sr->flags = v.flags();
 }

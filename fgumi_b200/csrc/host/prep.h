@@ -112,10 +112,11 @@ inline size_t quality_trim_point(const std::vector<uint8_t>& q, uint8_t trim_qua
 // masks low qualities, clips and strips trailing Ns in separate sweeps; only the first
 // min(read_len - mate_clip, trim_to) oriented positions can survive, so only those are produced, each
 // straight from its nibble (a second 16-entry table decodes AND complements) and quality byte.
+static const char kFwd[17] = "=ACMGRSVTWYHKDBN";       // sequence.rs nibble codes
+static const char kRev[17] = "=TGMCRSVAWYHKDBN";       // ... complemented (A<->T, C<->G, rest unchanged)
+
 inline bool make_source_read(const PrepOptions& opt, const View& v, uint32_t idx, size_t mate_clip,
                              std::vector<uint32_t>* ops, SourceRead* sr) {
-  static const char kFwd[17] = "=ACMGRSVTWYHKDBN";     // sequence.rs nibble codes
-  static const char kRev[17] = "=TGMCRSVAWYHKDBN";     // ... complemented (A<->T, C<->G, rest unchanged)
   const bool neg = v.flags() & bam::kReverse;
   const uint8_t min_bq = opt.min_input_base_quality;
   const uint32_t read_len = v.l_seq();
@@ -298,16 +299,21 @@ struct Packer {
     u.read_begin = static_cast<uint32_t>(reads.size());
     static thread_local std::vector<size_t> lens;
     lens.clear();
+    size_t total = 0;
+    for (size_t k = 0; k < n; ++k) total += round_up(srs[k].bases.size(), FGB_READ_ALIGN);
+    size_t off = bases.size();
+    bases.resize(off + total);                               // one uninitialised growth per unit ...
+    quals.resize(off + total);
     for (size_t k = 0; k < n; ++k) {
       const SourceRead& sr = srs[k];
-      const size_t off = bases.size();
       const size_t len = sr.bases.size();
-      reads.push_back(FGB_READ_DESC(off, len));
       const size_t padded = round_up(len, FGB_READ_ALIGN);
-      bases.resize(off + padded, 0);                         // value-initialised: the padding is zero
-      quals.resize(off + padded, 0);
+      reads.push_back(FGB_READ_DESC(off, len));
       std::memcpy(bases.data() + off, sr.bases.data(), len);
       std::memcpy(quals.data() + off, sr.quals.data(), len);
+      std::memset(bases.data() + off + len, 0, padded - len); // ... rows and their zero padding written in place
+      std::memset(quals.data() + off + len, 0, padded - len);
+      off += padded;
       lens.push_back(len);
     }
     std::sort(lens.begin(), lens.end(), std::greater<size_t>());
