@@ -557,28 +557,29 @@ fgb_status add_group_duplex(fgb_caller* c, const std::vector<View>& recs) {
     }
   }
   // X = AB-R1 + BA-R2, Y = AB-R2 + BA-R1: pooled CIGAR filter, then split back (:1844-1892)
+  // (the SourceRead buffers live in two pools that persist across groups: Prepared::srs / n)
   auto pooled = [&](const std::vector<uint32_t>& p, const std::vector<uint32_t>& q,
-                    std::vector<uint32_t>* raws, std::vector<SourceRead>* srs) {
-    raws->clear(); srs->clear();
+                    std::vector<uint32_t>* raws, Prepared* pool) {
+    raws->clear(); pool->n = 0;
     raws->insert(raws->end(), p.begin(), p.end());
     raws->insert(raws->end(), q.begin(), q.end());
     for (uint32_t k = 0; k < raws->size(); ++k) {
       const View& v = recs[(*raws)[k]];
       bam::cigar_ops(v, &c->ops);
       size_t clip = bam::num_bases_extending_past_mate(v, c->ops);
-      SourceRead sr;
-      if (make_source_read(c->prep_opt, v, k, clip, &c->ops, &sr)) srs->push_back(std::move(sr));
+      if (pool->n == pool->srs.size()) pool->srs.emplace_back();
+      if (make_source_read(c->prep_opt, v, k, clip, &c->ops, &pool->srs[pool->n])) ++pool->n;
     }
-    filter_by_alignment(srs);   // MinorityAlignment is counted by the ss caller, not the duplex stats
+    pool->n = filter_by_alignment_n(&pool->srs, pool->n);   // MinorityAlignment is counted by the ss caller, not the duplex stats
   };
-  std::vector<uint32_t> x_raws, y_raws;
-  std::vector<SourceRead> fx, fy;
+  std::vector<uint32_t>&x_raws = c->scratch_idx[0], &y_raws = c->scratch_idx[1];
+  Prepared &fx = c->prepared[0], &fy = c->prepared[1];
   pooled(ab_r1, ba_r2, &x_raws, &fx);
   pooled(ab_r2, ba_r1, &y_raws, &fy);
-  std::vector<SourceRead> grp[4];   // AB-R1, AB-R2, BA-R1, BA-R2
+  std::vector<const SourceRead*> grp[4];   // AB-R1, AB-R2, BA-R1, BA-R2
   std::vector<uint32_t> grp_raw[4];
-  for (auto& sr : fx) { int g = (sr.flags & bam::kFirst) ? 0 : 3; grp_raw[g].push_back(x_raws[sr.original_idx]); grp[g].push_back(std::move(sr)); }
-  for (auto& sr : fy) { int g = (sr.flags & bam::kFirst) ? 2 : 1; grp_raw[g].push_back(y_raws[sr.original_idx]); grp[g].push_back(std::move(sr)); }
+  for (size_t i = 0; i < fx.n; ++i) { const SourceRead& sr = fx.srs[i]; int g = (sr.flags & bam::kFirst) ? 0 : 3; grp_raw[g].push_back(x_raws[sr.original_idx]); grp[g].push_back(&sr); }
+  for (size_t i = 0; i < fy.n; ++i) { const SourceRead& sr = fy.srs[i]; int g = (sr.flags & bam::kFirst) ? 2 : 1; grp_raw[g].push_back(y_raws[sr.original_idx]); grp[g].push_back(&sr); }
   const bool have[4] = {!grp[0].empty(), !grp[1].empty(), !grp[2].empty(), !grp[3].empty()};
   // consensus_call succeeds iff the group is non-empty (min_reads = 1); arm selection :1986-2190
   if (have[0] && have[1] && have[2] && have[3]) m.pattern = 0;

@@ -294,18 +294,26 @@ struct Packer {
   uint32_t add_unit(const std::vector<SourceRead>& srs, size_t min_reads) { return add_unit(srs, srs.size(), min_reads); }
   // ... the first `n` elements of `srs`
   uint32_t add_unit(const std::vector<SourceRead>& srs, size_t n, size_t min_reads) {
+    return add_unit_rows(n, min_reads, [&](size_t k) -> const SourceRead& { return srs[k]; });
+  }
+  // ... rows given by pointer (the duplex caller splits one pooled vector into four sub-families)
+  uint32_t add_unit(const std::vector<const SourceRead*>& rows, size_t min_reads) {
+    return add_unit_rows(rows.size(), min_reads, [&](size_t k) -> const SourceRead& { return *rows[k]; });
+  }
+  template <class Row>
+  uint32_t add_unit_rows(size_t n, size_t min_reads, Row row) {
     fgb_unit u;
     u.out_off = n_out;
     u.read_begin = static_cast<uint32_t>(reads.size());
     static thread_local std::vector<size_t> lens;
     lens.clear();
     size_t total = 0;
-    for (size_t k = 0; k < n; ++k) total += round_up(srs[k].bases.size(), FGB_READ_ALIGN);
+    for (size_t k = 0; k < n; ++k) total += round_up(row(k).bases.size(), FGB_READ_ALIGN);
     size_t off = bases.size();
     bases.resize(off + total);                               // one uninitialised growth per unit ...
     quals.resize(off + total);
     for (size_t k = 0; k < n; ++k) {
-      const SourceRead& sr = srs[k];
+      const SourceRead& sr = row(k);
       const size_t len = sr.bases.size();
       const size_t padded = round_up(len, FGB_READ_ALIGN);
       reads.push_back(FGB_READ_DESC(off, len));
