@@ -8,6 +8,6 @@ from .engine import (Engine, PackedBatch, HostColumns, DeviceBatch, DeviceColumn
                      pack_raw_reads, RawColumns, RAW_READ_DTYPE,
                      consensus_length, UNIT_DTYPE, TILE_DTYPE, DUPLEX_JOB_DTYPE, CODEC_JOB_DTYPE)
 from . import lib  # noqa: F401
-from .caller import VanillaUmiConsensusCaller, DuplexConsensusCaller, CodecConsensusCaller, ConsensusOutput, ConsensusFilter, DuplexConsensusFilter, apply_overlapping_consensus  # noqa: F401
+from .caller import VanillaUmiConsensusCaller, DuplexConsensusCaller, CodecConsensusCaller, ConsensusOutput, ConsensusFilter, DuplexConsensusFilter, apply_overlapping_consensus, bgzf_compress, write_bam  # noqa: F401
 
 __version__ = "0.1.0"

@@ -20,6 +20,32 @@ class ConsensusOutput:
         self.data, self.count = data, count
 
 
+def bgzf_compress(data: bytes, level: int = 1, n_threads: int = 1, eof: bool = True) -> bytes:
+    """BGZF members for a byte stream (fgb_bgzf_compress; host code, zlib bound at call time)."""
+    lib = _l.load()
+    cap = lib.fgb_bgzf_bound(len(data))
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t()
+    src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, dtype=np.uint8)
+    st = lib.fgb_bgzf_compress(src.ctypes.data, len(data), level, n_threads, int(eof), out.ctypes.data, cap, C.addressof(n))
+    if st != _l.FGB_OK:
+        raise _l.FgbError(st, "fgb_bgzf_compress")
+    return out[:n.value].tobytes()
+
+
+def write_bam(path: str, sam_header_text: bytes, output: "ConsensusOutput", level: int = 1, n_threads: int = 1):
+    """A BAM file from a caller's ConsensusOutput: header (no reference dictionary -- consensus reads are
+    unmapped) + the record stream as it is, BGZF-compressed, EOF member appended."""
+    lib = _l.load()
+    hdr = np.empty(len(sam_header_text) + 16, dtype=np.uint8)
+    n = C.c_size_t()
+    st = lib.fgb_bam_header(sam_header_text, len(sam_header_text), hdr.ctypes.data, len(hdr), C.addressof(n))
+    if st != _l.FGB_OK:
+        raise _l.FgbError(st, "fgb_bam_header")
+    with open(path, "wb") as f:
+        f.write(bgzf_compress(hdr[:n.value].tobytes() + output.data, level, n_threads, True))
+
+
 class ConsensusFilter:
     """`fgumi filter` options for single-strand consensus reads (commands/filter.rs:100-160):
     -M min_reads, -E max_read_error_rate, -e max_base_error_rate, -N min_base_quality,

@@ -1,0 +1,134 @@
+// BGZF framing of the callers' output stream (the role of the reference's fgumi-bgzf
+// writer, crates/fgumi-bgzf): the `ConsensusOutput` bytes are already BAM records with their
+// block_size words, so a BAM file is  header | records  cut into <= 64 KiB gzip members with the "BC"
+// extra field, followed by the 28-byte EOF member (SAM spec §4.1).  Host code, blocks compressed on
+// several threads.  zlib is bound at call time (dlopen "libz.so.1"), so the engine library itself
+// carries no dependency on it; without zlib the calls fail with FGB_ERR_INVALID_ARG and a message.
+#include <dlfcn.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../../include/fgumi_b200.h"
+
+namespace {
+
+constexpr size_t kBlockInput = 0xFF00;      // uncompressed bytes per member (htslib's choice)
+constexpr size_t kHeader = 18, kFooter = 8;
+const uint8_t kEof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0x00, 0x42, 0x43,
+                          0x02, 0x00, 0x1b, 0x00, 0x03, 0x00, 0, 0, 0, 0, 0, 0, 0, 0};
+
+struct Zlib {
+  void* handle = nullptr;
+  int (*deflateInit2_)(z_streamp, int, int, int, int, int, const char*, int) = nullptr;
+  int (*deflate)(z_streamp, int) = nullptr;
+  int (*deflateEnd)(z_streamp) = nullptr;
+  int (*deflateReset)(z_streamp) = nullptr;
+  uLong (*crc32)(uLong, const Bytef*, uInt) = nullptr;
+  bool ok = false;
+};
+
+const Zlib& zlib() {
+  static Zlib z;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    z.handle = dlopen("libz.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!z.handle) z.handle = dlopen("libz.so", RTLD_NOW | RTLD_LOCAL);
+    if (!z.handle) return;
+    z.deflateInit2_ = reinterpret_cast<decltype(z.deflateInit2_)>(dlsym(z.handle, "deflateInit2_"));
+    z.deflate = reinterpret_cast<decltype(z.deflate)>(dlsym(z.handle, "deflate"));
+    z.deflateEnd = reinterpret_cast<decltype(z.deflateEnd)>(dlsym(z.handle, "deflateEnd"));
+    z.deflateReset = reinterpret_cast<decltype(z.deflateReset)>(dlsym(z.handle, "deflateReset"));
+    z.crc32 = reinterpret_cast<decltype(z.crc32)>(dlsym(z.handle, "crc32"));
+    z.ok = z.deflateInit2_ && z.deflate && z.deflateEnd && z.deflateReset && z.crc32;
+  });
+  return z;
+}
+
+void put16(uint8_t* p, uint32_t v) { p[0] = static_cast<uint8_t>(v); p[1] = static_cast<uint8_t>(v >> 8); }
+void put32(uint8_t* p, uint32_t v) { put16(p, v & 0xFFFFu); put16(p + 2, v >> 16); }
+
+// One member; returns its size, 0 on failure.  `out` holds at least 64 KiB.
+size_t compress_block(const Zlib& z, z_stream* zs, const uint8_t* in, size_t n, uint8_t* out) {
+  if (z.deflateReset(zs) != Z_OK) return 0;
+  zs->next_in = const_cast<Bytef*>(in);
+  zs->avail_in = static_cast<uInt>(n);
+  zs->next_out = out + kHeader;
+  zs->avail_out = static_cast<uInt>(65536 - kHeader - kFooter);
+  if (z.deflate(zs, Z_FINISH) != Z_STREAM_END) return 0;
+  const size_t clen = (65536 - kHeader - kFooter) - zs->avail_out;
+  const size_t total = kHeader + clen + kFooter;
+  static const uint8_t kHead[16] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0x00, 0x42, 0x43, 0x02, 0x00};
+  std::memcpy(out, kHead, 16);
+  put16(out + 16, static_cast<uint32_t>(total - 1));                       // BSIZE
+  put32(out + kHeader + clen, static_cast<uint32_t>(z.crc32(z.crc32(0, nullptr, 0), in, static_cast<uInt>(n))));
+  put32(out + kHeader + clen + 4, static_cast<uint32_t>(n));               // ISIZE
+  return total;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t fgb_bgzf_bound(size_t len) {
+  const size_t blocks = (len + kBlockInput - 1) / kBlockInput;
+  return blocks * 65536 + sizeof(kEof);
+}
+
+fgb_status fgb_bgzf_compress(const uint8_t* data, size_t len, int level, uint32_t n_threads, int append_eof,
+                             uint8_t* out, size_t cap, size_t* out_len) {
+  if ((len && !data) || !out || !out_len || level < 0 || level > 9) return FGB_ERR_INVALID_ARG;
+  const Zlib& z = zlib();
+  if (!z.ok) return FGB_ERR_INVALID_ARG;                                   // zlib not available on this host
+  const size_t blocks = (len + kBlockInput - 1) / kBlockInput;
+  if (cap < blocks * 65536 + (append_eof ? sizeof(kEof) : 0)) return FGB_ERR_INVALID_ARG;   // fgb_bgzf_bound(len)
+  uint32_t T = std::max<uint32_t>(1, std::min<uint32_t>(n_threads ? n_threads : 1, static_cast<uint32_t>(std::max<size_t>(blocks, 1))));
+  std::vector<uint32_t> sizes(blocks, 0);
+  std::vector<int> failed(T, 0);
+  // every block is compressed into its own 64 KiB slot of `out`, then the slots are closed up
+  auto work = [&](uint32_t t) {
+    z_stream zs;
+    std::memset(&zs, 0, sizeof(zs));
+    if (z.deflateInit2_(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY, ZLIB_VERSION, static_cast<int>(sizeof(z_stream))) != Z_OK) { failed[t] = 1; return; }
+    for (size_t b = t; b < blocks; b += T) {
+      const size_t o = b * kBlockInput, n = std::min(kBlockInput, len - o);
+      const size_t s = compress_block(z, &zs, data + o, n, out + b * 65536);
+      if (!s) { failed[t] = 1; break; }
+      sizes[b] = static_cast<uint32_t>(s);
+    }
+    z.deflateEnd(&zs);
+  };
+  std::vector<std::thread> th;
+  for (uint32_t t = 1; t < T; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  for (int f : failed) if (f) return FGB_ERR_INVALID_ARG;
+  size_t w = 0;
+  for (size_t b = 0; b < blocks; ++b) {
+    if (w != b * 65536) std::memmove(out + w, out + b * 65536, sizes[b]);
+    w += sizes[b];
+  }
+  if (append_eof) { std::memcpy(out + w, kEof, sizeof(kEof)); w += sizeof(kEof); }
+  *out_len = w;
+  return FGB_OK;
+}
+
+// "BAM\1" | l_text | text | n_ref = 0: consensus reads are unmapped (ref_id -1), so no reference
+// dictionary is needed for the records to be valid (commands write @HD / @RG / @PG here).
+fgb_status fgb_bam_header(const char* sam_text, size_t l_text, uint8_t* out, size_t cap, size_t* out_len) {
+  if ((l_text && !sam_text) || !out || !out_len || l_text > 0x7FFFFFFFu) return FGB_ERR_INVALID_ARG;
+  const size_t total = 4 + 4 + l_text + 4;
+  if (cap < total) return FGB_ERR_INVALID_ARG;
+  std::memcpy(out, "BAM\1", 4);
+  put32(out + 4, static_cast<uint32_t>(l_text));
+  if (l_text) std::memcpy(out + 8, sam_text, l_text);
+  put32(out + 8 + l_text, 0);
+  *out_len = total;
+  return FGB_OK;
+}
+
+}  // extern "C"

@@ -286,6 +286,17 @@ typedef struct fgb_duplex_filter_params {
   uint8_t require_ss_agreement;         /* --require-single-strand-agreement                       */
   uint8_t reserved[7];
 } fgb_duplex_filter_params;
+/* ---- the on-disk framing of the output (host code) ----------------------------------- */
+/* The ConsensusOutput stream is the record section of a BAM file as it stands.  fgb_bam_header writes
+ * "BAM\1" | l_text | text | n_ref = 0 (consensus reads are unmapped); fgb_bgzf_compress cuts a byte
+ * stream into BGZF members (<= 0xFF00 input bytes each, SAM spec §4.1) on n_threads threads and, when
+ * asked, appends the 28-byte EOF member.  `out` must hold fgb_bgzf_bound(len) bytes.  zlib is looked up
+ * at call time (libz.so.1); if it is missing these calls return FGB_ERR_INVALID_ARG. */
+size_t fgb_bgzf_bound(size_t len);
+fgb_status fgb_bgzf_compress(const uint8_t* data, size_t len, int level, uint32_t n_threads, int append_eof,
+                             uint8_t* out, size_t cap, size_t* out_len);
+fgb_status fgb_bam_header(const char* sam_text, size_t l_text, uint8_t* out, size_t cap, size_t* out_len);
+
 /* ---- raw-record helpers of the host prep (pure host code, no device needed) ------------------ */
 /* The reference exposes these from fgumi-raw-bam; the callers use them for every source read, and
  * they are exported so a host integration -- and the CPU test-suite -- can call the same code.

@@ -1,0 +1,92 @@
+"""BGZF / BAM framing of the callers' output (host code): every member is a valid gzip
+member with the BC extra field and a correct BSIZE, the members decompress to the input, the stream
+ends in the standard EOF member, and a header + ConsensusOutput stream parses back as a BAM file."""
+import ctypes as C
+import gzip
+import os
+import struct
+import sys
+import zlib
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests.bam_builder import make_record       # noqa: E402
+
+EOF_BLOCK = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def bgzf(data: bytes, level=6, threads=1, eof=True) -> bytes:
+    import fgumi_b200 as fg
+    lib = fg.lib.load()
+    cap = lib.fgb_bgzf_bound(len(data))
+    out = np.zeros(cap, np.uint8)
+    n = C.c_size_t()
+    src = np.frombuffer(data, np.uint8) if data else np.zeros(1, np.uint8)
+    assert lib.fgb_bgzf_compress(src.ctypes.data, len(data), level, threads, int(eof), out.ctypes.data, cap, C.addressof(n)) == 0
+    return bytes(out[:n.value])
+
+
+def members(stream: bytes):
+    p, out = 0, []
+    while p < len(stream):
+        assert stream[p:p + 4] == b"\x1f\x8b\x08\x04" and stream[p + 10:p + 16] == b"\x06\x00BC\x02\x00"
+        bsize = struct.unpack_from("<H", stream, p + 16)[0] + 1
+        block = stream[p:p + bsize]
+        crc, isize = struct.unpack_from("<II", block, bsize - 8)
+        raw = zlib.decompress(block[18:bsize - 8], -15)
+        assert len(raw) == isize and zlib.crc32(raw) == crc and isize <= 0xFF00
+        out.append(raw)
+        p += bsize
+    assert p == len(stream)
+    return out
+
+
+@pytest.mark.parametrize("n,level,threads", [(0, 6, 1), (1, 1, 1), (0xFF00, 6, 2), (0xFF00 + 1, 0, 3), (1_000_003, 5, 4)])
+def test_bgzf_members_round_trip(n, level, threads):
+    rng = np.random.default_rng(n + level)
+    data = (rng.integers(0, 4, size=n).astype(np.uint8) * 17 + rng.integers(0, 2, size=n).astype(np.uint8)).tobytes()
+    if n > 100000:                                       # a stretch of incompressible bytes too
+        data = data[:500000] + rng.integers(0, 256, size=200000).astype(np.uint8).tobytes() + data[700000:]
+    s = bgzf(data, level, threads)
+    assert s.endswith(EOF_BLOCK)
+    blocks = members(s)
+    assert blocks[-1] == b"" and b"".join(blocks) == data
+    assert gzip.decompress(s) == data                    # any gzip reader accepts the stream
+    assert bgzf(data, level, 1) == s                     # the thread count does not change the bytes
+    assert not bgzf(data, level, threads, eof=False).endswith(EOF_BLOCK) or n == 0
+
+
+def test_bam_file_from_a_consensus_output_stream():
+    import fgumi_b200 as fg
+    lib = fg.lib.load()
+    recs = [make_record(name=b"fgumi:%d" % i, flags=0x4D if i % 2 == 0 else 0x8D, ref_id=-1, pos=-1, cigar=[],
+                        seq=b"ACGT" * (5 + i % 7), quals=[30] * (4 * (5 + i % 7)), tags=[(b"MI", "Z", b"%d" % (i // 2))])
+            for i in range(5000)]
+    stream = b"".join(struct.pack("<I", len(r)) + r for r in recs)       # what fgb_caller_flush returns
+    text = b"@HD\tVN:1.6\tSO:unsorted\n@RG\tID:A\tSM:s\n"
+    hdr = np.zeros(len(text) + 64, np.uint8)
+    n = C.c_size_t()
+    assert lib.fgb_bam_header(text, len(text), hdr.ctypes.data, len(hdr), C.addressof(n)) == 0
+    bam = bgzf(bytes(hdr[:n.value]) + stream, 6, 3)
+    raw = gzip.decompress(bam)
+    assert raw[:4] == b"BAM\x01"
+    (l_text,) = struct.unpack_from("<i", raw, 4)
+    assert raw[8:8 + l_text] == text and struct.unpack_from("<i", raw, 8 + l_text)[0] == 0
+    p, got = 12 + l_text, []
+    while p < len(raw):
+        (bs,) = struct.unpack_from("<I", raw, p)
+        got.append(raw[p + 4:p + 4 + bs])
+        p += 4 + bs
+    assert got == recs
+
+
+def test_write_bam_helper(tmp_path):
+    import fgumi_b200 as fg
+    recs = [make_record(name=b"c:%d" % i, flags=4, ref_id=-1, pos=-1, cigar=[], seq=b"ACGTN", quals=[30] * 5) for i in range(10)]
+    out = fg.ConsensusOutput(b"".join(struct.pack("<I", len(r)) + r for r in recs), len(recs))
+    path = tmp_path / "c.bam"
+    fg.write_bam(str(path), b"@HD\tVN:1.6\n", out, level=5, n_threads=2)
+    raw = gzip.decompress(open(path, "rb").read())
+    assert raw[:4] == b"BAM\x01" and raw.endswith(recs[-1]) and open(path, "rb").read().endswith(EOF_BLOCK)
