@@ -1514,6 +1514,35 @@ fgb_status fgb_overlap_apply_group(uint8_t* records, const uint64_t* rec_off, ui
   return FGB_OK;
 }
 
+fgb_status fgb_host_group_by_mi(const uint8_t* records, const uint64_t* rec_off, uint64_t n_records,
+                                const char tag[2], int strip_strand_suffix, const char* cell_tag,
+                                uint8_t* keep, uint64_t* group_begin, uint64_t* n_groups) {
+  if (!tag || !keep || !group_begin || !n_groups || (n_records && (!records || !rec_off))) return FGB_ERR_INVALID_ARG;
+  std::string cur, key;
+  bool have = false;
+  uint64_t kept = 0, groups = 0;
+  for (uint64_t i = 0; i < n_records; ++i) {
+    if (rec_off[i + 1] < rec_off[i] || rec_off[i + 1] - rec_off[i] < 32) return FGB_ERR_LAYOUT;
+    const View v(records + rec_off[i], rec_off[i + 1] - rec_off[i]);
+    if (!v.cigar_in_bounds() || v.aux_off() > v.n) return FGB_ERR_LAYOUT;
+    const uint8_t* val; size_t len;
+    if (!bam::find_string_tag(v, tag, &val, &len)) { keep[i] = 0; continue; }
+    keep[i] = 1;
+    key.assign(reinterpret_cast<const char*>(val), len);
+    if (strip_strand_suffix && key.size() >= 2 && key[key.size() - 2] == '/' && (key.back() == 'A' || key.back() == 'B'))
+      key.resize(key.size() - 2);
+    if (cell_tag) {
+      key.push_back('\t');
+      if (bam::find_string_tag(v, cell_tag, &val, &len)) key.append(reinterpret_cast<const char*>(val), len);
+    }
+    if (!have || key != cur) { group_begin[groups++] = kept; cur = key; have = true; }
+    ++kept;
+  }
+  group_begin[groups] = kept;
+  *n_groups = groups;
+  return FGB_OK;
+}
+
 fgb_status fgb_host_source_reads(const uint8_t* records, const uint64_t* rec_off, uint32_t n_records,
                                  uint8_t min_input_base_quality, int trim, uint8_t* out_bases,
                                  uint8_t* out_quals, uint64_t* row_off, uint32_t* orig_idx,

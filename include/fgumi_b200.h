@@ -297,6 +297,17 @@ fgb_status fgb_bgzf_compress(const uint8_t* data, size_t len, int level, uint32_
                              uint8_t* out, size_t cap, size_t* out_len);
 fgb_status fgb_bam_header(const char* sam_text, size_t l_text, uint8_t* out, size_t cap, size_t* out_len);
 
+/* MI grouping of an input record stream (src/lib/mi_group.rs:386-470 MiGroupIterator): consecutive records
+ * with the same key form a group; the key is the value of `tag` (a Z tag), with a trailing "/A" or "/B"
+ * removed when strip_strand_suffix is set (duplex: fgumi-umi lib.rs:355-363 extract_mi_base), followed --
+ * when cell_tag is given -- by a tab and the value of that tag (empty if absent).  Records without `tag`
+ * are skipped: keep[i] = 0.  group_begin[g] .. group_begin[g+1] delimit group g IN THE SEQUENCE OF KEPT
+ * RECORDS (group_begin has room for n_records + 1 entries); when nothing is skipped the table can be handed
+ * to fgb_caller_add_groups as group_rec directly. */
+fgb_status fgb_host_group_by_mi(const uint8_t* records, const uint64_t* rec_off, uint64_t n_records,
+                                const char tag[2], int strip_strand_suffix, const char* cell_tag,
+                                uint8_t* keep, uint64_t* group_begin, uint64_t* n_groups);
+
 /* ---- raw-record helpers of the host prep (pure host code, no device needed) ------------------ */
 /* The reference exposes these from fgumi-raw-bam; the callers use them for every source read, and
  * they are exported so a host integration -- and the CPU test-suite -- can call the same code.

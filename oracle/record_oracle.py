@@ -1743,3 +1743,32 @@ class DuplexFilterOracle(SimplexFilterOracle):
         if filter_duplex_read(Rec(bytes(rec)).aux(), self.th, self.ab, self.ba) != FILTER_PASS:
             return False
         return check_no_call_and_quality(bytes(rec), self.min_mean, self.max_nc)
+
+
+# =================================================================================================
+# MI grouping of the input stream -- src/lib/mi_group.rs:386-470 (MiGroupIterator), fgumi-umi lib.rs:355-363
+# =================================================================================================
+def extract_mi_base(mi: str) -> str:
+    return mi[:-2] if mi.endswith("/A") or mi.endswith("/B") else mi
+
+
+def mi_groups(records: List[bytes], tag: bytes = b"MI", strip_strand_suffix: bool = False,
+              cell_tag: Optional[bytes] = None) -> List[Tuple[str, List[int]]]:
+    """[(key, indices of the group's records)]; records without the tag are skipped."""
+    out: List[Tuple[str, List[int]]] = []
+    for i, b in enumerate(records):
+        r = Rec(b)
+        v = r.find_string(tag)
+        if v is None:
+            continue
+        key = v.decode("utf-8", "replace")
+        if strip_strand_suffix:
+            key = extract_mi_base(key)
+        if cell_tag is not None:
+            cv = r.find_string(cell_tag)
+            key += "\t" + (cv.decode("utf-8", "replace") if cv is not None else "")
+        if out and out[-1][0] == key:
+            out[-1][1].append(i)
+        else:
+            out.append((key, [i]))
+    return out
