@@ -72,6 +72,30 @@ int main(int argc, char** argv) {
     if (fgb_caller_add_groups(many, blob.data(), off.data(), grp.data(), n_groups) != FGB_OK) return 5;
     if (!same_pending(one, many)) { std::printf("MISMATCH\n"); return 6; }
   }
+  // corrupted input: every group once more with a few bytes of one record overwritten (header fields,
+  // CIGAR, sequence, tags) -- any status is fine, an invalid access is not (the sanitizer aborts)
+  {
+    uint64_t lcg = 12345;
+    auto rnd = [&]() { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; return static_cast<uint32_t>(lcg >> 33); };
+    unsigned long long ok = 0, refused = 0;
+    for (uint32_t g = 0; g < n_groups; ++g) {
+      const uint64_t r0 = grp[g], r1 = grp[g + 1];
+      if (r1 == r0) continue;
+      std::vector<uint8_t> copy(blob.begin() + off[r0], blob.begin() + off[r1]);       // exact-size block
+      std::vector<uint64_t> o2(r1 - r0 + 1);
+      for (uint64_t r = r0; r <= r1; ++r) o2[r - r0] = off[r] - off[r0];
+      const uint64_t victim = r0 + rnd() % (r1 - r0);
+      const uint64_t vb = off[victim] - off[r0], vl = off[victim + 1] - off[victim];
+      const int mode = rnd() % 4;
+      if (mode == 0) for (int k = 0; k < 3; ++k) copy[vb + rnd() % vl] = static_cast<uint8_t>(rnd());
+      else if (mode == 1 && vl >= 20) { uint32_t v = rnd() % 70000; std::memcpy(&copy[vb + 16], &v, 4); }      // l_seq
+      else if (mode == 2 && vl >= 14) { uint16_t v = static_cast<uint16_t>(rnd()); std::memcpy(&copy[vb + 12], &v, 2); }   // n_cigar_op
+      else if (vl >= 9) copy[vb + 8] = static_cast<uint8_t>(rnd());                                                  // l_read_name
+      fgb_status st = fgb_caller_add_group(one, copy.data(), o2.data(), static_cast<uint32_t>(r1 - r0));
+      if (st == FGB_OK) ++ok; else ++refused;
+    }
+    std::printf("fuzz: %llu accepted, %llu refused\n", ok, refused);
+  }
   const uint8_t* d; uint64_t n, c;
   if (fgb_caller_flush(one, &d, &n, &c) != FGB_ERR_NO_DEVICE) return 7;     // planning only: loud refusal
   fgb_batch b; fgb_caller_pending(many, &b, nullptr, nullptr, nullptr, nullptr);
