@@ -1608,6 +1608,43 @@ fgb_status fgb_host_simplex_record(const char* read_name_prefix, const char* rea
   return FGB_OK;
 }
 
+fgb_status fgb_host_duplex_record(const char* read_name_prefix, const char* read_group_id, const char* base_mi,
+                                  int first_of_pair, int produce_per_base_tags, const uint8_t* bases,
+                                  const uint8_t* quals, const uint16_t* errors, uint32_t len,
+                                  const fgb_strand_columns* ab, const fgb_strand_columns* ba,
+                                  const char cell_tag[2], const char* cell, const char* const* rx,
+                                  const uint8_t* rx_first, uint32_t n_rx, uint8_t* out, size_t cap, size_t* out_len) {
+  if (!read_name_prefix || !read_group_id || !base_mi || !ab || !out || !out_len ||
+      (len && (!bases || !quals || !errors)) || (n_rx && (!rx || !rx_first)))
+    return FGB_ERR_INVALID_ARG;
+  fgb_caller c;
+  c.prefix = read_name_prefix;
+  c.rg = read_group_id;
+  c.opt.produce_per_base_tags = produce_per_base_tags ? 1 : 0;
+  Molecule m;
+  m.base_mi = base_mi;
+  if (cell_tag && cell) { c.opt.cell_tag[0] = cell_tag[0]; c.opt.cell_tag[1] = cell_tag[1]; m.has_cell = true; m.cell = cell; }
+  auto strand = [](const fgb_strand_columns* s) {
+    Strand r;
+    if (s && s->present) { r.bases = s->bases; r.quals = s->quals; r.depths = s->depths; r.errors = s->errors; r.len = s->len; r.present = true; }
+    return r;
+  };
+  DuplexRead d;
+  d.bases = bases; d.quals = quals; d.errors = errors; d.len = len;
+  d.ab = strand(ab); d.ba = strand(ba);
+  if (!d.ab.present) return FGB_ERR_INVALID_ARG;
+  std::vector<RxSource> src;
+  for (uint32_t i = 0; i < n_rx; ++i) { if (!rx[i]) return FGB_ERR_INVALID_ARG; src.push_back(RxSource{rx[i], rx_first[i] != 0}); }
+  static const std::vector<RxSource> kNone;
+  bam::Writer w(&c.out);
+  fgb_status st = write_duplex_record(&c, &w, d, first_of_pair != 0, m, src, kNone);
+  if (st != FGB_OK) return st;
+  if (c.out.size() > cap) return FGB_ERR_INVALID_ARG;
+  std::memcpy(out, c.out.data(), c.out.size());
+  *out_len = c.out.size();
+  return FGB_OK;
+}
+
 fgb_status fgb_host_consensus_umis(const char* const* umis, uint32_t n, char* out, size_t cap) {
   if ((n && !umis) || !out || !cap) return FGB_ERR_INVALID_ARG;
   static const prep::UmiBuilder builder;

@@ -125,6 +125,11 @@ class FgbDuplexFilterParams(C.Structure):
                 ("require_ss_agreement", C.c_uint8), ("reserved", C.c_uint8 * 7)]
 
 
+class FgbStrandColumns(C.Structure):
+    _fields_ = [("bases", C.c_void_p), ("quals", C.c_void_p), ("depths", C.c_void_p), ("errors", C.c_void_p),
+                ("len", C.c_uint32), ("present", C.c_uint32)]
+
+
 class FgbSubmitOptions(C.Structure):
     _fields_ = [("input_format", C.c_uint32), ("output_format", C.c_uint32), ("raw", C.c_void_p),
                 ("filter", C.c_void_p), ("unit_status", C.c_void_p), ("unit_masked", C.c_void_p)]
@@ -188,7 +193,7 @@ SYMBOLS = (
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
     "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups", "fgb_filter_record", "fgb_host_is_fr_pair",
-    "fgb_host_num_bases_extending_past_mate", "fgb_host_clip_cigar_ops", "fgb_host_read_pos_at_ref_pos", "fgb_host_simplify_cigar", "fgb_host_source_reads", "fgb_host_consensus_umis", "fgb_caller_pending", "fgb_host_simplex_record", "fgb_bgzf_bound", "fgb_bgzf_compress", "fgb_bam_header", "fgb_host_group_by_mi",
+    "fgb_host_num_bases_extending_past_mate", "fgb_host_clip_cigar_ops", "fgb_host_read_pos_at_ref_pos", "fgb_host_simplify_cigar", "fgb_host_source_reads", "fgb_host_consensus_umis", "fgb_caller_pending", "fgb_host_simplex_record", "fgb_bgzf_bound", "fgb_bgzf_compress", "fgb_bam_header", "fgb_host_group_by_mi", "fgb_host_duplex_record",
 )
 
 _lib = None
@@ -315,6 +320,10 @@ def load() -> C.CDLL:
     lib.fgb_host_simplex_record.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint8, C.c_int, vp, vp, vp, vp, u32,
                                             C.c_char_p, C.c_char_p, vp, u32, vp, C.c_size_t, vp]
     lib.fgb_host_simplex_record.restype = C.c_int32
+    lib.fgb_host_duplex_record.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, vp, vp, vp, u32,
+                                           C.POINTER(FgbStrandColumns), C.POINTER(FgbStrandColumns), C.c_char_p,
+                                           C.c_char_p, vp, vp, u32, vp, C.c_size_t, vp]
+    lib.fgb_host_duplex_record.restype = C.c_int32
     lib.fgb_host_group_by_mi.argtypes = [vp, vp, u64, C.c_char_p, C.c_int, C.c_char_p, vp, vp, vp]
     lib.fgb_host_group_by_mi.restype = C.c_int32
     lib.fgb_bgzf_bound.argtypes = [C.c_size_t]

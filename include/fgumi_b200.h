@@ -297,6 +297,23 @@ fgb_status fgb_bgzf_compress(const uint8_t* data, size_t len, int level, uint32_
                              uint8_t* out, size_t cap, size_t* out_len);
 fgb_status fgb_bam_header(const char* sam_text, size_t l_text, uint8_t* out, size_t cap, size_t* out_len);
 
+/*   fgb_host_duplex_record  duplex_read_into (duplex_caller.rs:1048-1285, methylation off): the BAM record
+ *                           (block_size word included) of one duplex consensus read.  `ab` / `ba` are the
+ *                           single-strand consensuses it was built from (ba may be absent: ba_len = 0 and
+ *                           NULL columns with ba_present = 0); rx / rx_first: n_rx RX values of the source
+ *                           reads with their FIRST_SEGMENT flag (RX halves are swapped for reads of the
+ *                           other segment, :1187-1211).  The flush of the duplex caller runs the same code. */
+typedef struct fgb_strand_columns {
+  const uint8_t* bases; const uint8_t* quals; const uint16_t* depths; const uint16_t* errors; uint32_t len;
+  uint32_t present;
+} fgb_strand_columns;
+fgb_status fgb_host_duplex_record(const char* read_name_prefix, const char* read_group_id, const char* base_mi,
+                                  int first_of_pair, int produce_per_base_tags, const uint8_t* bases,
+                                  const uint8_t* quals, const uint16_t* errors, uint32_t len,
+                                  const fgb_strand_columns* ab, const fgb_strand_columns* ba,
+                                  const char cell_tag[2], const char* cell, const char* const* rx,
+                                  const uint8_t* rx_first, uint32_t n_rx, uint8_t* out, size_t cap, size_t* out_len);
+
 /* MI grouping of an input record stream (src/lib/mi_group.rs:386-470 MiGroupIterator): consecutive records
  * with the same key form a group; the key is the value of `tag` (a Z tag), with a trailing "/A" or "/B"
  * removed when strip_strand_suffix is set (duplex: fgumi-umi lib.rs:355-363 extract_mi_base), followed --

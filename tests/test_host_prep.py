@@ -236,3 +236,55 @@ def test_simplex_record_builder_matches_oracle():
                                          C.addressof(n))
         assert st == 0
         assert bytes(out[:n.value]) == want, trial
+
+
+def test_duplex_record_builder_matches_oracle():
+    """fgb_host_duplex_record (the code the duplex flush runs per read) against the oracle's
+    duplex_read_into restatement: both strands / AB only, per-base tags on and off, depths beyond i16,
+    cell tag, RX values from both segments (halves swapped for the other segment)."""
+    import fgumi_b200 as fg
+    from tests.bam_builder import make_record
+    from tests.test_caller_parity import duplex_job_fn
+    from tests.test_record_oracle_kat import vote_fn
+    lib = fg.lib.load()
+    rng = np.random.default_rng(909)
+    keep = []                                            # ctypes arrays must outlive the call
+
+    def strand(n, hi):
+        b = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=n).astype(np.uint8)
+        q = rng.integers(2, 94, size=n).astype(np.uint8)
+        d = rng.integers(0, hi + 1, size=n).astype(np.uint16)
+        e = np.minimum(rng.integers(0, hi + 1, size=n), d).astype(np.uint16)
+        keep.extend([b, q, d, e])
+        sc = fg.lib.FgbStrandColumns(b.ctypes.data, q.ctypes.data, d.ctypes.data, e.ctypes.data, n, 1)
+        return sc, R.SsCons(bytes(b), bytes(q), [int(x) for x in d], [int(x) for x in e], [])
+    for trial in range(200):
+        L = int(rng.integers(1, 180))
+        hi = int(rng.choice([5, 300, 40000]))
+        per_base = bool(rng.random() < 0.7)
+        first = bool(rng.random() < 0.5)
+        ab_c, ab_o = strand(L if rng.random() < 0.8 else L + int(rng.integers(1, 5)), hi)
+        has_ba = rng.random() < 0.75
+        ba_c, ba_o = strand(L, hi) if has_ba else (fg.lib.FgbStrandColumns(None, None, None, None, 0, 0), None)
+        bases = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=L).astype(np.uint8)
+        quals = rng.integers(2, 94, size=L).astype(np.uint8)
+        errors = rng.integers(0, 50, size=L).astype(np.uint16)
+        cell = b"CELL%d" % trial if rng.random() < 0.5 else None
+        n_rx = int(rng.integers(0, 6))
+        rxs = ["".join(rng.choice(list("ACGT"), size=5)) + "-" + "".join(rng.choice(list("ACGT"), size=5)) for _ in range(n_rx)]
+        rx_first = rng.integers(0, 2, size=max(n_rx, 1)).astype(np.uint8)
+        o = R.DuplexCallerOracle("fgumi", "grp", per_base=per_base, cell_tag=b"CB" if cell else None, vote_fn=vote_fn,
+                                 builder_fn=O.builder_call, duplex_job_fn=duplex_job_fn)
+        raws = [R.Rec(make_record(name=b"r", flags=(0x41 if rx_first[i] else 0x81), seq=b"A", quals=[30],
+                                  tags=[(b"RX", "Z", rxs[i].encode())])) for i in range(n_rx)]
+        d = R.DuplexCons(bytes(bases), bytes(quals), [int(x) for x in errors], ab_o, ba_o)
+        want = o._record(d, "R1" if first else "R2", "mol%d" % trial, raws, [], first, cell)
+        rx_arr = (C.c_char_p * max(n_rx, 1))(*[x.encode() for x in rxs])
+        out = np.zeros(16 * L + 8192, np.uint8)
+        n = C.c_size_t()
+        st = lib.fgb_host_duplex_record(b"fgumi", b"grp", b"mol%d" % trial, int(first), int(per_base), bases.ctypes.data,
+                                        quals.ctypes.data, errors.ctypes.data, L, C.byref(ab_c), C.byref(ba_c),
+                                        b"CB" if cell else None, cell, rx_arr, rx_first.ctypes.data, n_rx,
+                                        out.ctypes.data, len(out), C.addressof(n))
+        assert st == 0
+        assert bytes(out[:n.value]) == want, trial
