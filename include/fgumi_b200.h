@@ -531,9 +531,10 @@ typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanill
   uint32_t min_duplex_length;              /* 1 */
   uint32_t reserved1;
   fgb_codec_params codec;                  /* single_strand_qual / outer_bases_* / disagreement gates */
-  /* simplex only: `fgumi simplex | fgumi filter` in one pass (template mode, commands/filter.rs:
-   * 614-697): consensus reads are masked on the device and a template -- the fragment / R1 / R2
-   * reads of one MI -- is emitted only if all of its reads pass. */
+  /* `fgumi simplex | fgumi filter` or `fgumi duplex | fgumi filter` in one pass (template mode,
+   * commands/filter.rs:614-697): a template -- the fragment / R1 / R2 reads of one MI -- is emitted only
+   * if all of its reads pass.  Simplex reads are masked on the device (`filter`), duplex reads on the
+   * assembled records (`duplex_filter`); CODEC mode rejects filter_enabled. */
   uint8_t filter_enabled;
   uint8_t reserved2[3];
   uint32_t n_threads;                      /* host threads for fgb_caller_add_groups and the record
