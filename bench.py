@@ -65,54 +65,82 @@ def recorded_traffic():
 
 
 class ClockSampler:
+    """`nvidia-smi -lms 20` in the background.  It is started before the warm-up (the tool needs a few
+    hundred ms to come up -- longer than a short timed region) and every sample is stamped on arrival;
+    begin() / end() bracket the timed region and the summary uses the samples that fall inside it
+    (all samples under load -- warm-up included -- if none does).  Never raises."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.samples = []
+    def __init__(self, index: int, cmd=None):
+        self.samples = []          # (arrival time, line)
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
+        self.cmd = cmd or ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                           "--format=csv,noheader,nounits", "-lms", "20"]
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "20"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+        try:
+            for line in self.proc.stdout:
+                self.samples.append((time.perf_counter(), line.strip()))
+        except Exception:
+            pass
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
         try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        mhz, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 6:
-                continue
+            if self.t1 is None:
+                self.t1 = time.perf_counter()
+            time.sleep(0.15)
+            self.proc.terminate()
             try:
-                mhz.append(float(f[0])); mx = float(f[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(mhz)}
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+            def parse(rows):
+                mhz, mx, reasons = [], None, set()
+                for _, s in rows:
+                    f = [x.strip() for x in s.split(",")]
+                    if len(f) < 6:
+                        continue
+                    try:
+                        mhz.append(float(f[0])); mx = float(f[1])
+                    except ValueError:
+                        continue
+                    for nm, v in zip(names, f[2:6]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+                return mhz, mx, reasons
+            rows = list(self.samples)
+            inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+            mhz, mx, reasons = parse(inside)
+            window = "timed region"
+            if not mhz:
+                mhz, mx, reasons = parse(rows)
+                window = "warm-up + timed region"
+            return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx,
+                    "reasons": sorted(reasons), "samples": len(mhz), "window": window}
+        except Exception as e:      # the clocks line must never cost the bench line
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling failed: %r" % (e,)]}
 
 
 def cpu_oracle_rate(n_units: int, threads: int, seed: int = 1234, min_seconds: float = 10.0):
@@ -244,15 +272,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clk = ClockSampler(local)
+    clk.start()
     for _ in range(args.warmup):
         step()
     barrier()
     eng.stats_reset()
     launches0 = eng.launch_count()
-    clk = ClockSampler(local)
-    clk.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    clk.begin()
     torch.cuda.nvtx.range_push("fgb_timed")
     ev[0].record()
     for i in range(args.steps):
@@ -268,6 +297,7 @@ def main():
         dist.all_reduce(ctr, op=dist.ReduceOp.SUM)
     barrier()
     torch.cuda.nvtx.range_pop()
+    clk.end()
     clocks = clk.stop()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]

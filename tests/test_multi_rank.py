@@ -108,3 +108,28 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
     meta = json.load(open(os.path.join(root, "BASELINE.json")))
     assert d["metric"].split(" (")[0] in meta["metric"]
+
+
+def test_clock_sampler_uses_the_samples_inside_the_timed_region():
+    """bench.py's clocks line: the sampler runs from before the warm-up, stamps every sample and
+    summarises those inside begin()..end(); a missing tool or garbage output never raises."""
+    import importlib.util
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    fake = [sys.executable, "-u", "-c",
+            "import time\nfor i in range(300):\n print('%d, 1965, Not Active, Not Active, Not Active, %s' % "
+            "(1000 + i, 'Active' if 40 <= i < 45 else 'Not Active'), flush=True); time.sleep(0.01)"]
+    c = b.ClockSampler(0, fake)
+    c.start()
+    time.sleep(0.35)
+    c.begin(); time.sleep(0.25); c.end()
+    r = c.stop()
+    assert r["window"] == "timed region" and 10 <= r["samples"] <= 40 and r["sm_max_mhz"] == 1965.0
+    assert 1020 < r["sm_mhz"] < 1075 and r["reasons"] in ([], ["sw_power_cap"])
+    assert b.ClockSampler(0, ["/nonexistent/tool"]).stop()["sm_mhz"] is None
+    c = b.ClockSampler(0, [sys.executable, "-c", "print('garbage')"])
+    c.start(); c.begin(); c.end()
+    assert c.stop()["sm_mhz"] is None
