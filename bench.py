@@ -96,6 +96,15 @@ class ClockSampler:
         except Exception:
             pass
 
+    def wait_ready(self, timeout: float = 2.0):
+        """Block (bounded) until the tool has delivered its first sample."""
+        try:
+            t_end = time.perf_counter() + timeout
+            while self.proc and not self.samples and time.perf_counter() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
+        except Exception:
+            pass
+
     def begin(self):
         self.t0 = time.perf_counter()
 
@@ -274,6 +283,7 @@ def main():
 
     clk = ClockSampler(local)
     clk.start()
+    clk.wait_ready()
     for _ in range(args.warmup):
         step()
     barrier()

@@ -124,12 +124,22 @@ def test_clock_sampler_uses_the_samples_inside_the_timed_region():
             "(1000 + i, 'Active' if 40 <= i < 45 else 'Not Active'), flush=True); time.sleep(0.01)"]
     c = b.ClockSampler(0, fake)
     c.start()
+    c.wait_ready()
+    assert c.samples
     time.sleep(0.35)
     c.begin(); time.sleep(0.25); c.end()
     r = c.stop()
     assert r["window"] == "timed region" and 10 <= r["samples"] <= 40 and r["sm_max_mhz"] == 1965.0
     assert 1020 < r["sm_mhz"] < 1075 and r["reasons"] in ([], ["sw_power_cap"])
-    assert b.ClockSampler(0, ["/nonexistent/tool"]).stop()["sm_mhz"] is None
+    dead = b.ClockSampler(0, ["/nonexistent/tool"])
+    dead.start(); dead.wait_ready(0.2)
+    assert dead.stop()["sm_mhz"] is None
+    quiet = b.ClockSampler(0, [sys.executable, "-c", "import time; time.sleep(5)"])
+    quiet.start()
+    t0 = time.perf_counter(); quiet.wait_ready(0.3)
+    assert time.perf_counter() - t0 < 1.0
+    quiet.begin(); quiet.end()
+    assert quiet.stop()["sm_mhz"] is None
     c = b.ClockSampler(0, [sys.executable, "-c", "print('garbage')"])
     c.start(); c.begin(); c.end()
     assert c.stop()["sm_mhz"] is None
