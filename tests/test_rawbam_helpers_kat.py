@@ -228,3 +228,58 @@ def test_sequence_packing():                          # sequence.rs:530-570, 684
     for seq in (b"ACGT", b"ACG", b"NNNN", b"T"):
         r = R.Rec(make_record(name=b"rd", flags=0, ref_id=0, pos=0, cigar=[], seq=seq, quals=[0] * len(seq)))
         assert bytes(r.sequence()) == seq
+
+
+def _random_cigar(rng, allow_clips=True):
+    body = []
+    for _ in range(int(rng.integers(1, 7))):
+        k = int(rng.choice([M, M, M, I, D, N_, EQ, X]))
+        if body and body[-1][0] == k:
+            continue
+        body.append((k, int(rng.integers(1, 12))))
+    if not any(k in (M, EQ, X) for k, _ in body):
+        body.append((M, int(rng.integers(1, 12))))
+    lead, trail = [], []
+    if allow_clips:
+        if rng.random() < 0.3:
+            lead.append((H, int(rng.integers(1, 6))))
+        if rng.random() < 0.4:
+            lead.append((S, int(rng.integers(1, 8))))
+        if rng.random() < 0.4:
+            trail.append((S, int(rng.integers(1, 8))))
+        if rng.random() < 0.3:
+            trail.append((H, int(rng.integers(1, 6))))
+    return lead + body + trail
+
+
+def test_product_helpers_match_oracle_on_random_cigars():
+    """Differential check of the product's host helpers against the oracle over a few thousand random
+    CIGARs (clips, indels, skips, =/X) and mate geometries."""
+    import numpy as np
+    rng = np.random.default_rng(515)
+    for trial in range(2500):
+        cig = _random_cigar(rng)
+        o = ops(*cig)
+        qlen = sum(n for k, n in cig if k in (M, I, S, EQ, X))
+        for clip in (0, 1, int(rng.integers(0, qlen + 3)), qlen):
+            for from_start in (True, False):
+                got, want = _Product.clip_cigar_ops(o, clip, from_start), R.clip_cigar_ops(o, clip, from_start)
+                assert (list(got[0]), got[1]) == (list(want[0]), want[1]), (cig, clip, from_start)
+        start = int(rng.integers(1, 500))
+        rlen = R.reference_length(o)
+        for ref_pos in (start - 1, start, start + rlen // 2, start + max(rlen - 1, 0), start + rlen):
+            for last in (False, True):
+                assert _Product.read_pos_at_ref_pos(o, start, ref_pos, last) == R.read_pos_at_ref_pos(o, start, ref_pos, last), (cig, start, ref_pos, last)
+        assert _Product.simplify_cigar(o) == R.simplify_cigar(o)
+        # mate-overlap clip on a record with this CIGAR
+        rev = bool(rng.random() < 0.5)
+        pos = int(rng.integers(50, 400))
+        mpos = pos + int(rng.integers(-60, 60))
+        mate_cig = "".join("%d%s" % (n, "MIDNSHP=X"[k]) for k, n in _random_cigar(rng))
+        flag = P | (REV if rev else MREV) | (F1 if rng.random() < 0.5 else F2)
+        if rng.random() < 0.1:
+            flag ^= MREV                                  # sometimes not an FR pair
+        tlen = int(rng.integers(-300, 300))
+        r = bam(0, pos, flag, o, qlen, 0, mpos, tlen=tlen, mc=mate_cig.encode() if rng.random() < 0.9 else None)
+        assert _Product.is_fr_pair(r) == R.is_fr_pair(r), (cig, pos, mpos, tlen, flag)
+        assert _Product.num_bases_extending_past_mate(r) == R.num_bases_extending_past_mate(r), (cig, mate_cig, pos, mpos, tlen, flag)
