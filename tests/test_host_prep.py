@@ -288,3 +288,47 @@ def test_duplex_record_builder_matches_oracle():
                                         out.ctypes.data, len(out), C.addressof(n))
         assert st == 0
         assert bytes(out[:n.value]) == want, trial
+
+
+def test_source_reads_match_oracle_on_random_records():
+    """make_source_read's fused decode / orientation / mask / clip / strip pass and the CIGAR filter
+    against the oracle on records with random CIGARs (clips, indels, =/X), lengths 1-70 (odd and even:
+    the two-bases-per-byte tables), every base code, missing qualities, both strands, mate overlaps."""
+    from tests.bam_builder import make_record, encode_op
+    from tests.test_rawbam_helpers_kat import _random_cigar, M, I, S, EQ, X, P, F1, F2, REV, MREV
+    rng = np.random.default_rng(6060)
+    codes = np.frombuffer(b"ACGTNRYKMacgtn=", np.uint8)
+    n_rows = n_empty = 0
+    for trial in range(600):
+        min_q, trim = int(rng.choice([2, 10, 25])), bool(rng.random() < 0.4)
+        group = []
+        for k in range(int(rng.integers(1, 9))):
+            cig = _random_cigar(rng)
+            qlen = sum(n for kk, n in cig if kk in (M, I, S, EQ, X))
+            seq = bytes(rng.choice(codes, size=qlen))
+            r = rng.random()
+            quals = [0xFF] * qlen if r < 0.05 else rng.integers(0, 45, size=qlen).tolist()
+            rev = bool(rng.random() < 0.5)
+            pos = int(rng.integers(100, 300))
+            flag = P | (REV if rev else MREV) | (F1 if rng.random() < 0.5 else F2)
+            tags = [(b"MI", "Z", b"1")]
+            if rng.random() < 0.8:
+                tags.append((b"MC", "Z", ("%dM" % int(rng.integers(20, 80))).encode()))
+            group.append(make_record(name=b"r%d" % k, flags=flag, ref_id=0, pos=pos, mate_ref_id=0,
+                                     mate_pos=pos + int(rng.integers(-40, 40)), tlen=int(rng.integers(-200, 200)),
+                                     cigar=[encode_op(kk, n) for kk, n in cig], seq=seq, quals=quals, tags=tags))
+        opt = R.VanillaOptions(min_input_base_quality=min_q, trim=trim)
+        srs = []
+        for i, b in enumerate(group):
+            rec = R.Rec(b)
+            sr = R.create_source_read(rec, i, R.num_bases_extending_past_mate(rec), opt)
+            if sr is not None:
+                srs.append(sr)
+            else:
+                n_empty += 1
+        kept, minority = R.filter_by_alignment(srs)
+        want = [(bytes(s.bases), bytes(s.quals), s.original_idx) for s in kept]
+        got, got_minority = product_source_reads(group, min_q, trim)
+        assert got == want and got_minority == minority, trial
+        n_rows += len(want)
+    assert n_rows > 1000 and n_empty > 20
