@@ -98,6 +98,17 @@ def test_simplex_host_prep_matches_oracle(min_reads, trim, overlap):
     st = c.statistics()
     c.close()
     assert n > 150 and skipped > 0 and st["total_reads"] == sum(len(g) for g in groups)
+    # every simplex decision is taken while planning: all counters already equal the oracle's
+    o = oracle.stats
+    assert st["total_reads"] == o.total_reads and st["consensus_reads"] == o.consensus_reads
+    assert st["filtered_reads"] == o.filtered_reads
+    for name in ("InsufficientReads", "SecondaryOrSupplementary", "ZeroLengthAfterTrimming", "MinorityAlignment",
+                 "OrphanConsensus"):
+        assert st[name] == o.rejections.get(name, 0), name
+    assert o.rejections.get("MinorityAlignment", 0) > 0 and o.rejections.get("OrphanConsensus", 0) > 0
+    if overlap:
+        assert (st["overlapping_bases"], st["overlap_bases_agreeing"], st["overlap_bases_disagreeing"],
+                st["overlap_bases_corrected"]) == ov.stats()
 
 
 @pytest.mark.parametrize("min_reads", [(1, 1, 1), (2, 1, 0), (3, 2, 1)])
@@ -127,8 +138,14 @@ def test_codec_host_prep_matches_oracle():
     c = fg.CodecConsensusCaller("fgumi", "A", device=fg.lib.FGB_DEVICE_NONE)
     n, _ = _compare_groups(fg, c, lambda g: oracle.consensus_reads(g)[1], cap, groups, unordered=True)
     pend = c.pending()
+    st = c.statistics()
     c.close()
     assert n > 100 and len(pend["codec_jobs"]) * 2 == n
+    # the CODEC rejections are all decided while planning (only the disagreement gate waits for the GPU)
+    assert st["total_reads"] == oracle.total_input_reads and st["filtered_reads"] == oracle.reads_filtered
+    for name in ("FragmentRead", "InsufficientReads", "MinorityAlignment", "InsufficientOverlap", "IndelErrorBetweenStrands"):
+        assert st[name] == oracle.rejections.get(name, 0), name
+    assert oracle.rejections.get("InsufficientOverlap", 0) > 0 and oracle.rejections.get("IndelErrorBetweenStrands", 0) > 0
 
 
 @pytest.mark.parametrize("mode", ["simplex", "duplex", "codec"])
