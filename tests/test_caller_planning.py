@@ -216,3 +216,88 @@ def test_host_caller_under_sanitizers(tmp_path, sanitizer):
             r = subprocess.run([str(exe), str(path), "6"], capture_output=True, text=True, timeout=600, env=env)
             assert r.returncode == 0 and "ok units" in r.stdout and "fuzz:" in r.stdout, (mode, merge_bytes, r.returncode,
                                                                           r.stdout[-300:], r.stderr[-3000:])
+
+
+def _oracle_stream(mode, variant, groups):
+    """What the reference pipeline would write for these groups (oracle callers, then the oracle filter)."""
+    from tests.test_codec_oracle_kat import codec_job_fn as cjf
+    if mode == 0:
+        oracle = R.VanillaCallerOracle("fgumi", "A", R.VanillaOptions(min_reads=1, min_consensus_base_quality=2,
+                                                                    cell_tag=b"CB"), vote_fn, O.builder_call)
+        ov = R.OverlappingOracle()
+        stream = bytearray()
+        for g in groups:
+            recs = [bytearray(r) for r in g]
+            ov.apply(recs)
+            stream += oracle.consensus_reads([bytes(r) for r in recs])[0]
+        if variant == 1:
+            flt = R.SimplexFilterOracle(R.FilterThresholds(1, 0.2, 0.3), 10, None, 0.5)
+            return flt.filter_stream(bytes(stream))[0]
+        return bytes(stream)
+    if mode == 1:
+        mr = (1, 1, 1) if variant == 1 else (1, 1, 0)
+        oracle = R.DuplexCallerOracle("fgumi", "A", min_reads=mr, per_base=True, cell_tag=b"CB", vote_fn=vote_fn,
+                                      builder_fn=O.builder_call, duplex_job_fn=duplex_job_fn)
+        stream = b"".join(oracle.consensus_reads(g)[0] for g in groups)
+        if variant == 1:
+            T = R.FilterThresholds
+            flt = R.DuplexFilterOracle(T(3, 0.05, 0.2), T(2, 0.05, 0.1), T(1, 0.1, 0.3), 20, None, 0.3, False)
+            return flt.filter_stream(stream)[0]
+        return stream
+    oracle = R.CodecCallerOracle("codec", "RG1", per_base=True, cell_tag=b"CB", vote_fn=vote_fn, builder_fn=O.builder_call,
+                                 codec_job_fn=cjf)
+    return b"".join(oracle.consensus_reads(g)[0] for g in groups)
+
+
+@pytest.mark.parametrize("sanitizer", ["address,undefined", "thread"])
+def test_callers_end_to_end_on_a_mock_engine(tmp_path, sanitizer):
+    """The WHOLE record-level path of the product's host code -- add_groups, tile planning, submit, record
+    assembly on threads, the simplex and duplex filter stages, two flushes on one caller -- run on the CPU
+    with tests/native/mock_engine.cpp (the oracle's vote / combine behind the engine's entry points) in
+    place of the GPU, under ASan+UBSan and under TSan; the bytes must equal the oracle callers' output."""
+    import shutil
+    import struct
+    import subprocess
+    import fgumi_b200 as fg
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "fgumi_b200")
+    fg.lib.load()
+    exe = tmp_path / "caller_e2e"
+    nat = os.path.join(root, "tests", "native")
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fsanitize=" + sanitizer,
+                        "-fno-sanitize-recover=all", "-o", str(exe), os.path.join(nat, "caller_e2e.cpp"),
+                        os.path.join(nat, "mock_engine.cpp"), os.path.join(libdir, "csrc", "host", "caller_host.cpp"),
+                        os.path.join(libdir, "csrc", "host_tables.cpp"), os.path.join(root, "oracle", "fgumi_oracle.cpp"),
+                        os.path.join(root, "oracle", "oracle_capi.cpp"),
+                        "-L" + libdir, "-lfgumi_b200", "-Wl,-rpath," + libdir, "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rng = np.random.default_rng(4)
+    cases = [(0, random_groups(rng, 120)), (1, random_duplex_groups(rng, 90)), (2, random_codec_groups(rng, 90))]
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", TSAN_OPTIONS="halt_on_error=1")
+    for mode, groups in cases:
+        path = tmp_path / ("groups%d.bin" % mode)
+        with open(path, "wb") as f:
+            f.write(struct.pack("<II", mode, len(groups)))
+            for g in groups:
+                f.write(struct.pack("<I", len(g)))
+                for rec in g:
+                    f.write(struct.pack("<I", len(rec)) + bytes(rec))
+        for variant in ((0, 1) if mode < 2 else (0,)):
+            want = _oracle_stream(mode, variant, groups)
+            assert len(want) > 1000
+            for threads in (1, 4):
+                outp = tmp_path / ("out_%d_%d_%d.bin" % (mode, variant, threads))
+                r = subprocess.run([str(exe), str(path), str(threads), str(variant), str(outp)], capture_output=True,
+                                   text=True, timeout=900, env=env)
+                assert r.returncode == 0 and r.stdout.startswith("ok count"), (mode, variant, threads, r.stdout[-300:], r.stderr[-3000:])
+                got = open(outp, "rb").read()
+                if got != want:
+                    from tests.bam_builder import parse_records
+                    a, b = parse_records(got), parse_records(want)
+                    assert len(a) == len(b), (mode, variant, threads, len(a), len(b))
+                    for i, (x, y) in enumerate(zip(a, b)):
+                        assert x == y, (mode, variant, threads, i, x, y)
+                assert got == want, (mode, variant, threads)
