@@ -384,6 +384,7 @@ fgb_status flush_simplex(fgb_caller* c) {
     std::string err;
     st = assemble(0, U, &c->out, &c->out_count, &err);
     if (st != FGB_OK) c->last_error = err;
+    trace.mark("assemble");
     return st;
   }
   if (c->tbufs.size() < T) c->tbufs.resize(T);

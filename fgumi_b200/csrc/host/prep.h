@@ -48,6 +48,28 @@ struct UmiBuilder {
   // One column of characters, all DNA (A/C/G/T/N, any case); returns the called base.
   uint8_t call(const std::vector<uint8_t>& col) const {
     using namespace hostmath;
+    {
+      // A column whose non-N characters are all the same base calls that base: the only observed base
+      // has ll = n * correct against n * err_alt for the others (a gap of >= 5.7 nats per observation),
+      // so neither the tie rule nor rounding can change the argmax; all-N columns have depth 0 -> 'N'.
+      static const int8_t kIdx[256] = {
+#define FGB_R16(v) v, v, v, v, v, v, v, v, v, v, v, v, v, v, v, v
+          FGB_R16(-1), FGB_R16(-1), FGB_R16(-1), FGB_R16(-1),
+          -1, 0, -1, 1, -1, -1, -1, 2, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+          -1, 0, -1, 1, -1, -1, -1, 2, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+          FGB_R16(-1), FGB_R16(-1), FGB_R16(-1), FGB_R16(-1), FGB_R16(-1), FGB_R16(-1), FGB_R16(-1), FGB_R16(-1)
+#undef FGB_R16
+      };
+      int first = -1;
+      bool uniform = true;
+      for (uint8_t ch : col) {
+        const int idx = kIdx[ch];
+        if (idx < 0) continue;
+        if (first < 0) first = idx;
+        else if (idx != first) { uniform = false; break; }
+      }
+      if (uniform) return first < 0 ? 'N' : static_cast<uint8_t>("ACGT"[first]);
+    }
     double ll[4] = {0, 0, 0, 0}, kc[4] = {0, 0, 0, 0};
     uint32_t obs[4] = {0, 0, 0, 0};
     const double c = t.correct[20], e = t.err_alt[20];
