@@ -19,6 +19,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -80,6 +83,63 @@ struct Prepared {
   std::vector<uint32_t> rec_idx;   // indices (into the group's records) of the surviving reads
 };
 
+// The host threads of one caller, started once: fgb_caller_add_groups and the record assembly of a flush
+// each fan out several times per batch, and starting 64 threads four times per batch costs more than some
+// of the phases they run.  run(n, fn) executes fn(0..n-1): task 0 on the calling thread, task t on helper
+// t, and returns when all have finished.  One caller, one user at a time (a caller is not thread-safe).
+class WorkerPool {
+ public:
+  explicit WorkerPool(uint32_t n_threads) {
+    for (uint32_t i = 1; i < n_threads; ++i) threads_.emplace_back([this, i]() { loop(i); });
+  }
+  ~WorkerPool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; ++gen_; }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  uint32_t size() const { return static_cast<uint32_t>(threads_.size()) + 1; }
+  void run(uint32_t n, const std::function<void(uint32_t)>& fn) {
+    if (n == 0) return;
+    if (n > 1) {
+      { std::lock_guard<std::mutex> l(m_); fn_ = &fn; n_ = n; pending_ = n - 1; ++gen_; }
+      cv_.notify_all();
+    }
+    fn(0);
+    if (n > 1) {
+      std::unique_lock<std::mutex> l(m_);
+      done_.wait(l, [&] { return pending_ == 0; });
+    }
+  }
+
+ private:
+  void loop(uint32_t idx) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(uint32_t)>* fn;
+      uint32_t n;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        fn = fn_; n = n_;
+      }
+      if (idx < n) {
+        (*fn)(idx);
+        std::lock_guard<std::mutex> l(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(uint32_t)>* fn_ = nullptr;
+  uint32_t n_ = 0, pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 }  // namespace
 
 struct fgb_caller {
@@ -107,6 +167,7 @@ struct fgb_caller {
   overlap::Caller overlap{overlap::kAgreeConsensus, overlap::kDisagreeConsensus};   // simplex.rs:384-387
   std::vector<uint8_t> group_copy;       // mutable copy of a group for the overlap pre-pass
   std::vector<std::unique_ptr<fgb_caller>> workers;   // per-thread prep state of fgb_caller_add_groups (no GPU handle)
+  std::unique_ptr<WorkerPool> pool;                    // the threads themselves, started on first use
   // flush scratch that outlives a flush, so steady-state flushes neither page-fault nor zero-fill:
   std::vector<std::vector<uint8_t>> tbufs;   // per-thread record buffers (capacity kept)
   uint8_t* joined = nullptr;                 // concatenated output of a threaded flush (malloc, grow-only)
@@ -117,6 +178,13 @@ struct fgb_caller {
 };
 
 namespace {
+
+// fn(0..T-1) on the caller's pool (T <= options.n_threads).
+void run_parallel(fgb_caller* c, uint32_t T, const std::function<void(uint32_t)>& fn) {
+  if (T <= 1) { if (T) fn(0); return; }
+  if (!c->pool || c->pool->size() < T) c->pool.reset(new WorkerPool(std::max<uint32_t>(T, c->opt.n_threads)));
+  c->pool->run(T, fn);
+}
 
 void reject(fgb_caller* c, int reason, uint64_t n) {
   c->stats[FGB_STAT_FILTERED_READS] += n;
@@ -391,15 +459,10 @@ fgb_status flush_simplex(fgb_caller* c) {
   std::vector<uint64_t> counts(T, 0);
   std::vector<std::string> errs(T);
   std::vector<fgb_status> sts(T, FGB_OK);
-  {
-    std::vector<std::thread> th;
-    for (uint32_t t = 0; t < T; ++t)
-      th.emplace_back([&, t]() {
-        c->tbufs[t].clear();
-        sts[t] = assemble(U * t / T, U * (t + 1) / T, &c->tbufs[t], &counts[t], &errs[t]);
-      });
-    for (auto& x : th) x.join();
-  }
+  run_parallel(c, T, [&](uint32_t t) {
+    c->tbufs[t].clear();
+    sts[t] = assemble(U * t / T, U * (t + 1) / T, &c->tbufs[t], &counts[t], &errs[t]);
+  });
   trace.mark("assemble (threads)");
   size_t total = 0;
   std::vector<size_t> at(T, 0);
@@ -415,12 +478,9 @@ fgb_status flush_simplex(fgb_caller* c) {
     c->joined = static_cast<uint8_t*>(std::malloc(c->joined_cap));
     if (!c->joined) { c->joined_cap = 0; c->last_error = "out of memory"; return FGB_ERR_NOMEM; }
   }
-  {
-    std::vector<std::thread> th;
-    for (uint32_t t = 0; t < T; ++t)
-      th.emplace_back([&, t]() { if (!c->tbufs[t].empty()) std::memcpy(c->joined + at[t], c->tbufs[t].data(), c->tbufs[t].size()); });
-    for (auto& x : th) x.join();
-  }
+  run_parallel(c, T, [&](uint32_t t) {
+    if (!c->tbufs[t].empty()) std::memcpy(c->joined + at[t], c->tbufs[t].data(), c->tbufs[t].size());
+  });
   c->joined_len = total;
   c->out_is_joined = true;
   trace.mark("concatenate");
@@ -449,16 +509,11 @@ fgb_status parallel_records(fgb_caller* c, uint64_t n, uint64_t min_per_thread, 
   if (T <= 1) return body(c, static_cast<uint64_t>(0), n);
   ensure_workers(c, T);
   std::vector<fgb_status> sts(T, FGB_OK);
-  {
-    std::vector<std::thread> th;
-    for (uint32_t t = 0; t < T; ++t)
-      th.emplace_back([&, t]() {
-        fgb_caller* w = c->workers[t].get();
-        w->out.clear(); w->out_count = 0; w->last_error.clear();
-        sts[t] = body(w, n * t / T, n * (t + 1) / T);
-      });
-    for (auto& x : th) x.join();
-  }
+  run_parallel(c, T, [&](uint32_t t) {
+    fgb_caller* w = c->workers[t].get();
+    w->out.clear(); w->out_count = 0; w->last_error.clear();
+    sts[t] = body(w, n * t / T, n * (t + 1) / T);
+  });
   size_t total = 0;
   std::vector<size_t> at(T, 0);
   fgb_status first = FGB_OK;
@@ -477,15 +532,10 @@ fgb_status parallel_records(fgb_caller* c, uint64_t n, uint64_t min_per_thread, 
     c->joined = static_cast<uint8_t*>(std::malloc(c->joined_cap));
     if (!c->joined) { c->joined_cap = 0; c->last_error = "out of memory"; return FGB_ERR_NOMEM; }
   }
-  {
-    std::vector<std::thread> th;
-    for (uint32_t t = 0; t < T; ++t)
-      th.emplace_back([&, t]() {
-        const auto& o = c->workers[t]->out;
-        if (!o.empty()) std::memcpy(c->joined + at[t], o.data(), o.size());
-      });
-    for (auto& x : th) x.join();
-  }
+  run_parallel(c, T, [&](uint32_t t) {
+    const auto& o = c->workers[t]->out;
+    if (!o.empty()) std::memcpy(c->joined + at[t], o.data(), o.size());
+  });
   c->joined_len = total;
   c->out_is_joined = true;
   return FGB_OK;
@@ -1405,10 +1455,7 @@ void merge_workers_parallel(fgb_caller* c, uint32_t T) {
       c->codec_molecules[o.cmols + i] = std::move(m);
     }
   };
-  std::vector<std::thread> th;
-  for (uint32_t t = 1; t < T; ++t) th.emplace_back(copy_one, t);
-  copy_one(0);
-  for (auto& x : th) x.join();
+  run_parallel(c, T, copy_one);
   c->pack.n_out = b[T].out;
   c->n_duplex_out = b[T].dout;
   c->n_codec_out = b[T].cout;
@@ -1458,10 +1505,7 @@ fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const ui
   }
   std::vector<fgb_status> sts(T, FGB_OK);
   std::vector<uint64_t> bad(T, 0);
-  std::vector<std::thread> th;
-  for (uint32_t t = 0; t < T; ++t)
-    th.emplace_back([&, t]() { sts[t] = run(c->workers[t].get(), cut[t], cut[t + 1], &bad[t]); });
-  for (auto& x : th) x.join();
+  run_parallel(c, T, [&](uint32_t t) { sts[t] = run(c->workers[t].get(), cut[t], cut[t + 1], &bad[t]); });
   for (uint32_t t = 0; t < T; ++t) {
     if (sts[t] != FGB_OK) {           // report the first failing group in input order; drop the partial work
       c->last_error = c->workers[t]->last_error;

@@ -72,6 +72,9 @@ int main(int argc, char** argv) {
     if (fgb_caller_add_groups(many, blob.data(), off.data(), grp.data(), n_groups) != FGB_OK) return 5;
     if (!same_pending(one, many)) { std::printf("MISMATCH\n"); return 6; }
   }
+  // the caller's thread pool: many fan-outs in a row on one caller (each add_groups call is one or two)
+  for (int rep = 0; rep < 60; ++rep)
+    if (fgb_caller_add_groups(many, blob.data(), off.data(), grp.data(), n_groups) != FGB_OK) return 8;
   // corrupted input: every group once more with a few bytes of one record overwritten (header fields,
   // CIGAR, sequence, tags) -- any status is fine, an invalid access is not (the sanitizer aborts)
   {
