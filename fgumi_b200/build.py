@@ -29,7 +29,7 @@ def _check_vote_kernel(ptxas_log: str) -> None:
     10-warp blocks: 65536 / (2 * 10 * 32) = 102 -> 96), and a spill in the item loop costs ~10 %.
     ptxas' choice is sensitive to small source changes, so say so loudly when it drifts."""
     import re
-    m = re.search(r"Function properties for \S*vote_kernel\S*\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores"
+    m = re.search(r"Function properties for \S*vote_kernelE\S*\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores"
                   r".*\n.*Used (\d+) registers", ptxas_log)
     if not m:
         return

@@ -17,8 +17,10 @@
 #include "fgb_config.h"
 #include "filter_kernel.cuh"
 #include "host_tables.h"
+#include "planner.h"
 #include "unpack_kernels.cuh"
 #include "vote_kernel.cuh"
+#include "vote_kernel_w.cuh"
 
 using namespace fgb;
 
@@ -50,6 +52,14 @@ struct Slot {
   uint8_t* qraw = nullptr;
   fgb_raw_read* rawreads = nullptr;
   uint64_t cap_seq4 = 0, cap_qraw = 0, cap_rawreads = 0;
+  uint8_t* recblob = nullptr;    // RECORDS transfer blob (fgb_submit_ex, FGB_IN_RECORDS)
+  uint64_t cap_recblob = 0;
+  // strand-combine jobs of fgb_submit_ex (duplex / CODEC callers)
+  fgb_duplex_job* djobs = nullptr; uint64_t cap_djobs = 0;
+  fgb_codec_job* cjobs = nullptr; uint64_t cap_cjobs = 0;
+  uint8_t* c_base = nullptr; uint8_t* c_qual = nullptr; uint16_t* c_depth = nullptr; uint16_t* c_errors = nullptr;
+  uint64_t cap_cout = 0;
+  uint8_t* c_status = nullptr; uint32_t* c_dis = nullptr; uint32_t* c_dup = nullptr; uint64_t cap_cjobout = 0;
   uint64_t* reads = nullptr;
   fgb_unit* units = nullptr;
   fgb_tile* tiles = nullptr;
@@ -79,6 +89,7 @@ struct fgb_handle {
   double emax_rate = -1.0;                          // the max_base_error_rate d_emax was built for
   int n_slots = 2;                                  // FGB_SUBMIT_SLOTS (1..kSlots)
   uint64_t chunk_bytes = kChunkColumnBytes;         // FGB_SUBMIT_CHUNK_MB
+  int vote_variant = 0;                             // FGB_VOTE_KERNEL: 0 = vote_kernel (thread per item), 1 = vote_kernel_w (warp per unit)
 };
 
 namespace {
@@ -121,7 +132,8 @@ fgb_status launch_vote(fgb_handle* h, const fgb_batch& b, const fgb_columns& out
   a.fast_qual = h->host_tables.fast_qual;
   uint64_t max_grid = static_cast<uint64_t>(h->sm_count) * 2u;
   unsigned grid = static_cast<unsigned>(std::min<uint64_t>(b.n_tiles, max_grid));
-  vote_kernel<<<grid, kThreads, sizeof(VoteSmem), stream>>>(a);
+  if (h->vote_variant == 0) vote_kernel<<<grid, kThreads, sizeof(VoteSmem), stream>>>(a);
+  else vote_kernel_w<<<grid, kThreads, sizeof(VoteSmemW), stream>>>(a);
   h->launches++;
   FGB_CUDA(h, cudaGetLastError());
   return FGB_OK;
@@ -180,6 +192,7 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   if (const char* e = std::getenv("FGB_SUBMIT_SLOTS")) h->n_slots = std::max(1, std::min(kSlots, std::atoi(e)));
   if (const char* e = std::getenv("FGB_SUBMIT_CHUNK_MB"))
     h->chunk_bytes = static_cast<uint64_t>(std::max(1, std::atoi(e))) << 20;
+  if (const char* e = std::getenv("FGB_VOTE_KERNEL")) h->vote_variant = std::atoi(e) ? 1 : 0;
   h->params = *params;
   build_host_tables(params->error_rate_pre_umi, params->error_rate_post_umi, &h->host_tables);
 
@@ -204,6 +217,7 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   dt.g2fix = h->host_tables.g2fix;
   dt.nmax2 = h->host_tables.nmax2;
   std::memcpy(dt.pair_q, h->host_tables.pair_q, sizeof(dt.pair_q));
+  std::memcpy(dt.sumt, h->host_tables.sumt, sizeof(dt.sumt));
   if ((e = cudaMemcpy(h->d_tables, &dt, sizeof(dt), cudaMemcpyHostToDevice)) != cudaSuccess)
     return fail(e, "cudaMemcpy tables");
   if ((e = cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * FGB_NCOUNTERS)) != cudaSuccess)
@@ -211,6 +225,9 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   if ((e = cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(sizeof(VoteSmem)))) != cudaSuccess)
     return fail(e, "cudaFuncSetAttribute(vote_kernel)");
+  if ((e = cudaFuncSetAttribute(vote_kernel_w, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(VoteSmemW)))) != cudaSuccess)
+    return fail(e, "cudaFuncSetAttribute(vote_kernel_w)");
   for (int s = 0; s < kSlots; ++s)
     if ((e = cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking)) != cudaSuccess)
       return fail(e, "cudaStreamCreate");
@@ -224,7 +241,7 @@ void fgb_destroy(fgb_handle* h) {
   for (int s = 0; s < kSlots; ++s) {
     Slot& sl = h->slots[s];
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
-    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.unit_status); cudaFree(sl.unit_masked); cudaFree(sl.out_depth8); cudaFree(sl.out_errors8); cudaFree(sl.seq4); cudaFree(sl.qraw); cudaFree(sl.rawreads); cudaFree(sl.reads); cudaFree(sl.units);
+    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.unit_status); cudaFree(sl.unit_masked); cudaFree(sl.out_depth8); cudaFree(sl.out_errors8); cudaFree(sl.seq4); cudaFree(sl.qraw); cudaFree(sl.rawreads); cudaFree(sl.recblob); cudaFree(sl.djobs); cudaFree(sl.cjobs); cudaFree(sl.c_base); cudaFree(sl.c_qual); cudaFree(sl.c_depth); cudaFree(sl.c_errors); cudaFree(sl.c_status); cudaFree(sl.c_dis); cudaFree(sl.c_dup); cudaFree(sl.reads); cudaFree(sl.units);
     cudaFree(sl.tiles); cudaFree(sl.out_base); cudaFree(sl.out_qual); cudaFree(sl.out_depth);
     cudaFree(sl.out_errors);
   }
@@ -280,105 +297,13 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
                           uint64_t n_reads, fgb_tile* out, uint64_t cap, uint64_t* n_tiles) {
   if (!n_tiles || (n_units && (!units || (!reads && n_reads)))) return FGB_ERR_INVALID_ARG;
   if (n_units >= 0xFFFFFFFFull || n_reads >= 0xFFFFFFFFull) return FGB_ERR_INVALID_ARG;
-  uint64_t nt = 0;
-  fgb_tile cur{};
-  bool open = false;
-  uint64_t cur_end = 0;   // exclusive end (unaligned) of the open tile's byte range
-  uint64_t prev_read_end = 0;
-
-  uint32_t cur_items = 0;     // 8-position items per unit if uniform so far, 0xFFFFFFFF = mixed
-  bool regular = false;       // open tile: equal-length rows packed at stride round_up(len, 8)
-  uint32_t reg_len = 0;
-  uint64_t reg_next = 0;      // where the next row must start for the tile to stay regular
-  uint32_t max_reads_in_unit = 0;
-  auto emit = [&]() {
-    cur.byte_len = static_cast<uint32_t>(((cur_end + 15u) & ~15ull) - cur.byte_begin);
-    if (cur.flags & kTileFlagDirect) { cur.byte_len = 0; }
-    const bool uniform = cur_items != 0xFFFFFFFFu && cur_items >= 2 && cur_items <= 4096;   // umulhi exactness
-    if (uniform) cur.flags |= cur_items << 8;    // hint: unit index = item / cur_items
-    if (!(cur.flags & kTileFlagDirect)) {
-      if (regular && uniform && cur.n_reads > 0) {
-        cur.flags |= kTileFlagRegular;
-        if (FGB_READ_OFF(reads[cur.read_begin]) != cur.byte_begin) cur.flags |= kTileFlagSkew8;
-      }
-      if (max_reads_in_unit <= 64) cur.flags |= kTileFlagShallow;
-    }
-    if (out && nt < cap) out[nt] = cur;
-    ++nt;
-    open = false;
-  };
-
   if (n_units && units[0].read_begin != 0) return FGB_ERR_LAYOUT;
-  for (uint64_t u = 0; u < n_units; ++u) {
-    const fgb_unit& un = units[u];
-    const fgb_unit& nx = units[u + 1];
-    if (nx.read_begin < un.read_begin || nx.read_begin > n_reads) return FGB_ERR_LAYOUT;
-    uint32_t nr = nx.read_begin - un.read_begin;
-    if (un.out_off % FGB_OUT_ALIGN) return FGB_ERR_LAYOUT;
-    if (nx.out_off != un.out_off + ((static_cast<uint64_t>(un.cons_len) + (FGB_OUT_ALIGN - 1u)) & ~static_cast<uint64_t>(FGB_OUT_ALIGN - 1u)))
-      return FGB_ERR_LAYOUT;   // output rows are dense, each padded to FGB_OUT_ALIGN
-    if (un.cons_len > FGB_MAX_READ_LEN) return FGB_ERR_UNIT_TOO_LARGE;
-    if (nr == 0 && un.cons_len != 0) return FGB_ERR_LAYOUT;
-    if (nr > 0xFFFFu) return FGB_ERR_UNIT_TOO_LARGE;   // u16 observation counters, base_builder.rs:236
-    uint64_t ub = 0, ue = 0;   // byte range of this unit
-    uint32_t maxlen = 0;
-    for (uint32_t r = un.read_begin; r < nx.read_begin; ++r) {
-      uint64_t off = FGB_READ_OFF(reads[r]);
-      uint32_t len = FGB_READ_LEN(reads[r]);
-      if (off % FGB_READ_ALIGN || len == 0) return FGB_ERR_LAYOUT;   // no empty rows
-      if (off < prev_read_end) return FGB_ERR_LAYOUT;   // rows ascend and do not overlap
-      prev_read_end = off + len;
-      if (r == un.read_begin) ub = off;
-      ue = off + len;
-      maxlen = std::max(maxlen, len);
-    }
-    if (un.cons_len > maxlen) return FGB_ERR_LAYOUT;
-    if (nr == 0) { ub = ue = open ? cur_end : prev_read_end; }
-
-    // Can the unit join the open tile?
-    if (open) {
-      uint64_t span = ((ue + 15u) & ~15ull) - cur.byte_begin;
-      uint32_t skew = cur.read_begin & 1u;
-      bool fits = !(cur.flags & kTileFlagDirect) && span <= kTileCapBytes &&
-                  cur.n_units + 1 <= kTileMaxUnits &&
-                  cur.n_reads + nr + skew <= kTileMaxReads;
-      if (!fits) emit();
-    }
-    if (!open) {
-      std::memset(&cur, 0, sizeof(cur));
-      cur.byte_begin = ub & ~15ull;
-      cur.unit_begin = static_cast<uint32_t>(u);
-      cur.read_begin = un.read_begin;
-      cur_end = ub;
-      open = true;
-      uint64_t span = ((ue + 15u) & ~15ull) - cur.byte_begin;
-      if (span > kTileCapBytes || nr + (cur.read_begin & 1u) > kTileMaxReads)
-        cur.flags |= kTileFlagDirect;   // oversize unit: kernel votes it straight from HBM
-      regular = nr > 0;
-      reg_len = nr ? FGB_READ_LEN(reads[un.read_begin]) : 0;
-      reg_next = ub;
-      max_reads_in_unit = 0;
-    }
-    if (regular) {   // still regular with this unit?
-      const uint64_t stride = (static_cast<uint64_t>(reg_len) + 7u) & ~7ull;
-      if (nr == 0 || un.cons_len != reg_len) regular = false;
-      for (uint32_t r = un.read_begin; regular && r < nx.read_begin; ++r) {
-        if (FGB_READ_LEN(reads[r]) != reg_len || FGB_READ_OFF(reads[r]) != reg_next) regular = false;
-        reg_next += stride;
-      }
-    }
-    max_reads_in_unit = std::max(max_reads_in_unit, nr);
-    {
-      uint32_t items = (un.cons_len + 7u) >> 3;
-      if (cur.n_units == 0) cur_items = items;
-      else if (cur_items != items) cur_items = 0xFFFFFFFFu;
-    }
-    cur.n_units += 1;
-    cur.n_reads += nr;
-    cur_end = std::max(cur_end, ue);
-    if (cur.flags & kTileFlagDirect) emit();
-  }
-  if (open) emit();
+  uint64_t nt = 0, prev_read_end = 0;
+  fgb_status st = plan_tiles_range(units, 0, n_units, reads, n_reads, &prev_read_end, [&](const fgb_tile& t) {
+    if (out && nt < cap) out[nt] = t;
+    ++nt;
+  });
+  if (st != FGB_OK) return st;
   *n_tiles = nt;
   return FGB_OK;
 }
@@ -405,7 +330,7 @@ void fgb_host_free(void* p) { if (p) cudaFreeHost(p); }
 }  // extern "C"
 
 namespace {
-enum class HostFormat { kBytes, kPack8, kBam4 };
+enum class HostFormat { kBytes, kPack8, kBam4, kRecords };
 
 // emax[d] = largest error count e (<= d) with (double)e / (double)d <= rate, i.e. exactly the
 // positions mask_bases keeps (`errors / depth > max_base_error_rate` masks, filter.rs:681-684).
@@ -475,6 +400,22 @@ fgb_status launch_unpack_bam4(fgb_handle* h, Bam4Args a, cudaStream_t s) {
   return FGB_OK;
 }
 
+fgb_status launch_unpack_records(fgb_handle* h, RecordsArgs a, cudaStream_t s) {
+  const uint64_t n = a.read_end - a.read_begin;
+  if (n == 0) return FGB_OK;
+  if (!h->d_bad) {
+    FGB_CUDA(h, cudaMalloc(&h->d_bad, sizeof(uint32_t)));
+    FGB_CUDA(h, cudaMemset(h->d_bad, 0, sizeof(uint32_t)));
+  }
+  a.bad = h->d_bad;
+  h->bam4_pending = true;
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + 7u) / 8u, static_cast<uint64_t>(h->sm_count) * 16u));
+  unpack_records_kernel<<<grid, 256, 0, s>>>(a);
+  h->launches++;
+  FGB_CUDA(h, cudaGetLastError());
+  return FGB_OK;
+}
+
 fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* out, HostFormat fmt,
                        const fgb_raw_columns* raw = nullptr, bool narrow = false,
                        const fgb_submit_options* opt = nullptr) {
@@ -501,8 +442,22 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
   if (fmt == HostFormat::kBam4 &&
       (!in->reads || !raw || !raw->seq4 || !raw->quals_raw || !raw->raw_reads))
     return FGB_ERR_INVALID_ARG;
+  const fgb_record_columns* rec = opt ? opt->records : nullptr;
+  if (fmt == HostFormat::kRecords && (!in->reads || !rec || !rec->records || !rec->raw_reads))
+    return FGB_ERR_INVALID_ARG;
+  const uint64_t n_djobs = opt ? opt->n_duplex_jobs : 0, n_cjobs = opt ? opt->n_codec_jobs : 0;
+  if (n_djobs && (!opt->duplex_jobs || !opt->duplex_out || !opt->duplex_out->base || !opt->duplex_out->qual ||
+                  !opt->duplex_out->errors))
+    return FGB_ERR_INVALID_ARG;
+  if (n_cjobs && (!opt->codec_jobs || !opt->codec_out || !opt->codec_params || !opt->codec_out->status ||
+                  !opt->codec_out->cols.base || !opt->codec_out->cols.qual || !opt->codec_out->cols.depth ||
+                  !opt->codec_out->cols.errors))
+    return FGB_ERR_INVALID_ARG;
+  if ((n_djobs || n_cjobs) && (narrow || fp || (n_djobs && n_cjobs))) return FGB_ERR_INVALID_ARG;
+  const bool one_piece = n_djobs || n_cjobs;   // a molecule's units are voted before its combine job runs
 
-  if (!in->tiles || !in->units || !in->reads || (fmt != HostFormat::kBam4 && !in->bases) ||
+  const bool rows_on_device = fmt == HostFormat::kBam4 || fmt == HostFormat::kRecords;
+  if (!in->tiles || !in->units || !in->reads || (!rows_on_device && !in->bases) ||
       (fmt == HostFormat::kBytes && !in->quals) || !out->base ||
       !out->qual || !out->depth || !out->errors)
     return FGB_ERR_INVALID_ARG;
@@ -539,7 +494,7 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
         end = tl.byte_begin + tl.byte_len;
       }
       end = std::max(end, byte1);
-      if (t1 > t0 && end - byte0 > h->chunk_bytes) break;
+      if (!one_piece && t1 > t0 && end - byte0 > h->chunk_bytes) break;
       byte1 = end;
       ++t1;
     }
@@ -601,6 +556,8 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
                                     cudaMemcpyHostToDevice, s));
       }
       // (the layout descriptors are uploaded below; the unpack launch follows them)
+    } else if (fmt == HostFormat::kRecords) {
+      // (the record blob of this chunk's reads is uploaded below, once the read range is known)
     } else {
       FGB_CUDA(h, cudaMemcpyAsync(sl.bases, in->bases + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
       FGB_CUDA(h, cudaMemcpyAsync(sl.quals, in->quals + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
@@ -641,7 +598,86 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
       ua.min_q = raw->min_input_base_quality;
       if ((st = launch_unpack_bam4(h, ua, s)) != FGB_OK) return st;
     }
+    if (fmt == HostFormat::kRecords && r1 > first.read_begin) {
+      // blob byte range this chunk's reads touch (a group's records are contiguous, its reads are not in
+      // record order), padded for the kernel's aligned window loads
+      const uint64_t rf = first.read_begin;
+      uint64_t lo = ~0ull, hi = 0;
+      for (uint64_t r = rf; r < r1; ++r) {
+        const fgb_raw_read& rr = rec->raw_reads[r];
+        const uint64_t e = rr.src_off + ((static_cast<uint64_t>(rr.raw_len) + 1u) >> 1) + rr.raw_len;
+        lo = std::min(lo, rr.src_off);
+        hi = std::max(hi, e);
+      }
+      if (hi > rec->n_bytes || lo > hi) {
+        h->last_error = "fgb_record_columns: a sequence / quality span runs past the record blob";
+        return FGB_ERR_LAYOUT;
+      }
+      const uint64_t a0 = (lo > 64u ? lo - 64u : 0u) & ~63ull;
+      const uint64_t a1 = std::min(rec->n_bytes, hi + 32u);
+      if ((st = ensure(h, &sl.recblob, &sl.cap_recblob, a1 - a0 + 128)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.rawreads, &sl.cap_rawreads, r1 - rf + 1)) != FGB_OK) return st;
+      FGB_CUDA(h, cudaMemcpyAsync(sl.recblob, rec->records + a0, a1 - a0, cudaMemcpyHostToDevice, s));
+      FGB_CUDA(h, cudaMemcpyAsync(sl.rawreads, rec->raw_reads + rf, (r1 - rf) * sizeof(fgb_raw_read),
+                                  cudaMemcpyHostToDevice, s));
+      RecordsArgs ua;
+      ua.records = sl.recblob - a0;
+      ua.raw_reads = sl.rawreads - rf;
+      ua.reads = db.reads;
+      ua.bases = const_cast<uint8_t*>(db.bases);
+      ua.quals = const_cast<uint8_t*>(db.quals);
+      ua.read_begin = rf; ua.read_end = r1;
+      ua.rec_lo = a0;                            // resident bytes [a0, a1) plus allocation slack behind them;
+      ua.rec_hi = a1 + 96u;                      // the kernel wants 16 bytes either side of every span (lo - a0 >= 16:
+      ua.min_q = rec->min_input_base_quality;    // a sequence field starts >= 33 bytes into its record)
+      if ((st = launch_unpack_records(h, ua, s)) != FGB_OK) return st;
+    }
     if ((st = launch_vote(h, db, dc, s)) != FGB_OK) return st;
+    if (n_djobs) {
+      const fgb_duplex_out* ho = opt->duplex_out;
+      const uint64_t nd = opt->n_duplex_out;
+      uint64_t c1 = sl.cap_cout, c2 = sl.cap_cout;
+      if ((st = ensure(h, &sl.djobs, &sl.cap_djobs, n_djobs)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.c_base, &sl.cap_cout, nd + 16)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.c_qual, &c1, nd + 16)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.c_errors, &c2, nd + 16)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.c_status, &sl.cap_cjobout, n_djobs + 16)) != FGB_OK) return st;
+      FGB_CUDA(h, cudaMemcpyAsync(sl.djobs, opt->duplex_jobs, n_djobs * sizeof(fgb_duplex_job), cudaMemcpyHostToDevice, s));
+      fgb_batch jb = db;                       // absolute unit indices: same biased pointers as the vote
+      fgb_duplex_out dout{sl.c_base, sl.c_qual, sl.c_errors, sl.c_status};
+      if ((st = fgb_duplex_combine_device(h, &jb, &dc, sl.djobs, n_djobs, &dout, s)) != FGB_OK) return st;
+      FGB_CUDA(h, cudaMemcpyAsync(ho->base, sl.c_base, nd, cudaMemcpyDeviceToHost, s));
+      FGB_CUDA(h, cudaMemcpyAsync(ho->qual, sl.c_qual, nd, cudaMemcpyDeviceToHost, s));
+      FGB_CUDA(h, cudaMemcpyAsync(ho->errors, sl.c_errors, nd * 2, cudaMemcpyDeviceToHost, s));
+      if (ho->status) FGB_CUDA(h, cudaMemcpyAsync(ho->status, sl.c_status, n_djobs, cudaMemcpyDeviceToHost, s));
+    }
+    if (n_cjobs) {
+      const fgb_codec_out* ho = opt->codec_out;
+      const uint64_t nc = opt->n_codec_out;
+      uint64_t c1 = sl.cap_cout, c2 = sl.cap_cout, c3 = sl.cap_cout;
+      if ((st = ensure(h, &sl.cjobs, &sl.cap_cjobs, n_cjobs)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.c_base, &sl.cap_cout, nc + 16)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.c_qual, &c1, nc + 16)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.c_depth, &c2, nc + 16)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.c_errors, &c3, nc + 16)) != FGB_OK) return st;
+      uint64_t cj1 = sl.cap_cjobout, cj2 = sl.cap_cjobout;
+      if ((st = ensure(h, &sl.c_status, &sl.cap_cjobout, n_cjobs + 16)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.c_dis, &cj1, n_cjobs + 16)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.c_dup, &cj2, n_cjobs + 16)) != FGB_OK) return st;
+      FGB_CUDA(h, cudaMemcpyAsync(sl.cjobs, opt->codec_jobs, n_cjobs * sizeof(fgb_codec_job), cudaMemcpyHostToDevice, s));
+      fgb_batch jb = db;
+      fgb_codec_out cout{};
+      cout.cols = fgb_columns{sl.c_base, sl.c_qual, sl.c_depth, sl.c_errors};
+      cout.status = sl.c_status; cout.disagreements = sl.c_dis; cout.duplex_bases = sl.c_dup;
+      if ((st = fgb_codec_combine_device(h, &jb, &dc, sl.cjobs, n_cjobs, opt->codec_params, &cout, s)) != FGB_OK) return st;
+      FGB_CUDA(h, cudaMemcpyAsync(ho->cols.base, sl.c_base, nc, cudaMemcpyDeviceToHost, s));
+      FGB_CUDA(h, cudaMemcpyAsync(ho->cols.qual, sl.c_qual, nc, cudaMemcpyDeviceToHost, s));
+      FGB_CUDA(h, cudaMemcpyAsync(ho->cols.depth, sl.c_depth, nc * 2, cudaMemcpyDeviceToHost, s));
+      FGB_CUDA(h, cudaMemcpyAsync(ho->cols.errors, sl.c_errors, nc * 2, cudaMemcpyDeviceToHost, s));
+      FGB_CUDA(h, cudaMemcpyAsync(ho->status, sl.c_status, n_cjobs, cudaMemcpyDeviceToHost, s));
+      if (ho->disagreements) FGB_CUDA(h, cudaMemcpyAsync(ho->disagreements, sl.c_dis, n_cjobs * 4, cudaMemcpyDeviceToHost, s));
+      if (ho->duplex_bases) FGB_CUDA(h, cudaMemcpyAsync(ho->duplex_bases, sl.c_dup, n_cjobs * 4, cudaMemcpyDeviceToHost, s));
+    }
     if (fp) {
       if ((st = ensure(h, &sl.unit_status, &sl.cap_ustat, u1 - u0 + 16)) != FGB_OK) return st;
       if (opt->unit_masked && (st = ensure(h, &sl.unit_masked, &sl.cap_umask, u1 - u0 + 16)) != FGB_OK) return st;
@@ -701,9 +737,10 @@ fgb_status fgb_submit_bam4(fgb_handle* h, const fgb_batch* in, const fgb_raw_col
 
 fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out,
                          const fgb_submit_options* opt) {
-  if (!opt || opt->input_format > FGB_IN_BAM4 || opt->output_format > FGB_OUT_U8) return FGB_ERR_INVALID_ARG;
+  if (!opt || opt->input_format > FGB_IN_RECORDS || opt->output_format > FGB_OUT_U8) return FGB_ERR_INVALID_ARG;
   const HostFormat f = opt->input_format == FGB_IN_PACK8 ? HostFormat::kPack8
-                       : opt->input_format == FGB_IN_BAM4 ? HostFormat::kBam4 : HostFormat::kBytes;
+                       : opt->input_format == FGB_IN_BAM4 ? HostFormat::kBam4
+                       : opt->input_format == FGB_IN_RECORDS ? HostFormat::kRecords : HostFormat::kBytes;
   return submit_impl(h, in, out, f, opt->raw, opt->output_format == FGB_OUT_U8, opt);
 }
 
@@ -733,6 +770,20 @@ fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_
   ua.raw_lo = 0; ua.raw_hi = raw->n_raw;
   ua.min_q = raw->min_input_base_quality;
   return launch_unpack_bam4(h, ua, static_cast<cudaStream_t>(stream));
+}
+
+fgb_status fgb_unpack_records_device(fgb_handle* h, const fgb_batch* in, const fgb_record_columns* rec,
+                                     uint8_t* bases, uint8_t* quals, void* stream) {
+  if (!h || !in || !rec || !bases || !quals || !in->reads || !rec->records || !rec->raw_reads)
+    return FGB_ERR_INVALID_ARG;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  RecordsArgs ua;
+  ua.records = rec->records; ua.raw_reads = rec->raw_reads;
+  ua.reads = in->reads; ua.bases = bases; ua.quals = quals;
+  ua.read_begin = 0; ua.read_end = in->n_reads;
+  ua.rec_lo = 0; ua.rec_hi = rec->n_bytes;          // the caller pads the device blob by 16 bytes at the end
+  ua.min_q = rec->min_input_base_quality;
+  return launch_unpack_records(h, ua, static_cast<cudaStream_t>(stream));
 }
 
 fgb_status fgb_pack8_encode(const uint8_t* bases, const uint8_t* quals, uint64_t n, uint8_t* out) {

@@ -122,6 +122,52 @@ inline bool find_string_tag(const View& v, const char tag[2], const uint8_t** va
   return false;
 }
 
+// One walk over the aux area for several Z tags at once: want[k] = the two tag letters, val[k] / len[k]
+// receive the value of the FIRST occurrence (val[k] = nullptr when absent or not a string), exactly what
+// find_string_tag would return for each tag on its own.
+inline void find_string_tags(const View& v, const char (*want)[2], int n_want, const uint8_t** val, size_t* len) {
+  for (int k = 0; k < n_want; ++k) { val[k] = nullptr; len[k] = 0; }
+  size_t off = v.aux_off();
+  if (off > v.n) return;
+  const uint8_t* a = v.b + off;
+  const size_t an = v.n - off;
+  auto fixed = [](uint8_t t) -> size_t {
+    switch (t) {
+      case 'A': case 'c': case 'C': return 1;
+      case 's': case 'S': return 2;
+      case 'i': case 'I': case 'f': return 4;
+      default: return 0;
+    }
+  };
+  uint32_t seen = 0;                   // tags already met (found or found-with-another-type): first occurrence wins
+  int left = n_want;
+  size_t p = 0;
+  while (p + 3 <= an && left > 0) {
+    const uint8_t vt = a[p + 2];
+    int hit = -1;
+    for (int k = 0; k < n_want; ++k)
+      if (!(seen & (1u << k)) && a[p] == static_cast<uint8_t>(want[k][0]) && a[p + 1] == static_cast<uint8_t>(want[k][1])) { hit = k; break; }
+    size_t size = fixed(vt);
+    if (!size) {
+      if (vt == 'Z' || vt == 'H') {
+        const void* z = std::memchr(a + p + 3, 0, an - (p + 3));
+        if (!z) return;
+        size = static_cast<const uint8_t*>(z) - (a + p + 3) + 1;
+        if (hit >= 0 && vt == 'Z') { val[hit] = a + p + 3; len[hit] = size - 1; }
+      } else if (vt == 'B') {
+        if (an - (p + 3) < 5) return;
+        const size_t es = fixed(a[p + 3]);
+        if (!es) return;
+        size = 5 + static_cast<size_t>(rd32(a + p + 4)) * es;
+      } else {
+        return;
+      }
+    }
+    if (hit >= 0) { seen |= 1u << hit; --left; }
+    p += 3 + size;
+  }
+}
+
 // ---- mate-overlap clip (overlap.rs) ----
 inline int32_t parse_int(const char* s, size_t a, size_t b) {
   if (a >= b) return 0;
@@ -228,10 +274,19 @@ inline size_t read_pos_at_ref(const std::vector<uint32_t>& ops, int32_t start1, 
   return 0;
 }
 
+// num_bases_extending_past_mate_raw (overlap.rs:65-136) with the MC value already located
+// (mc == nullptr: the record has no MC string tag).
+inline size_t num_bases_extending_past_mate_mc(const View& v, const std::vector<uint32_t>& ops, const uint8_t* mc, size_t mcn);
+
 inline size_t num_bases_extending_past_mate(const View& v, const std::vector<uint32_t>& ops) {
   if (!is_fr_pair(v, ops)) return 0;
   const uint8_t* mc; size_t mcn;
   if (!find_string_tag(v, "MC", &mc, &mcn)) return 0;
+  return num_bases_extending_past_mate_mc(v, ops, mc, mcn);
+}
+
+inline size_t num_bases_extending_past_mate_mc(const View& v, const std::vector<uint32_t>& ops, const uint8_t* mc, size_t mcn) {
+  if (!mc || !is_fr_pair(v, ops)) return 0;
   const char* mcs = reinterpret_cast<const char*>(mc);
   if (!valid_utf8(mc, mcn)) return 0;                            // std::str::from_utf8 fails
   const int32_t this_pos = v.pos() + 1, m_pos = v.mate_pos() + 1;

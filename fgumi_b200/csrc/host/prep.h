@@ -137,17 +137,22 @@ inline size_t quality_trim_point(const std::vector<uint8_t>& q, uint8_t trim_qua
 static const char kFwd[17] = "=ACMGRSVTWYHKDBN";       // sequence.rs nibble codes
 static const char kRev[17] = "=TGMCRSVAWYHKDBN";       // ... complemented (A<->T, C<->G, rest unchanged)
 
-inline bool make_source_read(const PrepOptions& opt, const View& v, uint32_t idx, size_t mate_clip,
-                             std::vector<uint32_t>* ops, SourceRead* sr) {
+// The per-read decisions of create_source_read (vanilla_caller.rs:863-955) WITHOUT decoding the read: the
+// length of the SourceRead row after the mate-overlap clip, the optional quality trim and the trailing-N
+// strip, 0 when the read yields no source read (no bases, truncated record, missing qualities, fully
+// clipped / trimmed / masked).  A position is 'N' when its quality is below min_input_base_quality or its
+// base nibble is 15; only those are stripped from the end (:918-927).  The record-level callers use it on
+// its own when the device builds the rows (FGB_IN_RECORDS).
+inline uint32_t plan_read_len(const PrepOptions& opt, const View& v, size_t mate_clip) {
   const bool neg = v.flags() & bam::kReverse;
   const uint8_t min_bq = opt.min_input_base_quality;
   const uint32_t read_len = v.l_seq();
-  if (read_len == 0 || v.qual_off() + read_len > v.n) return false;
+  if (read_len == 0 || v.qual_off() + read_len > v.n) return 0;
   const uint8_t* s = v.b + v.seq_off();
   const uint8_t* q = v.b + v.qual_off();
   bool all_ff = true;
   for (uint32_t i = 0; i < read_len; ++i) if (q[i] != 0xFF) { all_ff = false; break; }
-  if (all_ff) return false;                                  // missing qualities
+  if (all_ff) return 0;                                      // missing qualities
   size_t trim_to = read_len;
   if (opt.trim) {                                            // needs the oriented qualities as a whole
     static thread_local std::vector<uint8_t> oriented;
@@ -156,8 +161,24 @@ inline bool make_source_read(const PrepOptions& opt, const View& v, uint32_t idx
     trim_to = quality_trim_point(oriented, min_bq);
   }
   const size_t clip_position = read_len > mate_clip ? read_len - mate_clip : 0;
-  const size_t bound = std::min(clip_position, trim_to);
-  if (bound == 0) return false;                              // nothing can survive (final_len == 0 below)
+  size_t final_len = std::min(clip_position, trim_to);
+  while (final_len > 0) {                                    // oriented position i is record position j
+    const size_t i = final_len - 1, j = neg ? read_len - 1 - i : i;
+    const uint32_t nib = (j & 1) ? (s[j >> 1] & 15u) : (s[j >> 1] >> 4);
+    if (q[j] < min_bq || nib == 15u) --final_len; else break;
+  }
+  return static_cast<uint32_t>(final_len);
+}
+
+inline bool make_source_read(const PrepOptions& opt, const View& v, uint32_t idx, size_t mate_clip,
+                             std::vector<uint32_t>* ops, SourceRead* sr) {
+  const size_t bound = plan_read_len(opt, v, mate_clip);     // only these oriented positions survive
+  if (bound == 0) return false;
+  const bool neg = v.flags() & bam::kReverse;
+  const uint8_t min_bq = opt.min_input_base_quality;
+  const uint32_t read_len = v.l_seq();
+  const uint8_t* s = v.b + v.seq_off();
+  const uint8_t* q = v.b + v.qual_off();
   sr->bases.resize(bound);
   sr->quals.resize(bound);
   uint8_t* __restrict ob = sr->bases.data();
@@ -194,11 +215,7 @@ inline bool make_source_read(const PrepOptions& opt, const View& v, uint32_t idx
     ob[i] = low ? static_cast<uint8_t>('N') : ob[i];
     oq[i] = low ? static_cast<uint8_t>(2) : oq[i];
   }
-  size_t final_len = bound;
-  while (final_len > 0 && ob[final_len - 1] == 'N') --final_len;
-  if (final_len == 0) return false;
-  sr->bases.resize(final_len);
-  sr->quals.resize(final_len);
+  const size_t final_len = bound;                            // the trailing Ns are already gone
   bam::cigar_ops(v, ops);
   bam::simplify_cigar(*ops, &sr->cigar);
   if (neg) std::reverse(sr->cigar.begin(), sr->cigar.end());

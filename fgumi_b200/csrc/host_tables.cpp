@@ -137,6 +137,41 @@ void build_host_tables(unsigned pre, unsigned post, HostTables* t) {
     }
     t->qt[n] = static_cast<uint8_t>(qt);
   }
+
+  // Sum-of-qualities thresholds (vote_kernel_w.cuh): f[k][s] = the smallest sum of D over k qualities in
+  // 1..63 that add up to s, by dynamic programming; sumt[n] = the smallest t such that EVERY such multiset
+  // with sum >= t clears the same threshold the per-read minimum test uses.  Exact over the table values;
+  // the 1e-6 in the threshold covers the rounding of the reference's Kahan sums as above.
+  for (unsigned n = 0; n < 8; ++n) t->sumt[n] = 0xFFFF;
+  {
+    const double inf = std::numeric_limits<double>::infinity();
+    constexpr int kQ = 63, kN = 4;
+    static thread_local double f[kN + 1][kQ * kN + 1];
+    bool usable = finite_ok;
+    for (int q = 1; q <= kQ; ++q) if (t->dfix[q] == INT32_MIN) usable = false;
+    for (int k = 0; k <= kN; ++k) for (int s = 0; s <= kQ * kN; ++s) f[k][s] = inf;
+    f[0][0] = 0.0;
+    for (int k = 1; k <= kN; ++k)
+      for (int s = k; s <= kQ * k; ++s) {
+        double best = inf;
+        for (int q = 1; q <= kQ && q <= s; ++q) {
+          const double prev = f[k - 1][s - q];
+          if (prev == inf) continue;
+          const double v = prev + (t->correct[q] - t->err_alt[q]);
+          if (v < best) best = v;
+        }
+        f[k][s] = best;
+      }
+    for (int n = 3; usable && n <= kN; ++n) {
+      double thr = 23.0 + 1e-6;
+      if (static_cast<uint32_t>(n) <= t->nmax2 && t->g2 < thr) thr = t->g2;
+      int tmin = kQ * n + 1;                       // scan down while every sum above still clears thr
+      for (int s = kQ * n; s >= n; --s) {
+        if (f[n][s] > thr) tmin = s; else break;
+      }
+      if (tmin <= 255 && tmin <= kQ * n) t->sumt[n] = static_cast<uint16_t>(tmin);
+    }
+  }
 }
 
 }  // namespace fgb

@@ -20,6 +20,10 @@ struct HostTables {
   // sequence yields for two observations of one base with qualities q1 then q2 (before the
   // min-consensus-quality threshold); 255 = not tabulated (quality 0), evaluate literally.
   uint8_t pair_q[94 * 94];
+  // Sum-of-qualities proof of the fast path for shallow pileups: n unanimous observations whose qualities
+  // all lie in 1..63 and sum to at least sumt[n] have sum D[q_i] > min(23, G2); 0xFFFF = not available.
+  // Used for n = 3, 4 (the byte-wise sums of the kernel stay below 256).
+  uint16_t sumt[8];
 };
 
 void build_host_tables(unsigned pre, unsigned post, HostTables* t);

@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include "../../include/fgumi_b200.h"
+#include "swar.cuh"
 
 namespace fgb {
 
@@ -123,6 +124,136 @@ __global__ void __launch_bounds__(256) narrow_u16_kernel(const uint4* __restrict
     const uint4 d = depth16[i], e = errors16[i];
     depth8[i] = make_uint2(__byte_perm(d.x, d.y, 0x6420u), __byte_perm(d.z, d.w, 0x6420u));
     errors8[i] = make_uint2(__byte_perm(e.x, e.y, 0x6420u), __byte_perm(e.z, e.w, 0x6420u));
+  }
+}
+
+}  // namespace fgb
+
+// ---- RECORDS: source-read rows built straight from the BAM records' own bytes -----------------------
+// The host ships the records as they are (one DMA from pinned memory, no per-base host work) plus one
+// fgb_raw_read per surviving read: src_off = byte offset of the record's packed-sequence field inside the
+// record blob, raw_len = l_seq (the quality bytes start (l_seq + 1) / 2 bytes after src_off, raw-bam
+// fields.rs:6-23), flags bit 0 = reverse strand.  The kernel does the per-base part of create_source_read
+// (vanilla_caller.rs:893-916) and of to_source_read_for_codec_raw (codec_caller.rs:414-469): row position p
+// comes from raw base p (forward) or l_seq - 1 - p complemented (reverse), `q < min_q` turns the
+// observation into (N, Q2); the row length (after mate clip / quality trim / trailing-N strip) is the
+// host's decision and comes with the layout descriptor.
+namespace fgb {
+
+struct RecordsArgs {
+  const uint8_t* records;          // biased: blob byte i lives at records[i]
+  const fgb_raw_read* raw_reads;   // biased: raw_reads[r] for absolute read index r
+  const uint64_t* reads;           // layout descriptors (off << 16 | row length), biased the same way
+  uint8_t* bases;                  // byte columns being built (biased by the chunk origin)
+  uint8_t* quals;
+  uint64_t read_begin, read_end;   // absolute read range of this launch
+  uint64_t rec_lo, rec_hi;         // blob byte range [rec_lo, rec_hi) that is resident (bounds check)
+  uint32_t* bad;                   // set to 1 when a record span breaks the layout rules (read is skipped)
+  uint32_t min_q;                  // min_input_base_quality (0 = no masking)
+};
+
+// 4 bytes at an arbitrary address through two aligned loads (the blob allocation is padded on both sides)
+__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  return __funnelshift_r(__ldg(w), __ldg(w + 1), static_cast<uint32_t>(a & 3u) * 8u);
+}
+__device__ __forceinline__ uint2 ldg_u64_unaligned(const uint8_t* p) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
+  const uint32_t sh = static_cast<uint32_t>(a & 3u) * 8u;
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+  return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+
+// One warp per read, lanes over the row's 8-position words.
+__global__ void __launch_bounds__(256) unpack_records_kernel(const RecordsArgs a) {
+  // pair tables: one packed byte (two bases) -> two ASCII bytes; forward: (high, low) nibble in row order,
+  // reverse: (low, high) nibble complemented ("=ACMGRSVTWYHKDBN", A<->T, C<->G; fgumi-dna dna.rs:30-60)
+  __shared__ uint16_t lut_f[256], lut_r[256];
+  {
+    const char* f = "=ACMGRSVTWYHKDBN";
+    const char* c = "=TGMCRSVAWYHKDBN";
+    const uint32_t b = threadIdx.x;
+    lut_f[b] = static_cast<uint16_t>(static_cast<uint8_t>(f[b >> 4]) | (static_cast<uint32_t>(static_cast<uint8_t>(f[b & 15])) << 8));
+    lut_r[b] = static_cast<uint16_t>(static_cast<uint8_t>(c[b & 15]) | (static_cast<uint32_t>(static_cast<uint8_t>(c[b >> 4])) << 8));
+  }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+  const uint32_t tq = a.min_q > 127u ? 127u : a.min_q;     // SWAR compare handles thresholds up to 127
+  const bool wide_q = a.min_q > 127u;
+  for (uint64_t r = a.read_begin + ((static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+       r < a.read_end; r += warps) {
+    const fgb_raw_read rr = a.raw_reads[r];
+    const uint64_t d = a.reads[r];
+    const uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
+    const uint64_t off = d >> 16;
+    const uint32_t L = rr.raw_len;
+    const uint64_t qoff = rr.src_off + ((static_cast<uint64_t>(L) + 1u) >> 1);
+    // the sequence and quality fields must lie inside the resident blob (with 16 bytes of slack either side
+    // for the aligned window loads), and the row cannot be longer than the record's sequence
+    if (rr.src_off < a.rec_lo + 16u || qoff + L + 16u > a.rec_hi || len > L) {
+      if (lane == 0) atomicOr(a.bad, 1u);
+      continue;
+    }
+    const bool rev = rr.flags & 1u;
+    const uint8_t* seq = a.records + rr.src_off;
+    const uint8_t* qual = a.records + qoff;
+    const uint32_t words = (len + 7u) >> 3;
+    for (uint32_t w = lane; w < words; w += 32u) {
+      uint32_t x, q_lo, q_hi;
+      if (!rev) {
+        x = ldg_u32_unaligned(seq + 4u * w);                 // byte k = bases 8w+2k (high nibble), 8w+2k+1
+        const uint2 q = ldg_u64_unaligned(qual + 8u * w);
+        q_lo = q.x; q_hi = q.y;
+      } else {
+        // row positions 8w+j <- raw bases e-j, e = L-1-8w: the eight nibbles ending at raw index e, as a
+        // 32-bit value whose nibble j (from the least significant end) is raw base e-j
+        const int32_t e = static_cast<int32_t>(L) - 1 - static_cast<int32_t>(8u * w);
+        const int32_t first = e - 7;                          // may be negative on the row's last word
+        const int32_t s0 = first >> 1;                        // floor: byte holding raw base `first`
+        const uint8_t* p = seq + s0;
+        const uint64_t be = (static_cast<uint64_t>(__ldg(p)) << 32) | (static_cast<uint64_t>(__ldg(p + 1)) << 24) |
+                            (static_cast<uint64_t>(__ldg(p + 2)) << 16) | (static_cast<uint64_t>(__ldg(p + 3)) << 8) |
+                            static_cast<uint64_t>(__ldg(p + 4));
+        const uint32_t t0 = static_cast<uint32_t>(first - 2 * s0);   // 0 or 1
+        x = static_cast<uint32_t>(be >> (4u * (2u - t0)));
+        const uint2 q = ldg_u64_unaligned(qual + first);      // raw qualities first .. e
+        q_lo = __byte_perm(q.y, 0u, 0x0123u);                 // reversed: position j <- raw e - j
+        q_hi = __byte_perm(q.x, 0u, 0x0123u);
+      }
+      const uint16_t* lut = rev ? lut_r : lut_f;
+      uint32_t b_lo = static_cast<uint32_t>(lut[x & 0xFFu]) | (static_cast<uint32_t>(lut[(x >> 8) & 0xFFu]) << 16);
+      uint32_t b_hi = static_cast<uint32_t>(lut[(x >> 16) & 0xFFu]) | (static_cast<uint32_t>(lut[x >> 24]) << 16);
+      if (a.min_q) {                                          // vanilla_caller.rs:908-916
+        uint32_t ok_lo, ok_hi;
+        if (!wide_q) {
+          const uint32_t ts = tq * 0x01010101u;               // high bit survives iff (q & 0x7F) >= t; q >= 128 passes outright
+          ok_lo = (((q_lo | 0x80808080u) - ts) | q_lo) & 0x80808080u;
+          ok_hi = (((q_hi | 0x80808080u) - ts) | q_hi) & 0x80808080u;
+        } else {
+          ok_lo = ok_hi = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ok_lo |= (((q_lo >> (8 * j)) & 0xFFu) >= a.min_q) ? (0x80u << (8 * j)) : 0u;
+            ok_hi |= (((q_hi >> (8 * j)) & 0xFFu) >= a.min_q) ? (0x80u << (8 * j)) : 0u;
+          }
+        }
+        const uint32_t m_lo = spread_msb(ok_lo ^ 0x80808080u);   // 0xFF where the base is masked
+        const uint32_t m_hi = spread_msb(ok_hi ^ 0x80808080u);
+        b_lo = (b_lo & ~m_lo) | (0x4E4E4E4Eu & m_lo); q_lo = (q_lo & ~m_lo) | (0x02020202u & m_lo);
+        b_hi = (b_hi & ~m_hi) | (0x4E4E4E4Eu & m_hi); q_hi = (q_hi & ~m_hi) | (0x02020202u & m_hi);
+      }
+      const uint32_t live = len - 8u * w;                     // positions of this word inside the row (>= 1)
+      if (live < 8u) {                                        // zero the row padding
+        const uint32_t k_lo = live >= 4u ? 0xFFFFFFFFu : ((1u << (8u * live)) - 1u);
+        const uint32_t k_hi = live <= 4u ? 0u : ((1u << (8u * (live - 4u))) - 1u);
+        b_lo &= k_lo; q_lo &= k_lo; b_hi &= k_hi; q_hi &= k_hi;
+      }
+      *reinterpret_cast<uint2*>(a.bases + off + w * 8u) = make_uint2(b_lo, b_hi);
+      *reinterpret_cast<uint2*>(a.quals + off + w * 8u) = make_uint2(q_lo, q_hi);
+    }
   }
 }
 

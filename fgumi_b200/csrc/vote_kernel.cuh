@@ -32,6 +32,7 @@
 #include "../../include/fgumi_b200.h"
 #include "device_math.cuh"
 #include "fgb_config.h"
+#include "swar.cuh"
 
 namespace fgb {
 
@@ -45,6 +46,7 @@ struct DeviceTables {
   int32_t g2fix;                // dominant-winner threshold, fixed point
   uint32_t nmax2;               // dominant-winner proof valid up to this many observations
   uint8_t pair_q[94 * 94];      // unanimous two-read pileups: quality by (q1, q2); 255 = literal path
+  uint16_t sumt[8];             // sum-of-qualities thresholds by depth (host_tables.cpp), 0xFFFF = none
 };
 
 struct VoteArgs {

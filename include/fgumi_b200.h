@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define FGB_ABI_VERSION 1
+#define FGB_ABI_VERSION 2
 #define FGB_READ_ALIGN 8u   /* byte alignment of every read row in bases[]/quals[]          */
 #define FGB_OUT_ALIGN 8u    /* element alignment of every unit's output row                 */
 #define FGB_MAX_READ_LEN 65535u
@@ -238,6 +238,25 @@ typedef struct fgb_raw_columns {
   uint8_t reserved[7];
 } fgb_raw_columns;
 
+/* RECORDS: the BAM records themselves (raw-bam fields.rs:6-23), shipped as they are -- one DMA from pinned
+ * memory, no per-base host work.  raw_reads[r] describes read r of the batch: src_off = byte offset of the
+ * record's packed-sequence field inside `records`, raw_len = the record's l_seq (its quality bytes start
+ * (l_seq + 1) / 2 bytes after src_off), flags = FGB_RAW_REVERSE for a reverse-strand read.  The device does
+ * the per-base part of create_source_read (vanilla_caller.rs:893-916) / to_source_read_for_codec_raw
+ * (codec_caller.rs:414-469): row position p is raw base p (forward) or l_seq - 1 - p complemented (reverse),
+ * q < min_input_base_quality -> (N, Q2).  The host keeps the per-read decisions; the row length in
+ * fgb_batch.reads[r] is the length after mate clip / quality trim / trailing-N strip (<= raw_len).  Every
+ * sequence field must start at least 16 bytes into `records` (it always does: a record's fixed fields come
+ * first); spans are checked on the device, a violation skips the read and fails the next fgb_wait with
+ * FGB_ERR_LAYOUT. */
+typedef struct fgb_record_columns {
+  uint64_t n_bytes;               /* bytes in `records`                                                   */
+  const uint8_t* records;
+  const fgb_raw_read* raw_reads;  /* n_reads entries                                                      */
+  uint8_t min_input_base_quality; /* 0 = no masking (CODEC)                                               */
+  uint8_t reserved[7];
+} fgb_record_columns;
+
 /* fgb_submit for a batch whose rows are built on the device: `in` carries units / reads / tiles /
  * n_* as usual (row offsets and lengths describe the rows to build), in->bases and in->quals are
  * ignored.  Same chunking, ordering and completion rules as fgb_submit. */
@@ -382,19 +401,6 @@ fgb_status fgb_filter_simplex_device(fgb_handle* h, const fgb_batch* in, const f
                                      const fgb_filter_params* fp, uint8_t* unit_status,
                                      uint32_t* unit_masked, void* stream);
 
-enum { FGB_IN_BYTES = 0, FGB_IN_PACK8 = 1, FGB_IN_BAM4 = 2 };
-enum { FGB_OUT_U16 = 0, FGB_OUT_U8 = 1 };
-typedef struct fgb_submit_options {
-  uint32_t input_format;           /* FGB_IN_*  */
-  uint32_t output_format;          /* FGB_OUT_* */
-  const fgb_raw_columns* raw;      /* FGB_IN_BAM4 only */
-  const fgb_filter_params* filter; /* non-NULL: run the filter epilogue before the copy back      */
-  uint8_t* unit_status;            /* host, n_units bytes (required with `filter`)                */
-  uint32_t* unit_masked;           /* host, n_units words, may be NULL                            */
-} fgb_submit_options;
-fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out,
-                         const fgb_submit_options* opt);
-
 /* Device-resident variant of the unpack step alone (multi-kernel flows, tests): all pointers of
  * `in`, `raw` and the row columns are device pointers; enqueues one kernel on `stream`. */
 fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,
@@ -488,6 +494,39 @@ fgb_status fgb_duplex_submit(fgb_handle* h, const fgb_batch* in, const fgb_colum
 fgb_status fgb_codec_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss_out,
                             const fgb_codec_job* jobs, uint64_t n_jobs, const fgb_codec_params* cp,
                             uint64_t n_codec_out, const fgb_codec_out* out);
+
+/* ---- the general host-buffer call --------------------------------------------------------------------
+ * Any input format, optionally narrow outputs, the filter epilogue, and -- for the duplex / CODEC callers
+ * -- the strand combine of the voted units in the same call.  With combine jobs the batch is processed as
+ * ONE piece (a molecule's units must be voted before its job runs) and `out` receives the single-strand
+ * columns (they become the ac/ad/ae/aq, bc/bd/be/bq tags). */
+enum { FGB_IN_BYTES = 0, FGB_IN_PACK8 = 1, FGB_IN_BAM4 = 2, FGB_IN_RECORDS = 3 };
+enum { FGB_OUT_U16 = 0, FGB_OUT_U8 = 1 };
+typedef struct fgb_submit_options {
+  uint32_t input_format;           /* FGB_IN_*  */
+  uint32_t output_format;          /* FGB_OUT_* */
+  const fgb_raw_columns* raw;      /* FGB_IN_BAM4 only */
+  const fgb_filter_params* filter; /* non-NULL: run the filter epilogue before the copy back      */
+  uint8_t* unit_status;            /* host, n_units bytes (required with `filter`)                */
+  uint32_t* unit_masked;           /* host, n_units words, may be NULL                            */
+  /* ---- since ABI 2 ---- */
+  const fgb_record_columns* records;   /* FGB_IN_RECORDS only                                     */
+  const fgb_duplex_job* duplex_jobs;   /* host; K2 after the vote                                 */
+  uint64_t n_duplex_jobs;
+  uint64_t n_duplex_out;               /* elements in each column of duplex_out                   */
+  const fgb_duplex_out* duplex_out;    /* host columns                                            */
+  const fgb_codec_job* codec_jobs;     /* host; K3 after the vote                                 */
+  uint64_t n_codec_jobs;
+  uint64_t n_codec_out;
+  const fgb_codec_params* codec_params;
+  const fgb_codec_out* codec_out;      /* host columns                                            */
+} fgb_submit_options;
+fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out,
+                         const fgb_submit_options* opt);
+/* Device-resident variant of the RECORDS unpack step alone (tests, multi-kernel flows): every pointer of
+ * `in`, `rec` and the row columns is a device pointer; enqueues one kernel on `stream`. */
+fgb_status fgb_unpack_records_device(fgb_handle* h, const fgb_batch* in, const fgb_record_columns* rec,
+                                     uint8_t* bases, uint8_t* quals, void* stream);
 
 /* ---- statistics, K4 -------------------------------------------------------------------- */
 /* Synchronises the handle's streams and copies the device counters (cumulative). */

@@ -20,5 +20,6 @@ for r in csv.reader(io.StringIO(txt)):
             a[0] += samp; a[1] += inst; a[2] += tinst
 tot, toti = sum(a[0] for a in agg.values()) or 1, sum(a[1] for a in agg.values()) or 1
 print(f"total samples {tot}  warp instructions {toti}")
-for k, a in sorted(agg.items(), key=lambda x: -x[1][0])[:top]:
+key = (lambda x: -x[1][1]) if len(sys.argv) > 3 and sys.argv[3] == "inst" else (lambda x: -x[1][0])
+for k, a in sorted(agg.items(), key=key)[:top]:
     print(f"{k[0]}:{k[1]:4d} samp {100 * a[0] / tot:5.1f}% inst {100 * a[1] / toti:5.1f}% thr/inst {a[2] / max(a[1], 1):5.1f} | {a[3].strip()[:88]}")
