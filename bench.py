@@ -15,8 +15,14 @@ Keys beyond the base contract:
   e2e           same metric through the host-buffer C-ABI call (fgb_submit/fgb_wait) from pinned
                 host memory, H2D + vote + D2H inside the timed region
 
-`--impl reference` times the reference's CPU algorithm (the oracle, all host threads) on a
-bounded sample of the same workload.
+  e2e_records   the record-level boundary (the reference's `ConsensusCaller`): raw BAM records in pinned
+                host memory -> fgb_caller_add_groups + fgb_caller_flush -> ConsensusOutput bytes, beside
+                the same host code over the CPU oracle's vote (oracle/libfgb_cpu_caller.so)
+  duplex / codec / zipf   device-resident kernel legs for BASELINE configs 3, 4 and 5 (per-kernel ms and
+                fraction of the HBM roofline)
+
+`--impl reference` times the reference's CPU algorithm (the oracle built for speed,
+oracle/liboracle_native.so, best thread count) on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -62,6 +68,68 @@ def recorded_traffic():
             return json.load(f)
     except Exception:
         return None
+
+
+def cpu_quota() -> int:
+    """CPUs this process may actually use: the cgroup CPU quota (cpu.max) capped by the affinity mask."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
+
+
+def bind_to_gpu_numa(torch, local: int):
+    """Run this rank (and therefore first-touch its page-locked buffers) on the NUMA node its GPU hangs off.
+    Never raises; returns a short description for the bench line."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        dev = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read())
+        if node < 0:
+            return {"node": None, "note": "device reports no NUMA node"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception as e:      # pragma: no cover
+        return {"node": None, "note": repr(e)[:80]}
+
+
+def link_peak(torch, dev, nbytes: int = 1 << 30):
+    """Measured host<->device copy bandwidth of this box from page-locked memory (GB/s): the roofline of `e2e`."""
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, fn in (("h2d_gbs", lambda: d.copy_(h, non_blocking=True)), ("d2h_gbs", lambda: h.copy_(d, non_blocking=True))):
+        fn(); torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        out[name] = best
+    # both directions at once (the e2e pipeline overlaps the copy back of one chunk with the upload of the next)
+    h2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    s2 = torch.cuda.Stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    d.copy_(h, non_blocking=True)
+    with torch.cuda.stream(s2):
+        h2.copy_(d, non_blocking=True)
+    torch.cuda.current_stream().wait_stream(s2)
+    e1.record(); torch.cuda.synchronize()
+    out["duplex_gbs_each"] = nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del h, h2, d
+    return out
 
 
 class ClockSampler:
@@ -152,39 +220,80 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling failed: %r" % (e,)]}
 
 
-def cpu_oracle_rate(n_units: int, threads: int, seed: int = 1234, min_seconds: float = 10.0):
-    """Times the CPU oracle (TEST INFRASTRUCTURE used only as the measured baseline) on a sample."""
-    import fgumi_b200 as fg
-    from fgumi_b200 import synth
-    from tests import oracle_lib as O
-    b, q = synth.host_pileup(n_units, DEPTH, READ_LEN, ERR, seed=seed)
-    batch = fg.pack_uniform(b, q, 1)
-    outs = O.alloc_outputs(batch)
-    threads, probe = best_thread_count(batch, outs, threads)
-    O.simplex_batch(batch, 45, 40, 1, 2, threads, outs)    # warm (page faults, thread start)
-    reps, t = 0, time.perf_counter()
-    while True:                                            # ~10 s of CPU work
-        O.simplex_batch(batch, 45, 40, 1, 2, threads, outs)
-        reps += 1
-        dt = time.perf_counter() - t
-        if dt >= min_seconds or reps >= 2000:
-            break
-    return n_units * reps / dt, dt, reps, threads, probe
+def _pileup(n_units, depth, L, error_rate, seed, min_input_q=10):
+    """fgumi_b200/synth.py host_pileup, restated here so that the CPU arm imports no product code."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    tmpl = acgt[rng.integers(0, 4, size=(n_units, 1, L))]
+    bases = np.broadcast_to(tmpl, (n_units, depth, L)).copy()
+    if error_rate > 0:
+        err = rng.random((n_units, depth, L)) < error_rate
+        shift = rng.integers(1, 4, size=(n_units, depth, L))
+        code = np.searchsorted(acgt, bases)
+        bases = np.where(err, acgt[(code + shift) % 4], bases)
+    pos = np.arange(L, dtype=np.float64)
+    curve = np.where(pos < 10, 25.0 + (pos / 10.0) * 12.0, 37.0)
+    curve = np.where(pos >= 100, np.maximum(37.0 - (pos - 100.0) * 0.08, 2.0), curve)
+    q = np.clip(np.rint(curve[None, None, :] + rng.normal(0.0, 2.0, size=(n_units, depth, L))), 2, 41)
+    quals = q.astype(np.uint8)
+    low = quals < min_input_q
+    return np.where(low, np.uint8(ord("N")), bases).astype(np.uint8), np.where(low, np.uint8(2), quals).astype(np.uint8)
 
 
-def best_thread_count(batch, outs, max_threads: int):
-    """The host may expose more logical CPUs than it schedules well (SMT, shared boxes): probe a few
+def oracle_batch(n_units: int, seed: int = 1234):
+    """The CPU arm's input: the SoA batch of include/fgumi_b200.h built with numpy only (no product code is
+    imported or loaded by the CPU legs), same generator as the GPU arm."""
+    from types import SimpleNamespace
+    b, q = _pileup(n_units, DEPTH, READ_LEN, ERR, seed)
+    Lp = (READ_LEN + 7) // 8 * 8
+    R = n_units * DEPTH
+    bases = np.zeros((R, Lp), np.uint8); quals = np.zeros((R, Lp), np.uint8)
+    bases[:, :READ_LEN] = b.reshape(R, READ_LEN); quals[:, :READ_LEN] = q.reshape(R, READ_LEN)
+    reads = ((np.arange(R, dtype=np.uint64) * np.uint64(Lp)) << np.uint64(16)) | np.uint64(READ_LEN)
+    units = np.zeros(n_units + 1, dtype=np.dtype([("out_off", "<u8"), ("read_begin", "<u4"), ("cons_len", "<u4")]))
+    units["out_off"] = np.arange(n_units + 1, dtype=np.uint64) * np.uint64(Lp)
+    units["read_begin"] = np.arange(n_units + 1, dtype=np.uint32) * np.uint32(DEPTH)
+    units["cons_len"][:n_units] = READ_LEN
+    return SimpleNamespace(n_units=n_units, n_reads=R, n_out=n_units * Lp, bases=np.pad(bases.reshape(-1), (0, 16)),
+                           quals=np.pad(quals.reshape(-1), (0, 16)), reads=np.pad(reads, (0, 2)), units=units)
+
+
+def best_thread_count(batch, outs, max_threads: int, native: bool = True):
+    """The host may expose more logical CPUs than it schedules well (SMT, cgroup quotas): probe a few
     thread counts with one pass each and keep the fastest, so the baseline is the CPU at its best."""
     from tests import oracle_lib as O
-    cands = sorted({max(1, max_threads >> k) for k in range(0, 4)} | {1})
-    O.simplex_batch(batch, 45, 40, 1, 2, max_threads, outs)      # first-touch
+    quota = cpu_quota()
+    cands = sorted({max(1, max_threads >> k) for k in range(0, 4)} | {1, quota, min(max_threads, 2 * quota)})
+    O.simplex_batch(batch, 45, 40, 1, 2, max_threads, outs, native=native)      # first-touch
     rates = {}
     for th in cands:
         t = time.perf_counter()
-        O.simplex_batch(batch, 45, 40, 1, 2, th, outs)
+        O.simplex_batch(batch, 45, 40, 1, 2, th, outs, native=native)
         rates[th] = batch.n_units / (time.perf_counter() - t)
     best = max(rates, key=rates.get)
     return best, {str(k): round(v) for k, v in rates.items()}
+
+
+def cpu_oracle_rate(n_units: int, threads: int, seed: int = 1234, min_seconds: float = 8.0):
+    """Times the CPU oracle (TEST INFRASTRUCTURE used only as the measured baseline) on a sample: the build for
+    speed (-O3 -march=x86-64-v3, oracle/Makefile) and, for reference, the plain -O2 build the tests use."""
+    from tests import oracle_lib as O
+    batch = oracle_batch(n_units, seed)
+    outs = O.alloc_outputs(batch)
+    threads, probe = best_thread_count(batch, outs, threads)
+
+    def rate(native, secs):
+        O.simplex_batch(batch, 45, 40, 1, 2, threads, outs, native=native)    # warm (page faults, thread start)
+        reps, t = 0, time.perf_counter()
+        while True:
+            O.simplex_batch(batch, 45, 40, 1, 2, threads, outs, native=native)
+            reps += 1
+            dt = time.perf_counter() - t
+            if dt >= secs or reps >= 2000:
+                return n_units * reps / dt, dt, reps
+    v, dt, reps = rate(True, min_seconds)
+    v_scalar, _, _ = rate(False, 3.0)
+    return v, dt, reps, threads, probe, v_scalar
 
 
 def run_reference(args):
@@ -193,22 +302,20 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     n = int(os.environ.get("FGB_REF_SAMPLE_UNITS", "400000"))
-    import fgumi_b200 as fg
-    from fgumi_b200 import synth
     from tests import oracle_lib as O
-    b, q = synth.host_pileup(n, DEPTH, READ_LEN, ERR, seed=1234)
-    batch = fg.pack_uniform(b, q, 1)
+    O.build()
+    batch = oracle_batch(n, 1234)
     outs = O.alloc_outputs(batch)
     threads, probe = best_thread_count(batch, outs, threads)
     for _ in range(args.warmup):
-        O.simplex_batch(batch, 45, 40, 1, 2, threads, outs)
+        O.simplex_batch(batch, 45, 40, 1, 2, threads, outs, native=True)
     t = time.perf_counter()
     for _ in range(args.steps):
-        O.simplex_batch(batch, 45, 40, 1, 2, threads, outs)
+        O.simplex_batch(batch, 45, 40, 1, 2, threads, outs, native=True)
     dt = time.perf_counter() - t
     v = n * args.steps / dt
     sample = (f"{n} families depth {DEPTH} x {READ_LEN} bp per step (same generator as the GPU arm); "
-              f"threads probed (families/s): {probe}")
+              f"threads probed (families/s): {probe}; cgroup CPU quota {cpu_quota()}")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -218,10 +325,64 @@ def run_reference(args):
                                "(BASELINE.json configs[1]), bounded sample", "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample + "; oracle = C++ restatement of fgumi 0.2.0 "
-                                            "(Rust toolchain absent), std::thread over families"},
+                                            "(Rust toolchain absent), -O3 -march=x86-64-v3, std::thread over families"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def bench_records(torch, dist, fg, lib, dev, local, world, rank, args, barrier):
+    """Record-level leg (every rank runs it on its own GPU with its share of the host threads; rank 0 reports
+    the sum), plus -- on rank 0 at N=1 -- the record-level CPU baseline."""
+    from fgumi_b200 import benchlegs
+    threads = max(1, cpu_quota() // world)
+    barrier()
+    r = benchlegs.records_leg(torch, fg, lib, local, args.record_families, threads, steps=max(3, min(args.steps, 6)))
+    if world > 1:
+        t = torch.tensor([r["value"], r.get("one_caller", {}).get("value", 0.0)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        r["value"] = float(t[0].item())
+        r["note"] = f"sum over {world} ranks, {threads} host threads each (cgroup CPU quota {cpu_quota()})"
+    if rank == 0 and world == 1 and args.cpu_units > 0:
+        try:
+            r["cpu_baseline"] = benchlegs.records_cpu_baseline(min(args.record_families, 50000), cpu_quota())
+        except Exception as ex:       # pragma: no cover
+            r["cpu_baseline"] = {"error": repr(ex)[:200]}
+    return r
+
+
+def bench_duplex(torch, dist, fg, dev, local, world, rank, args):
+    from fgumi_b200 import benchlegs
+    r = benchlegs.duplex_leg(torch, fg, dev, local, int(os.environ.get("FGB_DUPLEX_MOLECULES", "5000000")))
+    return _sum_ranks(torch, dist, dev, world, r)
+
+
+def bench_codec(torch, dist, fg, dev, local, world, rank, args):
+    from fgumi_b200 import benchlegs
+    r = benchlegs.codec_leg(torch, fg, dev, local, int(os.environ.get("FGB_CODEC_MOLECULES", "2000000")))
+    return _sum_ranks(torch, dist, dev, world, r)
+
+
+def bench_zipf(torch, dist, fg, dev, local, world, rank, args):
+    from fgumi_b200 import benchlegs
+    r = benchlegs.zipf_leg(torch, fg, dev, local, int(os.environ.get("FGB_ZIPF_FAMILIES", "100000000")), world, rank)
+    if world > 1:      # whole job: all families over the slowest rank's time
+        t = torch.tensor([r["k1_ms"]], dtype=torch.float64, device=dev)
+        n = torch.tensor([float(r["families_this_rank"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        r["value"] = float(n.item()) / (float(t.item()) * 1e-3)
+        r["k1_ms_max_over_ranks"] = float(t.item())
+    return r
+
+
+def _sum_ranks(torch, dist, dev, world, r):
+    if world > 1:      # weak scaling: every rank runs the same size; the job's rate is the sum
+        t = torch.tensor([r["value"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        r["value"] = float(t.item())
+        r["note"] = f"sum over {world} ranks (per-kernel ms and fractions are rank 0's)"
+    return r
 
 
 def main():
@@ -234,14 +395,15 @@ def main():
                     help="families per GPU per step (BASELINE config: 10 M)")
     ap.add_argument("--e2e-units", type=int, default=int(os.environ.get("FGB_E2E_UNITS", "1000000")))
     ap.add_argument("--cpu-units", type=int, default=int(os.environ.get("FGB_CPU_UNITS", "400000")))
+    ap.add_argument("--record-families", type=int, default=int(os.environ.get("FGB_RECORD_FAMILIES", "200000")),
+                    help="families per batch of the record-level leg")
+    ap.add_argument("--no-modes", action="store_true", help="skip the duplex / CODEC / Zipf kernel legs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
 
     if args.impl == "reference":
-        import __graft_entry__ as g
-        g.build()
-        run_reference(args)
+        run_reference(args)                  # builds and loads oracle/ only: no product code on this arm
         return
 
     import torch
@@ -258,6 +420,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: fgumi_b200 has no CPU path")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    numa = bind_to_gpu_numa(torch, local)        # before any page-locked allocation (first touch = local node)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
@@ -385,10 +548,19 @@ def main():
             ho8 = fg.HostColumns(ho.base, ho.qual, pin(hb.n_out, torch.uint8).numpy(),
                                  pin(hb.n_out, torch.uint8).numpy())
             v_pack8n = timed_e2e(lambda: eng.submit_ex(hb, ho8, packed=ppn, narrow=True), "fgb_e2e_pack8_u8")
+            # (2c) the same with the host-side PACK8 encode (fgb_pack8_encode, one host thread) INSIDE the timed region
+            def encode_and_submit():
+                st = lib.fgb_pack8_encode(hb.bases.ctypes.data, hb.quals.ctypes.data, nb, ppn.ctypes.data)
+                if st != 0:
+                    raise fg.lib.FgbError(st, "fgb_pack8_encode")
+                eng.submit_ex(hb, ho8, packed=ppn, narrow=True)
+            v_pack8enc = timed_e2e(encode_and_submit, "fgb_e2e_pack8_encode")
             e2e = {"value": v_pack8n, "unit": UNIT, "h2d_bytes_per_step": int(nb + desc_bytes),
                    "d2h_bytes_per_step": int(hb.n_out * 4), "units_per_step": EU, "steps": esteps,
                    "api": "fgb_submit_ex(FGB_IN_PACK8, FGB_OUT_U8) + fgb_wait (pinned host buffers: "
-                          "1 byte per observation in, 4 bytes per consensus position out)",
+                          "1 byte per observation in, 4 bytes per consensus position out); rows arrive PACK8-encoded "
+                          "(the encode is part of source-read preparation; `pack8_encode_timed` has it inside)",
+                   "pack8_encode_timed": {"value": v_pack8enc, "note": "fgb_pack8_encode on ONE host thread per step + the call above"},
                    "pack8_u16": {"value": v_pack, "h2d_bytes_per_step": int(nb + desc_bytes),
                                  "d2h_bytes_per_step": int(d2h), "api": "fgb_submit_pack8 + fgb_wait"},
                    "two_column": {"value": v_bytes, "h2d_bytes_per_step": int(2 * nb + desc_bytes),
@@ -419,15 +591,44 @@ def main():
             e2e = {"value": v_bytes, "unit": UNIT, "h2d_bytes_per_step": int(2 * nb + desc_bytes),
                    "d2h_bytes_per_step": int(d2h), "units_per_step": EU, "steps": esteps,
                    "api": "fgb_submit + fgb_wait (pinned host buffers)"}
+        # the link is the roofline of every e2e leg: measured page-locked copy bandwidth of THIS box
+        try:
+            link = link_peak(torch, dev)
+            h2d_rate = e2e["h2d_bytes_per_step"] * e2e["value"] / EU / world / 1e9      # GB/s per GPU
+            e2e["link"] = dict(link, numa=numa)
+            e2e["roofline"] = {"bound": "pcie h2d", "achieved": h2d_rate, "peak": link["h2d_gbs"], "unit": "GB/s",
+                               "frac": h2d_rate / link["h2d_gbs"]}
+        except Exception as ex:       # pragma: no cover
+            e2e["link"] = {"error": repr(ex)[:200]}
+        del pb, pq, ho, preads
+    del tb, out, bstruct, cstruct
+    torch.cuda.empty_cache()
+
+    # ---- record-level boundary: raw BAM records -> ConsensusOutput bytes ----
+    records_leg = None
+    try:
+        records_leg = bench_records(torch, dist, fg, lib, dev, local, world, rank, args, barrier)
+    except Exception as ex:           # pragma: no cover  (an extra leg never costs the line)
+        records_leg = {"error": repr(ex)[:300]}
+    # ---- BASELINE configs 3, 4, 5: device-resident kernel legs ----
+    modes = {}
+    if not args.no_modes:
+        for name, fn in (("duplex", bench_duplex), ("codec", bench_codec), ("zipf", bench_zipf)):
+            try:
+                modes[name] = fn(torch, dist, fg, dev, local, world, rank, args)
+            except Exception as ex:   # pragma: no cover
+                modes[name] = {"error": repr(ex)[:300]}
+            torch.cuda.empty_cache()
 
     if rank == 0 and world == 1 and args.cpu_units > 0:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1)) if hasattr(os, "sched_setaffinity") else None   # the CPU arm may use every core
         threads = os.cpu_count() or 1
-        v, dtc, reps, threads, probe = cpu_oracle_rate(args.cpu_units, threads)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "logical_cpus": os.cpu_count(),
-               "thread_probe": probe, "kind": "port",
+        v, dtc, reps, threads, probe, v_scalar = cpu_oracle_rate(args.cpu_units, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "logical_cpus": os.cpu_count(), "cpu_quota": cpu_quota(),
+               "thread_probe": probe, "kind": "port", "value_O2_generic": v_scalar,
                "sample": f"{reps} passes over {args.cpu_units} families depth {DEPTH} x {READ_LEN} bp, {dtc:.1f} s; "
-                         "oracle = C++ restatement of fgumi 0.2.0 (no Rust toolchain), "
-                         "std::thread over families"}
+                         "oracle = C++ restatement of fgumi 0.2.0 (no Rust toolchain) built -O3 -march=x86-64-v3 "
+                         "(value_O2_generic: the -O2 build the tests use), std::thread over families"}
 
     if rank == 0:
         line = {
@@ -442,7 +643,8 @@ def main():
                                                     "--min-reads 1, overlapping pre-pass off",
                        "parallelism": f"range-shard x{world}",
                        "l2": "inputs (24 GB/GPU) larger than L2; no flush needed"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_records": records_leg,
+            "duplex": modes.get("duplex"), "codec": modes.get("codec"), "zipf": modes.get("zipf"),
             "gpu_launches": int(launches), "clocks": clocks,
             "counters": stats_all,
         }

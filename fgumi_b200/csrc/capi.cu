@@ -20,7 +20,6 @@
 #include "planner.h"
 #include "unpack_kernels.cuh"
 #include "vote_kernel.cuh"
-#include "vote_kernel_w.cuh"
 
 using namespace fgb;
 
@@ -54,6 +53,7 @@ struct Slot {
   uint64_t cap_seq4 = 0, cap_qraw = 0, cap_rawreads = 0;
   uint8_t* recblob = nullptr;    // RECORDS transfer blob (fgb_submit_ex, FGB_IN_RECORDS)
   uint64_t cap_recblob = 0;
+  std::vector<fgb_tile> tile_stage;   // class-sorted copy of a chunk's tiles (host)
   // strand-combine jobs of fgb_submit_ex (duplex / CODEC callers)
   fgb_duplex_job* djobs = nullptr; uint64_t cap_djobs = 0;
   fgb_codec_job* cjobs = nullptr; uint64_t cap_cjobs = 0;
@@ -89,7 +89,7 @@ struct fgb_handle {
   double emax_rate = -1.0;                          // the max_base_error_rate d_emax was built for
   int n_slots = 2;                                  // FGB_SUBMIT_SLOTS (1..kSlots)
   uint64_t chunk_bytes = kChunkColumnBytes;         // FGB_SUBMIT_CHUNK_MB
-  int vote_variant = 0;                             // FGB_VOTE_KERNEL: 0 = vote_kernel (thread per item), 1 = vote_kernel_w (warp per unit)
+  int vote_variant = 1;                             // FGB_VOTE_KERNEL=0: the general kernel votes every tile (A/B runs)
 };
 
 namespace {
@@ -130,15 +130,46 @@ fgb_status launch_vote(fgb_handle* h, const fgb_batch& b, const fgb_columns& out
   a.min_reads = h->params.min_reads;
   a.min_cons_q = h->params.min_consensus_base_quality;
   a.fast_qual = h->host_tables.fast_qual;
-  uint64_t max_grid = static_cast<uint64_t>(h->sm_count) * 2u;
-  unsigned grid = static_cast<unsigned>(std::min<uint64_t>(b.n_tiles, max_grid));
-  if (h->vote_variant == 0) vote_kernel<<<grid, kThreads, sizeof(VoteSmem), stream>>>(a);
-  else vote_kernel_w<<<grid, kThreads, sizeof(VoteSmemW), stream>>>(a);
-  h->launches++;
+  const uint64_t max_grid = static_cast<uint64_t>(h->sm_count) * 2u;
+  const uint64_t c0 = b.class_tiles[0], c1 = b.class_tiles[1], c2 = b.class_tiles[2];
+  const bool sorted = h->vote_variant != 0 && c0 + c1 + c2 == b.n_tiles;
+  auto launch = [&](int cls, uint64_t first, uint64_t n) {
+    if (!n) return;
+    VoteArgs x = a;
+    x.tiles = b.tiles + first;
+    x.n_tiles = n;
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, max_grid));
+    if (cls == 1) vote_kernel_shallow<<<grid, kThreads, sizeof(VoteSmem), stream>>>(x);
+    else if (cls == 2) vote_kernel_deep<<<grid, kThreads, sizeof(VoteSmem), stream>>>(x);
+    else vote_kernel<<<grid, kThreads, sizeof(VoteSmem), stream>>>(x);
+    h->launches++;
+  };
+  if (sorted) { launch(0, 0, c0); launch(1, c0, c1); launch(2, c0 + c1, c2); }
+  else launch(0, 0, b.n_tiles);
   FGB_CUDA(h, cudaGetLastError());
   return FGB_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+fgb_status fgb_sort_tiles_by_class(fgb_tile* tiles, uint64_t n_tiles, uint64_t class_tiles[3]) {
+  if ((n_tiles && !tiles) || !class_tiles) return FGB_ERR_INVALID_ARG;
+  class_tiles[0] = class_tiles[1] = class_tiles[2] = 0;
+  std::stable_sort(tiles, tiles + n_tiles, [](const fgb_tile& x, const fgb_tile& y) {
+    return ((x.flags & kTileClassMask) >> kTileClassShift) < ((y.flags & kTileClassMask) >> kTileClassShift);
+  });
+  for (uint64_t i = 0; i < n_tiles; ++i) {
+    const uint32_t c = (tiles[i].flags & kTileClassMask) >> kTileClassShift;
+    class_tiles[c < 3 ? c : 0]++;
+  }
+  return FGB_OK;
+}
+
+}  // extern "C"
+
+namespace {
 }  // namespace
 
 extern "C" {
@@ -225,9 +256,12 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   if ((e = cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(sizeof(VoteSmem)))) != cudaSuccess)
     return fail(e, "cudaFuncSetAttribute(vote_kernel)");
-  if ((e = cudaFuncSetAttribute(vote_kernel_w, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(sizeof(VoteSmemW)))) != cudaSuccess)
-    return fail(e, "cudaFuncSetAttribute(vote_kernel_w)");
+  if ((e = cudaFuncSetAttribute(vote_kernel_shallow, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(VoteSmem)))) != cudaSuccess)
+    return fail(e, "cudaFuncSetAttribute(vote_kernel_shallow)");
+  if ((e = cudaFuncSetAttribute(vote_kernel_deep, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(VoteSmem)))) != cudaSuccess)
+    return fail(e, "cudaFuncSetAttribute(vote_kernel_deep)");
   for (int s = 0; s < kSlots; ++s)
     if ((e = cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking)) != cudaSuccess)
       return fail(e, "cudaStreamCreate");
@@ -565,7 +599,20 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
     FGB_CUDA(h, cudaMemcpyAsync(sl.reads, in->reads + r0, (r1 - r0) * 8, cudaMemcpyHostToDevice, s));
     FGB_CUDA(h, cudaMemcpyAsync(sl.units, in->units + u0, (u1 - u0 + 1) * sizeof(fgb_unit),
                                 cudaMemcpyHostToDevice, s));
-    FGB_CUDA(h, cudaMemcpyAsync(sl.tiles, T + t0, (t1 - t0) * sizeof(fgb_tile),
+    // the chunk's tiles, sorted by class (the kernels do not care about tile order); the copy below is from
+    // pageable memory, which the runtime stages before cudaMemcpyAsync returns, so the vector can be reused
+    uint64_t chunk_classes[3] = {t1 - t0, 0, 0};
+    const fgb_tile* tsrc = T + t0;
+    {
+      bool mixed = false;
+      for (uint64_t t = t0; t < t1 && !mixed; ++t) mixed = (T[t].flags & kTileClassMask) != 0;
+      if (mixed) {
+        sl.tile_stage.assign(T + t0, T + t1);
+        fgb_sort_tiles_by_class(sl.tile_stage.data(), t1 - t0, chunk_classes);
+        tsrc = sl.tile_stage.data();
+      }
+    }
+    FGB_CUDA(h, cudaMemcpyAsync(sl.tiles, tsrc, (t1 - t0) * sizeof(fgb_tile),
                                 cudaMemcpyHostToDevice, s));
     // Descriptors keep their absolute offsets; the kernel gets base pointers biased by the chunk
     // origin (byte0 / r0 / u0 / o0 keep every TMA source 16-byte aligned).
@@ -577,6 +624,7 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
     db.reads = sl.reads - r0;
     db.units = sl.units - u0;
     db.tiles = sl.tiles;
+    db.class_tiles[0] = chunk_classes[0]; db.class_tiles[1] = chunk_classes[1]; db.class_tiles[2] = chunk_classes[2];
     fgb_columns dc;
     dc.base = sl.out_base - o0;
     dc.qual = sl.out_qual - o0;
@@ -923,6 +971,7 @@ fgb_status upload_and_vote(fgb_handle* h, const fgb_batch* in, DevPool* pool, De
   FGB_CUDA(h, cudaMemcpyAsync(units, in->units, (in->n_units + 1) * sizeof(fgb_unit), cudaMemcpyHostToDevice, s));
   FGB_CUDA(h, cudaMemcpyAsync(tiles, in->tiles, in->n_tiles * sizeof(fgb_tile), cudaMemcpyHostToDevice, s));
   d->b = *in;
+  d->b.class_tiles[0] = d->b.class_tiles[1] = d->b.class_tiles[2] = 0;   // tiles uploaded as planned: general kernel
   d->b.bases = bases; d->b.quals = quals; d->b.reads = reads; d->b.units = units; d->b.tiles = tiles;
   return launch_vote(h, d->b, d->ss, s);
 }

@@ -24,6 +24,13 @@ constexpr uint32_t kTileFlagRegular = 2u;  // all reads one length L, rows back 
                                            // round_up(L,8), every unit calls L positions (L > 8)
 constexpr uint32_t kTileFlagSkew8 = 4u;    // regular tiles: first row starts 8 bytes into the stage
 constexpr uint32_t kTileFlagShallow = 8u;  // no unit of the tile has more than 64 reads
+// bits 4..5: tile class -- 0 general, 1 shallow (every unit has at most kShallowMax reads), 2 deep (every unit has
+// at least kDeepMin reads); tiles are class-homogeneous and each class has its own kernel (vote_kernel.cuh)
+constexpr uint32_t kTileClassShift = 4u;
+constexpr uint32_t kTileClassMask = 3u << kTileClassShift;
+constexpr uint32_t kShallowMax = 4u;
+constexpr uint32_t kDeepMin = 24u;
+inline uint32_t unit_class(uint32_t n_reads) { return n_reads <= kShallowMax ? 1u : (n_reads >= kDeepMin ? 2u : 0u); }
 // bits 8..31: items (8-position words) per unit when uniform over the tile (2..4096), else 0
 
 }  // namespace fgb

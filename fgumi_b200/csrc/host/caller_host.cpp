@@ -28,6 +28,7 @@
 #include "../../../include/fgumi_b200.h"
 #include "bam.h"
 #include "overlap.h"
+#include "../planner.h"
 #include "prep.h"
 #include "record_filter.h"
 
@@ -140,6 +141,57 @@ class WorkerPool {
   bool stop_ = false;
 };
 
+
+// ---- direct path (callers with a device) -----------------------------------------------------------
+// The records of a batch are copied once into page-locked staging memory and shipped as they are
+// (FGB_IN_RECORDS); the host keeps only the per-read decisions (survival, row length, strand) and small
+// references into the staging copy (UMI, cell barcode, RX values).  Each context -- the caller itself
+// and each worker of fgb_caller_add_groups -- appends to its own plan; the parent keeps the order.
+struct StrRef { uint64_t off = 0; uint32_t len = 0; };    // bytes inside the record staging
+
+struct DUnit {                       // one unit (consensus read) of a plan
+  uint32_t n_reads = 0, cons_len = 0;
+  uint32_t rx_begin = 0, rx_n = 0;   // RX values of the surviving reads, in DirectPlan::rx
+  StrRef umi, cell;
+  uint8_t read_type = 0, has_cell = 0;
+  uint32_t rec_size = 0;             // simplex: size of the consensus record incl. its block_size word, 0 = decided after the vote
+};
+
+struct DirectPlan {
+  std::vector<fgb_raw_read> raws;    // per read: src_off relative to the staging, l_seq, strand
+  std::vector<uint16_t> lens;        // per read: SourceRead row length
+  std::vector<DUnit> units;
+  std::vector<StrRef> rx;
+  uint64_t row_bytes = 0;            // sum of round_up(len, 8) over the reads
+  uint64_t out_elems = 0;            // sum of round_up(cons_len, 8) over the units
+  void clear() { raws.clear(); lens.clear(); units.clear(); rx.clear(); row_bytes = out_elems = 0; }
+};
+
+struct DMark { size_t raws, units, rx; uint64_t row_bytes, out_elems; };   // a plan's size, for roll-back
+
+struct DSeg {                        // units [u0, u1) / reads [r0, r1) of one context's plan, in input order
+  struct fgb_caller* ctx;
+  uint32_t u0, u1;
+  uint64_t r0, r1;
+  uint64_t row_bytes, out_elems;
+};
+
+struct PinBuf {                      // grow-only page-locked buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  fgb_status ensure(size_t bytes, size_t keep = 0) {
+    if (bytes <= cap) return FGB_OK;
+    const size_t ncap = bytes + bytes / 2 + 4096;
+    void* np = nullptr;
+    if (fgb_host_alloc(&np, ncap) != FGB_OK) return FGB_ERR_NOMEM;
+    if (keep) std::memcpy(np, p, keep);
+    fgb_host_free(p);
+    p = np; cap = ncap;
+    return FGB_OK;
+  }
+  void release() { fgb_host_free(p); p = nullptr; cap = 0; }
+};
+
 }  // namespace
 
 struct fgb_caller {
@@ -175,6 +227,15 @@ struct fgb_caller {
   bool out_is_joined = false;
   void* pinned[4] = {nullptr, nullptr, nullptr, nullptr};   // consensus columns, page-locked (fgb_host_alloc)
   size_t pinned_cap = 0;                     // capacity in elements (same for the four columns)
+  // ---- direct path (see DirectPlan) ----
+  bool direct = false;                       // device caller, simplex: stage the records, build rows on the device
+  DirectPlan dplan;                          // what THIS context queued (the caller itself or a worker)
+  std::vector<DSeg> segs;                    // parent: ranges of the plans in input order
+  PinBuf stage;                              // parent: the staged records
+  size_t stage_len = 0;
+  PinBuf d_reads, d_raws, d_units;           // parent: descriptor arrays handed to the engine
+  std::vector<View> views;                   // scratch: the records of the group being planned
+  std::vector<uint64_t> rel_off;             // scratch: record offsets relative to the group
 };
 
 namespace {
@@ -284,6 +345,199 @@ fgb_status add_group_simplex(fgb_caller* c, const std::vector<View>& recs) {
     reject(c, FGB_STAT_REJ_ORPHAN_CONSENSUS, p1.surviving);
   } else if (p2.ok) {
     reject(c, FGB_STAT_REJ_ORPHAN_CONSENSUS, p2.surviving);
+  }
+  return FGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// simplex, direct path: the group rules of add_group_simplex on record headers only (no read is decoded;
+// the device builds the SourceRead rows from the staged records)
+// ------------------------------------------------------------------------------------------------
+struct DRead {                       // one record of a sub-group that yields a source read
+  uint32_t rec;                      // index into the group's records
+  uint32_t final_len;
+  const uint8_t* rx;                 // RX value inside the staged record (nullptr: none)
+  uint32_t rx_len;
+};
+
+// process_subgroup up to the vote (vanilla_caller.rs:1124-1227).  True when the sub-group yields a unit;
+// `out` then lists its surviving reads in order.
+bool plan_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::vector<uint32_t>& members,
+                   std::vector<DRead>* out, size_t* surviving) {
+  out->clear();
+  *surviving = 0;
+  const size_t min_reads = c->opt.min_reads;
+  if (members.empty()) return false;
+  if (members.size() < min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, members.size()); return false; }
+  static const char kWant[2][2] = {{'M', 'C'}, {'R', 'X'}};
+  size_t zero = 0;
+  for (uint32_t k = 0; k < members.size(); ++k) {
+    const View& v = recs[members[k]];
+    bam::cigar_ops(v, &c->ops);
+    const uint8_t* val[2]; size_t len[2];
+    bam::find_string_tags(v, kWant, 2, val, len);
+    const size_t clip = bam::num_bases_extending_past_mate_mc(v, c->ops, val[0], len[0]);
+    const uint32_t fl = plan_read_len(c->prep_opt, v, clip);
+    if (fl) out->push_back(DRead{members[k], fl, val[1], static_cast<uint32_t>(len[1])});
+    else ++zero;
+  }
+  if (zero) reject(c, FGB_STAT_REJ_ZERO_LENGTH, zero);
+  size_t n = out->size();
+  if (n < min_reads) {
+    if (n) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, n);
+    return false;
+  }
+  // filter_source_reads_by_alignment (vanilla_caller.rs:961-1013).  Reads with the same CIGAR on the same
+  // strand all join the group of the longest one (a truncated copy of a CIGAR is a prefix of the copy that
+  // was truncated later, clipper.rs:2425-2448), so nothing is dropped; anything else takes the grouping code.
+  bool same = true;
+  {
+    const View& v0 = recs[(*out)[0].rec];
+    const uint32_t nc = v0.n_cigar();
+    const bool rev0 = v0.flags() & bam::kReverse;
+    for (size_t i = 1; i < n && same; ++i) {
+      const View& v = recs[(*out)[i].rec];
+      same = v.n_cigar() == nc && ((v.flags() & bam::kReverse) != 0) == rev0 && v0.cigar_in_bounds() && v.cigar_in_bounds() &&
+             std::memcmp(v.b + v.cigar_off(), v0.b + v0.cigar_off(), 4 * static_cast<size_t>(nc)) == 0;
+    }
+  }
+  if (!same) {
+    Prepared& pool = c->prepared[0];
+    pool.n = 0;
+    for (size_t i = 0; i < n; ++i) {
+      const View& v = recs[(*out)[i].rec];
+      if (pool.n == pool.srs.size()) pool.srs.emplace_back();
+      SourceRead& sr = pool.srs[pool.n++];
+      sr.bases.resize((*out)[i].final_len);                  // only the length and the CIGAR take part
+      bam::cigar_ops(v, &c->ops);
+      bam::simplify_cigar(c->ops, &sr.cigar);
+      if (v.flags() & bam::kReverse) std::reverse(sr.cigar.begin(), sr.cigar.end());
+      bam::truncate_cigar(&sr.cigar, (*out)[i].final_len);
+      sr.original_idx = static_cast<uint32_t>(i);
+      sr.flags = v.flags();
+    }
+    const size_t kept = filter_by_alignment_n(&pool.srs, pool.n);
+    if (kept != n) {
+      reject(c, FGB_STAT_REJ_MINORITY_ALIGNMENT, n - kept);
+      static thread_local std::vector<DRead> tmp;
+      tmp.clear();
+      for (size_t i = 0; i < kept; ++i) tmp.push_back((*out)[pool.srs[i].original_idx]);
+      out->assign(tmp.begin(), tmp.end());
+      n = kept;
+    }
+    if (n < min_reads) {
+      if (n) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, n);
+      return false;
+    }
+  }
+  *surviving = n;
+  return true;
+}
+
+inline uint32_t int_tag_width(uint32_t v) { return v <= 255u ? 1u : (v <= 65535u ? 2u : 4u); }   // tags.rs:533-553, v >= 0
+
+// Size of the simplex consensus record write_simplex_record_at produces (block_size word included).
+inline uint32_t simplex_record_size(const fgb_caller* c, uint32_t L, uint32_t umi_len, bool has_cell, uint32_t cell_len,
+                                    bool has_rx, uint32_t rx_len, uint32_t w_cd, uint32_t w_cm) {
+  const uint32_t name = static_cast<uint32_t>(c->prefix.size()) + 1u + umi_len;
+  uint32_t n = 4u + 32u + name + 1u + (L + 1u) / 2u + L;
+  n += 3u + static_cast<uint32_t>(c->rg.size()) + 1u;          // RG
+  n += 3u + w_cd + 3u + w_cm + 3u + 4u;                        // cD cM cE
+  if (c->opt.produce_per_base_tags) n += 2u * (3u + 1u + 4u + 2u * L);
+  n += 3u + umi_len + 1u;                                      // MI
+  if (has_cell) n += 3u + cell_len + 1u;
+  if (has_rx) n += 3u + rx_len + 1u;
+  return n;
+}
+
+void pack_direct_unit(fgb_caller* c, const uint8_t* stage, const std::vector<View>& recs, const std::vector<DRead>& rd,
+                      uint8_t read_type, StrRef umi) {
+  DirectPlan& P = c->dplan;
+  DUnit u;
+  u.n_reads = static_cast<uint32_t>(rd.size());
+  u.read_type = read_type;
+  u.umi = umi;
+  u.rx_begin = static_cast<uint32_t>(P.rx.size());
+  static thread_local std::vector<uint32_t> lens;
+  lens.clear();
+  for (const DRead& r : rd) {
+    const View& v = recs[r.rec];
+    fgb_raw_read rr;
+    rr.src_off = static_cast<uint64_t>(v.b - stage) + v.seq_off();
+    rr.raw_len = v.l_seq();
+    rr.flags = (v.flags() & bam::kReverse) ? FGB_RAW_REVERSE : 0u;
+    P.raws.push_back(rr);
+    P.lens.push_back(static_cast<uint16_t>(r.final_len));
+    P.row_bytes += round_up(r.final_len, FGB_READ_ALIGN);
+    lens.push_back(r.final_len);
+    if (r.rx) P.rx.push_back(StrRef{static_cast<uint64_t>(r.rx - stage), r.rx_len});
+  }
+  u.rx_n = static_cast<uint32_t>(P.rx.size()) - u.rx_begin;
+  const size_t kth = c->opt.min_reads - 1;                      // vanilla_caller.rs:1269-1277
+  std::nth_element(lens.begin(), lens.begin() + kth, lens.end(), std::greater<uint32_t>());
+  u.cons_len = lens[kth];
+  P.out_elems += round_up(u.cons_len, FGB_OUT_ALIGN);
+  if (c->opt.cell_tag[0] && !rd.empty()) {
+    const uint8_t* val; size_t n;
+    if (bam::find_string_tag(recs[rd[0].rec], c->opt.cell_tag, &val, &n)) {
+      u.has_cell = 1;
+      u.cell = StrRef{static_cast<uint64_t>(val - stage), static_cast<uint32_t>(n)};
+    }
+  }
+  if (u.n_reads <= 255u)                                        // cD / cM fit one byte whatever the vote says
+    u.rec_size = simplex_record_size(c, u.cons_len, umi.len, u.has_cell, u.cell.len, u.rx_n > 0,
+                                     u.rx_n ? P.rx[u.rx_begin].len : 0u, 1u, 1u);
+  P.units.push_back(u);
+}
+
+// consensus_reads for one MI group (vanilla_caller.rs:1477-1499 + process_group :1042-1114); `recs` are
+// views of the STAGED records.
+fgb_status direct_group_simplex(fgb_caller* c, const uint8_t* stage, const std::vector<View>& recs) {
+  const uint32_t n_records = static_cast<uint32_t>(recs.size());
+  const uint8_t* uv; size_t un;
+  if (!bam::find_string_tag(recs[0], c->opt.tag, &uv, &un)) {   // vanilla_caller.rs:1493-1496
+    c->last_error = std::string("Missing UMI tag '") + c->opt.tag[0] + c->opt.tag[1] + "'";
+    return FGB_ERR_MISSING_TAG;
+  }
+  const StrRef umi{static_cast<uint64_t>(uv - stage), static_cast<uint32_t>(un)};
+  for (const View& v : recs)
+    if (v.l_seq() > FGB_MAX_READ_LEN) {
+      c->last_error = "a read is longer than 65535 bases (FGB_MAX_READ_LEN)";
+      return FGB_ERR_UNIT_TOO_LARGE;
+    }
+  c->stats[FGB_STAT_TOTAL_READS] += n_records;
+  std::vector<uint32_t>&kept = c->scratch_idx[0], &frag = c->scratch_idx[1], &r1 = c->scratch_idx[2], &r2 = c->scratch_idx[3];
+  kept.clear(); frag.clear(); r1.clear(); r2.clear();
+  for (uint32_t i = 0; i < n_records; ++i) {
+    const uint16_t f = recs[i].flags();
+    if (!(f & bam::kSecondary) && !(f & bam::kSupplementary)) kept.push_back(i);
+  }
+  if (kept.size() != n_records) reject(c, FGB_STAT_REJ_SECONDARY_SUPPLEMENTARY, n_records - kept.size());
+  if (kept.empty()) return FGB_OK;
+  if (kept.size() < c->opt.min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, kept.size()); return FGB_OK; }
+  if (kept.size() > 0xFFFFu) {
+    c->last_error = "an MI group has more than 65535 reads";
+    return FGB_ERR_UNIT_TOO_LARGE;
+  }
+  for (uint32_t i : kept) {   // subgroup_reads, vanilla_caller.rs:1018-1039
+    const uint16_t f = recs[i].flags();
+    if (!(f & bam::kPaired)) frag.push_back(i);
+    else if (f & bam::kFirst) r1.push_back(i);
+    else if (f & bam::kLast) r2.push_back(i);
+  }
+  static thread_local std::vector<DRead> df, d1, d2;
+  size_t sf, s1, s2;
+  if (plan_subgroup(c, recs, frag, &df, &sf)) { pack_direct_unit(c, stage, recs, df, kFragment, umi); c->stats[FGB_STAT_CONSENSUS_READS] += 1; }
+  const bool ok1 = plan_subgroup(c, recs, r1, &d1, &s1);
+  const bool ok2 = plan_subgroup(c, recs, r2, &d2, &s2);
+  if (ok1 && ok2) {   // orphan rule, vanilla_caller.rs:1089-1108
+    pack_direct_unit(c, stage, recs, d1, kR1, umi);
+    pack_direct_unit(c, stage, recs, d2, kR2, umi);
+    c->stats[FGB_STAT_CONSENSUS_READS] += 2;
+  } else if (ok1) {
+    reject(c, FGB_STAT_REJ_ORPHAN_CONSENSUS, s1);
+  } else if (ok2) {
+    reject(c, FGB_STAT_REJ_ORPHAN_CONSENSUS, s2);
   }
   return FGB_OK;
 }
@@ -484,6 +738,368 @@ fgb_status flush_simplex(fgb_caller* c) {
   c->joined_len = total;
   c->out_is_joined = true;
   trace.mark("concatenate");
+  return FGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// simplex, direct path: flush
+// ------------------------------------------------------------------------------------------------
+// consensus_umis (simple_umi.rs:65-122, 236-245) over references into the staged records.
+bool consensus_umis_refs(const UmiBuilder& builder, const uint8_t* base, const StrRef* refs, uint32_t n, std::string* out) {
+  out->clear();
+  if (n == 0) return true;
+  if (n == 1) { out->assign(reinterpret_cast<const char*>(base + refs[0].off), refs[0].len); return true; }
+  const uint32_t len = refs[0].len;
+  for (uint32_t k = 1; k < n; ++k) if (refs[k].len != len) return false;
+  auto is_dna = [](uint8_t ch) {
+    switch (ch) { case 'A': case 'C': case 'G': case 'T': case 'N':
+                  case 'a': case 'c': case 'g': case 't': case 'n': return true; default: return false; }
+  };
+  static thread_local std::vector<uint8_t> col;
+  col.resize(n);
+  const uint8_t* first = base + refs[0].off;
+  for (uint32_t i = 0; i < len; ++i) {
+    size_t non_dna = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+      col[k] = base[refs[k].off + i];
+      if (!is_dna(col[k])) {
+        ++non_dna;
+        if (col[k] != first[i]) return false;
+      }
+    }
+    if (non_dna == 0) out->push_back(static_cast<char>(builder.call(col)));
+    else if (non_dna == n) out->push_back(static_cast<char>(first[i]));
+    else return false;
+  }
+  return true;
+}
+
+// Record encoder over a raw buffer whose size is known up front (UnmappedSamBuilder + tag encoders,
+// raw-bam builder.rs:90-230, tags.rs:512-667; the vector-backed twin is bam::Writer).
+struct RawWriter {
+  uint8_t* p;
+  void put(const void* s, size_t n) { std::memcpy(p, s, n); p += n; }
+  template <class T> void le(T v) { std::memcpy(p, &v, sizeof(T)); p += sizeof(T); }
+  void tag(const char t[2], char type) { p[0] = static_cast<uint8_t>(t[0]); p[1] = static_cast<uint8_t>(t[1]); p[2] = static_cast<uint8_t>(type); p += 3; }
+  void str(const char t[2], const void* v, size_t n) { tag(t, 'Z'); put(v, n); *p++ = 0; }
+  void integer(const char t[2], int32_t v) {
+    if (v >= -128 && v <= 127) { tag(t, 'c'); *p++ = static_cast<uint8_t>(static_cast<int8_t>(v)); }
+    else if (v >= 0 && v <= 255) { tag(t, 'C'); *p++ = static_cast<uint8_t>(v); }
+    else if (v >= 0 && v <= 65535) { tag(t, 'S'); le<uint16_t>(static_cast<uint16_t>(v)); }
+    else if (v >= -32768 && v <= 32767) { tag(t, 's'); le<int16_t>(static_cast<int16_t>(v)); }
+    else { tag(t, 'i'); le<int32_t>(v); }
+  }
+  void real(const char t[2], float v) { tag(t, 'f'); le<float>(v); }
+  template <class D> void i16_array(const char t[2], const D* v, uint32_t n) {   // values clamp to i16::MAX
+    tag(t, 'B'); *p++ = 's'; le<uint32_t>(n);
+    for (uint32_t i = 0; i < n; ++i) { const uint16_t x = v[i] > 32767 ? 32767 : static_cast<uint16_t>(v[i]); std::memcpy(p + 2 * i, &x, 2); }
+    p += 2 * static_cast<size_t>(n);
+  }
+};
+
+// build_consensus_record_into (vanilla_caller.rs:1365-1473) at `dst`; returns the bytes written (block_size
+// word included), 0 with *err set when the reference would have failed.
+template <class D>
+size_t write_simplex_record_at(const fgb_caller* c, uint8_t* dst, const DUnit& u, const StrRef* rx, const uint8_t* stage,
+                               const uint8_t* bases, const uint8_t* quals, const D* depths, const D* errors,
+                               std::string* rx_scratch, std::string* err) {
+  static const bam::Writer::CodeTable kCodes;
+  const uint32_t L = u.cons_len;
+  const size_t name_len = c->prefix.size() + 1 + u.umi.len;
+  if (name_len >= 255) { *err = "read name too long"; return 0; }
+  uint16_t flag = bam::kUnmapped;
+  if (u.read_type == kR1) flag |= bam::kPaired | bam::kFirst | bam::kMateUnmapped;
+  else if (u.read_type == kR2) flag |= bam::kPaired | bam::kLast | bam::kMateUnmapped;
+  RawWriter w{dst + 4};
+  w.le<int32_t>(-1); w.le<int32_t>(-1);
+  *w.p++ = static_cast<uint8_t>(name_len + 1);
+  *w.p++ = 0;
+  w.le<uint16_t>(4680); w.le<uint16_t>(0); w.le<uint16_t>(flag); w.le<uint32_t>(L);
+  w.le<int32_t>(-1); w.le<int32_t>(-1); w.le<int32_t>(0);
+  w.put(c->prefix.data(), c->prefix.size());
+  *w.p++ = ':';
+  w.put(stage + u.umi.off, u.umi.len);
+  *w.p++ = 0;
+  {
+    uint8_t* sp = w.p;
+    for (uint32_t i = 0; i + 1 < L; i += 2) sp[i >> 1] = static_cast<uint8_t>((kCodes.t[bases[i]] << 4) | kCodes.t[bases[i + 1]]);
+    if (L & 1) sp[L >> 1] = static_cast<uint8_t>(kCodes.t[bases[L - 1]] << 4);
+    w.p += (static_cast<size_t>(L) + 1) / 2;
+    if (L) w.put(quals, L);
+  }
+  w.str("RG", c->rg.data(), c->rg.size());
+  uint32_t max_d = 0, min_d = L ? 0xFFFFFFFFu : 0;
+  uint64_t tot_e = 0, tot_d = 0;
+  for (uint32_t k = 0; k < L; ++k) {
+    const uint32_t d = depths[k];
+    max_d = d > max_d ? d : max_d;
+    min_d = d < min_d ? d : min_d;
+    tot_e += errors[k];
+    tot_d += d;
+  }
+  w.integer("cD", static_cast<int32_t>(max_d));
+  w.integer("cM", static_cast<int32_t>(min_d));
+  w.real("cE", error_rate(tot_e, tot_d));
+  if (c->opt.produce_per_base_tags) {
+    w.i16_array("cd", depths, L);
+    w.i16_array("ce", errors, L);
+  }
+  w.str("MI", stage + u.umi.off, u.umi.len);
+  if (u.has_cell) w.str(c->opt.cell_tag, stage + u.cell.off, u.cell.len);
+  if (u.rx_n) {
+    if (!consensus_umis_refs(c->umi_builder, stage, rx, u.rx_n, rx_scratch)) {   // the reference panics here (simple_umi.rs:78-116)
+      *err = "RX values of a family have different lengths or mix DNA and non-DNA characters";
+      return 0;
+    }
+    w.str("RX", rx_scratch->data(), rx_scratch->size());
+  }
+  const size_t total = static_cast<size_t>(w.p - dst);
+  const uint32_t bs = static_cast<uint32_t>(total - 4);
+  std::memcpy(dst, &bs, 4);
+  return total;
+}
+
+fgb_status flush_simplex_direct(fgb_caller* c) {
+  PhaseTrace trace;
+  // ---- global layout: prefix sums over the segments ----
+  const size_t NS = c->segs.size();
+  std::vector<uint64_t> ub(NS + 1, 0), rbase(NS + 1, 0), bb(NS + 1, 0), ob(NS + 1, 0);
+  uint32_t max_reads = 0;
+  for (size_t i = 0; i < NS; ++i) {
+    const DSeg& sg = c->segs[i];
+    ub[i + 1] = ub[i] + (sg.u1 - sg.u0);
+    rbase[i + 1] = rbase[i] + (sg.r1 - sg.r0);
+    bb[i + 1] = bb[i] + sg.row_bytes;
+    ob[i + 1] = ob[i] + sg.out_elems;
+  }
+  const uint64_t U = ub[NS], R = rbase[NS], n_bytes = bb[NS], no = ob[NS];
+  if (!U) return FGB_OK;
+  if (U >= 0xFFFFFFFFull || R >= 0xFFFFFFFFull) { c->last_error = "batch too large"; return FGB_ERR_INVALID_ARG; }
+  if (c->d_reads.ensure((R + 2) * sizeof(uint64_t)) != FGB_OK || c->d_raws.ensure((R + 1) * sizeof(fgb_raw_read)) != FGB_OK ||
+      c->d_units.ensure((U + 1) * sizeof(fgb_unit)) != FGB_OK) { c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM; }
+  uint64_t* g_reads = static_cast<uint64_t*>(c->d_reads.p);
+  fgb_raw_read* g_raws = static_cast<fgb_raw_read*>(c->d_raws.p);
+  fgb_unit* g_units = static_cast<fgb_unit*>(c->d_units.p);
+  const uint32_t T = std::max<uint32_t>(1u, std::min<uint32_t>(std::max<uint32_t>(c->opt.n_threads, 1u), static_cast<uint32_t>(NS)));
+  std::vector<uint32_t> seg_max(NS, 0);
+  auto for_segs = [&](const std::function<void(size_t)>& fn) {
+    if (T <= 1) { for (size_t i = 0; i < NS; ++i) fn(i); return; }
+    run_parallel(c, T, [&](uint32_t t) { for (size_t i = t; i < NS; i += T) fn(i); });
+  };
+  for_segs([&](size_t i) {       // descriptors of segment i at their global places
+    const DSeg& sg = c->segs[i];
+    const DirectPlan& P = sg.ctx->dplan;
+    uint64_t off = bb[i], oo = ob[i], r = rbase[i];
+    uint64_t lr = sg.r0;
+    uint32_t mx = 0;
+    for (uint32_t u = sg.u0; u < sg.u1; ++u) {
+      const DUnit& du = P.units[u];
+      fgb_unit gu;
+      gu.out_off = oo; gu.read_begin = static_cast<uint32_t>(r); gu.cons_len = du.cons_len;
+      g_units[ub[i] + (u - sg.u0)] = gu;
+      oo += round_up(du.cons_len, FGB_OUT_ALIGN);
+      mx = du.n_reads > mx ? du.n_reads : mx;
+      for (uint32_t k = 0; k < du.n_reads; ++k, ++lr, ++r) {
+        const uint32_t len = P.lens[lr];
+        g_reads[r] = FGB_READ_DESC(off, len);
+        g_raws[r] = P.raws[lr];
+        off += round_up(len, FGB_READ_ALIGN);
+      }
+    }
+    seg_max[i] = mx;
+  });
+  {
+    fgb_unit sentinel;
+    sentinel.out_off = no; sentinel.read_begin = static_cast<uint32_t>(R); sentinel.cons_len = 0;
+    g_units[U] = sentinel;
+    g_reads[R] = 0; g_reads[R + 1] = 0;
+  }
+  for (uint32_t m : seg_max) max_reads = m > max_reads ? m : max_reads;
+  trace.mark("descriptors");
+  // ---- tiles: every segment plans its own range (a tile never spans two segments) ----
+  std::vector<std::vector<fgb_tile>> seg_tiles(NS);
+  std::vector<fgb_status> seg_st(NS, FGB_OK);
+  for_segs([&](size_t i) {
+    uint64_t prev_end = bb[i];
+    seg_tiles[i].clear();
+    seg_st[i] = plan_tiles_range(g_units, ub[i], ub[i + 1], g_reads, R, &prev_end, [&](const fgb_tile& t) { seg_tiles[i].push_back(t); });
+  });
+  size_t n_tiles = 0;
+  for (size_t i = 0; i < NS; ++i) {
+    if (seg_st[i] != FGB_OK) { c->last_error = "tile planning failed"; return seg_st[i]; }
+    n_tiles += seg_tiles[i].size();
+  }
+  std::vector<fgb_tile> tiles;
+  tiles.reserve(n_tiles + 1);
+  for (size_t i = 0; i < NS; ++i) tiles.insert(tiles.end(), seg_tiles[i].begin(), seg_tiles[i].end());
+  trace.mark("tiles");
+  // ---- output columns (page-locked, grow-only); depth / errors travel as bytes when no unit is deeper than 255 ----
+  const bool narrow = max_reads <= 255u;
+  if (c->pinned_cap < no + 8) {
+    for (void*& p : c->pinned) { fgb_host_free(p); p = nullptr; }
+    c->pinned_cap = 0;
+    const size_t cap = (no + 8) + (no + 8) / 4;
+    const size_t bytes[4] = {cap, cap, cap * 2, cap * 2};
+    for (int i = 0; i < 4; ++i)
+      if (fgb_host_alloc(&c->pinned[i], bytes[i]) != FGB_OK) { c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM; }
+    c->pinned_cap = cap;
+  }
+  uint8_t* const o_base = static_cast<uint8_t*>(c->pinned[0]);
+  uint8_t* const o_qual = static_cast<uint8_t*>(c->pinned[1]);
+  fgb_batch b;
+  std::memset(&b, 0, sizeof(b));
+  b.n_units = U; b.n_reads = R; b.n_bytes = n_bytes; b.n_out = no; b.n_tiles = n_tiles;
+  b.reads = g_reads; b.units = g_units; b.tiles = tiles.data();
+  fgb_columns cols{o_base, o_qual, static_cast<uint16_t*>(c->pinned[2]), static_cast<uint16_t*>(c->pinned[3])};
+  fgb_record_columns rc;
+  std::memset(&rc, 0, sizeof(rc));
+  rc.n_bytes = c->stage_len; rc.records = static_cast<const uint8_t*>(c->stage.p); rc.raw_reads = g_raws;
+  rc.min_input_base_quality = c->prep_opt.min_input_base_quality;
+  std::vector<uint8_t> fstatus;
+  std::vector<uint32_t> fmasked;
+  fgb_filter_params fp = c->opt.filter;
+  fgb_submit_options so;
+  std::memset(&so, 0, sizeof(so));
+  so.input_format = FGB_IN_RECORDS; so.output_format = narrow ? FGB_OUT_U8 : FGB_OUT_U16;
+  so.records = &rc;
+  if (c->opt.filter_enabled) {   // `fgumi filter` as an epilogue of the vote (commands/filter.rs:738-905)
+    fstatus.assign(U + 1, FGB_FILTER_PASS);
+    fmasked.assign(U + 1, 0);
+    fp.per_base_tags = c->opt.produce_per_base_tags;
+    so.filter = &fp; so.unit_status = fstatus.data(); so.unit_masked = fmasked.data();
+  }
+  fgb_status st = fgb_submit_ex(c->h, &b, &cols, &so);
+  if (st == FGB_OK) st = fgb_wait(c->h);
+  if (st != FGB_OK) {
+    char buf[256];
+    fgb_last_error(c->h, buf, sizeof(buf));
+    c->last_error = buf;
+    return st;
+  }
+  trace.mark("submit + wait");
+  const uint8_t* const stage = static_cast<const uint8_t*>(c->stage.p);
+  // ---- which units are emitted (template rule of the filter, commands/filter.rs:640-672: the consecutive
+  //      units of one MI are emitted only if every one of them passed) ----
+  std::vector<char> emit;
+  auto unit_at = [&](uint64_t g, const DirectPlan** P) -> const DUnit& {
+    const size_t i = static_cast<size_t>(std::upper_bound(ub.begin(), ub.end(), g) - ub.begin()) - 1;
+    *P = &c->segs[i].ctx->dplan;
+    return (*P)->units[c->segs[i].u0 + (g - ub[i])];
+  };
+  if (c->opt.filter_enabled) {
+    emit.assign(U, 1);
+    for (uint64_t i = 0; i < U;) {
+      const DirectPlan* P0; const DUnit& u0 = unit_at(i, &P0);
+      uint64_t j = i;
+      bool pass = true;
+      while (j < U) {
+        const DirectPlan* Pj; const DUnit& uj = unit_at(j, &Pj);
+        if (uj.umi.len != u0.umi.len || std::memcmp(stage + uj.umi.off, stage + u0.umi.off, u0.umi.len) != 0) break;
+        pass = pass && fstatus[j] == FGB_FILTER_PASS;
+        ++j;
+      }
+      for (uint64_t k = i; k < j; ++k) {
+        emit[k] = pass;
+        c->stats[FGB_STAT_FILTER_RECORDS] += 1;
+        c->stats[FGB_STAT_FILTER_BASES_MASKED] += fmasked[k];
+        if (pass) c->stats[FGB_STAT_FILTER_PASSED] += 1;
+      }
+      i = j;
+    }
+  }
+  // ---- build_consensus_record_into (vanilla_caller.rs:1365-1473): pieces of segments, sized first, then
+  //      written at their final place in one output buffer ----
+  struct Piece { size_t seg; uint32_t u0, u1; uint64_t g0; size_t bytes; uint64_t count; };
+  std::vector<Piece> pieces;
+  {
+    const uint64_t want = std::max<uint64_t>(256, U / (std::max<uint32_t>(c->opt.n_threads, 1u) * 4u) + 1);
+    for (size_t i = 0; i < NS; ++i) {
+      const DSeg& sg = c->segs[i];
+      for (uint32_t u = sg.u0; u < sg.u1;) {
+        const uint32_t e = static_cast<uint32_t>(std::min<uint64_t>(sg.u1, static_cast<uint64_t>(u) + want));
+        pieces.push_back(Piece{i, u, e, ub[i] + (u - sg.u0), 0, 0});
+        u = e;
+      }
+    }
+  }
+  const uint32_t TP = std::max<uint32_t>(1u, std::min<uint32_t>(std::max<uint32_t>(c->opt.n_threads, 1u), static_cast<uint32_t>(pieces.size())));
+  auto for_pieces = [&](const std::function<void(size_t)>& fn) {
+    if (TP <= 1) { for (size_t i = 0; i < pieces.size(); ++i) fn(i); return; }
+    run_parallel(c, TP, [&](uint32_t t) {       // contiguous runs of pieces per thread
+      const size_t a = pieces.size() * t / TP, e = pieces.size() * (t + 1) / TP;
+      for (size_t i = a; i < e; ++i) fn(i);
+    });
+  };
+  auto depth_stats = [&](uint64_t out_off, uint32_t L, uint32_t* mx, uint32_t* mn) {
+    uint32_t a = 0, m = L ? 0xFFFFFFFFu : 0;
+    if (narrow) { const uint8_t* d = static_cast<const uint8_t*>(c->pinned[2]) + out_off; for (uint32_t k = 0; k < L; ++k) { a = d[k] > a ? d[k] : a; m = d[k] < m ? d[k] : m; } }
+    else { const uint16_t* d = static_cast<const uint16_t*>(c->pinned[2]) + out_off; for (uint32_t k = 0; k < L; ++k) { a = d[k] > a ? d[k] : a; m = d[k] < m ? d[k] : m; } }
+    *mx = a; *mn = m;
+  };
+  for_pieces([&](size_t pi) {                     // pass 1: sizes
+    Piece& pc = pieces[pi];
+    const DirectPlan& P = c->segs[pc.seg].ctx->dplan;
+    size_t bytes = 0; uint64_t count = 0;
+    for (uint32_t u = pc.u0; u < pc.u1; ++u) {
+      const uint64_t g = pc.g0 + (u - pc.u0);
+      if (!emit.empty() && !emit[g]) continue;
+      const DUnit& du = P.units[u];
+      uint32_t sz = du.rec_size;
+      if (!sz) {
+        uint32_t mx, mn;
+        depth_stats(g_units[g].out_off, du.cons_len, &mx, &mn);
+        sz = simplex_record_size(c, du.cons_len, du.umi.len, du.has_cell, du.cell.len, du.rx_n > 0,
+                                 du.rx_n ? P.rx[du.rx_begin].len : 0u, int_tag_width(mx), int_tag_width(mn));
+      }
+      bytes += sz; ++count;
+    }
+    pc.bytes = bytes; pc.count = count;
+  });
+  size_t total = 0;
+  std::vector<size_t> at(pieces.size() + 1, 0);
+  for (size_t i = 0; i < pieces.size(); ++i) { at[i] = total; total += pieces[i].bytes; c->out_count += pieces[i].count; }
+  if (c->joined_cap < total + 64) {
+    std::free(c->joined);
+    c->joined_cap = total + total / 4 + 4096;
+    c->joined = static_cast<uint8_t*>(std::malloc(c->joined_cap));
+    if (!c->joined) { c->joined_cap = 0; c->last_error = "out of memory"; return FGB_ERR_NOMEM; }
+  }
+  std::vector<fgb_status> pst(pieces.size(), FGB_OK);
+  std::vector<std::string> perr(TP);
+  trace.mark("sizes");
+  for_pieces([&](size_t pi) {                     // pass 2: the records
+    const Piece& pc = pieces[pi];
+    const DirectPlan& P = c->segs[pc.seg].ctx->dplan;
+    static thread_local std::string rx, err;
+    uint8_t* dst = c->joined + at[pi];
+    uint8_t* const end = dst + pc.bytes;
+    for (uint32_t u = pc.u0; u < pc.u1; ++u) {
+      const uint64_t g = pc.g0 + (u - pc.u0);
+      if (!emit.empty() && !emit[g]) continue;
+      const DUnit& du = P.units[u];
+      const uint64_t oo = g_units[g].out_off;
+      size_t n;
+      if (narrow) n = write_simplex_record_at<uint8_t>(c, dst, du, P.rx.data() + du.rx_begin, stage, o_base + oo, o_qual + oo,
+                                                       static_cast<const uint8_t*>(c->pinned[2]) + oo,
+                                                       static_cast<const uint8_t*>(c->pinned[3]) + oo, &rx, &err);
+      else n = write_simplex_record_at<uint16_t>(c, dst, du, P.rx.data() + du.rx_begin, stage, o_base + oo, o_qual + oo,
+                                                 static_cast<const uint16_t*>(c->pinned[2]) + oo,
+                                                 static_cast<const uint16_t*>(c->pinned[3]) + oo, &rx, &err);
+      if (!n) { pst[pi] = FGB_ERR_INVALID_ARG; return; }
+      dst += n;
+      if (dst > end) { pst[pi] = FGB_ERR_INVALID_ARG; return; }      // cannot happen: sizes come from the same formula
+    }
+    if (dst != end) pst[pi] = FGB_ERR_INVALID_ARG;
+  });
+  for (size_t i = 0; i < pieces.size(); ++i)
+    if (pst[i] != FGB_OK) {
+      c->last_error = "consensus record assembly failed (read name too long, or RX values of a family have different "
+                      "lengths or mix DNA and non-DNA characters)";
+      return pst[i];
+    }
+  c->joined_len = total;
+  c->out_is_joined = true;
+  trace.mark("assemble");
   return FGB_OK;
 }
 
@@ -1225,6 +1841,11 @@ fgb_status flush_codec(fgb_caller* c) {
 
 }  // namespace
 
+namespace {
+fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off, const uint64_t* group_rec,
+                      uint64_t n_groups);
+}
+
 extern "C" {
 
 fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_caller** out) {
@@ -1275,6 +1896,9 @@ fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_call
   if (device != FGB_DEVICE_NONE) {       // FGB_DEVICE_NONE: planning only, flush refuses (no CPU fallback)
     fgb_status st = fgb_create(device, &p, &c->h);
     if (st != FGB_OK) return st;
+    // simplex callers with a device build the source-read rows on the device (FGB_CALLER_LEGACY=1 keeps the
+    // host decode; planning-only callers always use it, so the packed rows can be inspected)
+    c->direct = opt->mode == FGB_MODE_SIMPLEX && std::getenv("FGB_CALLER_LEGACY") == nullptr;
   }
   *out = c.release();
   return FGB_OK;
@@ -1303,6 +1927,7 @@ fgb_status fgb_caller_pending(const fgb_caller* c, fgb_batch* batch, const fgb_d
 void fgb_caller_destroy(fgb_caller* c) {
   if (!c) return;
   for (void* p : c->pinned) fgb_host_free(p);
+  c->stage.release(); c->d_reads.release(); c->d_raws.release(); c->d_units.release();
   std::free(c->joined);
   fgb_destroy(c->h);
   delete c;
@@ -1322,9 +1947,14 @@ fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uin
                                 uint32_t n_records) {
   if (!c || (n_records && (!records || !rec_off))) return FGB_ERR_INVALID_ARG;
   if (n_records == 0) return FGB_OK;
+  if (c->direct) {
+    const uint64_t grp[2] = {0, n_records};
+    return direct_add(c, records, rec_off, grp, 1);
+  }
   std::vector<View> recs;
   recs.reserve(n_records);
   for (uint32_t i = 0; i < n_records; ++i) {
+    if (rec_off[i + 1] < rec_off[i]) { c->last_error = "record offsets must ascend"; return FGB_ERR_LAYOUT; }
     size_t len = static_cast<size_t>(rec_off[i + 1] - rec_off[i]);
     if (len < 32) { c->last_error = "BAM record shorter than its fixed header"; return FGB_ERR_INVALID_ARG; }
     recs.emplace_back(records + rec_off[i], len);
@@ -1476,12 +2106,120 @@ void merge_workers_parallel(fgb_caller* c, uint32_t T) {
 
 }  // namespace
 
+namespace {
+
+// The direct path's add: stages the records of groups [0, n_groups) (one contiguous slice of the blob) in
+// page-locked memory and plans them, on options.n_threads threads over contiguous ranges of groups.  All or
+// nothing: on an error nothing of this call stays queued (the same for one thread and for many).
+fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off, const uint64_t* group_rec,
+                      uint64_t n_groups) {
+  const uint64_t rec0 = group_rec[0], rec1 = group_rec[n_groups];
+  if (rec1 < rec0) { c->last_error = "bad group_rec table"; return FGB_ERR_INVALID_ARG; }
+  const uint64_t b0 = rec_off[rec0], b1 = rec_off[rec1];
+  if (b1 < b0) { c->last_error = "record offsets must ascend"; return FGB_ERR_LAYOUT; }
+  const size_t dst0 = round_up(c->stage_len, 64);
+  if (c->stage.ensure(dst0 + (b1 - b0) + 256, c->stage_len) != FGB_OK) { c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM; }
+  uint8_t* const stage = static_cast<uint8_t*>(c->stage.p);
+  const uint64_t n_rec = rec1 - rec0;
+  const uint32_t T = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint32_t>(c->opt.n_threads, 1u), (n_groups + 63) / 64));
+  if (T > 1) ensure_workers(c, T);
+  std::vector<uint64_t> cut(T + 1, n_groups);
+  cut[0] = 0;
+  for (uint32_t t = 1; t < T; ++t) {          // contiguous ranges balanced by record count
+    const uint64_t target = rec0 + n_rec * t / T;
+    cut[t] = static_cast<uint64_t>(std::lower_bound(group_rec, group_rec + n_groups, target) - group_rec);
+    if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+  }
+  std::vector<fgb_caller*> ctx(T);
+  std::vector<DMark> mark(T);
+  for (uint32_t t = 0; t < T; ++t) {
+    ctx[t] = T > 1 ? c->workers[t].get() : c;
+    const DirectPlan& P = ctx[t]->dplan;
+    mark[t] = DMark{P.raws.size(), P.units.size(), P.rx.size(), P.row_bytes, P.out_elems};
+  }
+  uint64_t stats0[FGB_NSTATS];
+  std::memcpy(stats0, c->stats, sizeof(stats0));
+  const overlap::Stats ostats0 = c->overlap.stats;
+  std::vector<fgb_status> sts(T, FGB_OK);
+  auto run = [&](uint32_t t) {
+    fgb_caller* x = ctx[t];
+    const uint64_t g0 = cut[t], g1 = cut[t + 1];
+    if (g0 >= g1) return;
+    const uint64_t s0 = rec_off[group_rec[g0]], s1 = rec_off[group_rec[g1]];
+    if (s1 < s0 || s0 < b0 || s1 > b1) { x->last_error = "record offsets must ascend"; sts[t] = FGB_ERR_LAYOUT; return; }
+    std::memcpy(stage + dst0 + (s0 - b0), records + s0, s1 - s0);
+    for (uint64_t g = g0; g < g1; ++g) {
+      const uint64_t r0 = group_rec[g], r1 = group_rec[g + 1];
+      if (r1 < r0 || r1 - r0 > 0xFFFFFFFFull || r1 > rec1) { x->last_error = "bad group_rec table"; sts[t] = FGB_ERR_INVALID_ARG; return; }
+      const uint32_t n = static_cast<uint32_t>(r1 - r0);
+      if (n == 0) continue;
+      x->views.clear();
+      for (uint64_t r = r0; r < r1; ++r) {
+        if (rec_off[r + 1] < rec_off[r] || rec_off[r + 1] > s1) { x->last_error = "record offsets must ascend"; sts[t] = FGB_ERR_LAYOUT; return; }
+        const size_t len = static_cast<size_t>(rec_off[r + 1] - rec_off[r]);
+        if (len < 32) { x->last_error = "BAM record shorter than its fixed header"; sts[t] = FGB_ERR_INVALID_ARG; return; }
+        x->views.emplace_back(stage + dst0 + (rec_off[r] - b0), len);
+        if (x->views.back().aux_off() > len) { x->last_error = "truncated BAM record"; sts[t] = FGB_ERR_INVALID_ARG; return; }
+      }
+      if (c->opt.consensus_call_overlapping_bases) {   // simplex.rs:395-398: in place, on the staged copy
+        x->rel_off.resize(n + 1);
+        for (uint32_t i = 0; i <= n; ++i) x->rel_off[i] = rec_off[r0 + i] - rec_off[r0];
+        x->overlap.apply_group(stage + dst0 + (rec_off[r0] - b0), x->rel_off.data(), n);
+      }
+      const fgb_status st = direct_group_simplex(x, stage, x->views);
+      if (st != FGB_OK) { sts[t] = st; return; }
+    }
+  };
+  if (T > 1) run_parallel(c, T, run); else run(0);
+  fgb_status first = FGB_OK;
+  for (uint32_t t = 0; t < T && first == FGB_OK; ++t)
+    if (sts[t] != FGB_OK) { first = sts[t]; if (ctx[t] != c) c->last_error = ctx[t]->last_error; }
+  if (first != FGB_OK) {                      // roll everything of this call back
+    for (uint32_t t = 0; t < T; ++t) {
+      DirectPlan& P = ctx[t]->dplan;
+      P.raws.resize(mark[t].raws); P.lens.resize(mark[t].raws); P.units.resize(mark[t].units); P.rx.resize(mark[t].rx);
+      P.row_bytes = mark[t].row_bytes; P.out_elems = mark[t].out_elems;
+      if (ctx[t] != c) { std::memset(ctx[t]->stats, 0, sizeof(ctx[t]->stats)); ctx[t]->overlap.stats = overlap::Stats(); }
+    }
+    std::memcpy(c->stats, stats0, sizeof(stats0));
+    c->overlap.stats = ostats0;
+    return first;
+  }
+  for (uint32_t t = 0; t < T; ++t) {
+    fgb_caller* x = ctx[t];
+    const DirectPlan& P = x->dplan;
+    if (P.units.size() > mark[t].units) {
+      DSeg sg{x, static_cast<uint32_t>(mark[t].units), static_cast<uint32_t>(P.units.size()), mark[t].raws, P.raws.size(),
+              P.row_bytes - mark[t].row_bytes, P.out_elems - mark[t].out_elems};
+      if (!c->segs.empty() && c->segs.back().ctx == x && c->segs.back().u1 == sg.u0) {   // serial add_group calls
+        DSeg& l = c->segs.back();
+        l.u1 = sg.u1; l.r1 = sg.r1; l.row_bytes += sg.row_bytes; l.out_elems += sg.out_elems;
+      } else {
+        c->segs.push_back(sg);
+      }
+    }
+    if (x != c) {
+      for (int i = 0; i < FGB_NSTATS; ++i) { c->stats[i] += x->stats[i]; x->stats[i] = 0; }
+      c->overlap.stats.overlapping_bases += x->overlap.stats.overlapping_bases;
+      c->overlap.stats.bases_agreeing += x->overlap.stats.bases_agreeing;
+      c->overlap.stats.bases_disagreeing += x->overlap.stats.bases_disagreeing;
+      c->overlap.stats.bases_corrected += x->overlap.stats.bases_corrected;
+      x->overlap.stats = overlap::Stats();
+    }
+  }
+  c->stage_len = dst0 + (b1 - b0);
+  return FGB_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
                                  const uint64_t* group_rec, uint64_t n_groups) {
   if (!c || (n_groups && (!records || !rec_off || !group_rec))) return FGB_ERR_INVALID_ARG;
   if (n_groups == 0) return FGB_OK;
+  if (c->direct) return direct_add(c, records, rec_off, group_rec, n_groups);
   const uint64_t n_rec = group_rec[n_groups] - group_rec[0];
   uint32_t T = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint32_t>(c->opt.n_threads, 1u), (n_groups + 63) / 64));
   auto run = [&](fgb_caller* dst, uint64_t g0, uint64_t g1, uint64_t* bad_group) -> fgb_status {
@@ -1531,7 +2269,14 @@ fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* o
     return FGB_ERR_NO_DEVICE;
   }
   fgb_status st = c->opt.mode == FGB_MODE_DUPLEX ? flush_duplex(c)
-                  : c->opt.mode == FGB_MODE_CODEC ? flush_codec(c) : flush_simplex(c);
+                  : c->opt.mode == FGB_MODE_CODEC ? flush_codec(c)
+                  : c->direct ? flush_simplex_direct(c) : flush_simplex(c);
+  if (c->direct) {
+    c->dplan.clear();
+    for (auto& w : c->workers) w->dplan.clear();
+    c->segs.clear();
+    c->stage_len = 0;
+  }
   c->pack.clear(); c->metas.clear(); c->molecules.clear(); c->jobs.clear();
   c->codec_molecules.clear(); c->codec_jobs.clear();
   c->n_duplex_out = 0; c->n_codec_out = 0;
@@ -1775,6 +2520,7 @@ uint32_t fgb_struct_size(uint32_t id) {
     case 6: return sizeof(fgb_codec_params);
     case 7: return sizeof(fgb_params);
     case 8: return sizeof(fgb_duplex_filter_params);
+    case 9: return sizeof(fgb_record_columns);
     default: return 0;
   }
 }

@@ -28,6 +28,7 @@ inline fgb_status plan_tiles_range(const fgb_unit* units, uint64_t u_begin, uint
   uint32_t reg_len = 0;
   uint64_t reg_next = 0;      // where the next row must start for the tile to stay regular
   uint32_t max_reads_in_unit = 0;
+  uint32_t cur_class = 0;     // class of the open tile (fgb_config.h unit_class)
   auto emit = [&]() {
     cur.byte_len = static_cast<uint32_t>(((cur_end + 15u) & ~15ull) - cur.byte_begin);
     if (cur.flags & kTileFlagDirect) { cur.byte_len = 0; }
@@ -40,6 +41,7 @@ inline fgb_status plan_tiles_range(const fgb_unit* units, uint64_t u_begin, uint
       }
       if (max_reads_in_unit <= 64) cur.flags |= kTileFlagShallow;
     }
+    cur.flags |= cur_class << kTileClassShift;
     emit_tile(cur);
     open = false;
   };
@@ -74,7 +76,7 @@ inline fgb_status plan_tiles_range(const fgb_unit* units, uint64_t u_begin, uint
     if (open) {
       uint64_t span = ((ue + 15u) & ~15ull) - cur.byte_begin;
       uint32_t skew = cur.read_begin & 1u;
-      bool fits = !(cur.flags & kTileFlagDirect) && span <= kTileCapBytes &&
+      bool fits = !(cur.flags & kTileFlagDirect) && span <= kTileCapBytes && unit_class(nr) == cur_class &&
                   cur.n_units + 1 <= kTileMaxUnits &&
                   cur.n_reads + nr + skew <= kTileMaxReads;
       if (!fits) emit();
@@ -93,6 +95,7 @@ inline fgb_status plan_tiles_range(const fgb_unit* units, uint64_t u_begin, uint
       reg_len = nr ? FGB_READ_LEN(reads[un.read_begin]) : 0;
       reg_next = ub;
       max_reads_in_unit = 0;
+      cur_class = unit_class(nr);
     }
     if (regular) {   // still regular with this unit?
       const uint64_t stride = (static_cast<uint64_t>(reg_len) + 7u) & ~7ull;

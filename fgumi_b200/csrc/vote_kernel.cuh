@@ -488,6 +488,14 @@ __device__ __forceinline__ uint32_t acgt_bytes(uint32_t x) {
   return (in0246 & ~is4) | isT;
 }
 
+// 0x80 in every byte of `sum` (bytes <= 255) that is >= t (t <= 255)
+__device__ __forceinline__ uint32_t bytes_ge(uint32_t sum, uint32_t t) {
+  const uint32_t add = (0x100u - t) * 0x00010001u;
+  const uint32_t ev = ((sum & 0x00FF00FFu) + add) & 0x01000100u;          // bytes 0, 2 -> bits 8, 24
+  const uint32_t od = (((sum >> 8) & 0x00FF00FFu) + add) & 0x01000100u;   // bytes 1, 3
+  return (ev >> 1) | (od << 7);
+}
+
 // Resolve one undecided position: integer proof first, the literal f64 algorithm otherwise.
 template <class M>
 __device__ __forceinline__ Called resolve_position(const TileView<M>& tv, const VoteSmem& S,
@@ -654,7 +662,10 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
 // Regular tiles (planner flag): every read of the tile has the same length L, rows are packed back
 // to back at stride round_up(L, 8) and every unit calls L positions.  The read descriptors are then
 // redundant for the scan: read r of the tile starts at word (r - tile.read_begin) * m, m = stride/8.
-template <class M, bool Regular>
+// V = 0: the general kernel; V = 1: the shallow-class kernel (tiles whose units have at most four reads):
+// two-read units take the pair table in line, three- and four-read units prove the fast path through the
+// SUM of the qualities (host_tables.cpp sumt) instead of their minimum.
+template <class M, bool Regular, int V = 0>
 __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const Stage& st,
                                           const TileView<M>& tv, uint32_t vt, uint32_t warp,
                                           uint32_t n_items, LocalStats& ls) {
@@ -755,11 +766,110 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
       wq_lo = static_cast<uint32_t>(oqw); wq_hi = static_cast<uint32_t>(oqw >> 32);
       dep = make_uint4(static_cast<uint32_t>(odw_lo), static_cast<uint32_t>(odw_lo >> 32),
                        static_cast<uint32_t>(odw_hi), static_cast<uint32_t>(odw_hi >> 32));
+    } else if (V == 1 && n == 2u && min_reads <= 2u) {
+      // two-read units: where both reads cover the position and agree on an A/C/G/T base, the result is the
+      // host-evaluated outcome of the reference's add / add / call sequence (host_tables.cpp pair_quality)
+      typename M::off_t ra, rc;
+      uint32_t l0, l1;
+      if (Regular) {
+        ra = reg_row0 + reg_word * 8u; rc = ra + uni_m * 8u; l0 = l1 = reg_len;
+      } else {
+        typename M::addr_t rd = tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u;
+        const uint64_t d0 = M::ld64(rd), d1 = M::ld64(rd + 8u);
+        l0 = static_cast<uint32_t>(d0) & 0xFFFFu; l1 = static_cast<uint32_t>(d1) & 0xFFFFu;
+        ra = M::row_offset(d0, tv.byte_base, base32) + (l0 > p0 ? p0 : 0u);
+        rc = M::row_offset(d1, tv.byte_base, base32) + (l1 > p0 ? p0 : 0u);
+      }
+      const uint64_t b0w = M::ld64(tv.bases + ra), b1w = M::ld64(tv.bases + rc);
+      const uint64_t q0w = M::ld64(tv.quals + ra), q1w = M::ld64(tv.quals + rc);
+      const uint32_t ml = l0 < l1 ? l0 : l1;
+      const uint32_t covered = ml > p0 ? ml - p0 : 0u;
+      const uint32_t e_lo = zero_bytes(static_cast<uint32_t>(b0w) ^ static_cast<uint32_t>(b1w)) &
+                            acgt_bytes(static_cast<uint32_t>(b0w)) & low_bytes_mask(covered) & rm_lo;
+      const uint32_t e_hi = zero_bytes(static_cast<uint32_t>(b0w >> 32) ^ static_cast<uint32_t>(b1w >> 32)) &
+                            acgt_bytes(static_cast<uint32_t>(b0w >> 32)) &
+                            low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
+      uint64_t obw = 0, oqw = 0;
+      uint32_t ok_lo = 0, ok_hi = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (((j < 4 ? e_lo >> (8 * j) : e_hi >> (8 * (j - 4))) >> 7) & 1u) {
+          uint32_t qa = static_cast<uint32_t>(q0w >> (8 * j)) & 0xFFu, qb = static_cast<uint32_t>(q1w >> (8 * j)) & 0xFFu;
+          qa = qa > FGB_MAX_PHRED ? FGB_MAX_PHRED : qa;
+          qb = qb > FGB_MAX_PHRED ? FGB_MAX_PHRED : qb;
+          const uint32_t cq = __ldg(S.pair_q + qa * 94u + qb);
+          if (cq != 255u) {
+            const bool masked = cq < min_cons_q;                               // vanilla_caller.rs:1347-1348
+            obw |= static_cast<uint64_t>(masked ? 'N' : (static_cast<uint32_t>(b0w >> (8 * j)) & 0xFFu)) << (8 * j);
+            oqw |= static_cast<uint64_t>(masked ? 2u : cq) << (8 * j);
+            ls.nocall += masked;
+            if (j < 4) ok_lo |= 0x80u << (8 * j); else ok_hi |= 0x80u << (8 * (j - 4));
+          }
+        }
+      }
+      wb_lo = static_cast<uint32_t>(obw); wb_hi = static_cast<uint32_t>(obw >> 32);
+      wq_lo = static_cast<uint32_t>(oqw); wq_hi = static_cast<uint32_t>(oqw >> 32);
+      const uint32_t kb_lo = spread_msb(ok_lo), kb_hi = spread_msb(ok_hi);
+      dep.x = 0x00020002u & __byte_perm(kb_lo, 0u, 0x1100u);
+      dep.y = 0x00020002u & __byte_perm(kb_lo, 0u, 0x3322u);
+      dep.z = 0x00020002u & __byte_perm(kb_hi, 0u, 0x1100u);
+      dep.w = 0x00020002u & __byte_perm(kb_hi, 0u, 0x3322u);
+      todo_lo = rm_lo & ~ok_lo; todo_hi = rm_hi & ~ok_hi;
+      if (todo_lo | todo_hi) {
+        const uint32_t cnt = static_cast<uint32_t>(__popc(todo_lo) + __popc(todo_hi));
+        uint32_t slot = atomicAdd(wcount, cnt);
+        const uint32_t ent = (u << 16) | p0;
+        uint32_t keep_lo = 0, keep_hi = 0;
+        for (uint32_t t = todo_lo; t; t &= t - 1u, ++slot) {
+          if (slot < kWarpQueueCap) wqueue[slot] = ent + ((__ffs(t) - 1) >> 3);
+          else keep_lo |= t & (0u - t);
+        }
+        for (uint32_t t = todo_hi; t; t &= t - 1u, ++slot) {
+          if (slot < kWarpQueueCap) wqueue[slot] = ent + 4u + ((__ffs(t) - 1) >> 3);
+          else keep_hi |= t & (0u - t);
+        }
+        todo_lo = keep_lo; todo_hi = keep_hi;
+      }
     } else {
       const uint32_t qt = S.qt[n < kQtEntries ? n : kQtEntries - 1];
-      const bool fast_ok = (qt <= FGB_MAX_PHRED) && (n >= min_reads) && (n <= 0xFFFFu);
+      const uint32_t sumt = (V == 1 && (n == 3u || n == 4u)) ? a.tables->sumt[n] : 0xFFFFu;
+      const bool by_sum = V == 1 && sumt <= 255u;
+      const bool fast_ok = (by_sum || qt <= FGB_MAX_PHRED) && (n >= min_reads) && (n <= 0xFFFFu);
       uint32_t fm_lo = 0, fm_hi = 0, b0_lo = 0, b0_hi = 0;
-      if (fast_ok) {
+      if (V == 1 && by_sum && fast_ok) {
+        // three / four reads: every quality in 1..63 and the SUM of the qualities at or above the threshold
+        // proves sum D[q_i] > min(23, G2) (host_tables.cpp, exact dynamic programme over the gap table)
+        uint32_t diff_lo = 0, diff_hi = 0, minlen = 0xFFFFFFFFu;
+        uint32_t s_lo = 0, s_hi = 0, or_lo = 0, or_hi = 0, nz_lo = 0x40404040u, nz_hi = 0x40404040u;
+        typename M::addr_t rd = tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u;
+        for (uint32_t r = 0; r < n; ++r) {
+          typename M::off_t row;
+          uint32_t len;
+          if (Regular) { len = reg_len; row = reg_row0 + (reg_word + r * uni_m) * 8u; }
+          else {
+            const uint64_t d = M::ld64(rd + r * 8u);
+            len = static_cast<uint32_t>(d) & 0xFFFFu;
+            row = M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u);
+          }
+          minlen = len < minlen ? len : minlen;
+          const uint64_t wb = M::ld64(tv.bases + row);
+          const uint64_t wq = M::ld64(tv.quals + row);
+          if (r == 0) { b0_lo = static_cast<uint32_t>(wb); b0_hi = static_cast<uint32_t>(wb >> 32); }
+          diff_lo |= static_cast<uint32_t>(wb) ^ b0_lo;
+          diff_hi |= static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+          const uint32_t ql = static_cast<uint32_t>(wq), qh = static_cast<uint32_t>(wq >> 32);
+          s_lo += ql; s_hi += qh;                          // bytes stay <= 4 * 63 while or_* proves q < 64
+          or_lo |= ql; or_hi |= qh;
+          nz_lo &= ql + 0x3F3F3F3Fu; nz_hi &= qh + 0x3F3F3F3Fu;   // bit 6 survives iff every q >= 1 (q < 64: no carries)
+        }
+        // a quality >= 64 anywhere in a word voids the whole word (its carry may have touched a neighbour)
+        const uint32_t okq_lo = (or_lo & 0xC0C0C0C0u) ? 0u : ((nz_lo << 1) & bytes_ge(s_lo, sumt));
+        const uint32_t okq_hi = (or_hi & 0xC0C0C0C0u) ? 0u : ((nz_hi << 1) & bytes_ge(s_hi, sumt));
+        const uint32_t covered = minlen > p0 ? minlen - p0 : 0u;
+        fm_lo = zero_bytes(diff_lo) & okq_lo & acgt_bytes(b0_lo) & low_bytes_mask(covered) & rm_lo;
+        fm_hi = zero_bytes(diff_hi) & okq_hi & acgt_bytes(b0_hi) &
+                low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
+      } else if (fast_ok) {
         const uint32_t tsplat = qt * 0x01010101u;
         uint32_t diff_lo = 0, diff_hi = 0, okq_lo = 0x80808080u, okq_hi = 0x80808080u;
         if (Regular) {
@@ -869,7 +979,201 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
   if (lane == 0) *wcount = 0;
 }
 
-__global__ void __launch_bounds__(kThreads) vote_kernel(const VoteArgs a) {
+
+// Deep-class tiles (every unit has at least kDeepMin reads): a tile is one to five units, 19 .. 95 items --
+// too few to keep 256 threads busy one item each, and every item is a walk over 24 .. 512 rows.  So a GROUP
+// of g lanes (g = 2^k, chosen per tile so that items * g fills the CTA) shares an item: lane `sub` walks rows
+// sub, sub + g, ..., a __shfl_xor butterfly folds the partial masks, and the group's first lane finishes the
+// item exactly as vote_tile does.  Undecided positions are resolved by the warp-wide slow pass.
+template <class M, bool Regular>
+__device__ __forceinline__ void vote_tile_deep(const VoteArgs& a, VoteSmem& S, const Stage& st,
+                                               const TileView<M>& tv, uint32_t tid, uint32_t warp,
+                                               uint32_t n_items, LocalStats& ls) {
+  const uint32_t lane = tid & 31u;
+  const uint32_t n_units = st.tile.n_units;
+  const uint64_t out0 = st.units[0].out_off;
+  const uint32_t min_reads = a.min_reads, min_cons_q = a.min_cons_q, fast_qual = a.fast_qual;
+  const uint32_t reg_len = st.units[0].cons_len;
+  const uint32_t reg_row0 = (st.tile.flags & kTileFlagSkew8) ? 8u : 0u;
+  const bool fast_masked = fast_qual < min_cons_q;
+  const uint32_t fq4 = (fast_masked ? 2u : fast_qual) * 0x01010101u;
+  const uint32_t uni_m = st.tile.flags >> 8;
+  const uint32_t uni_recip = st.aux[0];
+  const uint32_t base32 = static_cast<uint32_t>(tv.byte_base);
+  uint32_t* const wqueue = S.queue[warp];
+  uint32_t* const wcount = &S.q_count[warp];
+  // lanes per item: the largest power of two with n_items * g <= kVoteThreads (at least 1, at most 32)
+  uint32_t gs = 0;
+  while (gs < 5u && (n_items << (gs + 1u)) <= static_cast<uint32_t>(kVoteThreads)) ++gs;
+  const uint32_t g = 1u << gs;
+  const uint32_t sub = tid & (g - 1u);
+  const uint32_t per_round = static_cast<uint32_t>(kVoteThreads) >> gs;
+
+  for (uint32_t base = 0; base < n_items; base += per_round) {
+    const uint32_t item_raw = base + (tid >> gs);
+    const bool valid = item_raw < n_items;                  // idle groups shadow the last item; nothing of theirs is stored
+    const uint32_t item = valid ? item_raw : n_items - 1u;
+    uint32_t u;
+    if (Regular || uni_m) {
+      u = __umulhi(item, uni_recip);
+    } else {
+      uint32_t lo = 0, hi = n_units;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint32_t start = static_cast<uint32_t>((st.units[mid].out_off - out0) >> 3);
+        if (start <= item) lo = mid; else hi = mid;
+      }
+      u = lo;
+    }
+    const fgb_unit un = st.units[u];
+    const uint32_t rb = un.read_begin;
+    const uint32_t n = st.units[u + 1].read_begin - rb;
+    const uint32_t cons_len = un.cons_len;
+    const uint64_t o = out0 + (static_cast<uint64_t>(item) << 3);
+    const uint32_t p0 = Regular ? (item - u * uni_m) << 3
+                                : (item - static_cast<uint32_t>((un.out_off - out0) >> 3)) << 3;
+    const uint32_t real = cons_len - p0 < 8u ? cons_len - p0 : 8u;
+    const uint32_t rm_lo = low_bytes_mask(real), rm_hi = low_bytes_mask(real > 4u ? real - 4u : 0u);
+    const uint32_t qt = S.qt[n < kQtEntries ? n : kQtEntries - 1];
+    const bool fast_ok = (qt <= FGB_MAX_PHRED) && (n >= min_reads) && (n <= 0xFFFFu) && n >= 2u;
+    if (n == 1u) {
+      // a single-read unit never belongs to a deep tile (planner); kept correct for hand-made tile arrays:
+      // the group's first lane applies the single-input rule (vanilla_caller.rs:1285-1316) position by position
+      if (valid && sub == 0) {
+        const uint64_t d = M::ld64(tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u);
+        const uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
+        for (uint32_t j = 0; j < real; ++j) {
+          const uint32_t pos = p0 + j;
+          Called c; c.base = 'N'; c.qual = 2; c.depth = 0; c.errors = 0;
+          if (pos < len) {
+            const typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + pos;
+            const uint32_t b = M::ld8(tv.bases + row), q = M::ld8(tv.quals + row);
+            const uint32_t adj = q < FGB_NTABLE ? S.single_q[q] : 0u;
+            if (adj >= min_cons_q) { c.base = b; c.qual = adj; }
+            c.depth = (b != 'N');
+          }
+          ls.nocall += (c.base == 'N');
+          write_called(a, o + j, c);
+        }
+        ls.positions += real;
+      }
+      __syncwarp();
+      continue;
+    }
+    uint32_t b0_lo = 0, b0_hi = 0;
+    uint32_t diff_lo = 0, diff_hi = 0, okq_lo = 0x80808080u, okq_hi = 0x80808080u, minlen = 0xFFFFFFFFu;
+    if (fast_ok) {
+      const uint32_t tsplat = qt * 0x01010101u;
+      if (Regular) {
+        const uint32_t step = uni_m * 8u;
+        typename M::addr_t pb = tv.bases + reg_row0 + ((rb - st.tile.read_begin) * uni_m + (p0 >> 3)) * 8u;
+        {
+          const uint64_t w = M::ld64(pb);
+          b0_lo = static_cast<uint32_t>(w); b0_hi = static_cast<uint32_t>(w >> 32);
+        }
+        pb += sub * step;
+        const uint32_t gstep = step << gs;
+#pragma unroll 4
+        for (uint32_t r = sub; r < n; r += g, pb += gstep) {
+          const uint64_t wb = M::ld64(pb);
+          const uint64_t wq = M::ld64(pb + kTileCapBytes);
+          diff_lo |= static_cast<uint32_t>(wb) ^ b0_lo;
+          diff_hi |= static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+          okq_lo &= (static_cast<uint32_t>(wq) | 0x80808080u) - tsplat;
+          okq_hi &= (static_cast<uint32_t>(wq >> 32) | 0x80808080u) - tsplat;
+        }
+        minlen = reg_len;
+      } else {
+        typename M::addr_t rd = tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u;
+        {
+          const uint64_t d = M::ld64(rd);
+          const uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
+          const uint64_t w = M::ld64(tv.bases + M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u));
+          b0_lo = static_cast<uint32_t>(w); b0_hi = static_cast<uint32_t>(w >> 32);
+        }
+#pragma unroll 4
+        for (uint32_t r = sub; r < n; r += g) {
+          const uint64_t d = M::ld64(rd + r * 8u);
+          const uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
+          minlen = len < minlen ? len : minlen;
+          const typename M::off_t row = M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u);
+          const uint64_t wb = M::ld64(tv.bases + row);
+          const uint64_t wq = M::ld64(tv.quals + row);
+          diff_lo |= static_cast<uint32_t>(wb) ^ b0_lo;
+          diff_hi |= static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+          okq_lo &= (static_cast<uint32_t>(wq) | 0x80808080u) - tsplat;
+          okq_hi &= (static_cast<uint32_t>(wq >> 32) | 0x80808080u) - tsplat;
+        }
+      }
+    }
+    // fold the group (every lane of the warp takes part; groups are aligned runs of g lanes)
+    for (uint32_t off = g >> 1; off > 0; off >>= 1) {
+      diff_lo |= __shfl_xor_sync(0xFFFFFFFFu, diff_lo, off);
+      diff_hi |= __shfl_xor_sync(0xFFFFFFFFu, diff_hi, off);
+      okq_lo &= __shfl_xor_sync(0xFFFFFFFFu, okq_lo, off);
+      okq_hi &= __shfl_xor_sync(0xFFFFFFFFu, okq_hi, off);
+      const uint32_t ml = __shfl_xor_sync(0xFFFFFFFFu, minlen, off);
+      minlen = ml < minlen ? ml : minlen;
+    }
+    if (valid && sub == 0) {
+      uint32_t fm_lo = 0, fm_hi = 0;
+      if (fast_ok) {
+        const uint32_t covered = minlen > p0 ? minlen - p0 : 0u;
+        fm_lo = zero_bytes(diff_lo) & okq_lo & acgt_bytes(b0_lo) & low_bytes_mask(covered) & rm_lo;
+        fm_hi = zero_bytes(diff_hi) & okq_hi & acgt_bytes(b0_hi) &
+                low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
+      }
+      const uint32_t fb_lo = spread_msb(fm_lo), fb_hi = spread_msb(fm_hi);
+      const uint32_t wb_lo = (fast_masked ? 0x4E4E4E4Eu : b0_lo) & fb_lo;
+      const uint32_t wb_hi = (fast_masked ? 0x4E4E4E4Eu : b0_hi) & fb_hi;
+      const uint32_t nn = n | (n << 16);
+      uint4 dep;
+      dep.x = nn & __byte_perm(fb_lo, 0u, 0x1100u);
+      dep.y = nn & __byte_perm(fb_lo, 0u, 0x3322u);
+      dep.z = nn & __byte_perm(fb_hi, 0u, 0x1100u);
+      dep.w = nn & __byte_perm(fb_hi, 0u, 0x3322u);
+      ls.nocall += fast_masked ? (__popc(fm_lo) + __popc(fm_hi)) : 0;
+      ls.positions += real;
+      *reinterpret_cast<uint2*>(a.out_base + o) = make_uint2(wb_lo, wb_hi);
+      *reinterpret_cast<uint2*>(a.out_qual + o) = make_uint2(fq4 & fb_lo, fq4 & fb_hi);
+      *reinterpret_cast<uint4*>(a.out_depth + o) = dep;
+      *reinterpret_cast<uint4*>(a.out_errors + o) = make_uint4(0, 0, 0, 0);
+      uint32_t todo_lo = rm_lo & ~fm_lo, todo_hi = rm_hi & ~fm_hi;
+      if (todo_lo | todo_hi) {
+        const uint32_t cnt = static_cast<uint32_t>(__popc(todo_lo) + __popc(todo_hi));
+        uint32_t slot = atomicAdd(wcount, cnt);
+        const uint32_t ent = (u << 16) | p0;
+        uint32_t keep_lo = 0, keep_hi = 0;
+        for (uint32_t t = todo_lo; t; t &= t - 1u, ++slot) {
+          if (slot < kWarpQueueCap) wqueue[slot] = ent + ((__ffs(t) - 1) >> 3);
+          else keep_lo |= t & (0u - t);
+        }
+        for (uint32_t t = todo_hi; t; t &= t - 1u, ++slot) {
+          if (slot < kWarpQueueCap) wqueue[slot] = ent + 4u + ((__ffs(t) - 1) >> 3);
+          else keep_hi |= t & (0u - t);
+        }
+        if (keep_lo | keep_hi) {                             // rare: the warp queue overflowed
+          for (uint32_t j = 0; j < 8u; ++j) {
+            if ((j < 4u ? keep_lo >> (8u * j) : keep_hi >> (8u * (j - 4u))) & 0x80u) {
+              const Called c = resolve_position<M>(tv, S, rb, n, p0 + j, a, ls);
+              write_called(a, o + j, c);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  uint32_t qn = *wcount;
+  qn = qn < kWarpQueueCap ? qn : kWarpQueueCap;
+  if (qn) slow_pass<M>(a, S, st, tv, wqueue, qn, lane, ls);
+  __syncwarp();
+  if (lane == 0) *wcount = 0;
+}
+
+template <int V>
+__device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   VoteSmem& S = *reinterpret_cast<VoteSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x;
@@ -961,14 +1265,20 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteArgs a) {
       tv.bases = a.bases; tv.quals = a.quals;
       tv.reads = reinterpret_cast<const uint8_t*>(a.reads + st.tile.read_begin);
       tv.byte_base = 0; tv.read_base = st.tile.read_begin;
-      vote_tile<GlMem, false>(a, S, st, tv, vt, warp, n_items, ls);
+      if (V == 2) vote_tile_deep<GlMem, false>(a, S, st, tv, tid, warp, n_items, ls);
+      else vote_tile<GlMem, false, V>(a, S, st, tv, vt, warp, n_items, ls);
     } else {
       TileView<ShMem> tv;
       tv.bases = st.bases; tv.quals = st.quals;
       tv.reads = reinterpret_cast<const uint8_t*>(st.reads) + (st.tile.read_begin & 1u) * 8u;
       tv.byte_base = st.tile.byte_begin; tv.read_base = st.tile.read_begin;
-      if (st.tile.flags & kTileFlagRegular) vote_tile<ShMem, true>(a, S, st, tv, vt, warp, n_items, ls);
-      else vote_tile<ShMem, false>(a, S, st, tv, vt, warp, n_items, ls);
+      if (V == 2) {
+        if (st.tile.flags & kTileFlagRegular) vote_tile_deep<ShMem, true>(a, S, st, tv, tid, warp, n_items, ls);
+        else vote_tile_deep<ShMem, false>(a, S, st, tv, tid, warp, n_items, ls);
+      } else {
+        if (st.tile.flags & kTileFlagRegular) vote_tile<ShMem, true, V>(a, S, st, tv, vt, warp, n_items, ls);
+        else vote_tile<ShMem, false, V>(a, S, st, tv, vt, warp, n_items, ls);
+      }
     }
     rot = (rot + n_items) & (kVoteThreads - 1);
     __syncwarp();
@@ -989,5 +1299,13 @@ __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteArgs a) {
     if (v2) atomicAdd(a.counters + FGB_CTR_NOCALL_POSITIONS, static_cast<unsigned long long>(v2));
   }
 }
+
+
+// Three instantiations, one per tile class (fgb_config.h): the planner cuts class-homogeneous tiles and the
+// engine launches each kernel on its own run of the (class-sorted) tile array.  Every one of them is correct
+// for any tile; they differ in how the work of a tile is dealt to the threads.
+__global__ void __launch_bounds__(kThreads) vote_kernel(const VoteArgs a) { vote_kernel_body<0>(a); }
+__global__ void __launch_bounds__(kThreads) vote_kernel_shallow(const VoteArgs a) { vote_kernel_body<1>(a); }
+__global__ void __launch_bounds__(kThreads) vote_kernel_deep(const VoteArgs a) { vote_kernel_body<2>(a); }
 
 }  // namespace fgb

@@ -224,6 +224,18 @@ def plan_tiles(batch: PackedBatch) -> np.ndarray:
     return batch.tiles
 
 
+def sort_tiles_by_class(tiles: np.ndarray):
+    """fgb_sort_tiles_by_class on a COPY of the tile table: (sorted tiles, run lengths per class).  For
+    device-resident batches (fgb_vote_device); the host-buffer calls sort their chunks themselves."""
+    lib = _l.load()
+    out = np.ascontiguousarray(tiles).copy()
+    counts = (C.c_uint64 * 3)()
+    st = lib.fgb_sort_tiles_by_class(out.ctypes.data_as(C.c_void_p), len(out), counts)
+    if st != 0:
+        raise _l.FgbError(st, "fgb_sort_tiles_by_class")
+    return out, (int(counts[0]), int(counts[1]), int(counts[2]))
+
+
 @dataclass
 class HostColumns:
     base: np.ndarray
@@ -252,14 +264,15 @@ class DeviceBatch:
         self.quals = t(batch.quals)
         self.reads = t(batch.reads)
         self.units = t(batch.units)
-        self.tiles = t(batch.tiles) if len(batch.tiles) else torch.zeros(32, dtype=torch.uint8, device=device)
+        sorted_tiles, self.class_tiles = sort_tiles_by_class(batch.tiles)   # the host copy keeps the unit order
+        self.tiles = t(sorted_tiles) if len(batch.tiles) else torch.zeros(32, dtype=torch.uint8, device=device)
         self.n_tiles = len(batch.tiles)
 
     def struct(self) -> _l.FgbBatch:
         b = self.host
         return _l.FgbBatch(b.n_units, b.n_reads, b.n_bytes, b.n_out, self.n_tiles,
                            self.bases.data_ptr(), self.quals.data_ptr(), self.reads.data_ptr(),
-                           self.units.data_ptr(), self.tiles.data_ptr())
+                           self.units.data_ptr(), self.tiles.data_ptr(), (C.c_uint64 * 3)(*self.class_tiles))
 
 
 class DeviceColumns:

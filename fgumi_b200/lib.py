@@ -73,6 +73,7 @@ class FgbBatch(C.Structure):
         ("reads", C.c_void_p),
         ("units", C.c_void_p),
         ("tiles", C.c_void_p),
+        ("class_tiles", C.c_uint64 * 3),   # since ABI 2: run lengths of a class-sorted tile array (0,0,0 = unsorted)
     ]
 
 
@@ -130,9 +131,20 @@ class FgbStrandColumns(C.Structure):
                 ("len", C.c_uint32), ("present", C.c_uint32)]
 
 
+class FgbRecordColumns(C.Structure):
+    _fields_ = [("n_bytes", C.c_uint64), ("records", C.c_void_p), ("raw_reads", C.c_void_p),
+                ("min_input_base_quality", C.c_uint8), ("reserved", C.c_uint8 * 7)]
+
+
 class FgbSubmitOptions(C.Structure):
     _fields_ = [("input_format", C.c_uint32), ("output_format", C.c_uint32), ("raw", C.c_void_p),
-                ("filter", C.c_void_p), ("unit_status", C.c_void_p), ("unit_masked", C.c_void_p)]
+                ("filter", C.c_void_p), ("unit_status", C.c_void_p), ("unit_masked", C.c_void_p),
+                # since ABI 2
+                ("records", C.c_void_p),
+                ("duplex_jobs", C.c_void_p), ("n_duplex_jobs", C.c_uint64), ("n_duplex_out", C.c_uint64),
+                ("duplex_out", C.c_void_p),
+                ("codec_jobs", C.c_void_p), ("n_codec_jobs", C.c_uint64), ("n_codec_out", C.c_uint64),
+                ("codec_params", C.c_void_p), ("codec_out", C.c_void_p)]
 
 
 FGB_DEVICE_NONE = -1      # fgb_caller_create: planning-only caller (no engine, flush refuses)
@@ -140,7 +152,7 @@ FGB_FILTER_PASS, FGB_FILTER_INSUFFICIENT_READS, FGB_FILTER_EXCESSIVE_ERROR_RATE 
 FGB_FILTER_LOW_MEAN_QUALITY, FGB_FILTER_TOO_MANY_NO_CALLS, FGB_FILTER_NO_RECORD = 3, 4, 255
 
 
-FGB_IN_BYTES, FGB_IN_PACK8, FGB_IN_BAM4 = 0, 1, 2
+FGB_IN_BYTES, FGB_IN_PACK8, FGB_IN_BAM4, FGB_IN_RECORDS = 0, 1, 2, 3
 FGB_OUT_U16, FGB_OUT_U8 = 0, 1
 
 
@@ -187,12 +199,12 @@ class FgbCodecOut(C.Structure):
 SYMBOLS = (
     "fgb_abi_version", "fgb_create", "fgb_destroy", "fgb_strerror", "fgb_last_error",
     "fgb_get_tables", "fgb_host_tables", "fgb_host_proof_tables", "fgb_tile_capacity_bytes", "fgb_tile_max_units", "fgb_tile_max_reads",
-    "fgb_plan_tiles", "fgb_vote_device", "fgb_submit", "fgb_wait", "fgb_host_alloc",
+    "fgb_plan_tiles", "fgb_sort_tiles_by_class", "fgb_vote_device", "fgb_submit", "fgb_wait", "fgb_host_alloc",
     "fgb_host_free", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
-    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups", "fgb_filter_record", "fgb_host_is_fr_pair",
+    "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_unpack_records_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups", "fgb_filter_record", "fgb_host_is_fr_pair",
     "fgb_host_num_bases_extending_past_mate", "fgb_host_clip_cigar_ops", "fgb_host_read_pos_at_ref_pos", "fgb_host_simplify_cigar", "fgb_host_source_reads", "fgb_host_consensus_umis", "fgb_caller_pending", "fgb_host_simplex_record", "fgb_bgzf_bound", "fgb_bgzf_compress", "fgb_bam_header", "fgb_host_group_by_mi", "fgb_host_duplex_record",
 )
 
@@ -243,6 +255,8 @@ def load() -> C.CDLL:
         getattr(lib, f).argtypes = []
     lib.fgb_plan_tiles.argtypes = [vp, u64, vp, u64, vp, u64, C.POINTER(u64)]
     lib.fgb_plan_tiles.restype = C.c_int32
+    lib.fgb_sort_tiles_by_class.argtypes = [vp, u64, vp]
+    lib.fgb_sort_tiles_by_class.restype = C.c_int32
     lib.fgb_vote_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), vp]
     lib.fgb_vote_device.restype = C.c_int32
     lib.fgb_submit.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns)]
@@ -296,6 +310,8 @@ def load() -> C.CDLL:
     lib.fgb_submit_bam4.restype = C.c_int32
     lib.fgb_unpack_bam4_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbRawColumns), vp, vp, vp]
     lib.fgb_unpack_bam4_device.restype = C.c_int32
+    lib.fgb_unpack_records_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbRecordColumns), vp, vp, vp]
+    lib.fgb_unpack_records_device.restype = C.c_int32
     lib.fgb_submit_ex.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), C.POINTER(FgbSubmitOptions)]
     lib.fgb_submit_ex.restype = C.c_int32
     lib.fgb_filter_simplex_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns),

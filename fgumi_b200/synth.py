@@ -72,16 +72,18 @@ def zipf_depths(n_units: int, lo: int = 1, hi: int = 100, s: float = 1.0, seed: 
 class TorchBatch:
     """A device-resident fgb_batch built by torch (same fields as engine.DeviceBatch)."""
 
-    def __init__(self, bases, quals, reads, units, tiles, host: PackedBatch):
+    def __init__(self, bases, quals, reads, units, tiles, host: PackedBatch, class_tiles=(0, 0, 0)):
         self.bases, self.quals, self.reads, self.units, self.tiles = bases, quals, reads, units, tiles
         self.host = host
         self.n_tiles = len(host.tiles)
+        self.class_tiles = class_tiles
 
     def struct(self) -> _l.FgbBatch:
+        import ctypes as C
         b = self.host
         return _l.FgbBatch(b.n_units, b.n_reads, b.n_bytes, b.n_out, self.n_tiles,
                            self.bases.data_ptr(), self.quals.data_ptr(), self.reads.data_ptr(),
-                           self.units.data_ptr(), self.tiles.data_ptr())
+                           self.units.data_ptr(), self.tiles.data_ptr(), (C.c_uint64 * 3)(*self.class_tiles))
 
 
 def _hashed_templates(torch, dev, template_ids, L, seed):
@@ -175,6 +177,76 @@ def device_batch(torch, device, depths: np.ndarray, L: int = 150, error_rate: fl
         _gen_rows(torch, dev, gen, d, L, Lp, error_rate, bmat, qmat, int(read_begin[u0]), u1 - u0, tid, seed)
         u0 = u1
     to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(dev)
-    tiles = host.tiles if len(host.tiles) else np.zeros(1, dtype=TILE_DTYPE)
+    from .engine import sort_tiles_by_class
+    tiles, classes = sort_tiles_by_class(host.tiles) if len(host.tiles) else (np.zeros(1, dtype=TILE_DTYPE), (0, 0, 0))
     return TorchBatch(bmat.reshape(-1), qmat.reshape(-1), to_dev(reads), to_dev(units), to_dev(tiles),
-                      host)
+                      host, classes)
+
+
+def record_families(n_families: int, depth: int = 8, L: int = 150, error_rate: float = 1e-3, seed: int = 42,
+                    reverse_fraction: float = 0.0):
+    """Synthetic MI-grouped BAM records for the record-level callers, built with numpy (no Python loop):
+    `n_families` groups of `depth` unpaired mapped reads of length L (CIGAR `<L>M`), bases and qualities from
+    the same model as host_pileup (no masking: the callers do that), tags MI:Z:<8 digits>, RX:Z:<8 bases>.
+    Every record has the same size, so the blob is one [reads, record] byte matrix.
+    Returns (blob uint8[...], rec_off uint64[R + 1], group_rec uint64[G + 1])."""
+    rng = np.random.default_rng(seed)
+    U, D = int(n_families), int(depth)
+    bases, quals = host_pileup(U, D, L, error_rate, seed=seed, min_input_q=0)      # [U, D, L]
+    R = U * D
+    bases = bases.reshape(R, L)
+    quals = quals.reshape(R, L)
+    fam = np.repeat(np.arange(U, dtype=np.int64), D)
+    rd = np.tile(np.arange(D, dtype=np.int64), U)
+    rev = np.zeros(R, dtype=bool)
+    if reverse_fraction > 0:
+        rev = np.repeat(rng.random(U) < reverse_fraction, D)
+    nseq = (L + 1) // 2
+    name_len = 12                                                     # 'q' + 7 digits + '.' + 2 digits + NUL
+    rec_len = 32 + name_len + 4 + nseq + L + 12 + 12
+    rec = np.zeros((R, rec_len), dtype=np.uint8)
+
+    def put(col, values, dtype):
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=dtype), (R,)))
+        rec[:, col:col + v.dtype.itemsize] = v.view(np.uint8).reshape(R, v.dtype.itemsize)
+
+    put(0, 0, "<i4"); put(4, 1000 + (fam % 100000), "<i4")
+    rec[:, 8] = name_len; rec[:, 9] = 60
+    put(10, 4680, "<u2"); put(12, 1, "<u2"); put(14, np.where(rev, 16, 0), "<u2"); put(16, L, "<u4")
+    put(20, -1, "<i4"); put(24, -1, "<i4"); put(28, 0, "<i4")
+
+    def digits(col, values, n):
+        v = values.copy()
+        for k in range(n - 1, -1, -1):
+            rec[:, col + k] = 48 + (v % 10)
+            v //= 10
+
+    o = 32
+    rec[:, o] = ord("q"); digits(o + 1, fam % 10_000_000, 7); rec[:, o + 8] = ord("."); digits(o + 9, rd % 100, 2)
+    o += name_len
+    put(o, (L << 4) | 0, "<u4"); o += 4
+    # 4-bit sequence; a reverse-strand record stores the reverse complement of the read
+    code = np.zeros(256, dtype=np.uint8); code[:] = 15
+    for i, ch in enumerate(b"=ACMGRSVTWYHKDBN"):
+        code[ch] = i
+    comp = np.arange(256, dtype=np.uint8)
+    for x, y in (b"AT", b"TA", b"CG", b"GC"):
+        comp[x] = y
+    sb = np.where(rev[:, None], comp[bases][:, ::-1], bases)
+    sq = np.where(rev[:, None], quals[:, ::-1], quals)
+    nib = code[sb]
+    if L % 2:
+        nib = np.concatenate([nib, np.zeros((R, 1), dtype=np.uint8)], axis=1)
+    rec[:, o:o + nseq] = (nib[:, 0::2] << 4) | nib[:, 1::2]
+    o += nseq
+    rec[:, o:o + L] = sq
+    o += L
+    rec[:, o:o + 3] = np.frombuffer(b"MIZ", np.uint8); digits(o + 3, fam % 100_000_000, 8); o += 12
+    rec[:, o:o + 3] = np.frombuffer(b"RXZ", np.uint8)
+    umi = ACGT[rng.integers(0, 4, size=(U, 8))]
+    rec[:, o + 3:o + 11] = np.repeat(umi, D, axis=0)
+    o += 12
+    assert o == rec_len
+    rec_off = np.arange(R + 1, dtype=np.uint64) * np.uint64(rec_len)
+    group_rec = np.arange(U + 1, dtype=np.uint64) * np.uint64(D)
+    return rec.reshape(-1), rec_off, group_rec

@@ -112,6 +112,12 @@ typedef struct fgb_batch {
   const fgb_read_desc* reads;  /* [R]   */
   const fgb_unit* units;       /* [U+1] */
   const fgb_tile* tiles;       /* [T]   */
+  /* since ABI 2: tiles come in three classes (flags bits 4..5: general, shallow = every unit has at most 4
+   * reads, deep = every unit has at least 24), each with its own kernel.  When the tile array is sorted by
+   * class (fgb_sort_tiles_by_class) these are the three run lengths; all zero = not sorted, the general
+   * kernel votes every tile (correct, slower on shallow and deep units).  The host-buffer calls
+   * (fgb_submit*) sort their tiles themselves and ignore this field. */
+  uint64_t class_tiles[3];
 } fgb_batch;
 
 typedef struct fgb_columns {   /* consensus output columns, [n_out] each                      */
@@ -180,6 +186,10 @@ uint32_t fgb_tile_max_reads(void);
  * layout rules (FGB_ERR_LAYOUT) and the capacity (FGB_ERR_UNIT_TOO_LARGE). */
 fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_read_desc* reads,
                           uint64_t n_reads, fgb_tile* out, uint64_t cap, uint64_t* n_tiles);
+
+/* Stable partition of a tile array by class (general, shallow, deep); class_tiles receives the run lengths
+ * to put in fgb_batch.class_tiles.  The order of the tiles is immaterial to the kernels. */
+fgb_status fgb_sort_tiles_by_class(fgb_tile* tiles, uint64_t n_tiles, uint64_t class_tiles[3]);
 
 /* ---- the vote (simplex / single-strand consensus), K1 --------------------------------- */
 /* Device-resident form: every pointer in `in`/`out` is a DEVICE pointer on the handle's GPU.
@@ -655,7 +665,8 @@ fgb_status fgb_caller_stats(const fgb_caller* c, uint64_t stats[FGB_NSTATS]);
 
 /* sizeof() of the ABI structs as this library was compiled, so a binding can check its own layout:
  * 0 fgb_caller_options, 1 fgb_filter_params, 2 fgb_submit_options, 3 fgb_raw_columns,
- * 4 fgb_raw_read, 5 fgb_batch, 6 fgb_codec_params, 7 fgb_params; 0 for an unknown id. */
+ * 4 fgb_raw_read, 5 fgb_batch, 6 fgb_codec_params, 7 fgb_params, 8 fgb_duplex_filter_params,
+ * 9 fgb_record_columns; 0 for an unknown id. */
 uint32_t fgb_struct_size(uint32_t id);
 
 #ifdef __cplusplus

@@ -49,7 +49,7 @@ recs = [r for g in groups for r in g]
 blob = np.frombuffer(b"".join(recs), np.uint8)
 off = np.zeros(len(recs) + 1, dtype=np.uint64); off[1:] = np.cumsum([len(r) for r in recs])
 grp = np.arange(G + 1, dtype=np.uint64) * np.uint64(2 * D)
-for T in (1, 4, 8, 16, 32, 64):
+for T in (1, 4, 8, 16, 32):
     c = fg.VanillaUmiConsensusCaller("fgumi", "A", fg.VanillaUmiConsensusOptions(min_reads=1, min_consensus_base_quality=2), n_threads=T)
     best = None
     for rep in range(3):

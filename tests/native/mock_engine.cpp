@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/fgumi_b200.h"
@@ -35,6 +36,18 @@ struct fgb_handle { fgb_params p; };
 
 namespace {
 
+// bench.py's record-level CPU baseline builds this file with -DFGB_MOCK_THREADS: the vote and the row building
+// then run on FGB_CPU_THREADS threads (default 1), like the caller's own host phases.
+int mock_threads() {
+#ifdef FGB_MOCK_THREADS
+  const char* e = std::getenv("FGB_CPU_THREADS");
+  const int n = e ? std::atoi(e) : 1;
+  return n > 0 ? n : 1;
+#else
+  return 1;
+#endif
+}
+
 fgb_status vote(const fgb_handle* h, const fgb_batch* in, const fgb_columns* out) {
   static_assert(sizeof(OrcUnit) == sizeof(fgb_unit), "unit layout");
   if (in->n_units == 0) return FGB_OK;
@@ -42,7 +55,7 @@ fgb_status vote(const fgb_handle* h, const fgb_batch* in, const fgb_columns* out
                              reinterpret_cast<const uint64_t*>(in->reads), in->bases, in->quals,
                              h->p.error_rate_pre_umi, h->p.error_rate_post_umi, h->p.min_reads,
                              h->p.min_consensus_base_quality, out->base, out->qual, out->depth, out->errors,
-                             nullptr, 1);
+                             nullptr, mock_threads());
   return rc == 0 ? FGB_OK : FGB_ERR_INVALID_ARG;
 }
 
@@ -99,12 +112,63 @@ void fgb_host_free(void* p) { std::free(p); }
 
 fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out) { return vote(h, in, out); }
 
+// FGB_IN_RECORDS restated on the host (unpack_kernels.cuh unpack_records_kernel): row position p is raw base p
+// (forward) or l_seq - 1 - p complemented (reverse); q < min_q -> (N, Q2); row padding is zero.
+void build_rows(const fgb_batch* in, const fgb_record_columns* rc, std::vector<uint8_t>* bases, std::vector<uint8_t>* quals) {
+  static const char* kF = "=ACMGRSVTWYHKDBN";
+  static const char* kC = "=TGMCRSVAWYHKDBN";
+  bases->assign(in->n_bytes + 16, 0);
+  quals->assign(in->n_bytes + 16, 0);
+  const int T = mock_threads();
+  auto range = [&](uint64_t r_lo, uint64_t r_hi) {
+  for (uint64_t r = r_lo; r < r_hi; ++r) {
+    const fgb_raw_read& rr = rc->raw_reads[r];
+    const uint64_t off = FGB_READ_OFF(in->reads[r]);
+    const uint32_t len = FGB_READ_LEN(in->reads[r]);
+    const uint8_t* seq = rc->records + rr.src_off;
+    const uint8_t* q = seq + (static_cast<uint64_t>(rr.raw_len) + 1) / 2;
+    const bool rev = rr.flags & FGB_RAW_REVERSE;
+    for (uint32_t p = 0; p < len; ++p) {
+      const uint32_t i = rev ? rr.raw_len - 1 - p : p;
+      const uint32_t nib = (i & 1) ? (seq[i >> 1] & 15u) : (seq[i >> 1] >> 4);
+      uint8_t b = static_cast<uint8_t>(rev ? kC[nib] : kF[nib]), qq = q[i];
+      if (qq < rc->min_input_base_quality) { b = 'N'; qq = 2; }
+      (*bases)[off + p] = b; (*quals)[off + p] = qq;
+    }
+  }
+  };
+  if (T <= 1) { range(0, in->n_reads); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t) th.emplace_back(range, in->n_reads * t / T, in->n_reads * (t + 1) / T);
+  for (auto& x : th) x.join();
+}
+
 fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out, const fgb_submit_options* opt) {
-  if (opt && (opt->input_format != FGB_IN_BYTES || opt->output_format != 0)) return FGB_ERR_INVALID_ARG;   // what the callers use
-  fgb_status st = vote(h, in, out);
-  if (st != FGB_OK || !opt || !opt->filter) return st;
-  if (!opt->unit_status) return FGB_ERR_INVALID_ARG;
-  filter_units(in, out, *opt->filter, opt->unit_status, opt->unit_masked);
+  if (!opt) return vote(h, in, out);
+  if (opt->input_format != FGB_IN_BYTES && opt->input_format != FGB_IN_RECORDS) return FGB_ERR_INVALID_ARG;   // what the callers use
+  if (opt->n_duplex_jobs || opt->n_codec_jobs) return FGB_ERR_INVALID_ARG;
+  fgb_batch b = *in;
+  std::vector<uint8_t> rb, rq;
+  if (opt->input_format == FGB_IN_RECORDS) {
+    if (!opt->records) return FGB_ERR_INVALID_ARG;
+    build_rows(in, opt->records, &rb, &rq);
+    b.bases = rb.data(); b.quals = rq.data();
+  }
+  const bool narrow = opt->output_format == FGB_OUT_U8;
+  std::vector<uint16_t> d16, e16;
+  fgb_columns cols = *out;
+  if (narrow) { d16.assign(in->n_out + 8, 0); e16.assign(in->n_out + 8, 0); cols.depth = d16.data(); cols.errors = e16.data(); }
+  fgb_status st = vote(h, &b, &cols);
+  if (st != FGB_OK) return st;
+  if (opt->filter) {
+    if (!opt->unit_status) return FGB_ERR_INVALID_ARG;
+    filter_units(&b, &cols, *opt->filter, opt->unit_status, opt->unit_masked);
+  }
+  if (narrow) {
+    uint8_t* d8 = reinterpret_cast<uint8_t*>(out->depth);
+    uint8_t* e8 = reinterpret_cast<uint8_t*>(out->errors);
+    for (uint64_t i = 0; i < in->n_out; ++i) { d8[i] = static_cast<uint8_t>(d16[i]); e8[i] = static_cast<uint8_t>(e16[i]); }
+  }
   return FGB_OK;
 }
 

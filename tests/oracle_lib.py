@@ -11,8 +11,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 SO = os.path.join(ORACLE_DIR, "liboracle.so")
+SO_NATIVE = os.path.join(ORACLE_DIR, "liboracle_native.so")     # same sources, -O3 -march=x86-64-v3 (timing legs)
+SO_CPU_CALLER = os.path.join(ORACLE_DIR, "libfgb_cpu_caller.so")  # the product's host code over the oracle's vote
 
 _lib = None
+_native = None
 
 
 def build():
@@ -88,10 +91,24 @@ def alloc_outputs(batch):
             np.zeros(n, np.uint16), np.zeros(max(batch.n_units, 1), np.uint32))
 
 
-def simplex_batch(batch, pre=45, post=40, min_reads=1, min_cons_q=2, threads=1, outputs=None):
+def load_native():
+    """The oracle compiled for speed (oracle/Makefile): only orc_simplex_batch is declared."""
+    global _native
+    if _native is None:
+        if not os.path.exists(SO_NATIVE):
+            build()
+        lib = C.CDLL(SO_NATIVE)
+        vp, u8 = C.c_void_p, C.c_uint8
+        lib.orc_simplex_batch.argtypes = [C.c_uint64, vp, vp, vp, vp, u8, u8, C.c_uint32, u8, vp, vp, vp, vp, vp, C.c_int]
+        lib.orc_simplex_batch.restype = C.c_int
+        _native = lib
+    return _native
+
+
+def simplex_batch(batch, pre=45, post=40, min_reads=1, min_cons_q=2, threads=1, outputs=None, native=False):
     """Run the oracle over a PackedBatch; returns (base, qual, depth, errors, cons_len).
     Pass `outputs=alloc_outputs(batch)` to reuse buffers (timing runs)."""
-    lib = load()
+    lib = load_native() if native else load()
     ob, oq, od, oe, cl = outputs if outputs is not None else alloc_outputs(batch)
     rc = lib.orc_simplex_batch(batch.n_units, batch.units.ctypes.data, batch.reads.ctypes.data,
                                batch.bases.ctypes.data, batch.quals.ctypes.data, pre, post,

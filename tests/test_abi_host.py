@@ -31,7 +31,7 @@ def test_header_symbols_exported(fg):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(fg.lib.SYMBOLS)
-    assert lib.fgb_abi_version() == 1
+    assert lib.fgb_abi_version() == 2
 
 
 def test_struct_sizes_match_header(fg):
@@ -42,7 +42,8 @@ def test_struct_sizes_match_header(fg):
     assert C.sizeof(l.FgbCodecParams) == 24
     lib = l.load()
     for i, t in enumerate((l.FgbCallerOptions, l.FgbFilterParams, l.FgbSubmitOptions, l.FgbRawColumns,
-                           None, l.FgbBatch, l.FgbCodecParams, l.FgbParams)):
+                           None, l.FgbBatch, l.FgbCodecParams, l.FgbParams, l.FgbDuplexFilterParams,
+                           l.FgbRecordColumns)):
         if t is not None:
             assert lib.fgb_struct_size(i) == C.sizeof(t), (i, t)
     assert lib.fgb_struct_size(4) == 16 and lib.fgb_struct_size(99) == 0
