@@ -44,16 +44,144 @@ __device__ __forceinline__ uint32_t cap_quality(int32_t s) {
   return s < 2 ? 2u : (s > 93 ? 93u : static_cast<uint32_t>(s));
 }
 
+// One job's descriptors, fetched one job ahead of the combine (the loads of job j + stride are in flight while
+// job j is combined: two dependent rounds of global-memory latency leave the critical path).
+struct DuplexJobRegs {
+  fgb_duplex_job job;
+  fgb_unit ua, ub;
+  uint32_t ra1, rb1;      // read_begin of the units after a and b
+};
+__device__ __forceinline__ DuplexJobRegs load_duplex_job(const DuplexArgs& a, uint64_t j) {
+  DuplexJobRegs r;
+  r.job = a.jobs[j];
+  r.ua = a.units[r.job.unit_a];
+  r.ub = a.units[r.job.unit_b];
+  r.ra1 = a.units[r.job.unit_a + 1].read_begin;
+  r.rb1 = a.units[r.job.unit_b + 1].read_begin;
+  return r;
+}
+
 __global__ void __launch_bounds__(kCombineThreads) duplex_combine_kernel(const DuplexArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kCombineJobsPerCta + (threadIdx.x >> 5);
   const uint64_t wstride = static_cast<uint64_t>(gridDim.x) * kCombineJobsPerCta;
   uint32_t done = 0;
+  DuplexJobRegs nx;
+  if (warp0 < a.n_jobs) nx = load_duplex_job(a, warp0);
   for (uint64_t j = warp0; j < a.n_jobs; j += wstride) {
-    const fgb_duplex_job job = a.jobs[j];
-    const fgb_unit ua = a.units[job.unit_a], ub = a.units[job.unit_b];
+    const DuplexJobRegs cur = nx;
+    if (j + wstride < a.n_jobs) nx = load_duplex_job(a, j + wstride);
+    const fgb_duplex_job job = cur.job;
+    const fgb_unit ua = cur.ua, ub = cur.ub;
     const uint32_t la = ua.cons_len, lb = ub.cons_len;
     const uint32_t len = la < lb ? la : lb;                       // duplex_caller.rs:846-849
+    const uint32_t ra0 = ua.read_begin, ra1 = cur.ra1;
+    const uint32_t rb0 = ub.read_begin, rb1 = cur.rb1;
+    // Word path: 8 positions per lane with byte-parallel arithmetic.  Needs 8-aligned rows (the layout rule
+    // for inputs; job.out_off is the caller's) and per-position error counts that fit a byte.
+    const bool words = ((ua.out_off | ub.out_off | job.out_off) & 7u) == 0 && (ra1 - ra0) + (rb1 - rb0) <= 255u;
+    uint8_t status;
+    if (words && len <= 256u) {
+      // ---- one block per job (reads up to 256 bases): everything the job needs is requested at once ----
+      const uint32_t p0 = lane * 8u;
+      const bool active = p0 < len;
+      uint2 ab2 = make_uint2(0, 0), bb2 = ab2, aq2 = ab2, bq2 = ab2;
+      uint4 ad4 = make_uint4(0, 0, 0, 0), bd4 = ad4;
+      if (active) {
+        ab2 = *reinterpret_cast<const uint2*>(a.ss_base + ua.out_off + p0);
+        bb2 = *reinterpret_cast<const uint2*>(a.ss_base + ub.out_off + p0);
+        aq2 = *reinterpret_cast<const uint2*>(a.ss_qual + ua.out_off + p0);
+        bq2 = *reinterpret_cast<const uint2*>(a.ss_qual + ub.out_off + p0);
+        ad4 = *reinterpret_cast<const uint4*>(a.ss_depth + ua.out_off + p0);
+        bd4 = *reinterpret_cast<const uint4*>(a.ss_depth + ub.out_off + p0);
+      }
+      const uint32_t na = ra1 - ra0, nr = na + (rb1 - rb0);
+      // descriptors of the pooled source rows (AB rows then BA rows), one per lane, 32 at a time
+      const uint64_t first_desc = lane < nr ? a.reads[lane < na ? ra0 + lane : rb0 + (lane - na)] : 0ull;
+      // :852-853 strands with no coverage inside the truncated region are dropped (rows are padded with
+      // zero depth, but a longer strand has real depths behind `len`: mask the last word)
+      const uint32_t live = active ? (len - p0 < 8u ? len - p0 : 8u) : 0u;
+      auto any16 = [&](const uint4& d) {
+        const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t keep = live >= 2u * k + 2u ? 0xFFFFFFFFu : (live == 2u * k + 1u ? 0x0000FFFFu : 0u);
+          acc |= w[k] & keep;
+        }
+        return acc != 0u;
+      };
+      const bool a_any = __any_sync(0xFFFFFFFFu, any16(ad4));
+      const bool b_any = __any_sync(0xFFFFFFFFu, any16(bd4));
+      if (a_any && b_any) {
+        status = FGB_DUPLEX_BOTH;
+        uint32_t ob[2], oq[2], rawb[2], cnt[2] = {0u, 0u};
+        const uint32_t abw[2] = {ab2.x, ab2.y}, bbw[2] = {bb2.x, bb2.y};
+        const uint32_t aqw[2] = {aq2.x, aq2.y}, bqw[2] = {bq2.x, bq2.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t eq = __vcmpeq4(abw[h], bbw[h]);                    // :912-927, bytewise
+          const uint32_t sum = __vminu4(__vaddus4(aqw[h], bqw[h]), 0x5D5D5D5Du);
+          const uint32_t dif = __vminu4(__vabsdiffu4(aqw[h], bqw[h]), 0x5D5D5D5Du);
+          const uint32_t rq = __vmaxu4((eq & sum) | (~eq & dif), 0x02020202u);   // cap_quality; equal-quality dissent -> 2
+          const uint32_t b_wins = ~eq & __vcmpgtu4(bqw[h], aqw[h]);
+          rawb[h] = (bbw[h] & b_wins) | (abw[h] & ~b_wins);
+          const uint32_t mask = __vcmpeq4(abw[h], 0x4E4E4E4Eu) | __vcmpeq4(bbw[h], 0x4E4E4E4Eu) |
+                                __vcmpeq4(rq, 0x02020202u);                 // :930-935
+          ob[h] = (0x4E4E4E4Eu & mask) | (rawb[h] & ~mask);
+          oq[h] = (0x02020202u & mask) | (rq & ~mask);
+        }
+        // :943-951 exact error recount against the pooled source reads
+        auto recount_word = [&](uint64_t d) {
+          const uint32_t rl = static_cast<uint32_t>(d & 0xFFFFu);
+          if (active && rl > p0) {
+            const uint2 sb = *reinterpret_cast<const uint2*>(a.bases + (d >> 16) + p0);
+            const uint32_t cov = rl - p0;                                   // covered positions of this word
+            const uint32_t c0 = cov >= 4u ? 0xFFFFFFFFu : ((1u << (8u * cov)) - 1u);
+            const uint32_t c1 = cov >= 8u ? 0xFFFFFFFFu : (cov > 4u ? ((1u << (8u * (cov - 4u))) - 1u) : 0u);
+            const uint32_t sw[2] = {sb.x, sb.y}, cw[2] = {c0, c1};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t ne = ~__vcmpeq4(sw[h], rawb[h]) & ~__vcmpeq4(sw[h], 0x4E4E4E4Eu) & cw[h];
+              cnt[h] += ne & 0x01010101u;
+            }
+          }
+        };
+        for (uint32_t c0 = 0; c0 < nr; c0 += 32u) {
+          const uint32_t k = c0 + lane;
+          const uint64_t mine = c0 == 0 ? first_desc : (k < nr ? a.reads[k < na ? ra0 + k : rb0 + (k - na)] : 0ull);
+          const uint32_t m = nr - c0 < 32u ? nr - c0 : 32u;
+#pragma unroll 8
+          for (uint32_t r = 0; r < m; ++r) recount_word(__shfl_sync(0xFFFFFFFFu, mine, r));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) cnt[h] &= ~__vcmpeq4(rawb[h], 0x4E4E4E4Eu);   // raw base N: no recount
+        if (active) {
+          *reinterpret_cast<uint2*>(a.out_base + job.out_off + p0) = make_uint2(ob[0], ob[1]);
+          *reinterpret_cast<uint2*>(a.out_qual + job.out_off + p0) = make_uint2(oq[0], oq[1]);
+          *reinterpret_cast<uint4*>(a.out_errors + job.out_off + p0) =
+              make_uint4(__byte_perm(cnt[0], 0u, 0x4140u), __byte_perm(cnt[0], 0u, 0x4342u),
+                         __byte_perm(cnt[1], 0u, 0x4140u), __byte_perm(cnt[1], 0u, 0x4342u));
+        }
+      } else if (a_any || b_any) {
+        // :855-882 single-strand passthrough keeps the FULL length of the surviving strand
+        status = a_any ? FGB_DUPLEX_A_ONLY : FGB_DUPLEX_B_ONLY;
+        const fgb_unit us = a_any ? ua : ub;
+        for (uint32_t i = lane; i < us.cons_len; i += 32) {
+          a.out_base[job.out_off + i] = a.ss_base[us.out_off + i];
+          a.out_qual[job.out_off + i] = a.ss_qual[us.out_off + i];
+          a.out_errors[job.out_off + i] = a.ss_errors[us.out_off + i];
+        }
+      } else {
+        status = FGB_DUPLEX_NONE;
+      }
+      if (lane == 0) {
+        if (a.out_status) a.out_status[j] = status;
+        ++done;
+      }
+      continue;
+    }
+    // ---- general path (long reads, unaligned rows, more than 255 pooled source reads) ----
     // :852-853 strands with no coverage inside the truncated region are dropped
     bool a_any = false, b_any = false;
     for (uint32_t i = lane; i < len; i += 32) {
@@ -62,16 +190,8 @@ __global__ void __launch_bounds__(kCombineThreads) duplex_combine_kernel(const D
     }
     a_any = __any_sync(0xFFFFFFFFu, a_any);
     b_any = __any_sync(0xFFFFFFFFu, b_any);
-    uint8_t status;
     if (a_any && b_any) {
       status = FGB_DUPLEX_BOTH;
-      const uint32_t ra0 = ua.read_begin, ra1 = a.units[job.unit_a + 1].read_begin;
-      const uint32_t rb0 = ub.read_begin, rb1 = a.units[job.unit_b + 1].read_begin;
-      // Word path: 8 positions per lane with byte-parallel arithmetic.  Needs 8-aligned rows (the
-      // layout rule for inputs; job.out_off is the caller's) and per-position error counts that fit
-      // a byte.  Everything else takes the position-by-position loop below.
-      const bool words = ((ua.out_off | ub.out_off | job.out_off) & 7u) == 0 &&
-                         (ra1 - ra0) + (rb1 - rb0) <= 255u;
       if (words) {
         for (uint32_t base0 = 0; base0 < len; base0 += 256u) {
           const uint32_t p0 = base0 + lane * 8u;

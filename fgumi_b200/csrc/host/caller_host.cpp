@@ -12,6 +12,7 @@
 //                           :1048-1285 (duplex_read_into)
 // There is no CPU vote here: without a device, fgb_caller_create fails.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -99,17 +100,22 @@ class WorkerPool {
     for (auto& t : threads_) t.join();
   }
   uint32_t size() const { return static_cast<uint32_t>(threads_.size()) + 1; }
-  void run(uint32_t n, const std::function<void(uint32_t)>& fn) {
-    if (n == 0) return;
+  // Returns false when a task threw (std::bad_alloc from a growing buffer, typically): the exception is
+  // caught on the thread it was raised on, every task is still waited for -- the lambda's captures live on the
+  // caller's frame -- and the caller turns the flag into FGB_ERR_NOMEM.
+  bool run(uint32_t n, const std::function<void(uint32_t)>& fn) {
+    if (n == 0) return true;
+    failed_.store(false, std::memory_order_relaxed);
     if (n > 1) {
       { std::lock_guard<std::mutex> l(m_); fn_ = &fn; n_ = n; pending_ = n - 1; ++gen_; }
       cv_.notify_all();
     }
-    fn(0);
+    try { fn(0); } catch (...) { failed_.store(true, std::memory_order_relaxed); }
     if (n > 1) {
       std::unique_lock<std::mutex> l(m_);
       done_.wait(l, [&] { return pending_ == 0; });
     }
+    return !failed_.load(std::memory_order_relaxed);
   }
 
  private:
@@ -126,12 +132,13 @@ class WorkerPool {
         fn = fn_; n = n_;
       }
       if (idx < n) {
-        (*fn)(idx);
+        try { (*fn)(idx); } catch (...) { failed_.store(true, std::memory_order_relaxed); }
         std::lock_guard<std::mutex> l(m_);
         if (--pending_ == 0) done_.notify_one();
       }
     }
   }
+  std::atomic<bool> failed_{false};
   std::vector<std::thread> threads_;
   std::mutex m_;
   std::condition_variable cv_, done_;
@@ -234,6 +241,7 @@ struct fgb_caller {
   PinBuf stage;                              // parent: the staged records
   size_t stage_len = 0;
   PinBuf d_reads, d_raws, d_units;           // parent: descriptor arrays handed to the engine
+  PinBuf px[12];                             // duplex / CODEC: page-locked result columns of a flush (grow-only)
   std::vector<View> views;                   // scratch: the records of the group being planned
   std::vector<uint64_t> rel_off;             // scratch: record offsets relative to the group
 };
@@ -244,8 +252,8 @@ namespace {
 void run_parallel(fgb_caller* c, uint32_t T, const std::function<void(uint32_t)>& fn) {
   if (T <= 1) { if (T) fn(0); return; }
   if (!c->pool || c->pool->size() < T) c->pool.reset(new WorkerPool(std::max<uint32_t>(T, c->opt.n_threads)));
-  c->pool->run(T, fn);
-}
+  if (!c->pool->run(T, fn)) throw std::bad_alloc();   // re-raised on the calling thread once every task has finished;
+}                                                      // the extern "C" entry points turn it into FGB_ERR_NOMEM
 
 void reject(fgb_caller* c, int reason, uint64_t n) {
   c->stats[FGB_STAT_FILTERED_READS] += n;
@@ -638,6 +646,7 @@ fgb_status flush_simplex(fgb_caller* c) {
   const Col16 od{static_cast<uint16_t*>(c->pinned[2])}, oe{static_cast<uint16_t*>(c->pinned[3])};
   trace.mark("output buffers");
   fgb_batch b;
+  std::memset(&b, 0, sizeof(b));
   b.n_units = U; b.n_reads = R; b.n_bytes = n_bytes; b.n_out = no; b.n_tiles = n_tiles;
   b.bases = c->pack.bases.data(); b.quals = c->pack.quals.data(); b.reads = c->pack.reads.data();
   b.units = c->pack.units.data(); b.tiles = tiles.data();
@@ -1399,16 +1408,35 @@ fgb_status flush_duplex(fgb_caller* c) {
   if (st != FGB_OK) { c->last_error = "fgb_plan_tiles failed"; return st; }
   std::vector<fgb_tile> tiles(n_tiles ? n_tiles : 1);
   if ((st = fgb_plan_tiles(c->pack.units.data(), U, c->pack.reads.data(), R, tiles.data(), n_tiles, &n_tiles)) != FGB_OK) return st;
-  const uint64_t no = c->pack.n_out, nd = c->n_duplex_out;
-  std::vector<uint8_t> sb(no + 8), sq(no + 8), db(nd + 8), dq(nd + 8), dst(c->jobs.size() + 1);
-  std::vector<uint16_t> sd(no + 8), se(no + 8), de(nd + 8);
+  const uint64_t no = c->pack.n_out, nd = c->n_duplex_out, nj = c->jobs.size();
+  // result columns in page-locked memory that outlives the flush (no zero-fill, asynchronous copies back)
+  const size_t want[8] = {no + 8, no + 8, 2 * (no + 8), 2 * (no + 8), nd + 8, nd + 8, 2 * (nd + 8), nj + 8};
+  for (int i = 0; i < 8; ++i)
+    if (c->px[i].ensure(want[i]) != FGB_OK) { c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM; }
+  struct P8 { uint8_t* p; uint8_t* data() const { return p; } uint8_t& operator[](size_t i) const { return p[i]; } };
+  struct P16 { uint16_t* p; uint16_t* data() const { return p; } };
+  const P8 sb{static_cast<uint8_t*>(c->px[0].p)}, sq{static_cast<uint8_t*>(c->px[1].p)};
+  const P16 sd{static_cast<uint16_t*>(c->px[2].p)}, se{static_cast<uint16_t*>(c->px[3].p)};
+  const P8 db{static_cast<uint8_t*>(c->px[4].p)}, dq{static_cast<uint8_t*>(c->px[5].p)};
+  const P16 de{static_cast<uint16_t*>(c->px[6].p)};
+  const P8 dst{static_cast<uint8_t*>(c->px[7].p)};
   fgb_batch b;
+  std::memset(&b, 0, sizeof(b));
   b.n_units = U; b.n_reads = R; b.n_bytes = n_bytes; b.n_out = no; b.n_tiles = n_tiles;
   b.bases = c->pack.bases.data(); b.quals = c->pack.quals.data(); b.reads = c->pack.reads.data();
   b.units = c->pack.units.data(); b.tiles = tiles.data();
   fgb_columns ss{sb.data(), sq.data(), sd.data(), se.data()};
   fgb_duplex_out dout{db.data(), dq.data(), de.data(), dst.data()};
-  st = fgb_duplex_submit(c->h, &b, &ss, c->jobs.data(), c->jobs.size(), nd, &dout);
+  if (nj) {                        // vote + strand combine in one call, buffers owned by the engine's slots
+    fgb_submit_options so;
+    std::memset(&so, 0, sizeof(so));
+    so.input_format = FGB_IN_BYTES; so.output_format = FGB_OUT_U16;
+    so.duplex_jobs = c->jobs.data(); so.n_duplex_jobs = nj; so.n_duplex_out = nd; so.duplex_out = &dout;
+    st = fgb_submit_ex(c->h, &b, &ss, &so);
+  } else {
+    st = fgb_submit(c->h, &b, &ss);
+  }
+  if (st == FGB_OK) st = fgb_wait(c->h);
   if (st != FGB_OK) {
     char buf[256];
     fgb_last_error(c->h, buf, sizeof(buf));
@@ -1744,10 +1772,21 @@ fgb_status flush_codec(fgb_caller* c) {
   std::vector<fgb_tile> tiles(n_tiles ? n_tiles : 1);
   if ((st = fgb_plan_tiles(c->pack.units.data(), U, c->pack.reads.data(), R, tiles.data(), n_tiles, &n_tiles)) != FGB_OK) return st;
   const uint64_t no = c->pack.n_out, nc = c->n_codec_out, nj = c->codec_jobs.size();
-  std::vector<uint8_t> sb(no + 8), sq(no + 8), cb(nc + 8), cq(nc + 8), cst(nj + 1);
-  std::vector<uint16_t> sd(no + 8), se(no + 8), cd(nc + 8), ce(nc + 8);
-  std::vector<uint32_t> dis(nj + 1), dup(nj + 1);
+  const size_t want[11] = {no + 8, no + 8, 2 * (no + 8), 2 * (no + 8), nc + 8, nc + 8, 2 * (nc + 8), 2 * (nc + 8),
+                           nj + 8, 4 * (nj + 2), 4 * (nj + 2)};
+  for (int i = 0; i < 11; ++i)
+    if (c->px[i].ensure(want[i]) != FGB_OK) { c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM; }
+  struct P8 { uint8_t* p; uint8_t* data() const { return p; } uint8_t& operator[](size_t i) const { return p[i]; } };
+  struct P16 { uint16_t* p; uint16_t* data() const { return p; } };
+  struct P32 { uint32_t* p; uint32_t* data() const { return p; } uint32_t& operator[](size_t i) const { return p[i]; } };
+  const P8 sb{static_cast<uint8_t*>(c->px[0].p)}, sq{static_cast<uint8_t*>(c->px[1].p)};
+  const P16 sd{static_cast<uint16_t*>(c->px[2].p)}, se{static_cast<uint16_t*>(c->px[3].p)};
+  const P8 cb{static_cast<uint8_t*>(c->px[4].p)}, cq{static_cast<uint8_t*>(c->px[5].p)};
+  const P16 cd{static_cast<uint16_t*>(c->px[6].p)}, ce{static_cast<uint16_t*>(c->px[7].p)};
+  const P8 cst{static_cast<uint8_t*>(c->px[8].p)};
+  const P32 dis{static_cast<uint32_t*>(c->px[9].p)}, dup{static_cast<uint32_t*>(c->px[10].p)};
   fgb_batch b;
+  std::memset(&b, 0, sizeof(b));
   b.n_units = U; b.n_reads = R; b.n_bytes = n_bytes; b.n_out = no; b.n_tiles = n_tiles;
   b.bases = c->pack.bases.data(); b.quals = c->pack.quals.data(); b.reads = c->pack.reads.data();
   b.units = c->pack.units.data(); b.tiles = tiles.data();
@@ -1755,7 +1794,17 @@ fgb_status flush_codec(fgb_caller* c) {
   fgb_codec_out cout;
   cout.cols = fgb_columns{cb.data(), cq.data(), cd.data(), ce.data()};
   cout.status = cst.data(); cout.disagreements = dis.data(); cout.duplex_bases = dup.data();
-  st = fgb_codec_submit(c->h, &b, &ss, c->codec_jobs.data(), nj, &c->opt.codec, nc, &cout);
+  if (nj) {
+    fgb_submit_options so;
+    std::memset(&so, 0, sizeof(so));
+    so.input_format = FGB_IN_BYTES; so.output_format = FGB_OUT_U16;
+    so.codec_jobs = c->codec_jobs.data(); so.n_codec_jobs = nj; so.n_codec_out = nc;
+    so.codec_params = &c->opt.codec; so.codec_out = &cout;
+    st = fgb_submit_ex(c->h, &b, &ss, &so);
+  } else {
+    st = fgb_submit(c->h, &b, &ss);
+  }
+  if (st == FGB_OK) st = fgb_wait(c->h);
   if (st != FGB_OK) {
     char buf[256];
     fgb_last_error(c->h, buf, sizeof(buf));
@@ -1848,7 +1897,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
 
 extern "C" {
 
-fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_caller** out) {
+static fgb_status caller_create_impl(int device, const fgb_caller_options* opt, fgb_caller** out) {
   if (!opt || !out || !opt->read_name_prefix || !opt->read_group_id) return FGB_ERR_INVALID_ARG;
   *out = nullptr;
   if (opt->mode > FGB_MODE_CODEC) return FGB_ERR_INVALID_ARG;
@@ -1928,6 +1977,7 @@ void fgb_caller_destroy(fgb_caller* c) {
   if (!c) return;
   for (void* p : c->pinned) fgb_host_free(p);
   c->stage.release(); c->d_reads.release(); c->d_raws.release(); c->d_units.release();
+  for (PinBuf& b : c->px) b.release();
   std::free(c->joined);
   fgb_destroy(c->h);
   delete c;
@@ -1943,7 +1993,7 @@ size_t fgb_caller_last_error(const fgb_caller* c, char* buf, size_t buf_len) {
   return c->last_error.size();
 }
 
-fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
+static fgb_status caller_add_group_impl(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
                                 uint32_t n_records) {
   if (!c || (n_records && (!records || !rec_off))) return FGB_ERR_INVALID_ARG;
   if (n_records == 0) return FGB_OK;
@@ -2215,7 +2265,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
 
 extern "C" {
 
-fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
+static fgb_status caller_add_groups_impl(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
                                  const uint64_t* group_rec, uint64_t n_groups) {
   if (!c || (n_groups && (!records || !rec_off || !group_rec))) return FGB_ERR_INVALID_ARG;
   if (n_groups == 0) return FGB_OK;
@@ -2226,7 +2276,7 @@ fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const ui
     for (uint64_t g = g0; g < g1; ++g) {
       const uint64_t r0 = group_rec[g], r1 = group_rec[g + 1];
       if (r1 < r0 || r1 - r0 > 0xFFFFFFFFull) { dst->last_error = "bad group_rec table"; *bad_group = g; return FGB_ERR_INVALID_ARG; }
-      fgb_status st = fgb_caller_add_group(dst, records, rec_off + r0, static_cast<uint32_t>(r1 - r0));
+      fgb_status st = caller_add_group_impl(dst, records, rec_off + r0, static_cast<uint32_t>(r1 - r0));
       if (st != FGB_OK) { *bad_group = g; return st; }
     }
     return FGB_OK;
@@ -2258,7 +2308,7 @@ fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const ui
   return FGB_OK;
 }
 
-fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* out_len,
+static fgb_status caller_flush_impl(fgb_caller* c, const uint8_t** out_data, uint64_t* out_len,
                             uint64_t* out_count) {
   if (!c || !out_data || !out_len || !out_count) return FGB_ERR_INVALID_ARG;
   c->out.clear();
@@ -2533,6 +2583,28 @@ fgb_status fgb_caller_stats(const fgb_caller* c, uint64_t stats[FGB_NSTATS]) {
   stats[FGB_STAT_OVERLAP_DISAGREEING] = c->overlap.stats.bases_disagreeing;
   stats[FGB_STAT_OVERLAP_CORRECTED] = c->overlap.stats.bases_corrected;
   return FGB_OK;
+}
+
+// No exception crosses the C ABI: an allocation failure anywhere below (on any of the caller's threads, see
+// WorkerPool::run) becomes FGB_ERR_NOMEM; a failed add leaves nothing of the call queued on the direct path.
+#define FGB_GUARD(c, call)                                                      \
+  try { return (call); }                                                        \
+  catch (const std::bad_alloc&) { if (c) (c)->last_error = "out of memory"; return FGB_ERR_NOMEM; } \
+  catch (...) { if (c) (c)->last_error = "internal error"; return FGB_ERR_INVALID_ARG; }
+
+fgb_status fgb_caller_create(int device, const fgb_caller_options* opt, fgb_caller** out) {
+  fgb_caller* none = nullptr;
+  FGB_GUARD(none, caller_create_impl(device, opt, out))
+}
+fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off, uint32_t n_records) {
+  FGB_GUARD(c, caller_add_group_impl(c, records, rec_off, n_records))
+}
+fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
+                                 const uint64_t* group_rec, uint64_t n_groups) {
+  FGB_GUARD(c, caller_add_groups_impl(c, records, rec_off, group_rec, n_groups))
+}
+fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* out_len, uint64_t* out_count) {
+  FGB_GUARD(c, caller_flush_impl(c, out_data, out_len, out_count))
 }
 
 }  // extern "C"

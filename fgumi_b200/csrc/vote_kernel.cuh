@@ -277,6 +277,45 @@ __device__ __forceinline__ bool certified_quality(const double (&ll)[4], int mi,
   return true;
 }
 
+// The same certified evaluation fed by the FIXED-POINT likelihood gaps of the integer pass (sums of
+// round(D[q] * 65536), host_tables.cpp): best = the winner's sum, o1..o3 = the sums of the three other bases
+// (0 for an unobserved base), each gap within e = 2 * depth + 1 units of the exact one.  Decides the quality of
+// a position the dominant-winner proof could not (a shallow or low-quality pileup, a pileup with dissent)
+// without the f64 Kahan sums; returns false -- the literal path decides -- when a gap is too small for the
+// fixed-point sums to rule out a tie, when the reference's unanimous fast path (gap > 23.0,
+// base_builder.rs:338-379) cannot be told from the full call, or when the interval straddles a branch or a
+// quality boundary.
+__device__ __noinline__ bool certified_from_fixed(int32_t best, int32_t o1, int32_t o2, int32_t o3, uint32_t depth,
+                                                     bool unanimous, double ln_pre, uint32_t fast_qual, uint32_t* q_out) {
+  const int32_t e = static_cast<int32_t>(2u * depth + 1u);
+  const int32_t g1 = best - o1, g2 = best - o2, g3 = best - o3;
+  const int32_t gmin = min(g1, min(g2, g3));
+  if (gmin <= e + 64) return false;
+  if (unanimous) {                                     // all three gaps equal the winner's sum
+    const int32_t t23 = 23 * 65536;
+    if (gmin - e > t23) { *q_out = fast_qual; return true; }
+    if (gmin + e >= t23) return false;
+  }
+  const float k = -1.0f / 65536.0f;
+  float s_hi = __expf(static_cast<float>(g1 - e) * k) + __expf(static_cast<float>(g2 - e) * k) + __expf(static_cast<float>(g3 - e) * k);
+  float s_lo = __expf(static_cast<float>(g1 + e) * k) + __expf(static_cast<float>(g2 + e) * k) + __expf(static_cast<float>(g3 + e) * k);
+  const float lp = static_cast<float>(ln_pre);
+  const float noise = static_cast<float>(depth) * 32.0f * 1.8e-15f;   // 8 ulp(max |ll|) on the reference's s, |ll| <= 32 * depth
+  s_hi = (s_hi + noise) * 1.0002f;
+  s_lo = fmaxf(s_lo - noise, 0.0f) * 0.9998f;
+  float x_lo, x_hi;
+  int b_lo, b_hi;
+  if (!tail_phred(__logf(s_hi) - log1pf(s_hi), lp, &x_lo, &b_lo)) return false;
+  const float err_lo = s_lo > 0.0f ? __logf(s_lo) - log1pf(s_lo) : -CUDART_INF_F;
+  if (!tail_phred(err_lo, lp, &x_hi, &b_hi)) return false;
+  if (b_lo != b_hi) return false;
+  if (b_lo == 0) { *q_out = fast_qual; return true; }
+  const float qa = clamp_floor_phred(x_lo - 2.0e-3f), qb = clamp_floor_phred(x_hi + 2.0e-3f);
+  if (qa != qb) return false;
+  *q_out = static_cast<uint32_t>(qa);
+  return true;
+}
+
 // The literal per-position algorithm (vanilla_caller.rs:1319-1355 + base_builder.rs:295-458).
 //
 // Two-read units take a shortcut first: when both reads cover the position, agree on an A/C/G/T base
@@ -415,7 +454,11 @@ __device__ __forceinline__ void write_called(const VoteArgs& a, uint64_t o, cons
 // "Dominant winner" evaluation of one position in integers (proof: host_tables.cpp).  Returns true
 // and fills `out` when the reference's result is PROVEN to be (winner, phred(ln_pre)) after the
 // thresholds of vanilla_caller.rs:1345-1349; returns false when the literal f64 path must decide.
-template <class M>
+// Cert: try the certified evaluation from the fixed-point gaps before giving a position to the literal path.
+// Enabled in the shallow-class kernel only: the call keeps registers live across it, which costs the general
+// kernel's item loop a quarter of its speed (measured), and shallow pileups are where the dominant-winner
+// proof fails most.
+template <class M, bool Cert = false>
 __device__ __forceinline__ bool dominant_position(const TileView<M>& tv, const VoteSmem& S,
                                                   uint32_t read_begin, uint32_t n_reads,
                                                   uint32_t pos, uint32_t min_reads,
@@ -461,13 +504,17 @@ __device__ __forceinline__ bool dominant_position(const TileView<M>& tv, const V
   consider(s2, 2u, c2);
   consider(s3, 3u, c3);
   // every fixed-point term is within half a unit of D[q]*65536; two sums of <= depth terms
-  if (static_cast<int64_t>(best) - second < static_cast<int64_t>(S.g2fix) + 2 * static_cast<int64_t>(depth) + 1)
-    return false;
+  uint32_t q = fast_qual;
+  if (static_cast<int64_t>(best) - second < static_cast<int64_t>(S.g2fix) + 2 * static_cast<int64_t>(depth) + 1) {
+    if (!Cert) return false;
+    const int32_t oa = w == 0 ? s1 : s0, ob = w <= 1 ? s2 : s1, oc = w == 3 ? s2 : s3;   // the three other sums
+    if (!certified_from_fixed(best, oa, ob, oc, depth, depth == cw, S.ln_pre, fast_qual, &q)) return false;
+  }
   out.depth = depth;
   out.errors = depth - cw;
   if (depth < min_reads) { out.base = 'N'; out.qual = 0; }
-  else if (fast_qual < min_cons_q) { out.base = 'N'; out.qual = 2; }
-  else { out.base = (0x54474341u >> (8u * w)) & 0xFFu; out.qual = fast_qual; }
+  else if (q < min_cons_q) { out.base = 'N'; out.qual = 2; }
+  else { out.base = (0x54474341u >> (8u * w)) & 0xFFu; out.qual = q; }
   return true;
 }
 
@@ -497,12 +544,12 @@ __device__ __forceinline__ uint32_t bytes_ge(uint32_t sum, uint32_t t) {
 }
 
 // Resolve one undecided position: integer proof first, the literal f64 algorithm otherwise.
-template <class M>
+template <class M, bool Cert = false>
 __device__ __forceinline__ Called resolve_position(const TileView<M>& tv, const VoteSmem& S,
                                                    uint32_t rb, uint32_t n, uint32_t pos,
                                                    const VoteArgs& a, LocalStats& ls) {
   Called c;
-  if (!dominant_position<M>(tv, S, rb, n, pos, a.min_reads, a.min_cons_q, a.fast_qual, c)) {
+  if (!dominant_position<M, Cert>(tv, S, rb, n, pos, a.min_reads, a.min_cons_q, a.fast_qual, c)) {
     c = exact_position<M>(tv, S, rb, n, pos, a.min_reads, a.min_cons_q, a.fast_qual);
     ls.exact += c.depth >> 31;
     c.depth &= ~kLiteralFlag;
@@ -516,7 +563,7 @@ __device__ __forceinline__ Called resolve_position(const TileView<M>& tv, const 
 // its reads and looks up their fixed-point likelihood gaps, a __shfl_xor butterfly sums the four
 // per-base gap sums and counts over the group, and the group leader applies the dominant-winner
 // proof (host_tables.cpp).  Whatever the proof cannot decide runs the literal f64 algorithm.
-template <class M, uint32_t G>
+template <class M, uint32_t G, bool Cert = false>
 __device__ __forceinline__ void slow_pass_g(const VoteArgs& a, const VoteSmem& S, const Stage& st,
                                             const TileView<M>& tv, const uint32_t* wqueue, uint32_t qn,
                                             uint32_t lane, LocalStats& ls) {
@@ -587,13 +634,19 @@ __device__ __forceinline__ void slow_pass_g(const VoteArgs& a, const VoteSmem& S
           if (s2 > best) { second = best; best = s2; w = 2; cw = c2; } else if (s2 > second) second = s2;
           if (s3 > best) { second = best; best = s3; w = 3; cw = c3; } else if (s3 > second) second = s3;
           // every fixed-point term is within half a unit of D[q]*65536; two sums of <= depth terms
-          if (static_cast<int64_t>(best) - second >=
-              static_cast<int64_t>(S.g2fix) + 2 * static_cast<int64_t>(depth) + 1) {
+          uint32_t q = a.fast_qual;
+          bool proven = static_cast<int64_t>(best) - second >=
+                        static_cast<int64_t>(S.g2fix) + 2 * static_cast<int64_t>(depth) + 1;
+          if (Cert && !proven) {
+            const int32_t oa = w == 0 ? s1 : s0, ob = w <= 1 ? s2 : s1, oc = w == 3 ? s2 : s3;
+            proven = certified_from_fixed(best, oa, ob, oc, depth, depth == cw, S.ln_pre, a.fast_qual, &q);
+          }
+          if (proven) {
             c.depth = depth;
             c.errors = depth - cw;
             if (depth < a.min_reads) { c.base = 'N'; c.qual = 0; }
-            else if (a.fast_qual < a.min_cons_q) { c.base = 'N'; c.qual = 2; }
-            else { c.base = (0x54474341u >> (8u * w)) & 0xFFu; c.qual = a.fast_qual; }
+            else if (q < a.min_cons_q) { c.base = 'N'; c.qual = 2; }
+            else { c.base = (0x54474341u >> (8u * w)) & 0xFFu; c.qual = q; }
             done = true;
           }
         }
@@ -612,7 +665,7 @@ __device__ __forceinline__ void slow_pass_g(const VoteArgs& a, const VoteSmem& S
 // Group width (warp-uniform): 8 lanes per position (each lane strides the depth axis by 8) when no
 // queued pileup is deeper than 64 reads -- the planner's shallow-tile hint answers that without
 // looking -- else the whole warp per position.
-template <class M>
+template <class M, bool Cert = false>
 __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, const Stage& st,
                                           const TileView<M>& tv, const uint32_t* wqueue, uint32_t qn,
                                           uint32_t lane, LocalStats& ls) {
@@ -638,7 +691,7 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
 #define FGB_LANE_MIN_QUEUE 24u
 #endif
   if (shallow && (!FGB_SLOW_PER_LANE || qn < FGB_LANE_MIN_QUEUE)) {
-    slow_pass_g<M, 8u>(a, S, st, tv, wqueue, qn, lane, ls);
+    slow_pass_g<M, 8u, Cert>(a, S, st, tv, wqueue, qn, lane, ls);
   } else if (shallow) {
     // one lane per queued position: with at most 64 reads the depth loop is short, and 32 positions
     // per pass beat splitting each pileup over a group of lanes
@@ -646,12 +699,12 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
       const uint32_t ent = wqueue[e];
       const uint32_t u = ent >> 16, pos = ent & 0xFFFFu;
       const fgb_unit un = st.units[u];
-      const Called c = resolve_position<M>(tv, S, un.read_begin, st.units[u + 1].read_begin - un.read_begin,
-                                           pos, a, ls);
+      const Called c = resolve_position<M, Cert>(tv, S, un.read_begin, st.units[u + 1].read_begin - un.read_begin,
+                                                 pos, a, ls);
       write_called(a, un.out_off + pos, c);
     }
   } else {
-    slow_pass_g<M, 32u>(a, S, st, tv, wqueue, qn, lane, ls);
+    slow_pass_g<M, 32u, Cert>(a, S, st, tv, wqueue, qn, lane, ls);
   }
 }
 
@@ -663,8 +716,9 @@ __device__ __forceinline__ void slow_pass(const VoteArgs& a, const VoteSmem& S, 
 // to back at stride round_up(L, 8) and every unit calls L positions.  The read descriptors are then
 // redundant for the scan: read r of the tile starts at word (r - tile.read_begin) * m, m = stride/8.
 // V = 0: the general kernel; V = 1: the shallow-class kernel (tiles whose units have at most four reads):
-// two-read units take the pair table in line, three- and four-read units prove the fast path through the
-// SUM of the qualities (host_tables.cpp sumt) instead of their minimum.
+// two-read units take the pair table in line.  (A sum-of-qualities proof for three- and four-read units was
+// built and measured: the exact threshold -- host_tables.cpp sumt -- has to guard against one very low
+// quality among high ones and ends up above what the per-read minimum test already accepts; dropped.)
 template <class M, bool Regular, int V = 0>
 __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const Stage& st,
                                           const TileView<M>& tv, uint32_t vt, uint32_t warp,
@@ -832,44 +886,9 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
       }
     } else {
       const uint32_t qt = S.qt[n < kQtEntries ? n : kQtEntries - 1];
-      const uint32_t sumt = (V == 1 && (n == 3u || n == 4u)) ? a.tables->sumt[n] : 0xFFFFu;
-      const bool by_sum = V == 1 && sumt <= 255u;
-      const bool fast_ok = (by_sum || qt <= FGB_MAX_PHRED) && (n >= min_reads) && (n <= 0xFFFFu);
+      const bool fast_ok = (qt <= FGB_MAX_PHRED) && (n >= min_reads) && (n <= 0xFFFFu);
       uint32_t fm_lo = 0, fm_hi = 0, b0_lo = 0, b0_hi = 0;
-      if (V == 1 && by_sum && fast_ok) {
-        // three / four reads: every quality in 1..63 and the SUM of the qualities at or above the threshold
-        // proves sum D[q_i] > min(23, G2) (host_tables.cpp, exact dynamic programme over the gap table)
-        uint32_t diff_lo = 0, diff_hi = 0, minlen = 0xFFFFFFFFu;
-        uint32_t s_lo = 0, s_hi = 0, or_lo = 0, or_hi = 0, nz_lo = 0x40404040u, nz_hi = 0x40404040u;
-        typename M::addr_t rd = tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u;
-        for (uint32_t r = 0; r < n; ++r) {
-          typename M::off_t row;
-          uint32_t len;
-          if (Regular) { len = reg_len; row = reg_row0 + (reg_word + r * uni_m) * 8u; }
-          else {
-            const uint64_t d = M::ld64(rd + r * 8u);
-            len = static_cast<uint32_t>(d) & 0xFFFFu;
-            row = M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u);
-          }
-          minlen = len < minlen ? len : minlen;
-          const uint64_t wb = M::ld64(tv.bases + row);
-          const uint64_t wq = M::ld64(tv.quals + row);
-          if (r == 0) { b0_lo = static_cast<uint32_t>(wb); b0_hi = static_cast<uint32_t>(wb >> 32); }
-          diff_lo |= static_cast<uint32_t>(wb) ^ b0_lo;
-          diff_hi |= static_cast<uint32_t>(wb >> 32) ^ b0_hi;
-          const uint32_t ql = static_cast<uint32_t>(wq), qh = static_cast<uint32_t>(wq >> 32);
-          s_lo += ql; s_hi += qh;                          // bytes stay <= 4 * 63 while or_* proves q < 64
-          or_lo |= ql; or_hi |= qh;
-          nz_lo &= ql + 0x3F3F3F3Fu; nz_hi &= qh + 0x3F3F3F3Fu;   // bit 6 survives iff every q >= 1 (q < 64: no carries)
-        }
-        // a quality >= 64 anywhere in a word voids the whole word (its carry may have touched a neighbour)
-        const uint32_t okq_lo = (or_lo & 0xC0C0C0C0u) ? 0u : ((nz_lo << 1) & bytes_ge(s_lo, sumt));
-        const uint32_t okq_hi = (or_hi & 0xC0C0C0C0u) ? 0u : ((nz_hi << 1) & bytes_ge(s_hi, sumt));
-        const uint32_t covered = minlen > p0 ? minlen - p0 : 0u;
-        fm_lo = zero_bytes(diff_lo) & okq_lo & acgt_bytes(b0_lo) & low_bytes_mask(covered) & rm_lo;
-        fm_hi = zero_bytes(diff_hi) & okq_hi & acgt_bytes(b0_hi) &
-                low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
-      } else if (fast_ok) {
+      if (fast_ok) {
         const uint32_t tsplat = qt * 0x01010101u;
         uint32_t diff_lo = 0, diff_hi = 0, okq_lo = 0x80808080u, okq_hi = 0x80808080u;
         if (Regular) {
@@ -961,7 +980,7 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
     if (todo_lo | todo_hi) {                    // rare: the warp queue overflowed
       for (uint32_t j = 0; j < 8u; ++j) {
         if ((j < 4u ? todo_lo >> (8u * j) : todo_hi >> (8u * (j - 4u))) & 0x80u) {
-          Called c = resolve_position<M>(tv, S, rb, n, p0 + j, a, ls);
+          Called c = resolve_position<M, V == 1>(tv, S, rb, n, p0 + j, a, ls);
           write_called(a, o + j, c);
         }
       }
@@ -974,7 +993,7 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
   //  the warp + __syncwarp() orders the byte stores below after it)
   uint32_t qn = *wcount;
   qn = qn < kWarpQueueCap ? qn : kWarpQueueCap;
-  if (qn) slow_pass<M>(a, S, st, tv, wqueue, qn, lane, ls);
+  if (qn) slow_pass<M, V == 1>(a, S, st, tv, wqueue, qn, lane, ls);
   __syncwarp();
   if (lane == 0) *wcount = 0;
 }
@@ -1009,8 +1028,11 @@ __device__ __forceinline__ void vote_tile_deep(const VoteArgs& a, VoteSmem& S, c
   const uint32_t sub = tid & (g - 1u);
   const uint32_t per_round = static_cast<uint32_t>(kVoteThreads) >> gs;
 
+  // group j of warp w takes item base + j * 8 + w: the items -- and with them the queued positions -- are spread
+  // over all eight warps even when a tile has only 19 of them
+  const uint32_t in_round = ((lane >> gs) << 3) + warp;
   for (uint32_t base = 0; base < n_items; base += per_round) {
-    const uint32_t item_raw = base + (tid >> gs);
+    const uint32_t item_raw = base + in_round;
     const bool valid = item_raw < n_items;                  // idle groups shadow the last item; nothing of theirs is stored
     const uint32_t item = valid ? item_raw : n_items - 1u;
     uint32_t u;
@@ -1167,7 +1189,12 @@ __device__ __forceinline__ void vote_tile_deep(const VoteArgs& a, VoteSmem& S, c
   __syncwarp();
   uint32_t qn = *wcount;
   qn = qn < kWarpQueueCap ? qn : kWarpQueueCap;
-  if (qn) slow_pass<M>(a, S, st, tv, wqueue, qn, lane, ls);
+  if (qn) {
+    // eight lanes per queued position (four positions per pass) as long as a lane's share of the rows stays
+    // short; the whole warp per position for the oversize units voted from HBM
+    if (st.tile.flags & kTileFlagDirect) slow_pass_g<M, 32u>(a, S, st, tv, wqueue, qn, lane, ls);
+    else slow_pass_g<M, 8u>(a, S, st, tv, wqueue, qn, lane, ls);
+  }
   __syncwarp();
   if (lane == 0) *wcount = 0;
 }

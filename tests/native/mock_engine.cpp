@@ -112,6 +112,11 @@ void fgb_host_free(void* p) { std::free(p); }
 
 fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out) { return vote(h, in, out); }
 
+static void run_duplex_jobs(const fgb_batch* in, const fgb_columns* ss, const fgb_duplex_job* jobs, uint64_t n_jobs,
+                            const fgb_duplex_out* out);
+static void run_codec_jobs(const fgb_batch* in, const fgb_columns* ss, const fgb_codec_job* jobs, uint64_t n_jobs,
+                           const fgb_codec_params* cp, const fgb_codec_out* out);
+
 // FGB_IN_RECORDS restated on the host (unpack_kernels.cuh unpack_records_kernel): row position p is raw base p
 // (forward) or l_seq - 1 - p complemented (reverse); q < min_q -> (N, Q2); row padding is zero.
 void build_rows(const fgb_batch* in, const fgb_record_columns* rc, std::vector<uint8_t>* bases, std::vector<uint8_t>* quals) {
@@ -146,7 +151,6 @@ void build_rows(const fgb_batch* in, const fgb_record_columns* rc, std::vector<u
 fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out, const fgb_submit_options* opt) {
   if (!opt) return vote(h, in, out);
   if (opt->input_format != FGB_IN_BYTES && opt->input_format != FGB_IN_RECORDS) return FGB_ERR_INVALID_ARG;   // what the callers use
-  if (opt->n_duplex_jobs || opt->n_codec_jobs) return FGB_ERR_INVALID_ARG;
   fgb_batch b = *in;
   std::vector<uint8_t> rb, rq;
   if (opt->input_format == FGB_IN_RECORDS) {
@@ -164,6 +168,8 @@ fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* 
     if (!opt->unit_status) return FGB_ERR_INVALID_ARG;
     filter_units(&b, &cols, *opt->filter, opt->unit_status, opt->unit_masked);
   }
+  if (opt->n_duplex_jobs) run_duplex_jobs(&b, &cols, opt->duplex_jobs, opt->n_duplex_jobs, opt->duplex_out);
+  if (opt->n_codec_jobs) run_codec_jobs(&b, &cols, opt->codec_jobs, opt->n_codec_jobs, opt->codec_params, opt->codec_out);
   if (narrow) {
     uint8_t* d8 = reinterpret_cast<uint8_t*>(out->depth);
     uint8_t* e8 = reinterpret_cast<uint8_t*>(out->errors);
@@ -172,10 +178,8 @@ fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* 
   return FGB_OK;
 }
 
-fgb_status fgb_duplex_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss, const fgb_duplex_job* jobs,
-                             uint64_t n_jobs, uint64_t, const fgb_duplex_out* out) {
-  fgb_status st = vote(h, in, ss);
-  if (st != FGB_OK) return st;
+static void run_duplex_jobs(const fgb_batch* in, const fgb_columns* ss, const fgb_duplex_job* jobs, uint64_t n_jobs,
+                            const fgb_duplex_out* out) {
   std::vector<const uint8_t*> src; std::vector<size_t> len;
   for (uint64_t j = 0; j < n_jobs; ++j) {
     const fgb_unit &ua = in->units[jobs[j].unit_a], &ub = in->units[jobs[j].unit_b];
@@ -192,13 +196,18 @@ fgb_status fgb_duplex_submit(fgb_handle* h, const fgb_batch* in, const fgb_colum
                                 out->base + o, out->qual + o, out->errors + o, &n);
     if (out->status) out->status[j] = static_cast<uint8_t>(status);
   }
+}
+
+fgb_status fgb_duplex_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss, const fgb_duplex_job* jobs,
+                             uint64_t n_jobs, uint64_t, const fgb_duplex_out* out) {
+  fgb_status st = vote(h, in, ss);
+  if (st != FGB_OK) return st;
+  run_duplex_jobs(in, ss, jobs, n_jobs, out);
   return FGB_OK;
 }
 
-fgb_status fgb_codec_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss, const fgb_codec_job* jobs,
-                            uint64_t n_jobs, const fgb_codec_params* cp, uint64_t, const fgb_codec_out* out) {
-  fgb_status st = vote(h, in, ss);
-  if (st != FGB_OK) return st;
+static void run_codec_jobs(const fgb_batch* in, const fgb_columns* ss, const fgb_codec_job* jobs, uint64_t n_jobs,
+                           const fgb_codec_params* cp, const fgb_codec_out* out) {
   for (uint64_t j = 0; j < n_jobs; ++j) {
     const fgb_codec_job& job = jobs[j];
     const fgb_unit &ua = in->units[job.unit_a], &ub = in->units[job.unit_b];
@@ -216,6 +225,13 @@ fgb_status fgb_codec_submit(fgb_handle* h, const fgb_batch* in, const fgb_column
     if (out->disagreements) out->disagreements[j] = static_cast<uint32_t>(dis);
     if (out->duplex_bases) out->duplex_bases[j] = static_cast<uint32_t>(dup);
   }
+}
+
+fgb_status fgb_codec_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss, const fgb_codec_job* jobs,
+                            uint64_t n_jobs, const fgb_codec_params* cp, uint64_t, const fgb_codec_out* out) {
+  fgb_status st = vote(h, in, ss);
+  if (st != FGB_OK) return st;
+  run_codec_jobs(in, ss, jobs, n_jobs, cp, out);
   return FGB_OK;
 }
 
