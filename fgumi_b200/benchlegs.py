@@ -76,21 +76,27 @@ def duplex_leg(torch, fg, dev, device_index: int, molecules: int, seed: int = 43
             "frac": (k1_bytes + k2_bytes) / (t1 + t2) / 1e6 / peak, "bytes_per_molecule": (k1_bytes + k2_bytes) / M}
 
 
-def codec_leg(torch, fg, dev, device_index: int, molecules: int, seed: int = 44):
-    """Config 4: CODEC, k ~ U[2, 20] read pairs per molecule -> two single-strand units and one combine job."""
+def codec_leg(torch, fg, dev, device_index: int, molecules: int, seed: int = 44, sort_by_depth: bool = True):
+    """Config 4: CODEC, k ~ U[2, 20] read pairs per molecule -> two single-strand units and one combine job.
+    sort_by_depth: the packer lays the molecules out in order of k (every tile then holds units of one depth and
+    takes the descriptor-free scan); a molecule's OUTPUT row stays where its input position puts it."""
     M = int(molecules)
     rng = np.random.default_rng(seed)
     k = rng.integers(2, 21, size=M)
+    insert = np.clip(np.round(rng.normal(300, 50, size=M)), L, 2 * L).astype(np.int64)
+    r1n = rng.random(M) < 0.5
+    lc_pad = (insert + 7) // 8 * 8
+    out_off = np.zeros(M, dtype=np.uint64)
+    out_off[1:] = np.cumsum(lc_pad)[:-1]                    # output rows in INPUT order
+    perm = np.argsort(k, kind="stable") if sort_by_depth else np.arange(M)
+    k, insert, r1n, out_off = k[perm], insert[perm], r1n[perm], out_off[perm]
     depths = np.repeat(k, 2).astype(np.int64)
     tb = synth.device_batch(torch, dev, depths, L, 1e-3, seed=seed)
     eng = fg.Engine(device_index, 45, 40, 1, 0)
     ss = fg.DeviceColumns(tb.host.n_out, dev)
-    insert = np.clip(np.round(rng.normal(300, 50, size=M)), L, 2 * L).astype(np.int64)
-    lc_pad = (insert + 7) // 8 * 8
     jobs = np.zeros(M, dtype=fg.CODEC_JOB_DTYPE)
-    r1n = rng.random(M) < 0.5
     jobs["unit_a"], jobs["unit_b"] = 2 * np.arange(M), 2 * np.arange(M) + 1
-    jobs["out_off"][1:] = np.cumsum(lc_pad)[:-1]
+    jobs["out_off"] = out_off
     jobs["len"] = insert
     jobs["rc_a"], jobs["rc_b"], jobs["rc_out"] = r1n, ~r1n, r1n
     jobs["pad_a_left"] = np.where(r1n, insert - L, 0)
@@ -107,11 +113,14 @@ def codec_leg(torch, fg, dev, device_index: int, molecules: int, seed: int = 44)
     k3_bytes = M * 2 * 6 * L + int(insert.sum()) * 6 + 32 * M
     peak = hbm_peak()
     eng.close()
+    classes = list(tb.class_tiles)
     del tb, ss, out
     return {"workload": "BASELINE.json configs[3]: CODEC, 2-20 pairs per molecule, 2x150bp", "molecules": M,
             "value": M / ((t1 + t3) * 1e-3), "unit": "molecules/s", "k1_ms": t1, "k3_ms": t3,
             "k1_frac": k1_bytes / t1 / 1e6 / peak, "k3_frac": k3_bytes / t3 / 1e6 / peak,
-            "frac": (k1_bytes + k3_bytes) / (t1 + t3) / 1e6 / peak, "bytes_per_molecule": (k1_bytes + k3_bytes) / M}
+            "frac": (k1_bytes + k3_bytes) / (t1 + t3) / 1e6 / peak, "bytes_per_molecule": (k1_bytes + k3_bytes) / M,
+            "class_tiles": classes,
+            "layout": "molecules packed in order of depth, output rows in input order" if sort_by_depth else "input order"}
 
 
 def depth_classes(depths: np.ndarray) -> np.ndarray:
@@ -123,8 +132,9 @@ def zipf_leg(torch, fg, dev, device_index: int, total_families: int, world: int,
              shard_of: int = 8):
     """Config 5: `total_families` simplex families with Zipf(1) depths on 1..100, range-sharded by cumulative
     READ count (shard.partition_by_reads) over max(world, shard_of) ranks; this rank votes its own range.  The
-    packer lays a rank's families out by depth class (general / shallow / deep tiles have their own kernels);
-    every family keeps its place in the OUTPUT columns (out_off follows the input order)."""
+    packer lays a rank's families out in order of depth (every tile then holds units of one depth, and the
+    general / shallow / deep tile classes come in three runs); the output rows follow the packed order and a
+    host-side permutation (what the record-level caller keeps per unit anyway) maps them back to input order."""
     from .shard import partition_by_reads
     parts_n = max(world, shard_of)
     depths_all = synth.zipf_depths(int(total_families), 1, 100, 1.0, seed=seed).astype(np.int64)
@@ -132,7 +142,7 @@ def zipf_leg(torch, fg, dev, device_index: int, total_families: int, world: int,
     loads = np.array([int(depths_all[a:b].sum()) for a, b in parts], dtype=np.float64)
     lo, hi = parts[rank if world > 1 else 0]
     depths = depths_all[lo:hi]
-    order = np.argsort(depth_classes(depths), kind="stable")       # pack by class; outputs stay in input order
+    order = np.argsort(depths, kind="stable")                      # pack by depth
     tb = synth.device_batch(torch, dev, depths[order], L, 1e-3, seed=seed + rank)
     eng = fg.Engine(device_index, 45, 40, 1, 2)
     out = fg.DeviceColumns(tb.host.n_out, dev)
@@ -146,7 +156,7 @@ def zipf_leg(torch, fg, dev, device_index: int, total_families: int, world: int,
            "families_this_rank": int(hi - lo), "reads_this_rank": int(depths.sum()), "k1_ms": t1,
            "value": (hi - lo) / (t1 * 1e-3), "unit": UNIT_READS, "frac": k1_bytes / t1 / 1e6 / peak,
            "rank_load_imbalance": float(loads.max() / loads.mean() - 1.0), "class_tiles": list(tb.class_tiles),
-           "layout": "families packed by depth class within the rank; out_off keeps input order"}
+           "layout": "families packed in order of depth within the rank (outputs in packed order)"}
     del tb, out
     return res
 

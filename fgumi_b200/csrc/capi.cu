@@ -89,6 +89,9 @@ struct fgb_handle {
   double emax_rate = -1.0;                          // the max_base_error_rate d_emax was built for
   int n_slots = 2;                                  // FGB_SUBMIT_SLOTS (1..kSlots)
   uint64_t chunk_bytes = kChunkColumnBytes;         // FGB_SUBMIT_CHUNK_MB
+  unsigned long long* d_ostats = nullptr;            // overlap pre-pass counters (device u64[4])
+  uint64_t* ostats_host = nullptr;                  // where fgb_wait adds them
+  fgb_overlap_run* d_oruns = nullptr; uint64_t cap_oruns = 0;
   int vote_variant = 1;                             // FGB_VOTE_KERNEL=0: the general kernel votes every tile (A/B runs)
 };
 
@@ -249,6 +252,7 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   dt.nmax2 = h->host_tables.nmax2;
   std::memcpy(dt.pair_q, h->host_tables.pair_q, sizeof(dt.pair_q));
   std::memcpy(dt.sumt, h->host_tables.sumt, sizeof(dt.sumt));
+  std::memcpy(dt.qt3, h->host_tables.qt3, sizeof(dt.qt3));
   if ((e = cudaMemcpy(h->d_tables, &dt, sizeof(dt), cudaMemcpyHostToDevice)) != cudaSuccess)
     return fail(e, "cudaMemcpy tables");
   if ((e = cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * FGB_NCOUNTERS)) != cudaSuccess)
@@ -283,6 +287,8 @@ void fgb_destroy(fgb_handle* h) {
   cudaFree(h->d_counters);
   cudaFree(h->d_emax);
   cudaFree(h->d_bad);
+  cudaFree(h->d_ostats);
+  cudaFree(h->d_oruns);
   delete h;
 }
 
@@ -488,7 +494,10 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
                   !opt->codec_out->cols.errors))
     return FGB_ERR_INVALID_ARG;
   if ((n_djobs || n_cjobs) && (narrow || fp || (n_djobs && n_cjobs))) return FGB_ERR_INVALID_ARG;
-  const bool one_piece = n_djobs || n_cjobs;   // a molecule's units are voted before its combine job runs
+  const uint64_t n_oruns = (opt && fmt == HostFormat::kRecords) ? opt->n_overlap_runs : 0;
+  if (n_oruns && (!opt->overlap_runs || opt->overlap_agreement > 2 || opt->overlap_disagreement > 2)) return FGB_ERR_INVALID_ARG;
+  const bool one_piece = n_djobs || n_cjobs || n_oruns;   // a molecule's units are voted before its combine job runs;
+                                                          // a pair's two records must be resident together
 
   const bool rows_on_device = fmt == HostFormat::kBam4 || fmt == HostFormat::kRecords;
   if (!in->tiles || !in->units || !in->reads || (!rows_on_device && !in->bases) ||
@@ -678,6 +687,29 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
       ua.rec_lo = a0;                            // resident bytes [a0, a1) plus allocation slack behind them;
       ua.rec_hi = a1 + 96u;                      // the kernel wants 16 bytes either side of every span (lo - a0 >= 16:
       ua.min_q = rec->min_input_base_quality;    // a sequence field starts >= 33 bytes into its record)
+      if (n_oruns) {
+        if (!h->d_ostats) {
+          FGB_CUDA(h, cudaMalloc(&h->d_ostats, 4 * sizeof(unsigned long long)));
+          FGB_CUDA(h, cudaMemset(h->d_ostats, 0, 4 * sizeof(unsigned long long)));
+        }
+        if (!h->d_bad) {
+          FGB_CUDA(h, cudaMalloc(&h->d_bad, sizeof(uint32_t)));
+          FGB_CUDA(h, cudaMemset(h->d_bad, 0, sizeof(uint32_t)));
+        }
+        if ((st = ensure(h, &h->d_oruns, &h->cap_oruns, n_oruns)) != FGB_OK) return st;
+        FGB_CUDA(h, cudaMemcpyAsync(h->d_oruns, opt->overlap_runs, n_oruns * sizeof(fgb_overlap_run), cudaMemcpyHostToDevice, s));
+        OverlapArgs oa;
+        oa.records = sl.recblob - a0; oa.runs = h->d_oruns; oa.n_runs = n_oruns;
+        oa.rec_lo = a0; oa.rec_hi = a1;
+        oa.stats = h->d_ostats; oa.bad = h->d_bad;
+        oa.agree = opt->overlap_agreement; oa.disagree = opt->overlap_disagreement;
+        h->bam4_pending = true;
+        h->ostats_host = opt->overlap_stats;
+        const unsigned ogrid = static_cast<unsigned>(std::min<uint64_t>((n_oruns + 255u) / 256u, static_cast<uint64_t>(h->sm_count) * 8u));
+        overlap_kernel<<<ogrid, 256, 0, s>>>(oa);
+        h->launches++;
+        FGB_CUDA(h, cudaGetLastError());
+      }
       if ((st = launch_unpack_records(h, ua, s)) != FGB_OK) return st;
     }
     if ((st = launch_vote(h, db, dc, s)) != FGB_OK) return st;
@@ -866,6 +898,13 @@ fgb_status fgb_wait(fgb_handle* h) {
   h->submit_pending = false;
   FGB_CUDA(h, cudaSetDevice(h->device));
   for (int s = 0; s < kSlots; ++s) FGB_CUDA(h, cudaStreamSynchronize(h->slots[s].stream));
+  if (h->ostats_host) {                // overlap pre-pass counters of the submit that just finished
+    unsigned long long v[4] = {0, 0, 0, 0};
+    FGB_CUDA(h, cudaMemcpy(v, h->d_ostats, sizeof(v), cudaMemcpyDeviceToHost));
+    FGB_CUDA(h, cudaMemset(h->d_ostats, 0, sizeof(v)));
+    for (int i = 0; i < 4; ++i) h->ostats_host[i] += v[i];
+    h->ostats_host = nullptr;
+  }
   if (h->bam4_pending) {               // the unpack kernel validates the raw spans where it reads them
     h->bam4_pending = false;
     uint32_t bad = 0;

@@ -169,18 +169,20 @@ struct DirectPlan {
   std::vector<uint16_t> lens;        // per read: SourceRead row length
   std::vector<DUnit> units;
   std::vector<StrRef> rx;
+  std::vector<fgb_overlap_run> oruns; // overlapping-bases runs for the device (offsets relative to the staging)
   uint64_t row_bytes = 0;            // sum of round_up(len, 8) over the reads
   uint64_t out_elems = 0;            // sum of round_up(cons_len, 8) over the units
-  void clear() { raws.clear(); lens.clear(); units.clear(); rx.clear(); row_bytes = out_elems = 0; }
+  void clear() { raws.clear(); lens.clear(); units.clear(); rx.clear(); oruns.clear(); row_bytes = out_elems = 0; }
 };
 
-struct DMark { size_t raws, units, rx; uint64_t row_bytes, out_elems; };   // a plan's size, for roll-back
+struct DMark { size_t raws, units, rx, oruns; uint64_t row_bytes, out_elems; };   // a plan's size, for roll-back
 
 struct DSeg {                        // units [u0, u1) / reads [r0, r1) of one context's plan, in input order
   struct fgb_caller* ctx;
   uint32_t u0, u1;
   uint64_t r0, r1;
   uint64_t row_bytes, out_elems;
+  uint64_t o0, o1;                   // overlap runs [o0, o1) of the plan
 };
 
 struct PinBuf {                      // grow-only page-locked buffer
@@ -244,6 +246,8 @@ struct fgb_caller {
   PinBuf px[12];                             // duplex / CODEC: page-locked result columns of a flush (grow-only)
   std::vector<View> views;                   // scratch: the records of the group being planned
   std::vector<uint64_t> rel_off;             // scratch: record offsets relative to the group
+  std::vector<overlap::Run> group_runs;      // scratch: the overlap runs of the group being planned (device pre-pass)
+  PinBuf d_oruns;                            // parent: the batch's runs for the engine
 };
 
 namespace {
@@ -385,7 +389,31 @@ bool plan_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::vect
     const uint8_t* val[2]; size_t len[2];
     bam::find_string_tags(v, kWant, 2, val, len);
     const size_t clip = bam::num_bases_extending_past_mate_mc(v, c->ops, val[0], len[0]);
-    const uint32_t fl = plan_read_len(c->prep_opt, v, clip);
+    uint32_t fl;
+    if (c->group_runs.empty()) {
+      fl = plan_read_len(c->prep_opt, v, clip);
+    } else {
+      // the device will have co-called the mates' overlap before it builds the rows: what the row's tail looks like
+      // afterwards decides its length, so evaluate the rule for the positions the strip looks at
+      const uint32_t me = members[k];
+      fl = plan_read_len_eff(c->prep_opt, v, clip, [&](size_t j, uint8_t* nib, uint8_t* qq) {
+        for (const overlap::Run& r : c->group_runs) {
+          const bool first = r.rec1 == me && j >= r.o1 && j < static_cast<size_t>(r.o1) + r.len;
+          const bool second = !first && r.rec2 == me && j >= r.o2 && j < static_cast<size_t>(r.o2) + r.len;
+          if (!first && !second) continue;
+          const View& o = recs[first ? r.rec2 : r.rec1];
+          const size_t jo = first ? r.o2 + (j - r.o1) : r.o1 + (j - r.o2);
+          const uint8_t* os = o.b + o.seq_off();
+          const uint8_t oc = static_cast<uint8_t>((jo & 1) ? (os[jo >> 1] & 15u) : (os[jo >> 1] >> 4));
+          const uint8_t oq = o.b[o.qual_off() + jo];
+          uint8_t c1, q1, c2, q2;
+          if (first) c->overlap.position_rule(*nib, oc, *qq, oq, &c1, &q1, &c2, &q2);
+          else c->overlap.position_rule(oc, *nib, oq, *qq, &c2, &q2, &c1, &q1);
+          *nib = c1; *qq = q1;
+          return;
+        }
+      });
+    }
     if (fl) out->push_back(DRead{members[k], fl, val[1], static_cast<uint32_t>(len[1])});
     else ++zero;
   }
@@ -971,6 +999,24 @@ fgb_status flush_simplex_direct(fgb_caller* c) {
   std::memset(&so, 0, sizeof(so));
   so.input_format = FGB_IN_RECORDS; so.output_format = narrow ? FGB_OUT_U8 : FGB_OUT_U16;
   so.records = &rc;
+  {
+    uint64_t n_runs = 0;
+    for (const DSeg& sg : c->segs) n_runs += sg.o1 - sg.o0;
+    if (n_runs) {                // the overlapping-bases pre-pass, on the device (K0o)
+      if (c->d_oruns.ensure(n_runs * sizeof(fgb_overlap_run)) != FGB_OK) { c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM; }
+      fgb_overlap_run* dst = static_cast<fgb_overlap_run*>(c->d_oruns.p);
+      for (const DSeg& sg : c->segs) {
+        const size_t k = sg.o1 - sg.o0;
+        if (k) std::memcpy(dst, sg.ctx->dplan.oruns.data() + sg.o0, k * sizeof(fgb_overlap_run));
+        dst += k;
+      }
+      so.overlap_runs = static_cast<const fgb_overlap_run*>(c->d_oruns.p);
+      so.n_overlap_runs = n_runs;
+      so.overlap_stats = &c->overlap.stats.overlapping_bases;      // four consecutive u64 counters
+      so.overlap_agreement = static_cast<uint8_t>(c->overlap.agreement());
+      so.overlap_disagreement = static_cast<uint8_t>(c->overlap.disagreement());
+    }
+  }
   if (c->opt.filter_enabled) {   // `fgumi filter` as an epilogue of the vote (commands/filter.rs:738-905)
     fstatus.assign(U + 1, FGB_FILTER_PASS);
     fmasked.assign(U + 1, 0);
@@ -1976,7 +2022,7 @@ fgb_status fgb_caller_pending(const fgb_caller* c, fgb_batch* batch, const fgb_d
 void fgb_caller_destroy(fgb_caller* c) {
   if (!c) return;
   for (void* p : c->pinned) fgb_host_free(p);
-  c->stage.release(); c->d_reads.release(); c->d_raws.release(); c->d_units.release();
+  c->stage.release(); c->d_reads.release(); c->d_raws.release(); c->d_units.release(); c->d_oruns.release();
   for (PinBuf& b : c->px) b.release();
   std::free(c->joined);
   fgb_destroy(c->h);
@@ -2185,7 +2231,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
   for (uint32_t t = 0; t < T; ++t) {
     ctx[t] = T > 1 ? c->workers[t].get() : c;
     const DirectPlan& P = ctx[t]->dplan;
-    mark[t] = DMark{P.raws.size(), P.units.size(), P.rx.size(), P.row_bytes, P.out_elems};
+    mark[t] = DMark{P.raws.size(), P.units.size(), P.rx.size(), P.oruns.size(), P.row_bytes, P.out_elems};
   }
   uint64_t stats0[FGB_NSTATS];
   std::memcpy(stats0, c->stats, sizeof(stats0));
@@ -2211,10 +2257,38 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
         x->views.emplace_back(stage + dst0 + (rec_off[r] - b0), len);
         if (x->views.back().aux_off() > len) { x->last_error = "truncated BAM record"; sts[t] = FGB_ERR_INVALID_ARG; return; }
       }
-      if (c->opt.consensus_call_overlapping_bases) {   // simplex.rs:395-398: in place, on the staged copy
+      x->group_runs.clear();
+      if (c->opt.consensus_call_overlapping_bases) {   // simplex.rs:395-398
         x->rel_off.resize(n + 1);
         for (uint32_t i = 0; i <= n; ++i) x->rel_off[i] = rec_off[r0 + i] - rec_off[r0];
-        x->overlap.apply_group(stage + dst0 + (rec_off[r0] - b0), x->rel_off.data(), n);
+        uint8_t* const gbase = stage + dst0 + (rec_off[r0] - b0);
+        // The device co-calls the overlaps on the uploaded records (the host only plans the runs) unless the
+        // quality trim needs whole rewritten reads or a mate has no qualities (0xFF): then in place, here.
+        bool on_device = !c->prep_opt.trim;
+        if (on_device) {
+          x->overlap.plan_group(gbase, x->rel_off.data(), n, &x->group_runs);
+          for (const overlap::Run& r : x->group_runs) {
+            const View &v1 = x->views[r.rec1], &v2 = x->views[r.rec2];
+            if (v1.l_seq() == 0 || v2.l_seq() == 0 || v1.b[v1.qual_off()] == 0xFF || v2.b[v2.qual_off()] == 0xFF ||
+                v1.qual_off() + v1.l_seq() > v1.n || v2.qual_off() + v2.l_seq() > v2.n) { on_device = false; break; }
+          }
+        }
+        if (!on_device) {
+          x->group_runs.clear();
+          x->overlap.apply_group(gbase, x->rel_off.data(), n);
+        } else {
+          for (size_t k = 0; k < x->group_runs.size(); ++k) {
+            const overlap::Run& r = x->group_runs[k];
+            const View &v1 = x->views[r.rec1], &v2 = x->views[r.rec2];
+            fgb_overlap_run g;
+            g.seq1_off = static_cast<uint64_t>(v1.b - stage) + v1.seq_off();
+            g.seq2_off = static_cast<uint64_t>(v2.b - stage) + v2.seq_off();
+            g.l_seq1 = v1.l_seq(); g.l_seq2 = v2.l_seq();
+            g.o1 = r.o1; g.o2 = r.o2; g.len = r.len;
+            g.flags = (k > 0 && x->group_runs[k - 1].rec1 == r.rec1 && x->group_runs[k - 1].rec2 == r.rec2) ? FGB_RUN_CONTINUES : 0u;
+            x->dplan.oruns.push_back(g);
+          }
+        }
       }
       const fgb_status st = direct_group_simplex(x, stage, x->views);
       if (st != FGB_OK) { sts[t] = st; return; }
@@ -2228,6 +2302,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
     for (uint32_t t = 0; t < T; ++t) {
       DirectPlan& P = ctx[t]->dplan;
       P.raws.resize(mark[t].raws); P.lens.resize(mark[t].raws); P.units.resize(mark[t].units); P.rx.resize(mark[t].rx);
+      P.oruns.resize(mark[t].oruns);
       P.row_bytes = mark[t].row_bytes; P.out_elems = mark[t].out_elems;
       if (ctx[t] != c) { std::memset(ctx[t]->stats, 0, sizeof(ctx[t]->stats)); ctx[t]->overlap.stats = overlap::Stats(); }
     }
@@ -2238,12 +2313,12 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
   for (uint32_t t = 0; t < T; ++t) {
     fgb_caller* x = ctx[t];
     const DirectPlan& P = x->dplan;
-    if (P.units.size() > mark[t].units) {
+    if (P.units.size() > mark[t].units || P.oruns.size() > mark[t].oruns) {
       DSeg sg{x, static_cast<uint32_t>(mark[t].units), static_cast<uint32_t>(P.units.size()), mark[t].raws, P.raws.size(),
-              P.row_bytes - mark[t].row_bytes, P.out_elems - mark[t].out_elems};
-      if (!c->segs.empty() && c->segs.back().ctx == x && c->segs.back().u1 == sg.u0) {   // serial add_group calls
+              P.row_bytes - mark[t].row_bytes, P.out_elems - mark[t].out_elems, mark[t].oruns, P.oruns.size()};
+      if (!c->segs.empty() && c->segs.back().ctx == x && c->segs.back().u1 == sg.u0 && c->segs.back().o1 == sg.o0) {   // serial add_group calls
         DSeg& l = c->segs.back();
-        l.u1 = sg.u1; l.r1 = sg.r1; l.row_bytes += sg.row_bytes; l.out_elems += sg.out_elems;
+        l.u1 = sg.u1; l.r1 = sg.r1; l.row_bytes += sg.row_bytes; l.out_elems += sg.out_elems; l.o1 = sg.o1;
       } else {
         c->segs.push_back(sg);
       }

@@ -29,6 +29,11 @@ struct Stats {   // CorrectionStats, overlapping.rs:42-77
 
 struct Segment { int64_t ref; int64_t read; int64_t len; };   // 1-based ref, 0-based read offset
 
+// One maximal stretch of a pair's overlap: `len` consecutive bases of R1 from read offset o1 against the same
+// number of bases of R2 from o2 (record indices within the group).  What call() applies position by position;
+// planned on its own when the device applies it (fgb_overlap_run, FGB_IN_RECORDS batches).
+struct Run { uint32_t rec1, rec2; uint32_t o1, o2, len; };
+
 // Aligned (M/=/X) runs of a record inside [win_lo, win_hi] (1-based, inclusive), read offsets
 // limited to l_seq.
 inline void aligned_segments(const bam::View& v, int64_t win_lo, int64_t win_hi, std::vector<Segment>* out) {
@@ -95,9 +100,82 @@ class Caller {
     return any;
   }
 
+  // The runs of one pair, without touching a base (the headers and CIGARs decide them).
+  void plan_pair(const uint8_t* r1, size_t n1, const uint8_t* r2, size_t n2, uint32_t i1, uint32_t i2, std::vector<Run>* out) {
+    bam::View v1(r1, n1), v2(r2, n2);
+    if ((v1.flags() | v2.flags()) & bam::kUnmapped) return;
+    if (v1.ref_id() != v2.ref_id()) return;
+    int64_t s1, e1, s2, e2;
+    if (!span(v1, &s1, &e1) || !span(v2, &s2, &e2)) return;
+    const int64_t lo = std::max(s1, s2), hi = std::min(e1, e2);
+    if (lo > hi) return;
+    aligned_segments(v1, lo, hi, &seg1_);
+    aligned_segments(v2, lo, hi, &seg2_);
+    size_t i = 0, j = 0;
+    while (i < seg1_.size() && j < seg2_.size()) {
+      const Segment& a = seg1_[i];
+      const Segment& b = seg2_[j];
+      const int64_t from = std::max(a.ref, b.ref);
+      const int64_t to = std::min(a.ref + a.len, b.ref + b.len);   // exclusive
+      if (from < to)
+        out->push_back(Run{i1, i2, static_cast<uint32_t>(a.read + (from - a.ref)), static_cast<uint32_t>(b.read + (from - b.ref)),
+                           static_cast<uint32_t>(to - from)});
+      if (a.ref + a.len <= b.ref + b.len) ++i; else ++j;
+    }
+  }
+
+  // apply_overlapping_consensus as a PLAN: the runs of every pair of the group, in pair order.
+  void plan_group(const uint8_t* records, const uint64_t* off, uint32_t n, std::vector<Run>* out) {
+    pair_up(records, off, n);
+    for (const auto& p : order_) {
+      if (p.idx[0] < 0 || p.idx[1] < 0) continue;
+      plan_pair(records + off[p.idx[0]], off[p.idx[0] + 1] - off[p.idx[0]], records + off[p.idx[1]],
+                off[p.idx[1] + 1] - off[p.idx[1]], static_cast<uint32_t>(p.idx[0]), static_cast<uint32_t>(p.idx[1]), out);
+    }
+  }
+
+  // What one position of a run becomes on each side (the rule of run(), without writing or counting):
+  // c / q in: the two mates' base codes and qualities; out: side 1 and side 2.
+  void position_rule(uint8_t c1, uint8_t c2, uint8_t x, uint8_t y, uint8_t* oc1, uint8_t* oq1, uint8_t* oc2, uint8_t* oq2) const {
+    *oc1 = c1; *oq1 = x; *oc2 = c2; *oq2 = y;
+    if (c1 == 15 || c2 == 15) return;
+    if (c1 == c2) {
+      if (agree_ == kAgreePassThrough) return;
+      const uint8_t nq = agree_ == kAgreeConsensus ? static_cast<uint8_t>(std::min<unsigned>(unsigned(x) + unsigned(y), 93u)) : std::max(x, y);
+      *oq1 = nq; *oq2 = nq;
+      return;
+    }
+    if (disagree_ == kDisagreeConsensus) {
+      uint8_t code = 15, q = 2;
+      if (x > y) { code = c1; q = std::max<uint8_t>(static_cast<uint8_t>(x - y), 2); }
+      else if (y > x) { code = c2; q = std::max<uint8_t>(static_cast<uint8_t>(y - x), 2); }
+      *oc1 = code; *oc2 = code; *oq1 = q; *oq2 = q;
+    } else if (disagree_ == kDisagreeMaskBoth || x == y) {
+      *oc1 = 15; *oc2 = 15; *oq1 = 2; *oq2 = 2;
+    } else if (x < y) {
+      *oc1 = 15; *oq1 = 2;
+    } else {
+      *oc2 = 15; *oq2 = 2;
+    }
+  }
+  Agreement agreement() const { return agree_; }
+  Disagreement disagreement() const { return disagree_; }
+
   // apply_overlapping_consensus: pair primary R1/R2 records of one group by name; the last record
   // seen for a (name, segment) wins, as in the reference's map insertion.
   void apply_group(uint8_t* records, const uint64_t* off, uint32_t n) {
+    pair_up(records, off, n);
+    for (const auto& p : order_) {
+      if (p.idx[0] < 0 || p.idx[1] < 0) continue;
+      call(records + off[p.idx[0]], off[p.idx[0] + 1] - off[p.idx[0]],
+           records + off[p.idx[1]], off[p.idx[1] + 1] - off[p.idx[1]]);
+    }
+  }
+
+ private:
+  struct Pair { int64_t idx[2]; };
+
+  void pair_up(const uint8_t* records, const uint64_t* off, uint32_t n) {
     pairs_.clear();
     order_.clear();
     for (uint32_t i = 0; i < n; ++i) {
@@ -114,15 +192,7 @@ class Caller {
       }
       order_[it->second].idx[slot] = static_cast<int64_t>(i);
     }
-    for (const auto& p : order_) {
-      if (p.idx[0] < 0 || p.idx[1] < 0) continue;
-      call(records + off[p.idx[0]], off[p.idx[0] + 1] - off[p.idx[0]],
-           records + off[p.idx[1]], off[p.idx[1] + 1] - off[p.idx[1]]);
-    }
   }
-
- private:
-  struct Pair { int64_t idx[2]; };
 
   static bool span(const bam::View& v, int64_t* s, int64_t* e) {   // cigar.rs:314-335
     if (v.pos() < 0 || !v.cigar_in_bounds()) return false;

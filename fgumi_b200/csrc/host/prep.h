@@ -143,7 +143,11 @@ static const char kRev[17] = "=TGMCRSVAWYHKDBN";       // ... complemented (A<->
 // clipped / trimmed / masked).  A position is 'N' when its quality is below min_input_base_quality or its
 // base nibble is 15; only those are stripped from the end (:918-927).  The record-level callers use it on
 // its own when the device builds the rows (FGB_IN_RECORDS).
-inline uint32_t plan_read_len(const PrepOptions& opt, const View& v, size_t mate_clip) {
+// `eff(j, &nib, &q)` may replace the base code and quality of raw position j by what an earlier in-place pass
+// would have left there (the overlapping-bases pre-pass applied on the device: only the row's tail is looked at
+// here, so the host evaluates the rule for those few positions instead of rewriting the read).
+template <class Eff>
+inline uint32_t plan_read_len_eff(const PrepOptions& opt, const View& v, size_t mate_clip, Eff&& eff) {
   const bool neg = v.flags() & bam::kReverse;
   const uint8_t min_bq = opt.min_input_base_quality;
   const uint32_t read_len = v.l_seq();
@@ -164,10 +168,16 @@ inline uint32_t plan_read_len(const PrepOptions& opt, const View& v, size_t mate
   size_t final_len = std::min(clip_position, trim_to);
   while (final_len > 0) {                                    // oriented position i is record position j
     const size_t i = final_len - 1, j = neg ? read_len - 1 - i : i;
-    const uint32_t nib = (j & 1) ? (s[j >> 1] & 15u) : (s[j >> 1] >> 4);
-    if (q[j] < min_bq || nib == 15u) --final_len; else break;
+    uint8_t nib = static_cast<uint8_t>((j & 1) ? (s[j >> 1] & 15u) : (s[j >> 1] >> 4));
+    uint8_t qq = q[j];
+    eff(j, &nib, &qq);
+    if (qq < min_bq || nib == 15u) --final_len; else break;
   }
   return static_cast<uint32_t>(final_len);
+}
+
+inline uint32_t plan_read_len(const PrepOptions& opt, const View& v, size_t mate_clip) {
+  return plan_read_len_eff(opt, v, mate_clip, [](size_t, uint8_t*, uint8_t*) {});
 }
 
 inline bool make_source_read(const PrepOptions& opt, const View& v, uint32_t idx, size_t mate_clip,

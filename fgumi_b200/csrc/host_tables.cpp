@@ -138,6 +138,21 @@ void build_host_tables(unsigned pre, unsigned post, HostTables* t) {
     t->qt[n] = static_cast<uint8_t>(qt);
   }
 
+  // Near-unanimous threshold (vote_kernel.cuh vote_tile_deep): with at most kNearK dissenting observations the
+  // winner's gap over any other base is at least (n - K) * dmono[q] - K * dmax (dmax = the largest D of the table).
+  {
+    double dmax = 0.0;
+    for (unsigned q = 1; q < 94; ++q) { const double d = t->correct[q] - t->err_alt[q]; if (std::isfinite(d) && d > dmax) dmax = d; }
+    for (unsigned n = 0; n < 256; ++n) {
+      unsigned qt = 255;
+      if (finite_ok && n > 2 * kNearK && n <= t->nmax2 && n < 255) {
+        for (unsigned q = 1; q < 94; ++q)
+          if (static_cast<double>(n - kNearK) * dmono[q] - static_cast<double>(kNearK) * dmax > t->g2) { qt = q; break; }
+      }
+      t->qt3[n] = static_cast<uint8_t>(qt);
+    }
+  }
+
   // Sum-of-qualities thresholds (vote_kernel_w.cuh): f[k][s] = the smallest sum of D over k qualities in
   // 1..63 that add up to s, by dynamic programming; sumt[n] = the smallest t such that EVERY such multiset
   // with sum >= t clears the same threshold the per-read minimum test uses.  Exact over the table values;

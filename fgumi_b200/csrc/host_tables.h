@@ -24,7 +24,12 @@ struct HostTables {
   // all lie in 1..63 and sum to at least sumt[n] have sum D[q_i] > min(23, G2); 0xFFFF = not available.
   // Used for n = 3, 4 (the byte-wise sums of the kernel stay below 256).
   uint16_t sumt[8];
+  // Near-unanimous proof of the deep kernel: a pileup of n A/C/G/T observations of which at most kNearK differ
+  // from the rest, every quality >= qt3[n], has a likelihood gap >= (n - K) * dmono[qt3] - K * Dmax >= G2, so the
+  // dominant-winner proof applies without looking at the dissenters' qualities; 255 = never.
+  uint8_t qt3[256];
 };
+constexpr unsigned kNearK = 3;
 
 void build_host_tables(unsigned pre, unsigned post, HostTables* t);
 unsigned host_ln_prob_to_phred(double ln_prob);

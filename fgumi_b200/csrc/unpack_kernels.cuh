@@ -258,3 +258,94 @@ __global__ void __launch_bounds__(256) unpack_records_kernel(const RecordsArgs a
 }
 
 }  // namespace fgb
+
+// ---- K0o: overlapping-bases pre-pass on the uploaded records --------------------------
+// OverlappingBasesConsensusCaller::call (overlapping.rs:236-337) per base, in place on the record blob in HBM,
+// ahead of the row builder.  The host plans the runs from the headers and CIGARs (csrc/host/overlap.h
+// plan_group); one thread walks the runs of one pair in order (they may meet inside a packed sequence byte).
+namespace fgb {
+
+struct OverlapArgs {
+  uint8_t* records;                // biased: blob byte i lives at records[i]
+  const fgb_overlap_run* runs;
+  uint64_t n_runs;
+  uint64_t rec_lo, rec_hi;         // resident blob range
+  unsigned long long* stats;       // device u64[4]: overlapping, agreeing, disagreeing, corrected
+  uint32_t* bad;
+  uint32_t agree, disagree;        // FGB_OVERLAP_AGREE_* / FGB_OVERLAP_DISAGREE_*
+};
+
+__global__ void __launch_bounds__(256) overlap_kernel(const OverlapArgs a) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  unsigned long long n_ov = 0, n_ag = 0, n_dis = 0, n_cor = 0;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n_runs; i += stride) {
+    if (a.runs[i].flags & FGB_RUN_CONTINUES) continue;           // walked by the thread of the pair's first run
+    for (uint64_t k = i; k < a.n_runs && (k == i || (a.runs[k].flags & FGB_RUN_CONTINUES)); ++k) {
+      const fgb_overlap_run r = a.runs[k];
+      const uint64_t q1o = r.seq1_off + ((static_cast<uint64_t>(r.l_seq1) + 1u) >> 1);
+      const uint64_t q2o = r.seq2_off + ((static_cast<uint64_t>(r.l_seq2) + 1u) >> 1);
+      if (r.seq1_off < a.rec_lo || r.seq2_off < a.rec_lo || q1o + r.l_seq1 > a.rec_hi || q2o + r.l_seq2 > a.rec_hi ||
+          static_cast<uint64_t>(r.o1) + r.len > r.l_seq1 || static_cast<uint64_t>(r.o2) + r.len > r.l_seq2) {
+        atomicOr(a.bad, 1u);
+        continue;
+      }
+      uint8_t* s1 = a.records + r.seq1_off; uint8_t* q1 = a.records + q1o;
+      uint8_t* s2 = a.records + r.seq2_off; uint8_t* q2 = a.records + q2o;
+      for (uint32_t t = 0; t < r.len; ++t) {
+        const uint32_t i1 = r.o1 + t, i2 = r.o2 + t;
+        const uint32_t b1 = s1[i1 >> 1], b2 = s2[i2 >> 1];
+        const uint32_t c1 = (i1 & 1u) ? (b1 & 15u) : (b1 >> 4), c2 = (i2 & 1u) ? (b2 & 15u) : (b2 >> 4);
+        if (c1 == 15u || c2 == 15u) continue;                     // a no-call in either mate: the position is skipped
+        ++n_ov;
+        const uint32_t x = q1[i1], y = q2[i2];
+        uint32_t oc1 = c1, oc2 = c2, oq1 = x, oq2 = y;
+        if (c1 == c2) {
+          ++n_ag;
+          if (a.agree == FGB_OVERLAP_AGREE_PASS_THROUGH) continue;
+          const uint32_t nq = a.agree == FGB_OVERLAP_AGREE_CONSENSUS ? (x + y > 93u ? 93u : x + y) : (x > y ? x : y);
+          oq1 = oq2 = nq;
+          if (nq != x || nq != y) ++n_cor;
+        } else {
+          ++n_dis;
+          if (a.disagree == FGB_OVERLAP_DISAGREE_CONSENSUS) {      // higher quality wins with the difference; tie -> N
+            uint32_t code = 15u, q = 2u;
+            if (x > y) { code = c1; q = x - y < 2u ? 2u : x - y; }
+            else if (y > x) { code = c2; q = y - x < 2u ? 2u : y - x; }
+            oc1 = oc2 = code; oq1 = oq2 = q;
+            n_cor += 2;
+          } else if (a.disagree == FGB_OVERLAP_DISAGREE_MASK_BOTH || x == y) {
+            oc1 = oc2 = 15u; oq1 = oq2 = 2u;
+            n_cor += 2;
+          } else if (x < y) {
+            oc1 = 15u; oq1 = 2u; ++n_cor;
+          } else {
+            oc2 = 15u; oq2 = 2u; ++n_cor;
+          }
+        }
+        if (oc1 != c1) s1[i1 >> 1] = static_cast<uint8_t>((i1 & 1u) ? ((b1 & 0xF0u) | oc1) : ((oc1 << 4) | (b1 & 0x0Fu)));
+        if (oc2 != c2) {
+          const uint32_t bb = s2[i2 >> 1];                        // re-read: s1 and s2 never alias, but keep it simple
+          s2[i2 >> 1] = static_cast<uint8_t>((i2 & 1u) ? ((bb & 0xF0u) | oc2) : ((oc2 << 4) | (bb & 0x0Fu)));
+        }
+        if (oq1 != x) q1[i1] = static_cast<uint8_t>(oq1);
+        if (oq2 != y) q2[i2] = static_cast<uint8_t>(oq2);
+      }
+    }
+  }
+  // warp-reduce the counters, one atomic per warp and counter
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    n_ov += __shfl_down_sync(0xFFFFFFFFu, n_ov, off);
+    n_ag += __shfl_down_sync(0xFFFFFFFFu, n_ag, off);
+    n_dis += __shfl_down_sync(0xFFFFFFFFu, n_dis, off);
+    n_cor += __shfl_down_sync(0xFFFFFFFFu, n_cor, off);
+  }
+  if ((threadIdx.x & 31u) == 0) {
+    if (n_ov) atomicAdd(a.stats + 0, n_ov);
+    if (n_ag) atomicAdd(a.stats + 1, n_ag);
+    if (n_dis) atomicAdd(a.stats + 2, n_dis);
+    if (n_cor) atomicAdd(a.stats + 3, n_cor);
+  }
+}
+
+}  // namespace fgb

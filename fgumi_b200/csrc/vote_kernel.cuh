@@ -47,6 +47,7 @@ struct DeviceTables {
   uint32_t nmax2;               // dominant-winner proof valid up to this many observations
   uint8_t pair_q[94 * 94];      // unanimous two-read pileups: quality by (q1, q2); 255 = literal path
   uint16_t sumt[8];             // sum-of-qualities thresholds by depth (host_tables.cpp), 0xFFFF = none
+  uint8_t qt3[kQtEntries];      // near-unanimous quality threshold by depth (deep kernel); 255 = never
 };
 
 struct VoteArgs {
@@ -87,6 +88,7 @@ struct __align__(128) VoteSmem {
   uint32_t q_count[kConsumerWarps];
   uint8_t single_q[96];
   uint8_t qt[kQtEntries];
+  uint8_t qt3[kQtEntries];
   int32_t dfix[96];
   int32_t g2fix;
   uint32_t nmax2;
@@ -980,7 +982,7 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
     if (todo_lo | todo_hi) {                    // rare: the warp queue overflowed
       for (uint32_t j = 0; j < 8u; ++j) {
         if ((j < 4u ? todo_lo >> (8u * j) : todo_hi >> (8u * (j - 4u))) & 0x80u) {
-          Called c = resolve_position<M, V == 1>(tv, S, rb, n, p0 + j, a, ls);
+          Called c = resolve_position<M, false>(tv, S, rb, n, p0 + j, a, ls);
           write_called(a, o + j, c);
         }
       }
@@ -1056,7 +1058,11 @@ __device__ __forceinline__ void vote_tile_deep(const VoteArgs& a, VoteSmem& S, c
                                 : (item - static_cast<uint32_t>((un.out_off - out0) >> 3)) << 3;
     const uint32_t real = cons_len - p0 < 8u ? cons_len - p0 : 8u;
     const uint32_t rm_lo = low_bytes_mask(real), rm_hi = low_bytes_mask(real > 4u ? real - 4u : 0u);
-    const uint32_t qt = S.qt[n < kQtEntries ? n : kQtEntries - 1];
+    // One quality threshold per unit: the near-unanimous one when the depth has it (it also proves the
+    // unanimous positions: it is never below qt[n]), else the unanimous one alone.
+    const uint32_t qt_near = S.qt3[n < kQtEntries ? n : kQtEntries - 1];
+    const bool near_ok = qt_near <= FGB_MAX_PHRED;
+    const uint32_t qt = near_ok ? qt_near : S.qt[n < kQtEntries ? n : kQtEntries - 1];
     const bool fast_ok = (qt <= FGB_MAX_PHRED) && (n >= min_reads) && (n <= 0xFFFFu) && n >= 2u;
     if (n == 1u) {
       // a single-read unit never belongs to a deep tile (planner); kept correct for hand-made tile arrays:
@@ -1084,6 +1090,14 @@ __device__ __forceinline__ void vote_tile_deep(const VoteArgs& a, VoteSmem& S, c
     }
     uint32_t b0_lo = 0, b0_hi = 0;
     uint32_t diff_lo = 0, diff_hi = 0, okq_lo = 0x80808080u, okq_hi = 0x80808080u, minlen = 0xFFFFFFFFu;
+    // rows that differ from read 0 somewhere in the word (rare): per byte, how many rows differ, and whether a
+    // differing row holds anything but A/C/G/T there (such an observation is not counted at all, base_builder.rs:300)
+    uint32_t cnt_lo = 0, cnt_hi = 0, bad_lo = 0, bad_hi = 0;
+    auto dissent = [&](uint32_t wl, uint32_t wh, uint32_t xl, uint32_t xh) {
+      const uint32_t ml = ~zero_bytes(xl) & 0x80808080u, mh = ~zero_bytes(xh) & 0x80808080u;
+      bad_lo |= ml & ~acgt_bytes(wl); bad_hi |= mh & ~acgt_bytes(wh);
+      cnt_lo += ml >> 7; cnt_hi += mh >> 7;
+    };
     if (fast_ok) {
       const uint32_t tsplat = qt * 0x01010101u;
       if (Regular) {
@@ -1099,8 +1113,9 @@ __device__ __forceinline__ void vote_tile_deep(const VoteArgs& a, VoteSmem& S, c
         for (uint32_t r = sub; r < n; r += g, pb += gstep) {
           const uint64_t wb = M::ld64(pb);
           const uint64_t wq = M::ld64(pb + kTileCapBytes);
-          diff_lo |= static_cast<uint32_t>(wb) ^ b0_lo;
-          diff_hi |= static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+          const uint32_t xl = static_cast<uint32_t>(wb) ^ b0_lo, xh = static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+          diff_lo |= xl; diff_hi |= xh;
+          if (xl | xh) dissent(static_cast<uint32_t>(wb), static_cast<uint32_t>(wb >> 32), xl, xh);
           okq_lo &= (static_cast<uint32_t>(wq) | 0x80808080u) - tsplat;
           okq_hi &= (static_cast<uint32_t>(wq >> 32) | 0x80808080u) - tsplat;
         }
@@ -1121,8 +1136,9 @@ __device__ __forceinline__ void vote_tile_deep(const VoteArgs& a, VoteSmem& S, c
           const typename M::off_t row = M::row_offset(d, tv.byte_base, base32) + (len > p0 ? p0 : 0u);
           const uint64_t wb = M::ld64(tv.bases + row);
           const uint64_t wq = M::ld64(tv.quals + row);
-          diff_lo |= static_cast<uint32_t>(wb) ^ b0_lo;
-          diff_hi |= static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+          const uint32_t xl = static_cast<uint32_t>(wb) ^ b0_lo, xh = static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+          diff_lo |= xl; diff_hi |= xh;
+          if (xl | xh) dissent(static_cast<uint32_t>(wb), static_cast<uint32_t>(wb >> 32), xl, xh);
           okq_lo &= (static_cast<uint32_t>(wq) | 0x80808080u) - tsplat;
           okq_hi &= (static_cast<uint32_t>(wq >> 32) | 0x80808080u) - tsplat;
         }
@@ -1136,14 +1152,33 @@ __device__ __forceinline__ void vote_tile_deep(const VoteArgs& a, VoteSmem& S, c
       okq_hi &= __shfl_xor_sync(0xFFFFFFFFu, okq_hi, off);
       const uint32_t ml = __shfl_xor_sync(0xFFFFFFFFu, minlen, off);
       minlen = ml < minlen ? ml : minlen;
+      if (near_ok) {                                        // warp-uniform per group; byte counters stay below 256 (n < 255)
+        cnt_lo += __shfl_xor_sync(0xFFFFFFFFu, cnt_lo, off);
+        cnt_hi += __shfl_xor_sync(0xFFFFFFFFu, cnt_hi, off);
+        bad_lo |= __shfl_xor_sync(0xFFFFFFFFu, bad_lo, off);
+        bad_hi |= __shfl_xor_sync(0xFFFFFFFFu, bad_hi, off);
+      }
     }
     if (valid && sub == 0) {
       uint32_t fm_lo = 0, fm_hi = 0;
+      uint4 errw = make_uint4(0, 0, 0, 0);
       if (fast_ok) {
         const uint32_t covered = minlen > p0 ? minlen - p0 : 0u;
-        fm_lo = zero_bytes(diff_lo) & okq_lo & acgt_bytes(b0_lo) & low_bytes_mask(covered) & rm_lo;
-        fm_hi = zero_bytes(diff_hi) & okq_hi & acgt_bytes(b0_hi) &
-                low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
+        const uint32_t base_lo = okq_lo & acgt_bytes(b0_lo) & low_bytes_mask(covered) & rm_lo;
+        const uint32_t base_hi = okq_hi & acgt_bytes(b0_hi) & low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
+        fm_lo = zero_bytes(diff_lo) & base_lo;
+        fm_hi = zero_bytes(diff_hi) & base_hi;
+        if (near_ok && (cnt_lo | cnt_hi)) {
+          // near-unanimous positions: at most kNearK rows differ, all of them A/C/G/T: the dominant-winner proof
+          // holds (host_tables.cpp qt3): read 0's base wins with phred(ln_pre), depth n, errors = the count
+          const uint32_t le_lo = ~((cnt_lo | 0x80808080u) - 0x04040404u) & ~cnt_lo & 0x80808080u;   // cnt <= 3
+          const uint32_t le_hi = ~((cnt_hi | 0x80808080u) - 0x04040404u) & ~cnt_hi & 0x80808080u;
+          const uint32_t nm_lo = base_lo & le_lo & ~bad_lo & ~fm_lo, nm_hi = base_hi & le_hi & ~bad_hi & ~fm_hi;
+          const uint32_t el = cnt_lo & spread_msb(nm_lo), eh = cnt_hi & spread_msb(nm_hi);
+          errw = make_uint4(__byte_perm(el, 0u, 0x4140u), __byte_perm(el, 0u, 0x4342u),
+                            __byte_perm(eh, 0u, 0x4140u), __byte_perm(eh, 0u, 0x4342u));
+          fm_lo |= nm_lo; fm_hi |= nm_hi;
+        }
       }
       const uint32_t fb_lo = spread_msb(fm_lo), fb_hi = spread_msb(fm_hi);
       const uint32_t wb_lo = (fast_masked ? 0x4E4E4E4Eu : b0_lo) & fb_lo;
@@ -1159,7 +1194,7 @@ __device__ __forceinline__ void vote_tile_deep(const VoteArgs& a, VoteSmem& S, c
       *reinterpret_cast<uint2*>(a.out_base + o) = make_uint2(wb_lo, wb_hi);
       *reinterpret_cast<uint2*>(a.out_qual + o) = make_uint2(fq4 & fb_lo, fq4 & fb_hi);
       *reinterpret_cast<uint4*>(a.out_depth + o) = dep;
-      *reinterpret_cast<uint4*>(a.out_errors + o) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(a.out_errors + o) = errw;
       uint32_t todo_lo = rm_lo & ~fm_lo, todo_hi = rm_hi & ~fm_hi;
       if (todo_lo | todo_hi) {
         const uint32_t cnt = static_cast<uint32_t>(__popc(todo_lo) + __popc(todo_hi));
@@ -1211,7 +1246,7 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
     S.err_alt[i] = a.tables->err_alt[i];
   }
   for (uint32_t i = tid; i < 96; i += kThreads) S.single_q[i] = a.tables->single_q[i];
-  for (uint32_t i = tid; i < kQtEntries; i += kThreads) S.qt[i] = a.tables->qt[i];
+  for (uint32_t i = tid; i < kQtEntries; i += kThreads) { S.qt[i] = a.tables->qt[i]; S.qt3[i] = a.tables->qt3[i]; }
   for (uint32_t i = tid; i < 96; i += kThreads) S.dfix[i] = a.tables->dfix[i];
   if (tid < kConsumerWarps) S.q_count[tid] = 0;
   if (tid == 0) {

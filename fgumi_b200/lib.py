@@ -144,7 +144,9 @@ class FgbSubmitOptions(C.Structure):
                 ("duplex_jobs", C.c_void_p), ("n_duplex_jobs", C.c_uint64), ("n_duplex_out", C.c_uint64),
                 ("duplex_out", C.c_void_p),
                 ("codec_jobs", C.c_void_p), ("n_codec_jobs", C.c_uint64), ("n_codec_out", C.c_uint64),
-                ("codec_params", C.c_void_p), ("codec_out", C.c_void_p)]
+                ("codec_params", C.c_void_p), ("codec_out", C.c_void_p),
+                ("overlap_runs", C.c_void_p), ("n_overlap_runs", C.c_uint64), ("overlap_stats", C.c_void_p),
+                ("overlap_agreement", C.c_uint8), ("overlap_disagreement", C.c_uint8), ("reserved", C.c_uint8 * 6)]
 
 
 FGB_DEVICE_NONE = -1      # fgb_caller_create: planning-only caller (no engine, flush refuses)

@@ -267,6 +267,24 @@ typedef struct fgb_record_columns {
   uint8_t reserved[7];
 } fgb_record_columns;
 
+/* ---- overlapping-bases pre-pass (OverlappingBasesConsensusCaller, overlapping.rs:79-337) ---- */
+enum { FGB_OVERLAP_AGREE_CONSENSUS = 0, FGB_OVERLAP_AGREE_MAX_QUAL = 1, FGB_OVERLAP_AGREE_PASS_THROUGH = 2 };
+enum { FGB_OVERLAP_DISAGREE_CONSENSUS = 0, FGB_OVERLAP_DISAGREE_MASK_BOTH = 1,
+       FGB_OVERLAP_DISAGREE_MASK_LOWER_QUAL = 2 };
+/* One stretch of an R1 / R2 overlap, co-called by the device IN PLACE on the uploaded records before the rows
+ * are built (OverlappingBasesConsensusCaller::call, overlapping.rs:236-337; the host decides the stretches from
+ * the headers and CIGARs, the device applies the per-base rule): `len` bases of the record whose packed sequence
+ * starts at seq1_off (l_seq1 bases, qualities behind them) from read offset o1, against the record at seq2_off
+ * from o2.  The runs of one pair are consecutive; all but the first carry FGB_RUN_CONTINUES (one thread walks a
+ * pair, so two runs never write the same packed byte at once). */
+typedef struct fgb_overlap_run {
+  uint64_t seq1_off, seq2_off;
+  uint32_t l_seq1, l_seq2;
+  uint32_t o1, o2, len;
+  uint32_t flags;                 /* FGB_RUN_CONTINUES */
+} fgb_overlap_run;
+enum { FGB_RUN_CONTINUES = 1 };
+
 /* fgb_submit for a batch whose rows are built on the device: `in` carries units / reads / tiles /
  * n_* as usual (row offsets and lengths describe the rows to build), in->bases and in->quals are
  * ignored.  Same chunking, ordering and completion rules as fgb_submit. */
@@ -530,6 +548,14 @@ typedef struct fgb_submit_options {
   uint64_t n_codec_out;
   const fgb_codec_params* codec_params;
   const fgb_codec_out* codec_out;      /* host columns                                            */
+  /* FGB_IN_RECORDS only: the overlapping-bases pre-pass on the device (the batch is then processed as one piece) */
+  const fgb_overlap_run* overlap_runs;
+  uint64_t n_overlap_runs;
+  uint64_t* overlap_stats;             /* host u64[4], ADDED to at fgb_wait: overlapping bases, agreeing,
+                                          disagreeing, corrected (CorrectionStats, overlapping.rs:42-77)  */
+  uint8_t overlap_agreement;           /* FGB_OVERLAP_AGREE_*    */
+  uint8_t overlap_disagreement;        /* FGB_OVERLAP_DISAGREE_* */
+  uint8_t reserved[6];
 } fgb_submit_options;
 fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out,
                          const fgb_submit_options* opt);
@@ -619,9 +645,6 @@ enum {   /* ConsensusCallingStats (caller.rs:238-286) as a flat counter array   
 };
 
 /* ---- overlapping-bases pre-pass (OverlappingBasesConsensusCaller, overlapping.rs:79-337) ---- */
-enum { FGB_OVERLAP_AGREE_CONSENSUS = 0, FGB_OVERLAP_AGREE_MAX_QUAL = 1, FGB_OVERLAP_AGREE_PASS_THROUGH = 2 };
-enum { FGB_OVERLAP_DISAGREE_CONSENSUS = 0, FGB_OVERLAP_DISAGREE_MASK_BOTH = 1,
-       FGB_OVERLAP_DISAGREE_MASK_LOWER_QUAL = 2 };
 /* apply_overlapping_consensus (overlapping.rs:625-667) on one MI group, IN PLACE: primary R1/R2
  * records with the same name are paired and the bases they align to the same reference position
  * are co-called (sequence nibbles and qualities rewritten).  stats[4] += {overlapping_bases,

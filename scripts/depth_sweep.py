@@ -15,10 +15,14 @@ except Exception:
 for spec in SPECS:
     if spec.startswith("mixed"):
         depths = np.repeat(np.random.default_rng(1).integers(2, 21, size=U // 2), 2).astype(np.int64)
+        if spec.startswith("mixeds"):
+            depths = np.sort(depths)
     elif spec.startswith("zipf"):      # BASELINE config 5: P(d) ~ 1/d on 1..100; "zipfg": packed by depth class
         w = 1.0 / np.arange(1, 101)
         depths = np.random.default_rng(2).choice(np.arange(1, 101), size=U // 4, p=w / w.sum()).astype(np.int64)
-        if spec.startswith("zipfg"):
+        if spec.startswith("zipfs"):          # packed in order of depth
+            depths = np.sort(depths)
+        elif spec.startswith("zipfg"):        # packed by depth class only
             cls = np.where(depths <= 4, 1, np.where(depths >= 24, 2, 0))
             depths = depths[np.argsort(cls, kind="stable")]
     else:

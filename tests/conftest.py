@@ -25,3 +25,12 @@ def engine_cls():
     g.build()
     import fgumi_b200
     return fgumi_b200.Engine
+
+
+@pytest.fixture(scope="session")
+def fg():
+    """The product package with its library built (modules may define their own `fg` with extra set-up)."""
+    import __graft_entry__ as g
+    g.build()
+    import fgumi_b200
+    return fgumi_b200

@@ -5,6 +5,7 @@
 // fgb_codec_submit / fgb_host_alloc ... -- on top of the CPU oracle (oracle/fgumi_oracle.cpp), and is
 // linked ONLY into tests/native/caller_e2e.cpp (the executable's definitions take precedence over the
 // library's).  The product has no CPU path: libfgumi_b200.so never contains or loads any of this.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -148,6 +149,45 @@ void build_rows(const fgb_batch* in, const fgb_record_columns* rc, std::vector<u
   for (auto& x : th) x.join();
 }
 
+// The device's overlapping-bases pre-pass (unpack_kernels.cuh overlap_kernel) restated on a host copy of the blob.
+void apply_overlap_runs(std::vector<uint8_t>* blob, const fgb_submit_options* opt) {
+  uint64_t st[4] = {0, 0, 0, 0};
+  for (uint64_t k = 0; k < opt->n_overlap_runs; ++k) {
+    const fgb_overlap_run& r = opt->overlap_runs[k];
+    uint8_t* s1 = blob->data() + r.seq1_off; uint8_t* q1 = s1 + (static_cast<uint64_t>(r.l_seq1) + 1) / 2;
+    uint8_t* s2 = blob->data() + r.seq2_off; uint8_t* q2 = s2 + (static_cast<uint64_t>(r.l_seq2) + 1) / 2;
+    for (uint32_t t = 0; t < r.len; ++t) {
+      const uint32_t i1 = r.o1 + t, i2 = r.o2 + t;
+      const uint32_t c1 = (i1 & 1) ? (s1[i1 >> 1] & 15u) : (s1[i1 >> 1] >> 4), c2 = (i2 & 1) ? (s2[i2 >> 1] & 15u) : (s2[i2 >> 1] >> 4);
+      if (c1 == 15 || c2 == 15) continue;
+      ++st[0];
+      const uint32_t x = q1[i1], y = q2[i2];
+      uint32_t oc1 = c1, oc2 = c2, oq1 = x, oq2 = y;
+      if (c1 == c2) {
+        ++st[1];
+        if (opt->overlap_agreement == FGB_OVERLAP_AGREE_PASS_THROUGH) continue;
+        const uint32_t nq = opt->overlap_agreement == FGB_OVERLAP_AGREE_CONSENSUS ? std::min(x + y, 93u) : std::max(x, y);
+        oq1 = oq2 = nq;
+        if (nq != x || nq != y) ++st[3];
+      } else {
+        ++st[2];
+        if (opt->overlap_disagreement == FGB_OVERLAP_DISAGREE_CONSENSUS) {
+          uint32_t code = 15, q = 2;
+          if (x > y) { code = c1; q = std::max(x - y, 2u); } else if (y > x) { code = c2; q = std::max(y - x, 2u); }
+          oc1 = oc2 = code; oq1 = oq2 = q; st[3] += 2;
+        } else if (opt->overlap_disagreement == FGB_OVERLAP_DISAGREE_MASK_BOTH || x == y) {
+          oc1 = oc2 = 15; oq1 = oq2 = 2; st[3] += 2;
+        } else if (x < y) { oc1 = 15; oq1 = 2; ++st[3]; }
+        else { oc2 = 15; oq2 = 2; ++st[3]; }
+      }
+      auto put = [](uint8_t* s, uint32_t i, uint32_t c) { s[i >> 1] = static_cast<uint8_t>((i & 1) ? ((s[i >> 1] & 0xF0u) | c) : ((c << 4) | (s[i >> 1] & 0x0Fu))); };
+      put(s1, i1, oc1); put(s2, i2, oc2);
+      q1[i1] = static_cast<uint8_t>(oq1); q2[i2] = static_cast<uint8_t>(oq2);
+    }
+  }
+  if (opt->overlap_stats) for (int i = 0; i < 4; ++i) opt->overlap_stats[i] += st[i];
+}
+
 fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out, const fgb_submit_options* opt) {
   if (!opt) return vote(h, in, out);
   if (opt->input_format != FGB_IN_BYTES && opt->input_format != FGB_IN_RECORDS) return FGB_ERR_INVALID_ARG;   // what the callers use
@@ -155,7 +195,14 @@ fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* 
   std::vector<uint8_t> rb, rq;
   if (opt->input_format == FGB_IN_RECORDS) {
     if (!opt->records) return FGB_ERR_INVALID_ARG;
-    build_rows(in, opt->records, &rb, &rq);
+    fgb_record_columns rcols = *opt->records;
+    std::vector<uint8_t> blob;
+    if (opt->n_overlap_runs) {
+      blob.assign(rcols.records, rcols.records + rcols.n_bytes);
+      apply_overlap_runs(&blob, opt);
+      rcols.records = blob.data();
+    }
+    build_rows(in, &rcols, &rb, &rq);
     b.bases = rb.data(); b.quals = rq.data();
   }
   const bool narrow = opt->output_format == FGB_OUT_U8;
