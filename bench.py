@@ -343,6 +343,10 @@ def bench_records(torch, dist, fg, lib, dev, local, world, rank, args, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         r["value"] = float(t[0].item())
         r["note"] = f"sum over {world} ranks, {threads} host threads each (cgroup CPU quota {cpu_quota()})"
+        # ConsensusCallingStats::merge (caller.rs:278-285): all 24 host counters of the ranks' callers, one all-reduce
+        cs = torch.tensor(r.get("caller_stats") or [0] * 24, dtype=torch.int64, device=dev)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+        r["caller_stats"] = [int(x) for x in cs.tolist()]
     if rank == 0 and world == 1 and args.cpu_units > 0:
         try:
             r["cpu_baseline"] = benchlegs.records_cpu_baseline(min(args.record_families, 50000), cpu_quota())

@@ -195,6 +195,11 @@ class _Caller:
             raise _l.FgbError(st, "fgb_caller_flush", buf.value.decode(errors="replace"))
         return data.value, int(n.value), int(cnt.value)
 
+    def stats(self):
+        arr = (C.c_uint64 * _l.FGB_NSTATS)()
+        self.lib.fgb_caller_stats(self.h, arr)
+        return [int(x) for x in arr]
+
     def close(self):
         if self.h:
             self.lib.fgb_caller_destroy(self.h)
@@ -242,7 +247,7 @@ def records_leg(torch, fg, lib, device_index: int, families: int, n_threads: int
 
     def run(ncall, threads_each):
         cs = [_Caller(lib, device_index, threads_each) for _ in range(ncall)]
-        out = {"count": 0, "bytes": 0}
+        out = {"count": 0, "bytes": 0, "stats": None}
 
         def worker(c, n):
             for _ in range(n):
@@ -261,6 +266,10 @@ def records_leg(torch, fg, lib, device_index: int, families: int, n_threads: int
                 for t in th:
                     t.join()
             dt = time.perf_counter() - t0
+            st = np.zeros(_l.FGB_NSTATS, dtype=np.int64)
+            for c in cs:
+                st += np.array(c.stats(), dtype=np.int64)
+            out["stats"] = st
         finally:
             for c in cs:
                 c.close()
@@ -278,6 +287,7 @@ def records_leg(torch, fg, lib, device_index: int, families: int, n_threads: int
                 "h2d_bytes_per_batch": int(R * rec_len + R * 24 + G * 16), "d2h_bytes_per_batch": int(G * Lo * 4),
                 "input_bytes_per_batch": int(R * rec_len), "output_bytes_per_batch": int(o1["bytes"]),
                 "consensus_reads_per_batch": int(o1["count"]),
+                "caller_stats": [int(x) for x in o1["stats"]],
                 "api": "fgb_caller_add_groups + fgb_caller_flush (raw BAM records in page-locked host memory -> "
                        "ConsensusOutput bytes in host memory; records staged, shipped whole, rows built on the device)"})
     del pinned

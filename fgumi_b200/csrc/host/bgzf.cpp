@@ -29,7 +29,11 @@ struct Zlib {
   int (*deflateEnd)(z_streamp) = nullptr;
   int (*deflateReset)(z_streamp) = nullptr;
   uLong (*crc32)(uLong, const Bytef*, uInt) = nullptr;
-  bool ok = false;
+  int (*inflateInit2_)(z_streamp, int, const char*, int) = nullptr;
+  int (*inflate)(z_streamp, int) = nullptr;
+  int (*inflateEnd)(z_streamp) = nullptr;
+  int (*inflateReset)(z_streamp) = nullptr;
+  bool ok = false, ok_inflate = false;
 };
 
 const Zlib& zlib() {
@@ -45,6 +49,11 @@ const Zlib& zlib() {
     z.deflateReset = reinterpret_cast<decltype(z.deflateReset)>(dlsym(z.handle, "deflateReset"));
     z.crc32 = reinterpret_cast<decltype(z.crc32)>(dlsym(z.handle, "crc32"));
     z.ok = z.deflateInit2_ && z.deflate && z.deflateEnd && z.deflateReset && z.crc32;
+    z.inflateInit2_ = reinterpret_cast<decltype(z.inflateInit2_)>(dlsym(z.handle, "inflateInit2_"));
+    z.inflate = reinterpret_cast<decltype(z.inflate)>(dlsym(z.handle, "inflate"));
+    z.inflateEnd = reinterpret_cast<decltype(z.inflateEnd)>(dlsym(z.handle, "inflateEnd"));
+    z.inflateReset = reinterpret_cast<decltype(z.inflateReset)>(dlsym(z.handle, "inflateReset"));
+    z.ok_inflate = z.crc32 && z.inflateInit2_ && z.inflate && z.inflateEnd && z.inflateReset;
   });
   return z;
 }
@@ -128,6 +137,132 @@ fgb_status fgb_bam_header(const char* sam_text, size_t l_text, uint8_t* out, siz
   if (l_text) std::memcpy(out + 8, sam_text, l_text);
   put32(out + 8 + l_text, 0);
   *out_len = total;
+  return FGB_OK;
+}
+
+// ---- reading (the input side of a file-level run: fgumi-bgzf reader.rs, raw-bam record framing) ----------------
+namespace {
+uint32_t get16(const uint8_t* p) { return p[0] | (static_cast<uint32_t>(p[1]) << 8); }
+uint32_t get32(const uint8_t* p) { return get16(p) | (get16(p + 2) << 16); }
+
+struct Member { size_t off, size, isize, out_off; };
+
+// Walks the gzip members of a BGZF stream (SAM spec 4.1: BSIZE in the "BC" extra subfield).
+bool scan_members(const uint8_t* d, size_t len, std::vector<Member>* out, size_t* total) {
+  size_t p = 0, o = 0;
+  while (p < len) {
+    if (len - p < kHeader + kFooter || d[p] != 0x1f || d[p + 1] != 0x8b || d[p + 2] != 8 || !(d[p + 3] & 4)) return false;
+    const size_t xlen = get16(d + p + 10);
+    size_t q = p + 12, bsize = 0;
+    if (q + xlen > len) return false;
+    while (q + 4 <= p + 12 + xlen) {
+      const size_t slen = get16(d + q + 2);
+      if (d[q] == 'B' && d[q + 1] == 'C' && slen == 2 && q + 6 <= len) bsize = get16(d + q + 4) + 1u;
+      q += 4 + slen;
+    }
+    if (bsize < 12 + xlen + kFooter || p + bsize > len) return false;
+    const size_t isize = get32(d + p + bsize - 4);
+    out->push_back(Member{p + 12 + xlen, bsize - 12 - xlen - kFooter, isize, o});
+    o += isize;
+    p += bsize;
+  }
+  *total = o;
+  return true;
+}
+}  // namespace
+
+// Sum of the members' ISIZE fields: the size fgb_bgzf_decompress needs.
+fgb_status fgb_bgzf_uncompressed_size(const uint8_t* data, size_t len, size_t* size) {
+  if ((len && !data) || !size) return FGB_ERR_INVALID_ARG;
+  std::vector<Member> m;
+  if (!scan_members(data, len, &m, size)) return FGB_ERR_LAYOUT;
+  return FGB_OK;
+}
+
+// Inflates every member at its place in `out`, members dealt to n_threads threads; CRC32 and ISIZE are checked.
+fgb_status fgb_bgzf_decompress(const uint8_t* data, size_t len, uint32_t n_threads, uint8_t* out, size_t cap,
+                               size_t* out_len) {
+  if ((len && !data) || !out_len || (cap && !out)) return FGB_ERR_INVALID_ARG;
+  const Zlib& z = zlib();
+  if (!z.ok_inflate) return FGB_ERR_INVALID_ARG;
+  std::vector<Member> m;
+  size_t total = 0;
+  if (!scan_members(data, len, &m, &total)) return FGB_ERR_LAYOUT;
+  if (total > cap) return FGB_ERR_INVALID_ARG;
+  const uint32_t T = std::max<uint32_t>(1, std::min<uint32_t>(n_threads ? n_threads : 1, static_cast<uint32_t>(std::max<size_t>(m.size(), 1))));
+  std::vector<int> failed(T, 0);
+  auto work = [&](uint32_t t) {
+    z_stream zs;
+    std::memset(&zs, 0, sizeof(zs));
+    if (z.inflateInit2_(&zs, -15, ZLIB_VERSION, static_cast<int>(sizeof(z_stream))) != Z_OK) { failed[t] = 1; return; }
+    // contiguous runs of members per thread (sequential output per thread)
+    const size_t a = m.size() * t / T, e = m.size() * (t + 1) / T;
+    for (size_t i = a; i < e; ++i) {
+      const Member& mb = m[i];
+      if (z.inflateReset(&zs) != Z_OK) { failed[t] = 1; break; }
+      zs.next_in = const_cast<Bytef*>(data + mb.off);
+      zs.avail_in = static_cast<uInt>(mb.size);
+      zs.next_out = out + mb.out_off;
+      zs.avail_out = static_cast<uInt>(mb.isize);
+      const int rc = z.inflate(&zs, Z_FINISH);
+      if (!(rc == Z_STREAM_END || (rc == Z_OK && mb.isize == 0) || (rc == Z_BUF_ERROR && mb.isize == 0)) || zs.avail_out != 0) { failed[t] = 1; break; }
+      const uint32_t crc = static_cast<uint32_t>(z.crc32(z.crc32(0, nullptr, 0), out + mb.out_off, static_cast<uInt>(mb.isize)));
+      if (crc != get32(data + mb.off + mb.size)) { failed[t] = 1; break; }
+    }
+    z.inflateEnd(&zs);
+  };
+  std::vector<std::thread> th;
+  for (uint32_t t = 1; t < T; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  for (int f : failed) if (f) return FGB_ERR_LAYOUT;
+  *out_len = total;
+  return FGB_OK;
+}
+
+// The header of an (uncompressed) BAM stream: "BAM\1", l_text, text, n_ref, references (l_name, name, l_ref).
+// *text_off / *text_len locate the SAM text, *records_off the first record's block_size word.
+fgb_status fgb_bam_read_header(const uint8_t* bam, size_t len, size_t* text_off, size_t* text_len, uint32_t* n_ref,
+                               size_t* records_off) {
+  if (!bam || !records_off || len < 12 || std::memcmp(bam, "BAM\1", 4) != 0) return FGB_ERR_LAYOUT;
+  const size_t l_text = get32(bam + 4);
+  if (8 + l_text + 4 > len) return FGB_ERR_LAYOUT;
+  size_t p = 8 + l_text;
+  const uint32_t nr = get32(bam + p);
+  p += 4;
+  for (uint32_t i = 0; i < nr; ++i) {
+    if (p + 4 > len) return FGB_ERR_LAYOUT;
+    const size_t l_name = get32(bam + p);
+    if (p + 4 + l_name + 4 > len) return FGB_ERR_LAYOUT;
+    p += 4 + l_name + 4;
+  }
+  if (text_off) *text_off = 8;
+  if (text_len) *text_len = l_text;
+  if (n_ref) *n_ref = nr;
+  *records_off = p;
+  return FGB_OK;
+}
+
+// The record section of a BAM stream ([u32 block_size][record]...) as the callers take it: the record bodies
+// back to back in `bodies` (may be `stream` itself: the copy only moves bytes down) and rec_off[0..n] with record
+// i at [rec_off[i], rec_off[i+1]).  Stops at the first incomplete record; *consumed = bytes of `stream` used.
+fgb_status fgb_bam_split_records(const uint8_t* stream, size_t len, uint8_t* bodies, uint64_t* rec_off, uint64_t cap_records,
+                                 uint64_t* n_records, size_t* consumed) {
+  if ((len && !stream) || !bodies || !rec_off || !n_records) return FGB_ERR_INVALID_ARG;
+  size_t p = 0, w = 0;
+  uint64_t n = 0;
+  rec_off[0] = 0;
+  while (p + 4 <= len && n < cap_records) {
+    const size_t bs = get32(stream + p);
+    if (bs < 32) return FGB_ERR_LAYOUT;
+    if (p + 4 + bs > len) break;
+    std::memmove(bodies + w, stream + p + 4, bs);
+    w += bs;
+    p += 4 + bs;
+    rec_off[++n] = w;
+  }
+  *n_records = n;
+  if (consumed) *consumed = p;
   return FGB_OK;
 }
 

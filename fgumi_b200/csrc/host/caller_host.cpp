@@ -344,6 +344,10 @@ fgb_status add_group_simplex(fgb_caller* c, const std::vector<View>& recs) {
     else if (f & bam::kFirst) r1.push_back(i);
     else if (f & bam::kLast) r2.push_back(i);
   }
+  if (frag.size() > 0xFFFFu || r1.size() > 0xFFFFu || r2.size() > 0xFFFFu) {
+    c->last_error = "a sub-group (fragment / R1 / R2 reads of one MI) has more than 65535 reads";
+    return FGB_ERR_UNIT_TOO_LARGE;
+  }
   Prepared &pf = c->prepared[0], &p1 = c->prepared[1], &p2 = c->prepared[2];   // pooled across groups
   prepare_subgroup(c, recs, frag, &pf);
   if (pf.ok) { pack_simplex_unit(c, recs, pf, kFragment, umi); c->stats[FGB_STAT_CONSENSUS_READS] += 1; }
@@ -551,15 +555,15 @@ fgb_status direct_group_simplex(fgb_caller* c, const uint8_t* stage, const std::
   if (kept.size() != n_records) reject(c, FGB_STAT_REJ_SECONDARY_SUPPLEMENTARY, n_records - kept.size());
   if (kept.empty()) return FGB_OK;
   if (kept.size() < c->opt.min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, kept.size()); return FGB_OK; }
-  if (kept.size() > 0xFFFFu) {
-    c->last_error = "an MI group has more than 65535 reads";
-    return FGB_ERR_UNIT_TOO_LARGE;
-  }
   for (uint32_t i : kept) {   // subgroup_reads, vanilla_caller.rs:1018-1039
     const uint16_t f = recs[i].flags();
     if (!(f & bam::kPaired)) frag.push_back(i);
     else if (f & bam::kFirst) r1.push_back(i);
     else if (f & bam::kLast) r2.push_back(i);
+  }
+  if (frag.size() > 0xFFFFu || r1.size() > 0xFFFFu || r2.size() > 0xFFFFu) {   // u16 observation counters, base_builder.rs:236
+    c->last_error = "a sub-group (fragment / R1 / R2 reads of one MI) has more than 65535 reads";
+    return FGB_ERR_UNIT_TOO_LARGE;
   }
   static thread_local std::vector<DRead> df, d1, d2;
   size_t sf, s1, s2;
@@ -2055,6 +2059,14 @@ static fgb_status caller_add_group_impl(fgb_caller* c, const uint8_t* records, c
     if (len < 32) { c->last_error = "BAM record shorter than its fixed header"; return FGB_ERR_INVALID_ARG; }
     recs.emplace_back(records + rec_off[i], len);
     if (recs.back().aux_off() > len) { c->last_error = "truncated BAM record"; return FGB_ERR_INVALID_ARG; }
+    if (recs.back().l_seq() > FGB_MAX_READ_LEN) {      // a row descriptor holds 16 bits of length
+      c->last_error = "a read is longer than 65535 bases (FGB_MAX_READ_LEN)";
+      return FGB_ERR_UNIT_TOO_LARGE;
+    }
+  }
+  if (n_records > 0xFFFFu && c->opt.mode != FGB_MODE_SIMPLEX) {   // u16 observation counters (base_builder.rs:236): say so
+    c->last_error = "an MI group has more than 65535 reads";       // now, not at flush time with every other group queued
+    return FGB_ERR_UNIT_TOO_LARGE;                                  // (simplex checks its three sub-groups)
   }
   if (c->opt.consensus_call_overlapping_bases) {   // simplex.rs:395-398, duplex.rs:464-467
     const uint64_t base = rec_off[0], total = rec_off[n_records] - base;

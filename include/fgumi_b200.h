@@ -343,6 +343,20 @@ size_t fgb_bgzf_bound(size_t len);
 fgb_status fgb_bgzf_compress(const uint8_t* data, size_t len, int level, uint32_t n_threads, int append_eof,
                              uint8_t* out, size_t cap, size_t* out_len);
 fgb_status fgb_bam_header(const char* sam_text, size_t l_text, uint8_t* out, size_t cap, size_t* out_len);
+/* The input side of a file-level run (the reference's fgumi-bgzf reader.rs and raw-bam record framing; host code):
+ *   fgb_bgzf_uncompressed_size  sum of the members' ISIZE fields
+ *   fgb_bgzf_decompress         every member inflated at its place in `out` (cap >= that sum) on n_threads threads,
+ *                               CRC32 / ISIZE checked; FGB_ERR_LAYOUT for a stream that is not BGZF
+ *   fgb_bam_read_header         locates the SAM text and the first record of an uncompressed BAM stream
+ *   fgb_bam_split_records       [u32 block_size][record]... -> record bodies back to back + rec_off[0..n], the form
+ *                               fgb_host_group_by_mi and fgb_caller_add_groups take; `bodies` may be `stream` */
+fgb_status fgb_bgzf_uncompressed_size(const uint8_t* data, size_t len, size_t* size);
+fgb_status fgb_bgzf_decompress(const uint8_t* data, size_t len, uint32_t n_threads, uint8_t* out, size_t cap,
+                               size_t* out_len);
+fgb_status fgb_bam_read_header(const uint8_t* bam, size_t len, size_t* text_off, size_t* text_len, uint32_t* n_ref,
+                               size_t* records_off);
+fgb_status fgb_bam_split_records(const uint8_t* stream, size_t len, uint8_t* bodies, uint64_t* rec_off,
+                                 uint64_t cap_records, uint64_t* n_records, size_t* consumed);
 
 /*   fgb_host_duplex_record  duplex_read_into (duplex_caller.rs:1048-1285, methylation off): the BAM record
  *                           (block_size word included) of one duplex consensus read.  `ab` / `ba` are the
@@ -677,7 +691,13 @@ fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uin
  * With options.n_threads > 1 the per-group host work (filtering, source-read preparation, CIGAR
  * grouping, ...) runs on that many threads over contiguous ranges of groups and the results are
  * merged in input order, so the output is identical to calling fgb_caller_add_group in a loop.  This
- * is the reference's "one caller per worker" (simplex.rs:574) folded behind one call. */
+ * is the reference's "one caller per worker" (simplex.rs:574) folded behind one call.
+ * Errors: a group whose first record lacks the UMI tag (FGB_ERR_MISSING_TAG), a malformed record
+ * (FGB_ERR_INVALID_ARG / FGB_ERR_LAYOUT: offsets must ascend), a read longer than FGB_MAX_READ_LEN or a group of
+ * more than 65535 reads (FGB_ERR_UNIT_TOO_LARGE) fail the CALL.  A simplex caller with a device (rows built on
+ * the device) then leaves nothing of the failing call queued, whatever n_threads is; the host-decode callers
+ * (duplex, CODEC, planning-only) keep the groups in front of the failing one when n_threads <= 1 and drop the whole
+ * call otherwise.  Work queued by earlier calls is never touched. */
 fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
                                  const uint64_t* group_rec, uint64_t n_groups);
 /* Votes everything queued (one fgb_submit) and returns the concatenated ConsensusOutput of all

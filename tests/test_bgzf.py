@@ -90,3 +90,35 @@ def test_write_bam_helper(tmp_path):
     fg.write_bam(str(path), b"@HD\tVN:1.6\n", out, level=5, n_threads=2)
     raw = gzip.decompress(open(path, "rb").read())
     assert raw[:4] == b"BAM\x01" and raw.endswith(recs[-1]) and open(path, "rb").read().endswith(EOF_BLOCK)
+
+
+def test_bgzf_reader_and_record_split_round_trip(tmp_path):
+    """The input side of a file-level run: fgb_bgzf_decompress (members on threads, CRC checked), the BAM header
+    reader and the in-place record split give back exactly the records that were written."""
+    import fgumi_b200 as fg
+    from fgumi_b200 import bamio
+    rng = np.random.default_rng(5)
+    recs = [make_record(name=b"r%d" % i, flags=0, pos=i, seq=bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(1, 200)))),
+                        tags=[(b"MI", "Z", b"%d" % (i // 3))]) for i in range(3000)]
+    text = b"@HD\tVN:1.6\n@SQ\tSN:chr1\tLN:1000\n@RG\tID:A\tSM:s\n"
+    hdr = b"BAM\1" + struct.pack("<I", len(text)) + text + struct.pack("<I", 1) + struct.pack("<I", 5) + b"chr1\0" + struct.pack("<I", 1000)
+    data = hdr + b"".join(struct.pack("<I", len(r)) + r for r in recs)
+    path = tmp_path / "in.bam"
+    path.write_bytes(bgzf(data, level=1, threads=3))
+    got_text, bodies, rec_off, tm = bamio.read_bam(str(path), n_threads=3)
+    assert got_text == text and len(rec_off) == len(recs) + 1
+    assert tm["uncompressed_bytes"] == len(data)
+    for i in (0, 1, 17, 2999):
+        assert bodies[int(rec_off[i]):int(rec_off[i + 1])].tobytes() == recs[i]
+    assert bodies.tobytes() == b"".join(recs)
+    groups = bamio.group_by_mi(bodies, rec_off)
+    assert len(groups) == 1001 and int(groups[-1]) == 3000 and int(groups[1]) == 3
+    # a corrupted member is refused
+    lib = fg.lib.load()
+    comp = np.frombuffer(path.read_bytes(), np.uint8).copy()
+    comp[40] ^= 0x55
+    out = np.zeros(len(data) + 16, np.uint8)
+    n = C.c_size_t()
+    assert lib.fgb_bgzf_decompress(comp.ctypes.data, len(comp), 2, out.ctypes.data, len(out), C.addressof(n)) != 0
+    hdr_out = bamio.output_header(text, "A")
+    assert hdr_out.startswith(b"@HD\tVN:1.6\tSO:unknown\tGO:query\n@RG\tID:A\tSM:s\n") and b"@PG\tID:fgumi_b200" in hdr_out
