@@ -14,6 +14,8 @@ NVCC_FLAGS = [
     "-maxrregcount=112",      # upper bound only; vote_kernel must land at <= 96 (see _check_vote_kernel)
     "-fmad=false",            # no FMA contraction anywhere near the f64 vote (DESIGN.md numerics)
     "-Xcompiler", "-fPIC", "-shared",
+    # host code (record parsing / assembly loops): AVX2-class auto-vectorisation; every B200 host has it
+    "-Xcompiler", "-march=x86-64-v3", "-Xcompiler", "-ffp-contract=off",
 ]
 
 

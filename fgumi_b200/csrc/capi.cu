@@ -366,6 +366,12 @@ fgb_status fgb_host_alloc(void** p, size_t bytes) {
   return FGB_OK;
 }
 void fgb_host_free(void* p) { if (p) cudaFreeHost(p); }
+int fgb_host_is_pinned(const void* p) {
+  if (!p) return 0;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return at.type == cudaMemoryTypeHost ? 1 : 0;
+}
 
 }  // extern "C"
 

@@ -362,60 +362,6 @@ __device__ __forceinline__ SsCol padded_column(const CodecArgs& a, const fgb_uni
   return c;
 }
 
-// ---- word path helpers: eight consecutive columns of a single-strand consensus per lane ----
-// Eight elements of a byte column starting at element `smin` of the row at `row` (8-aligned, `lpad` = padded
-// length); elements outside [0, lpad) read as zero.  smin may be anything from -7 up.
-__device__ __forceinline__ uint64_t window8(const uint8_t* col, uint64_t row, uint32_t lpad, int32_t smin) {
-  const int32_t a0 = smin & ~7;                              // floor to a multiple of 8 (two's complement)
-  const uint32_t sh = static_cast<uint32_t>(smin - a0) * 8u;
-  const uint64_t w0 = (a0 >= 0 && static_cast<uint32_t>(a0) < lpad) ? *reinterpret_cast<const uint64_t*>(col + row + a0) : 0ull;
-  const uint64_t w1 = (a0 + 8 >= 0 && static_cast<uint32_t>(a0 + 8) < lpad) ? *reinterpret_cast<const uint64_t*>(col + row + a0 + 8) : 0ull;
-  return sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0;
-}
-// The same for a u16 column: eight u16 as four words.  k = smin mod 8 is the same for every lane of a job.
-__device__ __forceinline__ uint4 window16(const uint16_t* col, uint64_t row, uint32_t lpad, int32_t smin) {
-  const int32_t a0 = smin & ~7;
-  const uint32_t k = static_cast<uint32_t>(smin - a0);
-  uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-  if (a0 >= 0 && static_cast<uint32_t>(a0) < lpad) q0 = *reinterpret_cast<const uint4*>(col + row + a0);
-  if (a0 + 8 >= 0 && static_cast<uint32_t>(a0 + 8) < lpad) q1 = *reinterpret_cast<const uint4*>(col + row + a0 + 8);
-  const uint32_t W[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-  const uint32_t sh = (k & 1u) * 16u;
-  uint4 r;
-  switch (k >> 1) {                                          // warp-uniform
-    case 0: r = make_uint4(__funnelshift_r(W[0], W[1], sh), __funnelshift_r(W[1], W[2], sh), __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh)); break;
-    case 1: r = make_uint4(__funnelshift_r(W[1], W[2], sh), __funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh)); break;
-    case 2: r = make_uint4(__funnelshift_r(W[2], W[3], sh), __funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh), __funnelshift_r(W[5], W[6], sh)); break;
-    default: r = make_uint4(__funnelshift_r(W[3], W[4], sh), __funnelshift_r(W[4], W[5], sh), __funnelshift_r(W[5], W[6], sh), __funnelshift_r(W[6], W[7], sh)); break;
-  }
-  return r;
-}
-__device__ __forceinline__ uint64_t reverse8(uint64_t w) {
-  return (static_cast<uint64_t>(__byte_perm(static_cast<uint32_t>(w), 0u, 0x0123u)) << 32) |
-         __byte_perm(static_cast<uint32_t>(w >> 32), 0u, 0x0123u);
-}
-__device__ __forceinline__ uint4 reverse16x8(uint4 v) {
-  return make_uint4(__byte_perm(v.w, 0u, 0x1032u), __byte_perm(v.z, 0u, 0x1032u), __byte_perm(v.y, 0u, 0x1032u), __byte_perm(v.x, 0u, 0x1032u));
-}
-
-// The eight columns [i0, i0 + 8) (ascending i) of a strand after orientation and padding, as registers:
-// bases / quals in two 64-bit words (byte j = column i0 + j), depths / errors as 8 x u16.  Columns outside the
-// strand are masked by the caller (pad_consensus: 'n', 0, 0, 0), which also complements the bases when rc.
-struct SsWords { uint64_t base, qual; uint4 depth, err; };
-__device__ __forceinline__ SsWords padded_words(const CodecArgs& a, const fgb_unit& un, int32_t i0, uint32_t pad_left, bool rc) {
-  const uint32_t L = un.cons_len, lpad = (L + 7u) & ~7u;
-  // column i -> strand position p = i - pad_left -> stored index s = rc ? L-1-p : p
-  const int32_t p0 = i0 - static_cast<int32_t>(pad_left);
-  const int32_t smin = rc ? static_cast<int32_t>(L) - 1 - (p0 + 7) : p0;       // stored index of the window's lowest element
-  SsWords w;
-  w.base = window8(a.ss_base, un.out_off, lpad, smin);
-  w.qual = window8(a.ss_qual, un.out_off, lpad, smin);
-  w.depth = window16(a.ss_depth, un.out_off, lpad, smin);
-  w.err = window16(a.ss_errors, un.out_off, lpad, smin);
-  if (rc) { w.base = reverse8(w.base); w.qual = reverse8(w.qual); w.depth = reverse16x8(w.depth); w.err = reverse16x8(w.err); }
-  return w;
-}
-
 __global__ void __launch_bounds__(kCombineThreads) codec_combine_kernel(const CodecArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t warp0 = static_cast<uint64_t>(blockIdx.x) * kCodecJobsPerCta + (threadIdx.x >> 5);
@@ -429,93 +375,7 @@ __global__ void __launch_bounds__(kCombineThreads) codec_combine_kernel(const Co
     const uint32_t outer_len = a.cp.outer_bases_length;
     const uint32_t outer_hi = len > outer_len ? len - outer_len : 0u;   // saturating_sub, :1205
     uint32_t n_dup = 0, n_dis = 0;
-    const bool word_path = (job.out_off & 7u) == 0 && ((ua.out_off | ub.out_off) & 7u) == 0;
-    // Word path: a lane owns eight consecutive OUTPUT columns (aligned vector stores); the matching input columns
-    // of both strands are eight consecutive stored elements each, fetched as (shifted, possibly reversed) windows.
-    for (uint32_t o0 = lane * 8u; word_path && o0 < len; o0 += 256u) {
-      const uint32_t live = len - o0 < 8u ? len - o0 : 8u;                     // output columns of this word
-      // output column oi <- combined column i = rc_out ? len-1-oi : oi; work on ascending i, flip at the end
-      const int32_t i0 = job.rc_out ? static_cast<int32_t>(len) - 1 - static_cast<int32_t>(o0 + 7u) : static_cast<int32_t>(o0);
-      const SsWords A8 = padded_words(a, ua, i0, job.pad_a_left, job.rc_a != 0);
-      const SsWords B8 = padded_words(a, ub, i0, job.pad_b_left, job.rc_b != 0);
-      const uint32_t Ad[4] = {A8.depth.x, A8.depth.y, A8.depth.z, A8.depth.w}, Ae[4] = {A8.err.x, A8.err.y, A8.err.z, A8.err.w};
-      const uint32_t Bd[4] = {B8.depth.x, B8.depth.y, B8.depth.z, B8.depth.w}, Be[4] = {B8.err.x, B8.err.y, B8.err.z, B8.err.w};
-      uint64_t ob = 0, oq = 0;
-      uint32_t od[4] = {0, 0, 0, 0}, oe[4] = {0, 0, 0, 0};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int32_t i = i0 + j;
-        if (i < 0 || i >= static_cast<int32_t>(len)) continue;                 // beyond the consensus (last word)
-        const int32_t pa = i - static_cast<int32_t>(job.pad_a_left), pb = i - static_cast<int32_t>(job.pad_b_left);
-        SsCol A, B;
-        if (pa >= 0 && pa < static_cast<int32_t>(ua.cons_len)) {
-          A.base = static_cast<uint32_t>(A8.base >> (8 * j)) & 0xFFu; A.qual = static_cast<uint32_t>(A8.qual >> (8 * j)) & 0xFFu;
-          A.depth = (Ad[j >> 1] >> (16 * (j & 1))) & 0xFFFFu; A.err = (Ae[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-          if (job.rc_a) A.base = complement_base(A.base);
-        } else { A.base = 'n'; A.qual = 0; A.depth = 0; A.err = 0; }
-        if (pb >= 0 && pb < static_cast<int32_t>(ub.cons_len)) {
-          B.base = static_cast<uint32_t>(B8.base >> (8 * j)) & 0xFFu; B.qual = static_cast<uint32_t>(B8.qual >> (8 * j)) & 0xFFu;
-          B.depth = (Bd[j >> 1] >> (16 * (j & 1))) & 0xFFFFu; B.err = (Be[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-          if (job.rc_b) B.base = complement_base(B.base);
-        } else { B.base = 'n'; B.qual = 0; B.depth = 0; B.err = 0; }
-        const bool a_has = A.base != 'N' && A.base != 'n';           // :1064-1065
-        const bool b_has = B.base != 'N' && B.base != 'n';
-        uint32_t dbase, dqual, depth, err;
-        if (a_has && b_has) {                                        // :1068-1113
-          ++n_dup;
-          uint32_t raw_base, raw_qual;
-          if (A.base == B.base) {
-            raw_base = A.base;
-            const uint32_t sq = A.qual + B.qual;
-            raw_qual = sq > 93u ? 93u : sq;
-          } else if (A.qual > B.qual) {
-            ++n_dis; raw_base = A.base;
-            const uint32_t d = A.qual - B.qual; raw_qual = d < 2u ? 2u : d;
-          } else if (B.qual > A.qual) {
-            ++n_dis; raw_base = B.base;
-            const uint32_t d = B.qual - A.qual; raw_qual = d < 2u ? 2u : d;
-          } else {
-            ++n_dis; raw_base = A.base; raw_qual = 2u;
-          }
-          if (raw_qual == 2u) { dbase = 'N'; dqual = 2u; } else { dbase = raw_base; dqual = raw_qual; }
-          if (A.base == B.base) err = A.err + B.err;
-          else if (A.base == raw_base) err = A.err + (B.depth > B.err ? B.depth - B.err : 0u);
-          else err = B.err + (A.depth > A.err ? A.depth - A.err : 0u);
-          depth = A.depth + B.depth;
-        } else if (a_has) {                                          // :1115-1122
-          if (A.qual == 2u) { dbase = 'N'; dqual = 2u; } else { dbase = A.base; dqual = A.qual; }
-          depth = A.depth; err = A.err;
-        } else if (b_has) {                                          // :1124-1131
-          if (B.qual == 2u) { dbase = 'N'; dqual = 2u; } else { dbase = B.base; dqual = B.qual; }
-          depth = B.depth; err = B.err;
-        } else {                                                     // :1133-1139
-          dbase = 'N'; dqual = 2u; depth = 0; err = A.err + B.err;
-        }
-        if (A.base == 'N' || B.base == 'N') { dbase = 'N'; dqual = 2u; }   // :1145-1149
-        if ((A.base == 'N' || B.base == 'N') && dbase != 'N') {            // mask_consensus_quals_query_based, :1191-1209
-          if (a.cp.single_strand_qual >= 0) dqual = static_cast<uint32_t>(a.cp.single_strand_qual);
-        }
-        if (a.cp.outer_bases_qual >= 0) {
-          if (static_cast<uint32_t>(i) < outer_len || static_cast<uint32_t>(i) >= outer_hi) {
-            const uint32_t oqv = static_cast<uint32_t>(a.cp.outer_bases_qual);
-            dqual = dqual < oqv ? dqual : oqv;
-          }
-        }
-        // final re-orientation, :783-784: ascending i is descending output column when rc_out
-        const int jj = job.rc_out ? 7 - j : j;
-        const uint32_t obv = job.rc_out ? complement_base(dbase) : dbase;
-        ob |= static_cast<uint64_t>(obv & 0xFFu) << (8 * jj);
-        oq |= static_cast<uint64_t>(dqual & 0xFFu) << (8 * jj);
-        od[jj >> 1] |= (depth & 0xFFFFu) << (16 * (jj & 1));
-        oe[jj >> 1] |= (err & 0xFFFFu) << (16 * (jj & 1));
-      }
-      (void)live;
-      *reinterpret_cast<uint64_t*>(a.out_base + job.out_off + o0) = ob;
-      *reinterpret_cast<uint64_t*>(a.out_qual + job.out_off + o0) = oq;
-      *reinterpret_cast<uint4*>(a.out_depth + job.out_off + o0) = make_uint4(od[0], od[1], od[2], od[3]);
-      *reinterpret_cast<uint4*>(a.out_errors + job.out_off + o0) = make_uint4(oe[0], oe[1], oe[2], oe[3]);
-    }
-    for (uint32_t i = lane; !word_path && i < len; i += 32) {
+    for (uint32_t i = lane; i < len; i += 32) {
       SsCol A = padded_column(a, ua, i, job.pad_a_left, job.rc_a != 0);
       SsCol B = padded_column(a, ub, i, job.pad_b_left, job.rc_b != 0);
       const bool a_has = A.base != 'N' && A.base != 'n';           // :1064-1065

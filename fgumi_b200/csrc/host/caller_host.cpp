@@ -242,6 +242,7 @@ struct fgb_caller {
   std::vector<DSeg> segs;                    // parent: ranges of the plans in input order
   PinBuf stage;                              // parent: the staged records
   size_t stage_len = 0;
+  const uint8_t* zc_base = nullptr;          // parent: zero-copy batch (options.zero_copy_records): the caller's own page-locked blob
   PinBuf d_reads, d_raws, d_units;           // parent: descriptor arrays handed to the engine
   PinBuf px[12];                             // duplex / CODEC: page-locked result columns of a flush (grow-only)
   std::vector<View> views;                   // scratch: the records of the group being planned
@@ -994,7 +995,7 @@ fgb_status flush_simplex_direct(fgb_caller* c) {
   fgb_columns cols{o_base, o_qual, static_cast<uint16_t*>(c->pinned[2]), static_cast<uint16_t*>(c->pinned[3])};
   fgb_record_columns rc;
   std::memset(&rc, 0, sizeof(rc));
-  rc.n_bytes = c->stage_len; rc.records = static_cast<const uint8_t*>(c->stage.p); rc.raw_reads = g_raws;
+  rc.n_bytes = c->stage_len; rc.records = c->zc_base ? c->zc_base : static_cast<const uint8_t*>(c->stage.p); rc.raw_reads = g_raws;
   rc.min_input_base_quality = c->prep_opt.min_input_base_quality;
   std::vector<uint8_t> fstatus;
   std::vector<uint32_t> fmasked;
@@ -1036,7 +1037,7 @@ fgb_status flush_simplex_direct(fgb_caller* c) {
     return st;
   }
   trace.mark("submit + wait");
-  const uint8_t* const stage = static_cast<const uint8_t*>(c->stage.p);
+  const uint8_t* const stage = c->zc_base ? c->zc_base : static_cast<const uint8_t*>(c->stage.p);
   // ---- which units are emitted (template rule of the filter, commands/filter.rs:640-672: the consecutive
   //      units of one MI are emitted only if every one of them passed) ----
   std::vector<char> emit;
@@ -2225,9 +2226,19 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
   if (rec1 < rec0) { c->last_error = "bad group_rec table"; return FGB_ERR_INVALID_ARG; }
   const uint64_t b0 = rec_off[rec0], b1 = rec_off[rec1];
   if (b1 < b0) { c->last_error = "record offsets must ascend"; return FGB_ERR_LAYOUT; }
-  const size_t dst0 = round_up(c->stage_len, 64);
-  if (c->stage.ensure(dst0 + (b1 - b0) + 256, c->stage_len) != FGB_OK) { c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM; }
-  uint8_t* const stage = static_cast<uint8_t*>(c->stage.p);
+  // zero-copy batches: the records are shipped from the caller's own page-locked blob (decided by the first add
+  // of a batch); otherwise this call's slice of the blob is staged in page-locked memory owned by the caller object
+  if (c->opt.zero_copy_records && c->segs.empty() && c->stage_len == 0 && !c->zc_base && fgb_host_is_pinned(records) &&
+      !(c->opt.consensus_call_overlapping_bases && c->prep_opt.trim))
+    c->zc_base = records;
+  const bool zc = c->zc_base != nullptr;
+  if (zc && records != c->zc_base) {
+    c->last_error = "zero_copy_records: every add call of a batch must pass the same records pointer";
+    return FGB_ERR_INVALID_ARG;
+  }
+  const size_t dst0 = zc ? static_cast<size_t>(b0) : round_up(c->stage_len, 64);
+  if (!zc && c->stage.ensure(dst0 + (b1 - b0) + 256, c->stage_len) != FGB_OK) { c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM; }
+  uint8_t* const stage = zc ? const_cast<uint8_t*>(c->zc_base) : static_cast<uint8_t*>(c->stage.p);   // never written in zero-copy mode
   const uint64_t n_rec = rec1 - rec0;
   const uint32_t T = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint32_t>(c->opt.n_threads, 1u), (n_groups + 63) / 64));
   if (T > 1) ensure_workers(c, T);
@@ -2255,7 +2266,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
     if (g0 >= g1) return;
     const uint64_t s0 = rec_off[group_rec[g0]], s1 = rec_off[group_rec[g1]];
     if (s1 < s0 || s0 < b0 || s1 > b1) { x->last_error = "record offsets must ascend"; sts[t] = FGB_ERR_LAYOUT; return; }
-    std::memcpy(stage + dst0 + (s0 - b0), records + s0, s1 - s0);
+    if (!zc) std::memcpy(stage + dst0 + (s0 - b0), records + s0, s1 - s0);
     for (uint64_t g = g0; g < g1; ++g) {
       const uint64_t r0 = group_rec[g], r1 = group_rec[g + 1];
       if (r1 < r0 || r1 - r0 > 0xFFFFFFFFull || r1 > rec1) { x->last_error = "bad group_rec table"; sts[t] = FGB_ERR_INVALID_ARG; return; }
@@ -2286,6 +2297,11 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
           }
         }
         if (!on_device) {
+          if (zc) {   // the host pre-pass rewrites records in place: not on the caller's own blob
+            x->last_error = "zero_copy_records: a mate pair without qualities needs the host overlapping-bases pre-pass; pass this batch without the flag";
+            sts[t] = FGB_ERR_INVALID_ARG;
+            return;
+          }
           x->group_runs.clear();
           x->overlap.apply_group(gbase, x->rel_off.data(), n);
         } else {
@@ -2320,6 +2336,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
     }
     std::memcpy(c->stats, stats0, sizeof(stats0));
     c->overlap.stats = ostats0;
+    if (c->segs.empty() && c->stage_len == 0) c->zc_base = nullptr;
     return first;
   }
   for (uint32_t t = 0; t < T; ++t) {
@@ -2344,7 +2361,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
       x->overlap.stats = overlap::Stats();
     }
   }
-  c->stage_len = dst0 + (b1 - b0);
+  c->stage_len = std::max<size_t>(c->stage_len, dst0 + (b1 - b0));
   return FGB_OK;
 }
 
@@ -2413,6 +2430,7 @@ static fgb_status caller_flush_impl(fgb_caller* c, const uint8_t** out_data, uin
     for (auto& w : c->workers) w->dplan.clear();
     c->segs.clear();
     c->stage_len = 0;
+    c->zc_base = nullptr;
   }
   c->pack.clear(); c->metas.clear(); c->molecules.clear(); c->jobs.clear();
   c->codec_molecules.clear(); c->codec_jobs.clear();

@@ -178,7 +178,7 @@ class FgbCallerOptions(C.Structure):
         ("tag", C.c_char * 2), ("cell_tag", C.c_char * 2),
         ("read_name_prefix", C.c_char_p), ("read_group_id", C.c_char_p),
         ("min_duplex_length", C.c_uint32), ("reserved1", C.c_uint32), ("codec", FgbCodecParams),
-        ("filter_enabled", C.c_uint8), ("reserved2", C.c_uint8 * 3), ("n_threads", C.c_uint32),
+        ("filter_enabled", C.c_uint8), ("zero_copy_records", C.c_uint8), ("reserved2", C.c_uint8 * 2), ("n_threads", C.c_uint32),
         ("filter", FgbFilterParams), ("duplex_filter", FgbDuplexFilterParams),
     ]
 
@@ -202,7 +202,7 @@ SYMBOLS = (
     "fgb_abi_version", "fgb_create", "fgb_destroy", "fgb_strerror", "fgb_last_error",
     "fgb_get_tables", "fgb_host_tables", "fgb_host_proof_tables", "fgb_tile_capacity_bytes", "fgb_tile_max_units", "fgb_tile_max_reads",
     "fgb_plan_tiles", "fgb_sort_tiles_by_class", "fgb_vote_device", "fgb_submit", "fgb_wait", "fgb_host_alloc",
-    "fgb_host_free", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
+    "fgb_host_free", "fgb_host_is_pinned", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
@@ -269,6 +269,8 @@ def load() -> C.CDLL:
     lib.fgb_host_alloc.restype = C.c_int32
     lib.fgb_host_free.argtypes = [vp]
     lib.fgb_host_free.restype = None
+    lib.fgb_host_is_pinned.argtypes = [vp]
+    lib.fgb_host_is_pinned.restype = C.c_int
     lib.fgb_duplex_combine_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), vp,
                                               u64, C.POINTER(FgbDuplexOut), vp]
     lib.fgb_duplex_combine_device.restype = C.c_int32

@@ -449,9 +449,11 @@ fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_
                                   uint8_t* bases, uint8_t* quals, void* stream);
 fgb_status fgb_wait(fgb_handle* h);
 
-/* Pinned host allocation helpers (cudaHostAlloc / cudaFreeHost). */
+/* Pinned host allocation helpers (cudaHostAlloc / cudaFreeHost); fgb_host_is_pinned: 1 when `p` lies in
+ * page-locked host memory known to the CUDA runtime. */
 fgb_status fgb_host_alloc(void** p, size_t bytes);
 void fgb_host_free(void* p);
+int fgb_host_is_pinned(const void* p);
 
 /* ---- strand combine, K2 (duplex) and K3 (CODEC) --------------------------------------- */
 /* One duplex combine job: AB single-strand unit ⊕ BA single-strand unit → one duplex read.
@@ -625,7 +627,13 @@ typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanill
    * if all of its reads pass.  Simplex reads are masked on the device (`filter`), duplex reads on the
    * assembled records (`duplex_filter`); CODEC mode rejects filter_enabled. */
   uint8_t filter_enabled;
-  uint8_t reserved2[3];
+  uint8_t zero_copy_records;               /* 1: the caller promises that the records passed to add_group(s) stay valid
+                                              and unchanged until the next flush returns.  A simplex caller with a device
+                                              then ships them from where they are when they lie in page-locked memory
+                                              (fgb_host_alloc / cudaHostAlloc / cudaHostRegister) instead of staging a copy;
+                                              every add call of a batch must pass the same `records` pointer.  Ignored
+                                              (a copy is staged) for pageable memory and by the other callers. */
+  uint8_t reserved2[2];
   uint32_t n_threads;                      /* host threads for fgb_caller_add_groups and the record
                                               assembly of flush; 0 or 1 = the calling thread only  */
   fgb_filter_params filter;                /* filter.per_base_tags is set from produce_per_base_tags */

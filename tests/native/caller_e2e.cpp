@@ -37,6 +37,7 @@ int main(int argc, char** argv) {
   o.read_name_prefix = mode == 2 ? "codec" : "fgumi"; o.read_group_id = mode == 2 ? "RG1" : "A";
   o.min_duplex_length = 1; o.n_threads = static_cast<uint32_t>(threads);
   o.consensus_call_overlapping_bases = mode == 0 ? 1 : 0;
+  o.zero_copy_records = 1;                       // used when the mock engine reports page-locked memory (FGB_MOCK_PINNED)
   o.codec.single_strand_qual = -1; o.codec.outer_bases_qual = -1; o.codec.outer_bases_length = 5;
   o.codec.max_duplex_disagreements = 0xFFFFFFFFu; o.codec.max_duplex_disagreement_rate = 1.0;
   if (variant == 1 && mode == 0) {

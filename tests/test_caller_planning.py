@@ -301,3 +301,10 @@ def test_callers_end_to_end_on_a_mock_engine(tmp_path, sanitizer):
                     for i, (x, y) in enumerate(zip(a, b)):
                         assert x == y, (mode, variant, threads, i, x, y)
                 assert got == want, (mode, variant, threads)
+            if mode == 0 and variant == 0:
+                # the zero-copy path: the mock engine reports the harness' blob as page-locked, no staging copy is made
+                outp = tmp_path / "out_zero_copy.bin"
+                r = subprocess.run([str(exe), str(path), "4", "0", str(outp)], capture_output=True, text=True, timeout=900,
+                                   env=dict(env, FGB_MOCK_PINNED="1"))
+                assert r.returncode == 0 and r.stdout.startswith("ok count"), (r.stdout[-300:], r.stderr[-3000:])
+                assert open(outp, "rb").read() == want
