@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/fgumi_b200.h"
+#include "assemble_kernel.cuh"
 #include "combine_kernels.cuh"
 #include "fgb_config.h"
 #include "filter_kernel.cuh"
@@ -54,6 +55,8 @@ struct Slot {
   uint8_t* recblob = nullptr;    // RECORDS transfer blob (fgb_submit_ex, FGB_IN_RECORDS)
   uint64_t cap_recblob = 0;
   std::vector<fgb_tile> tile_stage;   // class-sorted copy of a chunk's tiles (host)
+  fgb_record_job* recjobs = nullptr; uint64_t cap_recjobs = 0;   // record assembly (K5)
+  uint8_t* recout = nullptr; uint64_t cap_recout = 0;
   // strand-combine jobs of fgb_submit_ex (duplex / CODEC callers)
   fgb_duplex_job* djobs = nullptr; uint64_t cap_djobs = 0;
   fgb_codec_job* cjobs = nullptr; uint64_t cap_cjobs = 0;
@@ -92,6 +95,8 @@ struct fgb_handle {
   unsigned long long* d_ostats = nullptr;            // overlap pre-pass counters (device u64[4])
   uint64_t* ostats_host = nullptr;                  // where fgb_wait adds them
   fgb_overlap_run* d_oruns = nullptr; uint64_t cap_oruns = 0;
+  uint8_t* d_recstr = nullptr; uint64_t cap_recstr = 0;   // record assembly: the batch's string blob
+  cudaEvent_t ev_recstr = nullptr;                         // ... uploaded on the first chunk's stream
   int vote_variant = 1;                             // FGB_VOTE_KERNEL=0: the general kernel votes every tile (A/B runs)
 };
 
@@ -279,7 +284,7 @@ void fgb_destroy(fgb_handle* h) {
   for (int s = 0; s < kSlots; ++s) {
     Slot& sl = h->slots[s];
     if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
-    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.unit_status); cudaFree(sl.unit_masked); cudaFree(sl.out_depth8); cudaFree(sl.out_errors8); cudaFree(sl.seq4); cudaFree(sl.qraw); cudaFree(sl.rawreads); cudaFree(sl.recblob); cudaFree(sl.djobs); cudaFree(sl.cjobs); cudaFree(sl.c_base); cudaFree(sl.c_qual); cudaFree(sl.c_depth); cudaFree(sl.c_errors); cudaFree(sl.c_status); cudaFree(sl.c_dis); cudaFree(sl.c_dup); cudaFree(sl.reads); cudaFree(sl.units);
+    cudaFree(sl.bases); cudaFree(sl.quals); cudaFree(sl.packed); cudaFree(sl.unit_status); cudaFree(sl.unit_masked); cudaFree(sl.out_depth8); cudaFree(sl.out_errors8); cudaFree(sl.seq4); cudaFree(sl.qraw); cudaFree(sl.rawreads); cudaFree(sl.recblob); cudaFree(sl.djobs); cudaFree(sl.cjobs); cudaFree(sl.c_base); cudaFree(sl.c_qual); cudaFree(sl.c_depth); cudaFree(sl.c_errors); cudaFree(sl.c_status); cudaFree(sl.c_dis); cudaFree(sl.c_dup); cudaFree(sl.recjobs); cudaFree(sl.recout); cudaFree(sl.reads); cudaFree(sl.units);
     cudaFree(sl.tiles); cudaFree(sl.out_base); cudaFree(sl.out_qual); cudaFree(sl.out_depth);
     cudaFree(sl.out_errors);
   }
@@ -289,6 +294,8 @@ void fgb_destroy(fgb_handle* h) {
   cudaFree(h->d_bad);
   cudaFree(h->d_ostats);
   cudaFree(h->d_oruns);
+  cudaFree(h->d_recstr);
+  if (h->ev_recstr) cudaEventDestroy(h->ev_recstr);
   delete h;
 }
 
@@ -505,10 +512,14 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
   const bool one_piece = n_djobs || n_cjobs || n_oruns;   // a molecule's units are voted before its combine job runs;
                                                           // a pair's two records must be resident together
 
+  const fgb_record_job* rjobs = opt ? opt->rec_jobs : nullptr;
+  if (rjobs && (narrow || fp || n_djobs || n_cjobs || !opt->rec_strings || !opt->rec_out ||
+                opt->n_rec_string_bytes < static_cast<uint64_t>(opt->rec_prefix_len) + opt->rec_rg_len))
+    return FGB_ERR_INVALID_ARG;
   const bool rows_on_device = fmt == HostFormat::kBam4 || fmt == HostFormat::kRecords;
   if (!in->tiles || !in->units || !in->reads || (!rows_on_device && !in->bases) ||
-      (fmt == HostFormat::kBytes && !in->quals) || !out->base ||
-      !out->qual || !out->depth || !out->errors)
+      (fmt == HostFormat::kBytes && !in->quals) ||
+      (!rjobs && (!out->base || !out->qual || !out->depth || !out->errors)))
     return FGB_ERR_INVALID_ARG;
   FGB_CUDA(h, cudaSetDevice(h->device));
   h->submit_pending = true;
@@ -764,6 +775,37 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
       if (ho->disagreements) FGB_CUDA(h, cudaMemcpyAsync(ho->disagreements, sl.c_dis, n_cjobs * 4, cudaMemcpyDeviceToHost, s));
       if (ho->duplex_bases) FGB_CUDA(h, cudaMemcpyAsync(ho->duplex_bases, sl.c_dup, n_cjobs * 4, cudaMemcpyDeviceToHost, s));
     }
+    if (rjobs) {
+      // K5: the finished records of this chunk's units, straight into the host's output stream
+      if (chunk == 0) {
+        if ((st = ensure(h, &h->d_recstr, &h->cap_recstr, opt->n_rec_string_bytes + 16)) != FGB_OK) return st;
+        FGB_CUDA(h, cudaMemcpyAsync(h->d_recstr, opt->rec_strings, opt->n_rec_string_bytes, cudaMemcpyHostToDevice, s));
+        if (!h->ev_recstr) FGB_CUDA(h, cudaEventCreateWithFlags(&h->ev_recstr, cudaEventDisableTiming));
+        FGB_CUDA(h, cudaEventRecord(h->ev_recstr, s));
+      } else {
+        FGB_CUDA(h, cudaStreamWaitEvent(s, h->ev_recstr, 0));   // later chunks run on other streams
+      }
+      const uint64_t b_lo = rjobs[u0].out_off;
+      const uint64_t b_hi = u1 < in->n_units ? rjobs[u1].out_off : opt->n_rec_out_bytes;
+      if (b_hi < b_lo || b_hi > opt->n_rec_out_bytes) { h->last_error = "record jobs: offsets must ascend"; return FGB_ERR_LAYOUT; }
+      if ((st = ensure(h, &sl.recjobs, &sl.cap_recjobs, u1 - u0 + 1)) != FGB_OK) return st;
+      if ((st = ensure(h, &sl.recout, &sl.cap_recout, b_hi - b_lo + 16)) != FGB_OK) return st;
+      FGB_CUDA(h, cudaMemcpyAsync(sl.recjobs, rjobs + u0, (u1 - u0) * sizeof(fgb_record_job), cudaMemcpyHostToDevice, s));
+      AssembleArgs aa;
+      aa.units = db.units; aa.jobs = sl.recjobs - u0;
+      aa.unit_begin = u0; aa.unit_end = u1;
+      aa.base = dc.base; aa.qual = dc.qual; aa.depth = dc.depth; aa.errors = dc.errors;
+      aa.strings = h->d_recstr; aa.prefix_len = opt->rec_prefix_len; aa.rg_len = opt->rec_rg_len;
+      aa.cell_tag[0] = opt->rec_cell_tag[0]; aa.cell_tag[1] = opt->rec_cell_tag[1];
+      aa.per_base_tags = opt->rec_per_base_tags; aa.pad = 0;
+      aa.out = sl.recout - b_lo;
+      const uint64_t nu = u1 - u0;
+      const unsigned agrid = static_cast<unsigned>(std::min<uint64_t>((nu + 7u) / 8u, static_cast<uint64_t>(h->sm_count) * 16u));
+      assemble_simplex_kernel<<<agrid, 256, 0, s>>>(aa);
+      h->launches++;
+      FGB_CUDA(h, cudaGetLastError());
+      if (b_hi > b_lo) FGB_CUDA(h, cudaMemcpyAsync(opt->rec_out + b_lo, sl.recout, b_hi - b_lo, cudaMemcpyDeviceToHost, s));
+    }
     if (fp) {
       if ((st = ensure(h, &sl.unit_status, &sl.cap_ustat, u1 - u0 + 16)) != FGB_OK) return st;
       if (opt->unit_masked && (st = ensure(h, &sl.unit_masked, &sl.cap_umask, u1 - u0 + 16)) != FGB_OK) return st;
@@ -775,6 +817,11 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
                                     cudaMemcpyDeviceToHost, s));
     }
     const uint64_t no = o1 - o0;
+    if (!out->base) {                        // record assembly only: nothing else travels back
+      t0 = t1;
+      ++chunk;
+      continue;
+    }
     FGB_CUDA(h, cudaMemcpyAsync(out->base + o0, sl.out_base, no, cudaMemcpyDeviceToHost, s));
     FGB_CUDA(h, cudaMemcpyAsync(out->qual + o0, sl.out_qual, no, cudaMemcpyDeviceToHost, s));
     if (narrow) {
@@ -1128,5 +1175,6 @@ fgb_status fgb_stats_reset(fgb_handle* h) {
 }
 
 uint64_t fgb_launch_count(const fgb_handle* h) { return h ? h->launches : 0; }
+uint32_t fgb_engine_caps(void) { return FGB_CAP_RECORD_ASSEMBLY; }
 
 }  // extern "C"

@@ -172,10 +172,12 @@ struct DirectPlan {
   std::vector<fgb_overlap_run> oruns; // overlapping-bases runs for the device (offsets relative to the staging)
   uint64_t row_bytes = 0;            // sum of round_up(len, 8) over the reads
   uint64_t out_elems = 0;            // sum of round_up(cons_len, 8) over the units
-  void clear() { raws.clear(); lens.clear(); units.clear(); rx.clear(); oruns.clear(); row_bytes = out_elems = 0; }
+  uint64_t rec_bytes = 0;            // sum of the units' record sizes (units with rec_size 0 add nothing)
+  uint64_t str_bytes = 0;            // UMI + cell + RX bytes of the units (device record assembly)
+  void clear() { raws.clear(); lens.clear(); units.clear(); rx.clear(); oruns.clear(); row_bytes = out_elems = rec_bytes = str_bytes = 0; }
 };
 
-struct DMark { size_t raws, units, rx, oruns; uint64_t row_bytes, out_elems; };   // a plan's size, for roll-back
+struct DMark { size_t raws, units, rx, oruns; uint64_t row_bytes, out_elems, rec_bytes, str_bytes; };   // a plan's size, for roll-back
 
 struct DSeg {                        // units [u0, u1) / reads [r0, r1) of one context's plan, in input order
   struct fgb_caller* ctx;
@@ -183,6 +185,7 @@ struct DSeg {                        // units [u0, u1) / reads [r0, r1) of one c
   uint64_t r0, r1;
   uint64_t row_bytes, out_elems;
   uint64_t o0, o1;                   // overlap runs [o0, o1) of the plan
+  uint64_t rec_bytes, str_bytes;
 };
 
 struct PinBuf {                      // grow-only page-locked buffer
@@ -231,7 +234,7 @@ struct fgb_caller {
   std::unique_ptr<WorkerPool> pool;                    // the threads themselves, started on first use
   // flush scratch that outlives a flush, so steady-state flushes neither page-fault nor zero-fill:
   std::vector<std::vector<uint8_t>> tbufs;   // per-thread record buffers (capacity kept)
-  uint8_t* joined = nullptr;                 // concatenated output of a threaded flush (malloc, grow-only)
+  uint8_t* joined = nullptr;                 // output stream of a flush (page-locked, grow-only)
   size_t joined_cap = 0, joined_len = 0;
   bool out_is_joined = false;
   void* pinned[4] = {nullptr, nullptr, nullptr, nullptr};   // consensus columns, page-locked (fgb_host_alloc)
@@ -249,9 +252,23 @@ struct fgb_caller {
   std::vector<uint64_t> rel_off;             // scratch: record offsets relative to the group
   std::vector<overlap::Run> group_runs;      // scratch: the overlap runs of the group being planned (device pre-pass)
   PinBuf d_oruns;                            // parent: the batch's runs for the engine
+  PinBuf d_recjobs, d_recstr;                // parent: device record assembly (jobs, string blob)
 };
 
 namespace {
+
+// The flush's output stream lives in page-locked memory that outlives the flush (the device writes finished
+// records into it when it assembles them; the host assembly writes at final offsets).
+bool ensure_joined(fgb_caller* c, size_t total) {
+  if (c->joined_cap >= total + 64) return true;
+  fgb_host_free(c->joined);
+  c->joined = nullptr;
+  c->joined_cap = total + total / 4 + 4096;
+  void* p = nullptr;
+  if (fgb_host_alloc(&p, c->joined_cap) != FGB_OK) { c->joined_cap = 0; c->last_error = "out of page-locked memory"; return false; }
+  c->joined = static_cast<uint8_t*>(p);
+  return true;
+}
 
 // fn(0..T-1) on the caller's pool (T <= options.n_threads).
 void run_parallel(fgb_caller* c, uint32_t T, const std::function<void(uint32_t)>& fn) {
@@ -528,6 +545,8 @@ void pack_direct_unit(fgb_caller* c, const uint8_t* stage, const std::vector<Vie
   if (u.n_reads <= 255u)                                        // cD / cM fit one byte whatever the vote says
     u.rec_size = simplex_record_size(c, u.cons_len, umi.len, u.has_cell, u.cell.len, u.rx_n > 0,
                                      u.rx_n ? P.rx[u.rx_begin].len : 0u, 1u, 1u);
+  P.rec_bytes += u.rec_size;
+  P.str_bytes += umi.len + (u.has_cell ? u.cell.len : 0u) + (u.rx_n ? P.rx[u.rx_begin].len : 0u);
   P.units.push_back(u);
 }
 
@@ -768,12 +787,7 @@ fgb_status flush_simplex(fgb_caller* c) {
     total += c->tbufs[t].size();
     c->out_count += counts[t];
   }
-  if (c->joined_cap < total) {
-    std::free(c->joined);
-    c->joined_cap = total + total / 4 + 64;
-    c->joined = static_cast<uint8_t*>(std::malloc(c->joined_cap));
-    if (!c->joined) { c->joined_cap = 0; c->last_error = "out of memory"; return FGB_ERR_NOMEM; }
-  }
+  if (!ensure_joined(c, total)) return FGB_ERR_NOMEM;
   run_parallel(c, T, [&](uint32_t t) {
     if (!c->tbufs[t].empty()) std::memcpy(c->joined + at[t], c->tbufs[t].data(), c->tbufs[t].size());
   });
@@ -793,6 +807,19 @@ bool consensus_umis_refs(const UmiBuilder& builder, const uint8_t* base, const S
   if (n == 1) { out->assign(reinterpret_cast<const char*>(base + refs[0].off), refs[0].len); return true; }
   const uint32_t len = refs[0].len;
   for (uint32_t k = 1; k < n; ++k) if (refs[k].len != len) return false;
+  {
+    // Every value identical (the usual family) and free of lower-case bases: each DNA column is unanimous and calls
+    // its own base (UmiBuilder::call: no tie, no rounding can touch a unanimous column; an all-N column calls N),
+    // each non-DNA column passes its character through -- the consensus is the value itself.
+    const uint8_t* f = base + refs[0].off;
+    bool same = true;
+    for (uint32_t k = 1; k < n && same; ++k) same = std::memcmp(base + refs[k].off, f, len) == 0;
+    if (same) {
+      bool plain = true;
+      for (uint32_t i = 0; i < len && plain; ++i) { const uint8_t ch = f[i]; plain = !(ch == 'a' || ch == 'c' || ch == 'g' || ch == 't' || ch == 'n'); }
+      if (plain) { out->assign(reinterpret_cast<const char*>(f), len); return true; }
+    }
+  }
   auto is_dna = [](uint8_t ch) {
     switch (ch) { case 'A': case 'C': case 'G': case 'T': case 'N':
                   case 'a': case 'c': case 'g': case 't': case 'n': return true; default: return false; }
@@ -975,6 +1002,107 @@ fgb_status flush_simplex_direct(fgb_caller* c) {
   tiles.reserve(n_tiles + 1);
   for (size_t i = 0; i < NS; ++i) tiles.insert(tiles.end(), seg_tiles[i].begin(), seg_tiles[i].end());
   trace.mark("tiles");
+  // ---- record assembly on the device (K5) when the engine offers it, every record's size is known up front (no
+  //      unit deeper than 255 reads) and no filter decides what is emitted: the host supplies the strings only ----
+  static const bool kHostAssembly = std::getenv("FGB_CALLER_HOST_ASSEMBLY") != nullptr;
+  if (!kHostAssembly && !c->opt.filter_enabled && max_reads <= 255u && (fgb_engine_caps() & FGB_CAP_RECORD_ASSEMBLY)) {
+    std::vector<uint64_t> rb_(NS + 1, 0), sb_(NS + 1, 0);
+    const uint64_t head = c->prefix.size() + c->rg.size();
+    sb_[0] = head;
+    for (size_t i = 0; i < NS; ++i) { rb_[i + 1] = rb_[i] + c->segs[i].rec_bytes; sb_[i + 1] = sb_[i] + c->segs[i].str_bytes; }
+    const uint64_t total = rb_[NS], n_str = sb_[NS];
+    if (n_str >= 0xFFFFFFFFull) { c->last_error = "batch too large"; return FGB_ERR_INVALID_ARG; }
+    if (c->d_recjobs.ensure((U + 1) * sizeof(fgb_record_job)) != FGB_OK || c->d_recstr.ensure(n_str + 64) != FGB_OK || !ensure_joined(c, total)) {
+      c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM;
+    }
+    fgb_record_job* jobs = static_cast<fgb_record_job*>(c->d_recjobs.p);
+    uint8_t* strs = static_cast<uint8_t*>(c->d_recstr.p);
+    std::memcpy(strs, c->prefix.data(), c->prefix.size());
+    std::memcpy(strs + c->prefix.size(), c->rg.data(), c->rg.size());
+    const uint8_t* const stage0 = c->zc_base ? c->zc_base : static_cast<const uint8_t*>(c->stage.p);
+    std::vector<int> bad(NS, 0);
+    for_segs([&](size_t i) {       // jobs and strings of segment i; the RX consensus (simple_umi.rs:236-245) is computed here
+      const DSeg& sg = c->segs[i];
+      const DirectPlan& P = sg.ctx->dplan;
+      uint64_t ro = rb_[i], so_ = sb_[i];
+      static thread_local std::string rx;
+      for (uint32_t u = sg.u0; u < sg.u1; ++u) {
+        const DUnit& du = P.units[u];
+        fgb_record_job j;
+        j.out_off = ro; j.str_off = static_cast<uint32_t>(so_); j.size = du.rec_size;
+        j.umi_len = static_cast<uint16_t>(du.umi.len); j.cell_len = du.has_cell ? static_cast<uint16_t>(du.cell.len) : 0;
+        j.rx_len = 0; j.read_type = du.read_type;
+        j.flags = (du.has_cell ? FGB_RECJOB_HAS_CELL : 0) | (du.rx_n ? FGB_RECJOB_HAS_RX : 0);
+        if (c->prefix.size() + 1 + du.umi.len >= 255 || du.umi.len > 0xFFFFu || du.cell.len > 0xFFFFu) { bad[i] = 1; return; }
+        std::memcpy(strs + so_, stage0 + du.umi.off, du.umi.len); so_ += du.umi.len;
+        if (du.has_cell) { std::memcpy(strs + so_, stage0 + du.cell.off, du.cell.len); so_ += du.cell.len; }
+        if (du.rx_n) {
+          const uint32_t want = P.rx[du.rx_begin].len;
+          if (!consensus_umis_refs(c->umi_builder, stage0, P.rx.data() + du.rx_begin, du.rx_n, &rx) || rx.size() != want || want > 0xFFFFu) { bad[i] = 2; return; }
+          std::memcpy(strs + so_, rx.data(), want); so_ += want;
+          j.rx_len = static_cast<uint16_t>(want);
+        }
+        jobs[ub[i] + (u - sg.u0)] = j;
+        ro += du.rec_size;
+      }
+    });
+    for (size_t i = 0; i < NS; ++i)
+      if (bad[i]) {
+        c->last_error = bad[i] == 1 ? "read name too long"
+                                    : "RX values of a family have different lengths or mix DNA and non-DNA characters";
+        return FGB_ERR_INVALID_ARG;
+      }
+    std::memset(&jobs[U], 0, sizeof(fgb_record_job));
+    jobs[U].out_off = total;
+    trace.mark("record jobs");
+    fgb_batch b;
+    std::memset(&b, 0, sizeof(b));
+    b.n_units = U; b.n_reads = R; b.n_bytes = n_bytes; b.n_out = no; b.n_tiles = n_tiles;
+    b.reads = g_reads; b.units = g_units; b.tiles = tiles.data();
+    fgb_columns none{nullptr, nullptr, nullptr, nullptr};
+    fgb_record_columns rc;
+    std::memset(&rc, 0, sizeof(rc));
+    rc.n_bytes = c->stage_len; rc.records = stage0; rc.raw_reads = g_raws;
+    rc.min_input_base_quality = c->prep_opt.min_input_base_quality;
+    fgb_submit_options so;
+    std::memset(&so, 0, sizeof(so));
+    so.input_format = FGB_IN_RECORDS; so.output_format = FGB_OUT_U16;
+    so.records = &rc;
+    uint64_t n_runs = 0;
+    for (const DSeg& sg : c->segs) n_runs += sg.o1 - sg.o0;
+    if (n_runs) {
+      if (c->d_oruns.ensure(n_runs * sizeof(fgb_overlap_run)) != FGB_OK) { c->last_error = "out of page-locked memory"; return FGB_ERR_NOMEM; }
+      fgb_overlap_run* dst = static_cast<fgb_overlap_run*>(c->d_oruns.p);
+      for (const DSeg& sg : c->segs) {
+        const size_t k = sg.o1 - sg.o0;
+        if (k) std::memcpy(dst, sg.ctx->dplan.oruns.data() + sg.o0, k * sizeof(fgb_overlap_run));
+        dst += k;
+      }
+      so.overlap_runs = static_cast<const fgb_overlap_run*>(c->d_oruns.p);
+      so.n_overlap_runs = n_runs;
+      so.overlap_stats = &c->overlap.stats.overlapping_bases;
+      so.overlap_agreement = static_cast<uint8_t>(c->overlap.agreement());
+      so.overlap_disagreement = static_cast<uint8_t>(c->overlap.disagreement());
+    }
+    so.rec_jobs = jobs; so.rec_strings = strs; so.n_rec_string_bytes = n_str;
+    so.rec_prefix_len = static_cast<uint32_t>(c->prefix.size()); so.rec_rg_len = static_cast<uint32_t>(c->rg.size());
+    so.rec_cell_tag[0] = static_cast<uint8_t>(c->opt.cell_tag[0]); so.rec_cell_tag[1] = static_cast<uint8_t>(c->opt.cell_tag[1]);
+    so.rec_per_base_tags = c->opt.produce_per_base_tags;
+    so.rec_out = c->joined; so.n_rec_out_bytes = total;
+    fgb_status st = fgb_submit_ex(c->h, &b, &none, &so);
+    if (st == FGB_OK) st = fgb_wait(c->h);
+    if (st != FGB_OK) {
+      char buf[256];
+      fgb_last_error(c->h, buf, sizeof(buf));
+      c->last_error = buf;
+      return st;
+    }
+    trace.mark("submit + wait (records assembled on the device)");
+    c->out_count += U;
+    c->joined_len = total;
+    c->out_is_joined = true;
+    return FGB_OK;
+  }
   // ---- output columns (page-locked, grow-only); depth / errors travel as bytes when no unit is deeper than 255 ----
   const bool narrow = max_reads <= 255u;
   if (c->pinned_cap < no + 8) {
@@ -1118,12 +1246,7 @@ fgb_status flush_simplex_direct(fgb_caller* c) {
   size_t total = 0;
   std::vector<size_t> at(pieces.size() + 1, 0);
   for (size_t i = 0; i < pieces.size(); ++i) { at[i] = total; total += pieces[i].bytes; c->out_count += pieces[i].count; }
-  if (c->joined_cap < total + 64) {
-    std::free(c->joined);
-    c->joined_cap = total + total / 4 + 4096;
-    c->joined = static_cast<uint8_t*>(std::malloc(c->joined_cap));
-    if (!c->joined) { c->joined_cap = 0; c->last_error = "out of memory"; return FGB_ERR_NOMEM; }
-  }
+  if (!ensure_joined(c, total)) return FGB_ERR_NOMEM;
   std::vector<fgb_status> pst(pieces.size(), FGB_OK);
   std::vector<std::string> perr(TP);
   trace.mark("sizes");
@@ -1202,12 +1325,7 @@ fgb_status parallel_records(fgb_caller* c, uint64_t n, uint64_t min_per_thread, 
     for (int i = 0; i < FGB_NSTATS; ++i) { c->stats[i] += w->stats[i]; w->stats[i] = 0; }
   }
   if (first != FGB_OK) return first;
-  if (c->joined_cap < total) {
-    std::free(c->joined);
-    c->joined_cap = total + total / 4 + 64;
-    c->joined = static_cast<uint8_t*>(std::malloc(c->joined_cap));
-    if (!c->joined) { c->joined_cap = 0; c->last_error = "out of memory"; return FGB_ERR_NOMEM; }
-  }
+  if (!ensure_joined(c, total)) return FGB_ERR_NOMEM;
   run_parallel(c, T, [&](uint32_t t) {
     const auto& o = c->workers[t]->out;
     if (!o.empty()) std::memcpy(c->joined + at[t], o.data(), o.size());
@@ -2027,9 +2145,9 @@ fgb_status fgb_caller_pending(const fgb_caller* c, fgb_batch* batch, const fgb_d
 void fgb_caller_destroy(fgb_caller* c) {
   if (!c) return;
   for (void* p : c->pinned) fgb_host_free(p);
-  c->stage.release(); c->d_reads.release(); c->d_raws.release(); c->d_units.release(); c->d_oruns.release();
+  c->stage.release(); c->d_reads.release(); c->d_raws.release(); c->d_units.release(); c->d_oruns.release(); c->d_recjobs.release(); c->d_recstr.release();
   for (PinBuf& b : c->px) b.release();
-  std::free(c->joined);
+  fgb_host_free(c->joined);
   fgb_destroy(c->h);
   delete c;
 }
@@ -2254,7 +2372,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
   for (uint32_t t = 0; t < T; ++t) {
     ctx[t] = T > 1 ? c->workers[t].get() : c;
     const DirectPlan& P = ctx[t]->dplan;
-    mark[t] = DMark{P.raws.size(), P.units.size(), P.rx.size(), P.oruns.size(), P.row_bytes, P.out_elems};
+    mark[t] = DMark{P.raws.size(), P.units.size(), P.rx.size(), P.oruns.size(), P.row_bytes, P.out_elems, P.rec_bytes, P.str_bytes};
   }
   uint64_t stats0[FGB_NSTATS];
   std::memcpy(stats0, c->stats, sizeof(stats0));
@@ -2331,7 +2449,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
       DirectPlan& P = ctx[t]->dplan;
       P.raws.resize(mark[t].raws); P.lens.resize(mark[t].raws); P.units.resize(mark[t].units); P.rx.resize(mark[t].rx);
       P.oruns.resize(mark[t].oruns);
-      P.row_bytes = mark[t].row_bytes; P.out_elems = mark[t].out_elems;
+      P.row_bytes = mark[t].row_bytes; P.out_elems = mark[t].out_elems; P.rec_bytes = mark[t].rec_bytes; P.str_bytes = mark[t].str_bytes;
       if (ctx[t] != c) { std::memset(ctx[t]->stats, 0, sizeof(ctx[t]->stats)); ctx[t]->overlap.stats = overlap::Stats(); }
     }
     std::memcpy(c->stats, stats0, sizeof(stats0));
@@ -2344,10 +2462,12 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
     const DirectPlan& P = x->dplan;
     if (P.units.size() > mark[t].units || P.oruns.size() > mark[t].oruns) {
       DSeg sg{x, static_cast<uint32_t>(mark[t].units), static_cast<uint32_t>(P.units.size()), mark[t].raws, P.raws.size(),
-              P.row_bytes - mark[t].row_bytes, P.out_elems - mark[t].out_elems, mark[t].oruns, P.oruns.size()};
+              P.row_bytes - mark[t].row_bytes, P.out_elems - mark[t].out_elems, mark[t].oruns, P.oruns.size(),
+              P.rec_bytes - mark[t].rec_bytes, P.str_bytes - mark[t].str_bytes};
       if (!c->segs.empty() && c->segs.back().ctx == x && c->segs.back().u1 == sg.u0 && c->segs.back().o1 == sg.o0) {   // serial add_group calls
         DSeg& l = c->segs.back();
         l.u1 = sg.u1; l.r1 = sg.r1; l.row_bytes += sg.row_bytes; l.out_elems += sg.out_elems; l.o1 = sg.o1;
+        l.rec_bytes += sg.rec_bytes; l.str_bytes += sg.str_bytes;
       } else {
         c->segs.push_back(sg);
       }

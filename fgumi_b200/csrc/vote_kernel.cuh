@@ -1274,7 +1274,7 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
         const int s = k % kStages;
         const uint32_t use = k / kStages;
         if (use > 0) {                                          // consumers released the stage
-          mbar_wait(&S.empty[s], (use - 1u) & 1u, 20000u);
+          mbar_wait(&S.empty[s], (use - 1u) & 1u, V == 2 ? 1000u : 20000u);   // deep tiles are small: shorter naps
         }
         Stage& st = S.st[s];
         const uint4* gt = reinterpret_cast<const uint4*>(a.tiles + t);
@@ -1314,7 +1314,7 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
   uint32_t k = 0, rot = 0;
   for (uint32_t t = blockIdx.x; t < n_tiles; t += grid, ++k) {
     const int s = k % kStages;
-    mbar_wait(&S.full[s], (k / kStages) & 1u, 2000u);
+    mbar_wait(&S.full[s], (k / kStages) & 1u, V == 2 ? 300u : 2000u);
     Stage& st = S.st[s];
     // rotating item assignment: the partial last round of a tile lands on different warps from
     // tile to tile, so every warp does the same work in the long run

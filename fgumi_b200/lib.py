@@ -146,7 +146,11 @@ class FgbSubmitOptions(C.Structure):
                 ("codec_jobs", C.c_void_p), ("n_codec_jobs", C.c_uint64), ("n_codec_out", C.c_uint64),
                 ("codec_params", C.c_void_p), ("codec_out", C.c_void_p),
                 ("overlap_runs", C.c_void_p), ("n_overlap_runs", C.c_uint64), ("overlap_stats", C.c_void_p),
-                ("overlap_agreement", C.c_uint8), ("overlap_disagreement", C.c_uint8), ("reserved", C.c_uint8 * 6)]
+                ("overlap_agreement", C.c_uint8), ("overlap_disagreement", C.c_uint8),
+                ("rec_cell_tag", C.c_uint8 * 2), ("rec_per_base_tags", C.c_uint8), ("reserved", C.c_uint8 * 3),
+                ("rec_jobs", C.c_void_p), ("rec_strings", C.c_void_p), ("n_rec_string_bytes", C.c_uint64),
+                ("rec_prefix_len", C.c_uint32), ("rec_rg_len", C.c_uint32), ("rec_out", C.c_void_p),
+                ("n_rec_out_bytes", C.c_uint64)]
 
 
 FGB_DEVICE_NONE = -1      # fgb_caller_create: planning-only caller (no engine, flush refuses)
@@ -203,7 +207,7 @@ SYMBOLS = (
     "fgb_get_tables", "fgb_host_tables", "fgb_host_proof_tables", "fgb_tile_capacity_bytes", "fgb_tile_max_units", "fgb_tile_max_reads",
     "fgb_plan_tiles", "fgb_sort_tiles_by_class", "fgb_vote_device", "fgb_submit", "fgb_wait", "fgb_host_alloc",
     "fgb_host_free", "fgb_host_is_pinned", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
-    "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count",
+    "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count", "fgb_engine_caps",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
     "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
     "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_unpack_records_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups", "fgb_filter_record", "fgb_host_is_fr_pair",
@@ -292,6 +296,8 @@ def load() -> C.CDLL:
     lib.fgb_stats_reset.restype = C.c_int32
     lib.fgb_launch_count.argtypes = [vp]
     lib.fgb_launch_count.restype = u64
+    lib.fgb_engine_caps.argtypes = []
+    lib.fgb_engine_caps.restype = u32
     lib.fgb_caller_create.argtypes = [C.c_int, C.POINTER(FgbCallerOptions), C.POINTER(vp)]
     lib.fgb_caller_create.restype = C.c_int32
     lib.fgb_caller_destroy.argtypes = [vp]

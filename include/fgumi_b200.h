@@ -539,6 +539,22 @@ fgb_status fgb_codec_submit(fgb_handle* h, const fgb_batch* in, const fgb_column
                             const fgb_codec_job* jobs, uint64_t n_jobs, const fgb_codec_params* cp,
                             uint64_t n_codec_out, const fgb_codec_out* out);
 
+/* ---- simplex record assembly on the device (K5) ------------------------------------------------------
+ * build_consensus_record_into (vanilla_caller.rs:1365-1473) for the units of a batch, written by the device at
+ * their final place in the ConsensusOutput stream.  The host supplies what only it knows: per unit the read type,
+ * the UMI, the cell barcode and the RX consensus (in a string blob that starts with the read-name prefix and the
+ * read group id), the record's size and offset.  Only for units of at most 255 reads (cD / cM then fit one byte
+ * and the size is known before the vote). */
+typedef struct fgb_record_job {
+  uint64_t out_off;                /* byte offset of the record (its block_size word first) in the stream           */
+  uint32_t str_off;                /* offset of [umi][cell][rx] in the string blob                                   */
+  uint32_t size;                   /* bytes of the record incl. the block_size word                                  */
+  uint16_t umi_len, cell_len, rx_len;
+  uint8_t read_type;               /* 0 fragment, 1 R1, 2 R2                                                         */
+  uint8_t flags;                   /* FGB_RECJOB_*                                                                   */
+} fgb_record_job;
+enum { FGB_RECJOB_HAS_CELL = 1, FGB_RECJOB_HAS_RX = 2, FGB_RECJOB_SKIP = 4 /* no record for this unit */ };
+
 /* ---- the general host-buffer call --------------------------------------------------------------------
  * Any input format, optionally narrow outputs, the filter epilogue, and -- for the duplex / CODEC callers
  * -- the strand combine of the voted units in the same call.  With combine jobs the batch is processed as
@@ -571,7 +587,18 @@ typedef struct fgb_submit_options {
                                           disagreeing, corrected (CorrectionStats, overlapping.rs:42-77)  */
   uint8_t overlap_agreement;           /* FGB_OVERLAP_AGREE_*    */
   uint8_t overlap_disagreement;        /* FGB_OVERLAP_DISAGREE_* */
-  uint8_t reserved[6];
+  /* simplex record assembly on the device: n_units jobs; the finished stream lands in rec_out (host, page-locked
+   * for an asynchronous copy) and `out` may then hold NULL columns (nothing else is copied back).  Not with
+   * FGB_OUT_U8, the filter or combine jobs. */
+  uint8_t rec_cell_tag[2];
+  uint8_t rec_per_base_tags;
+  uint8_t reserved[3];
+  const fgb_record_job* rec_jobs;
+  const uint8_t* rec_strings;          /* [read-name prefix][read group id] then the units' strings              */
+  uint64_t n_rec_string_bytes;
+  uint32_t rec_prefix_len, rec_rg_len;
+  uint8_t* rec_out;
+  uint64_t n_rec_out_bytes;
 } fgb_submit_options;
 fgb_status fgb_submit_ex(fgb_handle* h, const fgb_batch* in, const fgb_columns* out,
                          const fgb_submit_options* opt);
@@ -589,6 +616,9 @@ fgb_status fgb_stats_device_ptr(fgb_handle* h, uint64_t** dev_counters);
 fgb_status fgb_stats_reset(fgb_handle* h);
 /* Number of kernel launches this handle has enqueued (for bench.py's gpu_launches). */
 uint64_t fgb_launch_count(const fgb_handle* h);
+/* Capability bits of the engine behind this ABI (a test stand-in may offer fewer). */
+enum { FGB_CAP_RECORD_ASSEMBLY = 1 };
+uint32_t fgb_engine_caps(void);
 
 /* ---- record-level caller: the ConsensusCaller boundary itself --------------------------- */
 /* Mirrors `trait ConsensusCaller` (caller.rs:205-234) for batches of MI groups: raw BAM records in,

@@ -110,6 +110,7 @@ size_t fgb_last_error(const fgb_handle*, char* buf, size_t n) { if (buf && n) bu
 fgb_status fgb_wait(fgb_handle*) { return FGB_OK; }
 fgb_status fgb_host_alloc(void** p, size_t bytes) { *p = std::malloc(bytes ? bytes : 1); return *p ? FGB_OK : FGB_ERR_NOMEM; }
 void fgb_host_free(void* p) { std::free(p); }
+uint32_t fgb_engine_caps(void) { return 0; }        // no device record assembly here: the callers assemble on the host
 int fgb_host_is_pinned(const void*) { return std::getenv("FGB_MOCK_PINNED") != nullptr; }   // lets the CPU harness take the zero-copy path
 
 fgb_status fgb_submit(fgb_handle* h, const fgb_batch* in, const fgb_columns* out) { return vote(h, in, out); }
