@@ -985,9 +985,19 @@ fgb_status fgb_duplex_combine_device(fgb_handle* h, const fgb_batch* in, const f
   a.out_base = out->base; a.out_qual = out->qual; a.out_errors = out->errors;
   a.out_status = out->status;
   a.counters = h->d_counters;
-  unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n_jobs + kCombineJobsPerCta - 1) / kCombineJobsPerCta,
-                                                           static_cast<uint64_t>(h->sm_count) * 8u));
-  duplex_combine_kernel<<<grid, kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  const uintptr_t align_all = reinterpret_cast<uintptr_t>(a.bases) | reinterpret_cast<uintptr_t>(a.ss_base) |
+                              reinterpret_cast<uintptr_t>(a.ss_qual) | reinterpret_cast<uintptr_t>(a.ss_depth) |
+                              reinterpret_cast<uintptr_t>(a.out_base) | reinterpret_cast<uintptr_t>(a.out_qual) |
+                              reinterpret_cast<uintptr_t>(a.out_errors);
+  const uint64_t chunks = (n_jobs + kDuplexChunk - 1) / kDuplexChunk;
+  if ((align_all & 15u) == 0 && chunks <= 0x7FFFFFFFull) {
+    // word kernel: 8 positions per thread, a CTA per chunk of consecutive jobs
+    duplex_combine_words_kernel<<<static_cast<unsigned>(chunks), kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  } else {
+    unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n_jobs + kCombineJobsPerCta - 1) / kCombineJobsPerCta,
+                                                             static_cast<uint64_t>(h->sm_count) * 8u));
+    duplex_combine_kernel<<<grid, kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  }
   h->launches++;
   FGB_CUDA(h, cudaGetLastError());
   return FGB_OK;
@@ -1011,9 +1021,19 @@ fgb_status fgb_codec_combine_device(fgb_handle* h, const fgb_batch* in, const fg
   a.out_errors = out->cols.errors;
   a.status = out->status; a.disagreements = out->disagreements; a.duplex_bases = out->duplex_bases;
   a.counters = h->d_counters;
-  unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n_jobs + kCodecJobsPerCta - 1) / kCodecJobsPerCta,
-                                                           static_cast<uint64_t>(h->sm_count) * 8u));
-  codec_combine_kernel<<<grid, kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  const uintptr_t align_all = reinterpret_cast<uintptr_t>(a.ss_base) | reinterpret_cast<uintptr_t>(a.ss_qual) |
+                              reinterpret_cast<uintptr_t>(a.ss_depth) | reinterpret_cast<uintptr_t>(a.ss_errors) |
+                              reinterpret_cast<uintptr_t>(a.out_base) | reinterpret_cast<uintptr_t>(a.out_qual) |
+                              reinterpret_cast<uintptr_t>(a.out_depth) | reinterpret_cast<uintptr_t>(a.out_errors);
+  const uint64_t chunks = (n_jobs + kCodecChunk - 1) / kCodecChunk;
+  if ((align_all & 15u) == 0 && chunks <= 0x7FFFFFFFull) {
+    // word kernel: 8 output positions per thread, a CTA per chunk of consecutive jobs
+    codec_combine_words_kernel<<<static_cast<unsigned>(chunks), kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  } else {
+    unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n_jobs + kCodecJobsPerCta - 1) / kCodecJobsPerCta,
+                                                             static_cast<uint64_t>(h->sm_count) * 8u));
+    codec_combine_kernel<<<grid, kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  }
   h->launches++;
   FGB_CUDA(h, cudaGetLastError());
   return FGB_OK;

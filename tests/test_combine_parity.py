@@ -218,3 +218,150 @@ def test_codec_combine_matches_oracle(fg):
         if max_dis < 100:
             assert statuses == {0, 1, 2}
     eng.close()
+
+
+class _UnitsOnly:
+    """fgb_batch that carries just a unit table (all the CODEC combine reads of it)."""
+
+    def __init__(self, fg, units, device):
+        import torch
+        self.units = torch.from_numpy(units.view(np.uint8).reshape(-1).copy()).to(device)
+        self.n_units = len(units) - 1
+        self._fg = fg
+
+    def struct(self):
+        z = 0
+        return self._fg.lib.FgbBatch(self.n_units, 0, 0, 0, 0, z, z, z, self.units.data_ptr(), z, (C.c_uint64 * 3)(0, 0, 0))
+
+
+_COMP = np.arange(256, dtype=np.uint8)
+for _x, _y in zip(b"ACGTacgt", b"TGCATGCA"):
+    _COMP[_x] = _y
+
+
+def _codec_job_reference(L, cols, ua, ub, job, cp):
+    """One fgb_codec_job through the oracle's padded combine + mask (orient / pad / re-orient done here with numpy:
+    codec_caller.rs:507-520, 980-1023, 783-784)."""
+    sb, sq, sd, se = cols
+    ss_q, outer_q, outer_len = cp
+    n = int(job["len"])
+
+    def padded(u, pad, rc):
+        o, l = int(u["out_off"]), int(u["cons_len"])
+        b, q, d, e = sb[o:o + l], sq[o:o + l], sd[o:o + l], se[o:o + l]
+        if rc:
+            b, q, d, e = _COMP[b[::-1]], q[::-1], d[::-1], e[::-1]
+        pb = np.full(n, ord("n"), np.uint8); pq = np.zeros(n, np.uint8)
+        pd_ = np.zeros(n, np.uint16); pe = np.zeros(n, np.uint16)
+        k = max(0, min(l, n - pad))
+        pb[pad:pad + k], pq[pad:pad + k], pd_[pad:pad + k], pe[pad:pad + k] = b[:k], q[:k], d[:k], e[:k]
+        return pb, pq, pd_, pe
+    A = padded(ua, int(job["pad_a_left"]), bool(job["rc_a"]))
+    B = padded(ub, int(job["pad_b_left"]), bool(job["rc_b"]))
+    ob = np.zeros(n, np.uint8); oq = np.zeros(n, np.uint8); od = np.zeros(n, np.uint16); oe = np.zeros(n, np.uint16)
+    nb, nd = C.c_uint64(), C.c_uint64()
+    if n:
+        L.orc_codec_combine(A[0].ctypes.data, A[1].ctypes.data, A[2].ctypes.data, A[3].ctypes.data,
+                            B[0].ctypes.data, B[1].ctypes.data, B[2].ctypes.data, B[3].ctypes.data, n,
+                            ob.ctypes.data, oq.ctypes.data, od.ctypes.data, oe.ctypes.data, C.addressof(nb), C.addressof(nd))
+        L.orc_codec_mask(ob.ctypes.data, oq.ctypes.data, n, A[0].ctypes.data, B[0].ctypes.data, ss_q, outer_q, outer_len)
+    if job["rc_out"]:
+        ob, oq, od, oe = _COMP[ob[::-1]], oq[::-1], od[::-1], oe[::-1]
+    return ob, oq, od, oe, nb.value, nd.value
+
+
+def test_codec_combine_generic_jobs(fg):
+    """Every orientation combination, arbitrary pads (strands may stick out of the consensus), lengths from 0 to
+    beyond a thousand, output rows that are not 8-aligned (scalar jobs inside a word-kernel launch), single-strand
+    columns with bases outside A/C/G/T/N (redo path), large depths / errors (u16 wrap-around): the kernel against the
+    oracle's padded combine + mask with orientation done in numpy."""
+    import torch
+    L = O.load()
+    L.orc_codec_combine.restype = None
+    L.orc_codec_mask.restype = None
+    rng = np.random.default_rng(77)
+    dev = "cuda:0"
+    n_jobs = 32 * 9 + 5
+    UNIT = np.dtype([("out_off", "<u8"), ("read_begin", "<u4"), ("cons_len", "<u4")])
+    units = np.zeros(2 * n_jobs + 1, dtype=UNIT)
+    jobs = np.zeros(n_jobs, dtype=fg.CODEC_JOB_DTYPE)
+    off = 0; ooff = 0
+    for m in range(n_jobs):
+        kind = m % 13
+        for s in range(2):
+            l = int(rng.integers(1, 200)) if kind != 7 else int(rng.integers(300, 1300))
+            if kind == 9 and s == 1:
+                l = 0
+            units[2 * m + s]["out_off"] = off; units[2 * m + s]["cons_len"] = l
+            off += (l + 7) // 8 * 8
+        la, lb = int(units[2 * m]["cons_len"]), int(units[2 * m + 1]["cons_len"])
+        n = max(la, lb) + int(rng.integers(0, 40))
+        if kind == 5:
+            n = max(0, min(la, lb) - int(rng.integers(0, 10)))      # strands longer than the consensus
+        if kind == 11:
+            n = 0
+        jobs[m]["unit_a"], jobs[m]["unit_b"] = 2 * m, 2 * m + 1
+        jobs[m]["len"] = n
+        jobs[m]["rc_a"], jobs[m]["rc_b"], jobs[m]["rc_out"] = rng.integers(0, 2, 3)
+        jobs[m]["pad_a_left"] = int(rng.integers(0, max(1, n - la + 1 if n >= la else 8)))
+        jobs[m]["pad_b_left"] = int(rng.integers(0, max(1, n - lb + 1 if n >= lb else 8)))
+        if kind == 3:
+            ooff += int(rng.integers(1, 8))                          # this job's output row is not 8-aligned
+        jobs[m]["out_off"] = ooff
+        ooff += n if kind == 3 else (n + 7) // 8 * 8
+        if kind == 3:
+            ooff = (ooff + 7) // 8 * 8
+    units[2 * n_jobs]["out_off"] = off
+    sb = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=off + 16, p=[0.23, 0.23, 0.23, 0.23, 0.08])
+    sq = rng.integers(0, 94, size=off + 16).astype(np.uint8)
+    sq[rng.random(off + 16) < 0.1] = 2
+    sd = rng.integers(0, 40, size=off + 16).astype(np.uint16)
+    se = np.minimum(sd, rng.integers(0, 6, size=off + 16)).astype(np.uint16)
+    big = rng.random(off + 16) < 0.01
+    sd[big] = 65000; se[big] = rng.integers(0, 65536, size=int(big.sum()))
+    for m in range(n_jobs):                                         # exotic bases in a few jobs
+        if m % 13 == 2:
+            o, l = int(units[2 * m]["out_off"]), int(units[2 * m]["cons_len"])
+            if l:
+                sb[o + int(rng.integers(0, l))] = rng.choice(np.frombuffer(b"acgtnRY", np.uint8))
+    ss = fg.DeviceColumns(off + 16, dev)
+    ss.base.copy_(torch.from_numpy(sb)); ss.qual.copy_(torch.from_numpy(sq))
+    ss.depth.copy_(torch.from_numpy(sd.view(np.int16))); ss.errors.copy_(torch.from_numpy(se.view(np.int16)))
+    db = _UnitsOnly(fg, units, dev)
+    eng = fg.Engine(0, 45, 40, 1, 0)
+    tj = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(dev)
+    for ss_q, outer_q, outer_len, max_dis, max_rate in ((-1, -1, 0, 0xFFFFFFFF, 1.0), (10, 7, 9, 12, 0.3)):
+        out = fg.DeviceColumns(ooff + 8, dev)
+        for t in (out.base, out.qual, out.depth, out.errors):
+            t.fill_(0x55)
+        st = torch.full((n_jobs,), 255, dtype=torch.uint8, device=dev)
+        dis = torch.zeros(n_jobs, dtype=torch.int32, device=dev); dup = torch.zeros_like(dis)
+        cp = fg.lib.FgbCodecParams(ss_q, outer_q, outer_len, max_dis, max_rate)
+        eng.stats_reset()
+        eng.codec_combine_device(db, ss, tj, n_jobs, cp, out, st, dis, dup, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        g = out.to_host()
+        gs, gdis, gdup = st.cpu().numpy(), dis.cpu().numpy(), dup.cpu().numpy()
+        written = np.zeros(ooff + 8, bool)
+        tot_dup = tot_dis = 0
+        for m in range(n_jobs):
+            rb, rq, rd, re_, nb, nd = _codec_job_reference(L, (sb, sq, sd, se), units[2 * m], units[2 * m + 1], jobs[m],
+                                                           (ss_q, outer_q, outer_len))
+            o, n = int(jobs[m]["out_off"]), int(jobs[m]["len"])
+            assert np.array_equal(g.base[o:o + n], rb), (m, m % 13)
+            assert np.array_equal(g.qual[o:o + n], rq), (m, m % 13)
+            assert np.array_equal(g.depth[o:o + n], rd), (m, m % 13)
+            assert np.array_equal(g.errors[o:o + n], re_), (m, m % 13)
+            assert gdup[m] == nb and gdis[m] == nd, (m, m % 13)
+            want = 0
+            if nb > 0:
+                want = 1 if nd > max_dis else (2 if nd / nb > max_rate else 0)
+            assert gs[m] == want, (m, m % 13)
+            written[o:o + n] = True
+            tot_dup += nb; tot_dis += nd
+        # nothing outside the jobs' own rows is touched
+        assert np.all(g.base[~written[:len(g.base)]] == 0x55) and np.all(g.qual[~written[:len(g.qual)]] == 0x55)
+        assert np.all(g.depth[~written[:len(g.depth)]] == 0x5555) and np.all(g.errors[~written[:len(g.errors)]] == 0x5555)
+        s = eng.stats()
+        assert s["duplex_bases"] == tot_dup and s["duplex_disagreements"] == tot_dis and s["combined_jobs"] == n_jobs
+    eng.close()
