@@ -280,9 +280,21 @@ def records_leg(torch, fg, lib, device_index: int, families: int, n_threads: int
     res["one_caller"] = {"value": v1, "host_threads": n_threads}
     best = v1
     if callers > 1:
+        # a caller's threads idle while its batch is on the link / the device: several callers (the reference's
+        # one-caller-per-worker pattern) fill that time.  Threads are either split between the callers or every
+        # caller gets the full count (oversubscribed: the waiting caller's threads sleep).
         v2, _ = run(callers, max(1, n_threads // callers))
         res["two_callers"] = {"value": v2, "host_threads": max(1, n_threads // callers) * callers}
         best = max(best, v2)
+        multi = {}
+        for ncall, each in ((2, n_threads), (3, n_threads), (4, max(1, n_threads // 2))):
+            try:
+                v, _ = run(ncall, each)
+                multi[f"{ncall}x{each}"] = v
+                best = max(best, v)
+            except Exception as ex:      # pragma: no cover
+                multi[f"{ncall}x{each}"] = repr(ex)[:80]
+        res["callers_x_threads"] = multi
     R = G * depth
     res.update({"value": best, "unit": UNIT_READS, "families_per_batch": G, "reads_per_family": depth,
                 "h2d_bytes_per_batch": int(R * rec_len + R * 24 + G * 16), "d2h_bytes_per_batch": int(G * Lo * 4),

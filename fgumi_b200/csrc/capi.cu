@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -92,11 +93,17 @@ struct fgb_handle {
   double emax_rate = -1.0;                          // the max_base_error_rate d_emax was built for
   int n_slots = 2;                                  // FGB_SUBMIT_SLOTS (1..kSlots)
   uint64_t chunk_bytes = kChunkColumnBytes;         // FGB_SUBMIT_CHUNK_MB
+  bool chunk_bytes_set = false;                     // the environment fixed it: no per-batch adjustment
   unsigned long long* d_ostats = nullptr;            // overlap pre-pass counters (device u64[4])
   uint64_t* ostats_host = nullptr;                  // where fgb_wait adds them
   fgb_overlap_run* d_oruns = nullptr; uint64_t cap_oruns = 0;
   uint8_t* d_recstr = nullptr; uint64_t cap_recstr = 0;   // record assembly: the batch's string blob
+  fgb_record_job* d_recjobs = nullptr; uint64_t cap_recjobs = 0;   // ... and its per-unit jobs (both uploaded ahead of chunk 0)
   cudaEvent_t ev_recstr = nullptr;                         // ... uploaded on the first chunk's stream
+  bool trace = false;                               // FGB_SUBMIT_TRACE=1: per-chunk device timeline printed by fgb_wait
+  struct TraceMark { cudaEvent_t ev; const char* what; int chunk; };
+  std::vector<TraceMark> trace_ev;                  // device timeline of the last submit
+  std::chrono::steady_clock::time_point trace_t0, trace_t1;
   int vote_variant = 1;                             // FGB_VOTE_KERNEL=0: the general kernel votes every tile (A/B runs)
 };
 
@@ -230,7 +237,8 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("FGB_SUBMIT_SLOTS")) h->n_slots = std::max(1, std::min(kSlots, std::atoi(e)));
   if (const char* e = std::getenv("FGB_SUBMIT_CHUNK_MB"))
-    h->chunk_bytes = static_cast<uint64_t>(std::max(1, std::atoi(e))) << 20;
+    { h->chunk_bytes = static_cast<uint64_t>(std::max(1, std::atoi(e))) << 20; h->chunk_bytes_set = true; }
+  if (const char* e = std::getenv("FGB_SUBMIT_TRACE")) h->trace = std::atoi(e) != 0;
   if (const char* e = std::getenv("FGB_VOTE_KERNEL")) h->vote_variant = std::atoi(e) ? 1 : 0;
   h->params = *params;
   build_host_tables(params->error_rate_pre_umi, params->error_rate_post_umi, &h->host_tables);
@@ -294,7 +302,7 @@ void fgb_destroy(fgb_handle* h) {
   cudaFree(h->d_bad);
   cudaFree(h->d_ostats);
   cudaFree(h->d_oruns);
-  cudaFree(h->d_recstr);
+  cudaFree(h->d_recstr); cudaFree(h->d_recjobs);
   if (h->ev_recstr) cudaEventDestroy(h->ev_recstr);
   delete h;
 }
@@ -430,8 +438,15 @@ fgb_status launch_filter(fgb_handle* h, const fgb_unit* units, uint64_t u0, uint
   a.min_mean_base_quality = fp.min_mean_base_quality;
   a.max_no_call_fraction = fp.max_no_call_fraction;
   const uint64_t n = u1 - u0;
-  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + 7u) / 8u, static_cast<uint64_t>(h->sm_count) * 16u));
-  filter_simplex_kernel<<<grid, 256, 0, s>>>(a);
+  const uintptr_t align8 = reinterpret_cast<uintptr_t>(a.base) | reinterpret_cast<uintptr_t>(a.qual);
+  const uintptr_t align16 = reinterpret_cast<uintptr_t>(a.depth) | reinterpret_cast<uintptr_t>(a.errors);
+  const uint64_t chunks = (n + kFilterChunk - 1) / kFilterChunk;
+  if ((align8 & 7u) == 0 && (align16 & 15u) == 0 && chunks <= 0x7FFFFFFFull) {
+    filter_simplex_words_kernel<<<static_cast<unsigned>(chunks), 256, 0, s>>>(a);   // 8 positions per thread
+  } else {
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + 7u) / 8u, static_cast<uint64_t>(h->sm_count) * 16u));
+    filter_simplex_kernel<<<grid, 256, 0, s>>>(a);
+  }
   h->launches++;
   FGB_CUDA(h, cudaGetLastError());
   return FGB_OK;
@@ -537,6 +552,21 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
   const fgb_tile* T = in->tiles;
   uint64_t t0 = 0;
   int chunk = 0;
+  // Chunk size: the first upload and the last copy back are not overlapped with anything, so a batch is cut into at
+  // least ~8 chunks (a record-level batch of 200 k families is 240 MB per column: 96 MB chunks left a third of the
+  // link time exposed); large batches keep the default, below 24 MB the per-chunk launches start to show.
+  const uint64_t chunk_bytes = h->chunk_bytes_set ? h->chunk_bytes
+                               : std::min<uint64_t>(h->chunk_bytes, std::max<uint64_t>(24ull << 20, in->n_bytes / 8u));
+  if (h->trace) {
+    for (auto& m : h->trace_ev) cudaEventDestroy(m.ev);
+    h->trace_ev.clear();
+    h->trace_t0 = std::chrono::steady_clock::now();
+  }
+  auto mark = [&](cudaStream_t st, const char* what) {
+    if (!h->trace) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); h->trace_ev.push_back({e, what, chunk}); }
+  };
   while (t0 < in->n_tiles) {
     // Grow the chunk tile by tile up to kChunkColumnBytes of column bytes.
     uint64_t t1 = t0;
@@ -554,7 +584,7 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
         end = tl.byte_begin + tl.byte_len;
       }
       end = std::max(end, byte1);
-      if (!one_piece && t1 > t0 && end - byte0 > h->chunk_bytes) break;
+      if (!one_piece && t1 > t0 && end - byte0 > chunk_bytes) break;
       byte1 = end;
       ++t1;
     }
@@ -583,6 +613,17 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
     if ((st = ensure(h, &sl.out_errors, &c3, o1 - o0 + 4)) != FGB_OK) return st;
 
     cudaStream_t s = sl.stream;
+    mark(s, "chunk begins");
+    if (rjobs && chunk == 0) {
+      // K5's own inputs (string blob, per-unit jobs) travel FIRST: queued behind a chunk's record blob they would
+      // hold the assembly of chunk c until the upload of chunk c+1 had passed through the copy engine
+      if ((st = ensure(h, &h->d_recstr, &h->cap_recstr, opt->n_rec_string_bytes + 16)) != FGB_OK) return st;
+      if ((st = ensure(h, &h->d_recjobs, &h->cap_recjobs, in->n_units + 1)) != FGB_OK) return st;
+      FGB_CUDA(h, cudaMemcpyAsync(h->d_recstr, opt->rec_strings, opt->n_rec_string_bytes, cudaMemcpyHostToDevice, s));
+      FGB_CUDA(h, cudaMemcpyAsync(h->d_recjobs, rjobs, in->n_units * sizeof(fgb_record_job), cudaMemcpyHostToDevice, s));
+      if (!h->ev_recstr) FGB_CUDA(h, cudaEventCreateWithFlags(&h->ev_recstr, cudaEventDisableTiming));
+      FGB_CUDA(h, cudaEventRecord(h->ev_recstr, s));
+    }
     if (fmt == HostFormat::kPack8) {
       if ((st = ensure(h, &sl.packed, &sl.cap_packed, nbytes + 16)) != FGB_OK) return st;
       FGB_CUDA(h, cudaMemcpyAsync(sl.packed, in->bases + byte0, valid_bytes, cudaMemcpyHostToDevice, s));
@@ -727,9 +768,12 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
         h->launches++;
         FGB_CUDA(h, cudaGetLastError());
       }
+      mark(s, "inputs resident");
       if ((st = launch_unpack_records(h, ua, s)) != FGB_OK) return st;
     }
+    mark(s, "rows ready");
     if ((st = launch_vote(h, db, dc, s)) != FGB_OK) return st;
+    mark(s, "voted");
     if (n_djobs) {
       const fgb_duplex_out* ho = opt->duplex_out;
       const uint64_t nd = opt->n_duplex_out;
@@ -777,22 +821,13 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
     }
     if (rjobs) {
       // K5: the finished records of this chunk's units, straight into the host's output stream
-      if (chunk == 0) {
-        if ((st = ensure(h, &h->d_recstr, &h->cap_recstr, opt->n_rec_string_bytes + 16)) != FGB_OK) return st;
-        FGB_CUDA(h, cudaMemcpyAsync(h->d_recstr, opt->rec_strings, opt->n_rec_string_bytes, cudaMemcpyHostToDevice, s));
-        if (!h->ev_recstr) FGB_CUDA(h, cudaEventCreateWithFlags(&h->ev_recstr, cudaEventDisableTiming));
-        FGB_CUDA(h, cudaEventRecord(h->ev_recstr, s));
-      } else {
-        FGB_CUDA(h, cudaStreamWaitEvent(s, h->ev_recstr, 0));   // later chunks run on other streams
-      }
+      if (chunk != 0) FGB_CUDA(h, cudaStreamWaitEvent(s, h->ev_recstr, 0));   // later chunks run on other streams
       const uint64_t b_lo = rjobs[u0].out_off;
       const uint64_t b_hi = u1 < in->n_units ? rjobs[u1].out_off : opt->n_rec_out_bytes;
       if (b_hi < b_lo || b_hi > opt->n_rec_out_bytes) { h->last_error = "record jobs: offsets must ascend"; return FGB_ERR_LAYOUT; }
-      if ((st = ensure(h, &sl.recjobs, &sl.cap_recjobs, u1 - u0 + 1)) != FGB_OK) return st;
       if ((st = ensure(h, &sl.recout, &sl.cap_recout, b_hi - b_lo + 16)) != FGB_OK) return st;
-      FGB_CUDA(h, cudaMemcpyAsync(sl.recjobs, rjobs + u0, (u1 - u0) * sizeof(fgb_record_job), cudaMemcpyHostToDevice, s));
       AssembleArgs aa;
-      aa.units = db.units; aa.jobs = sl.recjobs - u0;
+      aa.units = db.units; aa.jobs = h->d_recjobs;
       aa.unit_begin = u0; aa.unit_end = u1;
       aa.base = dc.base; aa.qual = dc.qual; aa.depth = dc.depth; aa.errors = dc.errors;
       aa.strings = h->d_recstr; aa.prefix_len = opt->rec_prefix_len; aa.rg_len = opt->rec_rg_len;
@@ -804,6 +839,7 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
       assemble_simplex_kernel<<<agrid, 256, 0, s>>>(aa);
       h->launches++;
       FGB_CUDA(h, cudaGetLastError());
+      mark(s, "records assembled");
       if (b_hi > b_lo) FGB_CUDA(h, cudaMemcpyAsync(opt->rec_out + b_lo, sl.recout, b_hi - b_lo, cudaMemcpyDeviceToHost, s));
     }
     if (fp) {
@@ -818,6 +854,7 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
     }
     const uint64_t no = o1 - o0;
     if (!out->base) {                        // record assembly only: nothing else travels back
+      mark(s, "results home");
       t0 = t1;
       ++chunk;
       continue;
@@ -845,9 +882,11 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
       FGB_CUDA(h, cudaMemcpyAsync(out->depth + o0, sl.out_depth, no * 2, cudaMemcpyDeviceToHost, s));
       FGB_CUDA(h, cudaMemcpyAsync(out->errors + o0, sl.out_errors, no * 2, cudaMemcpyDeviceToHost, s));
     }
+    mark(s, "results home");
     t0 = t1;
     ++chunk;
   }
+  if (h->trace) h->trace_t1 = std::chrono::steady_clock::now();
   guard.ok = true;
   return FGB_OK;
 }
@@ -951,6 +990,18 @@ fgb_status fgb_wait(fgb_handle* h) {
   h->submit_pending = false;
   FGB_CUDA(h, cudaSetDevice(h->device));
   for (int s = 0; s < kSlots; ++s) FGB_CUDA(h, cudaStreamSynchronize(h->slots[s].stream));
+  if (h->trace && !h->trace_ev.empty()) {     // FGB_SUBMIT_TRACE=1: where the device time of the last submit went
+    const double host_ms = std::chrono::duration<double, std::milli>(h->trace_t1 - h->trace_t0).count();
+    const double wait_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h->trace_t1).count();
+    std::fprintf(stderr, "fgb submit trace: host side of the submit call %.2f ms, then %.2f ms until the streams drained\n", host_ms, wait_ms);
+    for (auto& m : h->trace_ev) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->trace_ev.front().ev, m.ev);
+      std::fprintf(stderr, "  chunk %d  %-18s +%8.3f ms\n", m.chunk, m.what, ms);
+      }
+    for (auto& m : h->trace_ev) cudaEventDestroy(m.ev);
+    h->trace_ev.clear();
+  }
   if (h->ostats_host) {                // overlap pre-pass counters of the submit that just finished
     unsigned long long v[4] = {0, 0, 0, 0};
     FGB_CUDA(h, cudaMemcpy(v, h->d_ostats, sizeof(v), cudaMemcpyDeviceToHost));
@@ -985,12 +1036,13 @@ fgb_status fgb_duplex_combine_device(fgb_handle* h, const fgb_batch* in, const f
   a.out_base = out->base; a.out_qual = out->qual; a.out_errors = out->errors;
   a.out_status = out->status;
   a.counters = h->d_counters;
-  const uintptr_t align_all = reinterpret_cast<uintptr_t>(a.bases) | reinterpret_cast<uintptr_t>(a.ss_base) |
-                              reinterpret_cast<uintptr_t>(a.ss_qual) | reinterpret_cast<uintptr_t>(a.ss_depth) |
-                              reinterpret_cast<uintptr_t>(a.out_base) | reinterpret_cast<uintptr_t>(a.out_qual) |
-                              reinterpret_cast<uintptr_t>(a.out_errors);
+  // the word kernel moves 8 elements at a time: byte columns 8-byte aligned, u16 columns 16-byte aligned
+  const uintptr_t align8 = reinterpret_cast<uintptr_t>(a.bases) | reinterpret_cast<uintptr_t>(a.ss_base) |
+                           reinterpret_cast<uintptr_t>(a.ss_qual) | reinterpret_cast<uintptr_t>(a.out_base) |
+                           reinterpret_cast<uintptr_t>(a.out_qual);
+  const uintptr_t align16 = reinterpret_cast<uintptr_t>(a.ss_depth) | reinterpret_cast<uintptr_t>(a.out_errors);
   const uint64_t chunks = (n_jobs + kDuplexChunk - 1) / kDuplexChunk;
-  if ((align_all & 15u) == 0 && chunks <= 0x7FFFFFFFull) {
+  if ((align8 & 7u) == 0 && (align16 & 15u) == 0 && chunks <= 0x7FFFFFFFull) {
     // word kernel: 8 positions per thread, a CTA per chunk of consecutive jobs
     duplex_combine_words_kernel<<<static_cast<unsigned>(chunks), kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   } else {
@@ -1021,12 +1073,12 @@ fgb_status fgb_codec_combine_device(fgb_handle* h, const fgb_batch* in, const fg
   a.out_errors = out->cols.errors;
   a.status = out->status; a.disagreements = out->disagreements; a.duplex_bases = out->duplex_bases;
   a.counters = h->d_counters;
-  const uintptr_t align_all = reinterpret_cast<uintptr_t>(a.ss_base) | reinterpret_cast<uintptr_t>(a.ss_qual) |
-                              reinterpret_cast<uintptr_t>(a.ss_depth) | reinterpret_cast<uintptr_t>(a.ss_errors) |
-                              reinterpret_cast<uintptr_t>(a.out_base) | reinterpret_cast<uintptr_t>(a.out_qual) |
-                              reinterpret_cast<uintptr_t>(a.out_depth) | reinterpret_cast<uintptr_t>(a.out_errors);
+  const uintptr_t align8 = reinterpret_cast<uintptr_t>(a.ss_base) | reinterpret_cast<uintptr_t>(a.ss_qual) |
+                           reinterpret_cast<uintptr_t>(a.out_base) | reinterpret_cast<uintptr_t>(a.out_qual);
+  const uintptr_t align16 = reinterpret_cast<uintptr_t>(a.ss_depth) | reinterpret_cast<uintptr_t>(a.ss_errors) |
+                            reinterpret_cast<uintptr_t>(a.out_depth) | reinterpret_cast<uintptr_t>(a.out_errors);
   const uint64_t chunks = (n_jobs + kCodecChunk - 1) / kCodecChunk;
-  if ((align_all & 15u) == 0 && chunks <= 0x7FFFFFFFull) {
+  if ((align8 & 7u) == 0 && (align16 & 15u) == 0 && chunks <= 0x7FFFFFFFull) {
     // word kernel: 8 output positions per thread, a CTA per chunk of consecutive jobs
     codec_combine_words_kernel<<<static_cast<unsigned>(chunks), kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   } else {

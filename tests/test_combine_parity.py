@@ -332,8 +332,7 @@ def test_codec_combine_generic_jobs(fg):
     tj = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(dev)
     for ss_q, outer_q, outer_len, max_dis, max_rate in ((-1, -1, 0, 0xFFFFFFFF, 1.0), (10, 7, 9, 12, 0.3)):
         out = fg.DeviceColumns(ooff + 8, dev)
-        for t in (out.base, out.qual, out.depth, out.errors):
-            t.fill_(0x55)
+        out.base.fill_(0x55); out.qual.fill_(0x55); out.depth.fill_(0x5555); out.errors.fill_(0x5555)
         st = torch.full((n_jobs,), 255, dtype=torch.uint8, device=dev)
         dis = torch.zeros(n_jobs, dtype=torch.int32, device=dev); dup = torch.zeros_like(dis)
         cp = fg.lib.FgbCodecParams(ss_q, outer_q, outer_len, max_dis, max_rate)
