@@ -154,8 +154,8 @@ fgb_status launch_vote(fgb_handle* h, const fgb_batch& b, const fgb_columns& out
     x.tiles = b.tiles + first;
     x.n_tiles = n;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, max_grid));
-    if (cls == 1) vote_kernel_shallow<<<grid, kThreads, sizeof(VoteSmem), stream>>>(x);
-    else if (cls == 2) vote_kernel_deep<<<grid, kThreads, sizeof(VoteSmem), stream>>>(x);
+    if (cls == 1) vote_kernel_shallow<<<grid, kThreads, sizeof(VoteSmem) + kPairSmemBytes, stream>>>(x);
+    else if (cls == 2) vote_kernel_deep<<<grid, kThreads, sizeof(VoteSmem) + kDeepSmemBytes, stream>>>(x);
     else vote_kernel<<<grid, kThreads, sizeof(VoteSmem), stream>>>(x);
     h->launches++;
   };
@@ -274,10 +274,10 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
                                 static_cast<int>(sizeof(VoteSmem)))) != cudaSuccess)
     return fail(e, "cudaFuncSetAttribute(vote_kernel)");
   if ((e = cudaFuncSetAttribute(vote_kernel_shallow, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(sizeof(VoteSmem)))) != cudaSuccess)
+                                static_cast<int>(sizeof(VoteSmem) + kPairSmemBytes))) != cudaSuccess)
     return fail(e, "cudaFuncSetAttribute(vote_kernel_shallow)");
   if ((e = cudaFuncSetAttribute(vote_kernel_deep, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(sizeof(VoteSmem)))) != cudaSuccess)
+                                static_cast<int>(sizeof(VoteSmem) + kDeepSmemBytes))) != cudaSuccess)
     return fail(e, "cudaFuncSetAttribute(vote_kernel_deep)");
   for (int s = 0; s < kSlots; ++s)
     if ((e = cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking)) != cudaSuccess)

@@ -95,6 +95,10 @@ struct __align__(128) VoteSmem {
   const uint8_t* pair_q;        // DeviceTables::pair_q (global memory, L1-resident)
 };
 
+constexpr uint32_t kPairSmemBytes = 94u * 94u;                 // 8836 = 4 * 2209
+static_assert(kPairSmemBytes % 4u == 0, "pair table is copied as words");
+static_assert(sizeof(VoteSmem) % 16u == 0, "the pair table follows VoteSmem in dynamic shared memory");
+
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -152,6 +156,12 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
           "r"(smem_u32(dst)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+// L2 prefetch of a global range (no completion mechanism: a hint the memory system runs ahead on).  Size a multiple
+// of 16, address 16-byte aligned.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 // ---- memory-space policy: tiles live in shared memory, oversize units are read from HBM -------
@@ -743,6 +753,10 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
   const uint32_t base32 = static_cast<uint32_t>(tv.byte_base);
   uint32_t* const wqueue = S.queue[warp];
   uint32_t* const wcount = &S.q_count[warp];
+  // V == 1: the pair table sits in dynamic shared memory right behind VoteSmem (kPairSmemBytes, copied in the
+  // kernel prologue); from global memory the eight random lookups per item were what bound depth 2 (each a
+  // 32-line gather in L1)
+  const uint8_t* const pair_sm = reinterpret_cast<const uint8_t*>(&S) + sizeof(VoteSmem);
 
   // ---------------- FAST PASS: one thread per 8 positions ----------------
   for (uint32_t item = vt; item < n_items; item += kVoteThreads) {
@@ -798,30 +812,59 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
       }
       uint64_t rbw = 0, rqw = 0;
       if (p0 < len) { rbw = M::ld64(tv.bases + row); rqw = M::ld64(tv.quals + row); }
-      uint64_t obw = 0, oqw = 0, odw_lo = 0, odw_hi = 0;
+      if (V == 1) {
+        // byte-parallel form of the per-position rule: positions of the read (pos < len, pos < cons_len) get the
+        // table quality or, below min_consensus_base_quality, (N, 2); depth 1 unless the base is N; positions of the
+        // consensus row behind the read's end are (N, 2, 0)
+        const uint32_t lim = len < cons_len ? len : cons_len;
+        const uint32_t cov = lim > p0 ? lim - p0 : 0u;
+        const uint32_t cm_lo = low_bytes_mask(cov), cm_hi = low_bytes_mask(cov > 4u ? cov - 4u : 0u);
+        const uint32_t b_lo = static_cast<uint32_t>(rbw), b_hi = static_cast<uint32_t>(rbw >> 32);
+        const uint32_t ql = __vminu4(static_cast<uint32_t>(rqw), 0x5F5F5F5Fu);          // `.get(idx).unwrap_or(0)`:
+        const uint32_t qh = __vminu4(static_cast<uint32_t>(rqw >> 32), 0x5F5F5F5Fu);    // single_q[94] = [95] = 0
+        const uint32_t a_lo = static_cast<uint32_t>(S.single_q[ql & 0xFFu]) | (static_cast<uint32_t>(S.single_q[(ql >> 8) & 0xFFu]) << 8) |
+                              (static_cast<uint32_t>(S.single_q[(ql >> 16) & 0xFFu]) << 16) | (static_cast<uint32_t>(S.single_q[ql >> 24]) << 24);
+        const uint32_t a_hi = static_cast<uint32_t>(S.single_q[qh & 0xFFu]) | (static_cast<uint32_t>(S.single_q[(qh >> 8) & 0xFFu]) << 8) |
+                              (static_cast<uint32_t>(S.single_q[(qh >> 16) & 0xFFu]) << 16) | (static_cast<uint32_t>(S.single_q[qh >> 24]) << 24);
+        const uint32_t keep_lo = bytes_ge(a_lo, min_cons_q > 255u ? 255u : min_cons_q) & cm_lo & (min_cons_q > 255u ? 0u : 0xFFFFFFFFu);
+        const uint32_t keep_hi = bytes_ge(a_hi, min_cons_q > 255u ? 255u : min_cons_q) & cm_hi & (min_cons_q > 255u ? 0u : 0xFFFFFFFFu);
+        const uint32_t kb_lo = spread_msb(keep_lo), kb_hi = spread_msb(keep_hi);
+        const uint32_t rb_lo = spread_msb(rm_lo), rb_hi = spread_msb(rm_hi);
+        wb_lo = ((b_lo & kb_lo) | (0x4E4E4E4Eu & ~kb_lo)) & rb_lo;
+        wb_hi = ((b_hi & kb_hi) | (0x4E4E4E4Eu & ~kb_hi)) & rb_hi;
+        wq_lo = ((a_lo & kb_lo) | (0x02020202u & ~kb_lo)) & rb_lo;
+        wq_hi = ((a_hi & kb_hi) | (0x02020202u & ~kb_hi)) & rb_hi;
+        const uint32_t nn_lo = ~zero_bytes(b_lo ^ 0x4E4E4E4Eu) & 0x80808080u, nn_hi = ~zero_bytes(b_hi ^ 0x4E4E4E4Eu) & 0x80808080u;   // base is not N
+        const uint32_t d_lo = spread_msb(nn_lo & cm_lo), d_hi = spread_msb(nn_hi & cm_hi);
+        dep = make_uint4(0x00010001u & __byte_perm(d_lo, 0u, 0x1100u), 0x00010001u & __byte_perm(d_lo, 0u, 0x3322u),
+                         0x00010001u & __byte_perm(d_hi, 0u, 0x1100u), 0x00010001u & __byte_perm(d_hi, 0u, 0x3322u));
+        ls.nocall += __popc(rm_lo & ~(keep_lo & nn_lo)) + __popc(rm_hi & ~(keep_hi & nn_hi));
+      } else {      // general / deep kernels: the literal per-position loop (single-read units are the shallow class's)
+        uint64_t obw = 0, oqw = 0, odw_lo = 0, odw_hi = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t pos = p0 + j;
-        if (pos < cons_len) {
-          uint32_t b = static_cast<uint32_t>(rbw >> (8 * j)) & 0xFFu;
-          uint32_t q = static_cast<uint32_t>(rqw >> (8 * j)) & 0xFFu;
-          uint32_t ob = 'N', oq = 2, od = 0;
-          if (pos < len) {
-            uint32_t adj = q < FGB_NTABLE ? S.single_q[q] : 0u;   // `.get(idx).unwrap_or(0)`
-            if (adj >= min_cons_q) { ob = b; oq = adj; }
-            od = (b != 'N');
+        for (int j = 0; j < 8; ++j) {
+          uint32_t pos = p0 + j;
+          if (pos < cons_len) {
+            uint32_t b = static_cast<uint32_t>(rbw >> (8 * j)) & 0xFFu;
+            uint32_t q = static_cast<uint32_t>(rqw >> (8 * j)) & 0xFFu;
+            uint32_t ob = 'N', oq = 2, od = 0;
+            if (pos < len) {
+              uint32_t adj = q < FGB_NTABLE ? S.single_q[q] : 0u;   // `.get(idx).unwrap_or(0)`
+              if (adj >= min_cons_q) { ob = b; oq = adj; }
+              od = (b != 'N');
+            }
+            obw |= static_cast<uint64_t>(ob) << (8 * j);
+            oqw |= static_cast<uint64_t>(oq) << (8 * j);
+            if (j < 4) odw_lo |= static_cast<uint64_t>(od) << (16 * j);
+            else odw_hi |= static_cast<uint64_t>(od) << (16 * (j - 4));
+            ls.nocall += (ob == 'N');
           }
-          obw |= static_cast<uint64_t>(ob) << (8 * j);
-          oqw |= static_cast<uint64_t>(oq) << (8 * j);
-          if (j < 4) odw_lo |= static_cast<uint64_t>(od) << (16 * j);
-          else odw_hi |= static_cast<uint64_t>(od) << (16 * (j - 4));
-          ls.nocall += (ob == 'N');
         }
+        wb_lo = static_cast<uint32_t>(obw); wb_hi = static_cast<uint32_t>(obw >> 32);
+        wq_lo = static_cast<uint32_t>(oqw); wq_hi = static_cast<uint32_t>(oqw >> 32);
+        dep = make_uint4(static_cast<uint32_t>(odw_lo), static_cast<uint32_t>(odw_lo >> 32),
+                         static_cast<uint32_t>(odw_hi), static_cast<uint32_t>(odw_hi >> 32));
       }
-      wb_lo = static_cast<uint32_t>(obw); wb_hi = static_cast<uint32_t>(obw >> 32);
-      wq_lo = static_cast<uint32_t>(oqw); wq_hi = static_cast<uint32_t>(oqw >> 32);
-      dep = make_uint4(static_cast<uint32_t>(odw_lo), static_cast<uint32_t>(odw_lo >> 32),
-                       static_cast<uint32_t>(odw_hi), static_cast<uint32_t>(odw_hi >> 32));
     } else if (V == 1 && n == 2u && min_reads <= 2u) {
       // two-read units: where both reads cover the position and agree on an A/C/G/T base, the result is the
       // host-evaluated outcome of the reference's add / add / call sequence (host_tables.cpp pair_quality)
@@ -853,7 +896,7 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
           uint32_t qa = static_cast<uint32_t>(q0w >> (8 * j)) & 0xFFu, qb = static_cast<uint32_t>(q1w >> (8 * j)) & 0xFFu;
           qa = qa > FGB_MAX_PHRED ? FGB_MAX_PHRED : qa;
           qb = qb > FGB_MAX_PHRED ? FGB_MAX_PHRED : qb;
-          const uint32_t cq = __ldg(S.pair_q + qa * 94u + qb);
+          const uint32_t cq = pair_sm[qa * 94u + qb];      // shared-memory copy (kernel prologue): eight gathers per item
           if (cq != 255u) {
             const bool masked = cq < min_cons_q;                               // vanilla_caller.rs:1347-1348
             obw |= static_cast<uint64_t>(masked ? 'N' : (static_cast<uint32_t>(b0w >> (8 * j)) & 0xFFu)) << (8 * j);
@@ -1234,6 +1277,275 @@ __device__ __forceinline__ void vote_tile_deep(const VoteArgs& a, VoteSmem& S, c
   if (lane == 0) *wcount = 0;
 }
 
+// Deep-class tiles, second form (shared-memory tiles of at most kDeepItemsMax items -- every tile the planner
+// cuts for this class).  The (item, row) plane of the tile is dealt flat to the 256 voting threads: thread t walks
+// rows grp, grp + G, ... of item t mod n_items, G = 256 / n_items.  Lanes of a warp then read CONSECUTIVE words of one
+// row (no bank conflicts; the group-of-lanes form above strides over rows), 247 of 256 threads work on a 19-item tile
+// (152 with lane groups), and nothing is folded by shuffles: a thread whose partial result is not the identity --
+// a dissenting row, a low quality -- merges it into the item's slot in shared memory with an atomic.  One named
+// barrier per tile separates the walk from the finish; the finish of item i runs on lane i / 8 of warp i mod 8, so the
+// queued positions are spread over all warps.  The slots are double-buffered by tile parity: the finisher resets the
+// slot it read, two tiles before its next use.
+constexpr uint32_t kDeepItemsMax = 112u;        // >= kTileCapBytes / (8 * kDeepMin) = 106
+struct DeepSlots {
+  uint32_t diff_lo[kDeepItemsMax], diff_hi[kDeepItemsMax];
+  uint32_t okq_lo[kDeepItemsMax], okq_hi[kDeepItemsMax];
+  uint32_t cnt_lo[kDeepItemsMax], cnt_hi[kDeepItemsMax];
+  uint32_t bad_lo[kDeepItemsMax], bad_hi[kDeepItemsMax];
+  uint32_t minlen[kDeepItemsMax];
+};
+constexpr uint32_t kDeepSmemBytes = 2u * sizeof(DeepSlots);
+
+__device__ __forceinline__ void consumer_barrier() {      // the eight voting warps (the producer warp is not part of it)
+  asm volatile("bar.sync 1, %0;" ::"n"(kVoteThreads) : "memory");
+}
+
+template <bool Regular>
+__device__ __forceinline__ void vote_tile_deep_flat(const VoteArgs& a, VoteSmem& S, DeepSlots& R, const Stage& st,
+                                                    const TileView<ShMem>& tv, uint32_t tid, uint32_t warp,
+                                                    uint32_t n_items, LocalStats& ls) {
+  using M = ShMem;
+  const uint32_t lane = tid & 31u;
+  const uint32_t n_units = st.tile.n_units;
+  const uint64_t out0 = st.units[0].out_off;
+  const uint32_t min_reads = a.min_reads, min_cons_q = a.min_cons_q, fast_qual = a.fast_qual;
+  const uint32_t reg_len = st.units[0].cons_len;
+  const uint32_t reg_row0 = (st.tile.flags & kTileFlagSkew8) ? 8u : 0u;
+  const bool fast_masked = fast_qual < min_cons_q;
+  const uint32_t fq4 = (fast_masked ? 2u : fast_qual) * 0x01010101u;
+  const uint32_t uni_m = st.tile.flags >> 8;
+  const uint32_t uni_recip = st.aux[0];
+  const uint32_t base32 = static_cast<uint32_t>(tv.byte_base);
+  uint32_t* const wqueue = S.queue[warp];
+  uint32_t* const wcount = &S.q_count[warp];
+
+  struct Item {
+    uint32_t u, rb, n, cons_len, p0, qt;
+    bool near_ok, fast_ok;
+  };
+  auto locate = [&](uint32_t item) {
+    Item it;
+    if (Regular || uni_m) {
+      it.u = __umulhi(item, uni_recip);
+    } else {
+      uint32_t lo = 0, hi = n_units;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint32_t start = static_cast<uint32_t>((st.units[mid].out_off - out0) >> 3);
+        if (start <= item) lo = mid; else hi = mid;
+      }
+      it.u = lo;
+    }
+    const fgb_unit un = st.units[it.u];
+    it.rb = un.read_begin;
+    it.n = st.units[it.u + 1].read_begin - it.rb;
+    it.cons_len = un.cons_len;
+    it.p0 = Regular ? (item - it.u * uni_m) << 3 : (item - static_cast<uint32_t>((un.out_off - out0) >> 3)) << 3;
+    // One quality threshold per unit: the near-unanimous one when the depth has it (it also proves the unanimous
+    // positions: it is never below qt[n]), else the unanimous one alone.
+    const uint32_t qt_near = S.qt3[it.n < kQtEntries ? it.n : kQtEntries - 1];
+    it.near_ok = qt_near <= FGB_MAX_PHRED;
+    it.qt = it.near_ok ? qt_near : S.qt[it.n < kQtEntries ? it.n : kQtEntries - 1];
+    it.fast_ok = (it.qt <= FGB_MAX_PHRED) && (it.n >= min_reads) && (it.n <= 0xFFFFu) && it.n >= 2u;
+    return it;
+  };
+  // read 0's word of the item: the reference every row is compared with
+  auto ref_word = [&](const Item& it, uint32_t& b0_lo, uint32_t& b0_hi) {
+    uint64_t w;
+    if (Regular) {
+      w = M::ld64(tv.bases + reg_row0 + ((it.rb - st.tile.read_begin) * uni_m + (it.p0 >> 3)) * 8u);
+    } else {
+      const uint64_t d = M::ld64(tv.reads + static_cast<typename M::off_t>(it.rb - tv.read_base) * 8u);
+      const uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
+      w = M::ld64(tv.bases + M::row_offset(d, tv.byte_base, base32) + (len > it.p0 ? it.p0 : 0u));
+    }
+    b0_lo = static_cast<uint32_t>(w); b0_hi = static_cast<uint32_t>(w >> 32);
+  };
+
+  // ---------------- WALK: thread t -> item t mod n_items, rows grp, grp + G, ... ----------------
+  const uint32_t G = n_items ? static_cast<uint32_t>(kVoteThreads) / n_items : 0u;   // >= 2 (n_items <= kDeepItemsMax)
+  const uint32_t grp = n_items > 1u ? __umulhi(tid, 0xFFFFFFFFu / n_items + 1u) : tid;   // tid / n_items, exact for these sizes
+  if (grp < G) {
+    const uint32_t item = tid - grp * n_items;
+    const Item it = locate(item);
+    if (it.fast_ok && grp < it.n) {
+      uint32_t b0_lo, b0_hi;
+      ref_word(it, b0_lo, b0_hi);
+      const uint32_t tsplat = it.qt * 0x01010101u;
+      uint32_t diff_lo = 0, diff_hi = 0, okq_lo = 0x80808080u, okq_hi = 0x80808080u, minlen = 0xFFFFFFFFu;
+      // rows that differ from read 0 somewhere in the word (rare): per byte, how many rows differ, and whether a
+      // differing row holds anything but A/C/G/T there (such an observation is not counted at all, base_builder.rs:300)
+      uint32_t cnt_lo = 0, cnt_hi = 0, bad_lo = 0, bad_hi = 0;
+      auto dissent = [&](uint32_t wl, uint32_t wh, uint32_t xl, uint32_t xh) {
+        const uint32_t ml = ~zero_bytes(xl) & 0x80808080u, mh = ~zero_bytes(xh) & 0x80808080u;
+        bad_lo |= ml & ~acgt_bytes(wl); bad_hi |= mh & ~acgt_bytes(wh);
+        cnt_lo += ml >> 7; cnt_hi += mh >> 7;
+      };
+      if (Regular) {
+        const uint32_t step = uni_m * 8u;
+        typename M::addr_t pb = tv.bases + reg_row0 + ((it.rb - st.tile.read_begin + grp) * uni_m + (it.p0 >> 3)) * 8u;
+        const uint32_t gstep = step * G;
+#pragma unroll 4
+        for (uint32_t r = grp; r < it.n; r += G, pb += gstep) {
+          const uint64_t wb = M::ld64(pb);
+          const uint64_t wq = M::ld64(pb + kTileCapBytes);
+          const uint32_t xl = static_cast<uint32_t>(wb) ^ b0_lo, xh = static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+          diff_lo |= xl; diff_hi |= xh;
+          if (xl | xh) dissent(static_cast<uint32_t>(wb), static_cast<uint32_t>(wb >> 32), xl, xh);
+          okq_lo &= (static_cast<uint32_t>(wq) | 0x80808080u) - tsplat;
+          okq_hi &= (static_cast<uint32_t>(wq >> 32) | 0x80808080u) - tsplat;
+        }
+      } else {
+        typename M::addr_t rd = tv.reads + static_cast<typename M::off_t>(it.rb - tv.read_base) * 8u;
+#pragma unroll 4
+        for (uint32_t r = grp; r < it.n; r += G) {
+          const uint64_t d = M::ld64(rd + r * 8u);
+          const uint32_t len = static_cast<uint32_t>(d) & 0xFFFFu;
+          minlen = len < minlen ? len : minlen;
+          const typename M::off_t row = M::row_offset(d, tv.byte_base, base32) + (len > it.p0 ? it.p0 : 0u);
+          const uint64_t wb = M::ld64(tv.bases + row);
+          const uint64_t wq = M::ld64(tv.quals + row);
+          const uint32_t xl = static_cast<uint32_t>(wb) ^ b0_lo, xh = static_cast<uint32_t>(wb >> 32) ^ b0_hi;
+          diff_lo |= xl; diff_hi |= xh;
+          if (xl | xh) dissent(static_cast<uint32_t>(wb), static_cast<uint32_t>(wb >> 32), xl, xh);
+          okq_lo &= (static_cast<uint32_t>(wq) | 0x80808080u) - tsplat;
+          okq_hi &= (static_cast<uint32_t>(wq >> 32) | 0x80808080u) - tsplat;
+        }
+        if (minlen != 0xFFFFFFFFu) atomicMin(&R.minlen[item], minlen);
+      }
+      // merge what is not the identity (a unanimous, well-covered, high-quality word merges nothing)
+      if (diff_lo) atomicOr(&R.diff_lo[item], diff_lo);
+      if (diff_hi) atomicOr(&R.diff_hi[item], diff_hi);
+      if (okq_lo != 0x80808080u) atomicAnd(&R.okq_lo[item], okq_lo);
+      if (okq_hi != 0x80808080u) atomicAnd(&R.okq_hi[item], okq_hi);
+      if (cnt_lo) atomicAdd(&R.cnt_lo[item], cnt_lo);        // byte counters: at most n < 255 rows differ
+      if (cnt_hi) atomicAdd(&R.cnt_hi[item], cnt_hi);
+      if (bad_lo) atomicOr(&R.bad_lo[item], bad_lo);
+      if (bad_hi) atomicOr(&R.bad_hi[item], bad_hi);
+    }
+  }
+  consumer_barrier();
+
+  // ---------------- FINISH: item i on lane i / 8 of warp i mod 8 ----------------
+  {
+    const uint32_t item = (lane << 3) + warp;
+    if (item < n_items) {
+      const Item it = locate(item);
+      const uint32_t real = it.cons_len - it.p0 < 8u ? it.cons_len - it.p0 : 8u;
+      const uint32_t rm_lo = low_bytes_mask(real), rm_hi = low_bytes_mask(real > 4u ? real - 4u : 0u);
+      const uint64_t o = out0 + (static_cast<uint64_t>(item) << 3);
+      const uint32_t n = it.n, rb = it.rb, p0 = it.p0;
+      if (n == 1u) {
+        // a single-read unit never belongs to a deep tile (planner); kept correct for hand-made tile arrays:
+        // the single-input rule (vanilla_caller.rs:1285-1316) position by position
+        const uint64_t d = M::ld64(tv.reads + static_cast<typename M::off_t>(rb - tv.read_base) * 8u);
+        const uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
+        for (uint32_t j = 0; j < real; ++j) {
+          const uint32_t pos = p0 + j;
+          Called c; c.base = 'N'; c.qual = 2; c.depth = 0; c.errors = 0;
+          if (pos < len) {
+            const typename M::off_t row = static_cast<typename M::off_t>((d >> 16) - tv.byte_base) + pos;
+            const uint32_t b = M::ld8(tv.bases + row), q = M::ld8(tv.quals + row);
+            const uint32_t adj = q < FGB_NTABLE ? S.single_q[q] : 0u;
+            if (adj >= min_cons_q) { c.base = b; c.qual = adj; }
+            c.depth = (b != 'N');
+          }
+          ls.nocall += (c.base == 'N');
+          write_called(a, o + j, c);
+        }
+        ls.positions += real;
+      } else {
+        uint32_t b0_lo = 0, b0_hi = 0;
+        uint32_t fm_lo = 0, fm_hi = 0;
+        uint4 errw = make_uint4(0, 0, 0, 0);
+        if (it.fast_ok) {
+          ref_word(it, b0_lo, b0_hi);
+          const uint32_t diff_lo = R.diff_lo[item], diff_hi = R.diff_hi[item];
+          const uint32_t okq_lo = R.okq_lo[item], okq_hi = R.okq_hi[item];
+          const uint32_t cnt_lo = R.cnt_lo[item], cnt_hi = R.cnt_hi[item];
+          const uint32_t bad_lo = R.bad_lo[item], bad_hi = R.bad_hi[item];
+          const uint32_t minlen = Regular ? reg_len : R.minlen[item];
+          // back to the identities for this slot's next tile (two tiles from now, behind another barrier)
+          if (diff_lo) R.diff_lo[item] = 0u;
+          if (diff_hi) R.diff_hi[item] = 0u;
+          if (okq_lo != 0x80808080u) R.okq_lo[item] = 0x80808080u;
+          if (okq_hi != 0x80808080u) R.okq_hi[item] = 0x80808080u;
+          if (cnt_lo) R.cnt_lo[item] = 0u;
+          if (cnt_hi) R.cnt_hi[item] = 0u;
+          if (bad_lo) R.bad_lo[item] = 0u;
+          if (bad_hi) R.bad_hi[item] = 0u;
+          if (!Regular) R.minlen[item] = 0xFFFFFFFFu;
+          const uint32_t covered = minlen > p0 ? minlen - p0 : 0u;
+          const uint32_t base_lo = okq_lo & acgt_bytes(b0_lo) & low_bytes_mask(covered) & rm_lo;
+          const uint32_t base_hi = okq_hi & acgt_bytes(b0_hi) & low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
+          fm_lo = zero_bytes(diff_lo) & base_lo;
+          fm_hi = zero_bytes(diff_hi) & base_hi;
+          if (it.near_ok && (cnt_lo | cnt_hi)) {
+            // near-unanimous positions: at most kNearK rows differ, all of them A/C/G/T: the dominant-winner proof
+            // holds (host_tables.cpp qt3): read 0's base wins with phred(ln_pre), depth n, errors = the count
+            const uint32_t le_lo = ~((cnt_lo | 0x80808080u) - 0x04040404u) & ~cnt_lo & 0x80808080u;   // cnt <= 3
+            const uint32_t le_hi = ~((cnt_hi | 0x80808080u) - 0x04040404u) & ~cnt_hi & 0x80808080u;
+            const uint32_t nm_lo = base_lo & le_lo & ~bad_lo & ~fm_lo, nm_hi = base_hi & le_hi & ~bad_hi & ~fm_hi;
+            const uint32_t el = cnt_lo & spread_msb(nm_lo), eh = cnt_hi & spread_msb(nm_hi);
+            errw = make_uint4(__byte_perm(el, 0u, 0x4140u), __byte_perm(el, 0u, 0x4342u),
+                              __byte_perm(eh, 0u, 0x4140u), __byte_perm(eh, 0u, 0x4342u));
+            fm_lo |= nm_lo; fm_hi |= nm_hi;
+          }
+        }
+        const uint32_t fb_lo = spread_msb(fm_lo), fb_hi = spread_msb(fm_hi);
+        const uint32_t wb_lo = (fast_masked ? 0x4E4E4E4Eu : b0_lo) & fb_lo;
+        const uint32_t wb_hi = (fast_masked ? 0x4E4E4E4Eu : b0_hi) & fb_hi;
+        const uint32_t nn = n | (n << 16);
+        uint4 dep;
+        dep.x = nn & __byte_perm(fb_lo, 0u, 0x1100u);
+        dep.y = nn & __byte_perm(fb_lo, 0u, 0x3322u);
+        dep.z = nn & __byte_perm(fb_hi, 0u, 0x1100u);
+        dep.w = nn & __byte_perm(fb_hi, 0u, 0x3322u);
+        ls.nocall += fast_masked ? (__popc(fm_lo) + __popc(fm_hi)) : 0;
+        ls.positions += real;
+        *reinterpret_cast<uint2*>(a.out_base + o) = make_uint2(wb_lo, wb_hi);
+        *reinterpret_cast<uint2*>(a.out_qual + o) = make_uint2(fq4 & fb_lo, fq4 & fb_hi);
+        *reinterpret_cast<uint4*>(a.out_depth + o) = dep;
+        *reinterpret_cast<uint4*>(a.out_errors + o) = errw;
+        const uint32_t todo_lo = rm_lo & ~fm_lo, todo_hi = rm_hi & ~fm_hi;
+        if (todo_lo | todo_hi) {
+          const uint32_t cnt = static_cast<uint32_t>(__popc(todo_lo) + __popc(todo_hi));
+          uint32_t slot = atomicAdd(wcount, cnt);
+          const uint32_t ent = (it.u << 16) | p0;
+          uint32_t keep_lo = 0, keep_hi = 0;
+          for (uint32_t t = todo_lo; t; t &= t - 1u, ++slot) {
+            if (slot < kWarpQueueCap) wqueue[slot] = ent + ((__ffs(t) - 1) >> 3);
+            else keep_lo |= t & (0u - t);
+          }
+          for (uint32_t t = todo_hi; t; t &= t - 1u, ++slot) {
+            if (slot < kWarpQueueCap) wqueue[slot] = ent + 4u + ((__ffs(t) - 1) >> 3);
+            else keep_hi |= t & (0u - t);
+          }
+          if (keep_lo | keep_hi) {                             // rare: the warp queue overflowed
+            for (uint32_t j = 0; j < 8u; ++j) {
+              if ((j < 4u ? keep_lo >> (8u * j) : keep_hi >> (8u * (j - 4u))) & 0x80u) {
+                const Called c = resolve_position<M>(tv, S, rb, n, p0 + j, a, ls);
+                write_called(a, o + j, c);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  uint32_t qn = *wcount;
+  qn = qn < kWarpQueueCap ? qn : kWarpQueueCap;
+  if (qn) slow_pass_g<M, 8u>(a, S, st, tv, wqueue, qn, lane, ls);     // eight lanes per queued position
+  __syncwarp();
+  if (lane == 0) *wcount = 0;
+}
+
+#ifndef FGB_PREFETCH_AHEAD
+#define FGB_PREFETCH_AHEAD 2
+#endif
+constexpr uint32_t kPrefetchAhead = FGB_PREFETCH_AHEAD;   // rounds of tiles pulled into L2 ahead of the stage pipeline (0 = off)
+
 template <int V>
 __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -1249,6 +1561,20 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
   for (uint32_t i = tid; i < kQtEntries; i += kThreads) { S.qt[i] = a.tables->qt[i]; S.qt3[i] = a.tables->qt3[i]; }
   for (uint32_t i = tid; i < 96; i += kThreads) S.dfix[i] = a.tables->dfix[i];
   if (tid < kConsumerWarps) S.q_count[tid] = 0;
+  if (V == 1) {                                             // the shallow kernel's in-line pair table
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw + sizeof(VoteSmem));
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.tables->pair_q);
+    for (uint32_t i = tid; i < kPairSmemBytes / 4u; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  if (V == 2) {                                             // the deep kernel's reduction slots: identities
+    DeepSlots* R2 = reinterpret_cast<DeepSlots*>(smem_raw + sizeof(VoteSmem));
+    for (uint32_t i = tid; i < 2u * kDeepItemsMax; i += kThreads) {
+      DeepSlots& R = R2[i / kDeepItemsMax];
+      const uint32_t j = i % kDeepItemsMax;
+      R.diff_lo[j] = 0u; R.diff_hi[j] = 0u; R.okq_lo[j] = 0x80808080u; R.okq_hi[j] = 0x80808080u;
+      R.cnt_lo[j] = 0u; R.cnt_hi[j] = 0u; R.bad_lo[j] = 0u; R.bad_hi[j] = 0u; R.minlen[j] = 0xFFFFFFFFu;
+    }
+  }
   if (tid == 0) {
     S.ln_pre = a.tables->ln_pre;
     S.g2fix = a.tables->g2fix;
@@ -1273,6 +1599,23 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
       for (uint32_t t = blockIdx.x; t < n_tiles; t += grid, ++k) {
         const int s = k % kStages;
         const uint32_t use = k / kStages;
+        if (kPrefetchAhead) {
+          // The two stages bound the bytes this CTA has in flight to one tile while the other is voted; with small or
+          // quickly voted tiles (deep and shallow classes) that is less than the bandwidth-delay product.  So the
+          // byte columns of the tile kPrefetchAhead rounds on are pulled into L2 now: by the time a stage is free
+          // for it the TMA copy is an L2 hit.
+          const uint64_t ta = static_cast<uint64_t>(t) + static_cast<uint64_t>(kPrefetchAhead) * grid;
+          if (ta < n_tiles) {
+            const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(a.tiles + ta));
+            const uint4 p1 = __ldg(reinterpret_cast<const uint4*>(a.tiles + ta) + 1);
+            const uint64_t pb = (static_cast<uint64_t>(p0.y) << 32) | p0.x;
+            const uint32_t plen = (p0.z + 15u) & ~15u;
+            if (!(p1.w & kTileFlagDirect) && p0.z) {
+              l2_prefetch_bulk(a.bases + pb, plen);
+              l2_prefetch_bulk(a.quals + pb, plen);
+            }
+          }
+        }
         if (use > 0) {                                          // consumers released the stage
           mbar_wait(&S.empty[s], (use - 1u) & 1u, V == 2 ? 1000u : 20000u);   // deep tiles are small: shorter naps
         }
@@ -1335,7 +1678,11 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
       tv.reads = reinterpret_cast<const uint8_t*>(st.reads) + (st.tile.read_begin & 1u) * 8u;
       tv.byte_base = st.tile.byte_begin; tv.read_base = st.tile.read_begin;
       if (V == 2) {
-        if (st.tile.flags & kTileFlagRegular) vote_tile_deep<ShMem, true>(a, S, st, tv, tid, warp, n_items, ls);
+        if (n_items <= kDeepItemsMax) {          // (n_items is the same for every warp: the branch is CTA-uniform)
+          DeepSlots& R = reinterpret_cast<DeepSlots*>(smem_raw + sizeof(VoteSmem))[k & 1u];
+          if (st.tile.flags & kTileFlagRegular) vote_tile_deep_flat<true>(a, S, R, st, tv, tid, warp, n_items, ls);
+          else vote_tile_deep_flat<false>(a, S, R, st, tv, tid, warp, n_items, ls);
+        } else if (st.tile.flags & kTileFlagRegular) vote_tile_deep<ShMem, true>(a, S, st, tv, tid, warp, n_items, ls);
         else vote_tile_deep<ShMem, false>(a, S, st, tv, tid, warp, n_items, ls);
       } else {
         if (st.tile.flags & kTileFlagRegular) vote_tile<ShMem, true, V>(a, S, st, tv, vt, warp, n_items, ls);

@@ -10,6 +10,10 @@ from fgumi_b200 import benchlegs
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 lib = fg.lib.load()
+if os.environ.get("FGB_BIND_NUMA"):      # like bench.py: run (and first-touch page-locked memory) on the GPU's NUMA node
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    print("numa:", bench.bind_to_gpu_numa(torch, 0))
 pinned, rec_off, group_rec, rec_len = benchlegs.make_record_batch(torch, G, 8)
 bp, op, gp = pinned.data_ptr(), rec_off.ctypes.data, group_rec.ctypes.data
 c = benchlegs._Caller(lib, 0, T)
