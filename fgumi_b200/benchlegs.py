@@ -66,14 +66,23 @@ def duplex_leg(torch, fg, dev, device_index: int, molecules: int, seed: int = 43
     t1 = timed(torch, lambda: eng.vote_device(tb, ss, s))
     t2 = timed(torch, lambda: eng.duplex_combine_device(tb, ss, tj, 2 * M, ob, oq, oe, st, s))
     k1_bytes = vote_bytes(depths)
-    k2_bytes = 2 * M * (2 * 6 * L + 4 * L + 2 * 8 * L + 16)   # 2 SS columns in, (base, qual, errors) out, 8 source rows
+    # K2 traffic per job = the two single-strand rows in (2 x 6 L) + (base, qual, errors) out (4 L): 2 400 B,
+    # 13 392 B per molecule with the four votes.  The exact error recount also re-reads the 8 pooled source rows
+    # (8 L more per job, not in SURVEY's figure): `*_touched` counts them (and only the three SS columns K2 reads).
+    k2_bytes = 2 * M * (2 * 6 * L + 4 * L)
+    k2_touched = 2 * M * (2 * 4 * L + 4 * L + 8 * L + 16)
     peak = hbm_peak()
     eng.close()
     del tb, ss
     return {"workload": "BASELINE.json configs[2]: duplex, 4+4 reads per strand, 150bp", "molecules": M,
             "value": M / ((t1 + t2) * 1e-3), "unit": "molecules/s", "k1_ms": t1, "k2_ms": t2,
             "k1_frac": k1_bytes / t1 / 1e6 / peak, "k2_frac": k2_bytes / t2 / 1e6 / peak,
-            "frac": (k1_bytes + k2_bytes) / (t1 + t2) / 1e6 / peak, "bytes_per_molecule": (k1_bytes + k2_bytes) / M}
+            "frac": (k1_bytes + k2_bytes) / (t1 + t2) / 1e6 / peak, "bytes_per_molecule": (k1_bytes + k2_bytes) / M,
+            "k2_frac_touched": k2_touched / t2 / 1e6 / peak,
+            "frac_touched": (k1_bytes + k2_touched) / (t1 + t2) / 1e6 / peak,
+            "bytes_per_molecule_touched": (k1_bytes + k2_touched) / M,
+            "bytes": "frac / k2_frac use SURVEY 8(d)'s 13 392 B per molecule; *_touched add the 8 pooled source rows the exact "
+                     "error recount re-reads per job (and count only the SS columns K2 reads)"}
 
 
 def codec_leg(torch, fg, dev, device_index: int, molecules: int, seed: int = 44, sort_by_depth: bool = True):

@@ -154,7 +154,7 @@ fgb_status launch_vote(fgb_handle* h, const fgb_batch& b, const fgb_columns& out
     x.tiles = b.tiles + first;
     x.n_tiles = n;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, max_grid));
-    if (cls == 1) vote_kernel_shallow<<<grid, kThreads, sizeof(VoteSmem) + kPairSmemBytes, stream>>>(x);
+    if (cls == 1) vote_kernel_shallow<<<grid, kThreads, sizeof(VoteSmem) + kShallowSmemBytes, stream>>>(x);
     else if (cls == 2) vote_kernel_deep<<<grid, kThreads, sizeof(VoteSmem) + kDeepSmemBytes, stream>>>(x);
     else vote_kernel<<<grid, kThreads, sizeof(VoteSmem), stream>>>(x);
     h->launches++;
@@ -266,6 +266,8 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   std::memcpy(dt.pair_q, h->host_tables.pair_q, sizeof(dt.pair_q));
   std::memcpy(dt.sumt, h->host_tables.sumt, sizeof(dt.sumt));
   std::memcpy(dt.qt3, h->host_tables.qt3, sizeof(dt.qt3));
+  std::memcpy(dt.ugap_bp, h->host_tables.ugap_bp, sizeof(dt.ugap_bp));
+  std::memcpy(dt.ugap_q, h->host_tables.ugap_q, sizeof(dt.ugap_q));
   if ((e = cudaMemcpy(h->d_tables, &dt, sizeof(dt), cudaMemcpyHostToDevice)) != cudaSuccess)
     return fail(e, "cudaMemcpy tables");
   if ((e = cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * FGB_NCOUNTERS)) != cudaSuccess)
@@ -274,7 +276,7 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
                                 static_cast<int>(sizeof(VoteSmem)))) != cudaSuccess)
     return fail(e, "cudaFuncSetAttribute(vote_kernel)");
   if ((e = cudaFuncSetAttribute(vote_kernel_shallow, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(sizeof(VoteSmem) + kPairSmemBytes))) != cudaSuccess)
+                                static_cast<int>(sizeof(VoteSmem) + kShallowSmemBytes))) != cudaSuccess)
     return fail(e, "cudaFuncSetAttribute(vote_kernel_shallow)");
   if ((e = cudaFuncSetAttribute(vote_kernel_deep, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(sizeof(VoteSmem) + kDeepSmemBytes))) != cudaSuccess)
@@ -340,6 +342,18 @@ fgb_status fgb_host_proof_tables(uint8_t pre, uint8_t post, int32_t* dfix, int32
   if (dfix) std::memcpy(dfix, t.dfix, sizeof(t.dfix));
   if (g2fix) *g2fix = t.g2fix;
   if (nmax2) *nmax2 = t.nmax2;
+  return FGB_OK;
+}
+
+fgb_status fgb_host_unanimous_steps(uint8_t pre, uint8_t post, int32_t* gap_begin, uint8_t* quality,
+                                    uint32_t* n_steps, int32_t* guard) {
+  if (pre > FGB_MAX_PHRED || post > FGB_MAX_PHRED) return FGB_ERR_INVALID_ARG;
+  HostTables t;
+  build_host_tables(pre, post, &t);
+  if (gap_begin) std::memcpy(gap_begin, t.ugap_bp, sizeof(t.ugap_bp));
+  if (quality) std::memcpy(quality, t.ugap_q, sizeof(t.ugap_q));
+  if (n_steps) *n_steps = t.ugap_n;
+  if (guard) *guard = kUgapGuard;
   return FGB_OK;
 }
 

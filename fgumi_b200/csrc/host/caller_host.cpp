@@ -531,6 +531,17 @@ void pack_direct_unit(fgb_caller* c, const uint8_t* stage, const std::vector<Vie
     if (r.rx) P.rx.push_back(StrRef{static_cast<uint64_t>(r.rx - stage), r.rx_len});
   }
   u.rx_n = static_cast<uint32_t>(P.rx.size()) - u.rx_begin;
+  if (u.rx_n > 1) {
+    // The usual family: every RX value identical and free of lower-case bases.  Its consensus is the value itself
+    // (consensus_umis_refs' first case); deciding that HERE, while the tag bytes of the group's records are in cache,
+    // leaves the flush one reference to follow instead of rx_n cold ones.
+    const StrRef* rf = P.rx.data() + u.rx_begin;
+    const uint8_t* f = stage + rf[0].off;
+    bool same = true;
+    for (uint32_t k = 1; k < u.rx_n && same; ++k) same = rf[k].len == rf[0].len && std::memcmp(stage + rf[k].off, f, rf[0].len) == 0;
+    for (uint32_t i = 0; i < rf[0].len && same; ++i) { const uint8_t ch = f[i]; same = !(ch == 'a' || ch == 'c' || ch == 'g' || ch == 't' || ch == 'n'); }
+    if (same) { P.rx.resize(u.rx_begin + 1u); u.rx_n = 1; }
+  }
   const size_t kth = c->opt.min_reads - 1;                      // vanilla_caller.rs:1269-1277
   std::nth_element(lens.begin(), lens.begin() + kth, lens.end(), std::greater<uint32_t>());
   u.cons_len = lens[kth];

@@ -153,6 +153,45 @@ void build_host_tables(unsigned pre, unsigned post, HostTables* t) {
     }
   }
 
+  // Quality of a unanimous pileup as a step function of its likelihood gap (HostTables::ugap_*).  The tail is the
+  // reference's (base_builder.rs:401-457 then phred.rs:119-135) on ll = {0, -g, -g, -g}: only differences of the
+  // four sums enter it, and a unanimous pileup has one gap.  quality(g) is non-decreasing in g, so each step's start
+  // is found by bisection over the integer gaps.  What the table cannot know is absorbed by kUgapGuard on the device
+  // side: the reference evaluates the same tail on Kahan sums that carry a few ulp(|ll|) of absolute noise on
+  // s = 3 e^-g -- relative noise 8 * 2^-53 * 32 n / s, at most 4e-4 nat (25 units) for n <= 4 at g = 23 -- the host
+  // evaluation here has the same kind of noise, and the fixed-point gap is within 2 n + 1 units of the real one
+  // (added separately by the kernel).  160 units = 2.4e-3 nat = 0.011 phred on either side of every step.
+  {
+    auto quality_at = [&](int32_t units) -> unsigned {
+      const double g = static_cast<double>(units) / 65536.0;
+      const double ll[4] = {0.0, -g, -g, -g};
+      const double ln_sum = ln_add_array4(ll);
+      const double err = ln_1m_exp(0.0 - ln_sum);
+      return host_ln_prob_to_phred(two_trials(t->ln_pre, err));
+    };
+    for (int k = 0; k < 128; ++k) { t->ugap_bp[k] = INT32_MAX; t->ugap_q[k] = 0; }
+    t->ugap_n = 0;
+    const int32_t g_lo = 64, g_hi = 23 * 65536 + 4096;
+    unsigned q_cur = quality_at(g_lo);
+    int32_t start = g_lo;
+    uint32_t n = 0;
+    bool ok = finite_ok;
+    while (ok && n < 127) {
+      t->ugap_bp[n] = start; t->ugap_q[n] = static_cast<uint8_t>(q_cur); ++n;
+      if (quality_at(g_hi) <= q_cur) break;              // no further step below the fast-path gap
+      int32_t lo = start, hi = g_hi;                     // quality(lo) == q_cur < quality(hi)
+      while (hi - lo > 1) {
+        const int32_t mid = lo + (hi - lo) / 2;
+        if (quality_at(mid) > q_cur) hi = mid; else lo = mid;
+      }
+      const unsigned q_next = quality_at(hi);
+      if (q_next <= q_cur) { ok = false; break; }       // not monotone: leave the table empty
+      start = hi; q_cur = q_next;
+    }
+    if (!ok || n >= 127) { n = 0; for (int k = 0; k < 128; ++k) t->ugap_bp[k] = INT32_MAX; }
+    t->ugap_n = n;
+  }
+
   // Sum-of-qualities thresholds (vote_kernel_w.cuh): f[k][s] = the smallest sum of D over k qualities in
   // 1..63 that add up to s, by dynamic programming; sumt[n] = the smallest t such that EVERY such multiset
   // with sum >= t clears the same threshold the per-read minimum test uses.  Exact over the table values;

@@ -28,7 +28,17 @@ struct HostTables {
   // from the rest, every quality >= qt3[n], has a likelihood gap >= (n - K) * dmono[qt3] - K * Dmax >= G2, so the
   // dominant-winner proof applies without looking at the dissenters' qualities; 255 = never.
   uint8_t qt3[256];
+  // Unanimous pileups below the fast-path gap: the called quality is a monotone step function of the likelihood gap
+  // g = sum D[q_i] alone (the three other bases share one sum).  ugap_bp[k] = the smallest fixed-point gap (units of
+  // 2^-16 nat) at which the reference's call() tail -- evaluated on the host in f64 for ll = {0, -g, -g, -g} --
+  // reaches ugap_q[k]; the quality of a gap in [ugap_bp[k], ugap_bp[k+1]) is ugap_q[k].  Unused entries hold
+  // INT32_MAX.  The kernel accepts a table answer only when the gap's whole uncertainty interval, widened by
+  // kUgapGuard units, lies inside one step (vote_kernel.cuh cert_unanimous).
+  int32_t ugap_bp[128];
+  uint8_t ugap_q[128];
+  uint32_t ugap_n;
 };
+constexpr int32_t kUgapGuard = 160;      // units of 2^-16 nat: see host_tables.cpp
 constexpr unsigned kNearK = 3;
 
 void build_host_tables(unsigned pre, unsigned post, HostTables* t);

@@ -32,6 +32,7 @@
 #include "../../include/fgumi_b200.h"
 #include "device_math.cuh"
 #include "fgb_config.h"
+#include "host_tables.h"
 #include "swar.cuh"
 
 namespace fgb {
@@ -48,6 +49,8 @@ struct DeviceTables {
   uint8_t pair_q[94 * 94];      // unanimous two-read pileups: quality by (q1, q2); 255 = literal path
   uint16_t sumt[8];             // sum-of-qualities thresholds by depth (host_tables.cpp), 0xFFFF = none
   uint8_t qt3[kQtEntries];      // near-unanimous quality threshold by depth (deep kernel); 255 = never
+  int32_t ugap_bp[128];         // unanimous pileups: quality steps by fixed-point gap (host_tables.h ugap_*)
+  uint8_t ugap_q[128];
 };
 
 struct VoteArgs {
@@ -96,6 +99,8 @@ struct __align__(128) VoteSmem {
 };
 
 constexpr uint32_t kPairSmemBytes = 94u * 94u;                 // 8836 = 4 * 2209
+constexpr uint32_t kUgapSmemOff = (kPairSmemBytes + 15u) & ~15u;   // the unanimous-gap steps follow the pair table
+constexpr uint32_t kShallowSmemBytes = kUgapSmemOff + 128u * 4u + 128u;
 static_assert(kPairSmemBytes % 4u == 0, "pair table is copied as words");
 static_assert(sizeof(VoteSmem) % 16u == 0, "the pair table follows VoteSmem in dynamic shared memory");
 
@@ -470,6 +475,23 @@ __device__ __forceinline__ void write_called(const VoteArgs& a, uint64_t o, cons
 // Enabled in the shallow-class kernel only: the call keeps registers live across it, which costs the general
 // kernel's item loop a quarter of its speed (measured), and shallow pileups are where the dominant-winner
 // proof fails most.
+// Quality of a UNANIMOUS pileup from its fixed-point gap through the host-built step table (host_tables.h ugap_*;
+// shallow kernel only: the table sits in dynamic shared memory behind the pair table).  `g` is within 2 * depth + 1
+// units of the exact gap; the answer stands only if that interval, widened by kUgapGuard, lies inside one step.
+__device__ __forceinline__ bool cert_unanimous(const VoteSmem& S, int32_t g, uint32_t depth, uint32_t* q) {
+  const int32_t* bp = reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(&S) + sizeof(VoteSmem) + kUgapSmemOff);
+  const uint8_t* qv = reinterpret_cast<const uint8_t*>(bp + 128);
+  const int32_t e = static_cast<int32_t>(2u * depth + 1u) + kUgapGuard;
+  const int32_t glo = g - e, ghi = g + e;
+  uint32_t k = 0;
+#pragma unroll
+  for (uint32_t step = 64u; step > 0u; step >>= 1)
+    if (bp[k + step] <= glo) k += step;                 // largest k with bp[k] <= glo (entries past the table: INT32_MAX)
+  if (bp[k] > glo || bp[k + 1] <= ghi) return false;    // below the first step, or the interval reaches the next one
+  *q = qv[k];
+  return true;
+}
+
 template <class M, bool Cert = false>
 __device__ __forceinline__ bool dominant_position(const TileView<M>& tv, const VoteSmem& S,
                                                   uint32_t read_begin, uint32_t n_reads,
@@ -519,8 +541,20 @@ __device__ __forceinline__ bool dominant_position(const TileView<M>& tv, const V
   uint32_t q = fast_qual;
   if (static_cast<int64_t>(best) - second < static_cast<int64_t>(S.g2fix) + 2 * static_cast<int64_t>(depth) + 1) {
     if (!Cert) return false;
-    const int32_t oa = w == 0 ? s1 : s0, ob = w <= 1 ? s2 : s1, oc = w == 3 ? s2 : s3;   // the three other sums
-    if (!certified_from_fixed(best, oa, ob, oc, depth, depth == cw, S.ln_pre, fast_qual, &q)) return false;
+    bool have = false;
+    if (depth == cw && depth <= 4u) {
+      // unanimous (the three other sums are 0, every gap = best): the step table instead of the float evaluation --
+      // the unanimous low-quality cycles at the start of every shallow family come through here
+      const int32_t e = static_cast<int32_t>(2u * depth + 1u), t23 = 23 * 65536;
+      if (best > e + 64) {
+        if (best - e > t23) { q = fast_qual; have = true; }                   // base_builder.rs:338-379
+        else if (best + e < t23) have = cert_unanimous(S, best, depth, &q);
+      }
+    }
+    if (!have) {
+      const int32_t oa = w == 0 ? s1 : s0, ob = w <= 1 ? s2 : s1, oc = w == 3 ? s2 : s3;   // the three other sums
+      if (!certified_from_fixed(best, oa, ob, oc, depth, depth == cw, S.ln_pre, fast_qual, &q)) return false;
+    }
   }
   out.depth = depth;
   out.errors = depth - cw;
@@ -888,26 +922,31 @@ __device__ __forceinline__ void vote_tile(const VoteArgs& a, VoteSmem& S, const 
       const uint32_t e_hi = zero_bytes(static_cast<uint32_t>(b0w >> 32) ^ static_cast<uint32_t>(b1w >> 32)) &
                             acgt_bytes(static_cast<uint32_t>(b0w >> 32)) &
                             low_bytes_mask(covered > 4u ? covered - 4u : 0u) & rm_hi;
-      uint64_t obw = 0, oqw = 0;
-      uint32_t ok_lo = 0, ok_hi = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (((j < 4 ? e_lo >> (8 * j) : e_hi >> (8 * (j - 4))) >> 7) & 1u) {
-          uint32_t qa = static_cast<uint32_t>(q0w >> (8 * j)) & 0xFFu, qb = static_cast<uint32_t>(q1w >> (8 * j)) & 0xFFu;
-          qa = qa > FGB_MAX_PHRED ? FGB_MAX_PHRED : qa;
-          qb = qb > FGB_MAX_PHRED ? FGB_MAX_PHRED : qb;
-          const uint32_t cq = pair_sm[qa * 94u + qb];      // shared-memory copy (kernel prologue): eight gathers per item
-          if (cq != 255u) {
-            const bool masked = cq < min_cons_q;                               // vanilla_caller.rs:1347-1348
-            obw |= static_cast<uint64_t>(masked ? 'N' : (static_cast<uint32_t>(b0w >> (8 * j)) & 0xFFu)) << (8 * j);
-            oqw |= static_cast<uint64_t>(masked ? 2u : cq) << (8 * j);
-            ls.nocall += masked;
-            if (j < 4) ok_lo |= 0x80u << (8 * j); else ok_hi |= 0x80u << (8 * (j - 4));
-          }
-        }
+      // byte-parallel: eight table lookups (indices are in range whatever the flags say: qualities are clamped),
+      // then the thresholds of vanilla_caller.rs:1345-1349 on the assembled words
+      const uint32_t qa_lo = __vminu4(static_cast<uint32_t>(q0w), FGB_MAX_PHRED * 0x01010101u);
+      const uint32_t qa_hi = __vminu4(static_cast<uint32_t>(q0w >> 32), FGB_MAX_PHRED * 0x01010101u);
+      const uint32_t qb_lo = __vminu4(static_cast<uint32_t>(q1w), FGB_MAX_PHRED * 0x01010101u);
+      const uint32_t qb_hi = __vminu4(static_cast<uint32_t>(q1w >> 32), FGB_MAX_PHRED * 0x01010101u);
+      auto look4 = [&](uint32_t qa4, uint32_t qb4) {
+        const uint32_t c0 = pair_sm[(qa4 & 0xFFu) * 94u + (qb4 & 0xFFu)];
+        const uint32_t c1 = pair_sm[((qa4 >> 8) & 0xFFu) * 94u + ((qb4 >> 8) & 0xFFu)];
+        const uint32_t c2 = pair_sm[((qa4 >> 16) & 0xFFu) * 94u + ((qb4 >> 16) & 0xFFu)];
+        const uint32_t c3 = pair_sm[(qa4 >> 24) * 94u + (qb4 >> 24)];
+        return c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+      };
+      const uint32_t cq_lo = look4(qa_lo, qb_lo), cq_hi = look4(qa_hi, qb_hi);
+      const uint32_t mq = min_cons_q > 255u ? 255u : min_cons_q;
+      const uint32_t ok_lo = e_lo & ~zero_bytes(~cq_lo), ok_hi = e_hi & ~zero_bytes(~cq_hi);    // 255 = literal path
+      const uint32_t mk_lo = ok_lo & ~bytes_ge(cq_lo, mq), mk_hi = ok_hi & ~bytes_ge(cq_hi, mq);   // below min_cons_q: (N, 2)
+      {
+        const uint32_t vb_lo = spread_msb(ok_lo), vb_hi = spread_msb(ok_hi), mb_lo = spread_msb(mk_lo), mb_hi = spread_msb(mk_hi);
+        wb_lo = ((static_cast<uint32_t>(b0w) & ~mb_lo) | (0x4E4E4E4Eu & mb_lo)) & vb_lo;
+        wb_hi = ((static_cast<uint32_t>(b0w >> 32) & ~mb_hi) | (0x4E4E4E4Eu & mb_hi)) & vb_hi;
+        wq_lo = ((cq_lo & ~mb_lo) | (0x02020202u & mb_lo)) & vb_lo;
+        wq_hi = ((cq_hi & ~mb_hi) | (0x02020202u & mb_hi)) & vb_hi;
+        ls.nocall += __popc(mk_lo) + __popc(mk_hi);
       }
-      wb_lo = static_cast<uint32_t>(obw); wb_hi = static_cast<uint32_t>(obw >> 32);
-      wq_lo = static_cast<uint32_t>(oqw); wq_hi = static_cast<uint32_t>(oqw >> 32);
       const uint32_t kb_lo = spread_msb(ok_lo), kb_hi = spread_msb(ok_hi);
       dep.x = 0x00020002u & __byte_perm(kb_lo, 0u, 0x1100u);
       dep.y = 0x00020002u & __byte_perm(kb_lo, 0u, 0x3322u);
@@ -1541,10 +1580,22 @@ __device__ __forceinline__ void vote_tile_deep_flat(const VoteArgs& a, VoteSmem&
   if (lane == 0) *wcount = 0;
 }
 
+// Rounds of tiles pulled into L2 ahead of the stage pipeline, per kernel (0 = off).  Measured (profiles/
+// r02_prefetch_ab.log): the general kernel gains 3 % at distance 1 (depth 8: 5.67 -> 5.51 ms for 10 M families) and
+// loses at 2 and 4 (6.03 / 7.9 ms: the prefetched lines are evicted or compete with the demand stream); the shallow
+// kernel (output-heavy) loses at any distance; the deep kernel does not care (it is not bound by load latency).
 #ifndef FGB_PREFETCH_AHEAD
-#define FGB_PREFETCH_AHEAD 2
+#define FGB_PREFETCH_AHEAD 1
 #endif
-constexpr uint32_t kPrefetchAhead = FGB_PREFETCH_AHEAD;   // rounds of tiles pulled into L2 ahead of the stage pipeline (0 = off)
+#ifndef FGB_PREFETCH_AHEAD_SHALLOW
+#define FGB_PREFETCH_AHEAD_SHALLOW 0
+#endif
+#ifndef FGB_PREFETCH_AHEAD_DEEP
+#define FGB_PREFETCH_AHEAD_DEEP 0
+#endif
+#ifndef FGB_DEEP_FLAT_MIN
+#define FGB_DEEP_FLAT_MIN 64      // the flat deep form takes single-unit tiles of at least this many reads
+#endif
 
 template <int V>
 __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
@@ -1565,6 +1616,11 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
     uint32_t* dst = reinterpret_cast<uint32_t*>(smem_raw + sizeof(VoteSmem));
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.tables->pair_q);
     for (uint32_t i = tid; i < kPairSmemBytes / 4u; i += kThreads) dst[i] = __ldg(src + i);
+    int32_t* ub = reinterpret_cast<int32_t*>(smem_raw + sizeof(VoteSmem) + kUgapSmemOff);
+    for (uint32_t i = tid; i < 128u; i += kThreads) {
+      ub[i] = a.tables->ugap_bp[i];
+      reinterpret_cast<uint8_t*>(ub + 128)[i] = a.tables->ugap_q[i];
+    }
   }
   if (V == 2) {                                             // the deep kernel's reduction slots: identities
     DeepSlots* R2 = reinterpret_cast<DeepSlots*>(smem_raw + sizeof(VoteSmem));
@@ -1599,6 +1655,7 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
       for (uint32_t t = blockIdx.x; t < n_tiles; t += grid, ++k) {
         const int s = k % kStages;
         const uint32_t use = k / kStages;
+        constexpr uint32_t kPrefetchAhead = V == 0 ? FGB_PREFETCH_AHEAD : (V == 1 ? FGB_PREFETCH_AHEAD_SHALLOW : FGB_PREFETCH_AHEAD_DEEP);
         if (kPrefetchAhead) {
           // The two stages bound the bytes this CTA has in flight to one tile while the other is voted; with small or
           // quickly voted tiles (deep and shallow classes) that is less than the bandwidth-delay product.  So the
@@ -1678,7 +1735,9 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
       tv.reads = reinterpret_cast<const uint8_t*>(st.reads) + (st.tile.read_begin & 1u) * 8u;
       tv.byte_base = st.tile.byte_begin; tv.read_base = st.tile.read_begin;
       if (V == 2) {
-        if (n_items <= kDeepItemsMax) {          // (n_items is the same for every warp: the branch is CTA-uniform)
+        // The flat form pays one CTA-wide barrier per tile: it wins only where a tile is one very deep unit (depth 100:
+        // 0.49 -> 0.52 of the roofline; at depth 24-50 the lane-group form is 5-20 % faster, profiles/r02_depth_sweep_flat_deep.log)
+        if (n_items <= kDeepItemsMax && st.tile.n_units == 1u && st.tile.n_reads >= FGB_DEEP_FLAT_MIN) {   // CTA-uniform
           DeepSlots& R = reinterpret_cast<DeepSlots*>(smem_raw + sizeof(VoteSmem))[k & 1u];
           if (st.tile.flags & kTileFlagRegular) vote_tile_deep_flat<true>(a, S, R, st, tv, tid, warp, n_items, ls);
           else vote_tile_deep_flat<false>(a, S, R, st, tv, tid, warp, n_items, ls);

@@ -204,7 +204,7 @@ class FgbCodecOut(C.Structure):
 # Every symbol include/fgumi_b200.h declares; tests check the .so exports all of them.
 SYMBOLS = (
     "fgb_abi_version", "fgb_create", "fgb_destroy", "fgb_strerror", "fgb_last_error",
-    "fgb_get_tables", "fgb_host_tables", "fgb_host_proof_tables", "fgb_tile_capacity_bytes", "fgb_tile_max_units", "fgb_tile_max_reads",
+    "fgb_get_tables", "fgb_host_tables", "fgb_host_proof_tables", "fgb_host_unanimous_steps", "fgb_tile_capacity_bytes", "fgb_tile_max_units", "fgb_tile_max_reads",
     "fgb_plan_tiles", "fgb_sort_tiles_by_class", "fgb_vote_device", "fgb_submit", "fgb_wait", "fgb_host_alloc",
     "fgb_host_free", "fgb_host_is_pinned", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count", "fgb_engine_caps",
@@ -256,6 +256,8 @@ def load() -> C.CDLL:
     lib.fgb_host_tables.restype = C.c_int32
     lib.fgb_host_proof_tables.argtypes = [C.c_uint8, C.c_uint8, vp, vp, vp]
     lib.fgb_host_proof_tables.restype = C.c_int32
+    lib.fgb_host_unanimous_steps.argtypes = [C.c_uint8, C.c_uint8, vp, vp, vp, vp]
+    lib.fgb_host_unanimous_steps.restype = C.c_int32
     for f in ("fgb_tile_capacity_bytes", "fgb_tile_max_units", "fgb_tile_max_reads"):
         getattr(lib, f).restype = u32
         getattr(lib, f).argtypes = []

@@ -176,6 +176,15 @@ fgb_status fgb_host_tables(uint8_t error_rate_pre_umi, uint8_t error_rate_post_u
 fgb_status fgb_host_proof_tables(uint8_t error_rate_pre_umi, uint8_t error_rate_post_umi,
                                  int32_t* dfix, int32_t* g2fix, uint32_t* nmax2);
 
+/* Pure host function: the step table the shallow vote kernel uses for UNANIMOUS pileups whose likelihood gap is below
+ * the reference's fast path (base_builder.rs:338-379): the called quality as a function of the fixed-point gap
+ * g = sum round((correct[q]-err_alt[q])*65536).  gap_begin[128] ascending (unused entries INT32_MAX), quality[128]:
+ * a gap in [gap_begin[k], gap_begin[k+1]) calls quality[k].  The kernel accepts the answer only when the interval
+ * g +- (2 * depth + 1 + *guard) lies inside one step; anything else is evaluated literally.  Exposed so the table can
+ * be tested against the oracle on the CPU. */
+fgb_status fgb_host_unanimous_steps(uint8_t error_rate_pre_umi, uint8_t error_rate_post_umi,
+                                    int32_t* gap_begin, uint8_t* quality, uint32_t* n_steps, int32_t* guard);
+
 /* ---- batch planning (pure host code, no device needed) -------------------------------- */
 /* Bytes of one column that a tile may span. */
 uint32_t fgb_tile_capacity_bytes(void);

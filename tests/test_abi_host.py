@@ -121,6 +121,41 @@ def test_dominant_winner_proof_against_oracle(fg, pre, post):
         assert fired > 200
 
 
+@pytest.mark.parametrize("pre,post", [(45, 40), (30, 30), (93, 93), (20, 45), (60, 10), (45, 93)])
+def test_unanimous_step_table_against_oracle(fg, pre, post):
+    """The step table of the shallow kernel (quality of a unanimous pileup by its fixed-point likelihood gap): wherever
+    the kernel's acceptance rule lets the table answer, the oracle's literal add / call sequence gives that quality."""
+    lib = fg.lib.load()
+    bp = np.zeros(128, np.int32); qv = np.zeros(128, np.uint8)
+    n, guard = C.c_uint32(), C.c_int32()
+    assert lib.fgb_host_unanimous_steps(pre, post, bp.ctypes.data, qv.ctypes.data, C.addressof(n), C.addressof(guard)) == 0
+    n, guard = n.value, guard.value
+    assert 0 < n < 127 and guard >= 64
+    assert np.all(np.diff(bp[:n].astype(np.int64)) > 0) and np.all(np.diff(qv[:n].astype(np.int64)) > 0)
+    assert np.all(bp[n:] == np.iinfo(np.int32).max)
+    dfix, g2fix, nmax2 = _proof(fg, pre, post)
+    rng = np.random.default_rng(1000 * pre + post)
+    answered = 0
+    trials = 0
+    for depth in (1, 2, 3, 4):
+        for _ in range(2500):
+            # low and middling qualities: the gaps the table exists for (below the fast path's 23 nats)
+            qs = rng.integers(1, 50, size=depth)
+            g = int(sum(int(dfix[q]) for q in qs))
+            e = 2 * depth + 1
+            if g <= e + 64 or g + e >= 23 * 65536:
+                continue
+            trials += depth > 1      # one observation of quality q sits right at the start of "its" step: those go literal
+            lo, hi = g - e - guard, g + e + guard
+            k = int(np.searchsorted(bp[:n], lo, side="right")) - 1
+            if k < 0 or bp[k + 1] <= hi:
+                continue                       # the kernel would evaluate this one literally
+            answered += depth > 1
+            b, q, obs, _ = O.builder_call(pre, post, b"G" * depth, [int(x) for x in qs])
+            assert (b, q) == ("G", int(qv[k])), (depth, qs, g, k, bp[k], bp[k + 1])
+    assert answered > 0.8 * trials > 0
+
+
 def test_create_without_gpu_fails_loudly(fg):
     import torch
     if torch.cuda.is_available():
