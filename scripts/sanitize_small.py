@@ -18,6 +18,21 @@ for i in range(1500):
         q[b == ord("N")] = 2
         rows.append((b.tobytes(), q.tobytes()))
     units.append(rows)
+def deep_unit(depth, L):
+    t = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=L)
+    rows = []
+    for _ in range(depth):
+        b = t.copy()
+        m = rng.random(L) < 0.01
+        b[m] = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=int(m.sum()))
+        q = rng.integers(20, 42, size=L).astype(np.uint8)
+        q[b == ord("N")] = 2
+        rows.append((b.tobytes(), q.tobytes()))
+    return rows
+for i in range(40):                                               # deep class: lane-group form (several units per tile) ...
+    units.append(deep_unit(int(rng.integers(24, 60)), int(rng.integers(30, 60))))
+for i in range(12):                                               # ... and the flat form (one unit of >= 64 reads per tile)
+    units.append(deep_unit(int(rng.integers(70, 120)), 150))
 units.append([(b"ACGT" * 6000, bytes([30] * 24000))] * 3)        # oversize unit: direct path
 batch = fg.pack_source_reads(units, 1)
 eng = fg.Engine(0, 45, 40, 1, 2)
@@ -34,6 +49,9 @@ from tests.test_caller_parity import random_groups, random_duplex_groups, random
 c = fg.VanillaUmiConsensusCaller("f", "A", fg.VanillaUmiConsensusOptions(min_reads=1, min_consensus_base_quality=2),
                                  filter=fg.ConsensusFilter(min_reads=2, max_read_error_rate=0.1, max_base_error_rate=0.2, min_base_quality=10),
                                  consensus_call_overlapping_bases=True, n_threads=3)
+c.add_groups(random_groups(rng, 60)); c.flush(); c.close()
+c = fg.VanillaUmiConsensusCaller("f", "A", fg.VanillaUmiConsensusOptions(min_reads=1, min_consensus_base_quality=2),
+                                 consensus_call_overlapping_bases=True, n_threads=3)          # no filter: records assembled on the device (K5)
 c.add_groups(random_groups(rng, 60)); c.flush(); c.close()
 c = fg.DuplexConsensusCaller("f", "A", min_reads=(1, 1, 0)); c.consensus_reads_batch(random_duplex_groups(rng, 60)); c.close()
 c = fg.CodecConsensusCaller("c", "R"); c.consensus_reads_batch(random_codec_groups(rng, 60)); c.close()
