@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "../../include/fgumi_b200.h"
+#include "duplex_word.cuh"
 
 namespace fgb {
 
@@ -325,6 +326,8 @@ struct DuplexJobSm {
   unsigned long long out_off, a_off, b_off;
   uint32_t len, ra0, na, rb0, nb;
   uint32_t general;       // 1: duplex_job_warp does the whole job
+  uint32_t done;          // 1: combined in the vote's epilogue already (duplex_combine_pending_kernel)
+  uint32_t pad_;
 };
 
 __device__ __forceinline__ uint32_t chunk_job_of(const uint32_t* pref, uint32_t it) {
@@ -335,27 +338,35 @@ __device__ __forceinline__ uint32_t chunk_job_of(const uint32_t* pref, uint32_t 
   return jl;
 }
 
-__global__ void __launch_bounds__(kCombineThreads, 4) duplex_combine_words_kernel(const DuplexArgs a) {
-  __shared__ DuplexJobSm sj[kDuplexChunk];
-  __shared__ uint32_t s_pref[kDuplexChunk + 1];
-  __shared__ uint32_t s_any[kDuplexChunk];
+// `skip_done`: jobs whose status byte is not FGB_DUPLEX_PENDING were combined in the vote kernels' epilogue
+// (vote_kernel.cuh duplex_epilogue) and are left alone; a chunk without pending jobs costs one byte load per job.
+template <bool SkipDone>
+__device__ __forceinline__ void duplex_combine_words_chunk(const DuplexArgs& a, const uint64_t j0, DuplexJobSm* sj,
+                                                           uint32_t* s_pref, uint32_t* s_any) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
-  const uint64_t j0 = static_cast<uint64_t>(blockIdx.x) * kDuplexChunk;
   const uint32_t nj = static_cast<uint32_t>(a.n_jobs - j0 < kDuplexChunk ? a.n_jobs - j0 : kDuplexChunk);
   if (tid < 32u) {
     uint32_t items = 0;
+    bool is_new = false;
     if (tid < nj) {
-      const DuplexJobRegs r = load_duplex_job(a, j0 + tid);
       DuplexJobSm s;
-      s.out_off = r.job.out_off; s.a_off = r.ua.out_off; s.b_off = r.ub.out_off;
-      s.len = r.ua.cons_len < r.ub.cons_len ? r.ua.cons_len : r.ub.cons_len;       // duplex_caller.rs:846-849
-      s.ra0 = r.ua.read_begin; s.na = r.ra1 - r.ua.read_begin;
-      s.rb0 = r.ub.read_begin; s.nb = r.rb1 - r.ub.read_begin;
-      s.general = (((r.job.out_off | r.ua.out_off | r.ub.out_off) & 7ull) != 0ull ||
-                   static_cast<unsigned long long>(s.na) + s.nb > 255ull) ? 1u : 0u;
+      s.general = 0u;
+      s.done = (SkipDone && a.out_status[j0 + tid] != FGB_DUPLEX_PENDING) ? 1u : 0u;
+      if (!s.done) {
+        const DuplexJobRegs r = load_duplex_job(a, j0 + tid);
+        s.out_off = r.job.out_off; s.a_off = r.ua.out_off; s.b_off = r.ub.out_off;
+        s.len = r.ua.cons_len < r.ub.cons_len ? r.ua.cons_len : r.ub.cons_len;       // duplex_caller.rs:846-849
+        s.ra0 = r.ua.read_begin; s.na = r.ra1 - r.ua.read_begin;
+        s.rb0 = r.ub.read_begin; s.nb = r.rb1 - r.ub.read_begin;
+        s.general = (((r.job.out_off | r.ua.out_off | r.ub.out_off) & 7ull) != 0ull ||
+                     static_cast<unsigned long long>(s.na) + s.nb > 255ull) ? 1u : 0u;
+        items = s.general ? 0u : (s.len + 7u) >> 3;
+      } else {
+        s.out_off = s.a_off = s.b_off = 0ull; s.len = s.ra0 = s.na = s.rb0 = s.nb = 0u;
+      }
       sj[tid] = s;
-      items = s.general ? 0u : (s.len + 7u) >> 3;
       s_any[tid] = 0u;
+      is_new = !s.done;
     }
     uint32_t incl = items;
 #pragma unroll
@@ -364,32 +375,41 @@ __global__ void __launch_bounds__(kCombineThreads, 4) duplex_combine_words_kerne
       if (lane >= static_cast<uint32_t>(off)) incl += v;
     }
     s_pref[tid + 1] = incl;
-    if (tid == 0) s_pref[0] = 0u;
+    const uint32_t n_new = __popc(__ballot_sync(0xFFFFFFFFu, is_new));
+    if (tid == 0) {
+      s_pref[0] = 0u;
+      if (n_new) atomicAdd(a.counters + FGB_CTR_COMBINED, static_cast<unsigned long long>(n_new));
+    }
   }
   __syncthreads();
   const uint32_t total = s_pref[kDuplexChunk];
   // ---- pass 1: which strands have coverage inside the truncated region (:852-853) ----
-  for (uint32_t it = tid; it < total; it += kCombineThreads) {
-    const uint32_t jl = chunk_job_of(s_pref, it);
-    const uint32_t p0 = (it - s_pref[jl]) * 8u;
-    const uint32_t len = sj[jl].len;
-    const uint32_t live = len - p0 < 8u ? len - p0 : 8u;
-    const uint4 ad4 = __ldg(reinterpret_cast<const uint4*>(a.ss_depth + sj[jl].a_off + p0));
-    const uint4 bd4 = __ldg(reinterpret_cast<const uint4*>(a.ss_depth + sj[jl].b_off + p0));
-    auto any16 = [&](const uint4& d) {           // a longer strand has real depths behind `len`: mask the last word
-      const uint32_t w[4] = {d.x, d.y, d.z, d.w};
-      uint32_t acc = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t keep = live >= 2u * k + 2u ? 0xFFFFFFFFu : (live == 2u * k + 1u ? 0x0000FFFFu : 0u);
-        acc |= w[k] & keep;
-      }
-      return acc != 0u;
-    };
-    const uint32_t f = (any16(ad4) ? 1u : 0u) | (any16(bd4) ? 2u : 0u);
-    if (f & ~s_any[jl]) atomicOr(&s_any[jl], f);
+  // A strand almost always has depth in its first word: item 0 of every job settles the arm then, and the other
+  // depth words are read only for the jobs it leaves open (600 of a 150-base job's 3 016 bytes otherwise).
+  bool open_jobs = false;
+  if (tid < nj && !sj[tid].general && !sj[tid].done && sj[tid].len > 0u) {
+    const uint32_t len = sj[tid].len;
+    const uint32_t live = len < 8u ? len : 8u;
+    const uint4 ad4 = __ldg(reinterpret_cast<const uint4*>(a.ss_depth + sj[tid].a_off));
+    const uint4 bd4 = __ldg(reinterpret_cast<const uint4*>(a.ss_depth + sj[tid].b_off));
+    const uint32_t f = (duplex_any_depth(ad4, live) ? 1u : 0u) | (duplex_any_depth(bd4, live) ? 2u : 0u);
+    s_any[tid] = f;
+    open_jobs = f != 3u && len > 8u;
   }
-  __syncthreads();
+  if (__syncthreads_or(open_jobs ? 1 : 0)) {
+    for (uint32_t it = tid; it < total; it += kCombineThreads) {
+      const uint32_t jl = chunk_job_of(s_pref, it);
+      const uint32_t p0 = (it - s_pref[jl]) * 8u;
+      if (p0 == 0u || s_any[jl] == 3u) continue;
+      const uint32_t len = sj[jl].len;
+      const uint32_t live = len - p0 < 8u ? len - p0 : 8u;
+      const uint4 ad4 = __ldg(reinterpret_cast<const uint4*>(a.ss_depth + sj[jl].a_off + p0));
+      const uint4 bd4 = __ldg(reinterpret_cast<const uint4*>(a.ss_depth + sj[jl].b_off + p0));
+      const uint32_t f = (duplex_any_depth(ad4, live) ? 1u : 0u) | (duplex_any_depth(bd4, live) ? 2u : 0u);
+      if (f & ~s_any[jl]) atomicOr(&s_any[jl], f);
+    }
+    __syncthreads();
+  }
   // ---- pass 2: the both-strand jobs ----
   for (uint32_t it = tid; it < total; it += kCombineThreads) {
     const uint32_t jl = chunk_job_of(s_pref, it);
@@ -400,22 +420,8 @@ __global__ void __launch_bounds__(kCombineThreads, 4) duplex_combine_words_kerne
     const uint2 bb2 = __ldg(reinterpret_cast<const uint2*>(a.ss_base + s.b_off + p0));
     const uint2 aq2 = __ldg(reinterpret_cast<const uint2*>(a.ss_qual + s.a_off + p0));
     const uint2 bq2 = __ldg(reinterpret_cast<const uint2*>(a.ss_qual + s.b_off + p0));
-    uint32_t ob[2], oq[2], rawb[2], cnt[2] = {0u, 0u};
-    const uint32_t abw[2] = {ab2.x, ab2.y}, bbw[2] = {bb2.x, bb2.y};
-    const uint32_t aqw[2] = {aq2.x, aq2.y}, bqw[2] = {bq2.x, bq2.y};
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t eq = __vcmpeq4(abw[h], bbw[h]);                    // :912-927, bytewise
-      const uint32_t sum = __vminu4(__vaddus4(aqw[h], bqw[h]), 0x5D5D5D5Du);
-      const uint32_t dif = __vminu4(__vabsdiffu4(aqw[h], bqw[h]), 0x5D5D5D5Du);
-      const uint32_t rq = __vmaxu4((eq & sum) | (~eq & dif), 0x02020202u);   // cap_quality; equal-quality dissent -> 2
-      const uint32_t b_wins = ~eq & __vcmpgtu4(bqw[h], aqw[h]);
-      rawb[h] = (bbw[h] & b_wins) | (abw[h] & ~b_wins);
-      const uint32_t mask = __vcmpeq4(abw[h], 0x4E4E4E4Eu) | __vcmpeq4(bbw[h], 0x4E4E4E4Eu) |
-                            __vcmpeq4(rq, 0x02020202u);                 // :930-935
-      ob[h] = (0x4E4E4E4Eu & mask) | (rawb[h] & ~mask);
-      oq[h] = (0x02020202u & mask) | (rq & ~mask);
-    }
+    const DuplexWord w = duplex_combine_word(ab2, bb2, aq2, bq2);
+    uint32_t cnt[2] = {0u, 0u};
     // :943-951 exact error recount against the pooled source reads (AB rows then BA rows), four rows in flight
     const uint32_t nr = s.na + s.nb;
     for (uint32_t r0 = 0; r0 < nr; r0 += 4u) {
@@ -434,35 +440,56 @@ __global__ void __launch_bounds__(kCombineThreads, 4) duplex_combine_words_kerne
 #pragma unroll
       for (uint32_t k = 0; k < 4u; ++k) {
         const uint32_t rl = static_cast<uint32_t>(d[k] & 0xFFFFu);
-        const uint32_t cov = rl > p0 ? rl - p0 : 0u;                    // covered positions of this word
-        const uint32_t c0 = cov >= 4u ? 0xFFFFFFFFu : ((1u << (8u * cov)) - 1u);
-        const uint32_t c1 = cov >= 8u ? 0xFFFFFFFFu : (cov > 4u ? ((1u << (8u * (cov - 4u))) - 1u) : 0u);
-        const uint32_t sw[2] = {sb[k].x, sb[k].y}, cw[2] = {c0, c1};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t ne = ~__vcmpeq4(sw[h], rawb[h]) & ~__vcmpeq4(sw[h], 0x4E4E4E4Eu) & cw[h];
-          cnt[h] += ne & 0x01010101u;
-        }
+        duplex_recount_row(sb[k], rl > p0 ? rl - p0 : 0u, w.rawb, cnt);     // covered positions of this word
       }
     }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) cnt[h] &= ~__vcmpeq4(rawb[h], 0x4E4E4E4Eu);   // raw base N: no recount
-    *reinterpret_cast<uint2*>(a.out_base + s.out_off + p0) = make_uint2(ob[0], ob[1]);
-    *reinterpret_cast<uint2*>(a.out_qual + s.out_off + p0) = make_uint2(oq[0], oq[1]);
-    *reinterpret_cast<uint4*>(a.out_errors + s.out_off + p0) =
-        make_uint4(__byte_perm(cnt[0], 0u, 0x4140u), __byte_perm(cnt[0], 0u, 0x4342u),
-                   __byte_perm(cnt[1], 0u, 0x4140u), __byte_perm(cnt[1], 0u, 0x4342u));
+    *reinterpret_cast<uint2*>(a.out_base + s.out_off + p0) = make_uint2(w.ob[0], w.ob[1]);
+    *reinterpret_cast<uint2*>(a.out_qual + s.out_off + p0) = make_uint2(w.oq[0], w.oq[1]);
+    *reinterpret_cast<uint4*>(a.out_errors + s.out_off + p0) = duplex_errors_word(w.rawb, cnt);
   }
   // ---- the rest: single-strand arms and general layouts, one warp per job ----
   for (uint32_t jl = tid >> 5; jl < nj; jl += kCombineThreads / 32) {
+    if (sj[jl].done) continue;
     const uint32_t f = s_any[jl];
     const bool general = sj[jl].general != 0u;
     uint8_t status = f == 3u ? FGB_DUPLEX_BOTH : FGB_DUPLEX_NONE;
     if (general || f == 1u || f == 2u) status = duplex_job_warp(a, load_duplex_job(a, j0 + jl), lane);
     if (lane == 0 && a.out_status) a.out_status[j0 + jl] = status;
   }
-  if (tid == 0) atomicAdd(a.counters + FGB_CTR_COMBINED, static_cast<unsigned long long>(nj));
 }
+
+__global__ void __launch_bounds__(kCombineThreads, 4) duplex_combine_words_kernel(const DuplexArgs a) {
+  __shared__ DuplexJobSm sj[kDuplexChunk];
+  __shared__ uint32_t s_pref[kDuplexChunk + 1];
+  __shared__ uint32_t s_any[kDuplexChunk];
+  duplex_combine_words_chunk<false>(a, static_cast<uint64_t>(blockIdx.x) * kDuplexChunk, sj, s_pref, s_any);
+}
+
+// After a vote with the duplex epilogue: a CTA looks at the status bytes of kCombineThreads jobs (eight chunks) and
+// runs the word kernel's body on the chunks that still have pending jobs.
+__global__ void __launch_bounds__(kCombineThreads, 4) duplex_combine_pending_kernel(const DuplexArgs a) {
+  __shared__ DuplexJobSm sj[kDuplexChunk];
+  __shared__ uint32_t s_pref[kDuplexChunk + 1];
+  __shared__ uint32_t s_any[kDuplexChunk];
+  __shared__ uint32_t s_pending[kCombineThreads / kDuplexChunk];
+  const uint64_t groups = (a.n_jobs + kCombineThreads - 1) / kCombineThreads;
+  for (uint64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+    const uint64_t jg = g * kCombineThreads;
+    const uint64_t j = jg + threadIdx.x;
+    const bool pending = j < a.n_jobs && a.out_status[j] == FGB_DUPLEX_PENDING;
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pending);
+    if ((threadIdx.x & 31u) == 0u) s_pending[threadIdx.x >> 5] = ballot;     // kDuplexChunk == 32: one word per chunk
+    __syncthreads();
+    for (uint32_t c = 0; c < kCombineThreads / kDuplexChunk; ++c) {
+      const uint64_t j0 = jg + static_cast<uint64_t>(c) * kDuplexChunk;
+      if (j0 >= a.n_jobs || s_pending[c] == 0u) continue;                    // CTA-uniform
+      duplex_combine_words_chunk<true>(a, j0, sj, s_pref, s_any);
+      __syncthreads();                                                       // sj / s_pref / s_any are reused
+    }
+    __syncthreads();                                                         // s_pending is rewritten next round
+  }
+}
+static_assert(kDuplexChunk == 32, "duplex_combine_pending_kernel keeps one ballot word per chunk");
 
 // ---- CODEC ------------------------------------------------------------------------------------
 struct CodecArgs {

@@ -31,6 +31,7 @@
 
 #include "../../include/fgumi_b200.h"
 #include "device_math.cuh"
+#include "duplex_word.cuh"
 #include "fgb_config.h"
 #include "host_tables.h"
 #include "swar.cuh"
@@ -69,6 +70,18 @@ struct VoteArgs {
   uint32_t min_reads;
   uint32_t min_cons_q;
   uint32_t fast_qual;   // ln_prob_to_phred(ln_pre), host-evaluated (base_builder.rs:370)
+};
+
+// The kernels with the duplex epilogue (vote_kernel*_duplex, fgb_vote_duplex_device) take these on top.  (A separate
+// struct: ptxas' register allocation of the plain kernels is sensitive to the parameter block.)
+struct VoteArgsDuplex : VoteArgs {
+  const fgb_tile_jobs* tile_jobs;     // per tile of this launch
+  const uint32_t* job_index;
+  const fgb_duplex_job* djobs;
+  uint8_t* d_base;
+  uint8_t* d_qual;
+  uint16_t* d_errors;
+  uint8_t* d_status;                  // preset to FGB_DUPLEX_PENDING; the epilogue writes FGB_DUPLEX_BOTH
 };
 
 struct __align__(16) Stage {
@@ -460,6 +473,73 @@ __device__ __noinline__ Called exact_position(const TileView<M>& tv, const VoteS
 struct LocalStats {
   uint32_t positions, exact, nocall;
 };
+
+// ---- duplex epilogue -----------------------------------------------------------------------------------------
+// Runs on the eight voting warps after a tile's vote (and a barrier among them): the tile's attached duplex jobs,
+// both of whose single-strand units this tile has just voted, are combined 8 positions per thread.  The SS words
+// come back through L2 (ld.global.cg: they were written by other threads of this CTA a moment ago), the source rows
+// for the exact error recount (duplex_caller.rs:943-951) are still in the stage.  Only the both-strand arm of a
+// word-path job is taken (every item of a job reaches the same verdict from job-level data); anything else keeps
+// its FGB_DUPLEX_PENDING status byte and is done by duplex_combine_pending_kernel after the vote.
+__device__ __forceinline__ uint32_t duplex_epilogue(const VoteArgsDuplex& a, const Stage& st, const uint8_t* st_bases,
+                                                    const uint8_t* st_reads, const uint32_t base32,
+                                                    const uint32_t read_base, const uint32_t jbegin,
+                                                    const uint32_t count, const uint32_t M, const uint32_t tid) {
+  const uint32_t total = count * M;
+  const uint32_t ub0 = st.tile.unit_begin;
+  uint32_t done = 0;
+  for (uint32_t it = tid; it < total; it += kVoteThreads) {
+    const uint32_t jl = it / M, p0 = (it - jl * M) * 8u;
+    const uint32_t j = __ldg(a.job_index + jbegin + jl);
+    const uint4 jw = __ldg(reinterpret_cast<const uint4*>(a.djobs + j));     // {unit_a, unit_b, out_off}
+    const uint32_t la = jw.x - ub0, lb = jw.y - ub0;
+    const uint64_t out_off = (static_cast<uint64_t>(jw.w) << 32) | jw.z;
+    const fgb_unit ua = st.units[la], ub = st.units[lb];
+    const uint32_t len = ua.cons_len < ub.cons_len ? ua.cons_len : ub.cons_len;       // duplex_caller.rs:846-849
+    if (p0 >= len) continue;                                   // (an empty job is left pending, too)
+    const uint32_t na = st.units[la + 1u].read_begin - ua.read_begin;
+    const uint32_t nb = st.units[lb + 1u].read_begin - ub.read_begin;
+    if ((out_off & 7ull) != 0ull || na + nb > 255u) continue;  // not a word-path job
+    // :852-882 both strands must have coverage inside the truncated region; the first word nearly always shows it
+    const uint32_t live0 = len < 8u ? len : 8u;
+    const uint4 ad0 = __ldcg(reinterpret_cast<const uint4*>(a.out_depth + ua.out_off));
+    const uint4 bd0 = __ldcg(reinterpret_cast<const uint4*>(a.out_depth + ub.out_off));
+    if (!(duplex_any_depth(ad0, live0) && duplex_any_depth(bd0, live0))) continue;
+    const uint2 ab2 = __ldcg(reinterpret_cast<const uint2*>(a.out_base + ua.out_off + p0));
+    const uint2 bb2 = __ldcg(reinterpret_cast<const uint2*>(a.out_base + ub.out_off + p0));
+    const uint2 aq2 = __ldcg(reinterpret_cast<const uint2*>(a.out_qual + ua.out_off + p0));
+    const uint2 bq2 = __ldcg(reinterpret_cast<const uint2*>(a.out_qual + ub.out_off + p0));
+    const DuplexWord w = duplex_combine_word(ab2, bb2, aq2, bq2);
+    uint32_t cnt[2] = {0u, 0u};
+    const uint32_t ra0 = ua.read_begin - read_base, rb0 = ub.read_begin - read_base;
+    const uint32_t nr = na + nb;
+    for (uint32_t r0 = 0; r0 < nr; r0 += 4u) {                 // AB rows then BA rows, four in flight
+      uint64_t d[4];
+      uint2 sb[4];
+#pragma unroll
+      for (uint32_t k = 0; k < 4u; ++k) {
+        const uint32_t r = r0 + k;
+        d[k] = r < nr ? *reinterpret_cast<const uint64_t*>(st_reads + 8u * (r < na ? ra0 + r : rb0 + (r - na))) : 0ull;
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < 4u; ++k) {
+        sb[k] = make_uint2(0x4E4E4E4Eu, 0x4E4E4E4Eu);          // N: counts nothing
+        if (static_cast<uint32_t>(d[k] & 0xFFFFu) > p0)
+          sb[k] = *reinterpret_cast<const uint2*>(st_bases + (static_cast<uint32_t>(d[k] >> 16) - base32 + p0));
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < 4u; ++k) {
+        const uint32_t rl = static_cast<uint32_t>(d[k] & 0xFFFFu);
+        duplex_recount_row(sb[k], rl > p0 ? rl - p0 : 0u, w.rawb, cnt);
+      }
+    }
+    *reinterpret_cast<uint2*>(a.d_base + out_off + p0) = make_uint2(w.ob[0], w.ob[1]);
+    *reinterpret_cast<uint2*>(a.d_qual + out_off + p0) = make_uint2(w.oq[0], w.oq[1]);
+    *reinterpret_cast<uint4*>(a.d_errors + out_off + p0) = duplex_errors_word(w.rawb, cnt);
+    if (p0 == 0u) { a.d_status[j] = FGB_DUPLEX_BOTH; ++done; }
+  }
+  return done;
+}
 
 __device__ __forceinline__ void write_called(const VoteArgs& a, uint64_t o, const Called& c) {
   a.out_base[o] = static_cast<uint8_t>(c.base);
@@ -1597,8 +1677,8 @@ __device__ __forceinline__ void vote_tile_deep_flat(const VoteArgs& a, VoteSmem&
 #define FGB_DEEP_FLAT_MIN 64      // the flat deep form takes single-unit tiles of at least this many reads
 #endif
 
-template <int V>
-__device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
+template <int V, bool Fused = false, class Args = VoteArgs>
+__device__ __forceinline__ void vote_kernel_body(const Args& a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   VoteSmem& S = *reinterpret_cast<VoteSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x;
@@ -1711,6 +1791,7 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
 
   // ================= CONSUMER WARPS =================
   LocalStats ls = {0, 0, 0};
+  uint32_t combined = 0;
   uint32_t k = 0, rot = 0;
   for (uint32_t t = blockIdx.x; t < n_tiles; t += grid, ++k) {
     const int s = k % kStages;
@@ -1747,6 +1828,14 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
         if (st.tile.flags & kTileFlagRegular) vote_tile<ShMem, true, V>(a, S, st, tv, vt, warp, n_items, ls);
         else vote_tile<ShMem, false, V>(a, S, st, tv, vt, warp, n_items, ls);
       }
+      if constexpr (Fused) {
+        const uint2 tj = __ldg(reinterpret_cast<const uint2*>(a.tile_jobs + t));   // {begin, count | max_items << 16}
+        if (tj.y & 0xFFFFu) {                                  // CTA-uniform
+          consumer_barrier();                                  // every SS word of the tile is written
+          combined += duplex_epilogue(a, st, st.bases, tv.reads, static_cast<uint32_t>(st.tile.byte_begin),
+                                      st.tile.read_begin, tj.x, tj.y & 0xFFFFu, tj.y >> 16, tid);
+        }
+      }
     }
     rot = (rot + n_items) & (kVoteThreads - 1);
     __syncwarp();
@@ -1766,6 +1855,11 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
     if (v1) atomicAdd(a.counters + FGB_CTR_EXACT_POSITIONS, static_cast<unsigned long long>(v1));
     if (v2) atomicAdd(a.counters + FGB_CTR_NOCALL_POSITIONS, static_cast<unsigned long long>(v2));
   }
+  if constexpr (Fused) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) combined += __shfl_down_sync(0xFFFFFFFFu, combined, off);
+    if ((tid & 31u) == 0 && combined) atomicAdd(a.counters + FGB_CTR_COMBINED, static_cast<unsigned long long>(combined));
+  }
 }
 
 
@@ -1775,5 +1869,9 @@ __device__ __forceinline__ void vote_kernel_body(const VoteArgs& a) {
 __global__ void __launch_bounds__(kThreads) vote_kernel(const VoteArgs a) { vote_kernel_body<0>(a); }
 __global__ void __launch_bounds__(kThreads) vote_kernel_shallow(const VoteArgs a) { vote_kernel_body<1>(a); }
 __global__ void __launch_bounds__(kThreads) vote_kernel_deep(const VoteArgs a) { vote_kernel_body<2>(a); }
+// The same three with the duplex epilogue (fgb_vote_duplex_device).
+__global__ void __launch_bounds__(kThreads, 2) vote_kernel_duplex(const VoteArgsDuplex a) { vote_kernel_body<0, true, VoteArgsDuplex>(a); }
+__global__ void __launch_bounds__(kThreads, 2) vote_kernel_shallow_duplex(const VoteArgsDuplex a) { vote_kernel_body<1, true, VoteArgsDuplex>(a); }
+__global__ void __launch_bounds__(kThreads, 2) vote_kernel_deep_duplex(const VoteArgsDuplex a) { vote_kernel_body<2, true, VoteArgsDuplex>(a); }
 
 }  // namespace fgb

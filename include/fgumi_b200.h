@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define FGB_ABI_VERSION 2
+#define FGB_ABI_VERSION 3
 #define FGB_READ_ALIGN 8u   /* byte alignment of every read row in bases[]/quals[]          */
 #define FGB_OUT_ALIGN 8u    /* element alignment of every unit's output row                 */
 #define FGB_MAX_READ_LEN 65535u
@@ -478,7 +478,8 @@ enum {   /* per-job status: which arm of duplex_consensus (duplex_caller.rs:855-
   FGB_DUPLEX_BOTH = 0,     /* combined; output length = min(cons_len a, cons_len b)            */
   FGB_DUPLEX_A_ONLY = 1,   /* B had no coverage in the truncated region; output = A, full len  */
   FGB_DUPLEX_B_ONLY = 2,   /* A had no coverage; output = B, full len (is_ba_only)             */
-  FGB_DUPLEX_NONE = 3      /* neither strand has coverage: no duplex read                       */
+  FGB_DUPLEX_NONE = 3,     /* neither strand has coverage: no duplex read                       */
+  FGB_DUPLEX_PENDING = 255 /* internal to fgb_vote_duplex_device: not combined yet; never returned */
 };
 
 typedef struct fgb_duplex_out {
@@ -487,6 +488,37 @@ typedef struct fgb_duplex_out {
   uint16_t* errors;        /* [n_out] */
   uint8_t* status;         /* [n_jobs] FGB_DUPLEX_* (may be NULL)                              */
 } fgb_duplex_out;
+
+/* ---- since ABI 3: the duplex combine in the vote kernels' epilogue ------------------------------------
+ * A duplex molecule's single-strand units are voted in one tile and combined while the tile's source rows are
+ * still in shared memory and the single-strand words it just wrote are in L2: K2 neither reads the SS columns
+ * back from HBM nor re-reads the source rows for the exact error recount (duplex_caller.rs:943-951).
+ *
+ * fgb_plan_tiles_jobs plans like fgb_plan_tiles but keeps the two units of a job (and every unit between
+ * them) in one tile where they fit a stage, sorts the tiles by class (fills class_tiles like
+ * fgb_sort_tiles_by_class) and attaches to every tile the jobs both of whose units it holds:
+ * job_index[tile_jobs[t].begin .. +count) are indices into jobs[].  Jobs that cannot be attached (units in
+ * different tiles, an oversize unit) are simply not listed; *n_attached counts the listed ones.  Call with
+ * tiles == NULL to size the tile arrays (*n_tiles), job_index holds n_jobs entries. */
+typedef struct fgb_tile_jobs {
+  uint32_t begin;       /* first entry of job_index[] for this tile                              */
+  uint16_t count;       /* attached jobs                                                         */
+  uint16_t max_items;   /* 8-position words of the longest attached job                          */
+} fgb_tile_jobs;
+
+fgb_status fgb_plan_tiles_jobs(const fgb_unit* units, uint64_t n_units, const fgb_read_desc* reads,
+                               uint64_t n_reads, const fgb_duplex_job* jobs, uint64_t n_jobs,
+                               fgb_tile* tiles, uint64_t cap, uint64_t* n_tiles, uint64_t class_tiles[3],
+                               fgb_tile_jobs* tile_jobs, uint32_t* job_index, uint64_t* n_attached);
+
+/* Vote `in` (tiles from fgb_plan_tiles_jobs, class_tiles set) into `ss` and combine `jobs` into `out`: attached
+ * both-strand jobs in the vote's epilogue, every other job (single-strand arms, unattached jobs, rows that are
+ * not 8-aligned) by the standalone kernels afterwards.  Results are those of fgb_vote_device followed by
+ * fgb_duplex_combine_device, bit for bit.  All pointers are device pointers; tile_jobs has in->n_tiles entries. */
+fgb_status fgb_vote_duplex_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss,
+                                  const fgb_duplex_job* jobs, uint64_t n_jobs,
+                                  const fgb_tile_jobs* tile_jobs, const uint32_t* job_index,
+                                  const fgb_duplex_out* out, void* stream);
 
 /* `ss` are the four single-strand columns the vote wrote for `in` (device pointers). */
 fgb_status fgb_duplex_combine_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss,

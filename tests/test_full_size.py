@@ -7,6 +7,9 @@ properties plus an exact oracle comparison on a random sample of families (the o
   cfg 4  CODEC    2 M molecules, depth 2-20 per strand, 2 x 150 bp
   cfg 5  simplex  12.5 M families (one rank's shard of 100 M), Zipf depth 1-100
 
+Besides the sample, one contiguous slice of every vote (up to 2 M source rows: 250 k families at depth 8) is
+compared with a full oracle pass, every unit and position.
+
 Properties: device counters equal the descriptor sums; results do not depend on how the batch is cut
 into launches (prefix sub-batch == prefix of the full result); a second launch is bit-identical;
 depth/error invariants hold everywhere.  FGB_FULL_SCALE (default 1.0) shrinks every size."""
@@ -72,6 +75,43 @@ def _check_sample_against_oracle(fg, torch, tb, out, sample, min_reads, min_q):
     return pb, (ob, oq, od, oe)
 
 
+def _check_slice_against_oracle(fg, torch, tb, out, depths, min_reads, min_q, max_rows=2_000_000, where=0.37):
+    """EVERY unit of one contiguous slice of the batch (up to `max_rows` source rows, starting `where` of the way
+    in) against a full oracle pass over the same rows copied back from device memory: all four columns, every
+    called position.  The sampled comparison above draws units from everywhere; this one leaves no gaps."""
+    from fgumi_b200 import synth
+    host = tb.host
+    U = host.n_units
+    rb = host.units["read_begin"].astype(np.int64)
+    Lp, Lo = (L + 7) // 8 * 8, (L + 7) // 8 * 8
+    u0 = int(U * where)
+    u1 = int(np.searchsorted(rb, rb[u0] + max_rows, side="right")) - 1
+    u1 = max(u0 + 1, min(U, u1))
+    pb = synth.make_descriptors(depths[u0:u1], L, min_reads)
+    r0, r1 = int(rb[u0]), int(rb[u1])
+    pad = np.zeros(16, np.uint8)
+    pb.bases = np.concatenate([tb.bases.reshape(-1)[r0 * Lp:r1 * Lp].cpu().numpy(), pad])
+    pb.quals = np.concatenate([tb.quals.reshape(-1)[r0 * Lp:r1 * Lp].cpu().numpy(), pad])
+    ob, oq, od, oe, cl = O.simplex_batch(pb, 45, 40, min_reads, min_q, max(1, min(32, os.cpu_count() or 1)))
+    o0 = int(host.units["out_off"][u0])
+    n = (u1 - u0) * Lo
+    assert int(host.units["out_off"][u1]) - o0 == n and pb.n_out == n
+    assert np.array_equal(cl, host.units["cons_len"][u0:u1])
+    valid = (np.arange(Lo)[None, :] < cl.astype(np.int64)[:, None]).reshape(-1)
+    for name, g, o in (("base", out.base, ob), ("qual", out.qual, oq), ("depth", out.depth, od), ("errors", out.errors, oe)):
+        got = g[o0:o0 + n].cpu().numpy()
+        if got.dtype != o.dtype:
+            got = got.view(o.dtype)
+        bad = np.flatnonzero((got != o[:n]) & valid)
+        assert bad.size == 0, (name, u0 + int(bad[0]) // Lo, int(bad[0]) % Lo, bad.size)
+    _LAST_SLICE.clear()
+    _LAST_SLICE.update(u0=u0, u1=u1, pb=pb, cols=(ob, oq, od, oe, cl))
+    return u1 - u0
+
+
+_LAST_SLICE = {}      # the slice the last _vote_and_check compared in full, with the oracle's columns for it
+
+
 def _invariants(torch, out, depth_max):
     d, e = out.depth.view(torch.int16), out.errors.view(torch.int16)
     assert int(d.max()) <= depth_max and int(d.min()) >= 0
@@ -116,6 +156,7 @@ def _vote_and_check(fg, torch, tb, depths, min_reads=1, min_q=2, n_sample=1500, 
     rng = np.random.default_rng(seed)
     sample = np.sort(rng.choice(U, size=min(n_sample, U), replace=False))
     _check_sample_against_oracle(fg, torch, tb, out, sample, min_reads, min_q)
+    _check_slice_against_oracle(fg, torch, tb, out, depths, min_reads, min_q)
     return eng, out
 
 
@@ -201,6 +242,35 @@ def test_config3_duplex_5m_molecules(fg):
         assert st == 0 and n == L
         assert np.array_equal(gb[k][:n], rb[:n]) and np.array_equal(gq[k][:n], rq[:n])
         assert np.array_equal(ge[k][:n].view(np.uint16), re_[:n])
+    # ... and EVERY job of a contiguous run inside the slice the vote check compared in full (the oracle's own SS
+    # columns for those units are at hand): up to 20 000 jobs, all three columns, every position
+    u0, u1, spb, (sb_, sq_, sd_, se_, scl) = (_LAST_SLICE[k] for k in ("u0", "u1", "pb", "cols"))
+    j0, j1 = (u0 + 3) // 4 * 2, min(u1 // 4 * 2, (u0 + 3) // 4 * 2 + 20_000)
+    assert j1 > j0
+    soo = spb.units["out_off"].astype(np.int64)
+    srb = spb.units["read_begin"].astype(np.int64)
+    Lp = (L + 7) // 8 * 8
+    srows = spb.bases[: spb.n_reads * Lp].reshape(-1, Lp)
+    gb = o_base[j0 * Lo:j1 * Lo].cpu().numpy().reshape(-1, Lo)
+    gq = o_qual[j0 * Lo:j1 * Lo].cpu().numpy().reshape(-1, Lo)
+    ge = o_err[j0 * Lo:j1 * Lo].cpu().numpy().view(np.uint16).reshape(-1, Lo)
+    rb = np.zeros(L, np.uint8); rq = np.zeros(L, np.uint8); re_ = np.zeros(L, np.uint16)
+    olen = C.c_size_t()
+    for j in range(j0, j1):
+        a, b = int(jobs["unit_a"][j]) - u0, int(jobs["unit_b"][j]) - u0
+        ridx = list(range(srb[a], srb[a + 1])) + list(range(srb[b], srb[b + 1]))
+        ptrs = (C.c_void_p * len(ridx))(*[srows[r].ctypes.data for r in ridx])
+        lens = (C.c_size_t * len(ridx))(*([L] * len(ridx)))
+        oa, obo = int(soo[a]), int(soo[b])
+        st = lib.orc_duplex_job(sb_[oa:].ctypes.data, sq_[oa:].ctypes.data, sd_[oa:].ctypes.data,
+                                se_[oa:].ctypes.data, int(scl[a]), sb_[obo:].ctypes.data, sq_[obo:].ctypes.data,
+                                sd_[obo:].ctypes.data, se_[obo:].ctypes.data, int(scl[b]), ptrs, lens, len(ridx),
+                                rb.ctypes.data, rq.ctypes.data, re_.ctypes.data, C.addressof(olen))
+        n = olen.value
+        assert st == 0 and n == L, j
+        k = j - j0
+        assert np.array_equal(gb[k][:n], rb[:n]) and np.array_equal(gq[k][:n], rq[:n]), j
+        assert np.array_equal(ge[k][:n], re_[:n]), j
     eng.close()
 
 
