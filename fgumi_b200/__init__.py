@@ -6,7 +6,8 @@ include/fgumi_b200.h).  This package is the thin host-side mirror of that bounda
 from .engine import (Engine, PackedBatch, HostColumns, DeviceBatch, DeviceColumns,  # noqa: F401
                      VanillaUmiConsensusOptions, pack_source_reads, pack_uniform, plan_tiles, pack8_encode,
                      pack_raw_reads, RawColumns, RAW_READ_DTYPE,
-                     consensus_length, UNIT_DTYPE, TILE_DTYPE, DUPLEX_JOB_DTYPE, CODEC_JOB_DTYPE)
+                     consensus_length, UNIT_DTYPE, TILE_DTYPE, DUPLEX_JOB_DTYPE, CODEC_JOB_DTYPE,
+                     TILE_JOBS_DTYPE, plan_tiles_jobs)
 from . import lib  # noqa: F401
 from .caller import VanillaUmiConsensusCaller, DuplexConsensusCaller, CodecConsensusCaller, ConsensusOutput, ConsensusFilter, DuplexConsensusFilter, apply_overlapping_consensus, bgzf_compress, write_bam  # noqa: F401
 

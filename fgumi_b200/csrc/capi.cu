@@ -105,6 +105,7 @@ struct fgb_handle {
   std::vector<TraceMark> trace_ev;                  // device timeline of the last submit
   std::chrono::steady_clock::time_point trace_t0, trace_t1;
   int vote_variant = 1;                             // FGB_VOTE_KERNEL=0: the general kernel votes every tile (A/B runs)
+  uint8_t* d_dstatus = nullptr; uint64_t cap_dstatus = 0;   // fgb_vote_duplex_device: job status bytes when the caller wants none
 };
 
 namespace {
@@ -133,10 +134,18 @@ fgb_status ensure(fgb_handle* h, T** p, uint64_t* cap, uint64_t need) {
   return FGB_OK;
 }
 
+// The epilogue arguments of the vote kernels with the duplex combine (fgb_vote_duplex_device).
+struct DuplexEpilogueArgs {
+  const fgb_tile_jobs* tile_jobs;
+  const uint32_t* job_index;
+  const fgb_duplex_job* jobs;
+  fgb_duplex_out out;       // status non-null
+};
+
 fgb_status launch_vote(fgb_handle* h, const fgb_batch& b, const fgb_columns& out,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const DuplexEpilogueArgs* dx = nullptr) {
   if (b.n_tiles == 0) return FGB_OK;
-  VoteArgs a;
+  VoteArgsDuplex a{};
   a.bases = b.bases; a.quals = b.quals; a.reads = b.reads; a.units = b.units; a.tiles = b.tiles;
   a.n_tiles = b.n_tiles;
   a.out_base = out.base; a.out_qual = out.qual; a.out_depth = out.depth; a.out_errors = out.errors;
@@ -145,18 +154,30 @@ fgb_status launch_vote(fgb_handle* h, const fgb_batch& b, const fgb_columns& out
   a.min_reads = h->params.min_reads;
   a.min_cons_q = h->params.min_consensus_base_quality;
   a.fast_qual = h->host_tables.fast_qual;
+  if (dx) {
+    a.tile_jobs = dx->tile_jobs; a.job_index = dx->job_index; a.djobs = dx->jobs;
+    a.d_base = dx->out.base; a.d_qual = dx->out.qual; a.d_errors = dx->out.errors; a.d_status = dx->out.status;
+  }
   const uint64_t max_grid = static_cast<uint64_t>(h->sm_count) * 2u;
   const uint64_t c0 = b.class_tiles[0], c1 = b.class_tiles[1], c2 = b.class_tiles[2];
   const bool sorted = h->vote_variant != 0 && c0 + c1 + c2 == b.n_tiles;
   auto launch = [&](int cls, uint64_t first, uint64_t n) {
     if (!n) return;
-    VoteArgs x = a;
+    VoteArgsDuplex x = a;
     x.tiles = b.tiles + first;
     x.n_tiles = n;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, max_grid));
-    if (cls == 1) vote_kernel_shallow<<<grid, kThreads, sizeof(VoteSmem) + kShallowSmemBytes, stream>>>(x);
-    else if (cls == 2) vote_kernel_deep<<<grid, kThreads, sizeof(VoteSmem) + kDeepSmemBytes, stream>>>(x);
-    else vote_kernel<<<grid, kThreads, sizeof(VoteSmem), stream>>>(x);
+    if (dx) {
+      x.tile_jobs = dx->tile_jobs + first;
+      if (cls == 1) vote_kernel_shallow_duplex<<<grid, kThreads, sizeof(VoteSmem) + kShallowSmemBytes, stream>>>(x);
+      else if (cls == 2) vote_kernel_deep_duplex<<<grid, kThreads, sizeof(VoteSmem) + kDeepSmemBytes, stream>>>(x);
+      else vote_kernel_duplex<<<grid, kThreads, sizeof(VoteSmem), stream>>>(x);
+    } else {
+      const VoteArgs& v = x;
+      if (cls == 1) vote_kernel_shallow<<<grid, kThreads, sizeof(VoteSmem) + kShallowSmemBytes, stream>>>(v);
+      else if (cls == 2) vote_kernel_deep<<<grid, kThreads, sizeof(VoteSmem) + kDeepSmemBytes, stream>>>(v);
+      else vote_kernel<<<grid, kThreads, sizeof(VoteSmem), stream>>>(v);
+    }
     h->launches++;
   };
   if (sorted) { launch(0, 0, c0); launch(1, c0, c1); launch(2, c0 + c1, c2); }
@@ -281,6 +302,13 @@ fgb_status fgb_create(int device, const fgb_params* params, fgb_handle** out) {
   if ((e = cudaFuncSetAttribute(vote_kernel_deep, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(sizeof(VoteSmem) + kDeepSmemBytes))) != cudaSuccess)
     return fail(e, "cudaFuncSetAttribute(vote_kernel_deep)");
+  if ((e = cudaFuncSetAttribute(vote_kernel_duplex, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(VoteSmem)))) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(vote_kernel_shallow_duplex, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(VoteSmem) + kShallowSmemBytes))) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(vote_kernel_deep_duplex, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(VoteSmem) + kDeepSmemBytes))) != cudaSuccess)
+    return fail(e, "cudaFuncSetAttribute(vote_kernel_*_duplex)");
   for (int s = 0; s < kSlots; ++s)
     if ((e = cudaStreamCreateWithFlags(&h->slots[s].stream, cudaStreamNonBlocking)) != cudaSuccess)
       return fail(e, "cudaStreamCreate");
@@ -305,6 +333,7 @@ void fgb_destroy(fgb_handle* h) {
   cudaFree(h->d_ostats);
   cudaFree(h->d_oruns);
   cudaFree(h->d_recstr); cudaFree(h->d_recjobs);
+  cudaFree(h->d_dstatus);
   if (h->ev_recstr) cudaEventDestroy(h->ev_recstr);
   delete h;
 }
@@ -374,6 +403,79 @@ fgb_status fgb_plan_tiles(const fgb_unit* units, uint64_t n_units, const fgb_rea
   });
   if (st != FGB_OK) return st;
   *n_tiles = nt;
+  return FGB_OK;
+}
+
+// Planner for the duplex epilogue: see include/fgumi_b200.h.
+constexpr uint64_t kGlueSpanMax = 16;     // a job keeps its units (and those between them) together up to this distance
+fgb_status fgb_plan_tiles_jobs(const fgb_unit* units, uint64_t n_units, const fgb_read_desc* reads,
+                               uint64_t n_reads, const fgb_duplex_job* jobs, uint64_t n_jobs,
+                               fgb_tile* tiles, uint64_t cap, uint64_t* n_tiles, uint64_t class_tiles[3],
+                               fgb_tile_jobs* tile_jobs, uint32_t* job_index, uint64_t* n_attached) {
+  if (!n_tiles || (n_units && (!units || (!reads && n_reads))) || (n_jobs && !jobs)) return FGB_ERR_INVALID_ARG;
+  if (n_units >= 0xFFFFFFFFull || n_reads >= 0xFFFFFFFFull || n_jobs >= 0xFFFFFFFFull) return FGB_ERR_INVALID_ARG;
+  if (n_units && units[0].read_begin != 0) return FGB_ERR_LAYOUT;
+  try {
+    // glue[u]: some job has one unit before u and the other at or after it
+    std::vector<int32_t> diff(n_units + 2, 0);
+    for (uint64_t j = 0; j < n_jobs; ++j) {
+      const uint64_t a = jobs[j].unit_a, b = jobs[j].unit_b;
+      if (a >= n_units || b >= n_units) return FGB_ERR_INVALID_ARG;
+      const uint64_t lo = std::min(a, b), hi = std::max(a, b);
+      if (hi > lo && hi - lo < kGlueSpanMax) { diff[lo + 1]++; diff[hi + 1]--; }   // partners far apart share no tile anyway
+    }
+    std::vector<uint8_t> glue(n_units + 1, 0);
+    int32_t acc = 0;
+    for (uint64_t u = 0; u <= n_units; ++u) { acc += diff[u]; glue[u] = acc > 0 ? 1 : 0; }
+    diff = std::vector<int32_t>();
+    std::vector<fgb_tile> plan;
+    uint64_t prev_read_end = 0;
+    fgb_status st = plan_tiles_range(units, 0, n_units, reads, n_reads, &prev_read_end,
+                                     [&](const fgb_tile& t) { plan.push_back(t); }, glue.data());
+    if (st != FGB_OK) return st;
+    const uint64_t nt = plan.size();
+    *n_tiles = nt;
+    if (!tiles || cap < nt) return FGB_OK;                    // sizing call
+    if (!class_tiles || (nt && !tile_jobs) || (n_jobs && !job_index)) return FGB_ERR_INVALID_ARG;
+    // tiles in class order (stable), as fgb_sort_tiles_by_class leaves them
+    std::vector<uint32_t> order(nt);
+    for (uint64_t i = 0; i < nt; ++i) order[i] = static_cast<uint32_t>(i);
+    auto cls_of = [&](uint32_t i) { const uint32_t c = (plan[i].flags & kTileClassMask) >> kTileClassShift; return c < 3 ? c : 0u; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cls_of(x) < cls_of(y); });
+    class_tiles[0] = class_tiles[1] = class_tiles[2] = 0;
+    std::vector<uint32_t> tile_of(n_units);                   // unit -> tile (position in class order)
+    for (uint64_t k = 0; k < nt; ++k) {
+      const fgb_tile& t = plan[order[k]];
+      tiles[k] = t;
+      tile_jobs[k] = fgb_tile_jobs{0u, 0u, 0u};
+      class_tiles[cls_of(order[k])]++;
+      for (uint32_t u = t.unit_begin; u < t.unit_begin + t.n_units; ++u) tile_of[u] = static_cast<uint32_t>(k);
+    }
+    auto attach_to = [&](uint64_t j) -> int64_t {            // the tile a job runs in, or -1
+      const uint32_t ta = tile_of[jobs[j].unit_a];
+      if (ta != tile_of[jobs[j].unit_b] || (tiles[ta].flags & kTileFlagDirect)) return -1;
+      return ta;
+    };
+    for (uint64_t j = 0; j < n_jobs; ++j) {
+      const int64_t t = attach_to(j);
+      if (t < 0 || tile_jobs[t].count == 0xFFFFu) continue;
+      tile_jobs[t].count++;
+      const uint32_t la = units[jobs[j].unit_a].cons_len, lb = units[jobs[j].unit_b].cons_len;
+      const uint32_t items = (std::min(la, lb) + 7u) >> 3;
+      tile_jobs[t].max_items = static_cast<uint16_t>(std::max<uint32_t>(tile_jobs[t].max_items, items));
+    }
+    uint64_t total = 0;
+    for (uint64_t k = 0; k < nt; ++k) { tile_jobs[k].begin = static_cast<uint32_t>(total); total += tile_jobs[k].count; }
+    std::vector<uint16_t> fill(nt, 0);
+    for (uint64_t j = 0; j < n_jobs; ++j) {
+      const int64_t t = attach_to(j);
+      if (t < 0 || fill[t] == tile_jobs[t].count) continue;
+      job_index[tile_jobs[t].begin + fill[t]++] = static_cast<uint32_t>(j);
+    }
+    if (n_attached) *n_attached = total;
+  } catch (const std::bad_alloc&) {
+    return FGB_ERR_NOMEM;
+  }
   return FGB_OK;
 }
 
@@ -1064,6 +1166,52 @@ fgb_status fgb_duplex_combine_device(fgb_handle* h, const fgb_batch* in, const f
                                                              static_cast<uint64_t>(h->sm_count) * 8u));
     duplex_combine_kernel<<<grid, kCombineThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   }
+  h->launches++;
+  FGB_CUDA(h, cudaGetLastError());
+  return FGB_OK;
+}
+
+fgb_status fgb_vote_duplex_device(fgb_handle* h, const fgb_batch* in, const fgb_columns* ss,
+                                  const fgb_duplex_job* jobs, uint64_t n_jobs,
+                                  const fgb_tile_jobs* tile_jobs, const uint32_t* job_index,
+                                  const fgb_duplex_out* out, void* stream) {
+  if (!h || !in || !ss || !out || (n_jobs && !jobs)) return FGB_ERR_INVALID_ARG;
+  if (in->n_tiles && (!in->tiles || !in->units || !ss->base || !ss->qual || !ss->depth || !ss->errors))
+    return FGB_ERR_INVALID_ARG;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // the epilogue moves 8 elements at a time: byte columns 8-byte aligned, u16 columns and job records 16-byte aligned
+  const uintptr_t align8 = reinterpret_cast<uintptr_t>(ss->base) | reinterpret_cast<uintptr_t>(ss->qual) |
+                           reinterpret_cast<uintptr_t>(out->base) | reinterpret_cast<uintptr_t>(out->qual) |
+                           reinterpret_cast<uintptr_t>(tile_jobs) | reinterpret_cast<uintptr_t>(in->bases);
+  const uintptr_t align16 = reinterpret_cast<uintptr_t>(ss->depth) | reinterpret_cast<uintptr_t>(out->errors) |
+                            reinterpret_cast<uintptr_t>(jobs);
+  const bool fused = n_jobs && in->n_tiles && tile_jobs && job_index && (align8 & 7u) == 0 && (align16 & 15u) == 0;
+  if (!fused) {
+    fgb_status st = launch_vote(h, *in, *ss, s);
+    if (st != FGB_OK || n_jobs == 0) return st;
+    return fgb_duplex_combine_device(h, in, ss, jobs, n_jobs, out, stream);
+  }
+  DuplexEpilogueArgs dx{tile_jobs, job_index, jobs, *out};
+  if (!dx.out.status) {
+    fgb_status st = ensure(h, &h->d_dstatus, &h->cap_dstatus, n_jobs);
+    if (st != FGB_OK) return st;
+    dx.out.status = h->d_dstatus;
+  }
+  FGB_CUDA(h, cudaMemsetAsync(dx.out.status, FGB_DUPLEX_PENDING, n_jobs, s));
+  fgb_status st = launch_vote(h, *in, *ss, s, &dx);
+  if (st != FGB_OK) return st;
+  // what the epilogue left pending: single-strand arms, jobs whose units sit in different tiles, general layouts
+  DuplexArgs a;
+  a.bases = in->bases; a.reads = in->reads; a.units = in->units;
+  a.ss_base = ss->base; a.ss_qual = ss->qual; a.ss_depth = ss->depth; a.ss_errors = ss->errors;
+  a.jobs = jobs; a.n_jobs = n_jobs;
+  a.out_base = out->base; a.out_qual = out->qual; a.out_errors = out->errors;
+  a.out_status = dx.out.status;
+  a.counters = h->d_counters;
+  const uint64_t groups = (n_jobs + kCombineThreads - 1) / kCombineThreads;
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(groups, static_cast<uint64_t>(h->sm_count) * 8u));
+  duplex_combine_pending_kernel<<<grid, kCombineThreads, 0, s>>>(a);
   h->launches++;
   FGB_CUDA(h, cudaGetLastError());
   return FGB_OK;

@@ -224,6 +224,38 @@ def plan_tiles(batch: PackedBatch) -> np.ndarray:
     return batch.tiles
 
 
+TILE_JOBS_DTYPE = np.dtype([("begin", "<u4"), ("count", "<u2"), ("max_items", "<u2")])
+
+
+def plan_tiles_jobs(batch: PackedBatch, jobs: np.ndarray):
+    """fgb_plan_tiles_jobs: tiles (class-sorted) that keep a duplex job's two units together, plus the per-tile job
+    lists the vote kernels' duplex epilogue runs.  Returns (tiles, class_tiles, tile_jobs, job_index, n_attached);
+    `batch.tiles` is left alone (the returned tiles are in class order, not unit order)."""
+    lib = _l.load()
+    jobs = np.ascontiguousarray(jobs)
+    n = C.c_uint64(0)
+    na = C.c_uint64(0)
+    up = batch.units.ctypes.data_as(C.c_void_p)
+    rp = batch.reads.ctypes.data_as(C.c_void_p)
+    jp = jobs.ctypes.data_as(C.c_void_p)
+    st = lib.fgb_plan_tiles_jobs(up, batch.n_units, rp, batch.n_reads, jp, len(jobs), None, 0, C.byref(n),
+                                 None, None, None, None)
+    if st != _l.FGB_OK:
+        raise _l.FgbError(st, "fgb_plan_tiles_jobs")
+    nt = int(n.value)
+    tiles = np.zeros(max(nt, 1), dtype=TILE_DTYPE)
+    tile_jobs = np.zeros(max(nt, 1), dtype=TILE_JOBS_DTYPE)
+    job_index = np.zeros(max(len(jobs), 1), dtype=np.uint32)
+    counts = (C.c_uint64 * 3)()
+    st = lib.fgb_plan_tiles_jobs(up, batch.n_units, rp, batch.n_reads, jp, len(jobs),
+                                 tiles.ctypes.data_as(C.c_void_p), nt, C.byref(n), counts,
+                                 tile_jobs.ctypes.data_as(C.c_void_p), job_index.ctypes.data_as(C.c_void_p),
+                                 C.byref(na))
+    if st != _l.FGB_OK:
+        raise _l.FgbError(st, "fgb_plan_tiles_jobs")
+    return tiles[:nt], (int(counts[0]), int(counts[1]), int(counts[2])), tile_jobs[:nt], job_index, int(na.value)
+
+
 def sort_tiles_by_class(tiles: np.ndarray):
     """fgb_sort_tiles_by_class on a COPY of the tile table: (sorted tiles, run lengths per class).  For
     device-resident batches (fgb_vote_device); the host-buffer calls sort their chunks themselves."""
@@ -433,6 +465,21 @@ class Engine:
                                                         C.c_void_p(jobs.data_ptr()), n_jobs,
                                                         C.byref(o), C.c_void_p(stream or 0)),
                     "fgb_duplex_combine_device")
+
+    def vote_duplex_device(self, db, ss: DeviceColumns, jobs, n_jobs: int, tile_jobs, job_index,
+                           out_base, out_qual, out_errors, out_status=None, stream: Optional[int] = None):
+        """fgb_vote_duplex_device: the vote with the duplex combine in its epilogue.  `db` carries the tiles (and
+        class_tiles) of plan_tiles_jobs; tile_jobs / job_index are device tensors of its tables."""
+        b = db.struct()
+        c = ss.struct()
+        o = _l.FgbDuplexOut(out_base.data_ptr(), out_qual.data_ptr(), out_errors.data_ptr(),
+                            out_status.data_ptr() if out_status is not None else None)
+        self._check(self._lib.fgb_vote_duplex_device(self._h, C.byref(b), C.byref(c),
+                                                     C.c_void_p(jobs.data_ptr()), n_jobs,
+                                                     C.c_void_p(tile_jobs.data_ptr()),
+                                                     C.c_void_p(job_index.data_ptr()),
+                                                     C.byref(o), C.c_void_p(stream or 0)),
+                    "fgb_vote_duplex_device")
 
     def codec_combine_device(self, db: DeviceBatch, ss: DeviceColumns, jobs, n_jobs: int,
                              params: _l.FgbCodecParams, out: DeviceColumns, status, disagreements=None,

@@ -205,7 +205,7 @@ class FgbCodecOut(C.Structure):
 SYMBOLS = (
     "fgb_abi_version", "fgb_create", "fgb_destroy", "fgb_strerror", "fgb_last_error",
     "fgb_get_tables", "fgb_host_tables", "fgb_host_proof_tables", "fgb_host_unanimous_steps", "fgb_tile_capacity_bytes", "fgb_tile_max_units", "fgb_tile_max_reads",
-    "fgb_plan_tiles", "fgb_sort_tiles_by_class", "fgb_vote_device", "fgb_submit", "fgb_wait", "fgb_host_alloc",
+    "fgb_plan_tiles", "fgb_plan_tiles_jobs", "fgb_sort_tiles_by_class", "fgb_vote_device", "fgb_vote_duplex_device", "fgb_submit", "fgb_wait", "fgb_host_alloc",
     "fgb_host_free", "fgb_host_is_pinned", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count", "fgb_engine_caps",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
@@ -263,6 +263,11 @@ def load() -> C.CDLL:
         getattr(lib, f).argtypes = []
     lib.fgb_plan_tiles.argtypes = [vp, u64, vp, u64, vp, u64, C.POINTER(u64)]
     lib.fgb_plan_tiles.restype = C.c_int32
+    lib.fgb_plan_tiles_jobs.argtypes = [vp, u64, vp, u64, vp, u64, vp, u64, C.POINTER(u64), vp, vp, vp, C.POINTER(u64)]
+    lib.fgb_plan_tiles_jobs.restype = C.c_int32
+    lib.fgb_vote_duplex_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), vp, u64, vp, vp,
+                                           C.POINTER(FgbDuplexOut), vp]
+    lib.fgb_vote_duplex_device.restype = C.c_int32
     lib.fgb_sort_tiles_by_class.argtypes = [vp, u64, vp]
     lib.fgb_sort_tiles_by_class.restype = C.c_int32
     lib.fgb_vote_device.argtypes = [vp, C.POINTER(FgbBatch), C.POINTER(FgbColumns), vp]

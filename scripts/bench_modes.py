@@ -24,32 +24,9 @@ def timed(fn, n=8):
 
 
 def duplex():
-    M = int(5_000_000 * scale); U = 4 * M
-    depths = np.full(U, 4, dtype=np.int64)
-    m = np.arange(M, dtype=np.int64)
-    tid = np.empty(U, dtype=np.int64)
-    tid[0::4], tid[3::4], tid[1::4], tid[2::4] = 2 * m, 2 * m, 2 * m + 1, 2 * m + 1
-    tb = synth.device_batch(torch, DEV, depths, L, 1e-3, seed=43, template_ids=tid)
-    eng = fg.Engine(0, 45, 40, 1, 2)
-    ss = fg.DeviceColumns(tb.host.n_out, DEV)
-    jobs = np.zeros(2 * M, dtype=fg.DUPLEX_JOB_DTYPE)
-    jobs["unit_a"][0::2], jobs["unit_b"][0::2] = 4 * m, 4 * m + 3
-    jobs["unit_a"][1::2], jobs["unit_b"][1::2] = 4 * m + 1, 4 * m + 2
-    jobs["out_off"] = np.arange(2 * M, dtype=np.uint64) * np.uint64(Lo)
-    tj = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(DEV)
-    n_out = 2 * M * Lo
-    ob = torch.zeros(n_out, dtype=torch.uint8, device=DEV); oq = torch.zeros_like(ob)
-    oe = torch.zeros(n_out, dtype=torch.int16, device=DEV)
-    st = torch.zeros(2 * M, dtype=torch.uint8, device=DEV)
-    s = torch.cuda.current_stream().cuda_stream
-    t1 = timed(lambda: eng.vote_device(tb, ss, s))
-    t2 = timed(lambda: eng.duplex_combine_device(tb, ss, tj, 2 * M, ob, oq, oe, st, s))
-    k1_bytes = U * (2 * 4 * L + 6 * L + 8 * 5 + 8)
-    k2_bytes = 2 * M * (2 * 6 * L + 4 * L)     # 2 SS rows in, (base, qual, errors) out; the 8 pooled source rows re-read by the recount are not counted
-    eng.close()
-    return {"molecules": M, "k1_ms": t1, "k2_ms": t2, "molecules_per_s": M / ((t1 + t2) * 1e-3),
-            "k1_gbs": k1_bytes / t1 / 1e6, "k2_gbs": k2_bytes / t2 / 1e6,
-            "k1_frac": k1_bytes / t1 / 1e6 / peak, "k2_frac": k2_bytes / t2 / 1e6 / peak}
+    # the bench leg itself: K1 + K2 as two kernels and with the combine in the vote kernels' epilogue
+    from fgumi_b200 import benchlegs
+    return benchlegs.duplex_leg(torch, fg, DEV, 0, int(5_000_000 * scale))
 
 
 def codec():

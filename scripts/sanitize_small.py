@@ -55,6 +55,13 @@ c = fg.VanillaUmiConsensusCaller("f", "A", fg.VanillaUmiConsensusOptions(min_rea
 c.add_groups(random_groups(rng, 60)); c.flush(); c.close()
 c = fg.DuplexConsensusCaller("f", "A", min_reads=(1, 1, 0)); c.consensus_reads_batch(random_duplex_groups(rng, 60)); c.close()
 c = fg.CodecConsensusCaller("c", "R"); c.consensus_reads_batch(random_codec_groups(rng, 60)); c.close()
+# duplex combine in the vote kernels' epilogue (all three class kernels, attached and stray jobs, pending clean-up)
+from tests.test_combine_parity import _duplex_molecules, _duplex_against_oracle
+du, dp = _duplex_molecules(rng, 120, depth_hi=41, len_lo=100, len_hi=151, iupac=True)
+dp += [(4 * m, 4 * (m + 30) + 1) for m in range(0, 80, 9)]
+_duplex_against_oracle(fg, du, dp, True)
+du, dp = _duplex_molecules(rng, 200)
+_duplex_against_oracle(fg, du, dp, True)
 # BAM4
 layout, raw = fg.pack_raw_reads([[(b"ACGTNACGTACGTTTGA", bytes(range(5, 22)), bool(i & 1), 17 - (i % 3))] * (1 + i % 4) for i in range(200)], 1, 10)
 o = fg.HostColumns.alloc(layout.n_out)

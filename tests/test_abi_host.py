@@ -31,7 +31,7 @@ def test_header_symbols_exported(fg):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(fg.lib.SYMBOLS)
-    assert lib.fgb_abi_version() == 2
+    assert lib.fgb_abi_version() == 3
 
 
 def test_struct_sizes_match_header(fg):

@@ -53,46 +53,51 @@ def _vote(fg, units, min_cons_q):
     return eng, batch, db, ss, (ob, oq, od, oe)
 
 
-def test_duplex_combine_matches_oracle(fg):
+def _duplex_against_oracle(fg, units, pairs, fused, min_cons_q=2):
+    """Vote `units`, combine `pairs` (standalone K2, or in the vote kernels' epilogue with `fused`) and compare every
+    job with the oracle's duplex_consensus over the oracle's own SS columns.  Returns the set of arms seen."""
     import torch
-    rng = np.random.default_rng(31)
     L = O.load()
-    units = []
-    n_mol = 300
-    for m in range(n_mol):
-        # AB-R1, AB-R2, BA-R1, BA-R2 single-strand families; a few strands carry no coverage at all
-        for k in range(4):
-            depth = int(rng.integers(1, 6))
-            length = int(rng.integers(20, 90))
-            dead = (m % 17 == 3 and k >= 2) or (m % 23 == 5 and k < 2) or (m % 29 == 7)
-            rows, _ = _family(rng, depth, length, all_n=dead)
-            units.append(rows)
-    eng, batch, db, ss, (ob, oq, od, oe) = _vote(fg, units, 2)
+    dev = "cuda:0"
+    batch = fg.pack_source_reads(units, 1)
     cons_len = batch.units["cons_len"]
     out_off = batch.units["out_off"]
-    # duplex R1 = AB-R1 (+) BA-R2, duplex R2 = AB-R2 (+) BA-R1   (duplex_caller.rs:1999-2012)
-    pairs = []
-    for m in range(n_mol):
-        pairs.append((4 * m + 0, 4 * m + 3))
-        pairs.append((4 * m + 1, 4 * m + 2))
     jobs = np.zeros(len(pairs), dtype=fg.DUPLEX_JOB_DTYPE)
     off = 0
     for j, (ua, ub) in enumerate(pairs):
         jobs[j] = (ua, ub, off)
         off += (max(int(cons_len[ua]), int(cons_len[ub])) + 7) // 8 * 8
     n_out = max(off, 8)
-    dev = "cuda:0"
     tj = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(dev)
     o_base = torch.zeros(n_out, dtype=torch.uint8, device=dev)
     o_qual = torch.zeros(n_out, dtype=torch.uint8, device=dev)
     o_err = torch.zeros(n_out, dtype=torch.int16, device=dev)
-    o_st = torch.full((len(pairs),), 255, dtype=torch.uint8, device=dev)
-    eng.duplex_combine_device(db, ss, tj, len(pairs), o_base, o_qual, o_err, o_st,
-                              torch.cuda.current_stream().cuda_stream)
+    o_st = torch.full((len(pairs),), 77, dtype=torch.uint8, device=dev)
+    eng = fg.Engine(0, 45, 40, 1, min_cons_q)
+    db = fg.DeviceBatch(batch, dev)
+    ss = fg.DeviceColumns(batch.n_out, dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    n_attached = None
+    if fused:
+        tiles, class_tiles, tile_jobs, job_index, n_attached = fg.plan_tiles_jobs(batch, jobs)
+        t8 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
+        db.tiles, db.n_tiles, db.class_tiles = t8(tiles), len(tiles), class_tiles
+        d_tj, d_ji = t8(tile_jobs), t8(job_index)
+        eng.vote_duplex_device(db, ss, tj, len(pairs), d_tj, d_ji, o_base, o_qual, o_err, o_st, stream)
+    else:
+        eng.vote_device(db, ss, stream)
+        eng.duplex_combine_device(db, ss, tj, len(pairs), o_base, o_qual, o_err, o_st, stream)
     torch.cuda.synchronize()
+    ob, oq, od, oe, _ = O.simplex_batch(batch, 45, 40, 1, min_cons_q)
+    g = ss.to_host()
+    for sl in batch.unit_slices():
+        assert np.array_equal(g.base[sl], ob[sl]) and np.array_equal(g.qual[sl], oq[sl])
+        assert np.array_equal(g.depth[sl], od[sl]) and np.array_equal(g.errors[sl], oe[sl])
     gb, gq = o_base.cpu().numpy(), o_qual.cpu().numpy()
     ge, gs = o_err.cpu().numpy().view(np.uint16), o_st.cpu().numpy()
-    assert eng.stats()["combined_jobs"] == len(pairs)
+    st_ = eng.stats()
+    assert st_["combined_jobs"] == len(pairs)
+    assert st_["units"] == len(units)
     eng.close()
     seen = set()
     for j, (ua, ub) in enumerate(pairs):
@@ -115,7 +120,72 @@ def test_duplex_combine_matches_oracle(fg):
         assert np.array_equal(gb[o:o + n], rb[:n]), j
         assert np.array_equal(gq[o:o + n], rq[:n]), j
         assert np.array_equal(ge[o:o + n], re_[:n]), j
+    return seen, n_attached
+
+
+def _duplex_molecules(rng, n_mol, depth_hi=6, len_lo=20, len_hi=90, iupac=False):
+    units = []
+    for m in range(n_mol):
+        # AB-R1, AB-R2, BA-R1, BA-R2 single-strand families; a few strands carry no coverage at all
+        for k in range(4):
+            depth = int(rng.integers(1, depth_hi))
+            length = int(rng.integers(len_lo, len_hi))
+            dead = (m % 17 == 3 and k >= 2) or (m % 23 == 5 and k < 2) or (m % 29 == 7)
+            rows, _ = _family(rng, depth, length, all_n=dead)
+            if iupac and m % 5 == 1:      # codes the vote ignores but the exact recount counts (and a lower-case base)
+                b = bytearray(rows[0][0])
+                b[int(rng.integers(0, len(b)))] = ord("R")
+                b[int(rng.integers(0, len(b)))] = ord("a")
+                rows[0] = (bytes(b), rows[0][1])
+            units.append(rows)
+    # duplex R1 = AB-R1 (+) BA-R2, duplex R2 = AB-R2 (+) BA-R1   (duplex_caller.rs:1999-2012)
+    pairs = []
+    for m in range(n_mol):
+        pairs.append((4 * m + 0, 4 * m + 3))
+        pairs.append((4 * m + 1, 4 * m + 2))
+    return units, pairs
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_duplex_combine_matches_oracle(fg, fused):
+    rng = np.random.default_rng(31)
+    units, pairs = _duplex_molecules(rng, 300)
+    seen, n_attached = _duplex_against_oracle(fg, units, pairs, fused)
     assert seen == {0, 1, 2, 3}     # every arm of duplex_consensus was exercised
+    if fused:
+        assert n_attached == len(pairs)      # a molecule's four small units always fit one stage
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_duplex_combine_mixed_classes_and_odd_jobs(fg, fused):
+    """Strand depths from 1 to 40 (shallow, general and deep units inside one molecule), 150-base reads, codes outside
+    A/C/G/T/N in the source rows, jobs in shuffled order, and jobs whose units lie far apart (never attached to a
+    tile: the standalone kernel takes them after the vote)."""
+    rng = np.random.default_rng(32)
+    units, pairs = _duplex_molecules(rng, 160, depth_hi=41, len_lo=120, len_hi=151, iupac=True)
+    n_mol = len(units) // 4
+    for m in range(0, n_mol - 40, 7):                           # far-apart partners (and a repeated unit)
+        pairs.append((4 * m, 4 * (m + 37) + 2))
+    pairs.append((5, 5))
+    order = rng.permutation(len(pairs))
+    pairs = [pairs[i] for i in order]
+    seen, n_attached = _duplex_against_oracle(fg, units, pairs, fused)
+    assert {0, 1, 2} <= seen
+    if fused:
+        assert 3 * n_mol // 2 <= n_attached < len(pairs)
+
+
+def test_duplex_epilogue_uniform_molecules(fg):
+    """BASELINE config 3's shape in small: 4 + 4 reads per strand, 150 bp, regular tiles of eight molecules."""
+    rng = np.random.default_rng(33)
+    units = []
+    for m in range(700):
+        for k in range(4):
+            rows, _ = _family(rng, 4, 150, err=0.01, n_rate=0.002, qlo=20, qhi=40)
+            units.append(rows)
+    pairs = [p for m in range(700) for p in ((4 * m, 4 * m + 3), (4 * m + 1, 4 * m + 2))]
+    seen, n_attached = _duplex_against_oracle(fg, units, pairs, True)
+    assert seen == {0} and n_attached == len(pairs)
 
 
 def test_duplex_known_answers(fg):

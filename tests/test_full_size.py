@@ -242,6 +242,29 @@ def test_config3_duplex_5m_molecules(fg):
         assert st == 0 and n == L
         assert np.array_equal(gb[k][:n], rb[:n]) and np.array_equal(gq[k][:n], rq[:n])
         assert np.array_equal(ge[k][:n].view(np.uint16), re_[:n])
+    # the combine in the vote kernels' epilogue (fgb_plan_tiles_jobs + fgb_vote_duplex_device): every called position
+    # of all 10 M jobs, and the SS columns, equal the two-kernel form's; every job ran in the epilogue
+    tiles, class_tiles, tile_jobs, job_index, n_attached = fg.plan_tiles_jobs(tb.host, jobs)
+    assert n_attached == 2 * M
+    t8 = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(DEV)
+    tbf = synth.TorchBatch(tb.bases, tb.quals, tb.reads, tb.units, t8(tiles), tb.host, class_tiles)
+    tbf.n_tiles = len(tiles)
+    d_tj, d_ji = t8(tile_jobs), t8(job_index)
+    ss2 = fg.DeviceColumns(tb.host.n_out, DEV)
+    f_base = torch.zeros_like(o_base); f_qual = torch.zeros_like(o_qual); f_err = torch.zeros_like(o_err)
+    f_st = torch.full((2 * M,), 77, dtype=torch.uint8, device=DEV)
+    eng.stats_reset()
+    eng.vote_duplex_device(tbf, ss2, tj, 2 * M, d_tj, d_ji, f_base, f_qual, f_err, f_st,
+                           torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    s2 = eng.stats()
+    assert s2["combined_jobs"] == 2 * M and s2["units"] == U and int(f_st.max()) == 0
+    valid = lambda x: x.reshape(-1, Lo)[:, :L]
+    for got, want in ((f_base, o_base), (f_qual, o_qual), (f_err, o_err), (ss2.base[:U * Lo], ss.base[:U * Lo]),
+                      (ss2.qual[:U * Lo], ss.qual[:U * Lo]), (ss2.depth[:U * Lo], ss.depth[:U * Lo]),
+                      (ss2.errors[:U * Lo], ss.errors[:U * Lo])):
+        assert torch.equal(valid(got), valid(want))
+    del ss2, f_base, f_qual, f_err, tbf
     # ... and EVERY job of a contiguous run inside the slice the vote check compared in full (the oracle's own SS
     # columns for those units are at hand): up to 20 000 jobs, all three columns, every position
     u0, u1, spb, (sb_, sq_, sd_, se_, scl) = (_LAST_SLICE[k] for k in ("u0", "u1", "pb", "cols"))
