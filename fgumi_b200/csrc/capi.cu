@@ -568,7 +568,9 @@ fgb_status launch_filter(fgb_handle* h, const fgb_unit* units, uint64_t u0, uint
   return FGB_OK;
 }
 
-fgb_status launch_unpack_bam4(fgb_handle* h, Bam4Args a, cudaStream_t s) {
+// `padded`: both columns may be read up to the next multiple of 4 bytes past the resident range (the submit path's
+// staging buffers; a caller's columns whose sizes are multiples of 4).
+fgb_status launch_unpack_bam4(fgb_handle* h, Bam4Args a, cudaStream_t s, bool padded) {
   const uint64_t n = a.read_end - a.read_begin;
   if (n == 0) return FGB_OK;
   if (!h->d_bad) {
@@ -577,8 +579,14 @@ fgb_status launch_unpack_bam4(fgb_handle* h, Bam4Args a, cudaStream_t s) {
   }
   a.bad = h->d_bad;
   h->bam4_pending = true;
-  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + 7u) / 8u, static_cast<uint64_t>(h->sm_count) * 16u));
-  unpack_bam4_kernel<<<grid, 256, 0, s>>>(a);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(a.seq4 + (a.raw_lo >> 1)) | reinterpret_cast<uintptr_t>(a.quals_raw + a.raw_lo)) & 3u) == 0;
+  if (padded && aligned) {       // flat (read, word) items; window loads guarded to the resident range
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + kRowChunk - 1) / kRowChunk, static_cast<uint64_t>(h->sm_count) * 8u));
+    unpack_bam4_words_kernel<<<grid, 256, 0, s>>>(a);
+  } else {                       // one warp per read, byte loads: any alignment, touches nothing but the spans
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + 7u) / 8u, static_cast<uint64_t>(h->sm_count) * 16u));
+    unpack_bam4_kernel<<<grid, 256, 0, s>>>(a);
+  }
   h->launches++;
   FGB_CUDA(h, cudaGetLastError());
   return FGB_OK;
@@ -593,7 +601,7 @@ fgb_status launch_unpack_records(fgb_handle* h, RecordsArgs a, cudaStream_t s) {
   }
   a.bad = h->d_bad;
   h->bam4_pending = true;
-  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + 7u) / 8u, static_cast<uint64_t>(h->sm_count) * 16u));
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n + kRowChunk - 1) / kRowChunk, static_cast<uint64_t>(h->sm_count) * 8u));
   unpack_records_kernel<<<grid, 256, 0, s>>>(a);
   h->launches++;
   FGB_CUDA(h, cudaGetLastError());
@@ -827,7 +835,7 @@ fgb_status submit_impl(fgb_handle* h, const fgb_batch* in, const fgb_columns* ou
       ua.raw_lo = a0;
       ua.raw_hi = raw->raw_reads[r1 - 1].src_off + raw->raw_reads[r1 - 1].raw_len;
       ua.min_q = raw->min_input_base_quality;
-      if ((st = launch_unpack_bam4(h, ua, s)) != FGB_OK) return st;
+      if ((st = launch_unpack_bam4(h, ua, s, true)) != FGB_OK) return st;
     }
     if (fmt == HostFormat::kRecords && r1 > first.read_begin) {
       // blob byte range this chunk's reads touch (a group's records are contiguous, its reads are not in
@@ -1057,7 +1065,8 @@ fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_
   ua.read_begin = 0; ua.read_end = in->n_reads;
   ua.raw_lo = 0; ua.raw_hi = raw->n_raw;
   ua.min_q = raw->min_input_base_quality;
-  return launch_unpack_bam4(h, ua, static_cast<cudaStream_t>(stream));
+  return launch_unpack_bam4(h, ua, static_cast<cudaStream_t>(stream),
+                            ((raw->n_raw + 1u) / 2u) % 4u == 0 && raw->n_raw % 4u == 0);
 }
 
 fgb_status fgb_unpack_records_device(fgb_handle* h, const fgb_batch* in, const fgb_record_columns* rec,

@@ -152,109 +152,203 @@ struct RecordsArgs {
   uint32_t min_q;                  // min_input_base_quality (0 = no masking)
 };
 
-// 4 bytes at an arbitrary address through two aligned loads (the blob allocation is padded on both sides)
-__device__ __forceinline__ uint32_t ldg_u32_unaligned(const uint8_t* p) {
+// ---- the row builder shared by RECORDS and BAM4: flat (read, word) items over chunks of reads ----------------
+// One warp per read left 13 of 32 lanes idle on a 150-base row (19 words) and walked the reads one at a time.  Here a
+// CTA takes kRowChunk consecutive reads, 64 threads fetch and check their descriptors, a prefix sum of the rows' word
+// counts goes to shared memory and the 256 threads take 8-position words from ONE flat index (6-step search).
+constexpr uint32_t kRowChunk = 64;
+
+struct RowSrc {                    // one read of the chunk, as the word builder needs it
+  const uint8_t* seq;              // packed sequence, high nibble first (raw-bam sequence.rs:9-35)
+  const uint8_t* qual;             // raw qualities
+  uint64_t off;                    // row offset in the byte columns
+  uint32_t L;                      // raw bases in the record
+  uint32_t len_rev;                // row length | reverse strand << 31
+};
+
+// 4 / 8 bytes at an arbitrary address through aligned 32-bit loads; with Guard, words outside [lo, hi) (4-aligned
+// byte addresses: the resident part of a transfer column) read as zero instead of being touched.
+template <bool Guard>
+__device__ __forceinline__ uint32_t ldg_word(const uint32_t* w, const uintptr_t lo, const uintptr_t hi) {
+  if (Guard && reinterpret_cast<uintptr_t>(w) - lo >= hi - lo) return 0u;
+  return __ldg(w);
+}
+template <bool Guard>
+__device__ __forceinline__ uint32_t ldg_u32_at(const uint8_t* p, const uintptr_t lo, const uintptr_t hi) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
-  return __funnelshift_r(__ldg(w), __ldg(w + 1), static_cast<uint32_t>(a & 3u) * 8u);
+  return __funnelshift_r(ldg_word<Guard>(w, lo, hi), ldg_word<Guard>(w + 1, lo, hi), static_cast<uint32_t>(a & 3u) * 8u);
 }
-__device__ __forceinline__ uint2 ldg_u64_unaligned(const uint8_t* p) {
+template <bool Guard>
+__device__ __forceinline__ uint2 ldg_u64_at(const uint8_t* p, const uintptr_t lo, const uintptr_t hi) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~static_cast<uintptr_t>(3));
   const uint32_t sh = static_cast<uint32_t>(a & 3u) * 8u;
-  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+  const uint32_t w0 = ldg_word<Guard>(w, lo, hi), w1 = ldg_word<Guard>(w + 1, lo, hi), w2 = ldg_word<Guard>(w + 2, lo, hi);
   return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
 
-// One warp per read, lanes over the row's 8-position words.
-__global__ void __launch_bounds__(256) unpack_records_kernel(const RecordsArgs a) {
+// Word w (row positions 8w .. 8w+7) of one source-read row: the per-base part of create_source_read
+// (vanilla_caller.rs:893-916).  lut_f / lut_r: one packed byte -> two ASCII bytes in row order (reverse: complemented).
+template <bool Guard>
+__device__ __forceinline__ void build_row_word(const RowSrc& r, const uint32_t w, const uint16_t* lut_f,
+                                               const uint16_t* lut_r, const uint32_t min_q,
+                                               const uintptr_t s_lo, const uintptr_t s_hi, const uintptr_t q_lo_b,
+                                               const uintptr_t q_hi_b, uint2* ob, uint2* oq) {
+  const uint32_t len = r.len_rev & 0x7FFFFFFFu;
+  const bool rev = (r.len_rev >> 31) != 0u;
+  uint32_t x, q_lo, q_hi;
+  if (!rev) {
+    x = ldg_u32_at<Guard>(r.seq + 4u * w, s_lo, s_hi);       // byte k = bases 8w+2k (high nibble), 8w+2k+1
+    const uint2 q = ldg_u64_at<Guard>(r.qual + 8u * w, q_lo_b, q_hi_b);
+    q_lo = q.x; q_hi = q.y;
+  } else {
+    // row positions 8w+j <- raw bases e-j, e = L-1-8w: the eight nibbles ending at raw index e, as a 32-bit
+    // value whose nibble j (from the least significant end) is raw base e-j
+    const int32_t e = static_cast<int32_t>(r.L) - 1 - static_cast<int32_t>(8u * w);
+    const int32_t first = e - 7;                              // may be negative on the row's last word
+    const int32_t s0 = first >> 1;                            // floor: byte holding raw base `first`
+    const uint2 v = ldg_u64_at<Guard>(r.seq + s0, s_lo, s_hi);   // bytes s0 .. s0+7, little endian
+    const uint64_t be = (static_cast<uint64_t>(__byte_perm(v.x, 0u, 0x0123u)) << 8) | (v.y & 0xFFu);   // bytes s0 .. s0+4, big endian
+    const uint32_t t0 = static_cast<uint32_t>(first - 2 * s0);   // 0 or 1
+    x = static_cast<uint32_t>(be >> (4u * (2u - t0)));
+    const uint2 q = ldg_u64_at<Guard>(r.qual + first, q_lo_b, q_hi_b);   // raw qualities first .. e
+    q_lo = __byte_perm(q.y, 0u, 0x0123u);                     // reversed: position j <- raw e - j
+    q_hi = __byte_perm(q.x, 0u, 0x0123u);
+  }
+  const uint16_t* lut = rev ? lut_r : lut_f;
+  uint32_t b_lo = static_cast<uint32_t>(lut[x & 0xFFu]) | (static_cast<uint32_t>(lut[(x >> 8) & 0xFFu]) << 16);
+  uint32_t b_hi = static_cast<uint32_t>(lut[(x >> 16) & 0xFFu]) | (static_cast<uint32_t>(lut[x >> 24]) << 16);
+  if (min_q) {                                                // vanilla_caller.rs:908-916
+    uint32_t ok_lo, ok_hi;
+    if (min_q <= 127u) {
+      const uint32_t ts = min_q * 0x01010101u;                // high bit survives iff (q & 0x7F) >= t; q >= 128 passes outright
+      ok_lo = (((q_lo | 0x80808080u) - ts) | q_lo) & 0x80808080u;
+      ok_hi = (((q_hi | 0x80808080u) - ts) | q_hi) & 0x80808080u;
+    } else {
+      ok_lo = ok_hi = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ok_lo |= (((q_lo >> (8 * j)) & 0xFFu) >= min_q) ? (0x80u << (8 * j)) : 0u;
+        ok_hi |= (((q_hi >> (8 * j)) & 0xFFu) >= min_q) ? (0x80u << (8 * j)) : 0u;
+      }
+    }
+    const uint32_t m_lo = spread_msb(ok_lo ^ 0x80808080u);    // 0xFF where the base is masked
+    const uint32_t m_hi = spread_msb(ok_hi ^ 0x80808080u);
+    b_lo = (b_lo & ~m_lo) | (0x4E4E4E4Eu & m_lo); q_lo = (q_lo & ~m_lo) | (0x02020202u & m_lo);
+    b_hi = (b_hi & ~m_hi) | (0x4E4E4E4Eu & m_hi); q_hi = (q_hi & ~m_hi) | (0x02020202u & m_hi);
+  }
+  const uint32_t live = len - 8u * w;                         // positions of this word inside the row (>= 1)
+  if (live < 8u) {                                            // zero the row padding
+    const uint32_t k_lo = live >= 4u ? 0xFFFFFFFFu : ((1u << (8u * live)) - 1u);
+    const uint32_t k_hi = live <= 4u ? 0u : ((1u << (8u * (live - 4u))) - 1u);
+    b_lo &= k_lo; q_lo &= k_lo; b_hi &= k_hi; q_hi &= k_hi;
+  }
+  *ob = make_uint2(b_lo, b_hi);
+  *oq = make_uint2(q_lo, q_hi);
+}
+
+__device__ __forceinline__ void fill_pair_luts(uint16_t* lut_f, uint16_t* lut_r) {
   // pair tables: one packed byte (two bases) -> two ASCII bytes; forward: (high, low) nibble in row order,
   // reverse: (low, high) nibble complemented ("=ACMGRSVTWYHKDBN", A<->T, C<->G; fgumi-dna dna.rs:30-60)
+  const char* f = "=ACMGRSVTWYHKDBN";
+  const char* c = "=TGMCRSVAWYHKDBN";
+  const uint32_t b = threadIdx.x;
+  lut_f[b] = static_cast<uint16_t>(static_cast<uint8_t>(f[b >> 4]) | (static_cast<uint32_t>(static_cast<uint8_t>(f[b & 15])) << 8));
+  lut_r[b] = static_cast<uint16_t>(static_cast<uint8_t>(c[b & 15]) | (static_cast<uint32_t>(static_cast<uint8_t>(c[b >> 4])) << 8));
+}
+
+// The chunk loop.  Describe(r, &src) fills the RowSrc of absolute read r and returns false when its spans break the
+// layout rules (the read is skipped and *bad set).
+template <bool Guard, class Describe>
+__device__ __forceinline__ void unpack_rows(const uint64_t read_begin, const uint64_t read_end, uint8_t* bases,
+                                            uint8_t* quals, const uint32_t min_q, uint32_t* bad, const uintptr_t s_lo,
+                                            const uintptr_t s_hi, const uintptr_t q_lo, const uintptr_t q_hi,
+                                            Describe&& describe) {
   __shared__ uint16_t lut_f[256], lut_r[256];
-  {
-    const char* f = "=ACMGRSVTWYHKDBN";
-    const char* c = "=TGMCRSVAWYHKDBN";
-    const uint32_t b = threadIdx.x;
-    lut_f[b] = static_cast<uint16_t>(static_cast<uint8_t>(f[b >> 4]) | (static_cast<uint32_t>(static_cast<uint8_t>(f[b & 15])) << 8));
-    lut_r[b] = static_cast<uint16_t>(static_cast<uint8_t>(c[b & 15]) | (static_cast<uint32_t>(static_cast<uint8_t>(c[b >> 4])) << 8));
+  __shared__ RowSrc s_src[kRowChunk];
+  __shared__ uint32_t s_pref[kRowChunk + 1];
+  __shared__ uint32_t s_half;
+  fill_pair_luts(lut_f, lut_r);
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const uint64_t n = read_end - read_begin;
+  const uint64_t chunks = (n + kRowChunk - 1) / kRowChunk;
+  for (uint64_t c = blockIdx.x; c < chunks; c += gridDim.x) {
+    __syncthreads();                                          // the tables are filled / the last chunk's items are done
+    const uint64_t r0 = read_begin + c * kRowChunk;
+    const uint32_t nr = static_cast<uint32_t>(read_end - r0 < kRowChunk ? read_end - r0 : kRowChunk);
+    if (tid < kRowChunk) {
+      uint32_t items = 0;
+      if (tid < nr) {
+        RowSrc src;
+        if (describe(r0 + tid, &src)) items = ((src.len_rev & 0x7FFFFFFFu) + 7u) >> 3;
+        else atomicOr(bad, 1u);
+        s_src[tid] = src;
+      }
+      uint32_t incl = items;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= static_cast<uint32_t>(off)) incl += v;
+      }
+      if (tid == 31u) s_half = incl;
+      s_pref[tid + 1] = incl;                                 // the second warp's entries get s_half added below
+    }
+    __syncthreads();
+    if (tid >= 32u && tid < kRowChunk) s_pref[tid + 1] += s_half;
+    if (tid == 0) s_pref[0] = 0u;
+    __syncthreads();
+    const uint32_t total = s_pref[kRowChunk];
+    for (uint32_t it = tid; it < total; it += blockDim.x) {
+      uint32_t rl = 0;                                        // last read with s_pref[rl] <= it
+#pragma unroll
+      for (uint32_t step = kRowChunk / 2; step > 0; step >>= 1)
+        if (s_pref[rl + step] <= it) rl += step;
+      const uint32_t w = it - s_pref[rl];
+      uint2 ob, oq;
+      build_row_word<Guard>(s_src[rl], w, lut_f, lut_r, min_q, s_lo, s_hi, q_lo, q_hi, &ob, &oq);
+      const uint64_t o = s_src[rl].off + w * 8u;
+      *reinterpret_cast<uint2*>(bases + o) = ob;
+      *reinterpret_cast<uint2*>(quals + o) = oq;
+    }
   }
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint64_t warps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
-  const uint32_t tq = a.min_q > 127u ? 127u : a.min_q;     // SWAR compare handles thresholds up to 127
-  const bool wide_q = a.min_q > 127u;
-  for (uint64_t r = a.read_begin + ((static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
-       r < a.read_end; r += warps) {
+}
+
+__global__ void __launch_bounds__(256) unpack_records_kernel(const RecordsArgs a) {
+  unpack_rows<false>(a.read_begin, a.read_end, a.bases, a.quals, a.min_q, a.bad, 0, 0, 0, 0,
+                     [&](uint64_t r, RowSrc* s) {
     const fgb_raw_read rr = a.raw_reads[r];
     const uint64_t d = a.reads[r];
     const uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
-    const uint64_t off = d >> 16;
     const uint32_t L = rr.raw_len;
     const uint64_t qoff = rr.src_off + ((static_cast<uint64_t>(L) + 1u) >> 1);
+    s->seq = a.records + rr.src_off; s->qual = a.records + qoff; s->off = d >> 16; s->L = L;
+    s->len_rev = len | ((rr.flags & 1u) << 31);
     // the sequence and quality fields must lie inside the resident blob (with 16 bytes of slack either side
     // for the aligned window loads), and the row cannot be longer than the record's sequence
-    if (rr.src_off < a.rec_lo + 16u || qoff + L + 16u > a.rec_hi || len > L) {
-      if (lane == 0) atomicOr(a.bad, 1u);
-      continue;
-    }
-    const bool rev = rr.flags & 1u;
-    const uint8_t* seq = a.records + rr.src_off;
-    const uint8_t* qual = a.records + qoff;
-    const uint32_t words = (len + 7u) >> 3;
-    for (uint32_t w = lane; w < words; w += 32u) {
-      uint32_t x, q_lo, q_hi;
-      if (!rev) {
-        x = ldg_u32_unaligned(seq + 4u * w);                 // byte k = bases 8w+2k (high nibble), 8w+2k+1
-        const uint2 q = ldg_u64_unaligned(qual + 8u * w);
-        q_lo = q.x; q_hi = q.y;
-      } else {
-        // row positions 8w+j <- raw bases e-j, e = L-1-8w: the eight nibbles ending at raw index e, as a
-        // 32-bit value whose nibble j (from the least significant end) is raw base e-j
-        const int32_t e = static_cast<int32_t>(L) - 1 - static_cast<int32_t>(8u * w);
-        const int32_t first = e - 7;                          // may be negative on the row's last word
-        const int32_t s0 = first >> 1;                        // floor: byte holding raw base `first`
-        const uint8_t* p = seq + s0;
-        const uint64_t be = (static_cast<uint64_t>(__ldg(p)) << 32) | (static_cast<uint64_t>(__ldg(p + 1)) << 24) |
-                            (static_cast<uint64_t>(__ldg(p + 2)) << 16) | (static_cast<uint64_t>(__ldg(p + 3)) << 8) |
-                            static_cast<uint64_t>(__ldg(p + 4));
-        const uint32_t t0 = static_cast<uint32_t>(first - 2 * s0);   // 0 or 1
-        x = static_cast<uint32_t>(be >> (4u * (2u - t0)));
-        const uint2 q = ldg_u64_unaligned(qual + first);      // raw qualities first .. e
-        q_lo = __byte_perm(q.y, 0u, 0x0123u);                 // reversed: position j <- raw e - j
-        q_hi = __byte_perm(q.x, 0u, 0x0123u);
-      }
-      const uint16_t* lut = rev ? lut_r : lut_f;
-      uint32_t b_lo = static_cast<uint32_t>(lut[x & 0xFFu]) | (static_cast<uint32_t>(lut[(x >> 8) & 0xFFu]) << 16);
-      uint32_t b_hi = static_cast<uint32_t>(lut[(x >> 16) & 0xFFu]) | (static_cast<uint32_t>(lut[x >> 24]) << 16);
-      if (a.min_q) {                                          // vanilla_caller.rs:908-916
-        uint32_t ok_lo, ok_hi;
-        if (!wide_q) {
-          const uint32_t ts = tq * 0x01010101u;               // high bit survives iff (q & 0x7F) >= t; q >= 128 passes outright
-          ok_lo = (((q_lo | 0x80808080u) - ts) | q_lo) & 0x80808080u;
-          ok_hi = (((q_hi | 0x80808080u) - ts) | q_hi) & 0x80808080u;
-        } else {
-          ok_lo = ok_hi = 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ok_lo |= (((q_lo >> (8 * j)) & 0xFFu) >= a.min_q) ? (0x80u << (8 * j)) : 0u;
-            ok_hi |= (((q_hi >> (8 * j)) & 0xFFu) >= a.min_q) ? (0x80u << (8 * j)) : 0u;
-          }
-        }
-        const uint32_t m_lo = spread_msb(ok_lo ^ 0x80808080u);   // 0xFF where the base is masked
-        const uint32_t m_hi = spread_msb(ok_hi ^ 0x80808080u);
-        b_lo = (b_lo & ~m_lo) | (0x4E4E4E4Eu & m_lo); q_lo = (q_lo & ~m_lo) | (0x02020202u & m_lo);
-        b_hi = (b_hi & ~m_hi) | (0x4E4E4E4Eu & m_hi); q_hi = (q_hi & ~m_hi) | (0x02020202u & m_hi);
-      }
-      const uint32_t live = len - 8u * w;                     // positions of this word inside the row (>= 1)
-      if (live < 8u) {                                        // zero the row padding
-        const uint32_t k_lo = live >= 4u ? 0xFFFFFFFFu : ((1u << (8u * live)) - 1u);
-        const uint32_t k_hi = live <= 4u ? 0u : ((1u << (8u * (live - 4u))) - 1u);
-        b_lo &= k_lo; q_lo &= k_lo; b_hi &= k_hi; q_hi &= k_hi;
-      }
-      *reinterpret_cast<uint2*>(a.bases + off + w * 8u) = make_uint2(b_lo, b_hi);
-      *reinterpret_cast<uint2*>(a.quals + off + w * 8u) = make_uint2(q_lo, q_hi);
-    }
-  }
+    return !(rr.src_off < a.rec_lo + 16u || qoff + L + 16u > a.rec_hi || len > L);
+  });
+}
+
+// BAM4 through the same builder: the packed sequence and the raw qualities come in two columns (nibble i of the batch
+// in seq4[i >> 1], high nibble first; a read's span starts on an even nibble), so a read looks exactly like a record's
+// sequence / quality fields.  The window loads are guarded: nothing outside the resident part of the columns is
+// touched (4-byte granularity; fgb_raw_columns asks for columns padded to a multiple of 4 bytes).
+__global__ void __launch_bounds__(256) unpack_bam4_words_kernel(const Bam4Args a) {
+  const uintptr_t s_lo = reinterpret_cast<uintptr_t>(a.seq4 + (a.raw_lo >> 1)) & ~static_cast<uintptr_t>(3);
+  const uintptr_t s_hi = (reinterpret_cast<uintptr_t>(a.seq4 + ((a.raw_hi + 1u) >> 1)) + 3u) & ~static_cast<uintptr_t>(3);
+  const uintptr_t q_lo = reinterpret_cast<uintptr_t>(a.quals_raw + a.raw_lo) & ~static_cast<uintptr_t>(3);
+  const uintptr_t q_hi = (reinterpret_cast<uintptr_t>(a.quals_raw + a.raw_hi) + 3u) & ~static_cast<uintptr_t>(3);
+  unpack_rows<true>(a.read_begin, a.read_end, a.bases, a.quals, a.min_q, a.bad, s_lo, s_hi, q_lo, q_hi,
+                    [&](uint64_t r, RowSrc* s) {
+    const fgb_raw_read rr = a.raw_reads[r];
+    const uint64_t d = a.reads[r];
+    const uint32_t len = static_cast<uint32_t>(d & 0xFFFFu);
+    s->seq = a.seq4 + (rr.src_off >> 1); s->qual = a.quals_raw + rr.src_off; s->off = d >> 16; s->L = rr.raw_len;
+    s->len_rev = len | ((rr.flags & 1u) << 31);
+    // layout rules of fgb_raw_columns, checked where the data is touched (no host pass over the reads)
+    return !((rr.src_off & 1u) || rr.src_off < a.raw_lo || rr.src_off + rr.raw_len > a.raw_hi || len > rr.raw_len);
+  });
 }
 
 }  // namespace fgb

@@ -453,7 +453,9 @@ fgb_status fgb_filter_simplex_device(fgb_handle* h, const fgb_batch* in, const f
                                      uint32_t* unit_masked, void* stream);
 
 /* Device-resident variant of the unpack step alone (multi-kernel flows, tests): all pointers of
- * `in`, `raw` and the row columns are device pointers; enqueues one kernel on `stream`. */
+ * `in`, `raw` and the row columns are device pointers; enqueues one kernel on `stream`.  Columns that start on a
+ * 4-byte boundary and whose sizes ((n_raw + 1) / 2 and n_raw bytes) are multiples of 4 take the word kernel (aligned
+ * 32-bit window loads, nothing outside the columns is read); any other shape takes a byte-load kernel. */
 fgb_status fgb_unpack_bam4_device(fgb_handle* h, const fgb_batch* in, const fgb_raw_columns* raw,
                                   uint8_t* bases, uint8_t* quals, void* stream);
 fgb_status fgb_wait(fgb_handle* h);

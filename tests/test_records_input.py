@@ -100,6 +100,68 @@ def test_unpack_records_kernel_matches_the_per_base_rule(fg, min_q):
     eng.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("padded", [True, False])
+@pytest.mark.parametrize("min_q", [0, 10])
+def test_unpack_bam4_device_both_kernels(fg, padded, min_q):
+    """fgb_unpack_bam4_device on spans that start on arbitrary even nibbles: columns whose sizes are multiples of 4
+    take the flat word kernel (guarded window loads), any other size the byte-load kernel; both against the per-base
+    rule.  Guard bytes around the columns must stay untouched-looking: the kernels never need them."""
+    import torch
+    rng = np.random.default_rng(21 + min_q)
+    _, rows = _random_records(rng, 600)
+    code = {c: i for i, c in enumerate(FWD)}
+    nibs, quals, raw_list, reads = [], [], [], []
+    off_raw, off_row = 0, 0
+    for (L, rev, fl, seq, q) in rows:
+        gap = 2 * int(rng.integers(0, 4))                     # spans start on any even raw index
+        nibs.append(np.zeros(gap, np.uint8)); quals.append(np.zeros(gap, np.uint8))
+        off_raw += gap
+        raw_list.append((off_raw, L, 1 if rev else 0))
+        nibs.append(np.array([code.get(int(b), 15) for b in seq], dtype=np.uint8)); quals.append(q)
+        off_raw += L
+        if off_raw % 2:
+            nibs.append(np.zeros(1, np.uint8)); quals.append(np.zeros(1, np.uint8)); off_raw += 1
+        reads.append((off_row << 16) | fl)
+        off_row += (fl + 7) // 8 * 8
+    want_mod = 0 if padded else 2
+    while off_raw % 8 != want_mod:                            # n_raw % 4 and ((n_raw + 1) / 2) % 4 both 0, or not
+        nibs.append(np.zeros(2, np.uint8)); quals.append(np.zeros(2, np.uint8)); off_raw += 2
+    nib = np.concatenate(nibs); allq = np.concatenate(quals)
+    assert nib.size == off_raw and off_raw % 2 == 0
+    seq4 = ((nib[0::2] << 4) | nib[1::2]).astype(np.uint8)
+    R = len(rows)
+    raw = np.zeros(R, dtype=fg.RAW_READ_DTYPE)
+    for r, (o, L, f) in enumerate(raw_list):
+        raw[r] = (o, L, f)
+    rd = np.zeros(R + 2, dtype=np.uint64); rd[:R] = reads
+    dev = "cuda:0"
+    d_seq = torch.from_numpy(seq4.copy()).to(dev)
+    d_q = torch.from_numpy(allq.copy()).to(dev)
+    d_raw = torch.from_numpy(raw.view(np.uint8).reshape(-1).copy()).to(dev)
+    d_reads = torch.from_numpy(rd.view(np.uint8).copy()).to(dev)
+    d_b = torch.full((off_row + 64,), 0xAA, dtype=torch.uint8, device=dev)
+    d_qo = torch.full((off_row + 64,), 0xAA, dtype=torch.uint8, device=dev)
+    eng = fg.Engine(0, 45, 40, 1, 2)
+    lib = fg.lib.load()
+    batch = fg.lib.FgbBatch(0, R, off_row, 0, 0, None, None, d_reads.data_ptr(), None, None)
+    rc = fg.lib.FgbRawColumns(off_raw, d_seq.data_ptr(), d_q.data_ptr(), d_raw.data_ptr(), min_q)
+    st = lib.fgb_unpack_bam4_device(eng._h, C.byref(batch), C.byref(rc), C.c_void_p(d_b.data_ptr()),
+                                    C.c_void_p(d_qo.data_ptr()), None)
+    assert st == 0
+    torch.cuda.synchronize()
+    assert lib.fgb_wait(eng._h) == 0
+    hb, hq = d_b.cpu().numpy(), d_qo.cpu().numpy()
+    off = 0
+    for r, (L, rev, fl, seq, q) in enumerate(rows):
+        eb, eq = _expected_row(L, rev, fl, seq, q, min_q)
+        assert np.array_equal(hb[off:off + fl], eb), (r, L, rev, fl)
+        assert np.array_equal(hq[off:off + fl], eq), (r, L, rev, fl)
+        off += (fl + 7) // 8 * 8
+    assert (hb[off:] == 0xAA).all() and (hq[off:] == 0xAA).all()       # nothing written past the last row
+    eng.close()
+
+
 def _cpu_caller(n_threads=4):
     """The product's host code over the CPU oracle's vote (test infrastructure, oracle/Makefile)."""
     from fgumi_b200 import benchlegs
