@@ -9,8 +9,14 @@ namespace fgb {
 constexpr int kConsumerWarps = 8;
 constexpr int kVoteThreads = kConsumerWarps * 32;        // threads that vote
 constexpr int kThreads = kVoteThreads + 32;              // + one TMA producer warp
-constexpr int kStages = 2;
-constexpr uint32_t kTileCapBytes = 20480;  // per column per stage
+#ifndef FGB_STAGES
+#define FGB_STAGES 2
+#endif
+#ifndef FGB_TILE_CAP
+#define FGB_TILE_CAP 20480
+#endif
+constexpr int kStages = FGB_STAGES;
+constexpr uint32_t kTileCapBytes = FGB_TILE_CAP;  // per column per stage (multiple of 16)
 constexpr uint32_t kTileMaxReads = 512;    // read descriptors per stage (8 B each)
 constexpr uint32_t kTileMaxUnits = 127;    // unit descriptors per stage (16 B each, +1 sentinel)
 #ifndef FGB_WARP_QUEUE_CAP
