@@ -320,7 +320,12 @@ __global__ void __launch_bounds__(kCombineThreads) duplex_combine_kernel(const D
 // the pooled source rows once per warp instead of once per 8 positions of work).  Pass 1 reads the depth words and
 // settles each job's arm (:852-882) in shared memory; pass 2 combines the both-strand jobs (:912-951); the rare
 // single-strand arms and the layouts the word path does not take are redone by duplex_job_warp.
-constexpr int kDuplexChunk = 32;
+#ifndef FGB_DUPLEX_CHUNK
+#define FGB_DUPLEX_CHUNK 256   // measured on B200 (10 M jobs): 32 -> 7.94 ms, 64 -> 6.99, 128 -> 6.76, 256 -> 6.58
+#endif
+constexpr int kDuplexDescCache = 8;          // row descriptors of a job kept in shared memory (4 + 4 reads per strand fit)
+constexpr int kDuplexChunk = FGB_DUPLEX_CHUNK;     // 32, 64, 128 or 256: jobs whose descriptors are fetched in one round
+static_assert(kDuplexChunk >= 32 && kDuplexChunk <= kCombineThreads && (kDuplexChunk & (kDuplexChunk - 1)) == 0, "chunk size");
 
 struct DuplexJobSm {
   unsigned long long out_off, a_off, b_off;
@@ -342,10 +347,12 @@ __device__ __forceinline__ uint32_t chunk_job_of(const uint32_t* pref, uint32_t 
 // (vote_kernel.cuh duplex_epilogue) and are left alone; a chunk without pending jobs costs one byte load per job.
 template <bool SkipDone>
 __device__ __forceinline__ void duplex_combine_words_chunk(const DuplexArgs& a, const uint64_t j0, DuplexJobSm* sj,
-                                                           uint32_t* s_pref, uint32_t* s_any) {
+                                                           uint32_t* s_pref, uint32_t* s_any,
+                                                           uint64_t (*s_desc)[kDuplexDescCache]) {
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint32_t nj = static_cast<uint32_t>(a.n_jobs - j0 < kDuplexChunk ? a.n_jobs - j0 : kDuplexChunk);
-  if (tid < 32u) {
+  __shared__ uint32_t s_wsum[kDuplexChunk / 32];
+  if (tid < kDuplexChunk) {
     uint32_t items = 0;
     bool is_new = false;
     if (tid < nj) {
@@ -361,6 +368,12 @@ __device__ __forceinline__ void duplex_combine_words_chunk(const DuplexArgs& a, 
         s.general = (((r.job.out_off | r.ua.out_off | r.ub.out_off) & 7ull) != 0ull ||
                      static_cast<unsigned long long>(s.na) + s.nb > 255ull) ? 1u : 0u;
         items = s.general ? 0u : (s.len + 7u) >> 3;
+        if (!s.general) {        // the pooled rows' descriptors (AB rows then BA rows): pass 2 then asks for a word's
+          const uint32_t nr = s.na + s.nb;     // SS words and source rows in one round of loads
+#pragma unroll
+          for (uint32_t k = 0; k < static_cast<uint32_t>(kDuplexDescCache); ++k)
+            if (k < nr) s_desc[tid][k] = __ldg(a.reads + (k < s.na ? s.ra0 + k : s.rb0 + (k - s.na)));
+        }
       } else {
         s.out_off = s.a_off = s.b_off = 0ull; s.len = s.ra0 = s.na = s.rb0 = s.nb = 0u;
       }
@@ -374,13 +387,20 @@ __device__ __forceinline__ void duplex_combine_words_chunk(const DuplexArgs& a, 
       const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
       if (lane >= static_cast<uint32_t>(off)) incl += v;
     }
-    s_pref[tid + 1] = incl;
+    s_pref[tid + 1] = incl;                            // within the warp; the warps in front are added below
+    if (lane == 31u) s_wsum[tid >> 5] = incl;
     const uint32_t n_new = __popc(__ballot_sync(0xFFFFFFFFu, is_new));
-    if (tid == 0) {
-      s_pref[0] = 0u;
-      if (n_new) atomicAdd(a.counters + FGB_CTR_COMBINED, static_cast<unsigned long long>(n_new));
+    if (lane == 0 && n_new) atomicAdd(a.counters + FGB_CTR_COMBINED, static_cast<unsigned long long>(n_new));
+  }
+  __syncthreads();
+  if (kDuplexChunk > 32) {
+    if (tid >= 32u && tid < kDuplexChunk) {
+      uint32_t add = 0;
+      for (uint32_t w = 0; w < (tid >> 5); ++w) add += s_wsum[w];
+      s_pref[tid + 1] += add;
     }
   }
+  if (tid == 0) s_pref[0] = 0u;
   __syncthreads();
   const uint32_t total = s_pref[kDuplexChunk];
   // ---- pass 1: which strands have coverage inside the truncated region (:852-853) ----
@@ -430,7 +450,8 @@ __device__ __forceinline__ void duplex_combine_words_chunk(const DuplexArgs& a, 
 #pragma unroll
       for (uint32_t k = 0; k < 4u; ++k) {
         const uint32_t r = r0 + k;
-        d[k] = r < nr ? __ldg(a.reads + (r < s.na ? s.ra0 + r : s.rb0 + (r - s.na))) : 0ull;
+        d[k] = r < nr ? (r < static_cast<uint32_t>(kDuplexDescCache)
+                             ? s_desc[jl][r] : __ldg(a.reads + (r < s.na ? s.ra0 + r : s.rb0 + (r - s.na)))) : 0ull;
       }
 #pragma unroll
       for (uint32_t k = 0; k < 4u; ++k) {
@@ -462,7 +483,8 @@ __global__ void __launch_bounds__(kCombineThreads, 4) duplex_combine_words_kerne
   __shared__ DuplexJobSm sj[kDuplexChunk];
   __shared__ uint32_t s_pref[kDuplexChunk + 1];
   __shared__ uint32_t s_any[kDuplexChunk];
-  duplex_combine_words_chunk<false>(a, static_cast<uint64_t>(blockIdx.x) * kDuplexChunk, sj, s_pref, s_any);
+  __shared__ uint64_t s_desc[kDuplexChunk][kDuplexDescCache];
+  duplex_combine_words_chunk<false>(a, static_cast<uint64_t>(blockIdx.x) * kDuplexChunk, sj, s_pref, s_any, s_desc);
 }
 
 // After a vote with the duplex epilogue: a CTA looks at the status bytes of kCombineThreads jobs (eight chunks) and
@@ -471,25 +493,27 @@ __global__ void __launch_bounds__(kCombineThreads, 4) duplex_combine_pending_ker
   __shared__ DuplexJobSm sj[kDuplexChunk];
   __shared__ uint32_t s_pref[kDuplexChunk + 1];
   __shared__ uint32_t s_any[kDuplexChunk];
-  __shared__ uint32_t s_pending[kCombineThreads / kDuplexChunk];
+  __shared__ uint32_t s_pending[kCombineThreads / 32];
+  __shared__ uint64_t s_desc[kDuplexChunk][kDuplexDescCache];
   const uint64_t groups = (a.n_jobs + kCombineThreads - 1) / kCombineThreads;
   for (uint64_t g = blockIdx.x; g < groups; g += gridDim.x) {
     const uint64_t jg = g * kCombineThreads;
     const uint64_t j = jg + threadIdx.x;
     const bool pending = j < a.n_jobs && a.out_status[j] == FGB_DUPLEX_PENDING;
     const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pending);
-    if ((threadIdx.x & 31u) == 0u) s_pending[threadIdx.x >> 5] = ballot;     // kDuplexChunk == 32: one word per chunk
+    if ((threadIdx.x & 31u) == 0u) s_pending[threadIdx.x >> 5] = ballot;     // one word per 32 jobs
     __syncthreads();
     for (uint32_t c = 0; c < kCombineThreads / kDuplexChunk; ++c) {
       const uint64_t j0 = jg + static_cast<uint64_t>(c) * kDuplexChunk;
-      if (j0 >= a.n_jobs || s_pending[c] == 0u) continue;                    // CTA-uniform
-      duplex_combine_words_chunk<true>(a, j0, sj, s_pref, s_any);
+      uint32_t any = 0;
+      for (uint32_t w = 0; w < kDuplexChunk / 32; ++w) any |= s_pending[c * (kDuplexChunk / 32) + w];
+      if (j0 >= a.n_jobs || any == 0u) continue;                             // CTA-uniform
+      duplex_combine_words_chunk<true>(a, j0, sj, s_pref, s_any, s_desc);
       __syncthreads();                                                       // sj / s_pref / s_any are reused
     }
     __syncthreads();                                                         // s_pending is rewritten next round
   }
 }
-static_assert(kDuplexChunk == 32, "duplex_combine_pending_kernel keeps one ballot word per chunk");
 
 // ---- CODEC ------------------------------------------------------------------------------------
 struct CodecArgs {
@@ -664,7 +688,10 @@ __global__ void __launch_bounds__(kCombineThreads) codec_combine_kernel(const Co
 // The combine itself (:1029-1152) is byte-parallel on two 32-bit halves (bases, qualities) and four 2 x u16 words
 // (depths, errors).  Complementing both strands at once commutes with every comparison the rule makes as long as
 // all bases are A/C/G/T/N or the pad 'n'; a job with any other byte is redone by codec_job_scalar.
-constexpr int kCodecChunk = 32;
+#ifndef FGB_CODEC_CHUNK
+#define FGB_CODEC_CHUNK 256    // B200, 2 M jobs: 32 -> 2.62 ms, 128 / 256 -> 2.55 (issue-bound either way)
+#endif
+constexpr int kCodecChunk = FGB_CODEC_CHUNK;     // 32 .. 256 (power of two): units / jobs whose descriptors are fetched in one round
 
 struct CodecJobSm {
   unsigned long long out_off, a_off, b_off;
@@ -736,7 +763,8 @@ __global__ void __launch_bounds__(kCombineThreads) codec_combine_words_kernel(co
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint64_t j0 = static_cast<uint64_t>(blockIdx.x) * kCodecChunk;
   const uint32_t nj = static_cast<uint32_t>(a.n_jobs - j0 < kCodecChunk ? a.n_jobs - j0 : kCodecChunk);
-  if (tid < 32u) {
+  __shared__ uint32_t s_wsum[kCodecChunk / 32];
+  if (tid < static_cast<uint32_t>(kCodecChunk)) {
     uint32_t items = 0;
     if (tid < nj) {
       const fgb_codec_job job = a.jobs[j0 + tid];
@@ -764,9 +792,16 @@ __global__ void __launch_bounds__(kCombineThreads) codec_combine_words_kernel(co
       const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
       if (lane >= static_cast<uint32_t>(off)) incl += v;
     }
-    s_pref[tid + 1] = incl;
-    if (tid == 0) s_pref[0] = 0u;
+    s_pref[tid + 1] = incl;                            // within the warp; the warps in front are added below
+    if (lane == 31u) s_wsum[tid >> 5] = incl;
   }
+  __syncthreads();
+  if (kCodecChunk > 32 && tid >= 32u && tid < static_cast<uint32_t>(kCodecChunk)) {
+    uint32_t add = 0;
+    for (uint32_t w = 0; w < (tid >> 5); ++w) add += s_wsum[w];
+    s_pref[tid + 1] += add;
+  }
+  if (tid == 0) s_pref[0] = 0u;
   __syncthreads();
   const uint32_t total = s_pref[kCodecChunk];
   const int32_t oqual = a.cp.outer_bases_qual;
@@ -877,7 +912,7 @@ __global__ void __launch_bounds__(kCombineThreads) codec_combine_words_kernel(co
     }
   }
   __syncthreads();
-  if (tid < 32u) {
+  if (tid < static_cast<uint32_t>(kCodecChunk)) {
     unsigned long long tb = 0, td = 0;
     if (tid < nj) {
       const uint32_t n_dup = s_dup[tid], n_dis = s_dis[tid];
@@ -891,10 +926,10 @@ __global__ void __launch_bounds__(kCombineThreads) codec_combine_words_kernel(co
       tb += __shfl_xor_sync(0xFFFFFFFFu, tb, off);
       td += __shfl_xor_sync(0xFFFFFFFFu, td, off);
     }
-    if (tid == 0) {
+    if (lane == 0) {                         // one warp per 32 jobs of the chunk
       if (tb) atomicAdd(a.counters + FGB_CTR_DUPLEX_BASES, tb);
       if (td) atomicAdd(a.counters + FGB_CTR_DUPLEX_DISAGREE, td);
-      atomicAdd(a.counters + FGB_CTR_COMBINED, static_cast<unsigned long long>(nj));
+      if (tid == 0) atomicAdd(a.counters + FGB_CTR_COMBINED, static_cast<unsigned long long>(nj));
     }
   }
 }

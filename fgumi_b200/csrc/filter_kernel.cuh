@@ -117,7 +117,10 @@ __global__ void __launch_bounds__(256) filter_simplex_kernel(const FilterArgs a)
 // one flat index, so a 150-base unit (19 items) does not leave 13 lanes of a warp idle.  The per-unit reductions are
 // folded inside the warp first (items of one unit sit on consecutive lanes: a segmented shuffle reduction) and then
 // into shared memory by the first lane of each run.
-constexpr int kFilterChunk = 32;
+#ifndef FGB_FILTER_CHUNK
+#define FGB_FILTER_CHUNK 256   // B200, 4 M units: 32 -> 1.68 ms, 128 -> 1.35, 256 -> 1.30
+#endif
+constexpr int kFilterChunk = FGB_FILTER_CHUNK;     // 32 .. 256 (power of two): units / jobs whose descriptors are fetched in one round
 
 __global__ void __launch_bounds__(256, 4) filter_simplex_words_kernel(const FilterArgs a) {
   __shared__ unsigned long long s_off[kFilterChunk];
@@ -126,7 +129,8 @@ __global__ void __launch_bounds__(256, 4) filter_simplex_words_kernel(const Filt
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint64_t u0 = a.unit_begin + static_cast<uint64_t>(blockIdx.x) * kFilterChunk;
   const uint32_t nj = static_cast<uint32_t>(a.unit_end - u0 < kFilterChunk ? a.unit_end - u0 : kFilterChunk);
-  if (tid < 32u) {
+  __shared__ uint32_t s_wsum[kFilterChunk / 32];
+  if (tid < static_cast<uint32_t>(kFilterChunk)) {
     uint32_t items = 0;
     if (tid < nj) {
       const fgb_unit un = a.units[u0 + tid];
@@ -141,9 +145,16 @@ __global__ void __launch_bounds__(256, 4) filter_simplex_words_kernel(const Filt
       const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
       if (lane >= static_cast<uint32_t>(off)) incl += v;
     }
-    s_pref[tid + 1] = incl;
-    if (tid == 0) s_pref[0] = 0u;
+    s_pref[tid + 1] = incl;                            // within the warp; the warps in front are added below
+    if (lane == 31u) s_wsum[tid >> 5] = incl;
   }
+  __syncthreads();
+  if (kFilterChunk > 32 && tid >= 32u && tid < static_cast<uint32_t>(kFilterChunk)) {
+    uint32_t add = 0;
+    for (uint32_t w = 0; w < (tid >> 5); ++w) add += s_wsum[w];
+    s_pref[tid + 1] += add;
+  }
+  if (tid == 0) s_pref[0] = 0u;
   __syncthreads();
   const uint32_t total = s_pref[kFilterChunk];
   const uint32_t minq = a.min_base_quality, min_reads = a.min_reads;
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(256, 4) filter_simplex_words_kernel(const Filt
     }
   }
   __syncthreads();
-  if (tid < 32u) {
+  if (tid < static_cast<uint32_t>(kFilterChunk)) {
     unsigned long long rec = 0, pass = 0, msk = 0;
     if (tid < nj) {
       const uint32_t L = s_len[tid];
@@ -252,7 +263,7 @@ __global__ void __launch_bounds__(256, 4) filter_simplex_words_kernel(const Filt
       pass += __shfl_xor_sync(0xFFFFFFFFu, pass, off);
       msk += __shfl_xor_sync(0xFFFFFFFFu, msk, off);
     }
-    if (tid == 0 && rec) {
+    if (lane == 0 && rec) {                  // one warp per 32 units of the chunk
       atomicAdd(a.counters + FGB_CTR_FILTER_RECORDS, rec);
       atomicAdd(a.counters + FGB_CTR_FILTER_PASSED, pass);
       atomicAdd(a.counters + FGB_CTR_FILTER_BASES_MASKED, msk);
