@@ -658,5 +658,16 @@ def main():
         dist.destroy_process_group()
 
 
+def _one_line_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version from C on the first
+    collective), so file descriptor 1 is pointed at stderr for the whole run and Python's sys.stdout keeps the real
+    one: only print() calls of this script reach it."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _one_line_stdout()
     main()

@@ -156,7 +156,10 @@ struct RecordsArgs {
 // One warp per read left 13 of 32 lanes idle on a 150-base row (19 words) and walked the reads one at a time.  Here a
 // CTA takes kRowChunk consecutive reads, 64 threads fetch and check their descriptors, a prefix sum of the rows' word
 // counts goes to shared memory and the 256 threads take 8-position words from ONE flat index (6-step search).
-constexpr uint32_t kRowChunk = 64;
+#ifndef FGB_ROW_CHUNK
+#define FGB_ROW_CHUNK 256
+#endif
+constexpr uint32_t kRowChunk = FGB_ROW_CHUNK;     // 32 .. 256 (power of two): reads whose descriptors are fetched in one round
 
 struct RowSrc {                    // one read of the chunk, as the word builder needs it
   const uint8_t* seq;              // packed sequence, high nibble first (raw-bam sequence.rs:9-35)
@@ -268,7 +271,7 @@ __device__ __forceinline__ void unpack_rows(const uint64_t read_begin, const uin
   __shared__ uint16_t lut_f[256], lut_r[256];
   __shared__ RowSrc s_src[kRowChunk];
   __shared__ uint32_t s_pref[kRowChunk + 1];
-  __shared__ uint32_t s_half;
+  __shared__ uint32_t s_wsum[kRowChunk / 32];
   fill_pair_luts(lut_f, lut_r);
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint64_t n = read_end - read_begin;
@@ -291,11 +294,15 @@ __device__ __forceinline__ void unpack_rows(const uint64_t read_begin, const uin
         const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
         if (lane >= static_cast<uint32_t>(off)) incl += v;
       }
-      if (tid == 31u) s_half = incl;
-      s_pref[tid + 1] = incl;                                 // the second warp's entries get s_half added below
+      if (lane == 31u) s_wsum[tid >> 5] = incl;
+      s_pref[tid + 1] = incl;                                 // within the warp; the warps in front are added below
     }
     __syncthreads();
-    if (tid >= 32u && tid < kRowChunk) s_pref[tid + 1] += s_half;
+    if (kRowChunk > 32u && tid >= 32u && tid < kRowChunk) {
+      uint32_t add = 0;
+      for (uint32_t w = 0; w < (tid >> 5); ++w) add += s_wsum[w];
+      s_pref[tid + 1] += add;
+    }
     if (tid == 0) s_pref[0] = 0u;
     __syncthreads();
     const uint32_t total = s_pref[kRowChunk];
