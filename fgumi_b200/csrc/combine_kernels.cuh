@@ -493,25 +493,19 @@ __global__ void __launch_bounds__(kCombineThreads, 4) duplex_combine_pending_ker
   __shared__ DuplexJobSm sj[kDuplexChunk];
   __shared__ uint32_t s_pref[kDuplexChunk + 1];
   __shared__ uint32_t s_any[kDuplexChunk];
-  __shared__ uint32_t s_pending[kCombineThreads / 32];
   __shared__ uint64_t s_desc[kDuplexChunk][kDuplexDescCache];
   const uint64_t groups = (a.n_jobs + kCombineThreads - 1) / kCombineThreads;
   for (uint64_t g = blockIdx.x; g < groups; g += gridDim.x) {
     const uint64_t jg = g * kCombineThreads;
     const uint64_t j = jg + threadIdx.x;
     const bool pending = j < a.n_jobs && a.out_status[j] == FGB_DUPLEX_PENDING;
-    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pending);
-    if ((threadIdx.x & 31u) == 0u) s_pending[threadIdx.x >> 5] = ballot;     // one word per 32 jobs
-    __syncthreads();
     for (uint32_t c = 0; c < kCombineThreads / kDuplexChunk; ++c) {
       const uint64_t j0 = jg + static_cast<uint64_t>(c) * kDuplexChunk;
-      uint32_t any = 0;
-      for (uint32_t w = 0; w < kDuplexChunk / 32; ++w) any |= s_pending[c * (kDuplexChunk / 32) + w];
-      if (j0 >= a.n_jobs || any == 0u) continue;                             // CTA-uniform
+      // CTA-uniform verdict on this chunk; the barrier also separates the last chunk's use of sj / s_pref / s_any / s_desc
+      const int any = __syncthreads_or(pending && threadIdx.x / kDuplexChunk == c ? 1 : 0);
+      if (j0 >= a.n_jobs || !any) continue;
       duplex_combine_words_chunk<true>(a, j0, sj, s_pref, s_any, s_desc);
-      __syncthreads();                                                       // sj / s_pref / s_any are reused
     }
-    __syncthreads();                                                         // s_pending is rewritten next round
   }
 }
 
