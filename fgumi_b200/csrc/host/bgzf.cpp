@@ -8,12 +8,16 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 
 #include "../../../include/fgumi_b200.h"
+#include "fast_deflate.h"
 
 namespace {
 
@@ -79,6 +83,19 @@ size_t compress_block(const Zlib& z, z_stream* zs, const uint8_t* in, size_t n, 
   return total;
 }
 
+// One member through the built-in encoder (level 1): no zlib involved.
+size_t compress_block_fast(fgb::fastdeflate::Scratch& S, const uint8_t* in, size_t n, uint8_t* out) {
+  const size_t clen = fgb::fastdeflate::deflate_block(S, in, static_cast<uint32_t>(n), out + kHeader, 65536 - kHeader - kFooter);
+  if (!clen || clen > 65536 - kHeader - kFooter) return 0;
+  const size_t total = kHeader + clen + kFooter;
+  static const uint8_t kHead[16] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0x00, 0x42, 0x43, 0x02, 0x00};
+  std::memcpy(out, kHead, 16);
+  put16(out + 16, static_cast<uint32_t>(total - 1));                       // BSIZE
+  put32(out + kHeader + clen, fgb::fastdeflate::crc32(in, n));
+  put32(out + kHeader + clen + 4, static_cast<uint32_t>(n));               // ISIZE
+  return total;
+}
+
 }  // namespace
 
 extern "C" {
@@ -91,8 +108,10 @@ size_t fgb_bgzf_bound(size_t len) {
 fgb_status fgb_bgzf_compress(const uint8_t* data, size_t len, int level, uint32_t n_threads, int append_eof,
                              uint8_t* out, size_t cap, size_t* out_len) {
   if ((len && !data) || !out || !out_len || level < 0 || level > 9) return FGB_ERR_INVALID_ARG;
+  // level 1 = the built-in encoder (fast_deflate.h); every other level is zlib's
+  const bool fast = level == 1 && !std::getenv("FGB_BGZF_ZLIB");
   const Zlib& z = zlib();
-  if (!z.ok) return FGB_ERR_INVALID_ARG;                                   // zlib not available on this host
+  if (!fast && !z.ok) return FGB_ERR_INVALID_ARG;                          // zlib not available on this host
   const size_t blocks = (len + kBlockInput - 1) / kBlockInput;
   if (cap < blocks * 65536 + (append_eof ? sizeof(kEof) : 0)) return FGB_ERR_INVALID_ARG;   // fgb_bgzf_bound(len)
   uint32_t T = std::max<uint32_t>(1, std::min<uint32_t>(n_threads ? n_threads : 1, static_cast<uint32_t>(std::max<size_t>(blocks, 1))));
@@ -100,6 +119,17 @@ fgb_status fgb_bgzf_compress(const uint8_t* data, size_t len, int level, uint32_
   std::vector<int> failed(T, 0);
   // every block is compressed into its own 64 KiB slot of `out`, then the slots are closed up
   auto work = [&](uint32_t t) {
+    if (fast) {
+      std::unique_ptr<fgb::fastdeflate::Scratch> S(new (std::nothrow) fgb::fastdeflate::Scratch);
+      if (!S) { failed[t] = 1; return; }
+      for (size_t b = t; b < blocks; b += T) {
+        const size_t o = b * kBlockInput, n = std::min(kBlockInput, len - o);
+        const size_t s = compress_block_fast(*S, data + o, n, out + b * 65536);
+        if (!s) { failed[t] = 1; break; }
+        sizes[b] = static_cast<uint32_t>(s);
+      }
+      return;
+    }
     z_stream zs;
     std::memset(&zs, 0, sizeof(zs));
     if (z.deflateInit2_(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY, ZLIB_VERSION, static_cast<int>(sizeof(z_stream))) != Z_OK) { failed[t] = 1; return; }

@@ -346,8 +346,11 @@ typedef struct fgb_duplex_filter_params {
 /* The ConsensusOutput stream is the record section of a BAM file as it stands.  fgb_bam_header writes
  * "BAM\1" | l_text | text | n_ref = 0 (consensus reads are unmapped); fgb_bgzf_compress cuts a byte
  * stream into BGZF members (<= 0xFF00 input bytes each, SAM spec §4.1) on n_threads threads and, when
- * asked, appends the 28-byte EOF member.  `out` must hold fgb_bgzf_bound(len) bytes.  zlib is looked up
- * at call time (libz.so.1); if it is missing these calls return FGB_ERR_INVALID_ARG. */
+ * asked, appends the 28-byte EOF member.  `out` must hold fgb_bgzf_bound(len) bytes.  Level 1 is the library's
+ * own DEFLATE encoder (csrc/host/fast_deflate.h: greedy one-probe LZ77 + per-block Huffman codes, ~200-260 MB/s per
+ * thread on consensus BAM bytes, a little smaller than zlib -1's output; own CRC-32); the other levels are zlib's,
+ * looked up at call time (libz.so.1) -- if it is missing they return FGB_ERR_INVALID_ARG.  FGB_BGZF_ZLIB=1 in the
+ * environment sends level 1 to zlib too (A/B runs). */
 size_t fgb_bgzf_bound(size_t len);
 fgb_status fgb_bgzf_compress(const uint8_t* data, size_t len, int level, uint32_t n_threads, int append_eof,
                              uint8_t* out, size_t cap, size_t* out_len);

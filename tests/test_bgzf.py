@@ -43,7 +43,8 @@ def members(stream: bytes):
     return out
 
 
-@pytest.mark.parametrize("n,level,threads", [(0, 6, 1), (1, 1, 1), (0xFF00, 6, 2), (0xFF00 + 1, 0, 3), (1_000_003, 5, 4)])
+@pytest.mark.parametrize("n,level,threads", [(0, 6, 1), (1, 1, 1), (0xFF00, 6, 2), (0xFF00 + 1, 0, 3), (1_000_003, 5, 4),
+                                             (0, 1, 1), (0xFF00, 1, 2), (1_000_003, 1, 4)])
 def test_bgzf_members_round_trip(n, level, threads):
     rng = np.random.default_rng(n + level)
     data = (rng.integers(0, 4, size=n).astype(np.uint8) * 17 + rng.integers(0, 2, size=n).astype(np.uint8)).tobytes()
@@ -122,3 +123,49 @@ def test_bgzf_reader_and_record_split_round_trip(tmp_path):
     assert lib.fgb_bgzf_decompress(comp.ctypes.data, len(comp), 2, out.ctypes.data, len(out), C.addressof(n)) != 0
     hdr_out = bamio.output_header(text, "A")
     assert hdr_out.startswith(b"@HD\tVN:1.6\tSO:unknown\tGO:query\n@RG\tID:A\tSM:s\n") and b"@PG\tID:fgumi_b200" in hdr_out
+
+
+def _shapes(rng, kind, m):
+    if kind == 0:
+        return rng.integers(0, 256, size=m).astype(np.uint8)                       # incompressible
+    if kind == 1:
+        return np.zeros(m, np.uint8)                                               # maximal matches (258) back to back
+    if kind == 2:
+        return np.frombuffer((b"ACGTACGTTTGACA-" * (m // 15 + 1))[:m], np.uint8).copy()
+    if kind == 3:
+        return rng.integers(0, 4, size=m).astype(np.uint8)                         # four symbols: short codes
+    if kind == 4:
+        return np.repeat(rng.integers(0, 256, size=m // 7 + 1).astype(np.uint8), 7)[:m].copy()
+    d = rng.integers(0, 256, size=m).astype(np.uint8)                              # far matches inside noise
+    if m > 40000:
+        d[35000:35300] = d[0:300]
+        d[m // 2:m // 2 + 200] = 7
+    return d
+
+
+def test_builtin_level1_encoder_on_assorted_inputs():
+    """Level 1 is the repo's own DEFLATE encoder (csrc/host/fast_deflate.h): zlib and gzip must read every member back,
+    whatever the input looks like -- sizes around the encoder's thresholds and the 0xFF00 member boundary, all-literal,
+    all-match, few-symbol and far-match data -- and it must never lose to a stored block by more than its header."""
+    rng = np.random.default_rng(77)
+    sizes = [0, 1, 2, 15, 16, 17, 31, 100, 1000, 0xFF00 - 1, 0xFF00, 0xFF00 + 1, 70_000, 200_000]
+    for trial in range(6 * len(sizes)):
+        kind, m = trial % 6, sizes[trial // 6]
+        data = _shapes(rng, kind, m).tobytes()
+        s = bgzf(data, 1, 1 + trial % 3)
+        assert b"".join(members(s)) == data, (kind, m)
+        blocks = (m + 0xFF00 - 1) // 0xFF00
+        assert len(s) <= m + blocks * (18 + 8 + 5) + 28, (kind, m)
+    # it does compress what compresses
+    text = (b"RGZA\0cDi\x08\0\0\0cMi\x08\0\0\0MIZ1234567\0RXZACGTACGT-TTGACAGT\0" * 3000)
+    assert len(bgzf(text, 1)) < len(text) // 10
+
+
+def test_builtin_crc32_is_zlibs(fg_lib=None):
+    """The gzip trailer of a level-1 member carries the encoder's own CRC-32: members() checks it against zlib.crc32
+    for every block above; here lengths 0..70 (the slicing-by-8 loop's head and tail) explicitly."""
+    rng = np.random.default_rng(5)
+    for m in range(0, 71):
+        data = rng.integers(0, 256, size=m).astype(np.uint8).tobytes()
+        blk = members(bgzf(data, 1, 1, eof=False)) if m else [b""]
+        assert blk[0] == data
