@@ -1581,6 +1581,7 @@ void filter_duplex_template(fgb_caller* ctx, size_t mark) {
 fgb_status flush_duplex(fgb_caller* c) {
   const uint64_t U = c->pack.units.size();
   if (!U) return FGB_OK;
+  PhaseTrace trace;
   uint64_t n_bytes, R;
   c->pack.seal(&n_bytes, &R);
   uint64_t n_tiles = 0;
@@ -1616,7 +1617,9 @@ fgb_status flush_duplex(fgb_caller* c) {
   } else {
     st = fgb_submit(c->h, &b, &ss);
   }
+  trace.mark("seal + tiles + submit");
   if (st == FGB_OK) st = fgb_wait(c->h);
+  trace.mark("wait");
   if (st != FGB_OK) {
     char buf[256];
     fgb_last_error(c->h, buf, sizeof(buf));
@@ -1631,7 +1634,7 @@ fgb_status flush_duplex(fgb_caller* c) {
     s.len = len; s.present = true;
     return s;
   };
-  return parallel_records(c, c->molecules.size(), 128, [&](fgb_caller* ctx, uint64_t m0, uint64_t m1) -> fgb_status {
+  const fgb_status rst = parallel_records(c, c->molecules.size(), 128, [&](fgb_caller* ctx, uint64_t m0, uint64_t m1) -> fgb_status {
   // `ctx` owns the record buffer, the counters and the error text of this range; the voted columns,
   // jobs and molecules are the parent's (read-only here)
   fgb_status st = FGB_OK;
@@ -1697,6 +1700,8 @@ fgb_status flush_duplex(fgb_caller* c) {
   }
   return FGB_OK;
   });
+  trace.mark("records");
+  return rst;
 }
 
 
