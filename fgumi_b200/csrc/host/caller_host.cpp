@@ -2536,7 +2536,22 @@ static fgb_status caller_add_groups_impl(fgb_caller* c, const uint8_t* records, 
     }
     return FGB_OK;
   };
-  if (T <= 1) { uint64_t bg = 0; return run(c, 0, n_groups, &bg); }
+  if (T <= 1) {
+    // one thread: the call still goes to a worker context first, so that a failing call leaves nothing of itself
+    // queued -- the same outcome as with several threads (and as the direct path's roll-back)
+    ensure_workers(c, 1);
+    fgb_caller* w = c->workers[0].get();
+    uint64_t bg = 0;
+    const fgb_status st = run(w, 0, n_groups, &bg);
+    if (st != FGB_OK) {
+      c->last_error = w->last_error;
+      fgb_caller scratch;
+      merge_worker(&scratch, w);
+      return st;
+    }
+    merge_worker(c, w);
+    return FGB_OK;
+  }
   ensure_workers(c, T);
   // contiguous ranges balanced by record count
   std::vector<uint64_t> cut(T + 1, n_groups);

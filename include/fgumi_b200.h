@@ -778,10 +778,9 @@ fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uin
  * is the reference's "one caller per worker" (simplex.rs:574) folded behind one call.
  * Errors: a group whose first record lacks the UMI tag (FGB_ERR_MISSING_TAG), a malformed record
  * (FGB_ERR_INVALID_ARG / FGB_ERR_LAYOUT: offsets must ascend), a read longer than FGB_MAX_READ_LEN or a group of
- * more than 65535 reads (FGB_ERR_UNIT_TOO_LARGE) fail the CALL.  A simplex caller with a device (rows built on
- * the device) then leaves nothing of the failing call queued, whatever n_threads is; the host-decode callers
- * (duplex, CODEC, planning-only) keep the groups in front of the failing one when n_threads <= 1 and drop the whole
- * call otherwise.  Work queued by earlier calls is never touched. */
+ * more than 65535 reads (FGB_ERR_UNIT_TOO_LARGE) fail the CALL: nothing of a failing call stays queued, whatever the
+ * caller's mode and n_threads (counters included), and work queued by earlier calls is never touched.
+ * (fgb_caller_add_group, the one-group form, has nothing to roll back: a failing group is simply not queued.) */
 fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
                                  const uint64_t* group_rec, uint64_t n_groups);
 /* Votes everything queued (one fgb_submit) and returns the concatenated ConsensusOutput of all

@@ -177,6 +177,43 @@ def test_threaded_add_groups_queues_the_same_batch(mode):
     assert sa == sb
 
 
+@pytest.mark.parametrize("mode", ["simplex", "duplex", "codec"])
+@pytest.mark.parametrize("threads", [1, 5])
+def test_failing_add_groups_call_leaves_nothing_queued(mode, threads):
+    """A call that fails (here: a truncated record in a group in the middle of the call) queues nothing
+    of itself and counts nothing, whatever the thread count; what earlier calls queued stays, and the caller goes on
+    to queue later calls exactly as if the failing one had never been made."""
+    import fgumi_b200 as fg
+    from tests.bam_builder import make_record
+    rng = np.random.default_rng(21)
+    if mode == "simplex":
+        gen, mk = random_groups, lambda t: fg.VanillaUmiConsensusCaller("fgumi", "A", device=fg.lib.FGB_DEVICE_NONE, n_threads=t)
+    elif mode == "duplex":
+        gen, mk = random_duplex_groups, lambda t: fg.DuplexConsensusCaller("fgumi", "A", min_reads=(1, 1, 0), device=fg.lib.FGB_DEVICE_NONE, n_threads=t)
+    else:
+        gen, mk = random_codec_groups, lambda t: fg.CodecConsensusCaller("fgumi", "A", device=fg.lib.FGB_DEVICE_NONE, n_threads=t)
+    first, second, third = gen(rng, 150), gen(rng, 400), gen(rng, 150)
+    bad = [make_record(name=b"x", flags=0, pos=5, seq=b"ACGTACGTAC", quals=bytes([30] * 10), tags=[(b"MI", "Z", b"9")])[:20]]
+    broken = second[:250] + [bad] + second[250:]
+    c = mk(threads)
+    c.add_groups(first)
+    before, stats_before = c.pending(), c.statistics()
+    with pytest.raises(fg.lib.FgbError) as e:
+        c.add_groups(broken)
+    assert e.value.status in (fg.lib.FGB_ERR_INVALID_ARG, fg.lib.FGB_ERR_LAYOUT)
+    after, stats_after = c.pending(), c.statistics()
+    assert after["units"] == before["units"] and after["n_out"] == before["n_out"] and stats_after == stats_before
+    c.add_groups(third)
+    got, got_stats = c.pending(), c.statistics()
+    c.close()
+    ref = mk(threads)
+    ref.add_groups(first); ref.add_groups(third)
+    want, want_stats = ref.pending(), ref.statistics()
+    ref.close()
+    assert got["units"] == want["units"] and got["n_out"] == want["n_out"] and got_stats == want_stats
+    assert np.array_equal(got["duplex_jobs"], want["duplex_jobs"]) and np.array_equal(got["codec_jobs"], want["codec_jobs"])
+
+
 @pytest.mark.parametrize("sanitizer", ["address,undefined", "thread"])
 def test_host_caller_under_sanitizers(tmp_path, sanitizer):
     """caller_host.cpp itself compiled with ASan+UBSan, and with TSan, into tests/native/caller_plan.cpp:
