@@ -18,6 +18,7 @@
 #include "combine_kernels.cuh"
 #include "fgb_config.h"
 #include "filter_kernel.cuh"
+#include "inflate_kernel.cuh"
 #include "host_tables.h"
 #include "planner.h"
 #include "unpack_kernels.cuh"
@@ -1221,6 +1222,24 @@ fgb_status fgb_vote_duplex_device(fgb_handle* h, const fgb_batch* in, const fgb_
   const uint64_t groups = (n_jobs + kCombineThreads - 1) / kCombineThreads;
   const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(groups, static_cast<uint64_t>(h->sm_count) * 8u));
   duplex_combine_pending_kernel<<<grid, kCombineThreads, 0, s>>>(a);
+  h->launches++;
+  FGB_CUDA(h, cudaGetLastError());
+  return FGB_OK;
+}
+
+// ---- K0z: BGZF members inflated on the device -----------------------------------------------------------
+fgb_status fgb_bgzf_inflate_device(fgb_handle* h, const uint8_t* data, const fgb_bgzf_member* members,
+                                   uint64_t n_members, uint8_t* out, uint8_t* status, int check_crc,
+                                   unsigned long long* n_bad, void* stream) {
+  if (!h || (n_members && (!data || !members || !status))) return FGB_ERR_INVALID_ARG;
+  if (n_members == 0) return FGB_OK;
+  FGB_CUDA(h, cudaSetDevice(h->device));
+  InflateArgs a;
+  a.in = data; a.members = members; a.n_members = n_members; a.out = out; a.status = status;
+  a.check_crc = check_crc ? 1u : 0u; a.n_bad = n_bad;
+  const uint64_t blocks = (n_members + kInflateThreads - 1) / kInflateThreads;
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(blocks, static_cast<uint64_t>(h->sm_count) * 64u));
+  bgzf_inflate_kernel<<<grid, kInflateThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   h->launches++;
   FGB_CUDA(h, cudaGetLastError());
   return FGB_OK;

@@ -18,6 +18,7 @@
 
 #include "../../../include/fgumi_b200.h"
 #include "fast_deflate.h"
+#include "../inflate_core.h"
 
 namespace {
 
@@ -209,12 +210,41 @@ fgb_status fgb_bgzf_uncompressed_size(const uint8_t* data, size_t len, size_t* s
   return FGB_OK;
 }
 
+// The member table fgb_bgzf_inflate_device takes (capi.cu): framing only, nothing is inflated here.
+fgb_status fgb_bgzf_scan_members(const uint8_t* data, size_t len, fgb_bgzf_member* members, uint64_t cap,
+                                 uint64_t* n_members, uint64_t* out_len) {
+  if ((len && !data) || !n_members || !out_len) return FGB_ERR_INVALID_ARG;
+  std::vector<Member> m;
+  size_t total = 0;
+  if (!scan_members(data, len, &m, &total)) return FGB_ERR_LAYOUT;
+  for (const Member& mb : m) if (mb.isize > 65536 || mb.size > 0xFFFFFFFFull) return FGB_ERR_LAYOUT;
+  *n_members = m.size();
+  *out_len = total;
+  if (!members || cap < m.size()) return FGB_OK;              // sizing call
+  for (size_t i = 0; i < m.size(); ++i) {
+    fgb_bgzf_member& o = members[i];
+    o.in_off = m[i].off; o.out_off = m[i].out_off;
+    o.in_len = static_cast<uint32_t>(m[i].size); o.out_len = static_cast<uint32_t>(m[i].isize);
+    o.crc = get32(data + m[i].off + m[i].size);
+    o.reserved = 0;
+  }
+  return FGB_OK;
+}
+
+// The device decoder's code on the host (csrc/inflate_core.h), one member.
+uint32_t fgb_host_inflate_member(const uint8_t* payload, uint32_t in_len, uint8_t* out, uint32_t out_len) {
+  if ((in_len && !payload) || (out_len && !out)) return fgb::inflate::kErrInput;
+  static const fgb::inflate::Consts k = [] { fgb::inflate::Consts c; fgb::inflate::consts_init(c); return c; }();
+  fgb::inflate::Tables t;
+  return fgb::inflate::inflate_member(payload, in_len, out, out_len, t, k);
+}
+
 // Inflates every member at its place in `out`, members dealt to n_threads threads; CRC32 and ISIZE are checked.
 fgb_status fgb_bgzf_decompress(const uint8_t* data, size_t len, uint32_t n_threads, uint8_t* out, size_t cap,
                                size_t* out_len) {
   if ((len && !data) || !out_len || (cap && !out)) return FGB_ERR_INVALID_ARG;
   const Zlib& z = zlib();
-  if (!z.ok_inflate) return FGB_ERR_INVALID_ARG;
+  const bool own = !z.ok_inflate || std::getenv("FGB_BGZF_OWN_INFLATE");      // no zlib: the repo's decoder (slower)
   std::vector<Member> m;
   size_t total = 0;
   if (!scan_members(data, len, &m, &total)) return FGB_ERR_LAYOUT;
@@ -222,11 +252,20 @@ fgb_status fgb_bgzf_decompress(const uint8_t* data, size_t len, uint32_t n_threa
   const uint32_t T = std::max<uint32_t>(1, std::min<uint32_t>(n_threads ? n_threads : 1, static_cast<uint32_t>(std::max<size_t>(m.size(), 1))));
   std::vector<int> failed(T, 0);
   auto work = [&](uint32_t t) {
+    // contiguous runs of members per thread (sequential output per thread)
+    const size_t a = m.size() * t / T, e = m.size() * (t + 1) / T;
+    if (own) {
+      for (size_t i = a; i < e; ++i) {
+        const Member& mb = m[i];
+        if (mb.isize > 65536 || mb.size > 0xFFFFFFFFull ||
+            fgb_host_inflate_member(data + mb.off, static_cast<uint32_t>(mb.size), out + mb.out_off, static_cast<uint32_t>(mb.isize)) != 0 ||
+            fgb::fastdeflate::crc32(out + mb.out_off, mb.isize) != get32(data + mb.off + mb.size)) { failed[t] = 1; break; }
+      }
+      return;
+    }
     z_stream zs;
     std::memset(&zs, 0, sizeof(zs));
     if (z.inflateInit2_(&zs, -15, ZLIB_VERSION, static_cast<int>(sizeof(z_stream))) != Z_OK) { failed[t] = 1; return; }
-    // contiguous runs of members per thread (sequential output per thread)
-    const size_t a = m.size() * t / T, e = m.size() * (t + 1) / T;
     for (size_t i = a; i < e; ++i) {
       const Member& mb = m[i];
       if (z.inflateReset(&zs) != Z_OK) { failed[t] = 1; break; }

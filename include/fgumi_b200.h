@@ -352,6 +352,32 @@ typedef struct fgb_duplex_filter_params {
  * looked up at call time (libz.so.1) -- if it is missing they return FGB_ERR_INVALID_ARG.  FGB_BGZF_ZLIB=1 in the
  * environment sends level 1 to zlib too (A/B runs). */
 size_t fgb_bgzf_bound(size_t len);
+/* ---- since ABI 3: BGZF members inflated on the device (K0z) ----------------------------------------------
+ * The input side of a file-level run: the host frames the members (fgb_bgzf_scan_members: one pass over the 18-byte
+ * headers and 8-byte trailers, no inflate), the COMPRESSED stream crosses the link, and fgb_bgzf_inflate_device
+ * writes the inflated stream -- BAM header and records -- into device memory, one member per thread
+ * (csrc/inflate_kernel.cuh; the decoder is csrc/inflate_core.h, the same code the CPU tests run against zlib).
+ * status[m] = 0 or an error code of the decoder (1 input exhausted, 2 more output than ISIZE, 3 block type,
+ * 4 stored length, 5 code lengths, 6 symbol / distance, 7 short output, 8 CRC mismatch): a corrupt member never
+ * touches memory outside its own [out_off, out_off + out_len). */
+typedef struct fgb_bgzf_member {
+  uint64_t in_off;      /* first byte of the member's DEFLATE payload in the compressed stream      */
+  uint64_t out_off;     /* where its output starts in the inflated stream (sum of the ISIZEs before) */
+  uint32_t in_len;      /* payload bytes                                                           */
+  uint32_t out_len;     /* ISIZE                                                                   */
+  uint32_t crc;         /* CRC-32 of the output, from the member's trailer                         */
+  uint32_t reserved;
+} fgb_bgzf_member;
+/* Host: fills members[0 .. *n_members) (call with members == NULL to count) and *out_len = total inflated size.
+ * FGB_ERR_LAYOUT on a malformed header, a member that runs past `len`, or an ISIZE above 65536. */
+fgb_status fgb_bgzf_scan_members(const uint8_t* data, size_t len, fgb_bgzf_member* members, uint64_t cap,
+                                 uint64_t* n_members, uint64_t* out_len);
+/* Device pointers throughout; `status` holds n_members bytes; *n_bad (device, optional) is incremented per failed member. */
+fgb_status fgb_bgzf_inflate_device(fgb_handle* h, const uint8_t* data, const fgb_bgzf_member* members,
+                                   uint64_t n_members, uint8_t* out, uint8_t* status, int check_crc,
+                                   unsigned long long* n_bad, void* stream);
+/* The same decoder on the host, one member (tests, and callers without a device): returns the status code above. */
+uint32_t fgb_host_inflate_member(const uint8_t* payload, uint32_t in_len, uint8_t* out, uint32_t out_len);
 fgb_status fgb_bgzf_compress(const uint8_t* data, size_t len, int level, uint32_t n_threads, int append_eof,
                              uint8_t* out, size_t cap, size_t* out_len);
 fgb_status fgb_bam_header(const char* sam_text, size_t l_text, uint8_t* out, size_t cap, size_t* out_len);

@@ -169,3 +169,141 @@ def test_builtin_crc32_is_zlibs(fg_lib=None):
         data = rng.integers(0, 256, size=m).astype(np.uint8).tobytes()
         blk = members(bgzf(data, 1, 1, eof=False)) if m else [b""]
         assert blk[0] == data
+
+
+# ---- the repo's own DEFLATE decoder (csrc/inflate_core.h): host form here, device form in the gpu test below ----
+MEMBER_DTYPE = np.dtype([("in_off", "<u8"), ("out_off", "<u8"), ("in_len", "<u4"), ("out_len", "<u4"), ("crc", "<u4"), ("reserved", "<u4")])
+
+
+def _scan(lib, stream: np.ndarray):
+    n, total = C.c_uint64(), C.c_uint64()
+    assert lib.fgb_bgzf_scan_members(stream.ctypes.data, stream.size, None, 0, C.byref(n), C.byref(total)) == 0
+    members = np.zeros(max(n.value, 1), dtype=MEMBER_DTYPE)
+    assert lib.fgb_bgzf_scan_members(stream.ctypes.data, stream.size, members.ctypes.data, n.value, C.byref(n), C.byref(total)) == 0
+    return members[: n.value], total.value
+
+
+def _mixed_stream(rng, sizes=(0, 1, 17, 1000, 0xFF00, 0xFF00 + 5, 70_000, 300_000)):
+    """BGZF members written at levels 0 (stored blocks), 1 (the built-in encoder), 6 and 9 (zlib, dynamic and fixed
+    blocks) over assorted data; returns (stream bytes, the data)."""
+    parts, data = [], []
+    for i, m in enumerate(sizes):
+        for kind in range(6):
+            d = _shapes(rng, kind, m).tobytes()
+            parts.append(bgzf(d, (0, 1, 6, 9)[(i + kind) % 4], 1 + kind % 3, eof=False))
+            data.append(d)
+    return b"".join(parts) + EOF_BLOCK, b"".join(data)
+
+
+def test_member_table_and_host_decoder_against_zlib():
+    import fgumi_b200 as fg
+    lib = fg.lib.load()
+    rng = np.random.default_rng(91)
+    stream_b, data = _mixed_stream(rng)
+    stream = np.frombuffer(stream_b, np.uint8)
+    members, total = _scan(lib, stream)
+    assert total == len(data) and members[-1]["out_len"] == 0            # the EOF member
+    # the table against an independent walk of the stream
+    p = o = 0
+    for mb in members:
+        bsize = struct.unpack_from("<H", stream_b, p + 16)[0] + 1
+        crc, isize = struct.unpack_from("<II", stream_b, p + bsize - 8)
+        assert (mb["in_off"], mb["in_len"], mb["out_off"], mb["out_len"], mb["crc"]) == (p + 18, bsize - 26, o, isize, crc)
+        p += bsize; o += isize
+    # every member through the host form of the device decoder; guard bytes behind each output
+    for mb in members:
+        out = np.full(int(mb["out_len"]) + 16, 0xAB, np.uint8)
+        st = lib.fgb_host_inflate_member(stream.ctypes.data + int(mb["in_off"]), int(mb["in_len"]), out.ctypes.data, int(mb["out_len"]))
+        assert st == 0
+        want = data[int(mb["out_off"]):int(mb["out_off"]) + int(mb["out_len"])]
+        assert out[: mb["out_len"]].tobytes() == want and (out[mb["out_len"]:] == 0xAB).all()
+        assert zlib.crc32(want) == mb["crc"]
+
+
+def test_host_decoder_on_damaged_members_stays_inside_its_output():
+    import fgumi_b200 as fg
+    lib = fg.lib.load()
+    rng = np.random.default_rng(92)
+    stream_b, _ = _mixed_stream(rng, sizes=(1000, 0xFF00))
+    stream = np.frombuffer(stream_b, np.uint8).copy()
+    members, _ = _scan(lib, stream)
+    bad_seen = 0
+    for mb in members[:-1]:
+        lo, n = int(mb["in_off"]), int(mb["in_len"])
+        payload = stream[lo:lo + n].copy()
+        for trial in range(6):
+            dmg = payload.copy()
+            if trial < 4:
+                for _ in range(1 + trial):
+                    dmg[int(rng.integers(0, n))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            else:
+                dmg = dmg[: n // 2 if trial == 4 else max(n - 3, 0)].copy()            # truncated
+            out = np.full(int(mb["out_len"]) + 16, 0xAB, np.uint8)
+            st = lib.fgb_host_inflate_member(dmg.ctypes.data if dmg.size else None, dmg.size, out.ctypes.data, int(mb["out_len"]))
+            assert (out[mb["out_len"]:] == 0xAB).all()
+            ok = st == 0 and zlib.crc32(out[: mb["out_len"]].tobytes()) == mb["crc"]
+            bad_seen += not ok
+    assert bad_seen > 50                                                   # damage is noticed (status or CRC)
+
+
+def test_reader_with_the_own_decoder_equals_zlibs(monkeypatch):
+    import fgumi_b200 as fg
+    lib = fg.lib.load()
+    rng = np.random.default_rng(93)
+    stream_b, data = _mixed_stream(rng, sizes=(17, 0xFF00, 200_000))
+    stream = np.frombuffer(stream_b, np.uint8)
+    for own in (False, True):
+        if own:
+            monkeypatch.setenv("FGB_BGZF_OWN_INFLATE", "1")
+        out = np.zeros(len(data) + 1, np.uint8)
+        n = C.c_size_t()
+        assert lib.fgb_bgzf_decompress(stream.ctypes.data, stream.size, 3, out.ctypes.data, out.size, C.byref(n)) == 0
+        assert n.value == len(data) and out[: n.value].tobytes() == data
+
+
+@pytest.mark.gpu
+def test_bgzf_members_inflated_on_the_device():
+    """fgb_bgzf_inflate_device: a stream of members written at four levels (stored, built-in encoder, zlib dynamic /
+    fixed) comes out of the device byte for byte, CRCs checked there; damaged members are flagged one by one and
+    touch nothing but their own output range."""
+    import torch
+    import fgumi_b200 as fg
+    lib = fg.lib.load()
+    rng = np.random.default_rng(94)
+    stream_b, data = _mixed_stream(rng, sizes=(0, 1, 17, 1000, 0xFF00, 0xFF00 + 5, 70_000, 300_000, 2_000_000))
+    stream = np.frombuffer(stream_b, np.uint8).copy()
+    members, total = _scan(lib, stream)
+    dev = "cuda:0"
+    eng = fg.Engine(0, 45, 40, 1, 2)
+    d_members = torch.from_numpy(members.view(np.uint8).reshape(-1).copy()).to(dev)
+    d_out = torch.full((total + 64,), 0xCD, dtype=torch.uint8, device=dev)
+    d_st = torch.full((len(members),), 99, dtype=torch.uint8, device=dev)
+    d_bad = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def run(host_stream):
+        d_in = torch.from_numpy(host_stream).to(dev)
+        d_out.fill_(0xCD); d_st.fill_(99); d_bad.zero_()
+        assert lib.fgb_bgzf_inflate_device(eng._h, d_in.data_ptr(), d_members.data_ptr(), len(members), d_out.data_ptr(),
+                                           d_st.data_ptr(), 1, d_bad.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        return d_out.cpu().numpy(), d_st.cpu().numpy(), int(d_bad.item())
+
+    out, st, bad = run(stream)
+    assert bad == 0 and not st.any()
+    assert out[:total].tobytes() == data and (out[total:] == 0xCD).all()
+    # damage every third member that has a payload; its neighbours must come out whole
+    dmg = stream.copy()
+    hit = []
+    for i, mb in enumerate(members):
+        if i % 3 == 0 and mb["in_len"] > 8 and mb["out_len"] > 0:
+            for _ in range(3):
+                dmg[int(mb["in_off"]) + int(rng.integers(0, mb["in_len"]))] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            hit.append(i)
+    out, st, bad = run(dmg)
+    assert bad == int((st != 0).sum()) and set(np.flatnonzero(st).tolist()) <= set(hit) and bad >= len(hit) * 9 // 10
+    for i, mb in enumerate(members):
+        if i not in hit:
+            a, b = int(mb["out_off"]), int(mb["out_off"] + mb["out_len"])
+            assert out[a:b].tobytes() == data[a:b], i
+    assert (out[total:] == 0xCD).all()
+    eng.close()
