@@ -1237,8 +1237,8 @@ fgb_status fgb_bgzf_inflate_device(fgb_handle* h, const uint8_t* data, const fgb
   InflateArgs a;
   a.in = data; a.members = members; a.n_members = n_members; a.out = out; a.status = status;
   a.check_crc = check_crc ? 1u : 0u; a.n_bad = n_bad;
-  const uint64_t blocks = (n_members + kInflateThreads - 1) / kInflateThreads;
-  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(blocks, static_cast<uint64_t>(h->sm_count) * 64u));
+  const uint64_t blocks = (n_members + kInflateWarps - 1) / kInflateWarps;
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(blocks, static_cast<uint64_t>(h->sm_count) * 16u));   // 64 decoders per SM
   bgzf_inflate_kernel<<<grid, kInflateThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   h->launches++;
   FGB_CUDA(h, cudaGetLastError());

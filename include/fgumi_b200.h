@@ -355,7 +355,7 @@ size_t fgb_bgzf_bound(size_t len);
 /* ---- since ABI 3: BGZF members inflated on the device (K0z) ----------------------------------------------
  * The input side of a file-level run: the host frames the members (fgb_bgzf_scan_members: one pass over the 18-byte
  * headers and 8-byte trailers, no inflate), the COMPRESSED stream crosses the link, and fgb_bgzf_inflate_device
- * writes the inflated stream -- BAM header and records -- into device memory, one member per thread
+ * writes the inflated stream -- BAM header and records -- into device memory, one member per warp
  * (csrc/inflate_kernel.cuh; the decoder is csrc/inflate_core.h, the same code the CPU tests run against zlib).
  * status[m] = 0 or an error code of the decoder (1 input exhausted, 2 more output than ISIZE, 3 block type,
  * 4 stored length, 5 code lengths, 6 symbol / distance, 7 short output, 8 CRC mismatch): a corrupt member never
