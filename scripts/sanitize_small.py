@@ -62,6 +62,9 @@ dp += [(4 * m, 4 * (m + 30) + 1) for m in range(0, 80, 9)]
 _duplex_against_oracle(fg, du, dp, True)
 du, dp = _duplex_molecules(rng, 200)
 _duplex_against_oracle(fg, du, dp, True)
+# K0z: BGZF members inflated on the device (good and damaged members)
+from tests.test_bgzf import test_bgzf_members_inflated_on_the_device
+test_bgzf_members_inflated_on_the_device()
 # BAM4
 layout, raw = fg.pack_raw_reads([[(b"ACGTNACGTACGTTTGA", bytes(range(5, 22)), bool(i & 1), 17 - (i % 3))] * (1 + i % 4) for i in range(200)], 1, 10)
 o = fg.HostColumns.alloc(layout.n_out)
