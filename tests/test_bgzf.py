@@ -307,3 +307,25 @@ def test_bgzf_members_inflated_on_the_device():
             assert out[a:b].tobytes() == data[a:b], i
     assert (out[total:] == 0xCD).all()
     eng.close()
+
+
+def test_encoder_and_decoder_under_sanitizers(tmp_path):
+    """tests/native/deflate_fuzz.cpp: fast_deflate.h and inflate_core.h (the device decoder's code) compiled with
+    ASan + UBSan against zlib -- encoder blocks read back by zlib and the own decoder, zlib streams of every level and
+    strategy read by the own decoder, damaged / truncated / mis-sized streams ending in a status without a stray access."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "deflate_fuzz"
+    r = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                        "-o", str(exe), os.path.join(root, "tests", "native", "deflate_fuzz.cpp"), "-lz"],
+                       capture_output=True, text=True)
+    if r.returncode != 0 and "zlib.h" in r.stderr:
+        pytest.skip("zlib headers not available")
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe), "700"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1"))
+    assert r.returncode == 0 and "deflate_fuzz ok" in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
