@@ -121,12 +121,13 @@ class VanillaUmiConsensusCaller(_Caller):
     def __init__(self, read_name_prefix: str, read_group_id: str,
                  options: VanillaUmiConsensusOptions = VanillaUmiConsensusOptions(), device: int = 0,
                  tag: bytes = b"MI", cell_tag: bytes = b"", consensus_call_overlapping_bases: bool = False,
-                 filter: "ConsensusFilter" = None, n_threads: int = 1):
+                 filter: "ConsensusFilter" = None, n_threads: int = 1, track_rejects: bool = False):
         self._lib = _l.load()
         self._prefix = read_name_prefix.encode()
         self._rg = read_group_id.encode()
         o = _l.FgbCallerOptions()
         o.mode = 0
+        o.track_rejects = 1 if track_rejects else 0    # vanilla_caller.rs:371-374, 418-424
         o.error_rate_pre_umi = options.error_rate_pre_umi
         o.error_rate_post_umi = options.error_rate_post_umi
         o.min_input_base_quality = options.min_input_base_quality
@@ -219,6 +220,21 @@ class VanillaUmiConsensusCaller(_Caller):
                     "fgb_caller_flush")
         raw = C.string_at(data.value, n.value) if n.value else b""
         return ConsensusOutput(raw, int(cnt.value))
+
+    def take_rejects(self) -> List[bytes]:
+        """take_rejected_reads (vanilla_caller.rs:513-516): the raw records rejected since the last take (callers
+        created with track_rejects), in reject-site order."""
+        data, n, cnt = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.fgb_caller_take_rejects(self._h, C.byref(data), C.byref(n), C.byref(cnt)),
+                    "fgb_caller_take_rejects")
+        raw = C.string_at(data.value, n.value) if n.value else b""
+        out, p = [], 0
+        while p < len(raw):
+            size = int.from_bytes(raw[p:p + 4], "little")
+            out.append(raw[p + 4:p + 4 + size])
+            p += 4 + size
+        assert len(out) == cnt.value
+        return out
 
     def consensus_reads_batch(self, groups: Iterable[Sequence[bytes]]) -> ConsensusOutput:
         for g in groups:

@@ -208,6 +208,9 @@ struct PinBuf {                      // grow-only page-locked buffer
 
 struct fgb_caller {
   fgb_caller_options opt{};
+  // options.track_rejects: the rejected records (block_size word + bytes) of the add calls since the last take
+  std::vector<uint8_t> rejects, rejects_taken;
+  uint64_t reject_count = 0, reject_taken_count = 0;
   std::string prefix, rg;
   fgb_handle* h = nullptr;
   UmiBuilder umi_builder;
@@ -227,7 +230,7 @@ struct fgb_caller {
   std::string last_error;
   std::vector<uint32_t> ops;             // scratch
   Prepared prepared[3];                  // simplex: fragment / R1 / R2 sub-groups, buffers reused across groups
-  std::vector<uint32_t> scratch_idx[4];  // simplex: kept / fragment / R1 / R2 record indices
+  std::vector<uint32_t> scratch_idx[6];  // simplex: kept / fragment / R1 / R2 record indices, [4] / [5] the alignment filter's before / after (track_rejects)
   overlap::Caller overlap{overlap::kAgreeConsensus, overlap::kDisagreeConsensus};   // simplex.rs:384-387
   std::vector<uint8_t> group_copy;       // mutable copy of a group for the overlap pre-pass
   std::vector<std::unique_ptr<fgb_caller>> workers;   // per-thread prep state of fgb_caller_add_groups (no GPU handle)
@@ -293,12 +296,28 @@ bool get_string_tag(const View& v, const char tag[2], std::string* out) {
 // simplex
 // ------------------------------------------------------------------------------------------------
 // process_subgroup up to the vote, vanilla_caller.rs:1124-1227
+// vanilla_caller.rs:752-754, 1061-1063, ...: the raw bytes of a rejected read, kept as a BAM record (block_size first).
+inline void keep_reject(fgb_caller* c, const View& v) {
+  if (!c->opt.track_rejects) return;
+  const uint32_t n = static_cast<uint32_t>(v.n);
+  const size_t o = c->rejects.size();
+  c->rejects.resize(o + 4 + n);
+  std::memcpy(c->rejects.data() + o, &n, 4);
+  std::memcpy(c->rejects.data() + o + 4, v.b, n);
+  ++c->reject_count;
+}
+
 void prepare_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::vector<uint32_t>& members,
                       Prepared* p) {
   p->ok = false; p->surviving = 0; p->n = 0; p->rec_idx.clear();
   const size_t min_reads = c->opt.min_reads;
   if (members.empty()) return;
-  if (members.size() < min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, members.size()); return; }
+  const bool track = c->opt.track_rejects != 0;
+  if (members.size() < min_reads) {
+    reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, members.size());
+    if (track) for (uint32_t m : members) keep_reject(c, recs[m]);                     // :1137-1142
+    return;
+  }
   size_t zero = 0;
   for (uint32_t k = 0; k < members.size(); ++k) {
     const View& v = recs[members[k]];
@@ -306,18 +325,37 @@ void prepare_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::v
     size_t clip = bam::num_bases_extending_past_mate(v, c->ops);
     if (p->n == p->srs.size()) p->srs.emplace_back();
     if (make_source_read(c->prep_opt, v, k, clip, &c->ops, &p->srs[p->n])) ++p->n;
-    else ++zero;
+    else { ++zero; keep_reject(c, v); }                                                // :1170-1174
   }
   if (zero) reject(c, FGB_STAT_REJ_ZERO_LENGTH, zero);
   if (p->n < min_reads) {
-    if (p->n) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, p->n);
+    if (p->n) {
+      reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, p->n);
+      if (track) for (size_t i = 0; i < p->n; ++i) keep_reject(c, recs[members[p->srs[i].original_idx]]);   // :1180-1184
+    }
     return;
   }
+  std::vector<uint32_t>& before = c->scratch_idx[4];
+  if (track) { before.clear(); for (size_t i = 0; i < p->n; ++i) before.push_back(p->srs[i].original_idx); }
   const size_t kept = filter_by_alignment_n(&p->srs, p->n);
-  if (kept != p->n) reject(c, FGB_STAT_REJ_MINORITY_ALIGNMENT, p->n - kept);
+  if (kept != p->n) {
+    reject(c, FGB_STAT_REJ_MINORITY_ALIGNMENT, p->n - kept);
+    if (track) {                                                                       // :1193-1197, ascending
+      std::vector<uint32_t>& alive = c->scratch_idx[5];
+      alive.clear();
+      for (size_t i = 0; i < kept; ++i) alive.push_back(p->srs[i].original_idx);
+      std::sort(alive.begin(), alive.end());
+      std::sort(before.begin(), before.end());
+      for (uint32_t k : before)
+        if (!std::binary_search(alive.begin(), alive.end(), k)) keep_reject(c, recs[members[k]]);
+    }
+  }
   p->n = kept;
   if (p->n < min_reads) {
-    if (p->n) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, p->n);
+    if (p->n) {
+      reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, p->n);
+      if (track) for (size_t i = 0; i < p->n; ++i) keep_reject(c, recs[members[p->srs[i].original_idx]]);   // :1205-1209
+    }
     return;
   }
   p->ok = true;
@@ -353,9 +391,18 @@ fgb_status add_group_simplex(fgb_caller* c, const std::vector<View>& recs) {
     uint16_t f = recs[i].flags();
     if (!(f & bam::kSecondary) && !(f & bam::kSupplementary)) kept.push_back(i);
   }
-  if (kept.size() != n_records) reject(c, FGB_STAT_REJ_SECONDARY_SUPPLEMENTARY, n_records - kept.size());
+  if (kept.size() != n_records) {
+    reject(c, FGB_STAT_REJ_SECONDARY_SUPPLEMENTARY, n_records - kept.size());
+    if (c->opt.track_rejects)                                                          // filter_reads, :745-757
+      for (uint32_t i = 0; i < n_records; ++i)
+        if (recs[i].flags() & (bam::kSecondary | bam::kSupplementary)) keep_reject(c, recs[i]);
+  }
   if (kept.empty()) return FGB_OK;
-  if (kept.size() < c->opt.min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, kept.size()); return FGB_OK; }
+  if (kept.size() < c->opt.min_reads) {
+    reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, kept.size());
+    for (uint32_t i : kept) keep_reject(c, recs[i]);                                   // :1061-1063
+    return FGB_OK;
+  }
   for (uint32_t i : kept) {   // subgroup_reads, vanilla_caller.rs:1018-1039
     uint16_t f = recs[i].flags();
     if (!(f & bam::kPaired)) frag.push_back(i);
@@ -377,8 +424,10 @@ fgb_status add_group_simplex(fgb_caller* c, const std::vector<View>& recs) {
     c->stats[FGB_STAT_CONSENSUS_READS] += 2;
   } else if (p1.ok) {
     reject(c, FGB_STAT_REJ_ORPHAN_CONSENSUS, p1.surviving);
+    for (uint32_t ri : p1.rec_idx) keep_reject(c, recs[ri]);                           // :1095-1099
   } else if (p2.ok) {
     reject(c, FGB_STAT_REJ_ORPHAN_CONSENSUS, p2.surviving);
+    for (uint32_t ri : p2.rec_idx) keep_reject(c, recs[ri]);                           // :1101-1105
   }
   return FGB_OK;
 }
@@ -2088,6 +2137,7 @@ static fgb_status caller_create_impl(int device, const fgb_caller_options* opt, 
   if (opt->mode > FGB_MODE_CODEC) return FGB_ERR_INVALID_ARG;
   if (opt->mode != FGB_MODE_DUPLEX && opt->min_reads == 0) return FGB_ERR_INVALID_ARG;
   if (opt->filter_enabled && opt->mode == FGB_MODE_CODEC) return FGB_ERR_INVALID_ARG;
+  if (opt->track_rejects && opt->mode != FGB_MODE_SIMPLEX) return FGB_ERR_INVALID_ARG;   // the simplex caller's reject sites only
   if (opt->filter_enabled && opt->mode == FGB_MODE_DUPLEX) {
     const fgb_duplex_filter_params& f = opt->duplex_filter;
     const double rates[] = {f.cc.max_read_error_rate, f.cc.max_base_error_rate, f.ab_max_read_error_rate,
@@ -2132,9 +2182,22 @@ static fgb_status caller_create_impl(int device, const fgb_caller_options* opt, 
     if (st != FGB_OK) return st;
     // simplex callers with a device build the source-read rows on the device (FGB_CALLER_LEGACY=1 keeps the
     // host decode; planning-only callers always use it, so the packed rows can be inspected)
-    c->direct = opt->mode == FGB_MODE_SIMPLEX && std::getenv("FGB_CALLER_LEGACY") == nullptr;
+    // (track_rejects keeps the host decode too: the reject sites live in its sub-group preparation)
+    c->direct = opt->mode == FGB_MODE_SIMPLEX && !opt->track_rejects && std::getenv("FGB_CALLER_LEGACY") == nullptr;
   }
   *out = c.release();
+  return FGB_OK;
+}
+
+fgb_status fgb_caller_take_rejects(fgb_caller* c, const uint8_t** data, uint64_t* len, uint64_t* count) {
+  if (!c || !data || !len || !count) return FGB_ERR_INVALID_ARG;
+  c->rejects_taken.swap(c->rejects);
+  c->rejects.clear();
+  c->reject_taken_count = c->reject_count;
+  c->reject_count = 0;
+  *data = c->rejects_taken.data();
+  *len = c->rejects_taken.size();
+  *count = c->reject_taken_count;
   return FGB_OK;
 }
 
@@ -2256,6 +2319,9 @@ void merge_worker(fgb_caller* c, fgb_caller* w) {
   c->overlap.stats.bases_agreeing += w->overlap.stats.bases_agreeing;
   c->overlap.stats.bases_disagreeing += w->overlap.stats.bases_disagreeing;
   c->overlap.stats.bases_corrected += w->overlap.stats.bases_corrected;
+  c->rejects.insert(c->rejects.end(), w->rejects.begin(), w->rejects.end());
+  c->reject_count += w->reject_count;
+  w->rejects.clear(); w->reject_count = 0;
   w->pack.clear(); w->metas.clear(); w->molecules.clear(); w->jobs.clear();
   w->codec_molecules.clear(); w->codec_jobs.clear();
   w->n_duplex_out = 0; w->n_codec_out = 0;
@@ -2339,6 +2405,9 @@ void merge_workers_parallel(fgb_caller* c, uint32_t T) {
     c->overlap.stats.bases_agreeing += w->overlap.stats.bases_agreeing;
     c->overlap.stats.bases_disagreeing += w->overlap.stats.bases_disagreeing;
     c->overlap.stats.bases_corrected += w->overlap.stats.bases_corrected;
+    c->rejects.insert(c->rejects.end(), w->rejects.begin(), w->rejects.end());
+    c->reject_count += w->reject_count;
+    w->rejects.clear(); w->reject_count = 0;
     w->pack.clear(); w->metas.clear(); w->molecules.clear(); w->jobs.clear();
     w->codec_molecules.clear(); w->codec_jobs.clear();
     w->n_duplex_out = 0; w->n_codec_out = 0;

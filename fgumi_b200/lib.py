@@ -182,7 +182,7 @@ class FgbCallerOptions(C.Structure):
         ("tag", C.c_char * 2), ("cell_tag", C.c_char * 2),
         ("read_name_prefix", C.c_char_p), ("read_group_id", C.c_char_p),
         ("min_duplex_length", C.c_uint32), ("reserved1", C.c_uint32), ("codec", FgbCodecParams),
-        ("filter_enabled", C.c_uint8), ("zero_copy_records", C.c_uint8), ("reserved2", C.c_uint8 * 2), ("n_threads", C.c_uint32),
+        ("filter_enabled", C.c_uint8), ("zero_copy_records", C.c_uint8), ("track_rejects", C.c_uint8), ("reserved2", C.c_uint8), ("n_threads", C.c_uint32),
         ("filter", FgbFilterParams), ("duplex_filter", FgbDuplexFilterParams),
     ]
 
@@ -209,7 +209,7 @@ SYMBOLS = (
     "fgb_host_free", "fgb_host_is_pinned", "fgb_duplex_combine_device", "fgb_codec_combine_device", "fgb_stats",
     "fgb_stats_device_ptr", "fgb_stats_reset", "fgb_launch_count", "fgb_engine_caps",
     "fgb_duplex_submit", "fgb_codec_submit", "fgb_caller_create", "fgb_caller_destroy", "fgb_caller_last_error", "fgb_caller_add_group",
-    "fgb_caller_flush", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
+    "fgb_caller_flush", "fgb_caller_take_rejects", "fgb_caller_stats", "fgb_overlap_apply_group", "fgb_pack8_encode",
     "fgb_submit_pack8", "fgb_submit_bam4", "fgb_unpack_bam4_device", "fgb_unpack_records_device", "fgb_submit_ex", "fgb_filter_simplex_device", "fgb_struct_size", "fgb_caller_add_groups", "fgb_filter_record", "fgb_host_is_fr_pair",
     "fgb_host_num_bases_extending_past_mate", "fgb_host_clip_cigar_ops", "fgb_host_read_pos_at_ref_pos", "fgb_host_simplify_cigar", "fgb_host_source_reads", "fgb_host_consensus_umis", "fgb_caller_pending", "fgb_host_simplex_record", "fgb_bgzf_bound", "fgb_bgzf_compress", "fgb_bgzf_scan_members", "fgb_bgzf_inflate_device", "fgb_host_inflate_member", "fgb_bam_header", "fgb_bgzf_uncompressed_size", "fgb_bgzf_decompress", "fgb_bam_read_header", "fgb_bam_split_records", "fgb_host_group_by_mi", "fgb_host_duplex_record",
 )
@@ -321,6 +321,8 @@ def load() -> C.CDLL:
     lib.fgb_caller_add_group.restype = C.c_int32
     lib.fgb_caller_flush.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
     lib.fgb_caller_flush.restype = C.c_int32
+    lib.fgb_caller_take_rejects.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+    lib.fgb_caller_take_rejects.restype = C.c_int32
     lib.fgb_caller_stats.argtypes = [vp, C.POINTER(u64)]
     lib.fgb_caller_stats.restype = C.c_int32
     lib.fgb_overlap_apply_group.argtypes = [vp, vp, C.c_uint32, C.c_uint8, C.c_uint8, vp]

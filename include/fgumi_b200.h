@@ -735,7 +735,10 @@ typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanill
                                               (fgb_host_alloc / cudaHostAlloc / cudaHostRegister) instead of staging a copy;
                                               every add call of a batch must pass the same `records` pointer.  Ignored
                                               (a copy is staged) for pageable memory and by the other callers. */
-  uint8_t reserved2[2];
+  uint8_t track_rejects;                   /* simplex: keep the raw bytes of every rejected read (vanilla_caller.rs:371-374,
+                                              the --rejects output of `fgumi simplex`) for fgb_caller_take_rejects.  The
+                                              caller then decodes on the host (the rows are not built on the device). */
+  uint8_t reserved2;
   uint32_t n_threads;                      /* host threads for fgb_caller_add_groups and the record
                                               assembly of flush; 0 or 1 = the calling thread only  */
   fgb_filter_params filter;                /* filter.per_base_tags is set from produce_per_base_tags */
@@ -809,6 +812,13 @@ fgb_status fgb_caller_add_group(fgb_caller* c, const uint8_t* records, const uin
  * (fgb_caller_add_group, the one-group form, has nothing to roll back: a failing group is simply not queued.) */
 fgb_status fgb_caller_add_groups(fgb_caller* c, const uint8_t* records, const uint64_t* rec_off,
                                  const uint64_t* group_rec, uint64_t n_groups);
+/* Rejected reads (options.track_rejects, simplex callers): the records rejected by every add call since the last
+ * take, each with its block_size word in front (a BAM record stream like ConsensusOutput), in the order the
+ * reference's reject sites run -- secondary / supplementary reads, a group or sub-group below min_reads, reads of
+ * zero length after trimming, the minority of the alignment filter (ascending input order; the reference iterates
+ * a HashSet there, vanilla_caller.rs:964, 1193-1196), what is left below min_reads after it, and the surviving reads
+ * of an orphan R1 / R2 consensus (:1095-1105).  *data stays valid until the next add / take / destroy. */
+fgb_status fgb_caller_take_rejects(fgb_caller* c, const uint8_t** data, uint64_t* len, uint64_t* count);
 /* Votes everything queued (one fgb_submit) and returns the concatenated ConsensusOutput of all
  * groups in input order.  *out_data stays valid until the next flush / destroy. */
 fgb_status fgb_caller_flush(fgb_caller* c, const uint8_t** out_data, uint64_t* out_len,

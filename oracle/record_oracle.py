@@ -502,11 +502,16 @@ class Stats:                                          # caller.rs:238-286
 class VanillaCallerOracle:
     """VanillaUmiConsensusCaller::consensus_reads, vanilla_caller.rs:1042-1499."""
 
-    def __init__(self, prefix: str, rg: str, opt: VanillaOptions, vote_fn, builder_fn):
+    def __init__(self, prefix: str, rg: str, opt: VanillaOptions, vote_fn, builder_fn, track_rejects: bool = False):
         self.prefix, self.rg, self.opt = prefix, rg, opt
         self.stats = Stats()
         self.vote = vote_fn           # (rows, opt) -> (bases, quals, depths, errors)
         self.builder_call = builder_fn
+        # vanilla_caller.rs:371-374: raw bytes of every rejected read, in the order the reject sites run.  (The one
+        # site whose order the reference leaves open is the alignment filter's: it iterates a HashSet<usize>,
+        # vanilla_caller.rs:964, 1193-1196; here -- and in the product -- ascending original index.)
+        self.track_rejects = track_rejects
+        self.rejected_reads: List[bytes] = []
 
     def consensus_reads(self, records: List[bytes]) -> Tuple[bytes, int]:
         if not records:
@@ -521,12 +526,16 @@ class VanillaCallerOracle:
         st, opt = self.stats, self.opt
         st.total_reads += len(recs)
         reads = [r for r in recs if not (r.flags & SECONDARY) and not (r.flags & SUPPLEMENTARY)]
+        if self.track_rejects:                           # filter_reads, :745-757
+            self.rejected_reads += [r.b for r in recs if (r.flags & SECONDARY) or (r.flags & SUPPLEMENTARY)]
         if len(recs) - len(reads):
             st.reject("SecondaryOrSupplementary", len(recs) - len(reads))
         if not reads:
             return b"", 0
         if len(reads) < opt.min_reads:
             st.reject("InsufficientReads", len(reads))
+            if self.track_rejects:                       # :1061-1063
+                self.rejected_reads += [r.b for r in reads]
             return b"", 0
         frag = [r for r in reads if not r.flags & PAIRED]
         r1 = [r for r in reads if r.flags & PAIRED and r.flags & FIRST_SEGMENT]
@@ -538,23 +547,33 @@ class VanillaCallerOracle:
             out += rec
             count += 1
         ok1, n1, rec1 = self._subgroup(umi, "R1", r1)
+        surv1 = self._last_surviving
         ok2, n2, rec2 = self._subgroup(umi, "R2", r2)
+        surv2 = self._last_surviving
         if ok1 and ok2:
             st.consensus_reads += 2
             out += rec1 + rec2
             count += 2
         elif ok1:
             st.reject("OrphanConsensus", n1)
+            if self.track_rejects:                       # :1095-1099
+                self.rejected_reads += surv1
         elif ok2:
             st.reject("OrphanConsensus", n2)
+            if self.track_rejects:                       # :1101-1105
+                self.rejected_reads += surv2
         return bytes(out), count
 
     def _subgroup(self, umi: str, read_type: str, group: List[Rec]):
         st, opt = self.stats, self.opt
+        track = self.track_rejects
+        self._last_surviving: List[bytes] = []
         if not group:
             return False, 0, b""
         if len(group) < opt.min_reads:
             st.reject("InsufficientReads", len(group))
+            if track:                                    # :1137-1142
+                self.rejected_reads += [r.b for r in group]
             return False, 0, b""
         clips = [num_bases_extending_past_mate(r) for r in group]
         srs, zero = [], 0
@@ -562,6 +581,8 @@ class VanillaCallerOracle:
             sr = create_source_read(r, i, c, opt)
             if sr is None:
                 zero += 1
+                if track:                                # :1170-1174 (zero_length_indices, ascending)
+                    self.rejected_reads.append(r.b)
             else:
                 srs.append(sr)
         if zero:
@@ -569,14 +590,24 @@ class VanillaCallerOracle:
         if len(srs) < opt.min_reads:
             if srs:
                 st.reject("InsufficientReads", len(srs))
+                if track:                                # :1180-1184
+                    self.rejected_reads += [group[s.original_idx].b for s in srs]
             return False, 0, b""
+        before = [s.original_idx for s in srs]
         srs, n_rej = filter_by_alignment(srs)
         if n_rej:
             st.reject("MinorityAlignment", n_rej)
+        if track:                                        # :1193-1197 (a HashSet in the reference: ascending here)
+            kept_idx = {s.original_idx for s in srs}
+            self.rejected_reads += [group[i].b for i in sorted(before) if i not in kept_idx]
         if len(srs) < opt.min_reads:
             if srs:
                 st.reject("InsufficientReads", len(srs))
+                if track:                                # :1205-1209
+                    self.rejected_reads += [group[s.original_idx].b for s in srs]
             return False, 0, b""
+        if track:                                        # :1216-1220 surviving_reads (what the orphan rule forwards)
+            self._last_surviving = [group[s.original_idx].b for s in srs]
         bases, quals, depths, errors = self.vote([(bytes(s.bases), bytes(s.quals)) for s in srs], opt)
         raws = [group[s.original_idx] for s in srs]
         return True, len(srs), self._record(umi, read_type, raws, bases, quals, depths, errors)

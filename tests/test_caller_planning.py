@@ -5,6 +5,8 @@ what the oracle caller hands to its vote hook, and flushing must fail loudly (no
 import os
 import sys
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -109,6 +111,49 @@ def test_simplex_host_prep_matches_oracle(min_reads, trim, overlap):
     if overlap:
         assert (st["overlapping_bases"], st["overlap_bases_agreeing"], st["overlap_bases_disagreeing"],
                 st["overlap_bases_corrected"]) == ov.stats()
+
+
+@pytest.mark.parametrize("min_reads,trim,threads", [(1, False, 1), (2, True, 1), (3, False, 5), (2, False, 5)])
+def test_simplex_rejected_reads_match_oracle(min_reads, trim, threads):
+    """options.track_rejects: the raw bytes of every rejected read, in the order the reference's reject sites run
+    (vanilla_caller.rs:752-754, 1061-1063, 1095-1105, 1137-1142, 1170-1209), against the record oracle's restatement
+    -- every site is hit by these groups (the statistics say so), with one thread and with the groups spread over
+    five; a take in the middle splits the stream without losing or repeating a record."""
+    import fgumi_b200 as fg
+    rng = np.random.default_rng(71 + min_reads)
+    groups = random_groups(rng, 260)
+    oracle = R.VanillaCallerOracle("fgumi", "A", R.VanillaOptions(min_reads=min_reads, trim=trim), Capture(), O.builder_call,
+                                   track_rejects=True)
+    for g in groups:
+        oracle.consensus_reads(g)
+    want = oracle.rejected_reads
+    c = fg.VanillaUmiConsensusCaller("fgumi", "A", fg.VanillaUmiConsensusOptions(min_reads=min_reads, trim=trim),
+                                     device=fg.lib.FGB_DEVICE_NONE, n_threads=threads, track_rejects=True)
+    c.add_groups(groups[:100])
+    got = c.take_rejects()
+    assert c.take_rejects() == []                                   # taken means gone
+    c.add_groups(groups[100:])
+    got += c.take_rejects()
+    st = c.statistics()
+    c.close()
+    assert len(want) > 50 and st["filtered_reads"] == len(want) == oracle.stats.filtered_reads
+    assert got == want
+    rej = oracle.stats.rejections
+    assert rej.get("SecondaryOrSupplementary", 0) > 0 and rej.get("MinorityAlignment", 0) > 0 and rej.get("OrphanConsensus", 0) > 0
+    assert min_reads == 1 or rej.get("InsufficientReads", 0) > 0
+    # callers without the option keep nothing; the other modes refuse it
+    plain = fg.VanillaUmiConsensusCaller("fgumi", "A", device=fg.lib.FGB_DEVICE_NONE)
+    plain.add_groups(groups[:50])
+    assert plain.take_rejects() == []
+    plain.close()
+    with pytest.raises(fg.lib.FgbError):
+        o = fg.lib.FgbCallerOptions()
+        o.mode, o.track_rejects, o.min_reads, o.min_xy_reads, o.tag, o.cell_tag = 1, 1, 1, 1, b"MI", b"\0\0"
+        o.error_rate_pre_umi, o.error_rate_post_umi, o.min_input_base_quality, o.min_consensus_base_quality = 45, 40, 10, 2
+        h = C.c_void_p()
+        st = fg.lib.load().fgb_caller_create(fg.lib.FGB_DEVICE_NONE, C.byref(o), C.byref(h))
+        if st != 0:
+            raise fg.lib.FgbError(st, "fgb_caller_create")
 
 
 @pytest.mark.parametrize("min_reads", [(1, 1, 1), (2, 1, 0), (3, 2, 1)])
