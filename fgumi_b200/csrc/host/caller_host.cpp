@@ -177,7 +177,7 @@ struct DirectPlan {
   void clear() { raws.clear(); lens.clear(); units.clear(); rx.clear(); oruns.clear(); row_bytes = out_elems = rec_bytes = str_bytes = 0; }
 };
 
-struct DMark { size_t raws, units, rx, oruns; uint64_t row_bytes, out_elems, rec_bytes, str_bytes; };   // a plan's size, for roll-back
+struct DMark { size_t raws, units, rx, oruns; uint64_t row_bytes, out_elems, rec_bytes, str_bytes; size_t rejects; uint64_t reject_count; };   // a plan's size, for roll-back
 
 struct DSeg {                        // units [u0, u1) / reads [r0, r1) of one context's plan, in input order
   struct fgb_caller* ctx;
@@ -451,7 +451,12 @@ bool plan_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::vect
   *surviving = 0;
   const size_t min_reads = c->opt.min_reads;
   if (members.empty()) return false;
-  if (members.size() < min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, members.size()); return false; }
+  const bool track = c->opt.track_rejects != 0;
+  if (members.size() < min_reads) {
+    reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, members.size());
+    if (track) for (uint32_t m : members) keep_reject(c, recs[m]);                     // :1137-1142
+    return false;
+  }
   static const char kWant[2][2] = {{'M', 'C'}, {'R', 'X'}};
   size_t zero = 0;
   for (uint32_t k = 0; k < members.size(); ++k) {
@@ -486,12 +491,15 @@ bool plan_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::vect
       });
     }
     if (fl) out->push_back(DRead{members[k], fl, val[1], static_cast<uint32_t>(len[1])});
-    else ++zero;
+    else { ++zero; keep_reject(c, v); }                                                // :1170-1174
   }
   if (zero) reject(c, FGB_STAT_REJ_ZERO_LENGTH, zero);
   size_t n = out->size();
   if (n < min_reads) {
-    if (n) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, n);
+    if (n) {
+      reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, n);
+      if (track) for (const DRead& r : *out) keep_reject(c, recs[r.rec]);              // :1180-1184
+    }
     return false;
   }
   // filter_source_reads_by_alignment (vanilla_caller.rs:961-1013).  Reads with the same CIGAR on the same
@@ -526,6 +534,12 @@ bool plan_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::vect
     const size_t kept = filter_by_alignment_n(&pool.srs, pool.n);
     if (kept != n) {
       reject(c, FGB_STAT_REJ_MINORITY_ALIGNMENT, n - kept);
+      if (track) {                                                                     // :1193-1197, ascending input order
+        std::vector<uint32_t>& alive = c->scratch_idx[5];
+        alive.assign(n, 0u);
+        for (size_t i = 0; i < kept; ++i) alive[pool.srs[i].original_idx] = 1u;
+        for (size_t i = 0; i < n; ++i) if (!alive[i]) keep_reject(c, recs[(*out)[i].rec]);
+      }
       static thread_local std::vector<DRead> tmp;
       tmp.clear();
       for (size_t i = 0; i < kept; ++i) tmp.push_back((*out)[pool.srs[i].original_idx]);
@@ -533,7 +547,10 @@ bool plan_subgroup(fgb_caller* c, const std::vector<View>& recs, const std::vect
       n = kept;
     }
     if (n < min_reads) {
-      if (n) reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, n);
+      if (n) {
+        reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, n);
+        if (track) for (const DRead& r : *out) keep_reject(c, recs[r.rec]);            // :1205-1209
+      }
       return false;
     }
   }
@@ -632,9 +649,18 @@ fgb_status direct_group_simplex(fgb_caller* c, const uint8_t* stage, const std::
     const uint16_t f = recs[i].flags();
     if (!(f & bam::kSecondary) && !(f & bam::kSupplementary)) kept.push_back(i);
   }
-  if (kept.size() != n_records) reject(c, FGB_STAT_REJ_SECONDARY_SUPPLEMENTARY, n_records - kept.size());
+  if (kept.size() != n_records) {
+    reject(c, FGB_STAT_REJ_SECONDARY_SUPPLEMENTARY, n_records - kept.size());
+    if (c->opt.track_rejects)                                                          // filter_reads, :745-757
+      for (uint32_t i = 0; i < n_records; ++i)
+        if (recs[i].flags() & (bam::kSecondary | bam::kSupplementary)) keep_reject(c, recs[i]);
+  }
   if (kept.empty()) return FGB_OK;
-  if (kept.size() < c->opt.min_reads) { reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, kept.size()); return FGB_OK; }
+  if (kept.size() < c->opt.min_reads) {
+    reject(c, FGB_STAT_REJ_INSUFFICIENT_READS, kept.size());
+    for (uint32_t i : kept) keep_reject(c, recs[i]);                                   // :1061-1063
+    return FGB_OK;
+  }
   for (uint32_t i : kept) {   // subgroup_reads, vanilla_caller.rs:1018-1039
     const uint16_t f = recs[i].flags();
     if (!(f & bam::kPaired)) frag.push_back(i);
@@ -656,8 +682,10 @@ fgb_status direct_group_simplex(fgb_caller* c, const uint8_t* stage, const std::
     c->stats[FGB_STAT_CONSENSUS_READS] += 2;
   } else if (ok1) {
     reject(c, FGB_STAT_REJ_ORPHAN_CONSENSUS, s1);
+    for (const DRead& r : d1) keep_reject(c, recs[r.rec]);                             // :1095-1099
   } else if (ok2) {
     reject(c, FGB_STAT_REJ_ORPHAN_CONSENSUS, s2);
+    for (const DRead& r : d2) keep_reject(c, recs[r.rec]);                             // :1101-1105
   }
   return FGB_OK;
 }
@@ -2182,8 +2210,7 @@ static fgb_status caller_create_impl(int device, const fgb_caller_options* opt, 
     if (st != FGB_OK) return st;
     // simplex callers with a device build the source-read rows on the device (FGB_CALLER_LEGACY=1 keeps the
     // host decode; planning-only callers always use it, so the packed rows can be inspected)
-    // (track_rejects keeps the host decode too: the reject sites live in its sub-group preparation)
-    c->direct = opt->mode == FGB_MODE_SIMPLEX && !opt->track_rejects && std::getenv("FGB_CALLER_LEGACY") == nullptr;
+    c->direct = opt->mode == FGB_MODE_SIMPLEX && std::getenv("FGB_CALLER_LEGACY") == nullptr;
   }
   *out = c.release();
   return FGB_OK;
@@ -2432,7 +2459,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
   // zero-copy batches: the records are shipped from the caller's own page-locked blob (decided by the first add
   // of a batch); otherwise this call's slice of the blob is staged in page-locked memory owned by the caller object
   if (c->opt.zero_copy_records && c->segs.empty() && c->stage_len == 0 && !c->zc_base && fgb_host_is_pinned(records) &&
-      !(c->opt.consensus_call_overlapping_bases && c->prep_opt.trim))
+      !(c->opt.consensus_call_overlapping_bases && (c->prep_opt.trim || c->opt.track_rejects)))   // those run the pre-pass on the host, in the staged copy
     c->zc_base = records;
   const bool zc = c->zc_base != nullptr;
   if (zc && records != c->zc_base) {
@@ -2457,7 +2484,8 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
   for (uint32_t t = 0; t < T; ++t) {
     ctx[t] = T > 1 ? c->workers[t].get() : c;
     const DirectPlan& P = ctx[t]->dplan;
-    mark[t] = DMark{P.raws.size(), P.units.size(), P.rx.size(), P.oruns.size(), P.row_bytes, P.out_elems, P.rec_bytes, P.str_bytes};
+    mark[t] = DMark{P.raws.size(), P.units.size(), P.rx.size(), P.oruns.size(), P.row_bytes, P.out_elems, P.rec_bytes, P.str_bytes,
+                    ctx[t]->rejects.size(), ctx[t]->reject_count};
   }
   uint64_t stats0[FGB_NSTATS];
   std::memcpy(stats0, c->stats, sizeof(stats0));
@@ -2505,7 +2533,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
         uint8_t* const gbase = stage + dst0 + (rec_off[r0] - b0);
         // The device co-calls the overlaps on the uploaded records (the host only plans the runs) unless the
         // quality trim needs whole rewritten reads or a mate has no qualities (0xFF): then in place, here.
-        bool on_device = !c->prep_opt.trim;
+        bool on_device = !c->prep_opt.trim && !c->opt.track_rejects;   // (rejected reads are kept as the pre-pass leaves them: on the host then)
         if (on_device) {
           x->overlap.plan_group(gbase, x->rel_off.data(), n, &x->group_runs);
           for (const overlap::Run& r : x->group_runs) {
@@ -2550,6 +2578,7 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
       P.raws.resize(mark[t].raws); P.lens.resize(mark[t].raws); P.units.resize(mark[t].units); P.rx.resize(mark[t].rx);
       P.oruns.resize(mark[t].oruns);
       P.row_bytes = mark[t].row_bytes; P.out_elems = mark[t].out_elems; P.rec_bytes = mark[t].rec_bytes; P.str_bytes = mark[t].str_bytes;
+      ctx[t]->rejects.resize(mark[t].rejects); ctx[t]->reject_count = mark[t].reject_count;
       if (ctx[t] != c) { std::memset(ctx[t]->stats, 0, sizeof(ctx[t]->stats)); ctx[t]->overlap.stats = overlap::Stats(); }
     }
     std::memcpy(c->stats, stats0, sizeof(stats0));
@@ -2573,6 +2602,11 @@ fgb_status direct_add(fgb_caller* c, const uint8_t* records, const uint64_t* rec
       }
     }
     if (x != c) {
+      if (!x->rejects.empty()) {               // the workers' ranges are contiguous and in input order
+        c->rejects.insert(c->rejects.end(), x->rejects.begin(), x->rejects.end());
+        c->reject_count += x->reject_count;
+        x->rejects.clear(); x->reject_count = 0;
+      }
       for (int i = 0; i < FGB_NSTATS; ++i) { c->stats[i] += x->stats[i]; x->stats[i] = 0; }
       c->overlap.stats.overlapping_bases += x->overlap.stats.overlapping_bases;
       c->overlap.stats.bases_agreeing += x->overlap.stats.bases_agreeing;

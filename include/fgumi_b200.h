@@ -736,8 +736,9 @@ typedef struct fgb_caller_options {        /* VanillaUmiConsensusOptions, vanill
                                               every add call of a batch must pass the same `records` pointer.  Ignored
                                               (a copy is staged) for pageable memory and by the other callers. */
   uint8_t track_rejects;                   /* simplex: keep the raw bytes of every rejected read (vanilla_caller.rs:371-374,
-                                              the --rejects output of `fgumi simplex`) for fgb_caller_take_rejects.  The
-                                              caller then decodes on the host (the rows are not built on the device). */
+                                              the --rejects output of `fgumi simplex`) for fgb_caller_take_rejects.  With
+                                              consensus_call_overlapping_bases the pre-pass then runs on the host, in the
+                                              caller's staged copy (rejected reads are kept as the pre-pass leaves them). */
   uint8_t reserved2;
   uint32_t n_threads;                      /* host threads for fgb_caller_add_groups and the record
                                               assembly of flush; 0 or 1 = the calling thread only  */

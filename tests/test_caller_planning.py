@@ -113,6 +113,91 @@ def test_simplex_host_prep_matches_oracle(min_reads, trim, overlap):
                 st["overlap_bases_corrected"]) == ov.stats()
 
 
+@pytest.mark.parametrize("min_reads,overlap,threads", [(1, False, 1), (2, False, 6), (2, True, 1), (3, True, 6)])
+def test_simplex_rejected_reads_on_the_device_source_read_path(min_reads, overlap, threads):
+    """The same stream from the path device callers take (records staged and shipped whole, rows built on the device:
+    direct_add / plan_subgroup), run here over the CPU mock engine (oracle/libfgb_cpu_caller.so): rejected reads equal
+    the record oracle's -- with the overlapping-bases pre-pass on, the reads as the pre-pass leaves them -- a failing
+    call rolls its rejects back, and the consensus output is the one a caller without the option produces."""
+    import fgumi_b200 as fg
+    from tests.bam_builder import make_record
+    L = fg.lib
+    O.build()
+    os.environ["FGB_CPU_THREADS"] = "4"
+    cpu = C.CDLL(O.SO_CPU_CALLER)
+    vp, u64 = C.c_void_p, C.c_uint64
+    cpu.fgb_caller_create.argtypes = [C.c_int, C.POINTER(L.FgbCallerOptions), C.POINTER(vp)]
+    cpu.fgb_caller_add_groups.argtypes = [vp, vp, vp, vp, u64]
+    cpu.fgb_caller_flush.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+    cpu.fgb_caller_take_rejects.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+    cpu.fgb_caller_destroy.argtypes = [vp]
+    rng = np.random.default_rng(81 + min_reads)
+    groups = random_groups(rng, 240)
+
+    def table(gs):
+        recs = [r for g in gs for r in g]
+        blob = np.frombuffer(b"".join(recs), np.uint8).copy()
+        off = np.zeros(len(recs) + 1, dtype=np.uint64); off[1:] = np.cumsum([len(r) for r in recs])
+        grp = np.zeros(len(gs) + 1, dtype=np.uint64); grp[1:] = np.cumsum([len(g) for g in gs])
+        return blob, off, grp
+
+    def make(track):
+        o = L.FgbCallerOptions()
+        o.mode = 0; o.error_rate_pre_umi = 45; o.error_rate_post_umi = 40; o.min_input_base_quality = 10
+        o.min_consensus_base_quality = 2; o.produce_per_base_tags = 1; o.min_reads = min_reads
+        o.consensus_call_overlapping_bases = int(overlap); o.n_threads = threads; o.track_rejects = int(track)
+        o.tag = b"MI"; o.cell_tag = b"\0\0"; o.read_name_prefix = b"fgumi"; o.read_group_id = b"A"
+        h = vp()
+        assert cpu.fgb_caller_create(0, C.byref(o), C.byref(h)) == 0
+        return h
+
+    def take(h):
+        d, n, cnt = vp(), u64(), u64()
+        assert cpu.fgb_caller_take_rejects(h, C.byref(d), C.byref(n), C.byref(cnt)) == 0
+        raw = C.string_at(d.value, n.value) if n.value else b""
+        out, p = [], 0
+        while p < len(raw):
+            k = int.from_bytes(raw[p:p + 4], "little")
+            out.append(raw[p + 4:p + 4 + k]); p += 4 + k
+        assert len(out) == cnt.value
+        return out
+
+    def flush(h):
+        d, n, cnt = vp(), u64(), u64()
+        assert cpu.fgb_caller_flush(h, C.byref(d), C.byref(n), C.byref(cnt)) == 0
+        return C.string_at(d.value, n.value) if n.value else b""
+
+    oracle = R.VanillaCallerOracle("fgumi", "A", R.VanillaOptions(min_reads=min_reads), Capture(), O.builder_call, track_rejects=True)
+    ov = R.OverlappingOracle() if overlap else None
+    for g in groups:
+        if ov is not None:
+            recs = [bytearray(r) for r in g]
+            ov.apply(recs)
+            g = [bytes(r) for r in recs]
+        oracle.consensus_reads(g)
+    h = make(True)
+    blob, off, grp = table(groups[:90])
+    assert cpu.fgb_caller_add_groups(h, blob.ctypes.data, off.ctypes.data, grp.ctypes.data, 90) == 0
+    got = take(h)
+    # a failing call in between: nothing of it stays, rejects included
+    bad = [make_record(name=b"x", flags=0, pos=5, seq=b"ACGTACGTAC", quals=bytes([30] * 10), tags=[(b"MI", "Z", b"9")])[:20]]
+    bblob, boff, bgrp = table(groups[90:150] + [bad] + groups[150:160])
+    assert cpu.fgb_caller_add_groups(h, bblob.ctypes.data, boff.ctypes.data, bgrp.ctypes.data, len(bgrp) - 1) != 0
+    assert take(h) == []
+    blob2, off2, grp2 = table(groups[90:])
+    assert cpu.fgb_caller_add_groups(h, blob2.ctypes.data, off2.ctypes.data, grp2.ctypes.data, len(groups) - 90) == 0
+    got += take(h)
+    assert len(oracle.rejected_reads) > 40 and got == oracle.rejected_reads
+    out_tracked = flush(h)
+    cpu.fgb_caller_destroy(h)
+    h2 = make(False)
+    ball, oall, gall = table(groups)
+    assert cpu.fgb_caller_add_groups(h2, ball.ctypes.data, oall.ctypes.data, gall.ctypes.data, len(groups)) == 0
+    assert take(h2) == []
+    assert flush(h2) == out_tracked and len(out_tracked) > 10000
+    cpu.fgb_caller_destroy(h2)
+
+
 @pytest.mark.parametrize("min_reads,trim,threads", [(1, False, 1), (2, True, 1), (3, False, 5), (2, False, 5)])
 def test_simplex_rejected_reads_match_oracle(min_reads, trim, threads):
     """options.track_rejects: the raw bytes of every rejected read, in the order the reference's reject sites run
