@@ -1509,8 +1509,10 @@ fgb_status add_group_duplex(fgb_caller* c, const std::vector<View>& recs) {
   Prepared &fx = c->prepared[0], &fy = c->prepared[1];
   pooled(ab_r1, ba_r2, &x_raws, &fx);
   pooled(ab_r2, ba_r1, &y_raws, &fy);
-  std::vector<const SourceRead*> grp[4];   // AB-R1, AB-R2, BA-R1, BA-R2
-  std::vector<uint32_t> grp_raw[4];
+  // AB-R1, AB-R2, BA-R1, BA-R2 (per-thread scratch: eight heap vectors per group otherwise)
+  static thread_local std::vector<const SourceRead*> grp[4];
+  static thread_local std::vector<uint32_t> grp_raw[4];
+  for (int g = 0; g < 4; ++g) { grp[g].clear(); grp_raw[g].clear(); }
   for (size_t i = 0; i < fx.n; ++i) { const SourceRead& sr = fx.srs[i]; int g = (sr.flags & bam::kFirst) ? 0 : 3; grp_raw[g].push_back(x_raws[sr.original_idx]); grp[g].push_back(&sr); }
   for (size_t i = 0; i < fy.n; ++i) { const SourceRead& sr = fy.srs[i]; int g = (sr.flags & bam::kFirst) ? 2 : 1; grp_raw[g].push_back(y_raws[sr.original_idx]); grp[g].push_back(&sr); }
   const bool have[4] = {!grp[0].empty(), !grp[1].empty(), !grp[2].empty(), !grp[3].empty()};
