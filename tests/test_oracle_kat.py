@@ -437,6 +437,23 @@ def test_duplex_consensus_arms():                    # :4300-4337, :4702-4731, :
     assert st == 0 and b == b"NN"                                        # N in either strand masks
 
 
+def test_duplex_more_ss_pair_cases():                # :2688-2712, :2768-2803, :3003-3027, :3150-3176
+    # length mismatch: the duplex read is as long as the shorter strand
+    st, b, q, e = _duplex_arms(b"AAAA", [20] * 4, [3] * 4, [0] * 4, b"AAA", [20] * 3, [2] * 3, [0] * 3)
+    assert st == 0 and b == b"AAA" and q == [40, 40, 40]
+    # deep coverage on one strand does not change the quality rule: 45 + 20
+    b, q, _ = _duplex(b"AAAA", [45] * 4, b"AAAA", [20] * 4)
+    assert b == b"AAAA" and q == [65] * 4
+    # equal qualities on disagreeing strands: no call, quality 2
+    b, q, _ = _duplex(b"AAAA", [25] * 4, b"TTTT", [25] * 4)
+    assert b == b"NNNN" and q == [2] * 4
+    # an N strand masks the other one, whichever side it is on
+    b, q, _ = _duplex(b"NNNN", [2] * 4, b"TTTT", [30] * 4)
+    assert b == b"NNNN" and q == [2] * 4
+    b, q, _ = _duplex(b"AAAA", [30] * 4, b"NNNN", [2] * 4)
+    assert b == b"NNNN" and q == [2] * 4
+
+
 def test_duplex_error_approximation():               # :4339-4406, :5015-5078
     _, _, e = _duplex_cols(b"ACGT", [30] * 4, [5] * 4, [1, 0, 2, 0], b"ACGT", [25] * 4, [4] * 4, [0, 1, 0, 2])
     assert e == [1, 1, 2, 2]                                             # agreement: errors add
